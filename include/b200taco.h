@@ -1,0 +1,181 @@
+/*
+ * b200taco.h -- C ABI of the B200-native Tacotron 2 hot path.
+ *
+ * The reference (Angad8285/pytorch-tacotron2-implementation) has no FFI: its boundary for
+ * this path is the Python surface of `Tacotron2` in src/model.py.  This header is the
+ * native boundary the drop-in `b200taco.model.Tacotron2` binds (ctypes, see
+ * INTEGRATION.md); every entry point names the reference method it replaces.
+ *
+ * Conventions
+ *  - plain C: pointers and sizes only, no torch / C++ types.
+ *  - every pointer named d_* is DEVICE memory owned by the caller (PyTorch's caching
+ *    allocator); the library owns only the handle and its packed-weight cache.
+ *  - `stream` is a cudaStream_t passed as void* (the caller's current stream).
+ *  - all functions return 0 on success or a negative b200taco_status; the message is
+ *    available from b200taco_last_error() (thread-local).  Nothing throws.
+ *  - there is no CPU fallback: without a CUDA device every compute entry point fails
+ *    with B200TACO_ERR_CUDA.
+ *  - fp32 tensors are dense row-major with the shapes given in the comments.
+ */
+#ifndef B200TACO_H
+#define B200TACO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200TACO_ABI_VERSION 1
+
+typedef enum {
+    B200TACO_OK = 0,
+    B200TACO_ERR_INVALID = -1,     /* bad argument / shape */
+    B200TACO_ERR_HPARAMS = -2,     /* hparams differ from the compiled specialisation */
+    B200TACO_ERR_UNSUPPORTED = -3, /* size beyond a compiled limit (B, T) */
+    B200TACO_ERR_CUDA = -4,        /* CUDA runtime error, message has the detail */
+    B200TACO_ERR_STATE = -5,       /* weights not packed, workspace too small, ... */
+    B200TACO_ERR_TIMEOUT = -6      /* a device-side wait gave up (kernel bug guard) */
+} b200taco_status;
+
+/* Mirrors the model constants of the reference's src/config.py:26-59. */
+typedef struct {
+    int32_t n_symbols, embed_dim, enc_convs, enc_kernel;
+    int32_t n_mels, rnn_dim, prenet_dim, attn_rnn_dim, attn_dim;
+    int32_t loc_filters, loc_kernel;
+    int32_t postnet_dim, postnet_kernel, postnet_convs;
+    int32_t max_decoder_steps;
+} b200taco_hparams;
+
+/*
+ * Device pointers to the fp32 parameters/buffers, named after the reference state_dict
+ * (SURVEY.md section 8b).  All are read-only for the library.
+ */
+typedef struct {
+    /* Encoder, src/model.py:19-48 */
+    const float* enc_embedding;            /* (72, 512) */
+    const float* enc_conv_w[3];            /* (512, 512, 5) */
+    const float* enc_conv_b[3];            /* (512) */
+    const float* enc_bn_w[3];              /* BatchNorm1d weight/bias/running stats (512) */
+    const float* enc_bn_b[3];
+    const float* enc_bn_mean[3];
+    const float* enc_bn_var[3];
+    const float* enc_lstm_w_ih[2];         /* [0]=forward, [1]=reverse: (1024, 512) */
+    const float* enc_lstm_w_hh[2];         /* (1024, 256) */
+    const float* enc_lstm_b_ih[2];         /* (1024) */
+    const float* enc_lstm_b_hh[2];
+    /* Decoder, src/model.py:186-217 */
+    const float* prenet_w[2];              /* (256, 80), (256, 256), no bias */
+    const float* attn_query_w;             /* (128, 1024) */
+    const float* attn_memory_w;            /* (128, 512) */
+    const float* attn_loc_conv_w;          /* (32, 2, 31) */
+    const float* attn_loc_dense_w;         /* (128, 32) */
+    const float* attn_v_w;                 /* (1, 128) */
+    const float* attn_v_b;                 /* (1) */
+    const float* attn_energy_scale;        /* () */
+    const float* attn_lstm_w_ih;           /* (4096, 768) */
+    const float* attn_lstm_w_hh;           /* (4096, 1024) */
+    const float* attn_lstm_b_ih;           /* (4096) */
+    const float* attn_lstm_b_hh;
+    const float* dec_lstm_w_ih;            /* (4096, 1536) */
+    const float* dec_lstm_w_hh;            /* (4096, 1024) */
+    const float* dec_lstm_b_ih;
+    const float* dec_lstm_b_hh;
+    const float* proj_w;                   /* (80, 1536) */
+    const float* proj_b;                   /* (80) */
+    const float* gate_w;                   /* (1, 1536) */
+    const float* gate_b;                   /* (1) */
+    /* PostNet, src/model.py:347-390 */
+    const float* post_conv_w[5];           /* (512,80,5) (512,512,5)x3 (80,512,5) */
+    const float* post_conv_b[5];
+    const float* post_bn_w[5];
+    const float* post_bn_b[5];
+    const float* post_bn_mean[5];
+    const float* post_bn_var[5];
+} b200taco_weights;
+
+typedef struct b200taco_handle b200taco_handle;
+
+/* Stop rule of the free-running decoder. */
+#define B200TACO_STOP_BATCH_WIDE 0    /* reference: Decoder.inference, src/model.py:327 */
+#define B200TACO_STOP_PER_UTTERANCE 1 /* caller-side trim rule train.py:71-79, done on device */
+
+int32_t b200taco_abi_version(void);
+const char* b200taco_last_error(void);
+
+/* Limits of the compiled specialisation (max batch, max encoder length). */
+int32_t b200taco_max_batch(void);
+int32_t b200taco_max_text_len(void);
+
+/* Replaces: Tacotron2.__init__ reading src/config.py (src/model.py:415-422). */
+int32_t b200taco_create(const b200taco_hparams* hp, int32_t device, b200taco_handle** out);
+int32_t b200taco_destroy(b200taco_handle* h);
+
+/*
+ * Repack the fp32 parameters into the kernels' layouts (bf16 fragment order for the
+ * two decoder LSTMs, hi/lo bf16 planes for the GEMM operands, folded BatchNorm).  Call
+ * after load_state_dict / optimizer.step (the host tracks param._version).
+ * Replaces: nothing in the reference (PyTorch modules read their own parameters).
+ */
+int32_t b200taco_pack_weights(b200taco_handle* h, const b200taco_weights* w, void* stream);
+
+/* Bytes of caller-provided scratch needed for a (B, T, S) problem; S = decoder steps. */
+size_t b200taco_workspace_bytes(const b200taco_handle* h, int32_t B, int32_t T, int32_t S);
+
+/*
+ * Encoder.forward, src/model.py:50-77 (eval-mode BatchNorm).
+ * d_ids (B,T) int64 -> d_memory (B,T,512).
+ */
+int32_t b200taco_encoder_fwd(b200taco_handle* h, const int64_t* d_ids, int32_t B, int32_t T,
+                             float* d_memory, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Decoder.inference, src/model.py:299-333, as one persistent kernel: the discarded first
+ * step, the frame loop and the stop rule all run on the device.
+ *   d_memory (B,T,512); max_steps = min(max_decoder_steps, max_len_cap)
+ *   d_mel (B,max_steps,80)  d_gate (B,max_steps)  d_align (max_steps,B,T)
+ *   d_lengths (B) int32: per-utterance length under the chosen stop rule
+ *   d_steps_run (1) int32: S, number of output frames (same for all rows)
+ * Rows/steps beyond S are left untouched.
+ */
+int32_t b200taco_decoder_infer(b200taco_handle* h, const float* d_memory, int32_t B, int32_t T,
+                               int32_t max_steps, float gate_threshold, int32_t stop_mode,
+                               float* d_mel, float* d_gate, float* d_align,
+                               int32_t* d_lengths, int32_t* d_steps_run,
+                               void* d_workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Decoder.forward (teacher forcing), src/model.py:277-297, eval-mode dropout.
+ *   d_mel_targets (B,80,S) as the reference receives them; d_text_lengths (B) int64 or
+ *   NULL (= full length): positions >= length are masked with -1e9 (src/model.py:132).
+ *   d_mel (B,S,80)  d_gate (B,S)  d_align (S,B,T)
+ */
+int32_t b200taco_decoder_teacher_forced(b200taco_handle* h, const float* d_memory,
+                                        const float* d_mel_targets, const int64_t* d_text_lengths,
+                                        int32_t B, int32_t T, int32_t S,
+                                        float* d_mel, float* d_gate, float* d_align,
+                                        void* d_workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * PostNet.forward + the residual add of Tacotron2.forward/inference
+ * (src/model.py:392-407, :476-478, :498-500), eval mode.
+ *   d_mel_coarse (B,S,80) -> d_mel_post (B,S,80) = coarse + postnet(coarse)
+ */
+int32_t b200taco_postnet_fwd(b200taco_handle* h, const float* d_mel_coarse, int32_t B, int32_t S,
+                             float* d_mel_post, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Measurement aid used by bench.py for the roofline denominator (the L2
+ * peak is not in MEASURED_PEAKS.json): all SMs repeatedly read a `bytes`-sized buffer
+ * that fits in L2; returns GB/s through *gbps.  d_buf must hold `bytes` bytes.
+ */
+int32_t b200taco_measure_l2_read(void* d_buf, size_t bytes, int32_t iters, float* gbps, void* stream);
+
+/* Number of kernels this library launched on this thread since the last reset. */
+int64_t b200taco_launch_count(int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200TACO_H */

@@ -1,0 +1,191 @@
+"""Host-side owner of one ``b200taco_handle``: weight packing, workspace, launches.
+
+PyTorch is used here for device memory (the caching allocator owns every buffer the
+kernels touch) and for the current CUDA stream; all arithmetic happens inside
+``libb200taco.so`` behind the C ABI of include/b200taco.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _cabi, config
+from ._cabi import B200TacoError, check
+
+STOP_BATCH_WIDE = 0      # Decoder.inference rule, src/model.py:327
+STOP_PER_UTTERANCE = 1   # caller-side trim rule, train.py:71-79, evaluated on device
+
+# state_dict key -> field of b200taco_weights (index for array fields)
+_WEIGHT_MAP = [("encoder.embedding.weight", "enc_embedding", None)]
+for _i in range(3):
+    _p = f"encoder.convolutions.{_i}"
+    _WEIGHT_MAP += [(_p + ".0.weight", "enc_conv_w", _i), (_p + ".0.bias", "enc_conv_b", _i),
+                    (_p + ".1.weight", "enc_bn_w", _i), (_p + ".1.bias", "enc_bn_b", _i),
+                    (_p + ".1.running_mean", "enc_bn_mean", _i), (_p + ".1.running_var", "enc_bn_var", _i)]
+for _i, _s in enumerate(("", "_reverse")):
+    _WEIGHT_MAP += [(f"encoder.lstm.weight_ih_l0{_s}", "enc_lstm_w_ih", _i),
+                    (f"encoder.lstm.weight_hh_l0{_s}", "enc_lstm_w_hh", _i),
+                    (f"encoder.lstm.bias_ih_l0{_s}", "enc_lstm_b_ih", _i),
+                    (f"encoder.lstm.bias_hh_l0{_s}", "enc_lstm_b_hh", _i)]
+_WEIGHT_MAP += [
+    ("decoder.prenet.layers.0.weight", "prenet_w", 0), ("decoder.prenet.layers.1.weight", "prenet_w", 1),
+    ("decoder.attention.query_layer.weight", "attn_query_w", None),
+    ("decoder.attention.memory_layer.weight", "attn_memory_w", None),
+    ("decoder.attention.location_conv.weight", "attn_loc_conv_w", None),
+    ("decoder.attention.location_dense.weight", "attn_loc_dense_w", None),
+    ("decoder.attention.v.weight", "attn_v_w", None), ("decoder.attention.v.bias", "attn_v_b", None),
+    ("decoder.attention.energy_scale", "attn_energy_scale", None),
+    ("decoder.attention_lstm.weight_ih", "attn_lstm_w_ih", None),
+    ("decoder.attention_lstm.weight_hh", "attn_lstm_w_hh", None),
+    ("decoder.attention_lstm.bias_ih", "attn_lstm_b_ih", None),
+    ("decoder.attention_lstm.bias_hh", "attn_lstm_b_hh", None),
+    ("decoder.decoder_lstm.weight_ih", "dec_lstm_w_ih", None),
+    ("decoder.decoder_lstm.weight_hh", "dec_lstm_w_hh", None),
+    ("decoder.decoder_lstm.bias_ih", "dec_lstm_b_ih", None),
+    ("decoder.decoder_lstm.bias_hh", "dec_lstm_b_hh", None),
+    ("decoder.linear_projection.weight", "proj_w", None), ("decoder.linear_projection.bias", "proj_b", None),
+    ("decoder.gate_layer.weight", "gate_w", None), ("decoder.gate_layer.bias", "gate_b", None),
+]
+for _i in range(5):
+    _p = f"postnet.convolutions.{_i}"
+    _WEIGHT_MAP += [(_p + ".0.weight", "post_conv_w", _i), (_p + ".0.bias", "post_conv_b", _i),
+                    (_p + ".1.weight", "post_bn_w", _i), (_p + ".1.bias", "post_bn_b", _i),
+                    (_p + ".1.running_mean", "post_bn_mean", _i), (_p + ".1.running_var", "post_bn_var", _i)]
+WEIGHT_KEYS = [k for k, _, _ in _WEIGHT_MAP]
+
+
+def _hparams() -> _cabi.HParams:
+    return _cabi.HParams(**config.as_hparams())
+
+
+class Engine:
+    """One per model instance per device; not thread-safe."""
+
+    def __init__(self, device: torch.device):
+        if device.type != "cuda":
+            raise B200TacoError(
+                f"b200taco runs on CUDA devices only (got {device}); there is no CPU fallback")
+        self.device = device
+        self._lib = _cabi.lib()
+        self._h = C.c_void_p()
+        hp = _hparams()
+        check(self._lib.b200taco_create(C.byref(hp), device.index or 0, C.byref(self._h)), "b200taco_create")
+        self._packed_sig = None
+        self._ws = None
+        self.max_batch = self._lib.b200taco_max_batch()
+        self.max_text_len = self._lib.b200taco_max_text_len()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.b200taco_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _workspace(self, B, T, S):
+        need = int(self._lib.b200taco_workspace_bytes(self._h, B, T, S))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return C.c_void_p(self._ws.data_ptr()), C.c_size_t(self._ws.numel())
+
+    def ensure_packed(self, tensors: dict) -> None:
+        """(Re)pack when any parameter/buffer was replaced or modified in place."""
+        sig = tuple((tensors[k].data_ptr(), tensors[k]._version) for k in WEIGHT_KEYS)
+        if sig == self._packed_sig:
+            return
+        w = _cabi.Weights()
+        keep = []
+        for key, field, idx in _WEIGHT_MAP:
+            t = tensors[key]
+            if t.device != self.device or t.dtype != torch.float32:
+                raise B200TacoError(f"{key}: expected float32 on {self.device}, got {t.dtype} on {t.device}")
+            if not t.is_contiguous():
+                t = t.contiguous()
+                keep.append(t)
+            if idx is None:
+                setattr(w, field, t.data_ptr())
+            else:
+                getattr(w, field)[idx] = t.data_ptr()
+        with torch.cuda.device(self.device):
+            check(self._lib.b200taco_pack_weights(self._h, C.byref(w), self._stream()), "b200taco_pack_weights")
+            if keep:
+                torch.cuda.current_stream(self.device).synchronize()
+        self._packed_sig = sig
+
+    # ------------------------------------------------------------------ stages
+    def encoder(self, ids: torch.Tensor) -> torch.Tensor:
+        B, T = ids.shape
+        ids = ids.to(device=self.device, dtype=torch.int64).contiguous()
+        memory = torch.empty(B, T, config.encoder_embedding_dim, dtype=torch.float32, device=self.device)
+        ws, wsz = self._workspace(B, T, 1)
+        with torch.cuda.device(self.device):
+            check(self._lib.b200taco_encoder_fwd(self._h, ids.data_ptr(), B, T, memory.data_ptr(),
+                                                 ws, wsz, self._stream()), "b200taco_encoder_fwd")
+        return memory
+
+    def decoder_infer(self, memory, max_steps: int, gate_threshold: float, stop_mode: int):
+        B, T, _ = memory.shape
+        dev = self.device
+        mel = torch.empty(B, max_steps, config.n_mels, dtype=torch.float32, device=dev)
+        gate = torch.empty(B, max_steps, dtype=torch.float32, device=dev)
+        align = torch.empty(max_steps, B, T, dtype=torch.float32, device=dev)
+        lengths = torch.empty(B, dtype=torch.int32, device=dev)
+        steps = torch.empty(1, dtype=torch.int32, device=dev)
+        ws, wsz = self._workspace(B, T, max_steps)
+        with torch.cuda.device(dev):
+            check(self._lib.b200taco_decoder_infer(
+                self._h, memory.data_ptr(), B, T, max_steps, float(gate_threshold), int(stop_mode),
+                mel.data_ptr(), gate.data_ptr(), align.data_ptr(), lengths.data_ptr(), steps.data_ptr(),
+                ws, wsz, self._stream()), "b200taco_decoder_infer")
+        S = int(steps.item())            # the one host sync of an inference call
+        if S < 0:
+            raise B200TacoError("decoder kernel reported a device-side wait timeout")
+        return mel[:, :S], gate[:, :S], align[:S], lengths, S
+
+    def decoder_teacher_forced(self, memory, mel_targets, text_lengths):
+        B, T, _ = memory.shape
+        S = mel_targets.shape[2]
+        dev = self.device
+        mel_targets = mel_targets.to(device=dev, dtype=torch.float32).contiguous()
+        tl = None
+        if text_lengths is not None:
+            tl = text_lengths.to(device=dev, dtype=torch.int64).contiguous()
+        mel = torch.empty(B, S, config.n_mels, dtype=torch.float32, device=dev)
+        gate = torch.empty(B, S, dtype=torch.float32, device=dev)
+        align = torch.empty(S, B, T, dtype=torch.float32, device=dev)
+        ws, wsz = self._workspace(B, T, S)
+        with torch.cuda.device(dev):
+            check(self._lib.b200taco_decoder_teacher_forced(
+                self._h, memory.data_ptr(), mel_targets.data_ptr(),
+                tl.data_ptr() if tl is not None else None, B, T, S,
+                mel.data_ptr(), gate.data_ptr(), align.data_ptr(), ws, wsz, self._stream()),
+                "b200taco_decoder_teacher_forced")
+        return mel, gate, align
+
+    def postnet(self, mel_coarse: torch.Tensor) -> torch.Tensor:
+        mel_coarse = mel_coarse.contiguous()
+        B, S, _ = mel_coarse.shape
+        out = torch.empty_like(mel_coarse)
+        ws, wsz = self._workspace(B, 1, S)
+        with torch.cuda.device(self.device):
+            check(self._lib.b200taco_postnet_fwd(self._h, mel_coarse.data_ptr(), B, S, out.data_ptr(),
+                                                 ws, wsz, self._stream()), "b200taco_postnet_fwd")
+        return out
+
+    # ------------------------------------------------------------------ measurement aids
+    def measure_l2_read_gbps(self, nbytes: int = 36 << 20, iters: int = 50) -> float:
+        buf = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        out = C.c_float(0.0)
+        with torch.cuda.device(self.device):
+            check(self._lib.b200taco_measure_l2_read(buf.data_ptr(), nbytes, iters, C.byref(out),
+                                                     self._stream()), "b200taco_measure_l2_read")
+        return float(out.value)
+
+    def launch_count(self, reset: bool = False) -> int:
+        return int(self._lib.b200taco_launch_count(1 if reset else 0))

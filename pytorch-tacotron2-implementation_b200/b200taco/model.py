@@ -1,0 +1,196 @@
+"""Drop-in ``Tacotron2`` whose arithmetic runs in libb200taco.so (CUDA, sm_100a).
+
+Boundary preserved (reference src/model.py:410-501):
+
+* ``Tacotron2()`` takes no arguments; hparams come from :mod:`b200taco.config`.
+* ``forward(text_inputs, mel_targets, text_lengths=None, use_postnet=True)`` and
+  ``inference(text_inputs, text_lengths=None, max_len_cap=None, gate_threshold=None)``
+  return ``(mel_postnet (B,S,80), mel_coarse (B,S,80), gate_logits (B,S), alignments)``
+  with ``alignments`` a *list* of S tensors (B,T) as the reference's callers expect
+  (train.py:198, :227).
+* identical parameter tree, so reference checkpoints load unchanged and
+  ``model.decoder.attention.parameters()`` (train.py:345) resolves.
+
+The nn.Module tree below only *holds* parameters (created in the reference's order so
+that ``torch.manual_seed(s); Tacotron2()`` yields the same random initialisation); none
+of the sub-modules is ever called.  All compute goes through :class:`b200taco.engine.Engine`.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import config
+from ._cabi import B200TacoError
+from .engine import Engine, STOP_BATCH_WIDE, STOP_PER_UTTERANCE
+
+
+def _conv_bn(c_in: int, c_out: int, k: int) -> nn.Sequential:
+    return nn.Sequential(nn.Conv1d(c_in, c_out, k, padding=(k - 1) // 2), nn.BatchNorm1d(c_out))
+
+
+class _Holder(nn.Module):
+    """Parameter container; calling it is a bug (compute lives in the CUDA library)."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise B200TacoError(f"{type(self).__name__} holds parameters only; call Tacotron2.forward/inference")
+
+
+class Encoder(_Holder):
+    """Parameters of src/model.py:15-48."""
+
+    def __init__(self):
+        super().__init__()
+        d = config.encoder_embedding_dim
+        self.embedding = nn.Embedding(len(config.SYMBOLS), config.symbols_embedding_dim)
+        self.convolutions = nn.ModuleList(
+            _conv_bn(d, d, config.encoder_kernel_size) for _ in range(config.encoder_n_convolutions))
+        self.lstm = nn.LSTM(d, d // 2, 1, batch_first=True, bidirectional=True)
+
+
+class LocationSensitiveAttention(_Holder):
+    """Parameters of src/model.py:86-102."""
+
+    def __init__(self):
+        super().__init__()
+        a = config.attention_dim
+        self.query_layer = nn.Linear(config.attention_rnn_dim, a, bias=False)
+        self.memory_layer = nn.Linear(config.encoder_embedding_dim, a, bias=False)
+        k = config.location_kernel_size
+        self.location_conv = nn.Conv1d(2, config.location_n_filters, k, padding=(k - 1) // 2, bias=False)
+        self.location_dense = nn.Linear(config.location_n_filters, a, bias=False)
+        self.v = nn.Linear(a, 1, bias=True)
+        self.energy_scale = nn.Parameter(torch.tensor(1.2))
+
+
+class PreNet(_Holder):
+    """Parameters of src/model.py:159-164."""
+
+    def __init__(self, in_dim, sizes):
+        super().__init__()
+        dims = [in_dim] + list(sizes)
+        self.layers = nn.ModuleList(nn.Linear(i, o, bias=False) for i, o in zip(dims[:-1], dims[1:]))
+
+
+class Decoder(_Holder):
+    """Parameters and scalar attributes of src/model.py:179-217."""
+
+    def __init__(self):
+        super().__init__()
+        self.n_mels = config.n_mels
+        self.max_decoder_steps = config.max_decoder_steps
+        self.gate_threshold = config.gate_threshold
+        h, e = config.decoder_rnn_dim, config.encoder_embedding_dim
+        self.prenet = PreNet(self.n_mels, [config.prenet_dim, config.prenet_dim])
+        self.attention = LocationSensitiveAttention()
+        self.attention_lstm = nn.LSTMCell(config.prenet_dim + e, h)
+        self.decoder_lstm = nn.LSTMCell(h + e, h)
+        self.linear_projection = nn.Linear(h + e, self.n_mels)
+        self.gate_layer = nn.Linear(h + e, 1)
+        with torch.no_grad():
+            self.gate_layer.bias.fill_(-3.0)          # src/model.py:215-217
+
+
+class PostNet(_Holder):
+    """Parameters of src/model.py:341-390."""
+
+    def __init__(self):
+        super().__init__()
+        d, k, n = config.postnet_embedding_dim, config.postnet_kernel_size, config.postnet_n_convolutions
+        chans = [config.n_mels] + [d] * (n - 1) + [config.n_mels]
+        self.convolutions = nn.ModuleList(_conv_bn(chans[i], chans[i + 1], k) for i in range(n))
+
+
+class Tacotron2(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.encoder = Encoder()
+        self.decoder = Decoder()
+        self.postnet = PostNet()
+        self.n_mels = config.n_mels
+        self._projection_bias_initialized = False      # src/model.py:422 (plain attribute, F10)
+        self._engine = None
+        self.debug_first_step_print = False            # the reference's F6 prints, off by default
+
+    # ------------------------------------------------------------------ plumbing
+    def _tensors(self) -> dict:
+        d = dict(self.named_parameters())
+        d.update(dict(self.named_buffers()))
+        return d
+
+    def _get_engine(self) -> Engine:
+        dev = self.decoder.gate_layer.weight.device
+        if self._engine is None or self._engine.device != dev:
+            self._engine = Engine(dev)
+        self._engine.ensure_packed(self._tensors())
+        return self._engine
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._engine = None                             # .to(device) / .float(): rebuild lazily
+        return out
+
+    def _check_mode(self, what):
+        if self.training:
+            raise B200TacoError(
+                f"{what}: training-mode semantics (dropout, BatchNorm batch statistics, backward) are "
+                "not built yet in this round; call model.eval(). No PyTorch fallback is provided.")
+
+    def _maybe_init_projection_bias(self, mel_targets):
+        """F10 side effect, src/model.py:424-441: first forward sets the mel bias to the target mean."""
+        if self._projection_bias_initialized:
+            return
+        bias = self.decoder.linear_projection.bias
+        with torch.no_grad():
+            means = mel_targets.mean(dim=(0, 2))
+            if means.numel() == bias.numel():
+                bias.copy_(means)
+                self._projection_bias_initialized = True
+
+    # ------------------------------------------------------------------ public API
+    @torch.no_grad()
+    def forward(self, text_inputs, mel_targets, text_lengths=None, use_postnet=True):
+        """Teacher-forced pass, src/model.py:454-480."""
+        self._check_mode("Tacotron2.forward")
+        if not self._projection_bias_initialized:
+            self._maybe_init_projection_bias(mel_targets)
+        eng = self._get_engine()
+        memory = eng.encoder(text_inputs)
+        coarse, gate, align = eng.decoder_teacher_forced(memory, mel_targets, text_lengths)
+        post = eng.postnet(coarse) if use_postnet else coarse
+        return post, coarse, gate, list(align.unbind(0))
+
+    @torch.no_grad()
+    def inference(self, text_inputs, text_lengths=None, max_len_cap=None, gate_threshold=None):
+        """Free-running pass, src/model.py:482-501.  ``text_lengths`` is ignored, as there (F8)."""
+        post, coarse, gate, align, _ = self._infer(text_inputs, max_len_cap, gate_threshold, STOP_BATCH_WIDE)
+        return post, coarse, gate, list(align.unbind(0))
+
+    @torch.no_grad()
+    def inference_per_utterance(self, text_inputs, max_len_cap=None, gate_threshold=None):
+        """Same decode, but every row keeps running until *its own* gate fires (train.py:71-79 rule).
+
+        Only valid for exact-length batches (no padding; see F8).  Returns the 4-tuple plus
+        ``lengths`` (B,) int32; rows are padded to the longest utterance.
+        """
+        post, coarse, gate, align, lengths = self._infer(text_inputs, max_len_cap, gate_threshold,
+                                                         STOP_PER_UTTERANCE)
+        return post, coarse, gate, list(align.unbind(0)), lengths
+
+    def _infer(self, text_inputs, max_len_cap, gate_threshold, stop_mode):
+        self._check_mode("Tacotron2.inference")
+        thr = gate_threshold if gate_threshold is not None else self.decoder.gate_threshold
+        cap = self.decoder.max_decoder_steps
+        if max_len_cap:
+            cap = min(cap, int(max_len_cap))
+        eng = self._get_engine()
+        memory = eng.encoder(text_inputs)
+        coarse, gate, align, lengths, S = eng.decoder_infer(memory, cap, thr, stop_mode)
+        coarse = coarse.contiguous()
+        if S >= cap:
+            print(f"Warning! Reached decode cap ({cap}).")                  # src/model.py:330
+        if S < 3:
+            print(f"[WARN] Very short mel length ({S}) - possible premature stop. "
+                  f"Gate threshold={self.decoder.gate_threshold}")          # src/model.py:496-497
+        post = eng.postnet(coarse)
+        return post, coarse, gate.contiguous(), align, lengths
