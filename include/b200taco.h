@@ -27,6 +27,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define B200TACO_API __attribute__((visibility("default")))
+#else
+#define B200TACO_API
+#endif
+
 #define B200TACO_ABI_VERSION 1
 
 typedef enum {
@@ -101,16 +107,26 @@ typedef struct b200taco_handle b200taco_handle;
 #define B200TACO_STOP_BATCH_WIDE 0    /* reference: Decoder.inference, src/model.py:327 */
 #define B200TACO_STOP_PER_UTTERANCE 1 /* caller-side trim rule train.py:71-79, done on device */
 
-int32_t b200taco_abi_version(void);
-const char* b200taco_last_error(void);
+B200TACO_API int32_t b200taco_abi_version(void);
+B200TACO_API const char* b200taco_last_error(void);
 
 /* Limits of the compiled specialisation (max batch, max encoder length). */
-int32_t b200taco_max_batch(void);
-int32_t b200taco_max_text_len(void);
+B200TACO_API int32_t b200taco_max_batch(void);
+B200TACO_API int32_t b200taco_max_text_len(void);
 
 /* Replaces: Tacotron2.__init__ reading src/config.py (src/model.py:415-422). */
-int32_t b200taco_create(const b200taco_hparams* hp, int32_t device, b200taco_handle** out);
-int32_t b200taco_destroy(b200taco_handle* h);
+B200TACO_API int32_t b200taco_create(const b200taco_hparams* hp, int32_t device, b200taco_handle** out);
+B200TACO_API int32_t b200taco_destroy(b200taco_handle* h);
+
+/*
+ * Storage type of the four decoder LSTM matrices inside the packed cache (98 % of the bytes a
+ * decoder step reads).  BF16 (default) halves the L2 traffic; FP32 keeps the reference's
+ * values bit for bit.  Accumulation and all state are fp32 either way.  Takes effect at the
+ * next b200taco_pack_weights.  Replaces: nothing in the reference (fp32 nn.LSTMCell).
+ */
+#define B200TACO_WEIGHTS_BF16 0
+#define B200TACO_WEIGHTS_FP32 1
+B200TACO_API int32_t b200taco_set_weight_dtype(b200taco_handle* h, int32_t dtype);
 
 /*
  * Repack the fp32 parameters into the kernels' layouts (bf16 fragment order for the
@@ -118,16 +134,16 @@ int32_t b200taco_destroy(b200taco_handle* h);
  * after load_state_dict / optimizer.step (the host tracks param._version).
  * Replaces: nothing in the reference (PyTorch modules read their own parameters).
  */
-int32_t b200taco_pack_weights(b200taco_handle* h, const b200taco_weights* w, void* stream);
+B200TACO_API int32_t b200taco_pack_weights(b200taco_handle* h, const b200taco_weights* w, void* stream);
 
 /* Bytes of caller-provided scratch needed for a (B, T, S) problem; S = decoder steps. */
-size_t b200taco_workspace_bytes(const b200taco_handle* h, int32_t B, int32_t T, int32_t S);
+B200TACO_API size_t b200taco_workspace_bytes(const b200taco_handle* h, int32_t B, int32_t T, int32_t S);
 
 /*
  * Encoder.forward, src/model.py:50-77 (eval-mode BatchNorm).
  * d_ids (B,T) int64 -> d_memory (B,T,512).
  */
-int32_t b200taco_encoder_fwd(b200taco_handle* h, const int64_t* d_ids, int32_t B, int32_t T,
+B200TACO_API int32_t b200taco_encoder_fwd(b200taco_handle* h, const int64_t* d_ids, int32_t B, int32_t T,
                              float* d_memory, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /*
@@ -139,7 +155,7 @@ int32_t b200taco_encoder_fwd(b200taco_handle* h, const int64_t* d_ids, int32_t B
  *   d_steps_run (1) int32: S, number of output frames (same for all rows)
  * Rows/steps beyond S are left untouched.
  */
-int32_t b200taco_decoder_infer(b200taco_handle* h, const float* d_memory, int32_t B, int32_t T,
+B200TACO_API int32_t b200taco_decoder_infer(b200taco_handle* h, const float* d_memory, int32_t B, int32_t T,
                                int32_t max_steps, float gate_threshold, int32_t stop_mode,
                                float* d_mel, float* d_gate, float* d_align,
                                int32_t* d_lengths, int32_t* d_steps_run,
@@ -151,7 +167,7 @@ int32_t b200taco_decoder_infer(b200taco_handle* h, const float* d_memory, int32_
  *   NULL (= full length): positions >= length are masked with -1e9 (src/model.py:132).
  *   d_mel (B,S,80)  d_gate (B,S)  d_align (S,B,T)
  */
-int32_t b200taco_decoder_teacher_forced(b200taco_handle* h, const float* d_memory,
+B200TACO_API int32_t b200taco_decoder_teacher_forced(b200taco_handle* h, const float* d_memory,
                                         const float* d_mel_targets, const int64_t* d_text_lengths,
                                         int32_t B, int32_t T, int32_t S,
                                         float* d_mel, float* d_gate, float* d_align,
@@ -162,7 +178,7 @@ int32_t b200taco_decoder_teacher_forced(b200taco_handle* h, const float* d_memor
  * (src/model.py:392-407, :476-478, :498-500), eval mode.
  *   d_mel_coarse (B,S,80) -> d_mel_post (B,S,80) = coarse + postnet(coarse)
  */
-int32_t b200taco_postnet_fwd(b200taco_handle* h, const float* d_mel_coarse, int32_t B, int32_t S,
+B200TACO_API int32_t b200taco_postnet_fwd(b200taco_handle* h, const float* d_mel_coarse, int32_t B, int32_t S,
                              float* d_mel_post, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /*
@@ -170,10 +186,10 @@ int32_t b200taco_postnet_fwd(b200taco_handle* h, const float* d_mel_coarse, int3
  * peak is not in MEASURED_PEAKS.json): all SMs repeatedly read a `bytes`-sized buffer
  * that fits in L2; returns GB/s through *gbps.  d_buf must hold `bytes` bytes.
  */
-int32_t b200taco_measure_l2_read(void* d_buf, size_t bytes, int32_t iters, float* gbps, void* stream);
+B200TACO_API int32_t b200taco_measure_l2_read(void* d_buf, size_t bytes, int32_t iters, float* gbps, void* stream);
 
 /* Number of kernels this library launched on this thread since the last reset. */
-int64_t b200taco_launch_count(int32_t reset);
+B200TACO_API int64_t b200taco_launch_count(int32_t reset);
 
 #ifdef __cplusplus
 }

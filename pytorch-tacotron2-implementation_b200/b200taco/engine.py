@@ -15,6 +15,7 @@ from ._cabi import B200TacoError, check
 
 STOP_BATCH_WIDE = 0      # Decoder.inference rule, src/model.py:327
 STOP_PER_UTTERANCE = 1   # caller-side trim rule, train.py:71-79, evaluated on device
+WEIGHT_DTYPES = {"bf16": 0, "fp32": 1}   # storage of the four decoder LSTM matrices (include/b200taco.h)
 
 # state_dict key -> field of b200taco_weights (index for array fields)
 _WEIGHT_MAP = [("encoder.embedding.weight", "enc_embedding", None)]
@@ -62,7 +63,9 @@ def _hparams() -> _cabi.HParams:
 class Engine:
     """One per model instance per device; not thread-safe."""
 
-    def __init__(self, device: torch.device):
+    def __init__(self, device: torch.device, weight_dtype: str = "bf16"):
+        if weight_dtype not in WEIGHT_DTYPES:
+            raise B200TacoError(f"weight_dtype must be one of {sorted(WEIGHT_DTYPES)}, got {weight_dtype!r}")
         if device.type != "cuda":
             raise B200TacoError(
                 f"b200taco runs on CUDA devices only (got {device}); there is no CPU fallback")
@@ -70,7 +73,9 @@ class Engine:
         self._lib = _cabi.lib()
         self._h = C.c_void_p()
         hp = _hparams()
-        check(self._lib.b200taco_create(C.byref(hp), device.index or 0, C.byref(self._h)), "b200taco_create")
+        check(self._lib.b200taco_create(C.byref(hp), device.index if device.index is not None else torch.cuda.current_device(), C.byref(self._h)), "b200taco_create")
+        self.weight_dtype = weight_dtype
+        check(self._lib.b200taco_set_weight_dtype(self._h, WEIGHT_DTYPES[weight_dtype]), "b200taco_set_weight_dtype")
         self._packed_sig = None
         self._ws = None
         self.max_batch = self._lib.b200taco_max_batch()
@@ -129,7 +134,10 @@ class Engine:
                                                  ws, wsz, self._stream()), "b200taco_encoder_fwd")
         return memory
 
-    def decoder_infer(self, memory, max_steps: int, gate_threshold: float, stop_mode: int):
+    def decoder_infer(self, memory, max_steps: int, gate_threshold: float, stop_mode: int, sync: bool = True):
+        """Free-running decode.  ``sync=False`` returns the max-length buffers and the device
+        tensor holding S without waiting for the kernel (benchmarks time it with CUDA events)."""
+        memory = memory.contiguous()
         B, T, _ = memory.shape
         dev = self.device
         mel = torch.empty(B, max_steps, config.n_mels, dtype=torch.float32, device=dev)
@@ -143,12 +151,13 @@ class Engine:
                 self._h, memory.data_ptr(), B, T, max_steps, float(gate_threshold), int(stop_mode),
                 mel.data_ptr(), gate.data_ptr(), align.data_ptr(), lengths.data_ptr(), steps.data_ptr(),
                 ws, wsz, self._stream()), "b200taco_decoder_infer")
+        if not sync:
+            return mel, gate, align, lengths, steps
         S = int(steps.item())            # the one host sync of an inference call
-        if S < 0:
-            raise B200TacoError("decoder kernel reported a device-side wait timeout")
         return mel[:, :S], gate[:, :S], align[:S], lengths, S
 
     def decoder_teacher_forced(self, memory, mel_targets, text_lengths):
+        memory = memory.contiguous()
         B, T, _ = memory.shape
         S = mel_targets.shape[2]
         dev = self.device

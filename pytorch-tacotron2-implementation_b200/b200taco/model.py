@@ -110,7 +110,9 @@ class Tacotron2(nn.Module):
         self.n_mels = config.n_mels
         self._projection_bias_initialized = False      # src/model.py:422 (plain attribute, F10)
         self._engine = None
-        self.debug_first_step_print = False            # the reference's F6 prints, off by default
+        # storage of the decoder LSTM matrices in the packed cache: "bf16" (default, half the
+        # L2 traffic per step) or "fp32" (the reference's values bit for bit)
+        self.lstm_weight_dtype = "bf16"
 
     # ------------------------------------------------------------------ plumbing
     def _tensors(self) -> dict:
@@ -120,8 +122,9 @@ class Tacotron2(nn.Module):
 
     def _get_engine(self) -> Engine:
         dev = self.decoder.gate_layer.weight.device
-        if self._engine is None or self._engine.device != dev:
-            self._engine = Engine(dev)
+        if (self._engine is None or self._engine.device != dev
+                or self._engine.weight_dtype != self.lstm_weight_dtype):
+            self._engine = Engine(dev, self.lstm_weight_dtype)
         self._engine.ensure_packed(self._tensors())
         return self._engine
 

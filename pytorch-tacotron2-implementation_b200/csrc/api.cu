@@ -1,0 +1,321 @@
+// C ABI of libb200taco (include/b200taco.h): argument checking, workspace carving and the
+// launch sequences of the encoder / decoder / postnet stages.  Nothing throws; every entry
+// point returns a b200taco_status and records a message for b200taco_last_error().
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "handle.h"
+
+namespace b200taco {
+
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int64_t& launch_counter() { return g_launches; }
+
+namespace {
+
+// teacher forcing: decoder input frames, shifted right by one with a zero go-frame
+// (src/model.py:281-285).  X[s*B + b][o] = s == 0 ? 0 : targets[b][o][s-1]
+__global__ void tf_frames_kernel(const float* __restrict__ targets, float* __restrict__ X, int B, int S) {
+    const size_t total = (size_t)S * B * N_MELS;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int o = i % N_MELS, b = (i / N_MELS) % B, s = i / ((size_t)N_MELS * B);
+        X[i] = s == 0 ? 0.f : targets[((size_t)b * N_MELS + o) * S + (s - 1)];
+    }
+}
+// prenet outputs [s*B + b][256] -> the decoder's act layout p_all[s][k][BP]
+__global__ void p_all_pack_kernel(const float* __restrict__ Y, float* __restrict__ P, int B, int BP, int S) {
+    const size_t total = (size_t)S * PRENET * BP;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = i % BP, k = (i / BP) % PRENET, s = i / ((size_t)BP * PRENET);
+        P[i] = b < B ? Y[((size_t)s * B + b) * PRENET + k] : 0.f;
+    }
+}
+
+struct Carver {
+    uint8_t* base;
+    size_t off = 0;
+    float* f(size_t n) {
+        float* p = base ? reinterpret_cast<float*>(base + off) : nullptr;
+        off = align_up(off + n * sizeof(float), 256);
+        return p;
+    }
+    void* raw(size_t bytes) {
+        void* p = base ? base + off : nullptr;
+        off = align_up(off + bytes, 256);
+        return p;
+    }
+};
+
+struct EncoderWs { float *x0, *x1, *xproj; size_t total; };
+EncoderWs encoder_ws(void* base, int B, int T) {
+    Carver c{static_cast<uint8_t*>(base)};
+    EncoderWs w{};
+    w.x0 = c.f((size_t)B * T * EMB);
+    w.x1 = c.f((size_t)B * T * EMB);
+    w.xproj = c.f((size_t)B * T * 8 * ENC_H);
+    w.total = c.off;
+    return w;
+}
+struct DecoderWs { float *pm, *frames, *y1, *y2, *p_all; void* scratch; size_t scratch_bytes, total; };
+DecoderWs decoder_ws(void* base, int B, int T, int S_tf) {
+    Carver c{static_cast<uint8_t*>(base)};
+    DecoderWs w{};
+    w.pm = c.f((size_t)B * T * ATT_DIM);
+    w.scratch_bytes = decoder_scratch_bytes(B, T);
+    w.scratch = c.raw(w.scratch_bytes);
+    if (S_tf > 0) {
+        w.frames = c.f((size_t)S_tf * B * N_MELS);
+        w.y1 = c.f((size_t)S_tf * B * PRENET);
+        w.y2 = c.f((size_t)S_tf * B * PRENET);
+        w.p_all = c.f((size_t)S_tf * PRENET * decoder_batch_pad(B));
+    }
+    w.total = c.off;
+    return w;
+}
+struct PostnetWs { float *a, *b; size_t total; };
+PostnetWs postnet_ws(void* base, int B, int S) {
+    Carver c{static_cast<uint8_t*>(base)};
+    PostnetWs w{};
+    w.a = c.f((size_t)B * S * POST_DIM);
+    w.b = c.f((size_t)B * S * POST_DIM);
+    w.total = c.off;
+    return w;
+}
+
+int check_handle(const b200taco_handle* h, bool need_packed) {
+    TACO_REQUIRE(h != nullptr, B200TACO_ERR_INVALID, "null handle");
+    if (need_packed)
+        TACO_REQUIRE(h->packed, B200TACO_ERR_STATE, "weights not packed: call b200taco_pack_weights first");
+    TACO_CUDA(cudaSetDevice(h->device));
+    return B200TACO_OK;
+}
+
+int check_shape(int B, int T) {
+    TACO_REQUIRE(B >= 1 && B <= MAX_BATCH, B200TACO_ERR_UNSUPPORTED, "batch %d outside [1, %d]", B, MAX_BATCH);
+    TACO_REQUIRE(T >= 1 && T <= MAX_TEXT_LEN, B200TACO_ERR_UNSUPPORTED, "text length %d outside [1, %d]", T,
+                 MAX_TEXT_LEN);
+    return B200TACO_OK;
+}
+
+}  // namespace
+}  // namespace b200taco
+
+using namespace b200taco;
+
+#define TACO_TRY(expr)                   \
+    do {                                 \
+        int _s = (expr);                 \
+        if (_s != B200TACO_OK) return _s; \
+    } while (0)
+
+extern "C" {
+
+B200TACO_API int32_t b200taco_abi_version(void) { return B200TACO_ABI_VERSION; }
+B200TACO_API const char* b200taco_last_error(void) { return g_err; }
+B200TACO_API int32_t b200taco_max_batch(void) { return MAX_BATCH; }
+B200TACO_API int32_t b200taco_max_text_len(void) { return MAX_TEXT_LEN; }
+
+B200TACO_API int32_t b200taco_create(const b200taco_hparams* hp, int32_t device, b200taco_handle** out) {
+    TACO_REQUIRE(hp && out, B200TACO_ERR_INVALID, "b200taco_create: null argument");
+    *out = nullptr;
+    const b200taco_hparams want = {N_SYMBOLS, EMB, ENC_CONVS, ENC_KERNEL, N_MELS, RNN, PRENET, RNN, ATT_DIM,
+                                   LOC_F, LOC_K, POST_DIM, POST_KERNEL, POST_CONVS, hp->max_decoder_steps};
+    TACO_REQUIRE(memcmp(&want, hp, sizeof(want)) == 0 && hp->max_decoder_steps >= 1, B200TACO_ERR_HPARAMS,
+                 "hparams differ from the compiled specialisation (symbols %d, emb %d, convs %dx%d, mels %d, rnn %d, "
+                 "prenet %d, attention %d/%d/%d, postnet %d/%d/%d)",
+                 N_SYMBOLS, EMB, ENC_CONVS, ENC_KERNEL, N_MELS, RNN, PRENET, ATT_DIM, LOC_F, LOC_K, POST_DIM,
+                 POST_KERNEL, POST_CONVS);
+    int count = 0;
+    TACO_CUDA(cudaGetDeviceCount(&count));
+    TACO_REQUIRE(device >= 0 && device < count, B200TACO_ERR_CUDA, "no CUDA device %d (found %d); there is no CPU fallback",
+                 device, count);
+    TACO_CUDA(cudaSetDevice(device));
+    b200taco_handle* h = new (std::nothrow) b200taco_handle();
+    TACO_REQUIRE(h, B200TACO_ERR_STATE, "out of host memory");
+    h->device = device;
+    cudaError_t e = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
+    int coop = 0, major = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (e != cudaSuccess || !coop || major != 10) {
+        delete h;
+        set_error("device %d unusable: %s, cooperative launch %d, compute capability major %d (need sm_100a)", device,
+                  cudaGetErrorString(e), coop, major);
+        return B200TACO_ERR_CUDA;
+    }
+    *out = h;
+    return B200TACO_OK;
+}
+
+B200TACO_API int32_t b200taco_destroy(b200taco_handle* h) {
+    if (!h) return B200TACO_OK;
+    cudaSetDevice(h->device);
+    if (h->arena) cudaFree(h->arena);
+    delete h;
+    return B200TACO_OK;
+}
+
+B200TACO_API int32_t b200taco_set_weight_dtype(b200taco_handle* h, int32_t dtype) {
+    TACO_REQUIRE(h != nullptr, B200TACO_ERR_INVALID, "null handle");
+    TACO_REQUIRE(dtype == B200TACO_WEIGHTS_BF16 || dtype == B200TACO_WEIGHTS_FP32, B200TACO_ERR_INVALID,
+                 "unknown weight dtype %d", dtype);
+    if (h->weight_dtype != dtype) h->packed = false;
+    h->weight_dtype = dtype;
+    return B200TACO_OK;
+}
+
+B200TACO_API int32_t b200taco_pack_weights(b200taco_handle* h, const b200taco_weights* w, void* stream) {
+    TACO_TRY(check_handle(h, false));
+    TACO_REQUIRE(w != nullptr, B200TACO_ERR_INVALID, "null weights");
+    const void* const* ptrs = reinterpret_cast<const void* const*>(w);
+    for (size_t i = 0; i < sizeof(b200taco_weights) / sizeof(void*); ++i)
+        TACO_REQUIRE(ptrs[i] != nullptr, B200TACO_ERR_INVALID, "weights field %zu is null", i);
+    return pack_weights(h, w, static_cast<cudaStream_t>(stream));
+}
+
+B200TACO_API size_t b200taco_workspace_bytes(const b200taco_handle* h, int32_t B, int32_t T, int32_t S) {
+    (void)h;
+    if (B < 1 || T < 1 || S < 1) return 0;
+    size_t need = encoder_ws(nullptr, B, T).total;
+    size_t d = decoder_ws(nullptr, B, T, S).total + 1024;
+    size_t p = postnet_ws(nullptr, B, S).total;
+    need = d > need ? d : need;
+    need = p > need ? p : need;
+    return need;
+}
+
+B200TACO_API int32_t b200taco_encoder_fwd(b200taco_handle* h, const int64_t* d_ids, int32_t B, int32_t T, float* d_memory,
+                             void* d_workspace, size_t workspace_bytes, void* stream) {
+    TACO_TRY(check_handle(h, true));
+    TACO_TRY(check_shape(B, T));
+    TACO_REQUIRE(d_ids && d_memory && d_workspace, B200TACO_ERR_INVALID, "encoder_fwd: null pointer");
+    const EncoderWs ws = encoder_ws(d_workspace, B, T);
+    TACO_REQUIRE(workspace_bytes >= ws.total, B200TACO_ERR_STATE, "encoder workspace too small: %zu < %zu", workspace_bytes,
+                 ws.total);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int n = B * T;
+    TACO_TRY(embedding_gather(d_ids, h->enc_emb, ws.x0, n, st));
+    float* src = ws.x0;
+    float* dst = ws.x1;
+    for (int i = 0; i < ENC_CONVS; ++i) {
+        TACO_TRY(conv1d_channels_last(src, EMB, h->enc_conv_w[i], h->enc_conv_scale[i], h->enc_conv_shift[i], nullptr, 0,
+                                      dst, EMB, n, T, EMB, EMB, ENC_KERNEL, ACT_RELU, st));
+        float* t = src; src = dst; dst = t;
+    }
+    TACO_TRY(conv1d_channels_last(src, EMB, h->enc_lstm_wih, nullptr, h->enc_lstm_bias, nullptr, 0, ws.xproj, 8 * ENC_H, n,
+                                  n, EMB, 8 * ENC_H, 1, ACT_NONE, st));
+    return bilstm_recurrence(h, ws.xproj, d_memory, B, T, st);
+}
+
+static int run_decoder(b200taco_handle* h, int mode, const float* d_memory, const float* d_mel_targets,
+                       const int64_t* d_text_lengths, int B, int T, int S, float thr, int stop_mode, float* d_mel,
+                       float* d_gate, float* d_align, int32_t* d_lengths, int32_t* d_steps, void* d_workspace,
+                       size_t workspace_bytes, cudaStream_t st) {
+    const DecoderWs ws = decoder_ws(d_workspace, B, T, mode == 1 ? S : 0);
+    TACO_REQUIRE(workspace_bytes >= ws.total, B200TACO_ERR_STATE, "decoder workspace too small: %zu < %zu", workspace_bytes,
+                 ws.total);
+    // processed_memory = memory_layer(memory), once per utterance (src/model.py:112)
+    TACO_TRY(conv1d_channels_last(d_memory, EMB, h->attn_memory_wT, nullptr, nullptr, nullptr, 0, ws.pm, ATT_DIM, B * T,
+                                  B * T, EMB, ATT_DIM, 1, ACT_NONE, st));
+    if (mode == 1) {
+        // all prenet outputs at once: the inputs of every step are known (teacher forcing)
+        const int n = S * B;
+        tf_frames_kernel<<<(int)(((size_t)n * N_MELS + 255) / 256 > 2048 ? 2048 : ((size_t)n * N_MELS + 255) / 256), 256, 0,
+                           st>>>(d_mel_targets, ws.frames, B, S);
+        TACO_LAUNCHED();
+        TACO_TRY(conv1d_channels_last(ws.frames, N_MELS, h->prenet1T, nullptr, nullptr, nullptr, 0, ws.y1, PRENET, n, n,
+                                      N_MELS, PRENET, 1, ACT_RELU, st));
+        TACO_TRY(conv1d_channels_last(ws.y1, PRENET, h->prenet2T, nullptr, nullptr, nullptr, 0, ws.y2, PRENET, n, n, PRENET,
+                                      PRENET, 1, ACT_RELU, st));
+        const int BP = decoder_batch_pad(B);
+        p_all_pack_kernel<<<2048, 256, 0, st>>>(ws.y2, ws.p_all, B, BP, S);
+        TACO_LAUNCHED();
+    }
+    DecoderArgs a{};
+    a.B = B; a.T = T; a.max_steps = S; a.mode = mode; a.stop_mode = stop_mode; a.gate_threshold = thr;
+    a.memory = d_memory; a.pm = ws.pm; a.text_lengths = d_text_lengths; a.p_all = ws.p_all;
+    a.mel = d_mel; a.gate = d_gate; a.align = d_align; a.lengths = d_lengths; a.steps_run = d_steps;
+    a.scratch = ws.scratch; a.scratch_bytes = ws.scratch_bytes;
+    return decoder_run(h, a, st);
+}
+
+B200TACO_API int32_t b200taco_decoder_infer(b200taco_handle* h, const float* d_memory, int32_t B, int32_t T, int32_t max_steps,
+                               float gate_threshold, int32_t stop_mode, float* d_mel, float* d_gate, float* d_align,
+                               int32_t* d_lengths, int32_t* d_steps_run, void* d_workspace, size_t workspace_bytes,
+                               void* stream) {
+    TACO_TRY(check_handle(h, true));
+    TACO_TRY(check_shape(B, T));
+    TACO_REQUIRE(d_memory && d_mel && d_gate && d_align && d_lengths && d_steps_run && d_workspace, B200TACO_ERR_INVALID,
+                 "decoder_infer: null pointer");
+    TACO_REQUIRE(max_steps >= 1, B200TACO_ERR_INVALID, "max_steps must be >= 1 (got %d)", max_steps);
+    TACO_REQUIRE(stop_mode == B200TACO_STOP_BATCH_WIDE || stop_mode == B200TACO_STOP_PER_UTTERANCE, B200TACO_ERR_INVALID,
+                 "unknown stop mode %d", stop_mode);
+    return run_decoder(h, 0, d_memory, nullptr, nullptr, B, T, max_steps, gate_threshold, stop_mode, d_mel, d_gate, d_align,
+                       d_lengths, d_steps_run, d_workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+B200TACO_API int32_t b200taco_decoder_teacher_forced(b200taco_handle* h, const float* d_memory, const float* d_mel_targets,
+                                        const int64_t* d_text_lengths, int32_t B, int32_t T, int32_t S, float* d_mel,
+                                        float* d_gate, float* d_align, void* d_workspace, size_t workspace_bytes,
+                                        void* stream) {
+    TACO_TRY(check_handle(h, true));
+    TACO_TRY(check_shape(B, T));
+    TACO_REQUIRE(d_memory && d_mel_targets && d_mel && d_gate && d_align && d_workspace, B200TACO_ERR_INVALID,
+                 "decoder_teacher_forced: null pointer");
+    TACO_REQUIRE(S >= 1, B200TACO_ERR_INVALID, "S must be >= 1 (got %d)", S);
+    // lengths/steps outputs of the kernel land in the control area of the workspace tail
+    const DecoderWs ws = decoder_ws(d_workspace, B, T, S);
+    TACO_REQUIRE(workspace_bytes >= ws.total + 1024, B200TACO_ERR_STATE, "decoder workspace too small: %zu < %zu",
+                 workspace_bytes, ws.total + 1024);
+    int32_t* tail = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(d_workspace) + ws.total);
+    return run_decoder(h, 1, d_memory, d_mel_targets, d_text_lengths, B, T, S, 2.0f, B200TACO_STOP_BATCH_WIDE, d_mel, d_gate,
+                       d_align, tail, tail + MAX_BATCH, d_workspace, ws.total, static_cast<cudaStream_t>(stream));
+}
+
+B200TACO_API int32_t b200taco_postnet_fwd(b200taco_handle* h, const float* d_mel_coarse, int32_t B, int32_t S, float* d_mel_post,
+                             void* d_workspace, size_t workspace_bytes, void* stream) {
+    TACO_TRY(check_handle(h, true));
+    TACO_REQUIRE(d_mel_coarse && d_mel_post && d_workspace, B200TACO_ERR_INVALID, "postnet_fwd: null pointer");
+    TACO_REQUIRE(B >= 1 && S >= 1, B200TACO_ERR_INVALID, "postnet_fwd: B %d, S %d", B, S);
+    const PostnetWs ws = postnet_ws(d_workspace, B, S);
+    TACO_REQUIRE(workspace_bytes >= ws.total, B200TACO_ERR_STATE, "postnet workspace too small: %zu < %zu", workspace_bytes,
+                 ws.total);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int n = B * S;
+    const float* src = d_mel_coarse;
+    int c_in = N_MELS;
+    float* bufs[2] = {ws.a, ws.b};
+    for (int i = 0; i < POST_CONVS; ++i) {
+        const bool last = i == POST_CONVS - 1;
+        const int c_out = last ? N_MELS : POST_DIM;
+        float* dst = last ? d_mel_post : bufs[i & 1];
+        TACO_TRY(conv1d_channels_last(src, c_in, h->post_conv_w[i], h->post_conv_scale[i], h->post_conv_shift[i],
+                                      last ? d_mel_coarse : nullptr, N_MELS, dst, c_out, n, S, c_in, c_out, POST_KERNEL,
+                                      last ? ACT_NONE : ACT_TANH, st));
+        src = dst;
+        c_in = c_out;
+    }
+    return B200TACO_OK;
+}
+
+B200TACO_API int32_t b200taco_measure_l2_read(void* d_buf, size_t bytes, int32_t iters, float* gbps, void* stream) {
+    return measure_l2_read(d_buf, bytes, iters, gbps, static_cast<cudaStream_t>(stream));
+}
+
+B200TACO_API int64_t b200taco_launch_count(int32_t reset) {
+    const int64_t v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+}  // extern "C"

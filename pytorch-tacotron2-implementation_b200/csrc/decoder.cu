@@ -1,0 +1,877 @@
+// Persistent Tacotron 2 decoder: the whole frame loop of Decoder.inference / Decoder.forward
+// (reference src/model.py:277-333) in ONE cooperative kernel launch.
+//
+// Per decode step (Decoder._decode_step, src/model.py:246-275) the grid runs four phases
+// separated by a hand-rolled gpu-scope barrier:
+//   P1  attention LSTMCell   z = W[4096 x 1792] . [prenet; ctx; ah]      (128 "GEMM" CTAs, 32 gate rows each)
+//       + each CTA's slice of the query projection Wq . ah (partials, summed in P2)
+//   P2  location-sensitive attention (src/model.py:117-148), one work item per
+//       (utterance, slice of encoder positions); partial softmax/context per slice, the last
+//       slice to arrive (atomic ticket) merges them - no extra grid barrier
+//   P3  decoder LSTMCell     z = W[4096 x 2560] . [ctx; ah; dh]  + each CTA's slice of the
+//       mel/gate projection (partials); spare CTAs compute the context part of the projection
+//   P4  per utterance: sum projection partials -> mel frame, gate logit, stop rule, prenet
+//       of the next input frame
+// LSTM weights stream from L2 (they fit: 35.7 MB bf16) into shared memory through a
+// 4-stage mbarrier pipeline filled by TMA bulk copies (cp.async.bulk, SASS UBLKCP) issued by
+// a dedicated producer warp; weight chunks of the next GEMM phase are prefetched across the
+// grid barrier.  Cell state c never leaves the owning CTA; h, ctx and the prenet output are
+// exchanged through the double-buffered "act" matrix [2816][BP] in global memory (L2).
+#include <cooperative_groups.h>
+
+#include "handle.h"
+
+namespace b200taco {
+
+namespace {
+
+constexpr int NW = 8;                       // consumer warps
+constexpr int NTC = NW * 32;                // consumer threads
+constexpr int NT = NTC + 32;                // + producer warp
+constexpr int STAGES = 4;
+constexpr int TILE_POS = 40;                // encoder positions per attention tile (8 groups x 5)
+constexpr int MAX_NS = 16;                  // max slices per utterance
+constexpr int APART = 4 + EMB;              // per-slice partial: m, s, pad, pad, ctx[512]
+constexpr uint64_t SPIN_TIMEOUT_NS = 4000000000ull;
+
+// control words in scratch
+constexpr int CTRL_BARRIER = 0, CTRL_STOP = 1, CTRL_FINISHED = 2, CTRL_TICKETS = 32, CTRL_DONE = 32 + MAX_BATCH,
+              CTRL_LEN = 32 + 2 * MAX_BATCH, CTRL_WORDS = 32 + 3 * MAX_BATCH;
+
+struct KParams {
+    int B, T, Tp, NS, SL, NQ, max_steps, mode, stop_mode;
+    float thr;
+    const void* w_attn;
+    const void* w_dec;
+    const float *bias_attn, *bias_dec, *wq_slices, *wproj_slices, *wproj_ctxT, *proj_bias, *prenet1T, *prenet2T,
+        *loc_conv, *loc_denseT, *attn_v;
+    const float *memory, *pm, *p_all;
+    const int64_t* text_lengths;
+    float *mel, *gate, *align;
+    int32_t *lengths, *steps_run;
+    // scratch
+    float *act, *pqpart, *melpart, *melctx, *ctx_bj, *attn_prev, *attn_cum, *wtmp, *apart;
+    uint32_t* ctrl;
+};
+
+template <int BP, int WBYTES = 2>
+struct Tile {
+    static constexpr int BPL = BP >= 64 ? 8 : (BP >= 4 ? 4 : BP);   // batch columns per lane
+    static constexpr int LB = BP / BPL;                              // lanes along batch
+    static constexpr int LK = 32 / (4 * LB);                         // lanes along k (4 lanes along rows)
+    static constexpr int CK = (BP <= 4 ? 256 : (BP <= 16 ? 128 : 64)) * 2 / WBYTES;  // k rows per pipeline chunk
+    static constexpr int KPW = CK / NW;                              // k rows per warp per chunk
+    static constexpr int KPL = KPW / LK;                             // k rows per lane per chunk
+    static_assert(LB * BPL == BP && LK * LB * 4 == 32 && KPL * LK == KPW, "tile");
+};
+
+template <int BP, typename WT>
+struct Smem {
+    using TL = Tile<BP, sizeof(WT)>;
+    static constexpr int W_BYTES = TL::CK * ROWS_PER_CTA * (int)sizeof(WT);
+    static constexpr int A_BYTES = TL::CK * BP * 4;
+    static constexpr int STAGE_BYTES = W_BYTES + A_BYTES;
+    // persistent small arrays (floats)
+    static constexpr int OFF_BAR = 0;                                          // 2*STAGES u64
+    static constexpr int OFF_STAGE = 128;
+    static constexpr int OFF_RED = OFF_STAGE + STAGES * STAGE_BYTES;           // NW*32*BP floats, aliased by P2/P4 scratch
+    static constexpr int RED_BYTES_MIN = 72 * 1024;
+    static constexpr int RED_BYTES = (NW * 32 * BP * 4 > RED_BYTES_MIN) ? NW * 32 * BP * 4 : RED_BYTES_MIN;
+    static constexpr int OFF_Z = OFF_RED + RED_BYTES;                          // 32*BP
+    static constexpr int OFF_CA = OFF_Z + 32 * BP * 4;                         // 8*BP
+    static constexpr int OFF_CD = OFF_CA + 8 * BP * 4;
+    static constexpr int OFF_H = OFF_CD + 8 * BP * 4;
+    static constexpr int OFF_BIAS = OFF_H + 8 * BP * 4;                        // 64
+    static constexpr int OFF_WQ = OFF_BIAS + 64 * 4;                           // 128*8
+    static constexpr int OFF_WPROJ = OFF_WQ + 128 * 8 * 4;                     // 81*8 (pad 656)
+    static constexpr int OFF_WLOC = OFF_WPROJ + 656 * 4;                       // 32*63
+    static constexpr int OFF_WLD = OFF_WLOC + 32 * 63 * 4;                     // 32*128
+    static constexpr int OFF_V = OFF_WLD + 32 * 128 * 4;                       // 132
+    static constexpr int OFF_MISC = OFF_V + 132 * 4;                           // 64 floats of flags/scalars
+    static constexpr int TOTAL = OFF_MISC + 64 * 4;
+    static_assert(TOTAL <= 227 * 1024, "shared memory budget");
+    static_assert(STAGE_BYTES % 128 == 0 && W_BYTES % 128 == 0, "bulk copy alignment");
+};
+
+// Scratch carved from the "red" region during P2 (floats)
+struct P2Scratch {
+    static constexpr int PQ = 0;                                  // 256 (two halves)
+    static constexpr int WIN = 256;                               // 2 * WIN_LEN
+    static constexpr int WIN_LEN = MAX_TEXT_LEN + 2 * TILE_POS + 32;
+    static constexpr int E = WIN + 2 * WIN_LEN;                   // MAX_TEXT_LEN + TILE_POS
+    static constexpr int LOC = E + MAX_TEXT_LEN + TILE_POS;       // TILE_POS * 33
+    static constexpr int PM = LOC + TILE_POS * 33 + 8;            // TILE_POS * 128
+    static constexpr int EPART = PM + TILE_POS * 128;             // TILE_POS * 4
+    static constexpr int SC = EPART + TILE_POS * 4;               // MAX_NS scale factors + m,s
+    static constexpr int TOTAL = SC + 64;
+};
+static_assert(P2Scratch::TOTAL * 4 <= 72 * 1024, "P2 scratch must fit the red region");
+
+__device__ __forceinline__ void spin_fail() { __trap(); }
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint64_t t0 = global_timer_ns();
+    while (!mbar_try_wait(bar, parity)) {
+        if (global_timer_ns() - t0 > SPIN_TIMEOUT_NS) spin_fail();
+    }
+}
+
+// All NT threads of every CTA call this the same number of times.
+__device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t& epoch, uint32_t ncta) {
+    __syncthreads();
+    epoch += 1;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        fence_proxy_async();
+        red_release_add_u32(counter, 1u);
+        const uint32_t target = epoch * ncta;
+        if (ld_acquire_u32(counter) < target) {
+            uint64_t t0 = global_timer_ns();
+            while (ld_acquire_u32(counter) < target) {
+                if (global_timer_ns() - t0 > SPIN_TIMEOUT_NS) spin_fail();
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void consumer_sync() { named_bar_sync(1, NTC); }
+
+template <typename WT>
+__device__ __forceinline__ void load_w8(const WT* p, float (&w)[8]);
+template <>
+__device__ __forceinline__ void load_w8<__nv_bfloat16>(const __nv_bfloat16* p, float (&w)[8]) {
+    uint4 v = *reinterpret_cast<const uint4*>(p);
+    w[0] = bf16lo(v.x); w[1] = bf16hi(v.x); w[2] = bf16lo(v.y); w[3] = bf16hi(v.y);
+    w[4] = bf16lo(v.z); w[5] = bf16hi(v.z); w[6] = bf16lo(v.w); w[7] = bf16hi(v.w);
+}
+template <>
+__device__ __forceinline__ void load_w8<float>(const float* p, float (&w)[8]) {
+    float4 a = *reinterpret_cast<const float4*>(p);
+    float4 b = *reinterpret_cast<const float4*>(p + 4);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+}
+
+template <int N>
+__device__ __forceinline__ void load_a(const float* p, float (&a)[N]) {
+    if constexpr (N == 1) {
+        a[0] = p[0];
+    } else if constexpr (N == 2) {
+        float2 v = *reinterpret_cast<const float2*>(p);
+        a[0] = v.x; a[1] = v.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; i += 4) {
+            float4 v = *reinterpret_cast<const float4*>(p + i);
+            a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Pipeline bookkeeping shared by the producer warp and the consumer warps: both walk the
+// same deterministic sequence of chunks, so a running chunk counter gives stage and parity.
+struct Pipe {
+    uint64_t* full;
+    uint64_t* empty;
+    uint8_t* stages;
+};
+
+// Consumer side of one LSTM gate contraction: acc[r][j] += W[k][lr*8+r] * act[k][lb*BPL+j].
+template <int BP, typename WT>
+__device__ __forceinline__ void gemm_consume(const Pipe& pipe, uint32_t& g, int nchunks, int warp, int lane,
+                                             float (&acc)[8][Tile<BP>::BPL]) {
+    using TL = Tile<BP, sizeof(WT)>;
+    using SM = Smem<BP, WT>;
+    const int lk = lane % TL::LK;
+    const int lb = (lane / TL::LK) % TL::LB;
+    const int lr = lane / (TL::LK * TL::LB);
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int j = 0; j < TL::BPL; ++j) acc[r][j] = 0.f;
+    for (int ch = 0; ch < nchunks; ++ch, ++g) {
+        const uint32_t stage = g % STAGES, parity = (g / STAGES) & 1u;
+        mbar_wait(&pipe.full[stage], parity);
+        const WT* Ws = reinterpret_cast<const WT*>(pipe.stages + stage * SM::STAGE_BYTES);
+        const float* As = reinterpret_cast<const float*>(pipe.stages + stage * SM::STAGE_BYTES + SM::W_BYTES);
+#pragma unroll
+        for (int j = 0; j < TL::KPL; ++j) {
+            const int k = warp * TL::KPW + j * TL::LK + lk;
+            float w[8], a[TL::BPL];
+            load_w8<WT>(Ws + k * ROWS_PER_CTA + lr * 8, w);
+            load_a<TL::BPL>(As + k * BP + lb * TL::BPL, a);
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < TL::BPL; ++c) acc[r][c] = fmaf(w[r], a[c], acc[r][c]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pipe.empty[stage]);
+    }
+}
+
+// Reduce the per-warp partial tiles: over the k-lanes by shuffle, over warps through `red`;
+// result z[row][b] in shared memory.  Consumer warps only.
+template <int BP>
+__device__ __forceinline__ void gemm_reduce(float (&acc)[8][Tile<BP>::BPL], float* red, float* z, int warp, int lane,
+                                            int tid) {
+    using TL = Tile<BP>;
+    const int lk = lane % TL::LK;
+    const int lb = (lane / TL::LK) % TL::LB;
+    const int lr = lane / (TL::LK * TL::LB);
+#pragma unroll
+    for (int o = 1; o < TL::LK; o <<= 1)
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < TL::BPL; ++c) acc[r][c] += __shfl_xor_sync(0xffffffffu, acc[r][c], o);
+    if (lk == 0) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < TL::BPL; ++c)
+                red[(warp * ROWS_PER_CTA + lr * 8 + r) * BP + lb * TL::BPL + c] = acc[r][c];
+    }
+    consumer_sync();
+    for (int i = tid; i < ROWS_PER_CTA * BP; i += NTC) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s += red[w * ROWS_PER_CTA * BP + i];
+        z[i] = s;
+    }
+    consumer_sync();
+}
+
+// LSTMCell pointwise part (gate order i,f,g,o; src/model.py:195-203 via nn.LSTMCell).
+// z rows are unit*4+gate; c state stays in shared memory of the owning CTA.
+template <int BP>
+__device__ __forceinline__ void lstm_pointwise(const float* z, const float* bias, float* c_state, float* h_out,
+                                               float* act_dst /* &act[buf][row0][0] */, int B, int tid) {
+    for (int i = tid; i < UNITS_PER_CTA * BP; i += NTC) {
+        const int u = i / BP, b = i % BP;
+        if (b < B) {
+            const float zi = z[(u * 4 + 0) * BP + b] + bias[u * 4 + 0];
+            const float zf = z[(u * 4 + 1) * BP + b] + bias[u * 4 + 1];
+            const float zg = z[(u * 4 + 2) * BP + b] + bias[u * 4 + 2];
+            const float zo = z[(u * 4 + 3) * BP + b] + bias[u * 4 + 3];
+            const float c = sigmoid_acc(zf) * c_state[i] + sigmoid_acc(zi) * tanhf(zg);
+            const float h = sigmoid_acc(zo) * tanhf(c);
+            c_state[i] = c;
+            h_out[i] = h;
+            act_dst[u * BP + b] = h;
+        } else {
+            h_out[i] = 0.f;
+        }
+    }
+    consumer_sync();
+}
+
+// Producer: issue the weight part of chunks [c0, c1) of a GEMM phase (arms the full barrier
+// with the byte count of BOTH copies; the activation copy follows in produce_a).
+template <int BP, typename WT>
+__device__ __forceinline__ void produce_w(const Pipe& pipe, uint32_t g0, int c0, int c1, const WT* wsrc) {
+    using SM = Smem<BP, WT>;
+    using TL = Tile<BP, sizeof(WT)>;
+    for (int ch = c0; ch < c1; ++ch) {
+        const uint32_t g = g0 + ch, stage = g % STAGES, parity = ((g / STAGES) & 1u) ^ 1u;
+        mbar_wait(&pipe.empty[stage], parity);
+        mbar_arrive_expect_tx(&pipe.full[stage], SM::STAGE_BYTES);
+        bulk_g2s(pipe.stages + stage * SM::STAGE_BYTES, wsrc + (size_t)ch * TL::CK * ROWS_PER_CTA, SM::W_BYTES,
+                 &pipe.full[stage]);
+    }
+}
+// rows [0, split) of the phase's K range come from a0, the rest from a1 (teacher forcing
+// reads the prenet rows from the precomputed buffer).
+template <int BP, typename WT>
+__device__ __forceinline__ void produce_a(const Pipe& pipe, uint32_t g0, int c0, int c1, const float* a0,
+                                          const float* a1, int split_chunks) {
+    using SM = Smem<BP, WT>;
+    using TL = Tile<BP, sizeof(WT)>;
+    for (int ch = c0; ch < c1; ++ch) {
+        const uint32_t g = g0 + ch, stage = g % STAGES;
+        const float* src = ch < split_chunks ? a0 + (size_t)ch * TL::CK * BP : a1 + (size_t)ch * TL::CK * BP;
+        bulk_g2s(pipe.stages + stage * SM::STAGE_BYTES + SM::W_BYTES, src, SM::A_BYTES, &pipe.full[stage]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+template <int BP, typename WT>
+__global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
+    using TL = Tile<BP, sizeof(WT)>;
+    using SM = Smem<BP, WT>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cta = blockIdx.x, ncta = gridDim.x;
+    const bool is_gemm = cta < GEMM_CTAS;
+    const bool is_producer = warp == NW;
+    const int B = p.B, T = p.T;
+
+    Pipe pipe;
+    pipe.full = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
+    pipe.empty = pipe.full + STAGES;
+    pipe.stages = smem + SM::OFF_STAGE;
+    float* red = reinterpret_cast<float*>(smem + SM::OFF_RED);
+    float* z_s = reinterpret_cast<float*>(smem + SM::OFF_Z);
+    float* ca_s = reinterpret_cast<float*>(smem + SM::OFF_CA);
+    float* cd_s = reinterpret_cast<float*>(smem + SM::OFF_CD);
+    float* h_s = reinterpret_cast<float*>(smem + SM::OFF_H);
+    float* bias_s = reinterpret_cast<float*>(smem + SM::OFF_BIAS);
+    float* wq_s = reinterpret_cast<float*>(smem + SM::OFF_WQ);
+    float* wproj_s = reinterpret_cast<float*>(smem + SM::OFF_WPROJ);
+    float* wloc_s = reinterpret_cast<float*>(smem + SM::OFF_WLOC);
+    float* wld_s = reinterpret_cast<float*>(smem + SM::OFF_WLD);
+    float* v_s = reinterpret_cast<float*>(smem + SM::OFF_V);
+    int* misc_s = reinterpret_cast<int*>(smem + SM::OFF_MISC);
+
+    // ---- one-time setup ----
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&pipe.full[s], 1);
+            mbar_init(&pipe.empty[s], NW);
+        }
+        fence_mbar_init();
+    }
+    for (int i = tid; i < UNITS_PER_CTA * BP; i += NT) { ca_s[i] = 0.f; cd_s[i] = 0.f; h_s[i] = 0.f; }
+    if (is_gemm) {
+        for (int i = tid; i < 32; i += NT) {
+            bias_s[i] = p.bias_attn[cta * 32 + i];
+            bias_s[32 + i] = p.bias_dec[cta * 32 + i];
+        }
+        for (int i = tid; i < 128 * 8; i += NT) wq_s[i] = p.wq_slices[(size_t)cta * 1024 + i];
+        for (int i = tid; i < PROJ_OUT * 8; i += NT) wproj_s[i] = p.wproj_slices[(size_t)cta * PROJ_OUT * 8 + i];
+    }
+    for (int i = tid; i < LOC_F * 2 * LOC_K; i += NT) wloc_s[(i / 62) * 63 + (i % 62)] = p.loc_conv[i];
+    for (int i = tid; i < LOC_F * ATT_DIM; i += NT) wld_s[i] = p.loc_denseT[i];
+    for (int i = tid; i < 130; i += NT) v_s[i] = p.attn_v[i];
+    __syncthreads();
+
+    const WT* w_attn = reinterpret_cast<const WT*>(p.w_attn) + (size_t)cta * K_ATTN * ROWS_PER_CTA;
+    const WT* w_dec = reinterpret_cast<const WT*>(p.w_dec) + (size_t)cta * K_DEC * ROWS_PER_CTA;
+    constexpr int NCH1 = K_ATTN / TL::CK, NCH3 = K_DEC / TL::CK, PCH = PRENET / TL::CK;
+    constexpr int PRE1 = NCH1 < STAGES ? NCH1 : STAGES, PRE3 = NCH3 < STAGES ? NCH3 : STAGES;
+    static_assert(PRENET % TL::CK == 0, "prenet rows must be whole chunks");
+
+    uint32_t epoch = 0;
+    uint32_t g = 0;             // chunks consumed (consumers) / chunks fully issued (producer)
+    const bool tf = p.mode == 1;
+    const int total_steps = tf ? p.max_steps : p.max_steps + 1;
+    int steps_done = 0;         // decode steps executed
+    bool stopped = false;
+
+    // producer: weight chunks of the very first phase
+    if (is_producer && is_gemm && lane == 0) produce_w<BP, WT>(pipe, g, 0, PRE1, w_attn);
+
+    for (int s = 0; s < total_steps; ++s) {
+        const int cur = s & 1, prv = cur ^ 1;
+        float* act_cur = p.act + (size_t)cur * ACT_ROWS * BP;
+        float* act_prv = p.act + (size_t)prv * ACT_ROWS * BP;
+        const int out_idx = tf ? s : s - 1;          // F6: decode step 0 of inference is discarded
+
+        // =============================== P1: attention LSTM ===============================
+        if (is_gemm) {
+            if (is_producer) {
+                if (lane == 0) {
+                    fence_proxy_async();
+                    const float* a0 = tf ? p.p_all + (size_t)s * PRENET * BP : act_prv;
+                    // rows >= 256 always come from act_prv; a0 only differs for the prenet rows
+                    for (int ch = 0; ch < NCH1; ++ch) {
+                        if (ch >= PRE1) produce_w<BP, WT>(pipe, g, ch, ch + 1, w_attn);
+                        produce_a<BP, WT>(pipe, g, ch, ch + 1, a0, act_prv, PCH);
+                    }
+                    g += NCH1;
+                    produce_w<BP, WT>(pipe, g, 0, PRE3, w_dec);     // prefetch across P2
+                }
+            } else {
+                float acc[8][TL::BPL];
+                gemm_consume<BP, WT>(pipe, g, NCH1, warp, lane, acc);
+                gemm_reduce<BP>(acc, red, z_s, warp, lane, tid);
+                lstm_pointwise<BP>(z_s, bias_s, ca_s, h_s, act_cur + (size_t)(ACT_AH + cta * UNITS_PER_CTA) * BP, B, tid);
+                // this CTA's slice of the query projection (src/model.py:123): pqpart[b][cta][a]
+                for (int i = tid; i < ATT_DIM * B; i += NTC) {
+                    const int a = i % ATT_DIM, b = i / ATT_DIM;
+                    float sum = 0.f;
+#pragma unroll
+                    for (int u = 0; u < UNITS_PER_CTA; ++u) sum = fmaf(wq_s[a * 8 + u], h_s[u * BP + b], sum);
+                    p.pqpart[((size_t)b * GEMM_CTAS + cta) * ATT_DIM + a] = sum;
+                }
+            }
+        }
+        grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
+
+        // =============================== P2: attention ===============================
+        if (!is_producer) {
+            float* sc = red;
+            const int NS = p.NS, SL = p.SL;
+            const float* prev_in = p.attn_prev + (size_t)prv * B * p.Tp;
+            const float* cum_in = p.attn_cum + (size_t)prv * B * p.Tp;
+            float* prev_out = p.attn_prev + (size_t)cur * B * p.Tp;
+            float* cum_out = p.attn_cum + (size_t)cur * B * p.Tp;
+            for (int item = cta; item < B * NS; item += ncta) {
+                const int b = item / NS, sl = item % NS;
+                const int t0 = sl * SL, t1 = min(T, t0 + SL), n = max(0, t1 - t0);
+                const int len = p.text_lengths ? (int)p.text_lengths[b] : T;
+                consumer_sync();   // previous item's scratch is free
+                // processed query = sum of the 128 per-CTA partials
+                {
+                    const int a = tid & 127, hf = tid >> 7;
+                    const float* src = p.pqpart + ((size_t)b * GEMM_CTAS + hf * 64) * ATT_DIM + a;
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+                    for (int i = 0; i < 64; i += 4) {
+                        s0 += __ldcg(src + (i + 0) * ATT_DIM);
+                        s1 += __ldcg(src + (i + 1) * ATT_DIM);
+                        s2 += __ldcg(src + (i + 2) * ATT_DIM);
+                        s3 += __ldcg(src + (i + 3) * ATT_DIM);
+                    }
+                    sc[P2Scratch::PQ + tid] = (s0 + s1) + (s2 + s3);
+                }
+                // previous / cumulative attention windows with a 15-position halo, zero padded
+                const int ntiles = (n + TILE_POS - 1) / TILE_POS;
+                const int wlen = ntiles * TILE_POS + LOC_K - 1 + 4;
+                for (int i = tid; i < wlen; i += NTC) {
+                    const int t = t0 - (LOC_K - 1) / 2 + i;
+                    const bool ok = t >= 0 && t < T;
+                    sc[P2Scratch::WIN + i] = ok ? __ldcg(prev_in + (size_t)b * p.Tp + t) : 0.f;
+                    sc[P2Scratch::WIN + P2Scratch::WIN_LEN + i] = ok ? __ldcg(cum_in + (size_t)b * p.Tp + t) : 0.f;
+                }
+                consumer_sync();
+                float wld[LOC_F];
+                {
+                    const int a = tid & 127;
+#pragma unroll
+                    for (int f = 0; f < LOC_F; ++f) wld[f] = wld_s[f * ATT_DIM + a];
+                }
+                const float pq = sc[P2Scratch::PQ + (tid & 127)] + sc[P2Scratch::PQ + 128 + (tid & 127)];
+                const float vw = v_s[tid & 127];
+                for (int tile = 0; tile < ntiles; ++tile) {
+                    const int tb = tile * TILE_POS;          // offset inside the slice
+                    // ---- location conv (src/model.py:125-126): 32 filters x (2 x 31 taps)
+                    {
+                        const int f = tid & 31, tg = tid >> 5;
+                        float o5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            float x[LOC_K + 4];
+                            const float* wsrc = sc + P2Scratch::WIN + c * P2Scratch::WIN_LEN + tb + tg * 5;
+#pragma unroll
+                            for (int i = 0; i < LOC_K + 4; ++i) x[i] = wsrc[i];
+#pragma unroll
+                            for (int k = 0; k < LOC_K; ++k) {
+                                const float w = wloc_s[f * 63 + c * LOC_K + k];
+#pragma unroll
+                                for (int j = 0; j < 5; ++j) o5[j] = fmaf(w, x[k + j], o5[j]);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) sc[P2Scratch::LOC + (tg * 5 + j) * 33 + f] = o5[j];
+                    }
+                    // ---- processed-memory tile
+                    for (int i = tid; i < TILE_POS * ATT_DIM; i += NTC) {
+                        const int pl = i / ATT_DIM, a = i % ATT_DIM, t = t0 + tb + pl;
+                        sc[P2Scratch::PM + i] = t < t1 ? __ldg(p.pm + ((size_t)b * T + t) * ATT_DIM + a) : 0.f;
+                    }
+                    consumer_sync();
+                    // ---- energies (src/model.py:127-130): v . tanh(pq + pm + Wld loc)
+                    {
+                        const int a = tid & 127, hf = tid >> 7, wq4 = (tid >> 5) & 3;
+                        for (int pl = hf * (TILE_POS / 2); pl < (hf + 1) * (TILE_POS / 2); ++pl) {
+                            float x = pq + sc[P2Scratch::PM + pl * ATT_DIM + a];
+                            const float* l = sc + P2Scratch::LOC + pl * 33;
+#pragma unroll
+                            for (int f = 0; f < LOC_F; ++f) x = fmaf(wld[f], l[f], x);
+                            const float e = warp_sum(vw * tanh_fast(x));
+                            if (lane == 0) sc[P2Scratch::EPART + pl * 4 + wq4] = e;
+                        }
+                    }
+                    consumer_sync();
+                    if (tid < TILE_POS) {
+                        const float* ep = sc + P2Scratch::EPART + tid * 4;
+                        float e = ((ep[0] + ep[1]) + (ep[2] + ep[3]) + v_s[128]) * v_s[129];
+                        const int t = t0 + tb + tid;
+                        if (t >= len) e = -1e9f;                       // masked_fill, src/model.py:132
+                        sc[P2Scratch::E + tb + tid] = e;
+                    }
+                    // next tile's writes to LOC/PM happen after the sync at its own mid-point;
+                    // EPART is rewritten only after that sync, E is disjoint per tile.
+                    consumer_sync();
+                }
+                // ---- slice-local softmax statistics (warp 0) ----
+                if (warp == 0) {
+                    float m = -INFINITY;
+                    for (int i = lane; i < n; i += 32) m = fmaxf(m, sc[P2Scratch::E + i]);
+                    m = warp_max(m);
+                    float ssum = 0.f;
+                    for (int i = lane; i < n; i += 32) {
+                        const float ew = expf(sc[P2Scratch::E + i] - m);
+                        sc[P2Scratch::E + i] = ew;
+                        ssum += ew;
+                    }
+                    ssum = warp_sum(ssum);
+                    if (lane == 0) {
+                        sc[P2Scratch::SC + 32] = n > 0 ? m : -INFINITY;
+                        sc[P2Scratch::SC + 33] = ssum;
+                    }
+                }
+                consumer_sync();
+                // ---- slice-local un-normalised context: sum_t ew[t] * memory[b][t][:] ----
+                float2 cacc = make_float2(0.f, 0.f);
+                {
+                    const float2* mrow = reinterpret_cast<const float2*>(p.memory + ((size_t)b * T + t0) * EMB) + tid;
+#pragma unroll 8
+                    for (int i = 0; i < n; ++i) {
+                        const float2 mv = __ldg(mrow + (size_t)i * (EMB / 2));
+                        const float ew = sc[P2Scratch::E + i];
+                        cacc.x = fmaf(ew, mv.x, cacc.x);
+                        cacc.y = fmaf(ew, mv.y, cacc.y);
+                    }
+                }
+                float* part = p.apart + ((size_t)b * MAX_NS + sl) * APART;
+                if (NS > 1) {
+                    reinterpret_cast<float2*>(part + 4)[tid] = cacc;
+                    if (tid == 0) { part[0] = sc[P2Scratch::SC + 32]; part[1] = sc[P2Scratch::SC + 33]; }
+                    for (int i = tid; i < n; i += NTC) p.wtmp[(size_t)b * p.Tp + t0 + i] = sc[P2Scratch::E + i];
+                    __threadfence();
+                    consumer_sync();
+                    if (tid == 0) {
+                        const uint32_t ticket = atomicAdd(p.ctrl + CTRL_TICKETS + b, 1u);
+                        misc_s[0] = (ticket % (uint32_t)NS) == (uint32_t)(NS - 1);
+                        __threadfence();
+                    }
+                    consumer_sync();
+                    if (!misc_s[0]) continue;
+                    // last slice of this utterance: merge
+                    if (tid < 32) {
+                        float m = -INFINITY;
+                        if (tid < NS) m = __ldcg(p.apart + ((size_t)b * MAX_NS + tid) * APART);
+                        const float M = warp_max(m);
+                        float scale = 0.f, ssum = 0.f;
+                        if (tid < NS) {
+                            scale = expf(m - M);
+                            ssum = scale * __ldcg(p.apart + ((size_t)b * MAX_NS + tid) * APART + 1);
+                        }
+                        ssum = warp_sum(ssum);
+                        if (tid < NS) sc[P2Scratch::SC + tid] = scale;
+                        if (tid == 0) sc[P2Scratch::SC + 33] = ssum;
+                    }
+                    consumer_sync();
+                    cacc = make_float2(0.f, 0.f);
+                    for (int q = 0; q < NS; ++q) {
+                        const float2 cv =
+                            __ldcg(reinterpret_cast<const float2*>(p.apart + ((size_t)b * MAX_NS + q) * APART + 4) + tid);
+                        const float scale = sc[P2Scratch::SC + q];
+                        cacc.x = fmaf(scale, cv.x, cacc.x);
+                        cacc.y = fmaf(scale, cv.y, cacc.y);
+                    }
+                } else {
+                    if (tid == 0) sc[P2Scratch::SC + 0] = 1.f;
+                    consumer_sync();
+                }
+                const float S = sc[P2Scratch::SC + 33];
+                cacc.x = cacc.x / S;
+                cacc.y = cacc.y / S;
+                // context -> act (column b) and the utterance-major copy used by the projections
+                act_cur[(size_t)(ACT_CTX + 2 * tid) * BP + b] = cacc.x;
+                act_cur[(size_t)(ACT_CTX + 2 * tid + 1) * BP + b] = cacc.y;
+                reinterpret_cast<float2*>(p.ctx_bj + (size_t)b * EMB)[tid] = cacc;
+                // attention weights: alignment output, prev, cum (src/model.py:142-145)
+                for (int t = tid; t < T; t += NTC) {
+                    float ew;
+                    if (NS > 1) ew = __ldcg(p.wtmp + (size_t)b * p.Tp + t) * sc[P2Scratch::SC + t / SL];
+                    else ew = sc[P2Scratch::E + t];
+                    const float w = ew / S;
+                    prev_out[(size_t)b * p.Tp + t] = w;
+                    cum_out[(size_t)b * p.Tp + t] = __ldcg(cum_in + (size_t)b * p.Tp + t) + w;
+                    if (out_idx >= 0) p.align[((size_t)out_idx * B + b) * T + t] = w;
+                }
+            }
+        }
+        grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
+
+        // =============================== P3: decoder LSTM ===============================
+        if (is_gemm) {
+            if (is_producer) {
+                if (lane == 0) {
+                    fence_proxy_async();
+                    const float* a = act_cur + (size_t)ACT_CTX * BP;
+                    for (int ch = 0; ch < NCH3; ++ch) {
+                        if (ch >= PRE3) produce_w<BP, WT>(pipe, g, ch, ch + 1, w_dec);
+                        produce_a<BP, WT>(pipe, g, ch, ch + 1, a, a, 0);
+                    }
+                    g += NCH3;
+                    produce_w<BP, WT>(pipe, g, 0, PRE1, w_attn);    // prefetch next step's P1 across P4
+                }
+            } else {
+                float acc[8][TL::BPL];
+                gemm_consume<BP, WT>(pipe, g, NCH3, warp, lane, acc);
+                gemm_reduce<BP>(acc, red, z_s, warp, lane, tid);
+                lstm_pointwise<BP>(z_s, bias_s + 32, cd_s, h_s, act_prv + (size_t)(ACT_DH + cta * UNITS_PER_CTA) * BP, B,
+                                   tid);
+                // this CTA's slice of linear_projection / gate_layer (src/model.py:272-274)
+                for (int i = tid; i < PROJ_PAD * B; i += NTC) {
+                    const int o = i % PROJ_PAD, b = i / PROJ_PAD;
+                    if (o < PROJ_OUT) {
+                        float sum = 0.f;
+#pragma unroll
+                        for (int u = 0; u < UNITS_PER_CTA; ++u) sum = fmaf(wproj_s[o * 8 + u], h_s[u * BP + b], sum);
+                        p.melpart[((size_t)b * GEMM_CTAS + cta) * PROJ_PAD + o] = sum;
+                    }
+                }
+            }
+        } else if (!is_producer) {
+            // spare CTAs: context part of the projections + bias: melctx[b][o]
+            float* sc = red;
+            const int nspare = ncta - GEMM_CTAS;
+            for (int b = cta - GEMM_CTAS; b < B; b += nspare) {
+                consumer_sync();
+                for (int i = tid; i < EMB; i += NTC) sc[i] = __ldcg(p.ctx_bj + (size_t)b * EMB + i);
+                consumer_sync();
+                const int o = tid % PROJ_PAD, jg = tid / PROJ_PAD;       // 96 x 2 groups (+64 idle threads)
+                if (jg < 2) {
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                    const float* wsrc = p.wproj_ctxT + (size_t)(jg * 256) * PROJ_PAD + o;
+                    const float* cs = sc + jg * 256;
+#pragma unroll 4
+                    for (int j = 0; j < 256; j += 4) {
+                        s0 = fmaf(__ldg(wsrc + (size_t)(j + 0) * PROJ_PAD), cs[j + 0], s0);
+                        s1 = fmaf(__ldg(wsrc + (size_t)(j + 1) * PROJ_PAD), cs[j + 1], s1);
+                        s2 = fmaf(__ldg(wsrc + (size_t)(j + 2) * PROJ_PAD), cs[j + 2], s2);
+                        s3 = fmaf(__ldg(wsrc + (size_t)(j + 3) * PROJ_PAD), cs[j + 3], s3);
+                    }
+                    sc[EMB + jg * PROJ_PAD + o] = (s0 + s1) + (s2 + s3);
+                }
+                consumer_sync();
+                if (tid < PROJ_PAD)
+                    p.melctx[(size_t)b * PROJ_PAD + tid] = sc[EMB + tid] + sc[EMB + PROJ_PAD + tid] + __ldg(p.proj_bias + tid);
+            }
+        }
+        grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
+
+        // =============================== P4: projection sums, stop rule, prenet ===============================
+        if (!is_producer) {
+            float* sc = red;
+            const int NQ = p.NQ, RQ = PRENET / NQ;
+            for (int item = cta; item < B * NQ; item += ncta) {
+                const int b = item / NQ, q = item % NQ;
+                consumer_sync();
+                {
+                    const int o = tid & 127, ig = tid >> 7;
+                    if (o < PROJ_OUT) {
+                        const float* src = p.melpart + ((size_t)b * GEMM_CTAS + ig * 64) * PROJ_PAD + o;
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+                        for (int i = 0; i < 64; i += 4) {
+                            s0 += __ldcg(src + (i + 0) * PROJ_PAD);
+                            s1 += __ldcg(src + (i + 1) * PROJ_PAD);
+                            s2 += __ldcg(src + (i + 2) * PROJ_PAD);
+                            s3 += __ldcg(src + (i + 3) * PROJ_PAD);
+                        }
+                        sc[ig * 128 + o] = (s0 + s1) + (s2 + s3);
+                    }
+                }
+                consumer_sync();
+                if (tid < PROJ_OUT) {
+                    const float v = sc[tid] + sc[128 + tid] + __ldcg(p.melctx + (size_t)b * PROJ_PAD + tid);
+                    sc[256 + tid] = v;                                  // mel frame (0..79), gate logit (80)
+                    if (q == 0 && out_idx >= 0) {
+                        if (tid < N_MELS) p.mel[((size_t)b * p.max_steps + out_idx) * N_MELS + tid] = v;
+                        else p.gate[(size_t)b * p.max_steps + out_idx] = v;
+                    }
+                    if (q == 0 && !tf && tid == N_MELS && out_idx >= 1) {
+                        // stop rule: src/model.py:327 (batch-wide) or train.py:71-79 (per utterance)
+                        const bool fired = sigmoid_acc(v) > p.thr;
+                        if (fired) {
+                            if (p.stop_mode == B200TACO_STOP_BATCH_WIDE) {
+                                atomicExch(p.ctrl + CTRL_STOP, 1u);
+                            } else if (p.ctrl[CTRL_DONE + b] == 0u) {
+                                p.ctrl[CTRL_DONE + b] = 1u;
+                                p.ctrl[CTRL_LEN + b] = (uint32_t)(out_idx + 1);
+                                if (atomicAdd(p.ctrl + CTRL_FINISHED, 1u) + 1u == (uint32_t)B)
+                                    atomicExch(p.ctrl + CTRL_STOP, 1u);
+                            }
+                        }
+                    }
+                }
+                if (tf) continue;
+                consumer_sync();
+                // prenet layer 1 (all 256 outputs in every quarter CTA), eval mode: no dropout (F4)
+                {
+                    float s0 = 0.f, s1 = 0.f;
+                    const float* wsrc = p.prenet1T + tid;
+#pragma unroll 8
+                    for (int o = 0; o < N_MELS; o += 2) {
+                        s0 = fmaf(__ldg(wsrc + (size_t)o * PRENET), sc[256 + o], s0);
+                        s1 = fmaf(__ldg(wsrc + (size_t)(o + 1) * PRENET), sc[256 + o + 1], s1);
+                    }
+                    sc[384 + tid] = fmaxf(s0 + s1, 0.f);
+                }
+                consumer_sync();
+                // prenet layer 2: this CTA's RQ outputs, k split over NQ thread groups
+                {
+                    const int nl = tid % RQ, kg = tid / RQ, kn = PRENET / NQ;
+                    const float* wsrc = p.prenet2T + (size_t)(kg * kn) * PRENET + q * RQ + nl;
+                    const float* x = sc + 384 + kg * kn;
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+                    for (int m = 0; m < kn; m += 4) {
+                        s0 = fmaf(__ldg(wsrc + (size_t)(m + 0) * PRENET), x[m + 0], s0);
+                        s1 = fmaf(__ldg(wsrc + (size_t)(m + 1) * PRENET), x[m + 1], s1);
+                        s2 = fmaf(__ldg(wsrc + (size_t)(m + 2) * PRENET), x[m + 2], s2);
+                        s3 = fmaf(__ldg(wsrc + (size_t)(m + 3) * PRENET), x[m + 3], s3);
+                    }
+                    sc[640 + kg * RQ + nl] = (s0 + s1) + (s2 + s3);
+                }
+                consumer_sync();
+                if (tid < RQ) {
+                    float v = 0.f;
+                    for (int kg = 0; kg < NQ; ++kg) v += sc[640 + kg * RQ + tid];
+                    act_cur[(size_t)(ACT_P + q * RQ + tid) * BP + b] = fmaxf(v, 0.f);
+                }
+            }
+        }
+        steps_done = s + 1;
+        if (!tf) {
+            grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
+            if (__ldcg(p.ctrl + CTRL_STOP) != 0u) { stopped = true; break; }
+        }
+    }
+
+    // ---- drain: the producer prefetched weight chunks of a phase that will not run ----
+    if (is_producer && is_gemm && lane == 0) {
+        const float* dummy = p.act;
+        produce_a<BP, WT>(pipe, g, 0, PRE1, dummy, dummy, 0);
+        for (int ch = 0; ch < PRE1; ++ch) {
+            const uint32_t gg = g + ch;
+            mbar_wait(&pipe.full[gg % STAGES], (gg / STAGES) & 1u);
+        }
+    }
+    if (cta == 0 && tid == 0) {
+        const int S = tf ? p.max_steps : steps_done - 1;     // output frames (decode step 0 discarded)
+        *p.steps_run = S;
+        for (int b = 0; b < B; ++b) {
+            int len = S;
+            if (!tf && p.stop_mode == B200TACO_STOP_PER_UTTERANCE && __ldcg(p.ctrl + CTRL_DONE + b))
+                len = (int)__ldcg(p.ctrl + CTRL_LEN + b);
+            p.lengths[b] = len;
+        }
+    }
+    (void)stopped;
+}
+
+template <int BP, typename WT>
+int launch(const KParams& kp, int ncta, cudaStream_t stream) {
+    using SM = Smem<BP, WT>;
+    auto kern = decoder_kernel<BP, WT>;
+    TACO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    int per_sm = 0;
+    TACO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, SM::TOTAL));
+    TACO_REQUIRE(per_sm >= 1, B200TACO_ERR_UNSUPPORTED, "decoder kernel does not fit on an SM (smem %d B)", SM::TOTAL);
+    void* args[] = {const_cast<KParams*>(&kp)};
+    TACO_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(ncta), dim3(NT), args, SM::TOTAL, stream));
+    launch_counter()++;
+    return B200TACO_OK;
+}
+
+template <typename WT>
+int dispatch_bp(int BP, const KParams& kp, int ncta, cudaStream_t stream) {
+    switch (BP) {
+        case 1: return launch<1, WT>(kp, ncta, stream);
+        case 2: return launch<2, WT>(kp, ncta, stream);
+        case 4: return launch<4, WT>(kp, ncta, stream);
+        case 8: return launch<8, WT>(kp, ncta, stream);
+        case 16: return launch<16, WT>(kp, ncta, stream);
+        case 32: return launch<32, WT>(kp, ncta, stream);
+        case 64: return launch<64, WT>(kp, ncta, stream);
+    }
+    set_error("unsupported batch padding %d", BP);
+    return B200TACO_ERR_UNSUPPORTED;
+}
+
+struct ScratchLayout {
+    size_t act, pqpart, melpart, melctx, ctx_bj, attn_prev, attn_cum, wtmp, apart, ctrl, total;
+    size_t zero_begin, zero_end;
+};
+
+ScratchLayout scratch_layout(int B, int T) {
+    const int BP = decoder_batch_pad(B);
+    const int Tp = (T + 3) / 4 * 4;
+    ScratchLayout L{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    // zero-initialised region first (state), then write-before-read buffers
+    L.zero_begin = off;
+    L.act = take((size_t)2 * ACT_ROWS * BP * 4);
+    L.attn_prev = take((size_t)2 * B * Tp * 4);
+    L.attn_cum = take((size_t)2 * B * Tp * 4);
+    L.ctrl = take((size_t)CTRL_WORDS * 4);
+    L.zero_end = off;
+    L.pqpart = take((size_t)B * GEMM_CTAS * ATT_DIM * 4);
+    L.melpart = take((size_t)B * GEMM_CTAS * PROJ_PAD * 4);
+    L.melctx = take((size_t)B * PROJ_PAD * 4);
+    L.ctx_bj = take((size_t)B * EMB * 4);
+    L.wtmp = take((size_t)B * Tp * 4);
+    L.apart = take((size_t)B * MAX_NS * APART * 4);
+    L.total = off;
+    return L;
+}
+
+}  // namespace
+
+int decoder_batch_pad(int B) {
+    int bp = 1;
+    while (bp < B) bp <<= 1;
+    return bp;
+}
+
+size_t decoder_scratch_bytes(int B, int T) { return scratch_layout(B, T).total; }
+
+int decoder_run(const b200taco_handle* h, const DecoderArgs& a, cudaStream_t stream) {
+    TACO_REQUIRE(a.B >= 1 && a.B <= MAX_BATCH, B200TACO_ERR_UNSUPPORTED, "batch %d outside [1, %d]", a.B, MAX_BATCH);
+    TACO_REQUIRE(a.T >= 1 && a.T <= MAX_TEXT_LEN, B200TACO_ERR_UNSUPPORTED, "text length %d outside [1, %d]", a.T,
+                 MAX_TEXT_LEN);
+    TACO_REQUIRE(a.max_steps >= 1, B200TACO_ERR_INVALID, "max_steps must be >= 1");
+    TACO_REQUIRE(h->num_sms >= MIN_CTAS, B200TACO_ERR_UNSUPPORTED,
+                 "the persistent decoder needs >= %d SMs (device has %d)", MIN_CTAS, h->num_sms);
+    const ScratchLayout L = scratch_layout(a.B, a.T);
+    TACO_REQUIRE(a.scratch_bytes >= L.total, B200TACO_ERR_STATE, "decoder scratch too small: %zu < %zu",
+                 a.scratch_bytes, L.total);
+    const int ncta = h->num_sms;
+    const int BP = decoder_batch_pad(a.B);
+    uint8_t* base = static_cast<uint8_t*>(a.scratch);
+    TACO_CUDA(cudaMemsetAsync(base + L.zero_begin, 0, L.zero_end - L.zero_begin, stream));
+
+    KParams kp{};
+    kp.B = a.B; kp.T = a.T; kp.Tp = (a.T + 3) / 4 * 4;
+    int ns = ncta / a.B;
+    ns = ns < 1 ? 1 : (ns > MAX_NS ? MAX_NS : ns);
+    // keep slices at least 8 positions long
+    while (ns > 1 && (a.T + ns - 1) / ns < 8) --ns;
+    kp.NS = ns;
+    kp.SL = (a.T + ns - 1) / ns;
+    int nq = ncta / a.B;
+    kp.NQ = nq >= 4 ? 4 : (nq >= 2 ? 2 : 1);
+    kp.max_steps = a.max_steps; kp.mode = a.mode; kp.stop_mode = a.stop_mode; kp.thr = a.gate_threshold;
+    kp.w_attn = h->w_attn; kp.w_dec = h->w_dec;
+    kp.bias_attn = h->bias_attn; kp.bias_dec = h->bias_dec; kp.wq_slices = h->wq_slices;
+    kp.wproj_slices = h->wproj_slices; kp.wproj_ctxT = h->wproj_ctxT; kp.proj_bias = h->proj_bias;
+    kp.prenet1T = h->prenet1T; kp.prenet2T = h->prenet2T; kp.loc_conv = h->loc_conv; kp.loc_denseT = h->loc_denseT;
+    kp.attn_v = h->attn_v;
+    kp.memory = a.memory; kp.pm = a.pm; kp.p_all = a.p_all; kp.text_lengths = a.text_lengths;
+    kp.mel = a.mel; kp.gate = a.gate; kp.align = a.align; kp.lengths = a.lengths; kp.steps_run = a.steps_run;
+    kp.act = reinterpret_cast<float*>(base + L.act);
+    kp.pqpart = reinterpret_cast<float*>(base + L.pqpart);
+    kp.melpart = reinterpret_cast<float*>(base + L.melpart);
+    kp.melctx = reinterpret_cast<float*>(base + L.melctx);
+    kp.ctx_bj = reinterpret_cast<float*>(base + L.ctx_bj);
+    kp.attn_prev = reinterpret_cast<float*>(base + L.attn_prev);
+    kp.attn_cum = reinterpret_cast<float*>(base + L.attn_cum);
+    kp.wtmp = reinterpret_cast<float*>(base + L.wtmp);
+    kp.apart = reinterpret_cast<float*>(base + L.apart);
+    kp.ctrl = reinterpret_cast<uint32_t*>(base + L.ctrl);
+    if (h->weight_dtype == 1) return dispatch_bp<float>(BP, kp, ncta, stream);
+    return dispatch_bp<__nv_bfloat16>(BP, kp, ncta, stream);
+}
+
+}  // namespace b200taco

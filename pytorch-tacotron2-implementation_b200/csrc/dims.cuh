@@ -1,0 +1,44 @@
+// Compile-time specialisation of the Tacotron 2 hot path (reference src/config.py:26-59).
+// b200taco_create() rejects any hparams block that differs from these.
+#pragma once
+
+namespace b200taco {
+
+constexpr int N_SYMBOLS = 72;        // len(config.SYMBOLS), src/config.py:14-23
+constexpr int EMB = 512;             // symbols_embedding_dim == encoder_embedding_dim
+constexpr int ENC_CONVS = 3;
+constexpr int ENC_KERNEL = 5;
+constexpr int ENC_H = 256;           // BiLSTM hidden size per direction
+constexpr int N_MELS = 80;
+constexpr int RNN = 1024;            // decoder_rnn_dim == attention_rnn_dim
+constexpr int PRENET = 256;
+constexpr int ATT_DIM = 128;
+constexpr int LOC_F = 32;
+constexpr int LOC_K = 31;
+constexpr int POST_DIM = 512;
+constexpr int POST_KERNEL = 5;
+constexpr int POST_CONVS = 5;
+
+constexpr int MAX_BATCH = 64;        // rows one persistent-decoder launch carries
+constexpr int MAX_TEXT_LEN = 1024;   // encoder positions per utterance
+
+// ---- persistent decoder geometry -------------------------------------------------
+constexpr int GEMM_CTAS = 128;       // CTAs that own LSTM gate rows
+constexpr int UNITS_PER_CTA = RNN / GEMM_CTAS;     // 8 hidden units ...
+constexpr int ROWS_PER_CTA = 4 * UNITS_PER_CTA;    // ... = 32 gate rows (i,f,g,o of each unit)
+constexpr int MIN_CTAS = 136;        // GEMM CTAs + at least 8 spare CTAs for the ctx part of the projections
+
+// Activation exchange vector ("act"), one column per utterance:
+//   [ prenet out | context | attention h | decoder h ]
+constexpr int ACT_P = 0;
+constexpr int ACT_CTX = PRENET;                    // 256
+constexpr int ACT_AH = ACT_CTX + EMB;              // 768
+constexpr int ACT_DH = ACT_AH + RNN;               // 1792
+constexpr int ACT_ROWS = ACT_DH + RNN;             // 2816
+constexpr int K_ATTN = ACT_DH;                     // attention LSTM reads rows [0, 1792)
+constexpr int K_DEC = ACT_ROWS - ACT_CTX;          // decoder LSTM reads rows [256, 2816)
+
+constexpr int PROJ_OUT = N_MELS + 1;               // 80 mel rows + the gate row
+constexpr int PROJ_PAD = 96;                       // padded row length of projection partials
+
+}  // namespace b200taco

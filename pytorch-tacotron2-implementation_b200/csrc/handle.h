@@ -1,0 +1,85 @@
+// Internal definition of b200taco_handle: the packed-weight cache and device facts.
+#pragma once
+
+#include "common.cuh"
+
+struct b200taco_handle {
+    int device = 0;
+    int num_sms = 0;
+    int weight_dtype = 0;           // 0 = bf16 LSTM matrices (default), 1 = fp32
+    bool packed = false;
+
+    // one device allocation holding every packed tensor below
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+
+    // ---- decoder (decoder.cu) ----
+    void* w_attn = nullptr;         // [128 cta][K_ATTN][32 rows]  bf16 or fp32, rows = unit*4+gate
+    void* w_dec = nullptr;          // [128 cta][K_DEC ][32 rows]
+    float* bias_attn = nullptr;     // [128][32]  b_ih + b_hh
+    float* bias_dec = nullptr;
+    float* wq_slices = nullptr;     // [128 cta][128 a][8 u]    query_layer.weight[a][8*cta+u]
+    float* wproj_slices = nullptr;  // [128 cta][81 o][8 u]     rows 0..79 linear_projection, row 80 gate_layer (dh part)
+    float* wproj_ctxT = nullptr;    // [512 j][96]              ctx part, transposed, zero padded
+    float* proj_bias = nullptr;     // [96]
+    float* prenet1T = nullptr;      // [80][256]
+    float* prenet2T = nullptr;      // [256][256]
+    float* loc_conv = nullptr;      // [32][2][31]
+    float* loc_denseT = nullptr;    // [32 f][128 a]
+    float* attn_v = nullptr;        // [128] v.weight, [128] v.bias, [129] energy_scale
+    // ---- dense layers (dense.cu): weights as [tap][ci][co], folded BatchNorm scale/shift ----
+    float* enc_emb = nullptr;       // [72][512]
+    float* enc_conv_w[3] = {};      // [5][512][512]
+    float* enc_conv_scale[3] = {};  // [512]
+    float* enc_conv_shift[3] = {};
+    float* enc_lstm_wih = nullptr;  // [512][2048]  (fwd i,f,g,o | bwd i,f,g,o)
+    float* enc_lstm_bias = nullptr; // [2048]       b_ih + b_hh
+    float* enc_lstm_whh = nullptr;  // [2 dir][8 rank][128 rows][256 k], rows = unit*4+gate
+    float* attn_memory_wT = nullptr;// [512][128]
+    float* post_conv_w[5] = {};     // [5][ci][co]
+    float* post_conv_scale[5] = {};
+    float* post_conv_shift[5] = {};
+};
+
+namespace b200taco {
+
+// pack.cu
+int pack_weights(b200taco_handle* h, const b200taco_weights* w, cudaStream_t stream);
+size_t packed_arena_bytes(int weight_dtype);
+
+// dense.cu : Y[n][co] = act((sum_{tap,ci} X[n+tap-pad][ci] * W[tap][ci][co]) * scale[co] + shift[co]) (+ res[n][co])
+enum Activation { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
+int conv1d_channels_last(const float* X, int ldx, const float* W, const float* scale, const float* shift,
+                         const float* residual, int ldres, float* Y, int ldy, int n_rows, int seg_len,
+                         int c_in, int c_out, int taps, int act, cudaStream_t stream);
+int embedding_gather(const int64_t* ids, const float* table, float* out, int n, cudaStream_t stream);
+int transpose_bct_to_btc(const float* in, float* out, int B, int C, int T, cudaStream_t stream);
+
+// bilstm.cu
+int bilstm_recurrence(const b200taco_handle* h, const float* xproj, float* memory, int B, int T,
+                      cudaStream_t stream);
+
+// decoder.cu
+struct DecoderArgs {
+    int B, T, max_steps, mode, stop_mode;
+    float gate_threshold;
+    const float* memory;          // (B,T,512)
+    const float* pm;              // (B,T,128) processed memory
+    const int64_t* text_lengths;  // (B) or null
+    const float* p_all;           // teacher forcing: (S,256,BP) prenet outputs, else null
+    float* mel;                   // (B,max_steps,80)
+    float* gate;                  // (B,max_steps)
+    float* align;                 // (max_steps,B,T)
+    int32_t* lengths;             // (B)
+    int32_t* steps_run;           // (1)
+    void* scratch;                // decoder_scratch_bytes()
+    size_t scratch_bytes;
+};
+size_t decoder_scratch_bytes(int B, int T);
+int decoder_batch_pad(int B);
+int decoder_run(const b200taco_handle* h, const DecoderArgs& a, cudaStream_t stream);
+
+// measure.cu
+int measure_l2_read(void* d_buf, size_t bytes, int iters, float* gbps, cudaStream_t stream);
+
+}  // namespace b200taco

@@ -1,0 +1,227 @@
+"""Parity of the CUDA path (through the C ABI) with the reference: golden vectors produced by
+the unmodified reference, and the CPU oracle on the same seeded inputs.
+
+Tolerances (fp32 state and accumulation everywhere; only summation order and the
+exp/tanh implementations differ from the reference's CPU kernels):
+  mel / gate   : 2e-5 absolute on |mel| <= ~10     (measured ~2e-6)
+  alignments   : 2e-6 absolute on weights in [0,1]
+  stop indices / decoded lengths : exact
+"bf16" = decoder LSTM matrices stored as bf16 in the packed cache; the reference side then
+uses the same bf16-representable values, so the tolerance is unchanged.
+"""
+import pytest
+import torch
+
+import util
+from b200taco import synth
+from b200taco._cabi import B200TacoError
+from b200taco.model import Tacotron2
+from oracle import tacotron2_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_MEL = 2e-5
+TOL_ALIGN = 2e-6
+
+
+def gpu_model(sd, weight_dtype="bf16"):
+    m = Tacotron2().eval()
+    m.load_state_dict(sd)
+    m._projection_bias_initialized = True
+    m.lstm_weight_dtype = weight_dtype
+    return m.to("cuda:0")
+
+
+def check(out, gold, tol=TOL_MEL, tol_align=TOL_ALIGN, post_factor=5):
+    post, coarse, gate, aligns = out
+    assert isinstance(aligns, list) and len(aligns) == coarse.shape[1]          # F9
+    assert tuple(coarse.shape) == tuple(gold["mel_coarse"].shape)
+    assert tuple(post.shape) == tuple(gold["mel_post"].shape) and tuple(gate.shape) == tuple(gold["gate"].shape)
+    e = dict(mel=util.maxdiff(coarse.cpu(), gold["mel_coarse"]), gate=util.maxdiff(gate.cpu(), gold["gate"]),
+             post=util.maxdiff(post.cpu(), gold["mel_post"]),
+             align=util.maxdiff(util.stack(aligns).cpu(), gold["align"]))
+    print(e)
+    assert e["mel"] <= tol and e["gate"] <= tol and e["post"] <= tol * post_factor and e["align"] <= tol_align, e
+
+
+# ------------------------------------------------------------------ golden vectors (reference outputs)
+def test_encoder_golden():
+    m = gpu_model(util.weights())
+    ids = synth.phoneme_ids(3, 19, seed=5).cuda()
+    mem = m._get_engine().encoder(ids)
+    assert util.maxdiff(mem.cpu(), util.golden("encoder_b3_t19")["memory"]) <= 2e-6
+
+
+def test_postnet_golden():
+    m = gpu_model(util.weights())
+    g = torch.Generator().manual_seed(11)
+    coarse = torch.randn(2, 80, 37, generator=g)
+    x = coarse.transpose(1, 2).contiguous().cuda()
+    post = m._get_engine().postnet(x)
+    resid = (post - x).transpose(1, 2).cpu()
+    assert util.maxdiff(resid, util.golden("postnet_b2_s37")["residual"]) <= 1e-5
+
+
+@pytest.mark.parametrize("name,kind,bf16,wdt", [("c1_default", "default", False, "fp32"),
+                                                ("c1_default_bf16", "default", True, "bf16"),
+                                                ("c1_stress_bf16", "stress", True, "bf16"),
+                                                ("c1_stress_bf16", "stress", True, "fp32")])
+def test_c1_teacher_forced_golden(name, kind, bf16, wdt):
+    """BASELINE config 1: B=4, lengths [37,29,21,12], 120 target frames, masked attention."""
+    ids, lengths, mel = synth.c1_batch()
+    m = gpu_model(util.weights(kind, bf16), wdt)
+    check(m(ids.cuda(), mel.cuda(), lengths.cuda()), util.golden(name))
+
+
+def test_c1_variants_golden():
+    ids, lengths, mel = synth.c1_batch()
+    m = gpu_model(util.weights(), "fp32")
+    out = m(ids.cuda(), mel.cuda(), lengths.cuda(), use_postnet=False)
+    assert out[0] is out[1]                                       # src/model.py:479-480
+    check(out, util.golden("c1_default_nopostnet"))
+    check(m(ids.cuda(), mel.cuda(), None), util.golden("c1_default_nolengths"))
+
+
+def test_c1_first_call_bias_init_golden():
+    """F10: first forward overwrites linear_projection.bias with the target mean, once."""
+    ids, lengths, mel = synth.c1_batch()
+    m = gpu_model(util.weights(), "fp32")
+    m._projection_bias_initialized = False
+    gold = util.golden("c1_first_call_bias_init")
+    check(m(ids.cuda(), mel.cuda(), lengths.cuda()), gold)
+    assert m._projection_bias_initialized
+    assert util.maxdiff(m.decoder.linear_projection.bias.cpu(), gold["proj_bias_after"]) <= 1e-6
+    before = m.decoder.linear_projection.bias.clone()
+    m(ids.cuda(), (mel + 1).cuda(), lengths.cuda())
+    assert torch.equal(before, m.decoder.linear_projection.bias)
+
+
+@pytest.mark.parametrize("name,B,T,seed,cap,bf16", [("infer_default_b2_t33_cap40", 2, 33, 2, 40, True),
+                                                    ("infer_default_b1_t50_cap25", 1, 50, 3, 25, True),
+                                                    ("infer_default_fp32_b2_t33_cap40", 2, 33, 2, 40, False)])
+def test_free_running_default_golden(name, B, T, seed, cap, bf16, capsys):
+    m = gpu_model(util.weights("default", bf16), "bf16" if bf16 else "fp32")
+    out = m.inference(synth.phoneme_ids(B, T, seed=seed).cuda(), max_len_cap=cap)
+    assert "Reached decode cap" in capsys.readouterr().out        # src/model.py:330
+    check(out, util.golden(name))
+
+
+def test_free_running_planted_stop_golden():
+    """Stop indices exact: batch-wide rule (F7), threshold override, cap, and the per-utterance rule vs solo runs."""
+    gold = util.golden("infer_planted_b5_t41")
+    ids = synth.phoneme_ids(5, 41, seed=7).cuda()
+    m = gpu_model(util.weights("planted", True, ctx_center=gold["ctx_center"]))
+    check(m.inference(ids), gold)
+    check(m.inference(ids, text_lengths=torch.full((5,), 20).cuda()), gold)          # F8: lengths ignored
+    check(m.inference(ids, gate_threshold=0.3), util.golden("infer_planted_b5_t41_thr0.3"))
+    check(m.inference(ids, max_len_cap=9), util.golden("infer_planted_b5_t41_cap9"))
+    post, coarse, gate, aligns, lengths = m.inference_per_utterance(ids)
+    assert lengths.tolist() == gold["solo_lengths"].tolist()
+    assert coarse.shape[1] == int(gold["solo_lengths"].max())
+    for b, n in enumerate(lengths.tolist()):
+        assert util.maxdiff(coarse[b, :n].cpu(), gold["solo_mel_coarse"][b, :n]) <= TOL_MEL
+
+
+# ------------------------------------------------------------------ oracle on the same seeded inputs
+@pytest.mark.parametrize("B,T", [(1, 1), (1, 200), (2, 17), (3, 257), (7, 64), (8, 150), (13, 40), (16, 150),
+                                 (32, 150), (33, 90), (64, 150), (64, 7)])
+def test_shape_sweep_free_running_vs_oracle(B, T):
+    """Every batch-tile specialisation (1,2,4,...,64) and slice count, stress weights (F12), 12 steps."""
+    sd = util.weights("stress", True)
+    ids = synth.phoneme_ids(B, T, seed=100 + B)
+    m = gpu_model(sd)
+    out = m.inference(ids.cuda(), max_len_cap=12)
+    with torch.no_grad():
+        ref = O.tacotron2_inference(sd, ids, max_len_cap=12)
+    gold = dict(mel_post=ref[0], mel_coarse=ref[1], gate=ref[2], align=util.stack(ref[3]))
+    check(out, gold, tol=5e-5, tol_align=5e-6)
+
+
+@pytest.mark.parametrize("B,T,S", [(1, 23, 9), (5, 77, 30), (32, 150, 20), (64, 33, 6)])
+def test_shape_sweep_teacher_forced_vs_oracle(B, T, S):
+    sd = util.weights("stress", True)
+    ids = synth.phoneme_ids(B, T, seed=B)
+    g = torch.Generator().manual_seed(B)
+    lengths = torch.randint(1, T + 1, (B,), generator=g)
+    lengths[0] = T
+    mel = synth.mel_targets(B, S, seed=B)
+    m = gpu_model(sd)
+    out = m(ids.cuda(), mel.cuda(), lengths.cuda())
+    with torch.no_grad():
+        ref = O.tacotron2_forward(sd, ids, mel, lengths)
+    gold = dict(mel_post=ref[0], mel_coarse=ref[1], gate=ref[2], align=util.stack(ref[3]))
+    check(out, gold, tol=5e-5, tol_align=5e-6)
+    al = util.stack(out[3]).cpu()
+    for b in range(B):
+        assert float(al[:, b, int(lengths[b]):].abs().max() if lengths[b] < T else 0.0) == 0.0   # masked positions
+
+
+def test_c2_full_size_stop_lengths_exact():
+    """BASELINE config 2 at full size: B=32, T=150, planted stop counter, cap 1000.
+
+    Per-utterance decoded lengths must equal the oracle's exactly; mel within tolerance up to
+    each utterance's own length.  Margins of the gate logit around the threshold are reported.
+    """
+    B, T = 32, 150
+    ids = synth.phoneme_ids(B, T, seed=0)
+    sd0 = util.weights("default")
+    with torch.no_grad():
+        center = O.encoder(sd0, ids).mean((0, 1))
+    sd = util.weights("default")
+    with torch.no_grad():
+        synth.plant_stop_counter_(sd, rate=2e-3, jitter=1.2e-2, ctx_center=center)
+        synth.round_to_bf16_(sd)
+        ref = O.tacotron2_inference(sd, ids, gate_threshold=2.0, max_len_cap=400)
+    ref_len = O.per_utterance_lengths(ref[2], 0.5)
+    assert int(ref_len.min()) >= 20 and len(set(ref_len.tolist())) > 4, ref_len.tolist()
+    m = gpu_model(sd)
+    post, coarse, gate, aligns, lengths = m.inference_per_utterance(ids.cuda(), max_len_cap=400)
+    idx = (ref_len - 1).clamp(max=ref[2].shape[1] - 1)
+    margin = ref[2].gather(1, idx[:, None]).abs().min()
+    print("ref lengths", ref_len.tolist(), "min |logit| at the firing step", float(margin))
+    assert lengths.tolist() == ref_len.tolist()
+    assert coarse.shape[1] == int(ref_len.max())
+    for b, n in enumerate(ref_len.tolist()):
+        assert util.maxdiff(coarse[b, :n].cpu(), ref[1][b, :n]) <= 5e-5
+    # batch-wide rule on the same weights: S = min over rows
+    out = m.inference(ids.cuda(), max_len_cap=400)
+    assert out[1].shape[1] == int(ref_len.min())
+
+
+def test_long_horizon_default_init_1000_steps():
+    """Default init never fires (F11): 1000 frames, error must not grow with the horizon."""
+    ids = synth.phoneme_ids(2, 150, seed=1)
+    sd = util.weights("default", True)
+    m = gpu_model(sd)
+    out = m.inference(ids.cuda())
+    with torch.no_grad():
+        ref = O.tacotron2_inference(sd, ids)
+    assert out[1].shape == ref[1].shape == (2, 1000, 80)
+    gold = dict(mel_post=ref[0], mel_coarse=ref[1], gate=ref[2], align=util.stack(ref[3]))
+    check(out, gold)
+
+
+# ------------------------------------------------------------------ behaviour at the boundary
+def test_repack_after_inplace_weight_update():
+    sd = util.weights("stress", True)
+    m = gpu_model(sd)
+    ids = synth.phoneme_ids(2, 21, seed=9).cuda()
+    a = m.inference(ids, max_len_cap=5)[1].clone()
+    with torch.no_grad():
+        m.decoder.linear_projection.bias.add_(1.0)         # like an optimizer step: bumps _version
+    b = m.inference(ids, max_len_cap=5)[1]
+    assert float((b[:, 0] - a[:, 0] - 1.0).abs().max()) < 1e-4
+
+
+def test_errors():
+    m = gpu_model(util.weights())
+    ids = synth.phoneme_ids(2, 9).cuda()
+    m.train()
+    with pytest.raises(B200TacoError):
+        m.inference(ids)
+    m.eval()
+    with pytest.raises(B200TacoError):
+        m.inference(synth.phoneme_ids(65, 9).cuda())       # beyond b200taco_max_batch
+    with pytest.raises(B200TacoError):
+        m.inference(synth.phoneme_ids(1, 2000).cuda())     # beyond b200taco_max_text_len
+    assert m._engine.launch_count() > 0
