@@ -12,7 +12,7 @@ import os
 import threading
 
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libb200taco.so")
+LIB_PATH = os.environ.get("B200TACO_LIB") or os.path.join(_PKG_ROOT, "lib", "libb200taco.so")
 
 ABI_VERSION = 1
 

@@ -105,6 +105,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 // Order generic-proxy accesses before subsequent async-proxy (TMA) accesses.
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Same, restricted to shared memory: a consumer's generic-proxy reads of a pipeline stage must
+// be ordered before the TMA engine's next write into that stage (write-after-read across proxies).
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
     uint32_t v;

@@ -28,7 +28,10 @@ namespace {
 constexpr int NW = 8;                       // consumer warps
 constexpr int NTC = NW * 32;                // consumer threads
 constexpr int NT = NTC + 32;                // + producer warp
-constexpr int STAGES = 4;
+#ifndef TACO_STAGES
+#define TACO_STAGES 4
+#endif
+constexpr int STAGES = TACO_STAGES;
 constexpr int TILE_POS = 40;                // encoder positions per attention tile (8 groups x 5)
 constexpr int MAX_NS = 16;                  // max slices per utterance
 constexpr int APART = 4 + EMB;              // per-slice partial: m, s, pad, pad, ctx[512]
@@ -195,6 +198,9 @@ __device__ __forceinline__ void gemm_consume(const Pipe& pipe, uint32_t& g, int 
     for (int ch = 0; ch < nchunks; ++ch, ++g) {
         const uint32_t stage = g % STAGES, parity = (g / STAGES) & 1u;
         mbar_wait(&pipe.full[stage], parity);
+#ifdef TACO_DBG_SLEEP
+        __nanosleep(TACO_DBG_SLEEP);
+#endif
         const WT* Ws = reinterpret_cast<const WT*>(pipe.stages + stage * SM::STAGE_BYTES);
         const float* As = reinterpret_cast<const float*>(pipe.stages + stage * SM::STAGE_BYTES + SM::W_BYTES);
 #pragma unroll
@@ -208,6 +214,9 @@ __device__ __forceinline__ void gemm_consume(const Pipe& pipe, uint32_t& g, int 
 #pragma unroll
                 for (int c = 0; c < TL::BPL; ++c) acc[r][c] = fmaf(w[r], a[c], acc[r][c]);
         }
+        // the loads above are generic-proxy reads; the refill of this stage is an async-proxy
+        // (TMA) write: without this fence the bulk copy can overtake loads still in flight
+        fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&pipe.empty[stage]);
     }
@@ -351,7 +360,11 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
     const WT* w_attn = reinterpret_cast<const WT*>(p.w_attn) + (size_t)cta * K_ATTN * ROWS_PER_CTA;
     const WT* w_dec = reinterpret_cast<const WT*>(p.w_dec) + (size_t)cta * K_DEC * ROWS_PER_CTA;
     constexpr int NCH1 = K_ATTN / TL::CK, NCH3 = K_DEC / TL::CK, PCH = PRENET / TL::CK;
+#ifdef TACO_NO_PREFETCH
+    constexpr int PRE1 = 0, PRE3 = 0;
+#else
     constexpr int PRE1 = NCH1 < STAGES ? NCH1 : STAGES, PRE3 = NCH3 < STAGES ? NCH3 : STAGES;
+#endif
     static_assert(PRENET % TL::CK == 0, "prenet rows must be whole chunks");
 
     uint32_t epoch = 0;

@@ -203,14 +203,21 @@ def test_long_horizon_default_init_1000_steps():
 
 # ------------------------------------------------------------------ behaviour at the boundary
 def test_repack_after_inplace_weight_update():
+    """An optimizer-style in-place update bumps param._version; the packed cache must follow."""
     sd = util.weights("stress", True)
     m = gpu_model(sd)
-    ids = synth.phoneme_ids(2, 21, seed=9).cuda()
-    a = m.inference(ids, max_len_cap=5)[1].clone()
+    ids, lengths, mel = synth.c1_batch()
+    args = (ids.cuda(), mel[:, :, :4].contiguous().cuda(), lengths.cuda())
+    a = m(*args)[1].clone()
     with torch.no_grad():
-        m.decoder.linear_projection.bias.add_(1.0)         # like an optimizer step: bumps _version
-    b = m.inference(ids, max_len_cap=5)[1]
-    assert float((b[:, 0] - a[:, 0] - 1.0).abs().max()) < 1e-4
+        m.decoder.linear_projection.bias.add_(1.0)
+    b = m(*args)[1]
+    # frame 0 is decoded from the zero go-frame: only the bias changed
+    assert float((b[:, 0] - a[:, 0] - 1.0).abs().max()) < 1e-5
+    with torch.no_grad():
+        m.decoder.decoder_lstm.weight_hh.zero_()
+    c = m(*args)[1]
+    assert float((c[:, 1] - b[:, 1]).abs().max()) > 1e-4
 
 
 def test_errors():
