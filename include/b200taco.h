@@ -188,6 +188,15 @@ B200TACO_API int32_t b200taco_postnet_fwd(b200taco_handle* h, const float* d_mel
  */
 B200TACO_API int32_t b200taco_measure_l2_read(void* d_buf, size_t bytes, int32_t iters, float* gbps, void* stream);
 
+/*
+ * Measurement aid: per-phase device time of the LAST decoder launch on this handle, measured
+ * by CTA 0 between grid barriers (globaltimer, ns, summed over decode steps):
+ *   out5[0..3] = attention LSTM, attention, decoder LSTM, projection+stop+prenet;
+ *   out5[4]    = decode steps executed.  Synchronises `stream`.  The workspace of that launch
+ * must still be alive.
+ */
+B200TACO_API int32_t b200taco_decoder_profile(b200taco_handle* h, int64_t* out5, void* stream);
+
 /* Number of kernels this library launched on this thread since the last reset. */
 B200TACO_API int64_t b200taco_launch_count(int32_t reset);
 

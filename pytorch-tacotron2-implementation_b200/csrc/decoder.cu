@@ -39,7 +39,8 @@ constexpr uint64_t SPIN_TIMEOUT_NS = 4000000000ull;
 
 // control words in scratch
 constexpr int CTRL_BARRIER = 0, CTRL_STOP = 1, CTRL_FINISHED = 2, CTRL_TICKETS = 32, CTRL_DONE = 32 + MAX_BATCH,
-              CTRL_LEN = 32 + 2 * MAX_BATCH, CTRL_WORDS = 32 + 3 * MAX_BATCH;
+              CTRL_LEN = 32 + 2 * MAX_BATCH, CTRL_PROF = 32 + 3 * MAX_BATCH /* 5 x u64 */,
+              CTRL_WORDS = CTRL_PROF + 16;
 
 struct KParams {
     int B, T, Tp, NS, SL, NQ, max_steps, mode, stop_mode;
@@ -374,6 +375,17 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
     int steps_done = 0;         // decode steps executed
     bool stopped = false;
 
+    // phase timers (CTA 0, thread 0): time from the end of one grid barrier to the end of the next
+    const bool timing = cta == 0 && tid == 0;
+    unsigned long long t_phase[4] = {0ull, 0ull, 0ull, 0ull}, t_last = timing ? global_timer_ns() : 0ull;
+    auto stamp = [&](int ph) {
+        if (timing) {
+            const unsigned long long now = global_timer_ns();
+            t_phase[ph] += now - t_last;
+            t_last = now;
+        }
+    };
+
     // producer: weight chunks of the very first phase
     if (is_producer && is_gemm && lane == 0) produce_w<BP, WT>(pipe, g, 0, PRE1, w_attn);
 
@@ -413,6 +425,7 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
             }
         }
         grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
+        stamp(0);
 
         // =============================== P2: attention ===============================
         if (!is_producer) {
@@ -602,6 +615,7 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
             }
         }
         grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
+        stamp(1);
 
         // =============================== P3: decoder LSTM ===============================
         if (is_gemm) {
@@ -661,6 +675,7 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
             }
         }
         grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
+        stamp(2);
 
         // =============================== P4: projection sums, stop rule, prenet ===============================
         if (!is_producer) {
@@ -747,6 +762,7 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
         steps_done = s + 1;
         if (!tf) {
             grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
+            stamp(3);
             if (__ldcg(p.ctrl + CTRL_STOP) != 0u) { stopped = true; break; }
         }
     }
@@ -761,6 +777,9 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
         }
     }
     if (cta == 0 && tid == 0) {
+        unsigned long long* prof = reinterpret_cast<unsigned long long*>(p.ctrl + CTRL_PROF);
+        for (int i = 0; i < 4; ++i) prof[i] = t_phase[i];
+        prof[4] = (unsigned long long)steps_done;
         const int S = tf ? p.max_steps : steps_done - 1;     // output frames (decode step 0 discarded)
         *p.steps_run = S;
         for (int b = 0; b < B; ++b) {
@@ -883,6 +902,7 @@ int decoder_run(const b200taco_handle* h, const DecoderArgs& a, cudaStream_t str
     kp.wtmp = reinterpret_cast<float*>(base + L.wtmp);
     kp.apart = reinterpret_cast<float*>(base + L.apart);
     kp.ctrl = reinterpret_cast<uint32_t*>(base + L.ctrl);
+    const_cast<b200taco_handle*>(h)->last_profile = reinterpret_cast<const unsigned long long*>(kp.ctrl + CTRL_PROF);
     if (h->weight_dtype == 1) return dispatch_bp<float>(BP, kp, ncta, stream);
     return dispatch_bp<__nv_bfloat16>(BP, kp, ncta, stream);
 }

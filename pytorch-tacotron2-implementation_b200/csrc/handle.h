@@ -8,6 +8,7 @@ struct b200taco_handle {
     int num_sms = 0;
     int weight_dtype = 0;           // 0 = bf16 LSTM matrices (default), 1 = fp32
     bool packed = false;
+    const unsigned long long* last_profile = nullptr;   // device: phase timers of the last decoder launch
 
     // one device allocation holding every packed tensor below
     void* arena = nullptr;
