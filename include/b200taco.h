@@ -191,11 +191,20 @@ B200TACO_API int32_t b200taco_measure_l2_read(void* d_buf, size_t bytes, int32_t
 /*
  * Measurement aid: per-phase device time of the LAST decoder launch on this handle, measured
  * by CTA 0 between grid barriers (globaltimer, ns, summed over decode steps):
- *   out5[0..3] = attention LSTM, attention, decoder LSTM, projection+stop+prenet;
- *   out5[4]    = decode steps executed.  Synchronises `stream`.  The workspace of that launch
- * must still be alive.
+ *   out[0..3] = attention LSTM, attention, decoder LSTM, projection+stop+prenet;
+ *   out[4]    = decode steps executed; out[5..20] = sub-phase timers, zero unless the library
+ * was built with -DTACO_PROFILE_FINE.  5 <= n <= 21.  Synchronises `stream`.  The workspace of
+ * that launch must still be alive.
  */
-B200TACO_API int32_t b200taco_decoder_profile(b200taco_handle* h, int64_t* out5, void* stream);
+B200TACO_API int32_t b200taco_decoder_profile(b200taco_handle* h, int64_t* out, int32_t n, void* stream);
+
+/*
+ * Unit-test aid for the tcgen05 path: D[128][32] (fp32) = A[128][K] . B[32][K]^T with bf16
+ * operands (row-major device arrays), one CTA, accumulators in TMEM.  K a multiple of 64.
+ * variant 0 is the production descriptor convention; other values are bring-up experiments.
+ */
+B200TACO_API int32_t b200taco_debug_umma_gemm(const void* d_A, const void* d_B, float* d_D, int32_t K,
+                                              int32_t variant, void* stream);
 
 /* Number of kernels this library launched on this thread since the last reset. */
 B200TACO_API int64_t b200taco_launch_count(int32_t reset);

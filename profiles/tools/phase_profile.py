@@ -36,7 +36,8 @@ def main():
             prof = eng.decoder_profile()
             tot = e0.elapsed_time(e1) * 1e3 / prof["steps"]
             print(json.dumps({"wdt": wdt, "B": B, "T": T, "steps": prof["steps"], "us_per_step_total": round(tot, 2),
-                              "phases_us": {k: round(v, 2) for k, v in prof["us_per_step"].items()}}))
+                              "phases_us": {k: round(v, 2) for k, v in prof["us_per_step"].items()},
+                              **({"fine": prof["fine_us_per_step"]} if "fine_us_per_step" in prof else {})}))
 
 
 if __name__ == "__main__":

@@ -79,7 +79,8 @@ SIGNATURES = {
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200taco_measure_l2_read": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_int32,
                                              C.POINTER(C.c_float), C.c_void_p]),
-    "b200taco_decoder_profile": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
+    "b200taco_decoder_profile": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_void_p]),
+    "b200taco_debug_umma_gemm": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "b200taco_launch_count": (C.c_int64, [C.c_int32]),
 }
 

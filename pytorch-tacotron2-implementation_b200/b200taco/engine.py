@@ -198,12 +198,15 @@ class Engine:
 
     def decoder_profile(self) -> dict:
         """Phase timers of the last decoder launch (ns summed over steps) and the step count."""
-        out = (C.c_int64 * 5)()
+        out = (C.c_int64 * 21)()
         with torch.cuda.device(self.device):
-            check(self._lib.b200taco_decoder_profile(self._h, out, self._stream()), "b200taco_decoder_profile")
+            check(self._lib.b200taco_decoder_profile(self._h, out, 21, self._stream()), "b200taco_decoder_profile")
         names = ("attention_lstm", "attention", "decoder_lstm", "projection_prenet")
         steps = max(1, int(out[4]))
-        return {"steps": int(out[4]), "us_per_step": {n: out[i] / steps / 1e3 for i, n in enumerate(names)}}
+        prof = {"steps": int(out[4]), "us_per_step": {n: out[i] / steps / 1e3 for i, n in enumerate(names)}}
+        if any(out[5:]):
+            prof["fine_us_per_step"] = [round(out[i] / steps / 1e3, 2) for i in range(5, 21)]
+        return prof
 
     def launch_count(self, reset: bool = False) -> int:
         return int(self._lib.b200taco_launch_count(1 if reset else 0))

@@ -312,12 +312,12 @@ B200TACO_API int32_t b200taco_measure_l2_read(void* d_buf, size_t bytes, int32_t
     return measure_l2_read(d_buf, bytes, iters, gbps, static_cast<cudaStream_t>(stream));
 }
 
-B200TACO_API int32_t b200taco_decoder_profile(b200taco_handle* h, int64_t* out5, void* stream) {
+B200TACO_API int32_t b200taco_decoder_profile(b200taco_handle* h, int64_t* out, int32_t n, void* stream) {
     TACO_TRY(check_handle(h, false));
-    TACO_REQUIRE(out5 != nullptr, B200TACO_ERR_INVALID, "decoder_profile: null output");
+    TACO_REQUIRE(out != nullptr && n >= 5 && n <= 21, B200TACO_ERR_INVALID, "decoder_profile: bad output (n=%d)", n);
     TACO_REQUIRE(h->last_profile != nullptr, B200TACO_ERR_STATE, "decoder_profile: no decoder launch yet");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    TACO_CUDA(cudaMemcpyAsync(out5, h->last_profile, 5 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    TACO_CUDA(cudaMemcpyAsync(out, h->last_profile, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     TACO_CUDA(cudaStreamSynchronize(st));
     return B200TACO_OK;
 }

@@ -40,7 +40,7 @@ constexpr uint64_t SPIN_TIMEOUT_NS = 4000000000ull;
 // control words in scratch
 constexpr int CTRL_BARRIER = 0, CTRL_STOP = 1, CTRL_FINISHED = 2, CTRL_TICKETS = 32, CTRL_DONE = 32 + MAX_BATCH,
               CTRL_LEN = 32 + 2 * MAX_BATCH, CTRL_PROF = 32 + 3 * MAX_BATCH /* 5 x u64 */,
-              CTRL_WORDS = CTRL_PROF + 16;
+              CTRL_WORDS = CTRL_PROF + 48;
 
 struct KParams {
     int B, T, Tp, NS, SL, NQ, max_steps, mode, stop_mode;
@@ -113,6 +113,14 @@ static_assert(P2Scratch::TOTAL * 4 <= 72 * 1024, "P2 scratch must fit the red re
 
 __device__ __forceinline__ void spin_fail() { __trap(); }
 
+#ifdef TACO_PROFILE_FINE
+#define FT_RESET() do { if (timing) t_flast = global_timer_ns(); } while (0)
+#define FT(n) do { if (timing) { const unsigned long long _n = global_timer_ns(); t_fine[n] += _n - t_flast; t_flast = _n; } } while (0)
+#else
+#define FT_RESET()
+#define FT(n)
+#endif
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     uint64_t t0 = global_timer_ns();
@@ -122,12 +130,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // All NT threads of every CTA call this the same number of times.
+// Ordering: every thread's writes happen-before thread 0's red.release (bar.sync + cumulativity);
+// thread 0's ld.acquire happens-before every thread's later reads (second bar.sync).
 __device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t& epoch, uint32_t ncta) {
     __syncthreads();
     epoch += 1;
     if (threadIdx.x == 0) {
-        __threadfence();
-        fence_proxy_async();
+        fence_proxy_async();                       // generic writes -> visible to other CTAs' TMA reads
         red_release_add_u32(counter, 1u);
         const uint32_t target = epoch * ncta;
         if (ld_acquire_u32(counter) < target) {
@@ -136,9 +145,34 @@ __device__ __forceinline__ void grid_barrier(uint32_t* counter, uint32_t& epoch,
                 if (global_timer_ns() - t0 > SPIN_TIMEOUT_NS) spin_fail();
             }
         }
-        __threadfence();
     }
     __syncthreads();
+}
+
+// sum of N values spaced `stride` floats apart, 16 loads in flight (L2 latency bound otherwise)
+template <int N, int BATCH = 32>
+__device__ __forceinline__ float strided_sum_cg(const float* src, int stride) {
+    static_assert(N % BATCH == 0 && BATCH % 4 == 0, "N");
+    float total = 0.f;
+#pragma unroll 1
+    for (int i0 = 0; i0 < N; i0 += BATCH) {
+        float v[BATCH];
+#pragma unroll
+        for (int i = 0; i < BATCH; ++i) v[i] = __ldcg(src + (size_t)(i0 + i) * stride);
+#pragma unroll
+        for (int i = 0; i < BATCH; i += 4) total += (v[i] + v[i + 1]) + (v[i + 2] + v[i + 3]);
+    }
+    return total;
+}
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ uint32_t atom_add_acq_rel_gpu(uint32_t* p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
 }
 
 __device__ __forceinline__ void consumer_sync() { named_bar_sync(1, NTC); }
@@ -353,6 +387,13 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
         for (int i = tid; i < 128 * 8; i += NT) wq_s[i] = p.wq_slices[(size_t)cta * 1024 + i];
         for (int i = tid; i < PROJ_OUT * 8; i += NT) wproj_s[i] = p.wproj_slices[(size_t)cta * PROJ_OUT * 8 + i];
     }
+    if (!is_gemm) {
+        const int nspare = ncta - GEMM_CTAS, sidx = cta - GEMM_CTAS;
+        const int rows_per = (PROJ_OUT + nspare - 1) / nspare;
+        const int o0 = sidx * rows_per, nrow = max(0, min(PROJ_OUT, o0 + rows_per) - o0);
+        float* wsm = reinterpret_cast<float*>(pipe.stages);
+        for (int i = tid; i < nrow * EMB; i += NT) wsm[i] = p.wproj_ctxT[(size_t)(i % EMB) * PROJ_PAD + o0 + i / EMB];
+    }
     for (int i = tid; i < LOC_F * 2 * LOC_K; i += NT) wloc_s[(i / 62) * 63 + (i % 62)] = p.loc_conv[i];
     for (int i = tid; i < LOC_F * ATT_DIM; i += NT) wld_s[i] = p.loc_denseT[i];
     for (int i = tid; i < 130; i += NT) v_s[i] = p.attn_v[i];
@@ -378,6 +419,9 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
     // phase timers (CTA 0, thread 0): time from the end of one grid barrier to the end of the next
     const bool timing = cta == 0 && tid == 0;
     unsigned long long t_phase[4] = {0ull, 0ull, 0ull, 0ull}, t_last = timing ? global_timer_ns() : 0ull;
+#ifdef TACO_PROFILE_FINE
+    unsigned long long t_fine[16] = {}, t_flast = 0ull;
+#endif
     auto stamp = [&](int ph) {
         if (timing) {
             const unsigned long long now = global_timer_ns();
@@ -435,27 +479,21 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
             const float* cum_in = p.attn_cum + (size_t)prv * B * p.Tp;
             float* prev_out = p.attn_prev + (size_t)cur * B * p.Tp;
             float* cum_out = p.attn_cum + (size_t)cur * B * p.Tp;
+            FT_RESET();
             for (int item = cta; item < B * NS; item += ncta) {
                 const int b = item / NS, sl = item % NS;
                 const int t0 = sl * SL, t1 = min(T, t0 + SL), n = max(0, t1 - t0);
                 const int len = p.text_lengths ? (int)p.text_lengths[b] : T;
                 consumer_sync();   // previous item's scratch is free
-                // processed query = sum of the 128 per-CTA partials
-                {
-                    const int a = tid & 127, hf = tid >> 7;
-                    const float* src = p.pqpart + ((size_t)b * GEMM_CTAS + hf * 64) * ATT_DIM + a;
-                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll 4
-                    for (int i = 0; i < 64; i += 4) {
-                        s0 += __ldcg(src + (i + 0) * ATT_DIM);
-                        s1 += __ldcg(src + (i + 1) * ATT_DIM);
-                        s2 += __ldcg(src + (i + 2) * ATT_DIM);
-                        s3 += __ldcg(src + (i + 3) * ATT_DIM);
-                    }
-                    sc[P2Scratch::PQ + tid] = (s0 + s1) + (s2 + s3);
-                }
-                // previous / cumulative attention windows with a 15-position halo, zero padded
                 const int ntiles = (n + TILE_POS - 1) / TILE_POS;
+                // processed-memory tile 0: asynchronous copy, overlapped with the loads below
+                auto issue_pm_tile = [&](int tb) {
+                    const int rows = min(TILE_POS, n - tb);
+                    const float* src = p.pm + ((size_t)b * T + t0 + tb) * ATT_DIM;
+                    for (int i = tid; i < rows * (ATT_DIM / 4); i += NTC) cp_async16(sc + P2Scratch::PM + i * 4, src + i * 4);
+                };
+                issue_pm_tile(0);
+                // previous / cumulative attention windows with a 15-position halo, zero padded
                 const int wlen = ntiles * TILE_POS + LOC_K - 1 + 4;
                 for (int i = tid; i < wlen; i += NTC) {
                     const int t = t0 - (LOC_K - 1) / 2 + i;
@@ -463,7 +501,14 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                     sc[P2Scratch::WIN + i] = ok ? __ldcg(prev_in + (size_t)b * p.Tp + t) : 0.f;
                     sc[P2Scratch::WIN + P2Scratch::WIN_LEN + i] = ok ? __ldcg(cum_in + (size_t)b * p.Tp + t) : 0.f;
                 }
+                // processed query = sum of the 128 per-CTA partials
+                {
+                    const int a = tid & 127, hf = tid >> 7;
+                    const float* src = p.pqpart + ((size_t)b * GEMM_CTAS + hf * 64) * ATT_DIM + a;
+                    sc[P2Scratch::PQ + tid] = strided_sum_cg<64, 32>(src, ATT_DIM);
+                }
                 consumer_sync();
+                FT(1);
                 float wld[LOC_F];
                 {
                     const int a = tid & 127;
@@ -494,35 +539,41 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
 #pragma unroll
                         for (int j = 0; j < 5; ++j) sc[P2Scratch::LOC + (tg * 5 + j) * 33 + f] = o5[j];
                     }
-                    // ---- processed-memory tile
-                    for (int i = tid; i < TILE_POS * ATT_DIM; i += NTC) {
-                        const int pl = i / ATT_DIM, a = i % ATT_DIM, t = t0 + tb + pl;
-                        sc[P2Scratch::PM + i] = t < t1 ? __ldg(p.pm + ((size_t)b * T + t) * ATT_DIM + a) : 0.f;
-                    }
+                    if (tile > 0) issue_pm_tile(tb);
+                    cp_async_wait_all();
                     consumer_sync();
-                    // ---- energies (src/model.py:127-130): v . tanh(pq + pm + Wld loc)
+                FT(2);
+                    // ---- energies (src/model.py:127-130): v . tanh(pq + pm + Wld loc); four positions
+                    // per thread at a time (independent FMA chains), result overwrites the pm tile
+                    const int npl = min(TILE_POS, n - tb);
                     {
-                        const int a = tid & 127, hf = tid >> 7, wq4 = (tid >> 5) & 3;
-                        for (int pl = hf * (TILE_POS / 2); pl < (hf + 1) * (TILE_POS / 2); ++pl) {
-                            float x = pq + sc[P2Scratch::PM + pl * ATT_DIM + a];
-                            const float* l = sc + P2Scratch::LOC + pl * 33;
+                        const int a = tid & 127, hf = tid >> 7;
+                        for (int pl0 = hf * 4; pl0 < npl; pl0 += 8) {
+                            float x[4];
 #pragma unroll
-                            for (int f = 0; f < LOC_F; ++f) x = fmaf(wld[f], l[f], x);
-                            const float e = warp_sum(vw * tanh_fast(x));
-                            if (lane == 0) sc[P2Scratch::EPART + pl * 4 + wq4] = e;
+                            for (int j = 0; j < 4; ++j) x[j] = pq + sc[P2Scratch::PM + (pl0 + j) * ATT_DIM + a];
+#pragma unroll
+                            for (int f = 0; f < LOC_F; ++f) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) x[j] = fmaf(wld[f], sc[P2Scratch::LOC + (pl0 + j) * 33 + f], x[j]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) sc[P2Scratch::PM + (pl0 + j) * ATT_DIM + a] = vw * tanh_fast(x[j]);
                         }
                     }
                     consumer_sync();
-                    if (tid < TILE_POS) {
-                        const float* ep = sc + P2Scratch::EPART + tid * 4;
-                        float e = ((ep[0] + ep[1]) + (ep[2] + ep[3]) + v_s[128]) * v_s[129];
-                        const int t = t0 + tb + tid;
-                        if (t >= len) e = -1e9f;                       // masked_fill, src/model.py:132
-                        sc[P2Scratch::E + tb + tid] = e;
+                FT(3);
+                    for (int pl = warp; pl < npl; pl += NW) {
+                        const float* row = sc + P2Scratch::PM + pl * ATT_DIM;
+                        float e = warp_sum((row[lane] + row[lane + 32]) + (row[lane + 64] + row[lane + 96]));
+                        if (lane == 0) {
+                            e = (e + v_s[128]) * v_s[129];
+                            if (t0 + tb + pl >= len) e = -1e9f;               // masked_fill, src/model.py:132
+                            sc[P2Scratch::E + tb + pl] = e;
+                        }
                     }
-                    // next tile's writes to LOC/PM happen after the sync at its own mid-point;
-                    // EPART is rewritten only after that sync, E is disjoint per tile.
                     consumer_sync();
+                FT(4);
                 }
                 // ---- slice-local softmax statistics (warp 0) ----
                 if (warp == 0) {
@@ -542,6 +593,7 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                     }
                 }
                 consumer_sync();
+                FT(5);
                 // ---- slice-local un-normalised context: sum_t ew[t] * memory[b][t][:] ----
                 float2 cacc = make_float2(0.f, 0.f);
                 {
@@ -559,14 +611,14 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                     reinterpret_cast<float2*>(part + 4)[tid] = cacc;
                     if (tid == 0) { part[0] = sc[P2Scratch::SC + 32]; part[1] = sc[P2Scratch::SC + 33]; }
                     for (int i = tid; i < n; i += NTC) p.wtmp[(size_t)b * p.Tp + t0 + i] = sc[P2Scratch::E + i];
-                    __threadfence();
                     consumer_sync();
                     if (tid == 0) {
-                        const uint32_t ticket = atomicAdd(p.ctrl + CTRL_TICKETS + b, 1u);
+                        // release: this CTA's partials (ordered by the bar.sync above); acquire: the others'
+                        const uint32_t ticket = atom_add_acq_rel_gpu(p.ctrl + CTRL_TICKETS + b, 1u);
                         misc_s[0] = (ticket % (uint32_t)NS) == (uint32_t)(NS - 1);
-                        __threadfence();
                     }
                     consumer_sync();
+                FT(6);
                     if (!misc_s[0]) continue;
                     // last slice of this utterance: merge
                     if (tid < 32) {
@@ -583,13 +635,21 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                         if (tid == 0) sc[P2Scratch::SC + 33] = ssum;
                     }
                     consumer_sync();
+                FT(7);
                     cacc = make_float2(0.f, 0.f);
-                    for (int q = 0; q < NS; ++q) {
-                        const float2 cv =
-                            __ldcg(reinterpret_cast<const float2*>(p.apart + ((size_t)b * MAX_NS + q) * APART + 4) + tid);
-                        const float scale = sc[P2Scratch::SC + q];
-                        cacc.x = fmaf(scale, cv.x, cacc.x);
-                        cacc.y = fmaf(scale, cv.y, cacc.y);
+                    {
+                        float2 cv[MAX_NS];
+#pragma unroll
+                        for (int q = 0; q < MAX_NS; ++q)
+                            cv[q] = q < NS ? __ldcg(reinterpret_cast<const float2*>(
+                                                        p.apart + ((size_t)b * MAX_NS + q) * APART + 4) + tid)
+                                           : make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int q = 0; q < MAX_NS; ++q) {
+                            const float scale = q < NS ? sc[P2Scratch::SC + q] : 0.f;
+                            cacc.x = fmaf(scale, cv[q].x, cacc.x);
+                            cacc.y = fmaf(scale, cv[q].y, cacc.y);
+                        }
                     }
                 } else {
                     if (tid == 0) sc[P2Scratch::SC + 0] = 1.f;
@@ -612,6 +672,7 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                     cum_out[(size_t)b * p.Tp + t] = __ldcg(cum_in + (size_t)b * p.Tp + t) + w;
                     if (out_idx >= 0) p.align[((size_t)out_idx * B + b) * T + t] = w;
                 }
+                FT(8);
             }
         }
         grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
@@ -648,30 +709,29 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                 }
             }
         } else if (!is_producer) {
-            // spare CTAs: context part of the projections + bias: melctx[b][o]
-            float* sc = red;
-            const int nspare = ncta - GEMM_CTAS;
-            for (int b = cta - GEMM_CTAS; b < B; b += nspare) {
-                consumer_sync();
-                for (int i = tid; i < EMB; i += NTC) sc[i] = __ldcg(p.ctx_bj + (size_t)b * EMB + i);
-                consumer_sync();
-                const int o = tid % PROJ_PAD, jg = tid / PROJ_PAD;       // 96 x 2 groups (+64 idle threads)
-                if (jg < 2) {
-                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                    const float* wsrc = p.wproj_ctxT + (size_t)(jg * 256) * PROJ_PAD + o;
-                    const float* cs = sc + jg * 256;
-#pragma unroll 4
-                    for (int j = 0; j < 256; j += 4) {
-                        s0 = fmaf(__ldg(wsrc + (size_t)(j + 0) * PROJ_PAD), cs[j + 0], s0);
-                        s1 = fmaf(__ldg(wsrc + (size_t)(j + 1) * PROJ_PAD), cs[j + 1], s1);
-                        s2 = fmaf(__ldg(wsrc + (size_t)(j + 2) * PROJ_PAD), cs[j + 2], s2);
-                        s3 = fmaf(__ldg(wsrc + (size_t)(j + 3) * PROJ_PAD), cs[j + 3], s3);
+            // spare CTAs: context part of the projections + bias: melctx[b][o] for this CTA's rows o
+            // (weights cached in shared memory at kernel start); one warp per utterance at a time.
+            const int nspare = ncta - GEMM_CTAS, sidx = cta - GEMM_CTAS;
+            const int rows_per = (PROJ_OUT + nspare - 1) / nspare;            // <= SPARE_ROWS
+            const int o0 = sidx * rows_per, nrow = max(0, min(PROJ_OUT, o0 + rows_per) - o0);
+            const float* wsm = reinterpret_cast<const float*>(pipe.stages);  // [SPARE_ROWS][512], stage area is unused here
+            for (int b = warp; b < B && nrow > 0; b += NW) {
+                float4 c4[4];
+                const float4* csrc = reinterpret_cast<const float4*>(p.ctx_bj + (size_t)b * EMB) + lane * 4;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) c4[i] = __ldcg(csrc + i);
+                for (int r = 0; r < nrow; ++r) {
+                    const float4* w4 = reinterpret_cast<const float4*>(wsm + r * EMB) + lane * 4;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 w = w4[i];
+                        acc = fmaf(w.x, c4[i].x, acc); acc = fmaf(w.y, c4[i].y, acc);
+                        acc = fmaf(w.z, c4[i].z, acc); acc = fmaf(w.w, c4[i].w, acc);
                     }
-                    sc[EMB + jg * PROJ_PAD + o] = (s0 + s1) + (s2 + s3);
+                    acc = warp_sum(acc);
+                    if (lane == 0) p.melctx[(size_t)b * PROJ_PAD + o0 + r] = acc + __ldg(p.proj_bias + o0 + r);
                 }
-                consumer_sync();
-                if (tid < PROJ_PAD)
-                    p.melctx[(size_t)b * PROJ_PAD + tid] = sc[EMB + tid] + sc[EMB + PROJ_PAD + tid] + __ldg(p.proj_bias + tid);
             }
         }
         grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
@@ -688,15 +748,7 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                     const int o = tid & 127, ig = tid >> 7;
                     if (o < PROJ_OUT) {
                         const float* src = p.melpart + ((size_t)b * GEMM_CTAS + ig * 64) * PROJ_PAD + o;
-                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll 4
-                        for (int i = 0; i < 64; i += 4) {
-                            s0 += __ldcg(src + (i + 0) * PROJ_PAD);
-                            s1 += __ldcg(src + (i + 1) * PROJ_PAD);
-                            s2 += __ldcg(src + (i + 2) * PROJ_PAD);
-                            s3 += __ldcg(src + (i + 3) * PROJ_PAD);
-                        }
-                        sc[ig * 128 + o] = (s0 + s1) + (s2 + s3);
+                        sc[ig * 128 + o] = strided_sum_cg<64>(src, PROJ_PAD);
                     }
                 }
                 consumer_sync();
@@ -726,14 +778,17 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                 consumer_sync();
                 // prenet layer 1 (all 256 outputs in every quarter CTA), eval mode: no dropout (F4)
                 {
-                    float s0 = 0.f, s1 = 0.f;
                     const float* wsrc = p.prenet1T + tid;
-#pragma unroll 8
-                    for (int o = 0; o < N_MELS; o += 2) {
-                        s0 = fmaf(__ldg(wsrc + (size_t)o * PRENET), sc[256 + o], s0);
-                        s1 = fmaf(__ldg(wsrc + (size_t)(o + 1) * PRENET), sc[256 + o + 1], s1);
+                    float acc = 0.f;
+#pragma unroll 1
+                    for (int o0 = 0; o0 < N_MELS; o0 += 16) {
+                        float w[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) w[i] = __ldg(wsrc + (size_t)(o0 + i) * PRENET);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) acc = fmaf(w[i], sc[256 + o0 + i], acc);
                     }
-                    sc[384 + tid] = fmaxf(s0 + s1, 0.f);
+                    sc[384 + tid] = fmaxf(acc, 0.f);
                 }
                 consumer_sync();
                 // prenet layer 2: this CTA's RQ outputs, k split over NQ thread groups
@@ -741,15 +796,16 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                     const int nl = tid % RQ, kg = tid / RQ, kn = PRENET / NQ;
                     const float* wsrc = p.prenet2T + (size_t)(kg * kn) * PRENET + q * RQ + nl;
                     const float* x = sc + 384 + kg * kn;
-                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll 4
-                    for (int m = 0; m < kn; m += 4) {
-                        s0 = fmaf(__ldg(wsrc + (size_t)(m + 0) * PRENET), x[m + 0], s0);
-                        s1 = fmaf(__ldg(wsrc + (size_t)(m + 1) * PRENET), x[m + 1], s1);
-                        s2 = fmaf(__ldg(wsrc + (size_t)(m + 2) * PRENET), x[m + 2], s2);
-                        s3 = fmaf(__ldg(wsrc + (size_t)(m + 3) * PRENET), x[m + 3], s3);
+                    float acc = 0.f;
+#pragma unroll 1
+                    for (int m0 = 0; m0 < kn; m0 += 16) {
+                        float w[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) w[i] = __ldg(wsrc + (size_t)(m0 + i) * PRENET);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) acc = fmaf(w[i], x[m0 + i], acc);
                     }
-                    sc[640 + kg * RQ + nl] = (s0 + s1) + (s2 + s3);
+                    sc[640 + kg * RQ + nl] = acc;
                 }
                 consumer_sync();
                 if (tid < RQ) {
@@ -780,6 +836,9 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
         unsigned long long* prof = reinterpret_cast<unsigned long long*>(p.ctrl + CTRL_PROF);
         for (int i = 0; i < 4; ++i) prof[i] = t_phase[i];
         prof[4] = (unsigned long long)steps_done;
+#ifdef TACO_PROFILE_FINE
+        for (int i = 0; i < 16; ++i) prof[5 + i] = t_fine[i];
+#endif
         const int S = tf ? p.max_steps : steps_done - 1;     // output frames (decode step 0 discarded)
         *p.steps_run = S;
         for (int b = 0; b < B; ++b) {
