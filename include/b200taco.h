@@ -129,6 +129,16 @@ B200TACO_API int32_t b200taco_destroy(b200taco_handle* h);
 B200TACO_API int32_t b200taco_set_weight_dtype(b200taco_handle* h, int32_t dtype);
 
 /*
+ * Kernel selection for the LSTM gate contractions of the decoder.  AUTO (default): tcgen05 tensor-core
+ * tiles (bf16 operands, hi/lo split activations, fp32 accumulators in TMEM) when the batch is large
+ * enough to be a real GEMM (B >= 17) and the weights are stored bf16; the vectorised fp32 SIMT
+ * contraction otherwise.  SIMT forces the latter (A/B measurements, bit-for-bit fp32 activations).
+ */
+#define B200TACO_PATH_AUTO 0
+#define B200TACO_PATH_SIMT 1
+B200TACO_API int32_t b200taco_set_decoder_path(b200taco_handle* h, int32_t path);
+
+/*
  * Repack the fp32 parameters into the kernels' layouts (bf16 fragment order for the
  * two decoder LSTMs, hi/lo bf16 planes for the GEMM operands, folded BatchNorm).  Call
  * after load_state_dict / optimizer.step (the host tracks param._version).
@@ -187,6 +197,22 @@ B200TACO_API int32_t b200taco_postnet_fwd(b200taco_handle* h, const float* d_mel
  * that fits in L2; returns GB/s through *gbps.  d_buf must hold `bytes` bytes.
  */
 B200TACO_API int32_t b200taco_measure_l2_read(void* d_buf, size_t bytes, int32_t iters, float* gbps, void* stream);
+
+/*
+ * Measurement aid: per-SM L2 streaming rate.  `ctas` CTAs each re-read their own `per_cta` bytes of d_buf
+ * (ctas * per_cta bytes, L2 resident) `iters` times.  mode 0 = LDG.128 with 8 loads in flight per thread;
+ * mode 1 = TMA bulk copies of `chunk` bytes, `depth` in flight (the decoder's pipeline pattern).
+ * Returns GB/s per CTA (= per SM).
+ */
+B200TACO_API int32_t b200taco_measure_stream(void* d_buf, size_t per_cta, int32_t ctas, int32_t iters, int32_t mode,
+                                             int32_t chunk, int32_t depth, float* gbps_per_sm, void* stream);
+
+/*
+ * Measurement aid: SM cycles per operation (one thread, each preceded by a global store) of
+ * out8[0..7] = fence.proxy.async, fence.proxy.async.global, fence.proxy.async.shared::cta, __threadfence,
+ * red.release.gpu, ld.acquire.gpu, atomicAdd (returning), plain store.
+ */
+B200TACO_API int32_t b200taco_measure_sync_costs(int64_t* out8, void* stream);
 
 /*
  * Measurement aid: per-phase device time of the LAST decoder launch on this handle, measured

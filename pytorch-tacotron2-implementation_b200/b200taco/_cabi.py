@@ -62,6 +62,7 @@ SIGNATURES = {
     "b200taco_create": (C.c_int32, [C.POINTER(HParams), C.c_int32, C.POINTER(C.c_void_p)]),
     "b200taco_destroy": (C.c_int32, [C.c_void_p]),
     "b200taco_set_weight_dtype": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "b200taco_set_decoder_path": (C.c_int32, [C.c_void_p, C.c_int32]),
     "b200taco_pack_weights": (C.c_int32, [C.c_void_p, C.POINTER(Weights), C.c_void_p]),
     "b200taco_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     "b200taco_encoder_fwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
@@ -79,6 +80,9 @@ SIGNATURES = {
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200taco_measure_l2_read": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_int32,
                                              C.POINTER(C.c_float), C.c_void_p]),
+    "b200taco_measure_stream": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                            C.POINTER(C.c_float), C.c_void_p]),
+    "b200taco_measure_sync_costs": (C.c_int32, [C.POINTER(C.c_int64), C.c_void_p]),
     "b200taco_decoder_profile": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_void_p]),
     "b200taco_debug_umma_gemm": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "b200taco_launch_count": (C.c_int64, [C.c_int32]),

@@ -63,7 +63,7 @@ def _hparams() -> _cabi.HParams:
 class Engine:
     """One per model instance per device; not thread-safe."""
 
-    def __init__(self, device: torch.device, weight_dtype: str = "bf16"):
+    def __init__(self, device: torch.device, weight_dtype: str = "bf16", decoder_path: str = "auto"):
         if weight_dtype not in WEIGHT_DTYPES:
             raise B200TacoError(f"weight_dtype must be one of {sorted(WEIGHT_DTYPES)}, got {weight_dtype!r}")
         if device.type != "cuda":
@@ -76,6 +76,9 @@ class Engine:
         check(self._lib.b200taco_create(C.byref(hp), device.index if device.index is not None else torch.cuda.current_device(), C.byref(self._h)), "b200taco_create")
         self.weight_dtype = weight_dtype
         check(self._lib.b200taco_set_weight_dtype(self._h, WEIGHT_DTYPES[weight_dtype]), "b200taco_set_weight_dtype")
+        self.decoder_path = decoder_path
+        check(self._lib.b200taco_set_decoder_path(self._h, {"auto": 0, "simt": 1}[decoder_path]),
+              "b200taco_set_decoder_path")
         self._packed_sig = None
         self._ws = None
         self.max_batch = self._lib.b200taco_max_batch()

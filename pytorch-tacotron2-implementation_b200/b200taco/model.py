@@ -113,6 +113,8 @@ class Tacotron2(nn.Module):
         # storage of the decoder LSTM matrices in the packed cache: "bf16" (default, half the
         # L2 traffic per step) or "fp32" (the reference's values bit for bit)
         self.lstm_weight_dtype = "bf16"
+        # "auto": tcgen05 tensor-core gate contractions when B >= 17 and bf16 weights; "simt": never
+        self.decoder_path = "auto"
 
     # ------------------------------------------------------------------ plumbing
     def _tensors(self) -> dict:
@@ -123,8 +125,9 @@ class Tacotron2(nn.Module):
     def _get_engine(self) -> Engine:
         dev = self.decoder.gate_layer.weight.device
         if (self._engine is None or self._engine.device != dev
-                or self._engine.weight_dtype != self.lstm_weight_dtype):
-            self._engine = Engine(dev, self.lstm_weight_dtype)
+                or self._engine.weight_dtype != self.lstm_weight_dtype
+                or self._engine.decoder_path != self.decoder_path):
+            self._engine = Engine(dev, self.lstm_weight_dtype, self.decoder_path)
         self._engine.ensure_packed(self._tensors())
         return self._engine
 

@@ -32,15 +32,6 @@ __global__ void tf_frames_kernel(const float* __restrict__ targets, float* __res
         X[i] = s == 0 ? 0.f : targets[((size_t)b * N_MELS + o) * S + (s - 1)];
     }
 }
-// prenet outputs [s*B + b][256] -> the decoder's act layout p_all[s][k][BP]
-__global__ void p_all_pack_kernel(const float* __restrict__ Y, float* __restrict__ P, int B, int BP, int S) {
-    const size_t total = (size_t)S * PRENET * BP;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int b = i % BP, k = (i / BP) % PRENET, s = i / ((size_t)BP * PRENET);
-        P[i] = b < B ? Y[((size_t)s * B + b) * PRENET + k] : 0.f;
-    }
-}
-
 struct Carver {
     uint8_t* base;
     size_t off = 0;
@@ -174,6 +165,13 @@ B200TACO_API int32_t b200taco_set_weight_dtype(b200taco_handle* h, int32_t dtype
     return B200TACO_OK;
 }
 
+B200TACO_API int32_t b200taco_set_decoder_path(b200taco_handle* h, int32_t path) {
+    TACO_REQUIRE(h != nullptr, B200TACO_ERR_INVALID, "null handle");
+    TACO_REQUIRE(path == B200TACO_PATH_AUTO || path == B200TACO_PATH_SIMT, B200TACO_ERR_INVALID, "unknown decoder path %d", path);
+    h->decoder_path = path;
+    return B200TACO_OK;
+}
+
 B200TACO_API int32_t b200taco_pack_weights(b200taco_handle* h, const b200taco_weights* w, void* stream) {
     TACO_TRY(check_handle(h, false));
     TACO_REQUIRE(w != nullptr, B200TACO_ERR_INVALID, "null weights");
@@ -237,9 +235,7 @@ static int run_decoder(b200taco_handle* h, int mode, const float* d_memory, cons
                                       N_MELS, PRENET, 1, ACT_RELU, st));
         TACO_TRY(conv1d_channels_last(ws.y1, PRENET, h->prenet2T, nullptr, nullptr, nullptr, 0, ws.y2, PRENET, n, n, PRENET,
                                       PRENET, 1, ACT_RELU, st));
-        const int BP = decoder_batch_pad(B);
-        p_all_pack_kernel<<<2048, 256, 0, st>>>(ws.y2, ws.p_all, B, BP, S);
-        TACO_LAUNCHED();
+        TACO_TRY(decoder_pack_p_all(h, ws.y2, ws.p_all, B, S, st));
     }
     DecoderArgs a{};
     a.B = B; a.T = T; a.max_steps = S; a.mode = mode; a.stop_mode = stop_mode; a.gate_threshold = thr;
@@ -310,6 +306,16 @@ B200TACO_API int32_t b200taco_postnet_fwd(b200taco_handle* h, const float* d_mel
 
 B200TACO_API int32_t b200taco_measure_l2_read(void* d_buf, size_t bytes, int32_t iters, float* gbps, void* stream) {
     return measure_l2_read(d_buf, bytes, iters, gbps, static_cast<cudaStream_t>(stream));
+}
+
+B200TACO_API int32_t b200taco_measure_stream(void* d_buf, size_t per_cta, int32_t ctas, int32_t iters, int32_t mode,
+                                             int32_t chunk, int32_t depth, float* gbps_per_sm, void* stream) {
+    return measure_stream_probe(d_buf, per_cta, ctas, iters, mode, chunk, depth, gbps_per_sm, static_cast<cudaStream_t>(stream));
+}
+
+B200TACO_API int32_t b200taco_measure_sync_costs(int64_t* out8, void* stream) {
+    TACO_REQUIRE(out8 != nullptr, B200TACO_ERR_INVALID, "measure_sync_costs: null output");
+    return measure_sync_costs(reinterpret_cast<long long*>(out8), static_cast<cudaStream_t>(stream));
 }
 
 B200TACO_API int32_t b200taco_decoder_profile(b200taco_handle* h, int64_t* out, int32_t n, void* stream) {

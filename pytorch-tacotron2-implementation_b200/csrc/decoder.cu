@@ -20,6 +20,7 @@
 #include <cooperative_groups.h>
 
 #include "handle.h"
+#include "umma.cuh"
 
 namespace b200taco {
 
@@ -28,10 +29,12 @@ namespace {
 constexpr int NW = 8;                       // consumer warps
 constexpr int NTC = NW * 32;                // consumer threads
 constexpr int NT = NTC + 32;                // + producer warp
-#ifndef TACO_STAGES
-#define TACO_STAGES 4
-#endif
-constexpr int STAGES = TACO_STAGES;
+// Producer lanes: a thread's bulk copies complete one at a time (~0.4 us each whatever the size, measured:
+// profiles/r1_stream_probe.txt), so every pipeline stage has its own issuing lane (lane == stage) and the
+// copies of different stages proceed in parallel; one lane per stage also keeps each stage's uses in order.
+constexpr int MMA_WARP = 4;                 // consumer warp whose lane 0 issues tcgen05.mma (tensor-core path)
+constexpr int TC_CK = 64;                   // k per pipeline chunk on the tensor-core path
+constexpr int TC_KG = TC_CK / 8;
 constexpr int TILE_POS = 40;                // encoder positions per attention tile (8 groups x 5)
 constexpr int MAX_NS = 16;                  // max slices per utterance
 constexpr int APART = 4 + EMB;              // per-slice partial: m, s, pad, pad, ctx[512]
@@ -49,7 +52,10 @@ struct KParams {
     const void* w_dec;
     const float *bias_attn, *bias_dec, *wq_slices, *wproj_slices, *wproj_ctxT, *proj_bias, *prenet1T, *prenet2T,
         *loc_conv, *loc_denseT, *attn_v;
-    const float *memory, *pm, *p_all;
+    const float *memory, *pm;
+    const void* p_all;                 // teacher forcing: prenet outputs in the GEMM operand layout of the chosen path
+    const void *w_attn_tc, *w_dec_tc;  // tcgen05 path: bf16 weights as UMMA K-major tiles
+    __nv_bfloat16* act16;              // tcgen05 path: hi/lo bf16 activation tiles [2][44 chunks][2*BP rows x 64 k]
     const int64_t* text_lengths;
     float *mel, *gate, *align;
     int32_t *lengths, *steps_run;
@@ -69,18 +75,27 @@ struct Tile {
     static_assert(LB * BPL == BP && LK * LB * 4 == 32 && KPL * LK == KPW, "tile");
 };
 
-template <int BP, typename WT>
+// TC = tensor-core path (tcgen05, accumulators in TMEM): operands are bf16 K-major UMMA tiles,
+// activations split hi/lo (rows b and BP+b of the M=128 operand), N = this CTA's 32 gate rows.
+template <int BP, typename WT, bool TC>
 struct Smem {
     using TL = Tile<BP, sizeof(WT)>;
-    static constexpr int W_BYTES = TL::CK * ROWS_PER_CTA * (int)sizeof(WT);
-    static constexpr int A_BYTES = TL::CK * BP * 4;
+    static constexpr int CK = TC ? TC_CK : TL::CK;
+    static constexpr int NSTAGES = TC ? (BP <= 32 ? 8 : 6) : (BP >= 64 ? 4 : 6);
+    static constexpr int W_BYTES = CK * ROWS_PER_CTA * (int)sizeof(WT);
+    static constexpr int A_BYTES = TC ? 2 * BP * CK * 2 : CK * BP * 4;
     static constexpr int STAGE_BYTES = W_BYTES + A_BYTES;
+    static_assert(!TC || (sizeof(WT) == 2 && BP >= 32), "tensor-core path: bf16 weights, batch tile >= 32");
     // persistent small arrays (floats)
-    static constexpr int OFF_BAR = 0;                                          // 2*STAGES u64
-    static constexpr int OFF_STAGE = 128;
-    static constexpr int OFF_RED = OFF_STAGE + STAGES * STAGE_BYTES;           // NW*32*BP floats, aliased by P2/P4 scratch
-    static constexpr int RED_BYTES_MIN = 72 * 1024;
-    static constexpr int RED_BYTES = (NW * 32 * BP * 4 > RED_BYTES_MIN) ? NW * 32 * BP * 4 : RED_BYTES_MIN;
+    static constexpr int OFF_BAR = 0;                                          // full[], empty[], acc bar, tmem slot
+    static constexpr int OFF_ACCBAR = 2 * NSTAGES * 8;
+    static constexpr int OFF_TMEM = OFF_ACCBAR + 8;
+    static_assert(OFF_TMEM + 4 <= 256, "barrier area");
+    static constexpr int OFF_STAGE = 256;
+    static constexpr int OFF_RED = OFF_STAGE + NSTAGES * STAGE_BYTES;          // NW*32*BP floats, aliased by P2/P4 scratch
+    static constexpr int RED_BYTES_MIN = 48 * 1024;
+    static constexpr int RED_SIMT = TC ? 0 : NW * 32 * BP * 4;
+    static constexpr int RED_BYTES = RED_SIMT > RED_BYTES_MIN ? RED_SIMT : RED_BYTES_MIN;
     static constexpr int OFF_Z = OFF_RED + RED_BYTES;                          // 32*BP
     static constexpr int OFF_CA = OFF_Z + 32 * BP * 4;                         // 8*BP
     static constexpr int OFF_CD = OFF_CA + 8 * BP * 4;
@@ -97,6 +112,12 @@ struct Smem {
     static_assert(STAGE_BYTES % 128 == 0 && W_BYTES % 128 == 0, "bulk copy alignment");
 };
 
+// element offset of (row m, activation index k) inside one act16 buffer: [chunk][2*BP rows x 64 k tile]
+template <int BP>
+__device__ __forceinline__ size_t act16_off(int m, int k) {
+    return (size_t)(k / TC_CK) * (2 * BP * TC_CK) + umma::tile_offset(m, k % TC_CK, TC_KG);
+}
+
 // Scratch carved from the "red" region during P2 (floats)
 struct P2Scratch {
     static constexpr int PQ = 0;                                  // 256 (two halves)
@@ -109,7 +130,7 @@ struct P2Scratch {
     static constexpr int SC = EPART + TILE_POS * 4;               // MAX_NS scale factors + m,s
     static constexpr int TOTAL = SC + 64;
 };
-static_assert(P2Scratch::TOTAL * 4 <= 72 * 1024, "P2 scratch must fit the red region");
+static_assert(P2Scratch::TOTAL * 4 <= 48 * 1024 && 128 * 33 * 4 <= 48 * 1024, "P2 scratch must fit the red region");
 
 __device__ __forceinline__ void spin_fail() { __trap(); }
 
@@ -222,7 +243,8 @@ template <int BP, typename WT>
 __device__ __forceinline__ void gemm_consume(const Pipe& pipe, uint32_t& g, int nchunks, int warp, int lane,
                                              float (&acc)[8][Tile<BP>::BPL]) {
     using TL = Tile<BP, sizeof(WT)>;
-    using SM = Smem<BP, WT>;
+    using SM = Smem<BP, WT, false>;
+    constexpr int STAGES = SM::NSTAGES;
     const int lk = lane % TL::LK;
     const int lb = (lane / TL::LK) % TL::LB;
     const int lr = lane / (TL::LK * TL::LB);
@@ -291,9 +313,10 @@ __device__ __forceinline__ void gemm_reduce(float (&acc)[8][Tile<BP>::BPL], floa
 
 // LSTMCell pointwise part (gate order i,f,g,o; src/model.py:195-203 via nn.LSTMCell).
 // z rows are unit*4+gate; c state stays in shared memory of the owning CTA.
-template <int BP>
+template <int BP, bool TC>
 __device__ __forceinline__ void lstm_pointwise(const float* z, const float* bias, float* c_state, float* h_out,
-                                               float* act_dst /* &act[buf][row0][0] */, int B, int tid) {
+                                               float* act_dst /* &act[buf][row0][0] */, __nv_bfloat16* act16_buf,
+                                               int k0, int B, int tid) {
     for (int i = tid; i < UNITS_PER_CTA * BP; i += NTC) {
         const int u = i / BP, b = i % BP;
         if (b < B) {
@@ -305,7 +328,14 @@ __device__ __forceinline__ void lstm_pointwise(const float* z, const float* bias
             const float h = sigmoid_acc(zo) * tanhf(c);
             c_state[i] = c;
             h_out[i] = h;
-            act_dst[u * BP + b] = h;
+            if constexpr (TC) {
+                __nv_bfloat16 hi, lo;
+                umma::split_bf16(h, hi, lo);
+                act16_buf[act16_off<BP>(b, k0 + u)] = hi;
+                act16_buf[act16_off<BP>(BP + b, k0 + u)] = lo;
+            } else {
+                act_dst[u * BP + b] = h;
+            }
         } else {
             h_out[i] = 0.f;
         }
@@ -313,39 +343,156 @@ __device__ __forceinline__ void lstm_pointwise(const float* z, const float* bias
     consumer_sync();
 }
 
-// Producer: issue the weight part of chunks [c0, c1) of a GEMM phase (arms the full barrier
-// with the byte count of BOTH copies; the activation copy follows in produce_a).
-template <int BP, typename WT>
-__device__ __forceinline__ void produce_w(const Pipe& pipe, uint32_t g0, int c0, int c1, const WT* wsrc) {
-    using SM = Smem<BP, WT>;
-    using TL = Tile<BP, sizeof(WT)>;
-    for (int ch = c0; ch < c1; ++ch) {
-        const uint32_t g = g0 + ch, stage = g % STAGES, parity = ((g / STAGES) & 1u) ^ 1u;
-        mbar_wait(&pipe.empty[stage], parity);
-        mbar_arrive_expect_tx(&pipe.full[stage], SM::STAGE_BYTES);
-        bulk_g2s(pipe.stages + stage * SM::STAGE_BYTES, wsrc + (size_t)ch * TL::CK * ROWS_PER_CTA, SM::W_BYTES,
+// ---- producer warp -------------------------------------------------------------------------------
+// Every pipeline stage has its own issuing lane (lane == stage): a thread's bulk copies complete one at a
+// time (~0.4 us each whatever the size, profiles/r1_stream_probe.txt), copies of different threads overlap,
+// and one lane per stage keeps each stage's uses in order.  The lanes run ONE convergent loop and poll their
+// empty barriers with test_wait: a blocking try_wait would put the whole warp, i.e. all lanes, to sleep.
+// ch = position in this CTA's chunk order, pc(ch) = physical chunk (k range): every CTA walks the K range
+// from a different starting chunk so that the 128 CTAs do not request the same activation chunk at once.
+template <int BP, typename WT, bool TC>
+struct Producer {
+    using SM = Smem<BP, WT, TC>;
+    static constexpr int STAGES = SM::NSTAGES;
+
+    __device__ static __forceinline__ int first_chunk(uint32_t g0, int lane) {
+        return (lane + STAGES - (int)(g0 % STAGES)) % STAGES;
+    }
+    __device__ static __forceinline__ void issue_w(const Pipe& pipe, uint32_t stage, int pc, const WT* wsrc) {
+        mbar_arrive_expect_tx(&pipe.full[stage], SM::STAGE_BYTES);     // bytes of BOTH copies of the stage
+        bulk_g2s(pipe.stages + stage * SM::STAGE_BYTES, wsrc + (size_t)pc * SM::CK * ROWS_PER_CTA, SM::W_BYTES,
                  &pipe.full[stage]);
     }
-}
-// rows [0, split) of the phase's K range come from a0, the rest from a1 (teacher forcing
-// reads the prenet rows from the precomputed buffer).
-template <int BP, typename WT>
-__device__ __forceinline__ void produce_a(const Pipe& pipe, uint32_t g0, int c0, int c1, const float* a0,
-                                          const float* a1, int split_chunks) {
-    using SM = Smem<BP, WT>;
-    using TL = Tile<BP, sizeof(WT)>;
-    for (int ch = c0; ch < c1; ++ch) {
-        const uint32_t g = g0 + ch, stage = g % STAGES;
-        const float* src = ch < split_chunks ? a0 + (size_t)ch * TL::CK * BP : a1 + (size_t)ch * TL::CK * BP;
-        bulk_g2s(pipe.stages + stage * SM::STAGE_BYTES + SM::W_BYTES, src, SM::A_BYTES, &pipe.full[stage]);
+    __device__ static __forceinline__ void issue_a(const Pipe& pipe, uint32_t stage, int pc, const uint8_t* src) {
+        bulk_g2s(pipe.stages + stage * SM::STAGE_BYTES + SM::W_BYTES, src + (size_t)pc * SM::A_BYTES, SM::A_BYTES,
+                 &pipe.full[stage]);
     }
+    // All 32 lanes of the producer warp call this.  Chunks [0, pre) already have their weights in flight.
+    // Activation chunks with physical index < split come from a_lo, the others from a_hi.
+    __device__ static __forceinline__ void phase(const Pipe& pipe, uint32_t g0, int nch, int pre, int rot, int lane,
+                                                 const WT* wsrc, const uint8_t* a_lo, const uint8_t* a_hi, int split) {
+        int ch = lane < STAGES ? first_chunk(g0, lane) : nch;
+        const uint64_t t0 = global_timer_ns();
+        while (__any_sync(0xffffffffu, ch < nch)) {
+            if (ch < nch) {
+                const uint32_t g = g0 + ch, stage = g % STAGES, parity = ((g / STAGES) & 1u) ^ 1u;
+                if (ch < pre || mbar_test_wait(&pipe.empty[stage], parity)) {
+                    int pc = ch + rot;
+                    pc = pc >= nch ? pc - nch : pc;
+                    if (ch >= pre) issue_w(pipe, stage, pc, wsrc);
+                    issue_a(pipe, stage, pc, pc < split ? a_lo : a_hi);
+                    ch += STAGES;
+                } else if (global_timer_ns() - t0 > SPIN_TIMEOUT_NS) {
+                    spin_fail();
+                }
+            }
+        }
+    }
+    // weights of the first `pre` chunks of the NEXT phase (its activations are not ready yet)
+    __device__ static __forceinline__ void prefetch(const Pipe& pipe, uint32_t g0, int nch, int pre, int rot, int lane,
+                                                    const WT* wsrc) {
+        int ch = lane < STAGES ? first_chunk(g0, lane) : pre;
+        const uint64_t t0 = global_timer_ns();
+        while (__any_sync(0xffffffffu, ch < pre)) {
+            if (ch < pre) {
+                const uint32_t g = g0 + ch, stage = g % STAGES, parity = ((g / STAGES) & 1u) ^ 1u;
+                if (mbar_test_wait(&pipe.empty[stage], parity)) {
+                    int pc = ch + rot;
+                    pc = pc >= nch ? pc - nch : pc;
+                    issue_w(pipe, stage, pc, wsrc);
+                    ch += STAGES;
+                } else if (global_timer_ns() - t0 > SPIN_TIMEOUT_NS) {
+                    spin_fail();
+                }
+            }
+        }
+    }
+    // a phase that will never run was prefetched: complete its stages with dummy activation copies
+    __device__ static __forceinline__ void drain(const Pipe& pipe, uint32_t g0, int pre, int lane, const uint8_t* dummy) {
+        if (lane < STAGES) {
+            const int ch = first_chunk(g0, lane);
+            if (ch < pre) {
+                const uint32_t g = g0 + ch, stage = g % STAGES;
+                issue_a(pipe, stage, 0, dummy);
+                mbar_wait(&pipe.full[stage], (g / STAGES) & 1u);
+            }
+        }
+    }
+};
+
+// Tensor-core gate contraction: D[2*BP (hi rows | lo rows) x 32 gate rows] in TMEM, one tcgen05.mma
+// (M=128, N=32, K=16) per 16 k, issued by one thread; the stage is handed back to the TMA producer by
+// tcgen05.commit.  Result z[row][b] = D[b][row] + D[BP+b][row] in shared memory.
+#ifdef TACO_PROFILE_FINE
+__device__ unsigned long long g_dbg[4];
+#endif
+
+template <int BP, typename WT>
+__device__ __forceinline__ void gemm_tc(const Pipe& pipe, uint32_t& g, int nchunks, uint32_t tmem, uint64_t* acc_bar,
+                                        uint32_t& acc_phase, float* red, float* z, int warp, int lane, int tid) {
+    using SM = Smem<BP, WT, true>;
+    constexpr int STAGES = SM::NSTAGES;
+    if (warp == MMA_WARP) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma::instr_desc_bf16_f32(128, ROWS_PER_CTA);
+            uint32_t gg = g;
+#ifdef TACO_PROFILE_FINE
+            unsigned long long tw = 0, tl0 = global_timer_ns();
+#endif
+            for (int ch = 0; ch < nchunks; ++ch, ++gg) {
+                const uint32_t stage = gg % STAGES, parity = (gg / STAGES) & 1u;
+#ifdef TACO_PROFILE_FINE
+                const unsigned long long tw0 = global_timer_ns();
+#endif
+                mbar_wait(&pipe.full[stage], parity);
+#ifdef TACO_PROFILE_FINE
+                tw += global_timer_ns() - tw0;
+#endif
+                umma::fence_after_sync();
+                const uint32_t w_addr = smem_u32(pipe.stages + stage * SM::STAGE_BYTES);
+                const uint32_t a_addr = w_addr + SM::W_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < TC_CK / 16; ++ks)
+                    umma::mma_bf16(tmem, umma::smem_desc(a_addr + ks * 256, 128, TC_KG * 128),
+                                   umma::smem_desc(w_addr + ks * 256, 128, TC_KG * 128), idesc, ch > 0 || ks > 0);
+                umma::commit(&pipe.empty[stage]);       // stage is free once these MMAs have read it
+            }
+            umma::commit(acc_bar);
+#ifdef TACO_PROFILE_FINE
+            if (blockIdx.x == 0) {
+                atomicAdd(g_dbg + 0, tw);
+                atomicAdd(g_dbg + 1, global_timer_ns() - tl0);
+            }
+#endif
+        }
+        __syncwarp();
+    }
+    g += nchunks;
+    constexpr int EW = 2 * BP / 32;                     // warps whose TMEM lane quarter holds rows
+    if (warp < EW) {
+        mbar_wait(acc_bar, acc_phase);
+        umma::fence_after_sync();
+        float v[32];
+        umma::tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16), v);
+        umma::fence_before_sync();
+        const int m = warp * 32 + lane;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) red[m * 33 + r] = v[r];
+    }
+    acc_phase ^= 1u;
+    consumer_sync();
+    for (int i = tid; i < ROWS_PER_CTA * BP; i += NTC) {
+        const int r = i / BP, b = i % BP;
+        z[i] = red[b * 33 + r] + red[(BP + b) * 33 + r];
+    }
+    consumer_sync();
 }
 
 // ---------------------------------------------------------------------------------------
-template <int BP, typename WT>
+template <int BP, typename WT, bool TC>
 __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
-    using TL = Tile<BP, sizeof(WT)>;
-    using SM = Smem<BP, WT>;
+    using SM = Smem<BP, WT, TC>;
+    constexpr int STAGES = SM::NSTAGES;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cta = blockIdx.x, ncta = gridDim.x;
@@ -369,14 +516,21 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
     float* wld_s = reinterpret_cast<float*>(smem + SM::OFF_WLD);
     float* v_s = reinterpret_cast<float*>(smem + SM::OFF_V);
     int* misc_s = reinterpret_cast<int*>(smem + SM::OFF_MISC);
+    uint64_t* acc_bar = reinterpret_cast<uint64_t*>(smem + SM::OFF_ACCBAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_TMEM);
 
     // ---- one-time setup ----
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&pipe.full[s], 1);
-            mbar_init(&pipe.empty[s], NW);
+            mbar_init(&pipe.empty[s], TC ? 1 : NW);
         }
+        mbar_init(acc_bar, 1);
         fence_mbar_init();
+    }
+    if constexpr (TC) {
+        if (is_gemm && warp == 0) umma::tmem_alloc(tmem_slot, 32);      // 32 fp32 columns x 128 lanes
+        umma::fence_before_sync();
     }
     for (int i = tid; i < UNITS_PER_CTA * BP; i += NT) { ca_s[i] = 0.f; cd_s[i] = 0.f; h_s[i] = 0.f; }
     if (is_gemm) {
@@ -399,15 +553,23 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
     for (int i = tid; i < 130; i += NT) v_s[i] = p.attn_v[i];
     __syncthreads();
 
-    const WT* w_attn = reinterpret_cast<const WT*>(p.w_attn) + (size_t)cta * K_ATTN * ROWS_PER_CTA;
-    const WT* w_dec = reinterpret_cast<const WT*>(p.w_dec) + (size_t)cta * K_DEC * ROWS_PER_CTA;
-    constexpr int NCH1 = K_ATTN / TL::CK, NCH3 = K_DEC / TL::CK, PCH = PRENET / TL::CK;
+    uint32_t tmem = 0, acc_phase = 0;
+    if constexpr (TC) {
+        umma::fence_after_sync();
+        tmem = *tmem_slot;
+    }
+    const WT* w_attn = reinterpret_cast<const WT*>(TC ? p.w_attn_tc : p.w_attn) + (size_t)cta * K_ATTN * ROWS_PER_CTA;
+    const WT* w_dec = reinterpret_cast<const WT*>(TC ? p.w_dec_tc : p.w_dec) + (size_t)cta * K_DEC * ROWS_PER_CTA;
+    constexpr int NCH1 = K_ATTN / SM::CK, NCH3 = K_DEC / SM::CK, PCH = PRENET / SM::CK;
+    // bytes of one activation buffer in the GEMM operand layout and of one step of p_all
+    constexpr size_t ABUF_BYTES = TC ? (size_t)(ACT_ROWS / TC_CK) * SM::A_BYTES : (size_t)ACT_ROWS * BP * 4;
+    uint8_t* const abase = TC ? reinterpret_cast<uint8_t*>(p.act16) : reinterpret_cast<uint8_t*>(p.act);
 #ifdef TACO_NO_PREFETCH
     constexpr int PRE1 = 0, PRE3 = 0;
 #else
     constexpr int PRE1 = NCH1 < STAGES ? NCH1 : STAGES, PRE3 = NCH3 < STAGES ? NCH3 : STAGES;
 #endif
-    static_assert(PRENET % TL::CK == 0, "prenet rows must be whole chunks");
+    static_assert(PRENET % SM::CK == 0 && ACT_CTX % SM::CK == 0, "prenet / context rows must be whole chunks");
 
     uint32_t epoch = 0;
     uint32_t g = 0;             // chunks consumed (consumers) / chunks fully issued (producer)
@@ -431,33 +593,42 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
     };
 
     // producer: weight chunks of the very first phase
-    if (is_producer && is_gemm && lane == 0) produce_w<BP, WT>(pipe, g, 0, PRE1, w_attn);
+    const int rot1 = (cta * NCH1) / GEMM_CTAS, rot3 = (cta * NCH3) / GEMM_CTAS;       // this CTA's starting chunks
+    using PR = Producer<BP, WT, TC>;
+    if (is_producer && is_gemm) PR::prefetch(pipe, g, NCH1, PRE1, rot1, lane, w_attn);
 
     for (int s = 0; s < total_steps; ++s) {
         const int cur = s & 1, prv = cur ^ 1;
         float* act_cur = p.act + (size_t)cur * ACT_ROWS * BP;
         float* act_prv = p.act + (size_t)prv * ACT_ROWS * BP;
+        const uint8_t* a_cur = abase + (size_t)cur * ABUF_BYTES;        // GEMM operand view of the same buffers
+        const uint8_t* a_prv = abase + (size_t)prv * ABUF_BYTES;
+        __nv_bfloat16* act16_cur = p.act16 + (size_t)cur * (ABUF_BYTES / 2);
+        __nv_bfloat16* act16_prv = p.act16 + (size_t)prv * (ABUF_BYTES / 2);
         const int out_idx = tf ? s : s - 1;          // F6: decode step 0 of inference is discarded
 
         // =============================== P1: attention LSTM ===============================
         if (is_gemm) {
             if (is_producer) {
-                if (lane == 0) {
-                    fence_proxy_async();
-                    const float* a0 = tf ? p.p_all + (size_t)s * PRENET * BP : act_prv;
-                    // rows >= 256 always come from act_prv; a0 only differs for the prenet rows
-                    for (int ch = 0; ch < NCH1; ++ch) {
-                        if (ch >= PRE1) produce_w<BP, WT>(pipe, g, ch, ch + 1, w_attn);
-                        produce_a<BP, WT>(pipe, g, ch, ch + 1, a0, act_prv, PCH);
-                    }
-                    g += NCH1;
-                    produce_w<BP, WT>(pipe, g, 0, PRE3, w_dec);     // prefetch across P2
-                }
+                fence_proxy_async();
+                // prenet rows: previous buffer, or the precomputed buffer when teacher forcing
+                const uint8_t* a0 = tf ? static_cast<const uint8_t*>(p.p_all) + (size_t)s * PCH * SM::A_BYTES : a_prv;
+                PR::phase(pipe, g, NCH1, PRE1, rot1, lane, w_attn, a0, a_prv, PCH);
+                g += NCH1;
+                PR::prefetch(pipe, g, NCH3, PRE3, rot3, lane, w_dec);          // across P2
             } else {
-                float acc[8][TL::BPL];
-                gemm_consume<BP, WT>(pipe, g, NCH1, warp, lane, acc);
-                gemm_reduce<BP>(acc, red, z_s, warp, lane, tid);
-                lstm_pointwise<BP>(z_s, bias_s, ca_s, h_s, act_cur + (size_t)(ACT_AH + cta * UNITS_PER_CTA) * BP, B, tid);
+                FT_RESET();
+                if constexpr (TC) {
+                    gemm_tc<BP, WT>(pipe, g, NCH1, tmem, acc_bar, acc_phase, red, z_s, warp, lane, tid);
+                } else {
+                    float acc[8][Tile<BP>::BPL];
+                    gemm_consume<BP, WT>(pipe, g, NCH1, warp, lane, acc);
+                    gemm_reduce<BP>(acc, red, z_s, warp, lane, tid);
+                }
+                FT(9);
+                lstm_pointwise<BP, TC>(z_s, bias_s, ca_s, h_s, act_cur + (size_t)(ACT_AH + cta * UNITS_PER_CTA) * BP,
+                                       act16_cur, ACT_AH + cta * UNITS_PER_CTA, B, tid);
+                FT(10);
                 // this CTA's slice of the query projection (src/model.py:123): pqpart[b][cta][a]
                 for (int i = tid; i < ATT_DIM * B; i += NTC) {
                     const int a = i % ATT_DIM, b = i / ATT_DIM;
@@ -466,6 +637,7 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                     for (int u = 0; u < UNITS_PER_CTA; ++u) sum = fmaf(wq_s[a * 8 + u], h_s[u * BP + b], sum);
                     p.pqpart[((size_t)b * GEMM_CTAS + cta) * ATT_DIM + a] = sum;
                 }
+                FT(11);
             }
         }
         grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
@@ -659,8 +831,16 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                 cacc.x = cacc.x / S;
                 cacc.y = cacc.y / S;
                 // context -> act (column b) and the utterance-major copy used by the projections
-                act_cur[(size_t)(ACT_CTX + 2 * tid) * BP + b] = cacc.x;
-                act_cur[(size_t)(ACT_CTX + 2 * tid + 1) * BP + b] = cacc.y;
+                if constexpr (TC) {
+                    __nv_bfloat16 hx, lx, hy, ly;
+                    umma::split_bf16(cacc.x, hx, lx);
+                    umma::split_bf16(cacc.y, hy, ly);
+                    *reinterpret_cast<__nv_bfloat162*>(act16_cur + act16_off<BP>(b, ACT_CTX + 2 * tid)) = __nv_bfloat162(hx, hy);
+                    *reinterpret_cast<__nv_bfloat162*>(act16_cur + act16_off<BP>(BP + b, ACT_CTX + 2 * tid)) = __nv_bfloat162(lx, ly);
+                } else {
+                    act_cur[(size_t)(ACT_CTX + 2 * tid) * BP + b] = cacc.x;
+                    act_cur[(size_t)(ACT_CTX + 2 * tid + 1) * BP + b] = cacc.y;
+                }
                 reinterpret_cast<float2*>(p.ctx_bj + (size_t)b * EMB)[tid] = cacc;
                 // attention weights: alignment output, prev, cum (src/model.py:142-145)
                 for (int t = tid; t < T; t += NTC) {
@@ -681,22 +861,24 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
         // =============================== P3: decoder LSTM ===============================
         if (is_gemm) {
             if (is_producer) {
-                if (lane == 0) {
-                    fence_proxy_async();
-                    const float* a = act_cur + (size_t)ACT_CTX * BP;
-                    for (int ch = 0; ch < NCH3; ++ch) {
-                        if (ch >= PRE3) produce_w<BP, WT>(pipe, g, ch, ch + 1, w_dec);
-                        produce_a<BP, WT>(pipe, g, ch, ch + 1, a, a, 0);
-                    }
-                    g += NCH3;
-                    produce_w<BP, WT>(pipe, g, 0, PRE1, w_attn);    // prefetch next step's P1 across P4
-                }
+                fence_proxy_async();
+                const uint8_t* a = a_cur + (size_t)(ACT_CTX / SM::CK) * SM::A_BYTES;     // starts at the context rows
+                PR::phase(pipe, g, NCH3, PRE3, rot3, lane, w_dec, a, a, 0);
+                g += NCH3;
+                PR::prefetch(pipe, g, NCH1, PRE1, rot1, lane, w_attn);         // next step's P1, across P4
             } else {
-                float acc[8][TL::BPL];
-                gemm_consume<BP, WT>(pipe, g, NCH3, warp, lane, acc);
-                gemm_reduce<BP>(acc, red, z_s, warp, lane, tid);
-                lstm_pointwise<BP>(z_s, bias_s + 32, cd_s, h_s, act_prv + (size_t)(ACT_DH + cta * UNITS_PER_CTA) * BP, B,
-                                   tid);
+                FT_RESET();
+                if constexpr (TC) {
+                    gemm_tc<BP, WT>(pipe, g, NCH3, tmem, acc_bar, acc_phase, red, z_s, warp, lane, tid);
+                } else {
+                    float acc[8][Tile<BP>::BPL];
+                    gemm_consume<BP, WT>(pipe, g, NCH3, warp, lane, acc);
+                    gemm_reduce<BP>(acc, red, z_s, warp, lane, tid);
+                }
+                FT(12);
+                lstm_pointwise<BP, TC>(z_s, bias_s + 32, cd_s, h_s, act_prv + (size_t)(ACT_DH + cta * UNITS_PER_CTA) * BP,
+                                       act16_prv, ACT_DH + cta * UNITS_PER_CTA, B, tid);
+                FT(13);
                 // this CTA's slice of linear_projection / gate_layer (src/model.py:272-274)
                 for (int i = tid; i < PROJ_PAD * B; i += NTC) {
                     const int o = i % PROJ_PAD, b = i / PROJ_PAD;
@@ -811,7 +993,15 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                 if (tid < RQ) {
                     float v = 0.f;
                     for (int kg = 0; kg < NQ; ++kg) v += sc[640 + kg * RQ + tid];
-                    act_cur[(size_t)(ACT_P + q * RQ + tid) * BP + b] = fmaxf(v, 0.f);
+                    v = fmaxf(v, 0.f);
+                    if constexpr (TC) {
+                        __nv_bfloat16 hi, lo;
+                        umma::split_bf16(v, hi, lo);
+                        act16_cur[act16_off<BP>(b, ACT_P + q * RQ + tid)] = hi;
+                        act16_cur[act16_off<BP>(BP + b, ACT_P + q * RQ + tid)] = lo;
+                    } else {
+                        act_cur[(size_t)(ACT_P + q * RQ + tid) * BP + b] = v;
+                    }
                 }
             }
         }
@@ -824,20 +1014,15 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
     }
 
     // ---- drain: the producer prefetched weight chunks of a phase that will not run ----
-    if (is_producer && is_gemm && lane == 0) {
-        const float* dummy = p.act;
-        produce_a<BP, WT>(pipe, g, 0, PRE1, dummy, dummy, 0);
-        for (int ch = 0; ch < PRE1; ++ch) {
-            const uint32_t gg = g + ch;
-            mbar_wait(&pipe.full[gg % STAGES], (gg / STAGES) & 1u);
-        }
-    }
+    if (is_producer && is_gemm) PR::drain(pipe, g, PRE1, lane, abase);
     if (cta == 0 && tid == 0) {
         unsigned long long* prof = reinterpret_cast<unsigned long long*>(p.ctrl + CTRL_PROF);
         for (int i = 0; i < 4; ++i) prof[i] = t_phase[i];
         prof[4] = (unsigned long long)steps_done;
 #ifdef TACO_PROFILE_FINE
         for (int i = 0; i < 16; ++i) prof[5 + i] = t_fine[i];
+        prof[5 + 14] = g_dbg[0]; prof[5 + 15] = g_dbg[1];
+        g_dbg[0] = 0; g_dbg[1] = 0;
 #endif
         const int S = tf ? p.max_steps : steps_done - 1;     // output frames (decode step 0 discarded)
         *p.steps_run = S;
@@ -849,12 +1034,17 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
         }
     }
     (void)stopped;
+    if constexpr (TC) {
+        umma::fence_before_sync();
+        __syncthreads();
+        if (is_gemm && warp == 0) umma::tmem_dealloc(tmem, 32);
+    }
 }
 
-template <int BP, typename WT>
+template <int BP, typename WT, bool TC>
 int launch(const KParams& kp, int ncta, cudaStream_t stream) {
-    using SM = Smem<BP, WT>;
-    auto kern = decoder_kernel<BP, WT>;
+    using SM = Smem<BP, WT, TC>;
+    auto kern = decoder_kernel<BP, WT, TC>;
     TACO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     int per_sm = 0;
     TACO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, SM::TOTAL));
@@ -865,22 +1055,45 @@ int launch(const KParams& kp, int ncta, cudaStream_t stream) {
     return B200TACO_OK;
 }
 
+// prenet outputs Y[s*B + b][256] (fp32) -> the operand layout the chosen path streams per step
+__global__ void p_all_pack_simt_kernel(const float* __restrict__ Y, float* __restrict__ P, int B, int BP, int S) {
+    const size_t total = (size_t)S * PRENET * BP;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = i % BP, k = (i / BP) % PRENET, s = i / ((size_t)BP * PRENET);
+        P[i] = b < B ? Y[((size_t)s * B + b) * PRENET + k] : 0.f;
+    }
+}
+__global__ void p_all_pack_tc_kernel(const float* __restrict__ Y, __nv_bfloat16* __restrict__ P, int B, int BP, int S) {
+    const size_t per_step = (size_t)PRENET * 2 * BP;          // 4 chunks x (2*BP rows x 64 k)
+    const size_t total = (size_t)S * PRENET * BP;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int k = i % PRENET, b = (i / PRENET) % BP, s = i / ((size_t)PRENET * BP);
+        const float v = b < B ? Y[((size_t)s * B + b) * PRENET + k] : 0.f;
+        __nv_bfloat16 hi, lo;
+        umma::split_bf16(v, hi, lo);
+        const size_t chunk = (size_t)(k / TC_CK) * (2 * BP * TC_CK);
+        P[s * per_step + chunk + umma::tile_offset(b, k % TC_CK, TC_KG)] = hi;
+        P[s * per_step + chunk + umma::tile_offset(BP + b, k % TC_CK, TC_KG)] = lo;
+    }
+}
+
 template <typename WT>
 int dispatch_bp(int BP, const KParams& kp, int ncta, cudaStream_t stream) {
     switch (BP) {
-        case 1: return launch<1, WT>(kp, ncta, stream);
-        case 2: return launch<2, WT>(kp, ncta, stream);
-        case 4: return launch<4, WT>(kp, ncta, stream);
-        case 8: return launch<8, WT>(kp, ncta, stream);
-        case 16: return launch<16, WT>(kp, ncta, stream);
-        case 32: return launch<32, WT>(kp, ncta, stream);
-        case 64: return launch<64, WT>(kp, ncta, stream);
+        case 1: return launch<1, WT, false>(kp, ncta, stream);
+        case 2: return launch<2, WT, false>(kp, ncta, stream);
+        case 4: return launch<4, WT, false>(kp, ncta, stream);
+        case 8: return launch<8, WT, false>(kp, ncta, stream);
+        case 16: return launch<16, WT, false>(kp, ncta, stream);
+        case 32: return launch<32, WT, false>(kp, ncta, stream);
+        case 64: return launch<64, WT, false>(kp, ncta, stream);
     }
     set_error("unsupported batch padding %d", BP);
     return B200TACO_ERR_UNSUPPORTED;
 }
 
 struct ScratchLayout {
+    size_t act16;
     size_t act, pqpart, melpart, melctx, ctx_bj, attn_prev, attn_cum, wtmp, apart, ctrl, total;
     size_t zero_begin, zero_end;
 };
@@ -894,6 +1107,7 @@ ScratchLayout scratch_layout(int B, int T) {
     // zero-initialised region first (state), then write-before-read buffers
     L.zero_begin = off;
     L.act = take((size_t)2 * ACT_ROWS * BP * 4);
+    L.act16 = take(BP >= 32 ? (size_t)2 * ACT_ROWS * 2 * BP * 2 : 0);     // hi/lo bf16 operand tiles (tensor-core path)
     L.attn_prev = take((size_t)2 * B * Tp * 4);
     L.attn_cum = take((size_t)2 * B * Tp * 4);
     L.ctrl = take((size_t)CTRL_WORDS * 4);
@@ -909,6 +1123,22 @@ ScratchLayout scratch_layout(int B, int T) {
 }
 
 }  // namespace
+
+bool decoder_uses_tensor_cores(const b200taco_handle* h, int B) {
+    // tcgen05 only where batch x 4H is a real GEMM (north_star c); vectorised SIMT contraction otherwise
+    if (h->decoder_path == 1) return false;
+    return h->weight_dtype == 0 && decoder_batch_pad(B) >= 32;
+}
+
+int decoder_pack_p_all(const b200taco_handle* h, const float* Y, void* P, int B, int S, cudaStream_t stream) {
+    const int BP = decoder_batch_pad(B);
+    if (decoder_uses_tensor_cores(h, B))
+        p_all_pack_tc_kernel<<<2048, 256, 0, stream>>>(Y, static_cast<__nv_bfloat16*>(P), B, BP, S);
+    else
+        p_all_pack_simt_kernel<<<2048, 256, 0, stream>>>(Y, static_cast<float*>(P), B, BP, S);
+    TACO_LAUNCHED();
+    return B200TACO_OK;
+}
 
 int decoder_batch_pad(int B) {
     int bp = 1;
@@ -952,6 +1182,8 @@ int decoder_run(const b200taco_handle* h, const DecoderArgs& a, cudaStream_t str
     kp.memory = a.memory; kp.pm = a.pm; kp.p_all = a.p_all; kp.text_lengths = a.text_lengths;
     kp.mel = a.mel; kp.gate = a.gate; kp.align = a.align; kp.lengths = a.lengths; kp.steps_run = a.steps_run;
     kp.act = reinterpret_cast<float*>(base + L.act);
+    kp.act16 = reinterpret_cast<__nv_bfloat16*>(base + L.act16);
+    kp.w_attn_tc = h->w_attn_tc; kp.w_dec_tc = h->w_dec_tc;
     kp.pqpart = reinterpret_cast<float*>(base + L.pqpart);
     kp.melpart = reinterpret_cast<float*>(base + L.melpart);
     kp.melctx = reinterpret_cast<float*>(base + L.melctx);
@@ -962,6 +1194,11 @@ int decoder_run(const b200taco_handle* h, const DecoderArgs& a, cudaStream_t str
     kp.apart = reinterpret_cast<float*>(base + L.apart);
     kp.ctrl = reinterpret_cast<uint32_t*>(base + L.ctrl);
     const_cast<b200taco_handle*>(h)->last_profile = reinterpret_cast<const unsigned long long*>(kp.ctrl + CTRL_PROF);
+    if (decoder_uses_tensor_cores(h, a.B)) {
+        TACO_REQUIRE(h->w_attn_tc && h->w_dec_tc, B200TACO_ERR_STATE, "tensor-core weights not packed");
+        if (BP == 32) return launch<32, __nv_bfloat16, true>(kp, ncta, stream);
+        return launch<64, __nv_bfloat16, true>(kp, ncta, stream);
+    }
     if (h->weight_dtype == 1) return dispatch_bp<float>(BP, kp, ncta, stream);
     return dispatch_bp<__nv_bfloat16>(BP, kp, ncta, stream);
 }

@@ -7,6 +7,7 @@ struct b200taco_handle {
     int device = 0;
     int num_sms = 0;
     int weight_dtype = 0;           // 0 = bf16 LSTM matrices (default), 1 = fp32
+    int decoder_path = 0;           // 0 = auto (tcgen05 when batch >= 17 and bf16 weights), 1 = SIMT only
     bool packed = false;
     const unsigned long long* last_profile = nullptr;   // device: phase timers of the last decoder launch
 
@@ -17,6 +18,8 @@ struct b200taco_handle {
     // ---- decoder (decoder.cu) ----
     void* w_attn = nullptr;         // [128 cta][K_ATTN][32 rows]  bf16 or fp32, rows = unit*4+gate
     void* w_dec = nullptr;          // [128 cta][K_DEC ][32 rows]
+    void* w_attn_tc = nullptr;      // bf16 mode: [128 cta][K/64 chunks][32 rows x 64 k UMMA K-major tile]
+    void* w_dec_tc = nullptr;
     float* bias_attn = nullptr;     // [128][32]  b_ih + b_hh
     float* bias_dec = nullptr;
     float* wq_slices = nullptr;     // [128 cta][128 a][8 u]    query_layer.weight[a][8*cta+u]
@@ -67,7 +70,7 @@ struct DecoderArgs {
     const float* memory;          // (B,T,512)
     const float* pm;              // (B,T,128) processed memory
     const int64_t* text_lengths;  // (B) or null
-    const float* p_all;           // teacher forcing: (S,256,BP) prenet outputs, else null
+    const void* p_all;            // teacher forcing: prenet outputs packed by decoder_pack_p_all, else null
     float* mel;                   // (B,max_steps,80)
     float* gate;                  // (B,max_steps)
     float* align;                 // (max_steps,B,T)
@@ -78,9 +81,14 @@ struct DecoderArgs {
 };
 size_t decoder_scratch_bytes(int B, int T);
 int decoder_batch_pad(int B);
+bool decoder_uses_tensor_cores(const b200taco_handle* h, int B);
+int decoder_pack_p_all(const b200taco_handle* h, const float* Y, void* P, int B, int S, cudaStream_t stream);
 int decoder_run(const b200taco_handle* h, const DecoderArgs& a, cudaStream_t stream);
 
 // measure.cu
 int measure_l2_read(void* d_buf, size_t bytes, int iters, float* gbps, cudaStream_t stream);
+int measure_sync_costs(long long* out8_host, cudaStream_t stream);
+int measure_stream_probe(void* d_buf, size_t per_cta, int ctas, int iters, int mode, int chunk, int depth, float* gbps_per_sm,
+                         cudaStream_t stream);
 
 }  // namespace b200taco

@@ -35,6 +35,25 @@ __global__ void pack_lstm_kernel(WT* dst, int K, const float* s0, int ld0, int o
     }
 }
 
+// tensor-core layout: dst[cta][chunk = k/64][UMMA K-major tile of 32 rows x 64 k], same k order / row order
+__global__ void pack_lstm_tc_kernel(__nv_bfloat16* dst, int K, const float* s0, int ld0, int off0, int n0, const float* s1,
+                                    int ld1, int off1, int n1, const float* s2, int ld2, int off2) {
+    const size_t total = (size_t)GEMM_CTAS * K * ROWS_PER_CTA;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int k = i % K;
+        const int r = (i / K) % ROWS_PER_CTA;
+        const int cta = i / ((size_t)ROWS_PER_CTA * K);
+        const int row = (r & 3) * RNN + cta * UNITS_PER_CTA + (r >> 2);
+        float v;
+        if (k < n0) v = s0[(size_t)row * ld0 + off0 + k];
+        else if (k < n0 + n1) v = s1[(size_t)row * ld1 + off1 + (k - n0)];
+        else v = s2[(size_t)row * ld2 + off2 + (k - n0 - n1)];
+        const size_t o = (size_t)cta * K * ROWS_PER_CTA + (size_t)(k / 64) * (64 * ROWS_PER_CTA) +
+                         ((((r >> 3) * 8 + ((k % 64) >> 3)) << 6) + ((r & 7) << 3) + (k & 7));
+        dst[o] = __float2bfloat16_rn(v);
+    }
+}
+
 __global__ void pack_lstm_bias_kernel(float* dst, const float* b_ih, const float* b_hh) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < GEMM_CTAS * ROWS_PER_CTA) {
@@ -144,6 +163,8 @@ size_t carve(b200taco_handle* h, uint8_t* base, int weight_dtype) {
     const size_t wb = weight_dtype == 1 ? 4 : 2;
     void* w_attn = A.take<uint8_t>((size_t)GEMM_CTAS * K_ATTN * ROWS_PER_CTA * wb);
     void* w_dec = A.take<uint8_t>((size_t)GEMM_CTAS * K_DEC * ROWS_PER_CTA * wb);
+    void* w_attn_tc = A.take<uint8_t>(weight_dtype == 0 ? (size_t)GEMM_CTAS * K_ATTN * ROWS_PER_CTA * 2 : 0);
+    void* w_dec_tc = A.take<uint8_t>(weight_dtype == 0 ? (size_t)GEMM_CTAS * K_DEC * ROWS_PER_CTA * 2 : 0);
     float* bias_attn = A.take<float>(GEMM_CTAS * ROWS_PER_CTA);
     float* bias_dec = A.take<float>(GEMM_CTAS * ROWS_PER_CTA);
     float* wq = A.take<float>(GEMM_CTAS * ATT_DIM * UNITS_PER_CTA);
@@ -174,6 +195,8 @@ size_t carve(b200taco_handle* h, uint8_t* base, int weight_dtype) {
         pch[i] = A.take<float>(co);
     }
     if (h && base) {
+        h->w_attn_tc = weight_dtype == 0 ? w_attn_tc : nullptr;
+        h->w_dec_tc = weight_dtype == 0 ? w_dec_tc : nullptr;
         h->w_attn = w_attn; h->w_dec = w_dec; h->bias_attn = bias_attn; h->bias_dec = bias_dec;
         h->wq_slices = wq; h->wproj_slices = wproj; h->wproj_ctxT = wctx; h->proj_bias = pbias;
         h->prenet1T = p1; h->prenet2T = p2; h->loc_conv = lc; h->loc_denseT = ld; h->attn_v = av;
@@ -222,6 +245,14 @@ int pack_weights(b200taco_handle* h, const b200taco_weights* w, cudaStream_t st)
         TACO_LAUNCHED();
         pack_lstm_kernel<__nv_bfloat16><<<blocks_for(nd), 256, 0, st>>>(
             (__nv_bfloat16*)h->w_dec, K_DEC, w->dec_lstm_w_ih, RNN + EMB, RNN, EMB, w->dec_lstm_w_ih, RNN + EMB, 0, RNN,
+            w->dec_lstm_w_hh, RNN, 0);
+        TACO_LAUNCHED();
+        pack_lstm_tc_kernel<<<blocks_for(na), 256, 0, st>>>(
+            (__nv_bfloat16*)h->w_attn_tc, K_ATTN, w->attn_lstm_w_ih, PRENET + EMB, 0, PRENET + EMB, w->attn_lstm_w_hh, RNN,
+            0, RNN, w->attn_lstm_w_hh, RNN, 0);
+        TACO_LAUNCHED();
+        pack_lstm_tc_kernel<<<blocks_for(nd), 256, 0, st>>>(
+            (__nv_bfloat16*)h->w_dec_tc, K_DEC, w->dec_lstm_w_ih, RNN + EMB, RNN, EMB, w->dec_lstm_w_ih, RNN + EMB, 0, RNN,
             w->dec_lstm_w_hh, RNN, 0);
         TACO_LAUNCHED();
     }
