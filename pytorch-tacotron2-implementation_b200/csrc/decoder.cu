@@ -35,6 +35,8 @@ constexpr int NT = NTC + 32;                // + producer warp
 constexpr int MMA_WARP = 4;                 // consumer warp whose lane 0 issues tcgen05.mma (tensor-core path)
 constexpr int TC_CK = 64;                   // k per pipeline chunk on the tensor-core path
 constexpr int TC_KG = TC_CK / 8;
+constexpr int GS = 4;                       // tensor-core path: CTAs per split-K group
+constexpr int GN = GS * ROWS_PER_CTA;       // gate rows per group = N of one tcgen05.mma (128)
 constexpr int TILE_POS = 40;                // encoder positions per attention tile (8 groups x 5)
 constexpr int MAX_NS = 16;                  // max slices per utterance
 constexpr int APART = 4 + EMB;              // per-slice partial: m, s, pad, pad, ctx[512]
@@ -43,7 +45,8 @@ constexpr uint64_t SPIN_TIMEOUT_NS = 4000000000ull;
 // control words in scratch
 constexpr int CTRL_BARRIER = 0, CTRL_STOP = 1, CTRL_FINISHED = 2, CTRL_TICKETS = 32, CTRL_DONE = 32 + MAX_BATCH,
               CTRL_LEN = 32 + 2 * MAX_BATCH, CTRL_PROF = 32 + 3 * MAX_BATCH /* 5 x u64 */,
-              CTRL_WORDS = CTRL_PROF + 48;
+              CTRL_GCNT = CTRL_PROF + 48 /* 32 group counters */,
+              CTRL_WORDS = CTRL_GCNT + GEMM_CTAS / GS;
 
 struct KParams {
     int B, T, Tp, NS, SL, NQ, max_steps, mode, stop_mode;
@@ -61,6 +64,7 @@ struct KParams {
     int32_t *lengths, *steps_run;
     // scratch
     float *act, *pqpart, *melpart, *melctx, *ctx_bj, *attn_prev, *attn_cum, *wtmp, *apart;
+    float* zpart;                      // tcgen05 path: split-K partial gate sums [dst cta][src member][32 rows][BP]
     uint32_t* ctrl;
 };
 
@@ -81,8 +85,9 @@ template <int BP, typename WT, bool TC>
 struct Smem {
     using TL = Tile<BP, sizeof(WT)>;
     static constexpr int CK = TC ? TC_CK : TL::CK;
-    static constexpr int NSTAGES = TC ? (BP <= 32 ? 8 : 6) : (BP >= 64 ? 4 : 6);
-    static constexpr int W_BYTES = CK * ROWS_PER_CTA * (int)sizeof(WT);
+    static constexpr int NSTAGES = TC ? (BP <= 32 ? 4 : 3) : (BP >= 64 ? 4 : 6);
+    static constexpr int WROWS = TC ? GN : ROWS_PER_CTA;                       // weight rows per chunk
+    static constexpr int W_BYTES = CK * WROWS * (int)sizeof(WT);
     static constexpr int A_BYTES = TC ? 2 * BP * CK * 2 : CK * BP * 4;
     static constexpr int STAGE_BYTES = W_BYTES + A_BYTES;
     static_assert(!TC || (sizeof(WT) == 2 && BP >= 32), "tensor-core path: bf16 weights, batch tile >= 32");
@@ -360,7 +365,7 @@ struct Producer {
     }
     __device__ static __forceinline__ void issue_w(const Pipe& pipe, uint32_t stage, int pc, const WT* wsrc) {
         mbar_arrive_expect_tx(&pipe.full[stage], SM::STAGE_BYTES);     // bytes of BOTH copies of the stage
-        bulk_g2s(pipe.stages + stage * SM::STAGE_BYTES, wsrc + (size_t)pc * SM::CK * ROWS_PER_CTA, SM::W_BYTES,
+        bulk_g2s(pipe.stages + stage * SM::STAGE_BYTES, wsrc + (size_t)pc * SM::CK * SM::WROWS, SM::W_BYTES,
                  &pipe.full[stage]);
     }
     __device__ static __forceinline__ void issue_a(const Pipe& pipe, uint32_t stage, int pc, const uint8_t* src) {
@@ -368,9 +373,11 @@ struct Producer {
                  &pipe.full[stage]);
     }
     // All 32 lanes of the producer warp call this.  Chunks [0, pre) already have their weights in flight.
-    // Activation chunks with physical index < split come from a_lo, the others from a_hi.
+    // This CTA's nch chunks are the physical chunks abase .. abase+nch-1 of the activation vector (abase != 0
+    // on the split-K tensor-core path); those with physical index < split come from a_lo, the others from a_hi.
     __device__ static __forceinline__ void phase(const Pipe& pipe, uint32_t g0, int nch, int pre, int rot, int lane,
-                                                 const WT* wsrc, const uint8_t* a_lo, const uint8_t* a_hi, int split) {
+                                                 const WT* wsrc, const uint8_t* a_lo, const uint8_t* a_hi, int split,
+                                                 int abase) {
         int ch = lane < STAGES ? first_chunk(g0, lane) : nch;
         const uint64_t t0 = global_timer_ns();
         while (__any_sync(0xffffffffu, ch < nch)) {
@@ -380,7 +387,7 @@ struct Producer {
                     int pc = ch + rot;
                     pc = pc >= nch ? pc - nch : pc;
                     if (ch >= pre) issue_w(pipe, stage, pc, wsrc);
-                    issue_a(pipe, stage, pc, pc < split ? a_lo : a_hi);
+                    issue_a(pipe, stage, abase + pc, abase + pc < split ? a_lo : a_hi);
                     ch += STAGES;
                 } else if (global_timer_ns() - t0 > SPIN_TIMEOUT_NS) {
                     spin_fail();
@@ -420,21 +427,26 @@ struct Producer {
     }
 };
 
-// Tensor-core gate contraction: D[2*BP (hi rows | lo rows) x 32 gate rows] in TMEM, one tcgen05.mma
-// (M=128, N=32, K=16) per 16 k, issued by one thread; the stage is handed back to the TMA producer by
-// tcgen05.commit.  Result z[row][b] = D[b][row] + D[BP+b][row] in shared memory.
+// Tensor-core gate contraction, split-K over a group of GS=4 CTAs (cta = 4*group + member):
+// the group owns 128 gate rows (32 hidden units); member r multiplies them with its quarter of the K range:
+//   D_r[2*BP (hi rows | lo rows) x 128] += A[:, K_r] . W_group[:, K_r]^T     (tcgen05.mma M=128, N=128, K=16)
+// One MMA costs ~128 cycles whatever N (measured), so N=128 with a quarter of the K steps is 4x cheaper than
+// N=32 over the whole K, and each CTA streams only a quarter of the activations.  The four partial sums meet
+// through L2: member r sends the 32-row slice of member r' to zpart[r'][r], a group counter (release/acquire)
+// separates send and receive, and every member ends up with z[row][b] of its own 8 hidden units.
 #ifdef TACO_PROFILE_FINE
 __device__ unsigned long long g_dbg[4];
 #endif
 
 template <int BP, typename WT>
 __device__ __forceinline__ void gemm_tc(const Pipe& pipe, uint32_t& g, int nchunks, uint32_t tmem, uint64_t* acc_bar,
-                                        uint32_t& acc_phase, float* red, float* z, int warp, int lane, int tid) {
+                                        uint32_t& acc_phase, float* red, float* z, float* zpart, uint32_t* gcnt,
+                                        uint32_t& gepoch, int cta, int warp, int lane, int tid) {
     using SM = Smem<BP, WT, true>;
     constexpr int STAGES = SM::NSTAGES;
     if (warp == MMA_WARP) {
         if (lane == 0) {
-            constexpr uint32_t idesc = umma::instr_desc_bf16_f32(128, ROWS_PER_CTA);
+            constexpr uint32_t idesc = umma::instr_desc_bf16_f32(128, GN);
             uint32_t gg = g;
 #ifdef TACO_PROFILE_FINE
             unsigned long long tw = 0, tl0 = global_timer_ns();
@@ -468,23 +480,64 @@ __device__ __forceinline__ void gemm_tc(const Pipe& pipe, uint32_t& g, int nchun
         __syncwarp();
     }
     g += nchunks;
+    const int member = cta % GS, group = cta / GS;
     constexpr int EW = 2 * BP / 32;                     // warps whose TMEM lane quarter holds rows
+    constexpr int PB = BP <= 32 ? 4 : 2;                // 32-column blocks staged in `red` per pass
+    constexpr int RS = PB * 32 + 1;                     // red row stride
+    static_assert(2 * BP * RS * 4 <= Smem<BP, WT, true>::RED_BYTES, "epilogue staging must fit the red region");
     if (warp < EW) {
         mbar_wait(acc_bar, acc_phase);
         umma::fence_after_sync();
-        float v[32];
-        umma::tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16), v);
-        umma::fence_before_sync();
-        const int m = warp * 32 + lane;
-#pragma unroll
-        for (int r = 0; r < 32; ++r) red[m * 33 + r] = v[r];
     }
     acc_phase ^= 1u;
+#pragma unroll 1
+    for (int pass = 0; pass < GS / PB; ++pass) {
+        if (warp < EW) {
+            const int m = warp * 32 + lane;
+#pragma unroll
+            for (int cbl = 0; cbl < PB; ++cbl) {
+                float v[32];
+                umma::tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + (pass * PB + cbl) * 32, v);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) red[m * RS + cbl * 32 + c] = v[c];
+            }
+            umma::fence_before_sync();
+        }
+        consumer_sync();
+        // hi + lo rows; columns [32*dst, 32*dst+32) are the gate rows of member dst
+        for (int i = tid; i < PB * ROWS_PER_CTA * BP; i += NTC) {
+            const int b = i % BP, c = (i / BP) % ROWS_PER_CTA, cbl = i / (BP * ROWS_PER_CTA);
+            const int dst = pass * PB + cbl;
+            const float v = red[b * RS + cbl * 32 + c] + red[(BP + b) * RS + cbl * 32 + c];
+            if (dst == member) z[c * BP + b] = v;       // own slice stays in shared memory
+            else zpart[(((size_t)(group * GS + dst)) * GS + member) * (ROWS_PER_CTA * BP) + c * BP + b] = v;
+        }
+        consumer_sync();
+    }
+    // group rendezvous: all four partial slices are in L2
+    gepoch += 1;
+    if (tid == 0) {
+        red_release_add_u32(gcnt + group, 1u);
+        const uint32_t target = gepoch * GS;
+        if (ld_acquire_u32(gcnt + group) < target) {
+            const uint64_t t0 = global_timer_ns();
+            while (ld_acquire_u32(gcnt + group) < target) {
+                if (global_timer_ns() - t0 > SPIN_TIMEOUT_NS) spin_fail();
+            }
+        }
+    }
     consumer_sync();
     for (int i = tid; i < ROWS_PER_CTA * BP; i += NTC) {
-        const int r = i / BP, b = i % BP;
-        z[i] = red[b * 33 + r] + red[(BP + b) * 33 + r];
+        float acc = 0.f;
+#pragma unroll
+        for (int src = 0; src < GS; ++src) {            // fixed order: bitwise reproducible
+            const float v = src == member ? z[i] : __ldcg(zpart + ((size_t)cta * GS + src) * (ROWS_PER_CTA * BP) + i);
+            acc += v;
+        }
+        red[i] = acc;
     }
+    consumer_sync();
+    for (int i = tid; i < ROWS_PER_CTA * BP; i += NTC) z[i] = red[i];
     consumer_sync();
 }
 
@@ -529,7 +582,7 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
         fence_mbar_init();
     }
     if constexpr (TC) {
-        if (is_gemm && warp == 0) umma::tmem_alloc(tmem_slot, 32);      // 32 fp32 columns x 128 lanes
+        if (is_gemm && warp == 0) umma::tmem_alloc(tmem_slot, GN);      // 128 fp32 columns x 128 lanes
         umma::fence_before_sync();
     }
     for (int i = tid; i < UNITS_PER_CTA * BP; i += NT) { ca_s[i] = 0.f; cd_s[i] = 0.f; h_s[i] = 0.f; }
@@ -553,14 +606,18 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
     for (int i = tid; i < 130; i += NT) v_s[i] = p.attn_v[i];
     __syncthreads();
 
-    uint32_t tmem = 0, acc_phase = 0;
+    uint32_t tmem = 0, acc_phase = 0, gepoch = 0;
     if constexpr (TC) {
         umma::fence_after_sync();
         tmem = *tmem_slot;
     }
+    // per-CTA weight bytes are the same on both paths: 32 rows x K, or 128 rows x K/4 (split-K group)
     const WT* w_attn = reinterpret_cast<const WT*>(TC ? p.w_attn_tc : p.w_attn) + (size_t)cta * K_ATTN * ROWS_PER_CTA;
     const WT* w_dec = reinterpret_cast<const WT*>(TC ? p.w_dec_tc : p.w_dec) + (size_t)cta * K_DEC * ROWS_PER_CTA;
-    constexpr int NCH1 = K_ATTN / SM::CK, NCH3 = K_DEC / SM::CK, PCH = PRENET / SM::CK;
+    constexpr int KSPLIT = TC ? GS : 1;
+    constexpr int NCH1 = K_ATTN / SM::CK / KSPLIT, NCH3 = K_DEC / SM::CK / KSPLIT, PCH = PRENET / SM::CK;
+    static_assert((K_ATTN / SM::CK) % KSPLIT == 0 && (K_DEC / SM::CK) % KSPLIT == 0, "K split");
+    const int ab1 = TC ? (cta % GS) * NCH1 : 0, ab3 = TC ? (cta % GS) * NCH3 : 0;    // first physical chunk of this CTA
     // bytes of one activation buffer in the GEMM operand layout and of one step of p_all
     constexpr size_t ABUF_BYTES = TC ? (size_t)(ACT_ROWS / TC_CK) * SM::A_BYTES : (size_t)ACT_ROWS * BP * 4;
     uint8_t* const abase = TC ? reinterpret_cast<uint8_t*>(p.act16) : reinterpret_cast<uint8_t*>(p.act);
@@ -593,7 +650,7 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
     };
 
     // producer: weight chunks of the very first phase
-    const int rot1 = (cta * NCH1) / GEMM_CTAS, rot3 = (cta * NCH3) / GEMM_CTAS;       // this CTA's starting chunks
+    const int rot1 = ((cta / KSPLIT) * NCH1 * KSPLIT) / GEMM_CTAS, rot3 = ((cta / KSPLIT) * NCH3 * KSPLIT) / GEMM_CTAS;
     using PR = Producer<BP, WT, TC>;
     if (is_producer && is_gemm) PR::prefetch(pipe, g, NCH1, PRE1, rot1, lane, w_attn);
 
@@ -613,13 +670,14 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                 fence_proxy_async();
                 // prenet rows: previous buffer, or the precomputed buffer when teacher forcing
                 const uint8_t* a0 = tf ? static_cast<const uint8_t*>(p.p_all) + (size_t)s * PCH * SM::A_BYTES : a_prv;
-                PR::phase(pipe, g, NCH1, PRE1, rot1, lane, w_attn, a0, a_prv, PCH);
+                PR::phase(pipe, g, NCH1, PRE1, rot1, lane, w_attn, a0, a_prv, PCH, ab1);
                 g += NCH1;
                 PR::prefetch(pipe, g, NCH3, PRE3, rot3, lane, w_dec);          // across P2
             } else {
                 FT_RESET();
                 if constexpr (TC) {
-                    gemm_tc<BP, WT>(pipe, g, NCH1, tmem, acc_bar, acc_phase, red, z_s, warp, lane, tid);
+                    gemm_tc<BP, WT>(pipe, g, NCH1, tmem, acc_bar, acc_phase, red, z_s, p.zpart, p.ctrl + CTRL_GCNT, gepoch,
+                                    cta, warp, lane, tid);
                 } else {
                     float acc[8][Tile<BP>::BPL];
                     gemm_consume<BP, WT>(pipe, g, NCH1, warp, lane, acc);
@@ -863,13 +921,14 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
             if (is_producer) {
                 fence_proxy_async();
                 const uint8_t* a = a_cur + (size_t)(ACT_CTX / SM::CK) * SM::A_BYTES;     // starts at the context rows
-                PR::phase(pipe, g, NCH3, PRE3, rot3, lane, w_dec, a, a, 0);
+                PR::phase(pipe, g, NCH3, PRE3, rot3, lane, w_dec, a, a, 0, ab3);
                 g += NCH3;
                 PR::prefetch(pipe, g, NCH1, PRE1, rot1, lane, w_attn);         // next step's P1, across P4
             } else {
                 FT_RESET();
                 if constexpr (TC) {
-                    gemm_tc<BP, WT>(pipe, g, NCH3, tmem, acc_bar, acc_phase, red, z_s, warp, lane, tid);
+                    gemm_tc<BP, WT>(pipe, g, NCH3, tmem, acc_bar, acc_phase, red, z_s, p.zpart, p.ctrl + CTRL_GCNT, gepoch,
+                                    cta, warp, lane, tid);
                 } else {
                     float acc[8][Tile<BP>::BPL];
                     gemm_consume<BP, WT>(pipe, g, NCH3, warp, lane, acc);
@@ -1037,7 +1096,7 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
     if constexpr (TC) {
         umma::fence_before_sync();
         __syncthreads();
-        if (is_gemm && warp == 0) umma::tmem_dealloc(tmem, 32);
+        if (is_gemm && warp == 0) umma::tmem_dealloc(tmem, GN);
     }
 }
 
@@ -1093,7 +1152,7 @@ int dispatch_bp(int BP, const KParams& kp, int ncta, cudaStream_t stream) {
 }
 
 struct ScratchLayout {
-    size_t act16;
+    size_t act16, zpart;
     size_t act, pqpart, melpart, melctx, ctx_bj, attn_prev, attn_cum, wtmp, apart, ctrl, total;
     size_t zero_begin, zero_end;
 };
@@ -1118,6 +1177,7 @@ ScratchLayout scratch_layout(int B, int T) {
     L.ctx_bj = take((size_t)B * EMB * 4);
     L.wtmp = take((size_t)B * Tp * 4);
     L.apart = take((size_t)B * MAX_NS * APART * 4);
+    L.zpart = take(BP >= 32 ? (size_t)GEMM_CTAS * GS * ROWS_PER_CTA * BP * 4 : 0);
     L.total = off;
     return L;
 }
@@ -1184,6 +1244,7 @@ int decoder_run(const b200taco_handle* h, const DecoderArgs& a, cudaStream_t str
     kp.act = reinterpret_cast<float*>(base + L.act);
     kp.act16 = reinterpret_cast<__nv_bfloat16*>(base + L.act16);
     kp.w_attn_tc = h->w_attn_tc; kp.w_dec_tc = h->w_dec_tc;
+    kp.zpart = reinterpret_cast<float*>(base + L.zpart);
     kp.pqpart = reinterpret_cast<float*>(base + L.pqpart);
     kp.melpart = reinterpret_cast<float*>(base + L.melpart);
     kp.melctx = reinterpret_cast<float*>(base + L.melctx);

@@ -35,21 +35,27 @@ __global__ void pack_lstm_kernel(WT* dst, int K, const float* s0, int ld0, int o
     }
 }
 
-// tensor-core layout: dst[cta][chunk = k/64][UMMA K-major tile of 32 rows x 64 k], same k order / row order
+// tensor-core layout (split-K groups of 4 CTAs, decoder.cu gemm_tc): cta = 4*group + member owns, for the
+// group's 128 gate rows (n = unit_local*4 + gate, unit = 32*group + unit_local), the K quarter of `member`:
+// dst[cta][j = local chunk][UMMA K-major tile of 128 rows x 64 k], physical k = (member*K/4) + 64*j + kk
 __global__ void pack_lstm_tc_kernel(__nv_bfloat16* dst, int K, const float* s0, int ld0, int off0, int n0, const float* s1,
                                     int ld1, int off1, int n1, const float* s2, int ld2, int off2) {
-    const size_t total = (size_t)GEMM_CTAS * K * ROWS_PER_CTA;
+    const int KQ = K / 4;                                      // k per member
+    const size_t per_cta = (size_t)KQ * 128;
+    const size_t total = (size_t)GEMM_CTAS * per_cta;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int k = i % K;
-        const int r = (i / K) % ROWS_PER_CTA;
-        const int cta = i / ((size_t)ROWS_PER_CTA * K);
-        const int row = (r & 3) * RNN + cta * UNITS_PER_CTA + (r >> 2);
+        const int kl = i % KQ;                                 // k inside the member's quarter
+        const int n = (i / KQ) % 128;
+        const int cta = i / per_cta;
+        const int group = cta / 4, member = cta % 4;
+        const int k = member * KQ + kl;
+        const int row = (n & 3) * RNN + group * 32 + (n >> 2);
         float v;
         if (k < n0) v = s0[(size_t)row * ld0 + off0 + k];
         else if (k < n0 + n1) v = s1[(size_t)row * ld1 + off1 + (k - n0)];
         else v = s2[(size_t)row * ld2 + off2 + (k - n0 - n1)];
-        const size_t o = (size_t)cta * K * ROWS_PER_CTA + (size_t)(k / 64) * (64 * ROWS_PER_CTA) +
-                         ((((r >> 3) * 8 + ((k % 64) >> 3)) << 6) + ((r & 7) << 3) + (k & 7));
+        const size_t o = (size_t)cta * per_cta + (size_t)(kl / 64) * (64 * 128) +
+                         ((((n >> 3) * 8 + ((kl % 64) >> 3)) << 6) + ((n & 7) << 3) + (kl & 7));
         dst[o] = __float2bfloat16_rn(v);
     }
 }
