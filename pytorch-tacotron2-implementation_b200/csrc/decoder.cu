@@ -129,8 +129,9 @@ struct P2Scratch {
     static constexpr int WIN = 256;                               // 2 * WIN_LEN
     static constexpr int WIN_LEN = MAX_TEXT_LEN + 2 * TILE_POS + 32;
     static constexpr int E = WIN + 2 * WIN_LEN;                   // MAX_TEXT_LEN + TILE_POS
-    static constexpr int LOC = E + MAX_TEXT_LEN + TILE_POS;       // TILE_POS * 33
-    static constexpr int PM = LOC + TILE_POS * 33 + 8;            // TILE_POS * 128
+    static constexpr int LOC_LD = 36;                             // row stride of the location-feature tile (16 B aligned)
+    static constexpr int LOC = E + MAX_TEXT_LEN + TILE_POS;       // TILE_POS * LOC_LD
+    static constexpr int PM = LOC + TILE_POS * LOC_LD;            // TILE_POS * 128
     static constexpr int EPART = PM + TILE_POS * 128;             // TILE_POS * 4
     static constexpr int SC = EPART + TILE_POS * 4;               // MAX_NS scale factors + m,s
     static constexpr int TOTAL = SC + 64;
@@ -735,7 +736,7 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                 {
                     const int a = tid & 127, hf = tid >> 7;
                     const float* src = p.pqpart + ((size_t)b * GEMM_CTAS + hf * 64) * ATT_DIM + a;
-                    sc[P2Scratch::PQ + tid] = strided_sum_cg<64, 32>(src, ATT_DIM);
+                    sc[P2Scratch::PQ + tid] = strided_sum_cg<64, 64>(src, ATT_DIM);
                 }
                 consumer_sync();
                 FT(1);
@@ -767,40 +768,53 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                             }
                         }
 #pragma unroll
-                        for (int j = 0; j < 5; ++j) sc[P2Scratch::LOC + (tg * 5 + j) * 33 + f] = o5[j];
+                        for (int j = 0; j < 5; ++j) sc[P2Scratch::LOC + (tg * 5 + j) * P2Scratch::LOC_LD + f] = o5[j];
                     }
                     if (tile > 0) issue_pm_tile(tb);
                     cp_async_wait_all();
                     consumer_sync();
                 FT(2);
-                    // ---- energies (src/model.py:127-130): v . tanh(pq + pm + Wld loc); four positions
-                    // per thread at a time (independent FMA chains), result overwrites the pm tile
+                    // ---- energies (src/model.py:127-130): v . tanh(pq + pm + Wld loc); four positions per
+                    // thread at a time (independent FMA chains, 128-bit reads of the location features), then
+                    // the sum over the 128 attention dims: shuffle within the warp, 4 warp partials per position
                     const int npl = min(TILE_POS, n - tb);
                     {
-                        const int a = tid & 127, hf = tid >> 7;
+                        const int a = tid & 127, hf = tid >> 7, wq4 = (tid >> 5) & 3;
                         for (int pl0 = hf * 4; pl0 < npl; pl0 += 8) {
                             float x[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) x[j] = pq + sc[P2Scratch::PM + (pl0 + j) * ATT_DIM + a];
 #pragma unroll
-                            for (int f = 0; f < LOC_F; ++f) {
+                            for (int f4 = 0; f4 < LOC_F; f4 += 4) {
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) x[j] = fmaf(wld[f], sc[P2Scratch::LOC + (pl0 + j) * 33 + f], x[j]);
+                                for (int j = 0; j < 4; ++j) {
+                                    const float4 l = *reinterpret_cast<const float4*>(sc + P2Scratch::LOC + (pl0 + j) * P2Scratch::LOC_LD + f4);
+                                    x[j] = fmaf(wld[f4], l.x, x[j]);
+                                    x[j] = fmaf(wld[f4 + 1], l.y, x[j]);
+                                    x[j] = fmaf(wld[f4 + 2], l.z, x[j]);
+                                    x[j] = fmaf(wld[f4 + 3], l.w, x[j]);
+                                }
                             }
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) sc[P2Scratch::PM + (pl0 + j) * ATT_DIM + a] = vw * tanh_fast(x[j]);
+                            for (int j = 0; j < 4; ++j) x[j] = vw * tanh_fast(x[j]);
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) x[j] += __shfl_xor_sync(0xffffffffu, x[j], o);
+                            }
+                            if (lane == 0) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) sc[P2Scratch::EPART + (pl0 + j) * 4 + wq4] = x[j];
+                            }
                         }
                     }
                     consumer_sync();
                 FT(3);
-                    for (int pl = warp; pl < npl; pl += NW) {
-                        const float* row = sc + P2Scratch::PM + pl * ATT_DIM;
-                        float e = warp_sum((row[lane] + row[lane + 32]) + (row[lane + 64] + row[lane + 96]));
-                        if (lane == 0) {
-                            e = (e + v_s[128]) * v_s[129];
-                            if (t0 + tb + pl >= len) e = -1e9f;               // masked_fill, src/model.py:132
-                            sc[P2Scratch::E + tb + pl] = e;
-                        }
+                    if (tid < npl) {
+                        const float* ep = sc + P2Scratch::EPART + tid * 4;
+                        float e = ((ep[0] + ep[1]) + (ep[2] + ep[3]) + v_s[128]) * v_s[129];
+                        if (t0 + tb + tid >= len) e = -1e9f;                  // masked_fill, src/model.py:132
+                        sc[P2Scratch::E + tb + tid] = e;
                     }
                     consumer_sync();
                 FT(4);
@@ -828,8 +842,20 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                 float2 cacc = make_float2(0.f, 0.f);
                 {
                     const float2* mrow = reinterpret_cast<const float2*>(p.memory + ((size_t)b * T + t0) * EMB) + tid;
-#pragma unroll 8
-                    for (int i = 0; i < n; ++i) {
+                    int i = 0;
+                    for (; i + 20 <= n; i += 20) {                    // 20 rows (40 KB per CTA) in flight
+                        float2 mv[20];
+#pragma unroll
+                        for (int j = 0; j < 20; ++j) mv[j] = __ldg(mrow + (size_t)(i + j) * (EMB / 2));
+#pragma unroll
+                        for (int j = 0; j < 20; ++j) {
+                            const float ew = sc[P2Scratch::E + i + j];
+                            cacc.x = fmaf(ew, mv[j].x, cacc.x);
+                            cacc.y = fmaf(ew, mv[j].y, cacc.y);
+                        }
+                    }
+#pragma unroll 4
+                    for (; i < n; ++i) {
                         const float2 mv = __ldg(mrow + (size_t)i * (EMB / 2));
                         const float ew = sc[P2Scratch::E + i];
                         cacc.x = fmaf(ew, mv.x, cacc.x);
@@ -989,7 +1015,7 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                     const int o = tid & 127, ig = tid >> 7;
                     if (o < PROJ_OUT) {
                         const float* src = p.melpart + ((size_t)b * GEMM_CTAS + ig * 64) * PROJ_PAD + o;
-                        sc[ig * 128 + o] = strided_sum_cg<64>(src, PROJ_PAD);
+                        sc[ig * 128 + o] = strided_sum_cg<64, 64>(src, PROJ_PAD);
                     }
                 }
                 consumer_sync();
@@ -1022,12 +1048,12 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                     const float* wsrc = p.prenet1T + tid;
                     float acc = 0.f;
 #pragma unroll 1
-                    for (int o0 = 0; o0 < N_MELS; o0 += 16) {
-                        float w[16];
+                    for (int o0 = 0; o0 < N_MELS; o0 += 40) {
+                        float w[40];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) w[i] = __ldg(wsrc + (size_t)(o0 + i) * PRENET);
+                        for (int i = 0; i < 40; ++i) w[i] = __ldg(wsrc + (size_t)(o0 + i) * PRENET);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) acc = fmaf(w[i], sc[256 + o0 + i], acc);
+                        for (int i = 0; i < 40; ++i) acc = fmaf(w[i], sc[256 + o0 + i], acc);
                     }
                     sc[384 + tid] = fmaxf(acc, 0.f);
                 }
@@ -1039,12 +1065,12 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                     const float* x = sc + 384 + kg * kn;
                     float acc = 0.f;
 #pragma unroll 1
-                    for (int m0 = 0; m0 < kn; m0 += 16) {
-                        float w[16];
+                    for (int m0 = 0; m0 < kn; m0 += 32) {
+                        float w[32];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) w[i] = __ldg(wsrc + (size_t)(m0 + i) * PRENET);
+                        for (int i = 0; i < 32; ++i) w[i] = __ldg(wsrc + (size_t)(m0 + i) * PRENET);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) acc = fmaf(w[i], x[m0 + i], acc);
+                        for (int i = 0; i < 32; ++i) acc = fmaf(w[i], x[m0 + i], acc);
                     }
                     sc[640 + kg * RQ + nl] = acc;
                 }
