@@ -139,6 +139,21 @@ B200TACO_API int32_t b200taco_set_weight_dtype(b200taco_handle* h, int32_t dtype
 B200TACO_API int32_t b200taco_set_decoder_path(b200taco_handle* h, int32_t path);
 
 /*
+ * Kernel selection for the dense layers (encoder convolutions, BiLSTM input projection, memory layer,
+ * teacher-forced prenet, postnet).  The tensor-core kernel is a tcgen05 implicit GEMM with 3xTF32 operand
+ * splitting and fp32 accumulators in TMEM; the tensor core truncates when it accumulates, so its results sit
+ * ~1e-6 relative from round-to-nearest fp32 (measured).
+ *   AUTO (default): postnet and teacher-forced prenet on the tensor cores; the encoder and the memory layer,
+ *                   whose outputs are re-read by every one of up to 1000 recurrent decoder steps, on the fp32
+ *                   CUDA-core kernel.
+ *   TC            : every dense layer on the tensor cores (encoder with 8 rotating accumulators).
+ *   SIMT          : every dense layer on the CUDA cores.
+ * Replaces: nn.Conv1d / nn.Linear dispatch (src/model.py:25-39, :112, :166-171, :347-407).
+ */
+#define B200TACO_PATH_TC 2
+B200TACO_API int32_t b200taco_set_dense_path(b200taco_handle* h, int32_t path);
+
+/*
  * Repack the fp32 parameters into the kernels' layouts (bf16 fragment order for the
  * two decoder LSTMs, hi/lo bf16 planes for the GEMM operands, folded BatchNorm).  Call
  * after load_state_dict / optimizer.step (the host tracks param._version).

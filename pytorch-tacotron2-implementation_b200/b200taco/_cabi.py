@@ -63,6 +63,7 @@ SIGNATURES = {
     "b200taco_destroy": (C.c_int32, [C.c_void_p]),
     "b200taco_set_weight_dtype": (C.c_int32, [C.c_void_p, C.c_int32]),
     "b200taco_set_decoder_path": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "b200taco_set_dense_path": (C.c_int32, [C.c_void_p, C.c_int32]),
     "b200taco_pack_weights": (C.c_int32, [C.c_void_p, C.POINTER(Weights), C.c_void_p]),
     "b200taco_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     "b200taco_encoder_fwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,

@@ -63,7 +63,8 @@ def _hparams() -> _cabi.HParams:
 class Engine:
     """One per model instance per device; not thread-safe."""
 
-    def __init__(self, device: torch.device, weight_dtype: str = "bf16", decoder_path: str = "auto"):
+    def __init__(self, device: torch.device, weight_dtype: str = "bf16", decoder_path: str = "auto",
+                 dense_path: str = "auto"):
         if weight_dtype not in WEIGHT_DTYPES:
             raise B200TacoError(f"weight_dtype must be one of {sorted(WEIGHT_DTYPES)}, got {weight_dtype!r}")
         if device.type != "cuda":
@@ -79,6 +80,8 @@ class Engine:
         self.decoder_path = decoder_path
         check(self._lib.b200taco_set_decoder_path(self._h, {"auto": 0, "simt": 1}[decoder_path]),
               "b200taco_set_decoder_path")
+        self.dense_path = dense_path
+        check(self._lib.b200taco_set_dense_path(self._h, {"auto": 0, "simt": 1, "tc": 2}[dense_path]), "b200taco_set_dense_path")
         self._packed_sig = None
         self._ws = None
         self.max_batch = self._lib.b200taco_max_batch()

@@ -115,6 +115,9 @@ class Tacotron2(nn.Module):
         self.lstm_weight_dtype = "bf16"
         # "auto": tcgen05 tensor-core gate contractions when B >= 17 and bf16 weights; "simt": never
         self.decoder_path = "auto"
+        # dense layers: "auto" = postnet / teacher-forced prenet on tcgen05 (3xTF32), encoder on fp32 CUDA cores;
+        # "tc" = everything on tcgen05; "simt" = everything on CUDA cores (include/b200taco.h)
+        self.dense_path = "auto"
 
     # ------------------------------------------------------------------ plumbing
     def _tensors(self) -> dict:
@@ -126,8 +129,9 @@ class Tacotron2(nn.Module):
         dev = self.decoder.gate_layer.weight.device
         if (self._engine is None or self._engine.device != dev
                 or self._engine.weight_dtype != self.lstm_weight_dtype
-                or self._engine.decoder_path != self.decoder_path):
-            self._engine = Engine(dev, self.lstm_weight_dtype, self.decoder_path)
+                or self._engine.decoder_path != self.decoder_path
+                or self._engine.dense_path != self.dense_path):
+            self._engine = Engine(dev, self.lstm_weight_dtype, self.decoder_path, self.dense_path)
         self._engine.ensure_packed(self._tensors())
         return self._engine
 

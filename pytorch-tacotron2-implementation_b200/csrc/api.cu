@@ -172,6 +172,14 @@ B200TACO_API int32_t b200taco_set_decoder_path(b200taco_handle* h, int32_t path)
     return B200TACO_OK;
 }
 
+B200TACO_API int32_t b200taco_set_dense_path(b200taco_handle* h, int32_t path) {
+    TACO_REQUIRE(h != nullptr, B200TACO_ERR_INVALID, "null handle");
+    TACO_REQUIRE(path == B200TACO_PATH_AUTO || path == B200TACO_PATH_SIMT || path == B200TACO_PATH_TC, B200TACO_ERR_INVALID,
+                 "unknown dense path %d", path);
+    h->dense_path = path;
+    return B200TACO_OK;
+}
+
 B200TACO_API int32_t b200taco_pack_weights(b200taco_handle* h, const b200taco_weights* w, void* stream) {
     TACO_TRY(check_handle(h, false));
     TACO_REQUIRE(w != nullptr, B200TACO_ERR_INVALID, "null weights");
@@ -206,12 +214,12 @@ B200TACO_API int32_t b200taco_encoder_fwd(b200taco_handle* h, const int64_t* d_i
     float* src = ws.x0;
     float* dst = ws.x1;
     for (int i = 0; i < ENC_CONVS; ++i) {
-        TACO_TRY(conv1d_channels_last(src, EMB, h->enc_conv_w[i], h->enc_conv_scale[i], h->enc_conv_shift[i], nullptr, 0,
-                                      dst, EMB, n, T, EMB, EMB, ENC_KERNEL, ACT_RELU, st));
+        TACO_TRY(dense_layer(h, src, EMB, h->enc_conv_w[i], h->enc_conv_wtc[i], h->enc_conv_scale[i], h->enc_conv_shift[i], nullptr, 0,
+                                      dst, EMB, n, T, EMB, EMB, ENC_KERNEL, ACT_RELU, true, st));
         float* t = src; src = dst; dst = t;
     }
-    TACO_TRY(conv1d_channels_last(src, EMB, h->enc_lstm_wih, nullptr, h->enc_lstm_bias, nullptr, 0, ws.xproj, 8 * ENC_H, n,
-                                  n, EMB, 8 * ENC_H, 1, ACT_NONE, st));
+    TACO_TRY(dense_layer(h, src, EMB, h->enc_lstm_wih, h->enc_lstm_wih_tc, nullptr, h->enc_lstm_bias, nullptr, 0, ws.xproj, 8 * ENC_H, n,
+                                  n, EMB, 8 * ENC_H, 1, ACT_NONE, true, st));
     return bilstm_recurrence(h, ws.xproj, d_memory, B, T, st);
 }
 
@@ -223,18 +231,18 @@ static int run_decoder(b200taco_handle* h, int mode, const float* d_memory, cons
     TACO_REQUIRE(workspace_bytes >= ws.total, B200TACO_ERR_STATE, "decoder workspace too small: %zu < %zu", workspace_bytes,
                  ws.total);
     // processed_memory = memory_layer(memory), once per utterance (src/model.py:112)
-    TACO_TRY(conv1d_channels_last(d_memory, EMB, h->attn_memory_wT, nullptr, nullptr, nullptr, 0, ws.pm, ATT_DIM, B * T,
-                                  B * T, EMB, ATT_DIM, 1, ACT_NONE, st));
+    TACO_TRY(dense_layer(h, d_memory, EMB, h->attn_memory_wT, h->attn_memory_wtc, nullptr, nullptr, nullptr, 0, ws.pm, ATT_DIM, B * T,
+                                  B * T, EMB, ATT_DIM, 1, ACT_NONE, true, st));
     if (mode == 1) {
         // all prenet outputs at once: the inputs of every step are known (teacher forcing)
         const int n = S * B;
         tf_frames_kernel<<<(int)(((size_t)n * N_MELS + 255) / 256 > 2048 ? 2048 : ((size_t)n * N_MELS + 255) / 256), 256, 0,
                            st>>>(d_mel_targets, ws.frames, B, S);
         TACO_LAUNCHED();
-        TACO_TRY(conv1d_channels_last(ws.frames, N_MELS, h->prenet1T, nullptr, nullptr, nullptr, 0, ws.y1, PRENET, n, n,
-                                      N_MELS, PRENET, 1, ACT_RELU, st));
-        TACO_TRY(conv1d_channels_last(ws.y1, PRENET, h->prenet2T, nullptr, nullptr, nullptr, 0, ws.y2, PRENET, n, n, PRENET,
-                                      PRENET, 1, ACT_RELU, st));
+        TACO_TRY(dense_layer(h, ws.frames, N_MELS, h->prenet1T, h->prenet1_tc, nullptr, nullptr, nullptr, 0, ws.y1, PRENET, n, n,
+                                      N_MELS, PRENET, 1, ACT_RELU, false, st));
+        TACO_TRY(dense_layer(h, ws.y1, PRENET, h->prenet2T, h->prenet2_tc, nullptr, nullptr, nullptr, 0, ws.y2, PRENET, n, n, PRENET,
+                                      PRENET, 1, ACT_RELU, false, st));
         TACO_TRY(decoder_pack_p_all(h, ws.y2, ws.p_all, B, S, st));
     }
     DecoderArgs a{};
@@ -295,9 +303,9 @@ B200TACO_API int32_t b200taco_postnet_fwd(b200taco_handle* h, const float* d_mel
         const bool last = i == POST_CONVS - 1;
         const int c_out = last ? N_MELS : POST_DIM;
         float* dst = last ? d_mel_post : bufs[i & 1];
-        TACO_TRY(conv1d_channels_last(src, c_in, h->post_conv_w[i], h->post_conv_scale[i], h->post_conv_shift[i],
+        TACO_TRY(dense_layer(h, src, c_in, h->post_conv_w[i], h->post_conv_wtc[i], h->post_conv_scale[i], h->post_conv_shift[i],
                                       last ? d_mel_coarse : nullptr, N_MELS, dst, c_out, n, S, c_in, c_out, POST_KERNEL,
-                                      last ? ACT_NONE : ACT_TANH, st));
+                                      last ? ACT_NONE : ACT_TANH, false, st));
         src = dst;
         c_in = c_out;
     }

@@ -8,6 +8,7 @@ struct b200taco_handle {
     int num_sms = 0;
     int weight_dtype = 0;           // 0 = bf16 LSTM matrices (default), 1 = fp32
     int decoder_path = 0;           // 0 = auto (tcgen05 when batch >= 17 and bf16 weights), 1 = SIMT only
+    int dense_path = 0;             // 0 = tcgen05 3xTF32 dense layers (dense_tc.cu), 1 = fp32 SIMT (dense.cu)
     bool packed = false;
     const unsigned long long* last_profile = nullptr;   // device: phase timers of the last decoder launch
 
@@ -43,6 +44,13 @@ struct b200taco_handle {
     float* post_conv_w[5] = {};     // [5][ci][co]
     float* post_conv_scale[5] = {};
     float* post_conv_shift[5] = {};
+    // ---- the same dense weights pre-split into TF32 big/small planes, UMMA K-major tiles (dense_tc.cu) ----
+    float* enc_conv_wtc[3] = {};
+    float* enc_lstm_wih_tc = nullptr;
+    float* attn_memory_wtc = nullptr;
+    float* prenet1_tc = nullptr;
+    float* prenet2_tc = nullptr;
+    float* post_conv_wtc[5] = {};
 };
 
 namespace b200taco {
@@ -58,6 +66,14 @@ int conv1d_channels_last(const float* X, int ldx, const float* W, const float* s
                          int c_in, int c_out, int taps, int act, cudaStream_t stream);
 int embedding_gather(const int64_t* ids, const float* table, float* out, int n, cudaStream_t stream);
 int transpose_bct_to_btc(const float* in, float* out, int B, int C, int T, cudaStream_t stream);
+
+// dense_tc.cu : the same contract on the tensor cores (3xTF32); dense_layer picks the path of the handle
+bool dense_tc_supported(int c_in, int c_out, int ldx, int ldy);
+size_t dense_tc_weight_floats(int taps, int c_in, int c_out);
+int pack_dense_tc(float* dst, const float* w_tap_ci_co, int taps, int c_in, int c_out, cudaStream_t stream);
+int dense_layer(const b200taco_handle* h, const float* X, int ldx, const float* W, const float* Wtc, const float* scale,
+                const float* shift, const float* residual, int ldres, float* Y, int ldy, int n_rows, int seg_len, int c_in,
+                int c_out, int taps, int act, bool precise, cudaStream_t stream);
 
 // bilstm.cu
 int bilstm_recurrence(const b200taco_handle* h, const float* xproj, float* memory, int B, int T,

@@ -200,7 +200,20 @@ size_t carve(b200taco_handle* h, uint8_t* base, int weight_dtype) {
         pcs[i] = A.take<float>(co);
         pch[i] = A.take<float>(co);
     }
+    float *ecwt[3], *pcwt[5];
+    for (int i = 0; i < 3; ++i) ecwt[i] = A.take<float>(dense_tc_weight_floats(ENC_KERNEL, EMB, EMB));
+    float* wih_tc = A.take<float>(dense_tc_weight_floats(1, EMB, 8 * ENC_H));
+    float* mw_tc = A.take<float>(dense_tc_weight_floats(1, EMB, ATT_DIM));
+    float* p1_tc = A.take<float>(dense_tc_weight_floats(1, N_MELS, PRENET));
+    float* p2_tc = A.take<float>(dense_tc_weight_floats(1, PRENET, PRENET));
+    for (int i = 0; i < 5; ++i) {
+        const int ci = i == 0 ? N_MELS : POST_DIM, co = i == 4 ? N_MELS : POST_DIM;
+        pcwt[i] = A.take<float>(dense_tc_weight_floats(POST_KERNEL, ci, co));
+    }
     if (h && base) {
+        for (int i = 0; i < 3; ++i) h->enc_conv_wtc[i] = ecwt[i];
+        for (int i = 0; i < 5; ++i) h->post_conv_wtc[i] = pcwt[i];
+        h->enc_lstm_wih_tc = wih_tc; h->attn_memory_wtc = mw_tc; h->prenet1_tc = p1_tc; h->prenet2_tc = p2_tc;
         h->w_attn_tc = weight_dtype == 0 ? w_attn_tc : nullptr;
         h->w_dec_tc = weight_dtype == 0 ? w_dec_tc : nullptr;
         h->w_attn = w_attn; h->w_dec = w_dec; h->bias_attn = bias_attn; h->bias_dec = bias_dec;
@@ -311,6 +324,17 @@ int pack_weights(b200taco_handle* h, const b200taco_weights* w, cudaStream_t st)
         pack_bn_kernel<<<2, 256, 0, st>>>(h->post_conv_scale[i], h->post_conv_shift[i], w->post_conv_b[i], w->post_bn_w[i],
                                           w->post_bn_b[i], w->post_bn_mean[i], w->post_bn_var[i], co);
         TACO_LAUNCHED();
+    }
+    // ---- tensor-core copies of the dense weights (TF32 big/small planes)
+    for (int i = 0; i < 3; ++i)
+        if (int e = pack_dense_tc(h->enc_conv_wtc[i], h->enc_conv_w[i], ENC_KERNEL, EMB, EMB, st)) return e;
+    if (int e = pack_dense_tc(h->enc_lstm_wih_tc, h->enc_lstm_wih, 1, EMB, 8 * ENC_H, st)) return e;
+    if (int e = pack_dense_tc(h->attn_memory_wtc, h->attn_memory_wT, 1, EMB, ATT_DIM, st)) return e;
+    if (int e = pack_dense_tc(h->prenet1_tc, h->prenet1T, 1, N_MELS, PRENET, st)) return e;
+    if (int e = pack_dense_tc(h->prenet2_tc, h->prenet2T, 1, PRENET, PRENET, st)) return e;
+    for (int i = 0; i < 5; ++i) {
+        const int ci = i == 0 ? N_MELS : POST_DIM, co = i == 4 ? N_MELS : POST_DIM;
+        if (int e = pack_dense_tc(h->post_conv_wtc[i], h->post_conv_w[i], POST_KERNEL, ci, co, st)) return e;
     }
     h->packed = true;
     return B200TACO_OK;

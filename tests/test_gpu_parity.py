@@ -62,6 +62,32 @@ def test_postnet_golden():
     assert util.maxdiff(resid, util.golden("postnet_b2_s37")["residual"]) <= 1e-5
 
 
+@pytest.mark.parametrize("dense_path", ["auto", "simt", "tc"])
+def test_dense_paths_golden_and_large(dense_path):
+    """Both dense-layer paths (tcgen05 3xTF32 / fp32 SIMT) against the reference fixtures, then at BASELINE
+    C2 size against the CPU oracle (encoder B=32 x T=150; postnet 32 x 600 frames)."""
+    sd = util.weights()
+    m = Tacotron2().eval()
+    m.load_state_dict(sd)
+    m.dense_path = dense_path
+    m = m.to("cuda:0")
+    eng = m._get_engine()
+    ids = synth.phoneme_ids(3, 19, seed=5).cuda()
+    # tensor-core accumulation truncates: ~1e-6 relative instead of fp32 round-to-nearest (include/b200taco.h)
+    tol_mem = 4e-6 if dense_path == "tc" else 2e-6
+    assert util.maxdiff(eng.encoder(ids).cpu(), util.golden("encoder_b3_t19")["memory"]) <= tol_mem
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 80, 37, generator=g).transpose(1, 2).contiguous().cuda()
+    resid = (eng.postnet(x) - x).transpose(1, 2).cpu()
+    assert util.maxdiff(resid, util.golden("postnet_b2_s37")["residual"]) <= 1e-5
+    ids = synth.phoneme_ids(32, 150, seed=9)
+    assert util.maxdiff(eng.encoder(ids.cuda()).cpu(), O.encoder(sd, ids)) <= tol_mem
+    g = torch.Generator().manual_seed(12)
+    mel = torch.randn(32, 600, 80, generator=g) * 2 - 5
+    ref = mel + O.postnet(sd, mel.transpose(1, 2)).transpose(1, 2)
+    assert util.maxdiff(eng.postnet(mel.cuda()).cpu(), ref) <= 2e-5          # on |mel| up to ~12
+
+
 @pytest.mark.parametrize("name,kind,bf16,wdt", [("c1_default", "default", False, "fp32"),
                                                 ("c1_default_bf16", "default", True, "bf16"),
                                                 ("c1_stress_bf16", "stress", True, "bf16"),
