@@ -75,6 +75,9 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.t.start()
+            t_end = time.time() + 3.0
+            while not self.lines and time.time() < t_end:      # first sample = nvidia-smi is up
+                time.sleep(0.01)
         except OSError:
             self.proc = None
 
@@ -133,15 +136,18 @@ def run_b200(args, rank, world, local_rank):
 
     def step_resident():
         """value: inputs resident in HBM; returns (frames, decoder-kernel event pair)."""
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record()
         flush.zero_()
+        ev[1].record()
         mem = eng.encoder(ids_dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        ev[2].record()
         coarse, gate, align, lengths, S = eng.decoder_infer(mem, CAP, 0.5, STOP_PER_UTTERANCE, sync=False)
-        e1.record()
+        ev[3].record()
         S = int(S.item())
         post = eng.postnet(coarse[:, :S].contiguous())
-        return lengths, S, (e0, e1), post
+        ev[4].record()
+        return lengths, S, ev, post
 
     def step_e2e():
         flush.zero_()
@@ -158,11 +164,13 @@ def run_b200(args, rank, world, local_rank):
         torch.cuda.synchronize(dev)
 
     # ---------------- value (device resident) ----------------
+    # the sampler starts before the warm-up: nvidia-smi's own start-up stalls CUDA calls of this process for
+    # ~20 ms (measured), which must not land inside the timed region; its samples cover warm-up + timed steps
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_resident()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     eng.launch_count(reset=True)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
@@ -177,7 +185,9 @@ def run_b200(args, rank, world, local_rank):
     launches = eng.launch_count()
     clocks = sampler.stop()
     ms = t0.elapsed_time(t1)
-    dec_ms = sum(a.elapsed_time(b) for a, b in dec_events)
+    dec_ms = sum(ev[2].elapsed_time(ev[3]) for ev in dec_events)
+    stages_ms = {n: sum(ev[i].elapsed_time(ev[i + 1]) for ev in dec_events) / args.steps
+                 for i, n in enumerate(("l2_flush", "encoder", "decoder", "postnet"))}
 
     # ---------------- e2e (host buffers, public API) ----------------
     for _ in range(max(1, args.warmup // 2)):
@@ -217,6 +227,7 @@ def run_b200(args, rank, world, local_rank):
             "e2e": {"value": e2e_frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": ids_host.numel() * 8,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
+            "stages_ms": stages_ms,
             "clocks": clocks,
             "roofline": {"kernel": "decoder_kernel<32,bf16> (persistent, one launch per batch)", "bound": "hbm",
                          "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
@@ -312,7 +323,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
