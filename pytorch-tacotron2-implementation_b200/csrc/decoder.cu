@@ -141,9 +141,11 @@ static_assert(P2Scratch::TOTAL * 4 <= 48 * 1024 && 128 * 33 * 4 <= 48 * 1024, "P
 __device__ __forceinline__ void spin_fail() { __trap(); }
 
 #ifdef TACO_PROFILE_FINE
+#define TACO_FINE_ARGS t_fine, t_flast
 #define FT_RESET() do { if (timing) t_flast = global_timer_ns(); } while (0)
 #define FT(n) do { if (timing) { const unsigned long long _n = global_timer_ns(); t_fine[n] += _n - t_flast; t_flast = _n; } } while (0)
 #else
+#define TACO_FINE_ARGS nullptr, t_last
 #define FT_RESET()
 #define FT(n)
 #endif
@@ -203,6 +205,21 @@ __device__ __forceinline__ uint32_t atom_add_acq_rel_gpu(uint32_t* p, uint32_t v
 }
 
 __device__ __forceinline__ void consumer_sync() { named_bar_sync(1, NTC); }
+
+// where in the attention phase the background weight streaming of the tensor-core kernel may start:
+// 0 = after the first loads, 1 = after the energies, 2 = after the context partial
+#ifndef TACO_SIG_POINT
+#define TACO_SIG_POINT 2
+#endif
+
+// CTA-local signal in shared memory (written by consumer thread 0, polled by the producer warp)
+__device__ __forceinline__ void wait_signal(const int* flag, int value) {
+    const volatile int* f = flag;
+    const uint64_t t0 = global_timer_ns();
+    while (*f < value) {
+        if (global_timer_ns() - t0 > SPIN_TIMEOUT_NS) spin_fail();
+    }
+}
 
 template <typename WT>
 __device__ __forceinline__ void load_w8(const WT* p, float (&w)[8]);
@@ -543,6 +560,384 @@ __device__ __forceinline__ void gemm_tc(const Pipe& pipe, uint32_t& g, int nchun
 }
 
 // ---------------------------------------------------------------------------------------
+// P2: location-sensitive attention (src/model.py:117-148), consumer warps of every CTA.  One work item per
+// (utterance, slice of encoder positions); partial softmax/context per slice, the last slice to arrive
+// (atomic ticket) merges them - no extra grid barrier.
+template <int BP, bool TC>
+__device__ __forceinline__ void attention_phase(const KParams& p, float* red, const float* wld_s, const float* wloc_s,
+                                                const float* v_s, int* misc_s, int cur, int out_idx, int cta, int ncta,
+                                                int tid, int warp, int lane, float* act_cur, __nv_bfloat16* act16_cur,
+                                                bool timing, unsigned long long* t_fine, unsigned long long& t_flast,
+                                                volatile int* sig = nullptr, int sig_val = 0) {
+    // sig: set to sig_val once this CTA's latency-critical loads (pq partials, windows, first pm tile) have landed;
+    // the tensor-core kernel's producer warp starts its background weight streaming only then
+    const int B = p.B, T = p.T, prv = cur ^ 1;
+    (void)timing; (void)t_fine; (void)t_flast; (void)act_cur; (void)act16_cur;
+    float* sc = red;
+    const int NS = p.NS, SL = p.SL;
+    const float* prev_in = p.attn_prev + (size_t)prv * B * p.Tp;
+    const float* cum_in = p.attn_cum + (size_t)prv * B * p.Tp;
+    float* prev_out = p.attn_prev + (size_t)cur * B * p.Tp;
+    float* cum_out = p.attn_cum + (size_t)cur * B * p.Tp;
+    FT_RESET();
+    for (int item = cta; item < B * NS; item += ncta) {
+        const int b = item / NS, sl = item % NS;
+        const int t0 = sl * SL, t1 = min(T, t0 + SL), n = max(0, t1 - t0);
+        const int len = p.text_lengths ? (int)p.text_lengths[b] : T;
+        consumer_sync();   // previous item's scratch is free
+        const int ntiles = (n + TILE_POS - 1) / TILE_POS;
+        // processed-memory tile 0: asynchronous copy, overlapped with the loads below
+        auto issue_pm_tile = [&](int tb) {
+            const int rows = min(TILE_POS, n - tb);
+            const float* src = p.pm + ((size_t)b * T + t0 + tb) * ATT_DIM;
+            for (int i = tid; i < rows * (ATT_DIM / 4); i += NTC) cp_async16(sc + P2Scratch::PM + i * 4, src + i * 4);
+        };
+        issue_pm_tile(0);
+        // previous / cumulative attention windows with a 15-position halo, zero padded
+        const int wlen = ntiles * TILE_POS + LOC_K - 1 + 4;
+        for (int i = tid; i < wlen; i += NTC) {
+            const int t = t0 - (LOC_K - 1) / 2 + i;
+            const bool ok = t >= 0 && t < T;
+            sc[P2Scratch::WIN + i] = ok ? __ldcg(prev_in + (size_t)b * p.Tp + t) : 0.f;
+            sc[P2Scratch::WIN + P2Scratch::WIN_LEN + i] = ok ? __ldcg(cum_in + (size_t)b * p.Tp + t) : 0.f;
+        }
+        // processed query = sum of the 128 per-CTA partials
+        {
+            const int a = tid & 127, hf = tid >> 7;
+            const float* src = p.pqpart + ((size_t)b * GEMM_CTAS + hf * 64) * ATT_DIM + a;
+            sc[P2Scratch::PQ + tid] = strided_sum_cg<64, 64>(src, ATT_DIM);
+        }
+        consumer_sync();
+        if (TACO_SIG_POINT == 0 && sig != nullptr && tid == 0) *sig = sig_val;
+        FT(1);
+        float wld[LOC_F];
+        {
+            const int a = tid & 127;
+#pragma unroll
+            for (int f = 0; f < LOC_F; ++f) wld[f] = wld_s[f * ATT_DIM + a];
+        }
+        const float pq = sc[P2Scratch::PQ + (tid & 127)] + sc[P2Scratch::PQ + 128 + (tid & 127)];
+        const float vw = v_s[tid & 127];
+        for (int tile = 0; tile < ntiles; ++tile) {
+            const int tb = tile * TILE_POS;          // offset inside the slice
+            // ---- location conv (src/model.py:125-126): 32 filters x (2 x 31 taps)
+            {
+                const int f = tid & 31, tg = tid >> 5;
+                float o5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    float x[LOC_K + 4];
+                    const float* wsrc = sc + P2Scratch::WIN + c * P2Scratch::WIN_LEN + tb + tg * 5;
+#pragma unroll
+                    for (int i = 0; i < LOC_K + 4; ++i) x[i] = wsrc[i];
+#pragma unroll
+                    for (int k = 0; k < LOC_K; ++k) {
+                        const float w = wloc_s[f * 63 + c * LOC_K + k];
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) o5[j] = fmaf(w, x[k + j], o5[j]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 5; ++j) sc[P2Scratch::LOC + (tg * 5 + j) * P2Scratch::LOC_LD + f] = o5[j];
+            }
+            if (tile > 0) issue_pm_tile(tb);
+            cp_async_wait_all();
+            consumer_sync();
+        FT(2);
+            // ---- energies (src/model.py:127-130): v . tanh(pq + pm + Wld loc); four positions per
+            // thread at a time (independent FMA chains, 128-bit reads of the location features), then
+            // the sum over the 128 attention dims: shuffle within the warp, 4 warp partials per position
+            const int npl = min(TILE_POS, n - tb);
+            {
+                const int a = tid & 127, hf = tid >> 7, wq4 = (tid >> 5) & 3;
+                for (int pl0 = hf * 4; pl0 < npl; pl0 += 8) {
+                    float x[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) x[j] = pq + sc[P2Scratch::PM + (pl0 + j) * ATT_DIM + a];
+#pragma unroll
+                    for (int f4 = 0; f4 < LOC_F; f4 += 4) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 l = *reinterpret_cast<const float4*>(sc + P2Scratch::LOC + (pl0 + j) * P2Scratch::LOC_LD + f4);
+                            x[j] = fmaf(wld[f4], l.x, x[j]);
+                            x[j] = fmaf(wld[f4 + 1], l.y, x[j]);
+                            x[j] = fmaf(wld[f4 + 2], l.z, x[j]);
+                            x[j] = fmaf(wld[f4 + 3], l.w, x[j]);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) x[j] = vw * tanh_fast(x[j]);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) x[j] += __shfl_xor_sync(0xffffffffu, x[j], o);
+                    }
+                    if (lane == 0) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) sc[P2Scratch::EPART + (pl0 + j) * 4 + wq4] = x[j];
+                    }
+                }
+            }
+            consumer_sync();
+        FT(3);
+            if (tid < npl) {
+                const float* ep = sc + P2Scratch::EPART + tid * 4;
+                float e = ((ep[0] + ep[1]) + (ep[2] + ep[3]) + v_s[128]) * v_s[129];
+                if (t0 + tb + tid >= len) e = -1e9f;                  // masked_fill, src/model.py:132
+                sc[P2Scratch::E + tb + tid] = e;
+            }
+            consumer_sync();
+        FT(4);
+        }
+        // ---- slice-local softmax statistics (warp 0) ----
+        if (warp == 0) {
+            float m = -INFINITY;
+            for (int i = lane; i < n; i += 32) m = fmaxf(m, sc[P2Scratch::E + i]);
+            m = warp_max(m);
+            float ssum = 0.f;
+            for (int i = lane; i < n; i += 32) {
+                const float ew = expf(sc[P2Scratch::E + i] - m);
+                sc[P2Scratch::E + i] = ew;
+                ssum += ew;
+            }
+            ssum = warp_sum(ssum);
+            if (lane == 0) {
+                sc[P2Scratch::SC + 32] = n > 0 ? m : -INFINITY;
+                sc[P2Scratch::SC + 33] = ssum;
+            }
+        }
+        consumer_sync();
+        if (TACO_SIG_POINT == 1 && sig != nullptr && tid == 0) *sig = sig_val;
+        FT(5);
+        // ---- slice-local un-normalised context: sum_t ew[t] * memory[b][t][:] ----
+        float2 cacc = make_float2(0.f, 0.f);
+        {
+            const float2* mrow = reinterpret_cast<const float2*>(p.memory + ((size_t)b * T + t0) * EMB) + tid;
+            int i = 0;
+            for (; i + 20 <= n; i += 20) {                    // 20 rows (40 KB per CTA) in flight
+                float2 mv[20];
+#pragma unroll
+                for (int j = 0; j < 20; ++j) mv[j] = __ldg(mrow + (size_t)(i + j) * (EMB / 2));
+#pragma unroll
+                for (int j = 0; j < 20; ++j) {
+                    const float ew = sc[P2Scratch::E + i + j];
+                    cacc.x = fmaf(ew, mv[j].x, cacc.x);
+                    cacc.y = fmaf(ew, mv[j].y, cacc.y);
+                }
+            }
+#pragma unroll 4
+            for (; i < n; ++i) {
+                const float2 mv = __ldg(mrow + (size_t)i * (EMB / 2));
+                const float ew = sc[P2Scratch::E + i];
+                cacc.x = fmaf(ew, mv.x, cacc.x);
+                cacc.y = fmaf(ew, mv.y, cacc.y);
+            }
+        }
+        if (TACO_SIG_POINT == 2 && sig != nullptr && tid == 0) *sig = sig_val;
+        float* part = p.apart + ((size_t)b * MAX_NS + sl) * APART;
+        if (NS > 1) {
+            reinterpret_cast<float2*>(part + 4)[tid] = cacc;
+            if (tid == 0) { part[0] = sc[P2Scratch::SC + 32]; part[1] = sc[P2Scratch::SC + 33]; }
+            for (int i = tid; i < n; i += NTC) p.wtmp[(size_t)b * p.Tp + t0 + i] = sc[P2Scratch::E + i];
+            consumer_sync();
+            if (tid == 0) {
+                // release: this CTA's partials (ordered by the bar.sync above); acquire: the others'
+                const uint32_t ticket = atom_add_acq_rel_gpu(p.ctrl + CTRL_TICKETS + b, 1u);
+                misc_s[0] = (ticket % (uint32_t)NS) == (uint32_t)(NS - 1);
+            }
+            consumer_sync();
+        FT(6);
+            if (!misc_s[0]) continue;
+            // last slice of this utterance: merge
+            if (tid < 32) {
+                float m = -INFINITY;
+                if (tid < NS) m = __ldcg(p.apart + ((size_t)b * MAX_NS + tid) * APART);
+                const float M = warp_max(m);
+                float scale = 0.f, ssum = 0.f;
+                if (tid < NS) {
+                    scale = expf(m - M);
+                    ssum = scale * __ldcg(p.apart + ((size_t)b * MAX_NS + tid) * APART + 1);
+                }
+                ssum = warp_sum(ssum);
+                if (tid < NS) sc[P2Scratch::SC + tid] = scale;
+                if (tid == 0) sc[P2Scratch::SC + 33] = ssum;
+            }
+            consumer_sync();
+        FT(7);
+            cacc = make_float2(0.f, 0.f);
+            {
+                float2 cv[MAX_NS];
+#pragma unroll
+                for (int q = 0; q < MAX_NS; ++q)
+                    cv[q] = q < NS ? __ldcg(reinterpret_cast<const float2*>(
+                                                p.apart + ((size_t)b * MAX_NS + q) * APART + 4) + tid)
+                                   : make_float2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < MAX_NS; ++q) {
+                    const float scale = q < NS ? sc[P2Scratch::SC + q] : 0.f;
+                    cacc.x = fmaf(scale, cv[q].x, cacc.x);
+                    cacc.y = fmaf(scale, cv[q].y, cacc.y);
+                }
+            }
+        } else {
+            if (tid == 0) sc[P2Scratch::SC + 0] = 1.f;
+            consumer_sync();
+        }
+        const float S = sc[P2Scratch::SC + 33];
+        cacc.x = cacc.x / S;
+        cacc.y = cacc.y / S;
+        // context -> act (column b) and the utterance-major copy used by the projections
+        if constexpr (TC) {
+            __nv_bfloat16 hx, lx, hy, ly;
+            umma::split_bf16(cacc.x, hx, lx);
+            umma::split_bf16(cacc.y, hy, ly);
+            *reinterpret_cast<__nv_bfloat162*>(act16_cur + act16_off<BP>(b, ACT_CTX + 2 * tid)) = __nv_bfloat162(hx, hy);
+            *reinterpret_cast<__nv_bfloat162*>(act16_cur + act16_off<BP>(BP + b, ACT_CTX + 2 * tid)) = __nv_bfloat162(lx, ly);
+        } else {
+            act_cur[(size_t)(ACT_CTX + 2 * tid) * BP + b] = cacc.x;
+            act_cur[(size_t)(ACT_CTX + 2 * tid + 1) * BP + b] = cacc.y;
+        }
+        reinterpret_cast<float2*>(p.ctx_bj + (size_t)b * EMB)[tid] = cacc;
+        // attention weights: alignment output, prev, cum (src/model.py:142-145)
+        for (int t = tid; t < T; t += NTC) {
+            float ew;
+            if (NS > 1) ew = __ldcg(p.wtmp + (size_t)b * p.Tp + t) * sc[P2Scratch::SC + t / SL];
+            else ew = sc[P2Scratch::E + t];
+            const float w = ew / S;
+            prev_out[(size_t)b * p.Tp + t] = w;
+            cum_out[(size_t)b * p.Tp + t] = __ldcg(cum_in + (size_t)b * p.Tp + t) + w;
+            if (out_idx >= 0) p.align[((size_t)out_idx * B + b) * T + t] = w;
+        }
+        FT(8);
+    }
+    if (sig != nullptr && tid == 0) *sig = sig_val;       // CTAs without a work item
+}
+
+// P3 on the spare CTAs: context part of the projections + bias: melctx[b][o] for this CTA's rows o
+// (weights cached in shared memory at kernel start); one warp per utterance at a time.
+__device__ __forceinline__ void spare_melctx(const KParams& p, const uint8_t* stage_area, int cta, int ncta, int warp,
+                                             int lane) {
+    const int B = p.B;
+    const int nspare = ncta - GEMM_CTAS, sidx = cta - GEMM_CTAS;
+    const int rows_per = (PROJ_OUT + nspare - 1) / nspare;            // <= SPARE_ROWS
+    const int o0 = sidx * rows_per, nrow = max(0, min(PROJ_OUT, o0 + rows_per) - o0);
+    const float* wsm = reinterpret_cast<const float*>(stage_area);   // [rows][512], staged at kernel start
+    for (int b = warp; b < B && nrow > 0; b += NW) {
+        float4 c4[4];
+        const float4* csrc = reinterpret_cast<const float4*>(p.ctx_bj + (size_t)b * EMB) + lane * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c4[i] = __ldcg(csrc + i);
+        for (int r = 0; r < nrow; ++r) {
+            const float4* w4 = reinterpret_cast<const float4*>(wsm + r * EMB) + lane * 4;
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 w = w4[i];
+                acc = fmaf(w.x, c4[i].x, acc); acc = fmaf(w.y, c4[i].y, acc);
+                acc = fmaf(w.z, c4[i].z, acc); acc = fmaf(w.w, c4[i].w, acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) p.melctx[(size_t)b * PROJ_PAD + o0 + r] = acc + __ldg(p.proj_bias + o0 + r);
+        }
+    }
+}
+
+// P4: per utterance: sum projection partials -> mel frame, gate logit, stop rule (src/model.py:327 /
+// train.py:71-79), prenet of the next input frame (src/model.py:166-171).  Consumer warps of every CTA.
+template <int BP, bool TC>
+__device__ __forceinline__ void projection_phase(const KParams& p, float* red, bool tf, int out_idx, int cta, int ncta,
+                                                 int tid, float* act_cur, __nv_bfloat16* act16_cur,
+                                                 volatile int* sig = nullptr, int sig_val = 0) {
+    const int B = p.B;
+    (void)act_cur; (void)act16_cur;
+    float* sc = red;
+    const int NQ = p.NQ, RQ = PRENET / NQ;
+    for (int item = cta; item < B * NQ; item += ncta) {
+        const int b = item / NQ, q = item % NQ;
+        consumer_sync();
+        {
+            const int o = tid & 127, ig = tid >> 7;
+            if (o < PROJ_OUT) {
+                const float* src = p.melpart + ((size_t)b * GEMM_CTAS + ig * 64) * PROJ_PAD + o;
+                sc[ig * 128 + o] = strided_sum_cg<64, 64>(src, PROJ_PAD);
+            }
+        }
+        consumer_sync();
+        if (sig != nullptr && tid == 0) *sig = sig_val;
+        if (tid < PROJ_OUT) {
+            const float v = sc[tid] + sc[128 + tid] + __ldcg(p.melctx + (size_t)b * PROJ_PAD + tid);
+            sc[256 + tid] = v;                                  // mel frame (0..79), gate logit (80)
+            if (q == 0 && out_idx >= 0) {
+                if (tid < N_MELS) p.mel[((size_t)b * p.max_steps + out_idx) * N_MELS + tid] = v;
+                else p.gate[(size_t)b * p.max_steps + out_idx] = v;
+            }
+            if (q == 0 && !tf && tid == N_MELS && out_idx >= 1) {
+                // stop rule: src/model.py:327 (batch-wide) or train.py:71-79 (per utterance)
+                const bool fired = sigmoid_acc(v) > p.thr;
+                if (fired) {
+                    if (p.stop_mode == B200TACO_STOP_BATCH_WIDE) {
+                        atomicExch(p.ctrl + CTRL_STOP, 1u);
+                    } else if (p.ctrl[CTRL_DONE + b] == 0u) {
+                        p.ctrl[CTRL_DONE + b] = 1u;
+                        p.ctrl[CTRL_LEN + b] = (uint32_t)(out_idx + 1);
+                        if (atomicAdd(p.ctrl + CTRL_FINISHED, 1u) + 1u == (uint32_t)B)
+                            atomicExch(p.ctrl + CTRL_STOP, 1u);
+                    }
+                }
+            }
+        }
+        if (tf) continue;
+        consumer_sync();
+        // prenet layer 1 (all 256 outputs in every quarter CTA), eval mode: no dropout (F4)
+        {
+            const float* wsrc = p.prenet1T + tid;
+            float acc = 0.f;
+#pragma unroll 1
+            for (int o0 = 0; o0 < N_MELS; o0 += 40) {
+                float w[40];
+#pragma unroll
+                for (int i = 0; i < 40; ++i) w[i] = __ldg(wsrc + (size_t)(o0 + i) * PRENET);
+#pragma unroll
+                for (int i = 0; i < 40; ++i) acc = fmaf(w[i], sc[256 + o0 + i], acc);
+            }
+            sc[384 + tid] = fmaxf(acc, 0.f);
+        }
+        consumer_sync();
+        // prenet layer 2: this CTA's RQ outputs, k split over NQ thread groups
+        {
+            const int nl = tid % RQ, kg = tid / RQ, kn = PRENET / NQ;
+            const float* wsrc = p.prenet2T + (size_t)(kg * kn) * PRENET + q * RQ + nl;
+            const float* x = sc + 384 + kg * kn;
+            float acc = 0.f;
+#pragma unroll 1
+            for (int m0 = 0; m0 < kn; m0 += 32) {
+                float w[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) w[i] = __ldg(wsrc + (size_t)(m0 + i) * PRENET);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc = fmaf(w[i], x[m0 + i], acc);
+            }
+            sc[640 + kg * RQ + nl] = acc;
+        }
+        consumer_sync();
+        if (tid < RQ) {
+            float v = 0.f;
+            for (int kg = 0; kg < NQ; ++kg) v += sc[640 + kg * RQ + tid];
+            v = fmaxf(v, 0.f);
+            if constexpr (TC) {
+                __nv_bfloat16 hi, lo;
+                umma::split_bf16(v, hi, lo);
+                act16_cur[act16_off<BP>(b, ACT_P + q * RQ + tid)] = hi;
+                act16_cur[act16_off<BP>(BP + b, ACT_P + q * RQ + tid)] = lo;
+            } else {
+                act_cur[(size_t)(ACT_P + q * RQ + tid) * BP + b] = v;
+            }
+        }
+    }
+    if (sig != nullptr && tid == 0) *sig = sig_val;       // CTAs without a work item
+}
+
+// ---------------------------------------------------------------------------------------
 template <int BP, typename WT, bool TC>
 __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
     using SM = Smem<BP, WT, TC>;
@@ -703,242 +1098,9 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
         stamp(0);
 
         // =============================== P2: attention ===============================
-        if (!is_producer) {
-            float* sc = red;
-            const int NS = p.NS, SL = p.SL;
-            const float* prev_in = p.attn_prev + (size_t)prv * B * p.Tp;
-            const float* cum_in = p.attn_cum + (size_t)prv * B * p.Tp;
-            float* prev_out = p.attn_prev + (size_t)cur * B * p.Tp;
-            float* cum_out = p.attn_cum + (size_t)cur * B * p.Tp;
-            FT_RESET();
-            for (int item = cta; item < B * NS; item += ncta) {
-                const int b = item / NS, sl = item % NS;
-                const int t0 = sl * SL, t1 = min(T, t0 + SL), n = max(0, t1 - t0);
-                const int len = p.text_lengths ? (int)p.text_lengths[b] : T;
-                consumer_sync();   // previous item's scratch is free
-                const int ntiles = (n + TILE_POS - 1) / TILE_POS;
-                // processed-memory tile 0: asynchronous copy, overlapped with the loads below
-                auto issue_pm_tile = [&](int tb) {
-                    const int rows = min(TILE_POS, n - tb);
-                    const float* src = p.pm + ((size_t)b * T + t0 + tb) * ATT_DIM;
-                    for (int i = tid; i < rows * (ATT_DIM / 4); i += NTC) cp_async16(sc + P2Scratch::PM + i * 4, src + i * 4);
-                };
-                issue_pm_tile(0);
-                // previous / cumulative attention windows with a 15-position halo, zero padded
-                const int wlen = ntiles * TILE_POS + LOC_K - 1 + 4;
-                for (int i = tid; i < wlen; i += NTC) {
-                    const int t = t0 - (LOC_K - 1) / 2 + i;
-                    const bool ok = t >= 0 && t < T;
-                    sc[P2Scratch::WIN + i] = ok ? __ldcg(prev_in + (size_t)b * p.Tp + t) : 0.f;
-                    sc[P2Scratch::WIN + P2Scratch::WIN_LEN + i] = ok ? __ldcg(cum_in + (size_t)b * p.Tp + t) : 0.f;
-                }
-                // processed query = sum of the 128 per-CTA partials
-                {
-                    const int a = tid & 127, hf = tid >> 7;
-                    const float* src = p.pqpart + ((size_t)b * GEMM_CTAS + hf * 64) * ATT_DIM + a;
-                    sc[P2Scratch::PQ + tid] = strided_sum_cg<64, 64>(src, ATT_DIM);
-                }
-                consumer_sync();
-                FT(1);
-                float wld[LOC_F];
-                {
-                    const int a = tid & 127;
-#pragma unroll
-                    for (int f = 0; f < LOC_F; ++f) wld[f] = wld_s[f * ATT_DIM + a];
-                }
-                const float pq = sc[P2Scratch::PQ + (tid & 127)] + sc[P2Scratch::PQ + 128 + (tid & 127)];
-                const float vw = v_s[tid & 127];
-                for (int tile = 0; tile < ntiles; ++tile) {
-                    const int tb = tile * TILE_POS;          // offset inside the slice
-                    // ---- location conv (src/model.py:125-126): 32 filters x (2 x 31 taps)
-                    {
-                        const int f = tid & 31, tg = tid >> 5;
-                        float o5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            float x[LOC_K + 4];
-                            const float* wsrc = sc + P2Scratch::WIN + c * P2Scratch::WIN_LEN + tb + tg * 5;
-#pragma unroll
-                            for (int i = 0; i < LOC_K + 4; ++i) x[i] = wsrc[i];
-#pragma unroll
-                            for (int k = 0; k < LOC_K; ++k) {
-                                const float w = wloc_s[f * 63 + c * LOC_K + k];
-#pragma unroll
-                                for (int j = 0; j < 5; ++j) o5[j] = fmaf(w, x[k + j], o5[j]);
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 5; ++j) sc[P2Scratch::LOC + (tg * 5 + j) * P2Scratch::LOC_LD + f] = o5[j];
-                    }
-                    if (tile > 0) issue_pm_tile(tb);
-                    cp_async_wait_all();
-                    consumer_sync();
-                FT(2);
-                    // ---- energies (src/model.py:127-130): v . tanh(pq + pm + Wld loc); four positions per
-                    // thread at a time (independent FMA chains, 128-bit reads of the location features), then
-                    // the sum over the 128 attention dims: shuffle within the warp, 4 warp partials per position
-                    const int npl = min(TILE_POS, n - tb);
-                    {
-                        const int a = tid & 127, hf = tid >> 7, wq4 = (tid >> 5) & 3;
-                        for (int pl0 = hf * 4; pl0 < npl; pl0 += 8) {
-                            float x[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) x[j] = pq + sc[P2Scratch::PM + (pl0 + j) * ATT_DIM + a];
-#pragma unroll
-                            for (int f4 = 0; f4 < LOC_F; f4 += 4) {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float4 l = *reinterpret_cast<const float4*>(sc + P2Scratch::LOC + (pl0 + j) * P2Scratch::LOC_LD + f4);
-                                    x[j] = fmaf(wld[f4], l.x, x[j]);
-                                    x[j] = fmaf(wld[f4 + 1], l.y, x[j]);
-                                    x[j] = fmaf(wld[f4 + 2], l.z, x[j]);
-                                    x[j] = fmaf(wld[f4 + 3], l.w, x[j]);
-                                }
-                            }
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) x[j] = vw * tanh_fast(x[j]);
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) x[j] += __shfl_xor_sync(0xffffffffu, x[j], o);
-                            }
-                            if (lane == 0) {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) sc[P2Scratch::EPART + (pl0 + j) * 4 + wq4] = x[j];
-                            }
-                        }
-                    }
-                    consumer_sync();
-                FT(3);
-                    if (tid < npl) {
-                        const float* ep = sc + P2Scratch::EPART + tid * 4;
-                        float e = ((ep[0] + ep[1]) + (ep[2] + ep[3]) + v_s[128]) * v_s[129];
-                        if (t0 + tb + tid >= len) e = -1e9f;                  // masked_fill, src/model.py:132
-                        sc[P2Scratch::E + tb + tid] = e;
-                    }
-                    consumer_sync();
-                FT(4);
-                }
-                // ---- slice-local softmax statistics (warp 0) ----
-                if (warp == 0) {
-                    float m = -INFINITY;
-                    for (int i = lane; i < n; i += 32) m = fmaxf(m, sc[P2Scratch::E + i]);
-                    m = warp_max(m);
-                    float ssum = 0.f;
-                    for (int i = lane; i < n; i += 32) {
-                        const float ew = expf(sc[P2Scratch::E + i] - m);
-                        sc[P2Scratch::E + i] = ew;
-                        ssum += ew;
-                    }
-                    ssum = warp_sum(ssum);
-                    if (lane == 0) {
-                        sc[P2Scratch::SC + 32] = n > 0 ? m : -INFINITY;
-                        sc[P2Scratch::SC + 33] = ssum;
-                    }
-                }
-                consumer_sync();
-                FT(5);
-                // ---- slice-local un-normalised context: sum_t ew[t] * memory[b][t][:] ----
-                float2 cacc = make_float2(0.f, 0.f);
-                {
-                    const float2* mrow = reinterpret_cast<const float2*>(p.memory + ((size_t)b * T + t0) * EMB) + tid;
-                    int i = 0;
-                    for (; i + 20 <= n; i += 20) {                    // 20 rows (40 KB per CTA) in flight
-                        float2 mv[20];
-#pragma unroll
-                        for (int j = 0; j < 20; ++j) mv[j] = __ldg(mrow + (size_t)(i + j) * (EMB / 2));
-#pragma unroll
-                        for (int j = 0; j < 20; ++j) {
-                            const float ew = sc[P2Scratch::E + i + j];
-                            cacc.x = fmaf(ew, mv[j].x, cacc.x);
-                            cacc.y = fmaf(ew, mv[j].y, cacc.y);
-                        }
-                    }
-#pragma unroll 4
-                    for (; i < n; ++i) {
-                        const float2 mv = __ldg(mrow + (size_t)i * (EMB / 2));
-                        const float ew = sc[P2Scratch::E + i];
-                        cacc.x = fmaf(ew, mv.x, cacc.x);
-                        cacc.y = fmaf(ew, mv.y, cacc.y);
-                    }
-                }
-                float* part = p.apart + ((size_t)b * MAX_NS + sl) * APART;
-                if (NS > 1) {
-                    reinterpret_cast<float2*>(part + 4)[tid] = cacc;
-                    if (tid == 0) { part[0] = sc[P2Scratch::SC + 32]; part[1] = sc[P2Scratch::SC + 33]; }
-                    for (int i = tid; i < n; i += NTC) p.wtmp[(size_t)b * p.Tp + t0 + i] = sc[P2Scratch::E + i];
-                    consumer_sync();
-                    if (tid == 0) {
-                        // release: this CTA's partials (ordered by the bar.sync above); acquire: the others'
-                        const uint32_t ticket = atom_add_acq_rel_gpu(p.ctrl + CTRL_TICKETS + b, 1u);
-                        misc_s[0] = (ticket % (uint32_t)NS) == (uint32_t)(NS - 1);
-                    }
-                    consumer_sync();
-                FT(6);
-                    if (!misc_s[0]) continue;
-                    // last slice of this utterance: merge
-                    if (tid < 32) {
-                        float m = -INFINITY;
-                        if (tid < NS) m = __ldcg(p.apart + ((size_t)b * MAX_NS + tid) * APART);
-                        const float M = warp_max(m);
-                        float scale = 0.f, ssum = 0.f;
-                        if (tid < NS) {
-                            scale = expf(m - M);
-                            ssum = scale * __ldcg(p.apart + ((size_t)b * MAX_NS + tid) * APART + 1);
-                        }
-                        ssum = warp_sum(ssum);
-                        if (tid < NS) sc[P2Scratch::SC + tid] = scale;
-                        if (tid == 0) sc[P2Scratch::SC + 33] = ssum;
-                    }
-                    consumer_sync();
-                FT(7);
-                    cacc = make_float2(0.f, 0.f);
-                    {
-                        float2 cv[MAX_NS];
-#pragma unroll
-                        for (int q = 0; q < MAX_NS; ++q)
-                            cv[q] = q < NS ? __ldcg(reinterpret_cast<const float2*>(
-                                                        p.apart + ((size_t)b * MAX_NS + q) * APART + 4) + tid)
-                                           : make_float2(0.f, 0.f);
-#pragma unroll
-                        for (int q = 0; q < MAX_NS; ++q) {
-                            const float scale = q < NS ? sc[P2Scratch::SC + q] : 0.f;
-                            cacc.x = fmaf(scale, cv[q].x, cacc.x);
-                            cacc.y = fmaf(scale, cv[q].y, cacc.y);
-                        }
-                    }
-                } else {
-                    if (tid == 0) sc[P2Scratch::SC + 0] = 1.f;
-                    consumer_sync();
-                }
-                const float S = sc[P2Scratch::SC + 33];
-                cacc.x = cacc.x / S;
-                cacc.y = cacc.y / S;
-                // context -> act (column b) and the utterance-major copy used by the projections
-                if constexpr (TC) {
-                    __nv_bfloat16 hx, lx, hy, ly;
-                    umma::split_bf16(cacc.x, hx, lx);
-                    umma::split_bf16(cacc.y, hy, ly);
-                    *reinterpret_cast<__nv_bfloat162*>(act16_cur + act16_off<BP>(b, ACT_CTX + 2 * tid)) = __nv_bfloat162(hx, hy);
-                    *reinterpret_cast<__nv_bfloat162*>(act16_cur + act16_off<BP>(BP + b, ACT_CTX + 2 * tid)) = __nv_bfloat162(lx, ly);
-                } else {
-                    act_cur[(size_t)(ACT_CTX + 2 * tid) * BP + b] = cacc.x;
-                    act_cur[(size_t)(ACT_CTX + 2 * tid + 1) * BP + b] = cacc.y;
-                }
-                reinterpret_cast<float2*>(p.ctx_bj + (size_t)b * EMB)[tid] = cacc;
-                // attention weights: alignment output, prev, cum (src/model.py:142-145)
-                for (int t = tid; t < T; t += NTC) {
-                    float ew;
-                    if (NS > 1) ew = __ldcg(p.wtmp + (size_t)b * p.Tp + t) * sc[P2Scratch::SC + t / SL];
-                    else ew = sc[P2Scratch::E + t];
-                    const float w = ew / S;
-                    prev_out[(size_t)b * p.Tp + t] = w;
-                    cum_out[(size_t)b * p.Tp + t] = __ldcg(cum_in + (size_t)b * p.Tp + t) + w;
-                    if (out_idx >= 0) p.align[((size_t)out_idx * B + b) * T + t] = w;
-                }
-                FT(8);
-            }
-        }
+        if (!is_producer)
+            attention_phase<BP, TC>(p, red, wld_s, wloc_s, v_s, misc_s, cur, out_idx, cta, ncta, tid, warp, lane, act_cur,
+                                    act16_cur, timing, TACO_FINE_ARGS);
         grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
         stamp(1);
 
@@ -976,120 +1138,13 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                 }
             }
         } else if (!is_producer) {
-            // spare CTAs: context part of the projections + bias: melctx[b][o] for this CTA's rows o
-            // (weights cached in shared memory at kernel start); one warp per utterance at a time.
-            const int nspare = ncta - GEMM_CTAS, sidx = cta - GEMM_CTAS;
-            const int rows_per = (PROJ_OUT + nspare - 1) / nspare;            // <= SPARE_ROWS
-            const int o0 = sidx * rows_per, nrow = max(0, min(PROJ_OUT, o0 + rows_per) - o0);
-            const float* wsm = reinterpret_cast<const float*>(pipe.stages);  // [SPARE_ROWS][512], stage area is unused here
-            for (int b = warp; b < B && nrow > 0; b += NW) {
-                float4 c4[4];
-                const float4* csrc = reinterpret_cast<const float4*>(p.ctx_bj + (size_t)b * EMB) + lane * 4;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) c4[i] = __ldcg(csrc + i);
-                for (int r = 0; r < nrow; ++r) {
-                    const float4* w4 = reinterpret_cast<const float4*>(wsm + r * EMB) + lane * 4;
-                    float acc = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 w = w4[i];
-                        acc = fmaf(w.x, c4[i].x, acc); acc = fmaf(w.y, c4[i].y, acc);
-                        acc = fmaf(w.z, c4[i].z, acc); acc = fmaf(w.w, c4[i].w, acc);
-                    }
-                    acc = warp_sum(acc);
-                    if (lane == 0) p.melctx[(size_t)b * PROJ_PAD + o0 + r] = acc + __ldg(p.proj_bias + o0 + r);
-                }
-            }
+            spare_melctx(p, pipe.stages, cta, ncta, warp, lane);
         }
         grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
         stamp(2);
 
         // =============================== P4: projection sums, stop rule, prenet ===============================
-        if (!is_producer) {
-            float* sc = red;
-            const int NQ = p.NQ, RQ = PRENET / NQ;
-            for (int item = cta; item < B * NQ; item += ncta) {
-                const int b = item / NQ, q = item % NQ;
-                consumer_sync();
-                {
-                    const int o = tid & 127, ig = tid >> 7;
-                    if (o < PROJ_OUT) {
-                        const float* src = p.melpart + ((size_t)b * GEMM_CTAS + ig * 64) * PROJ_PAD + o;
-                        sc[ig * 128 + o] = strided_sum_cg<64, 64>(src, PROJ_PAD);
-                    }
-                }
-                consumer_sync();
-                if (tid < PROJ_OUT) {
-                    const float v = sc[tid] + sc[128 + tid] + __ldcg(p.melctx + (size_t)b * PROJ_PAD + tid);
-                    sc[256 + tid] = v;                                  // mel frame (0..79), gate logit (80)
-                    if (q == 0 && out_idx >= 0) {
-                        if (tid < N_MELS) p.mel[((size_t)b * p.max_steps + out_idx) * N_MELS + tid] = v;
-                        else p.gate[(size_t)b * p.max_steps + out_idx] = v;
-                    }
-                    if (q == 0 && !tf && tid == N_MELS && out_idx >= 1) {
-                        // stop rule: src/model.py:327 (batch-wide) or train.py:71-79 (per utterance)
-                        const bool fired = sigmoid_acc(v) > p.thr;
-                        if (fired) {
-                            if (p.stop_mode == B200TACO_STOP_BATCH_WIDE) {
-                                atomicExch(p.ctrl + CTRL_STOP, 1u);
-                            } else if (p.ctrl[CTRL_DONE + b] == 0u) {
-                                p.ctrl[CTRL_DONE + b] = 1u;
-                                p.ctrl[CTRL_LEN + b] = (uint32_t)(out_idx + 1);
-                                if (atomicAdd(p.ctrl + CTRL_FINISHED, 1u) + 1u == (uint32_t)B)
-                                    atomicExch(p.ctrl + CTRL_STOP, 1u);
-                            }
-                        }
-                    }
-                }
-                if (tf) continue;
-                consumer_sync();
-                // prenet layer 1 (all 256 outputs in every quarter CTA), eval mode: no dropout (F4)
-                {
-                    const float* wsrc = p.prenet1T + tid;
-                    float acc = 0.f;
-#pragma unroll 1
-                    for (int o0 = 0; o0 < N_MELS; o0 += 40) {
-                        float w[40];
-#pragma unroll
-                        for (int i = 0; i < 40; ++i) w[i] = __ldg(wsrc + (size_t)(o0 + i) * PRENET);
-#pragma unroll
-                        for (int i = 0; i < 40; ++i) acc = fmaf(w[i], sc[256 + o0 + i], acc);
-                    }
-                    sc[384 + tid] = fmaxf(acc, 0.f);
-                }
-                consumer_sync();
-                // prenet layer 2: this CTA's RQ outputs, k split over NQ thread groups
-                {
-                    const int nl = tid % RQ, kg = tid / RQ, kn = PRENET / NQ;
-                    const float* wsrc = p.prenet2T + (size_t)(kg * kn) * PRENET + q * RQ + nl;
-                    const float* x = sc + 384 + kg * kn;
-                    float acc = 0.f;
-#pragma unroll 1
-                    for (int m0 = 0; m0 < kn; m0 += 32) {
-                        float w[32];
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) w[i] = __ldg(wsrc + (size_t)(m0 + i) * PRENET);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) acc = fmaf(w[i], x[m0 + i], acc);
-                    }
-                    sc[640 + kg * RQ + nl] = acc;
-                }
-                consumer_sync();
-                if (tid < RQ) {
-                    float v = 0.f;
-                    for (int kg = 0; kg < NQ; ++kg) v += sc[640 + kg * RQ + tid];
-                    v = fmaxf(v, 0.f);
-                    if constexpr (TC) {
-                        __nv_bfloat16 hi, lo;
-                        umma::split_bf16(v, hi, lo);
-                        act16_cur[act16_off<BP>(b, ACT_P + q * RQ + tid)] = hi;
-                        act16_cur[act16_off<BP>(BP + b, ACT_P + q * RQ + tid)] = lo;
-                    } else {
-                        act_cur[(size_t)(ACT_P + q * RQ + tid) * BP + b] = v;
-                    }
-                }
-            }
-        }
+        if (!is_producer) projection_phase<BP, TC>(p, red, tf, out_idx, cta, ncta, tid, act_cur, act16_cur);
         steps_done = s + 1;
         if (!tf) {
             grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
@@ -1136,6 +1191,416 @@ int launch(const KParams& kp, int ncta, cudaStream_t stream) {
     TACO_REQUIRE(per_sm >= 1, B200TACO_ERR_UNSUPPORTED, "decoder kernel does not fit on an SM (smem %d B)", SM::TOTAL);
     void* args[] = {const_cast<KParams*>(&kp)};
     TACO_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(ncta), dim3(NT), args, SM::TOTAL, stream));
+    launch_counter()++;
+    return B200TACO_OK;
+}
+
+
+// =======================================================================================================
+// Tensor-core decoder kernel (batch tile >= 32, bf16 weights): same four phases, but the gate contractions
+// are HOISTED.  Both LSTM pre-activations are sums over K ranges that become known at different barriers:
+//     attention LSTM (step t+1):  ah_t (after barrier 1 of step t) | ctx_t (after barrier 2) | p_{t+1} (after barrier 4)
+//     decoder LSTM   (step t)  :  dh_{t-1} (after barrier 3 of step t-1) | ah_t (after barrier 1) | ctx_t (after barrier 2)
+// The tcgen05 contraction needs no consumer warp (TMA producer warp + one MMA-issuing thread + TMEM), so every
+// K range is multiplied as soon as it exists, in the BACKGROUND of the attention / projection phases, into two
+// TMEM accumulators.  Only the last range of each contraction is on the critical path:
+//     phase A: 1 chunk (prenet rows)  -> attention LSTM epilogue        (was 7 chunks)
+//     phase C: 2 chunks (context rows) -> decoder LSTM epilogue          (was 10 chunks)
+// Split-K over groups of GS=4 CTAs as before, but every availability class is dealt evenly to the four members
+// (dims.cuh tc_*_act_chunk), so the critical chunks load in parallel.
+constexpr int NT_TC = NTC + 64;                 // + producer warp (8) + MMA warp (9)
+constexpr int TC_PRODUCER_WARP = NW, TC_MMA_WARP = NW + 1;
+
+template <int BP>
+struct TcPipe {
+    using SM = Smem<BP, __nv_bfloat16, true>;
+    static constexpr int STAGES = SM::NSTAGES;
+
+    // All 32 lanes of the producer warp call this (one issuing lane per stage, see Producer).  Issues the n chunks
+    // of one job at ring positions g0.. ; mode 0: weights + activations, 1: weights only (activations not ready
+    // yet), 2: activations only (weights went out earlier with mode 1).
+    __device__ static __forceinline__ void produce(const Pipe& pipe, uint32_t g0, int n, int mode, int lane,
+                                                   const __nv_bfloat16* wsrc, const uint8_t* abuf, int achunk0) {
+        int c = lane < STAGES ? (lane + STAGES - (int)(g0 % STAGES)) % STAGES : n;
+        const uint64_t t0 = global_timer_ns();
+        while (__any_sync(0xffffffffu, c < n)) {
+            if (c < n) {
+                const uint32_t g = g0 + c, stage = g % STAGES, parity = ((g / STAGES) & 1u) ^ 1u;
+                if (mode == 2 || mbar_test_wait(&pipe.empty[stage], parity)) {
+                    uint8_t* dst = pipe.stages + stage * SM::STAGE_BYTES;
+                    if (mode != 2) {
+                        mbar_arrive_expect_tx(&pipe.full[stage], SM::STAGE_BYTES);
+                        bulk_g2s(dst, wsrc + (size_t)c * TC_CK * GN, SM::W_BYTES, &pipe.full[stage]);
+                    }
+                    if (mode != 1)
+                        bulk_g2s(dst + SM::W_BYTES, abuf + (size_t)(achunk0 + c) * SM::A_BYTES, SM::A_BYTES, &pipe.full[stage]);
+                    c += STAGES;
+                } else if (global_timer_ns() - t0 > SPIN_TIMEOUT_NS) {
+                    spin_fail();
+                }
+            }
+        }
+    }
+
+    // MMA-issuing thread: D[acc] (+)= A[chunk] . W[chunk]^T for the n chunks at ring positions g..; fresh = the
+    // first MMA overwrites the accumulator.
+    __device__ static __forceinline__ void consume(const Pipe& pipe, uint32_t& g, int n, uint32_t acc, bool fresh) {
+        constexpr uint32_t idesc = umma::instr_desc_bf16_f32(128, GN);
+        for (int c = 0; c < n; ++c, ++g) {
+            const uint32_t stage = g % STAGES, parity = (g / STAGES) & 1u;
+            mbar_wait(&pipe.full[stage], parity);
+            umma::fence_after_sync();
+            const uint32_t w_addr = smem_u32(pipe.stages + stage * SM::STAGE_BYTES);
+            const uint32_t a_addr = w_addr + SM::W_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < TC_CK / 16; ++ks)
+                umma::mma_bf16(acc, umma::smem_desc(a_addr + ks * 256, 128, TC_KG * 128),
+                               umma::smem_desc(w_addr + ks * 256, 128, TC_KG * 128), idesc, !(fresh && c == 0 && ks == 0));
+            umma::commit(&pipe.empty[stage]);       // stage is free once these MMAs have read it
+        }
+    }
+};
+
+// Consumer warps: accumulator (2*BP hi|lo rows x 128 gate rows of the group, this CTA's K share) -> split-K
+// exchange through L2 with the three other members -> z[row][b] of this CTA's own 8 hidden units.
+template <int BP>
+__device__ __forceinline__ void tc_epilogue(uint32_t acc, uint64_t* acc_bar, uint32_t& acc_phase, float* red, float* z,
+                                            float* zpart, uint32_t* gcnt, uint32_t& gepoch, int cta, int warp, int lane,
+                                            int tid) {
+    const int member = cta % GS, group = cta / GS;
+    constexpr int EW = 2 * BP / 32;                     // warps whose TMEM lane quarter holds rows
+    constexpr int PB = BP <= 32 ? 4 : 2;                // 32-column blocks staged in `red` per pass
+    constexpr int RS = PB * 32 + 1;                     // red row stride
+    static_assert(2 * BP * RS * 4 <= Smem<BP, __nv_bfloat16, true>::RED_BYTES, "epilogue staging must fit the red region");
+    if (warp < EW) {
+        mbar_wait(acc_bar, acc_phase);
+        umma::fence_after_sync();
+    }
+    acc_phase ^= 1u;
+#pragma unroll 1
+    for (int pass = 0; pass < GS / PB; ++pass) {
+        if (warp < EW) {
+            const int m = warp * 32 + lane;
+#pragma unroll
+            for (int cbl = 0; cbl < PB; ++cbl) {
+                float v[32];
+                umma::tmem_ld_32x32(acc + ((uint32_t)(warp * 32) << 16) + (pass * PB + cbl) * 32, v);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) red[m * RS + cbl * 32 + c] = v[c];
+            }
+            umma::fence_before_sync();
+        }
+        consumer_sync();
+        // hi + lo rows; columns [32*dst, 32*dst+32) are the gate rows of member dst
+        for (int i = tid; i < PB * ROWS_PER_CTA * BP; i += NTC) {
+            const int b = i % BP, c = (i / BP) % ROWS_PER_CTA, cbl = i / (BP * ROWS_PER_CTA);
+            const int dst = pass * PB + cbl;
+            const float v = red[b * RS + cbl * 32 + c] + red[(BP + b) * RS + cbl * 32 + c];
+            if (dst == member) z[c * BP + b] = v;       // own slice stays in shared memory
+            else zpart[(((size_t)(group * GS + dst)) * GS + member) * (ROWS_PER_CTA * BP) + c * BP + b] = v;
+        }
+        consumer_sync();
+    }
+    // group rendezvous: all four partial slices are in L2
+    gepoch += 1;
+    if (tid == 0) {
+        red_release_add_u32(gcnt + group, 1u);
+        const uint32_t target = gepoch * GS;
+        if (ld_acquire_u32(gcnt + group) < target) {
+            const uint64_t t0 = global_timer_ns();
+            while (ld_acquire_u32(gcnt + group) < target) {
+                if (global_timer_ns() - t0 > SPIN_TIMEOUT_NS) spin_fail();
+            }
+        }
+    }
+    consumer_sync();
+    for (int i = tid; i < ROWS_PER_CTA * BP; i += NTC) {
+        float accv = 0.f;
+#pragma unroll
+        for (int src = 0; src < GS; ++src) {            // fixed order: bitwise reproducible
+            const float v = src == member ? z[i] : __ldcg(zpart + ((size_t)cta * GS + src) * (ROWS_PER_CTA * BP) + i);
+            accv += v;
+        }
+        red[i] = accv;
+    }
+    consumer_sync();
+    for (int i = tid; i < ROWS_PER_CTA * BP; i += NTC) z[i] = red[i];
+    consumer_sync();
+}
+
+template <int BP>
+__global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
+    using WT = __nv_bfloat16;
+    using SM = Smem<BP, WT, true>;
+    using TP = TcPipe<BP>;
+    constexpr int STAGES = SM::NSTAGES;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cta = blockIdx.x, ncta = gridDim.x;
+    const bool is_gemm = cta < GEMM_CTAS;
+    const bool is_producer = warp == TC_PRODUCER_WARP, is_mma = warp == TC_MMA_WARP;
+    const bool is_consumer = warp < NW;
+    const int B = p.B;
+
+    Pipe pipe;
+    pipe.full = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
+    pipe.empty = pipe.full + STAGES;
+    pipe.stages = smem + SM::OFF_STAGE;
+    float* red = reinterpret_cast<float*>(smem + SM::OFF_RED);
+    float* z_s = reinterpret_cast<float*>(smem + SM::OFF_Z);
+    float* ca_s = reinterpret_cast<float*>(smem + SM::OFF_CA);
+    float* cd_s = reinterpret_cast<float*>(smem + SM::OFF_CD);
+    float* h_s = reinterpret_cast<float*>(smem + SM::OFF_H);
+    float* bias_s = reinterpret_cast<float*>(smem + SM::OFF_BIAS);
+    float* wq_s = reinterpret_cast<float*>(smem + SM::OFF_WQ);
+    float* wproj_s = reinterpret_cast<float*>(smem + SM::OFF_WPROJ);
+    float* wloc_s = reinterpret_cast<float*>(smem + SM::OFF_WLOC);
+    float* wld_s = reinterpret_cast<float*>(smem + SM::OFF_WLD);
+    float* v_s = reinterpret_cast<float*>(smem + SM::OFF_V);
+    int* misc_s = reinterpret_cast<int*>(smem + SM::OFF_MISC);
+    uint64_t* bar_attn = reinterpret_cast<uint64_t*>(smem + SM::OFF_ACCBAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_TMEM);
+    uint64_t* bar_dec = reinterpret_cast<uint64_t*>(smem + SM::OFF_ACCBAR + 16);
+    uint64_t* bar_exit = reinterpret_cast<uint64_t*>(smem + SM::OFF_ACCBAR + 24);
+    static_assert(SM::OFF_ACCBAR + 32 <= 256, "barrier area");
+
+    // ---- one-time setup ----
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&pipe.full[s], 1);
+            mbar_init(&pipe.empty[s], 1);
+        }
+        mbar_init(bar_attn, 1);
+        mbar_init(bar_dec, 1);
+        mbar_init(bar_exit, 1);
+        fence_mbar_init();
+        misc_s[1] = 0;
+    }
+    if (is_gemm && warp == 0) umma::tmem_alloc(tmem_slot, 2 * GN);          // two accumulators: 128 lanes x (128 + 128) columns
+    umma::fence_before_sync();
+    for (int i = tid; i < UNITS_PER_CTA * BP; i += NT_TC) { ca_s[i] = 0.f; cd_s[i] = 0.f; h_s[i] = 0.f; }
+    if (is_gemm) {
+        for (int i = tid; i < 32; i += NT_TC) {
+            bias_s[i] = p.bias_attn[cta * 32 + i];
+            bias_s[32 + i] = p.bias_dec[cta * 32 + i];
+        }
+        for (int i = tid; i < 128 * 8; i += NT_TC) wq_s[i] = p.wq_slices[(size_t)cta * 1024 + i];
+        for (int i = tid; i < PROJ_OUT * 8; i += NT_TC) wproj_s[i] = p.wproj_slices[(size_t)cta * PROJ_OUT * 8 + i];
+    } else {
+        const int nspare = ncta - GEMM_CTAS, sidx = cta - GEMM_CTAS;
+        const int rows_per = (PROJ_OUT + nspare - 1) / nspare;
+        const int o0 = sidx * rows_per, nrow = max(0, min(PROJ_OUT, o0 + rows_per) - o0);
+        float* wsm = reinterpret_cast<float*>(pipe.stages);
+        for (int i = tid; i < nrow * EMB; i += NT_TC) wsm[i] = p.wproj_ctxT[(size_t)(i % EMB) * PROJ_PAD + o0 + i / EMB];
+    }
+    for (int i = tid; i < LOC_F * 2 * LOC_K; i += NT_TC) wloc_s[(i / 62) * 63 + (i % 62)] = p.loc_conv[i];
+    for (int i = tid; i < LOC_F * ATT_DIM; i += NT_TC) wld_s[i] = p.loc_denseT[i];
+    for (int i = tid; i < 130; i += NT_TC) v_s[i] = p.attn_v[i];
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = is_gemm ? *tmem_slot : 0u;
+    const uint32_t acc_attn = tmem, acc_dec = tmem + GN;
+    uint32_t ph_attn = 0, ph_dec = 0, gepoch = 0;
+
+    // this CTA's weights: [local chunk j][128 rows x 64 k tile]; jobs are contiguous ranges of local chunks
+    const int member = cta % GS;
+    constexpr int NCH_A = K_ATTN / TC_CK / GS, NCH_D = K_DEC / TC_CK / GS;         // 7, 10
+    constexpr size_t WCH = (size_t)TC_CK * GN;                                        // elements per weight chunk
+    const WT* w_attn = reinterpret_cast<const WT*>(p.w_attn_tc) + (size_t)cta * NCH_A * WCH;
+    const WT* w_dec = reinterpret_cast<const WT*>(p.w_dec_tc) + (size_t)cta * NCH_D * WCH;
+    // activation chunks (64 rows of the act vector) behind each job, dims.cuh
+    const int ch_p = tc_attn_act_chunk(member, 0), ch_ctx = tc_attn_act_chunk(member, 1), ch_ah = tc_attn_act_chunk(member, 3),
+              ch_dh = tc_dec_act_chunk(member, 6);
+    constexpr size_t ABUF_BYTES = (size_t)(ACT_ROWS / TC_CK) * SM::A_BYTES;
+    uint8_t* const abase = reinterpret_cast<uint8_t*>(p.act16);
+
+    uint32_t epoch = 0;
+    uint32_t g = 0;             // ring position: chunks issued (producer) / consumed (MMA thread)
+    const bool tf = p.mode == 1;
+    const int total_steps = tf ? p.max_steps : p.max_steps + 1;
+    int steps_done = 0;
+
+    const bool timing = cta == 0 && tid == 0;
+    unsigned long long t_phase[4] = {0ull, 0ull, 0ull, 0ull}, t_last = timing ? global_timer_ns() : 0ull;
+#ifdef TACO_PROFILE_FINE
+    unsigned long long t_fine[16] = {}, t_flast = 0ull;
+#endif
+    auto stamp = [&](int ph) {
+        if (timing) {
+            const unsigned long long now = global_timer_ns();
+            t_phase[ph] += now - t_last;
+            t_last = now;
+        }
+    };
+
+    // ---- prologue = the background jobs of a virtual step -1 (all activations are zero): establishes the
+    // invariant "at the start of phase A the attention accumulator holds the ah/ctx ranges".
+    if (is_gemm) {
+        const uint8_t* a0 = abase + ABUF_BYTES;          // buffer 1 = prv of step 0 (zero-initialised)
+        if (is_producer) {
+            TP::produce(pipe, g, 4, 0, lane, w_attn + 3 * WCH, a0, ch_ah); g += 4;
+            TP::produce(pipe, g, 2, 0, lane, w_attn + 1 * WCH, a0, ch_ctx); g += 2;
+            TP::produce(pipe, g, 1, 1, lane, w_attn, nullptr, 0);            // weights of the first critical chunk
+        } else if (is_mma && lane == 0) {
+            TP::consume(pipe, g, 4, acc_attn, true);
+            TP::consume(pipe, g, 2, acc_attn, false);
+        }
+    }
+
+    for (int s = 0; s < total_steps; ++s) {
+        const int cur = s & 1, prv = cur ^ 1;
+        float* act_cur = p.act + (size_t)cur * ACT_ROWS * BP;
+        const uint8_t* a_cur = abase + (size_t)cur * ABUF_BYTES;
+        const uint8_t* a_prv = abase + (size_t)prv * ABUF_BYTES;
+        __nv_bfloat16* act16_cur = p.act16 + (size_t)cur * (ABUF_BYTES / 2);
+        __nv_bfloat16* act16_prv = p.act16 + (size_t)prv * (ABUF_BYTES / 2);
+        const int out_idx = tf ? s : s - 1;          // F6: decode step 0 of inference is discarded
+
+        // =============================== A: attention LSTM (critical: prenet rows) ===============================
+        if (is_gemm) {
+            if (is_producer) {
+                fence_proxy_async();
+                // prenet rows: previous buffer, or the precomputed buffer when teacher forcing (4 chunks per step)
+                const uint8_t* a0 = tf ? static_cast<const uint8_t*>(p.p_all) + (size_t)s * (PRENET / TC_CK) * SM::A_BYTES : a_prv;
+                TP::produce(pipe, g, 1, 2, lane, nullptr, a0, ch_p); g += 1;
+                TP::produce(pipe, g, 4, 0, lane, w_dec + 6 * WCH, a_cur, ch_dh); g += 4;   // background: decoder LSTM = W[dh] . dh_{t-1}
+            } else if (is_mma) {
+                if (lane == 0) {
+                    TP::consume(pipe, g, 1, acc_attn, false);
+                    umma::commit(bar_attn);
+                    TP::consume(pipe, g, 4, acc_dec, true);
+                }
+                __syncwarp();
+            } else {
+                FT_RESET();
+                tc_epilogue<BP>(acc_attn, bar_attn, ph_attn, red, z_s, p.zpart, p.ctrl + CTRL_GCNT, gepoch, cta, warp, lane, tid);
+                FT(9);
+                lstm_pointwise<BP, true>(z_s, bias_s, ca_s, h_s, nullptr, act16_cur, ACT_AH + cta * UNITS_PER_CTA, B, tid);
+                FT(10);
+                // this CTA's slice of the query projection (src/model.py:123): pqpart[b][cta][a]
+                for (int i = tid; i < ATT_DIM * B; i += NTC) {
+                    const int a = i % ATT_DIM, b = i / ATT_DIM;
+                    float sum = 0.f;
+#pragma unroll
+                    for (int u = 0; u < UNITS_PER_CTA; ++u) sum = fmaf(wq_s[a * 8 + u], h_s[u * BP + b], sum);
+                    p.pqpart[((size_t)b * GEMM_CTAS + cta) * ATT_DIM + a] = sum;
+                }
+                FT(11);
+            }
+        }
+        grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
+        stamp(0);
+
+        // =============================== B: attention; background: ah_t ranges ===============================
+        if (is_gemm && is_producer) {
+            fence_proxy_async();
+            wait_signal(misc_s + 1, 2 * s + 1);      // let the attention's own loads go first
+            TP::produce(pipe, g, 4, 0, lane, w_dec + 2 * WCH, a_cur, ch_ah); g += 4;     // decoder LSTM   += W[ah] . ah_t
+            TP::produce(pipe, g, 2, 1, lane, w_dec, nullptr, 0);                         // weights of phase C's critical chunks
+        } else if (is_gemm && is_mma) {
+            if (lane == 0) TP::consume(pipe, g, 4, acc_dec, false);
+            __syncwarp();
+        } else if (is_consumer) {
+            attention_phase<BP, true>(p, red, wld_s, wloc_s, v_s, misc_s, cur, out_idx, cta, ncta, tid, warp, lane, act_cur,
+                                      act16_cur, timing, TACO_FINE_ARGS, misc_s + 1, 2 * s + 1);
+        }
+        grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
+        stamp(1);
+
+        // =============================== C: decoder LSTM (critical: context rows) ===============================
+        if (is_gemm) {
+            if (is_producer) {
+                fence_proxy_async();
+                TP::produce(pipe, g, 2, 2, lane, nullptr, a_cur, ch_ctx); g += 2;
+                // background: attention LSTM(t+1) = W[ah] . ah_t + W[ctx] . ctx_t ; then the weights of the next phase A
+                TP::produce(pipe, g, 4, 0, lane, w_attn + 3 * WCH, a_cur, ch_ah); g += 4;
+                TP::produce(pipe, g, 2, 0, lane, w_attn + 1 * WCH, a_cur, ch_ctx); g += 2;
+                TP::produce(pipe, g, 1, 1, lane, w_attn, nullptr, 0);
+            } else if (is_mma) {
+                if (lane == 0) {
+                    TP::consume(pipe, g, 2, acc_dec, false);
+                    umma::commit(bar_dec);
+                    TP::consume(pipe, g, 4, acc_attn, true);
+                    TP::consume(pipe, g, 2, acc_attn, false);
+                }
+                __syncwarp();
+            } else {
+                FT_RESET();
+                tc_epilogue<BP>(acc_dec, bar_dec, ph_dec, red, z_s, p.zpart, p.ctrl + CTRL_GCNT, gepoch, cta, warp, lane, tid);
+                FT(12);
+                lstm_pointwise<BP, true>(z_s, bias_s + 32, cd_s, h_s, nullptr, act16_prv, ACT_DH + cta * UNITS_PER_CTA, B, tid);
+                FT(13);
+                // this CTA's slice of linear_projection / gate_layer (src/model.py:272-274)
+                for (int i = tid; i < PROJ_PAD * B; i += NTC) {
+                    const int o = i % PROJ_PAD, b = i / PROJ_PAD;
+                    if (o < PROJ_OUT) {
+                        float sum = 0.f;
+#pragma unroll
+                        for (int u = 0; u < UNITS_PER_CTA; ++u) sum = fmaf(wproj_s[o * 8 + u], h_s[u * BP + b], sum);
+                        p.melpart[((size_t)b * GEMM_CTAS + cta) * PROJ_PAD + o] = sum;
+                    }
+                }
+            }
+        } else if (is_consumer) {
+            spare_melctx(p, pipe.stages, cta, ncta, warp, lane);
+        }
+        grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
+        stamp(2);
+
+        // =============================== D: projection sums, stop rule, prenet; background: dh_t range ============
+        if (is_consumer) projection_phase<BP, true>(p, red, tf, out_idx, cta, ncta, tid, act_cur, act16_cur);
+        steps_done = s + 1;
+        if (!tf) {
+            grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
+            stamp(3);
+            if (__ldcg(p.ctrl + CTRL_STOP) != 0u) break;
+        }
+    }
+
+    // ---- drain: background MMAs may still be running; the weights of a phase-A chunk that will never run are
+    // in flight: wait for the former, complete the stage of the latter ----
+    if (is_gemm && is_mma && lane == 0) {
+        umma::commit(bar_exit);
+        mbar_wait(bar_exit, 0);
+    }
+    if (is_gemm && is_producer) {
+        const uint32_t stage = g % STAGES;
+        if (lane == (int)stage) {
+            bulk_g2s(pipe.stages + stage * SM::STAGE_BYTES + SM::W_BYTES, abase, SM::A_BYTES, &pipe.full[stage]);
+            mbar_wait(&pipe.full[stage], (g / STAGES) & 1u);
+        }
+    }
+    if (cta == 0 && tid == 0) {
+        unsigned long long* prof = reinterpret_cast<unsigned long long*>(p.ctrl + CTRL_PROF);
+        for (int i = 0; i < 4; ++i) prof[i] = t_phase[i];
+        prof[4] = (unsigned long long)steps_done;
+#ifdef TACO_PROFILE_FINE
+        for (int i = 0; i < 16; ++i) prof[5 + i] = t_fine[i];
+#endif
+        const int S = tf ? p.max_steps : steps_done - 1;     // output frames (decode step 0 discarded)
+        *p.steps_run = S;
+        for (int b = 0; b < B; ++b) {
+            int len = S;
+            if (!tf && p.stop_mode == B200TACO_STOP_PER_UTTERANCE && __ldcg(p.ctrl + CTRL_DONE + b))
+                len = (int)__ldcg(p.ctrl + CTRL_LEN + b);
+            p.lengths[b] = len;
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (is_gemm && warp == 0) umma::tmem_dealloc(tmem, 2 * GN);
+}
+
+template <int BP>
+int launch_tc(const KParams& kp, int ncta, cudaStream_t stream) {
+    using SM = Smem<BP, __nv_bfloat16, true>;
+    auto kern = decoder_tc_kernel<BP>;
+    TACO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    int per_sm = 0;
+    TACO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT_TC, SM::TOTAL));
+    TACO_REQUIRE(per_sm >= 1, B200TACO_ERR_UNSUPPORTED, "decoder kernel does not fit on an SM (smem %d B)", SM::TOTAL);
+    void* args[] = {const_cast<KParams*>(&kp)};
+    TACO_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(ncta), dim3(NT_TC), args, SM::TOTAL, stream));
     launch_counter()++;
     return B200TACO_OK;
 }
@@ -1283,8 +1748,8 @@ int decoder_run(const b200taco_handle* h, const DecoderArgs& a, cudaStream_t str
     const_cast<b200taco_handle*>(h)->last_profile = reinterpret_cast<const unsigned long long*>(kp.ctrl + CTRL_PROF);
     if (decoder_uses_tensor_cores(h, a.B)) {
         TACO_REQUIRE(h->w_attn_tc && h->w_dec_tc, B200TACO_ERR_STATE, "tensor-core weights not packed");
-        if (BP == 32) return launch<32, __nv_bfloat16, true>(kp, ncta, stream);
-        return launch<64, __nv_bfloat16, true>(kp, ncta, stream);
+        if (BP == 32) return launch_tc<32>(kp, ncta, stream);
+        return launch_tc<64>(kp, ncta, stream);
     }
     if (h->weight_dtype == 1) return dispatch_bp<float>(BP, kp, ncta, stream);
     return dispatch_bp<__nv_bfloat16>(BP, kp, ncta, stream);

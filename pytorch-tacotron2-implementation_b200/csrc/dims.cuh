@@ -38,6 +38,16 @@ constexpr int ACT_ROWS = ACT_DH + RNN;             // 2816
 constexpr int K_ATTN = ACT_DH;                     // attention LSTM reads rows [0, 1792)
 constexpr int K_DEC = ACT_ROWS - ACT_CTX;          // decoder LSTM reads rows [256, 2816)
 
+// Tensor-core decoder path (split-K groups of 4 CTAs): local weight chunk j of group member m -> 64-row chunk of
+// the act vector.  Every availability class (prenet / context / attention h / decoder h rows) is dealt evenly
+// to the four members, and the chunks of one class are contiguous in j (decoder.cu, decoder_tc_kernel).
+__host__ __device__ constexpr int tc_attn_act_chunk(int m, int j) {      // 7 chunks: 1 prenet, 2 ctx, 4 ah
+    return j < 1 ? m : (j < 3 ? 4 + 2 * m + (j - 1) : 12 + 4 * m + (j - 3));
+}
+__host__ __device__ constexpr int tc_dec_act_chunk(int m, int j) {       // 10 chunks: 2 ctx, 4 ah, 4 dh
+    return j < 2 ? 4 + 2 * m + j : (j < 6 ? 12 + 4 * m + (j - 2) : 28 + 4 * m + (j - 6));
+}
+
 constexpr int PROJ_OUT = N_MELS + 1;               // 80 mel rows + the gate row
 constexpr int PROJ_PAD = 96;                       // padded row length of projection partials
 

@@ -38,7 +38,7 @@ __global__ void pack_lstm_kernel(WT* dst, int K, const float* s0, int ld0, int o
 // tensor-core layout (split-K groups of 4 CTAs, decoder.cu gemm_tc): cta = 4*group + member owns, for the
 // group's 128 gate rows (n = unit_local*4 + gate, unit = 32*group + unit_local), the K quarter of `member`:
 // dst[cta][j = local chunk][UMMA K-major tile of 128 rows x 64 k], physical k = (member*K/4) + 64*j + kk
-__global__ void pack_lstm_tc_kernel(__nv_bfloat16* dst, int K, const float* s0, int ld0, int off0, int n0, const float* s1,
+__global__ void pack_lstm_tc_kernel(__nv_bfloat16* dst, int K, int which /* 0 attention, 1 decoder LSTM */, const float* s0, int ld0, int off0, int n0, const float* s1,
                                     int ld1, int off1, int n1, const float* s2, int ld2, int off2) {
     const int KQ = K / 4;                                      // k per member
     const size_t per_cta = (size_t)KQ * 128;
@@ -48,7 +48,9 @@ __global__ void pack_lstm_tc_kernel(__nv_bfloat16* dst, int K, const float* s0, 
         const int n = (i / KQ) % 128;
         const int cta = i / per_cta;
         const int group = cta / 4, member = cta % 4;
-        const int k = member * KQ + kl;
+        // local chunk kl/64 of this member -> chunk of the act vector -> position in this matrix' own K order
+        const int ach = which ? tc_dec_act_chunk(member, kl / 64) - ACT_CTX / 64 : tc_attn_act_chunk(member, kl / 64);
+        const int k = ach * 64 + kl % 64;
         const int row = (n & 3) * RNN + group * 32 + (n >> 2);
         float v;
         if (k < n0) v = s0[(size_t)row * ld0 + off0 + k];
@@ -267,11 +269,11 @@ int pack_weights(b200taco_handle* h, const b200taco_weights* w, cudaStream_t st)
             w->dec_lstm_w_hh, RNN, 0);
         TACO_LAUNCHED();
         pack_lstm_tc_kernel<<<blocks_for(na), 256, 0, st>>>(
-            (__nv_bfloat16*)h->w_attn_tc, K_ATTN, w->attn_lstm_w_ih, PRENET + EMB, 0, PRENET + EMB, w->attn_lstm_w_hh, RNN,
+            (__nv_bfloat16*)h->w_attn_tc, K_ATTN, 0, w->attn_lstm_w_ih, PRENET + EMB, 0, PRENET + EMB, w->attn_lstm_w_hh, RNN,
             0, RNN, w->attn_lstm_w_hh, RNN, 0);
         TACO_LAUNCHED();
         pack_lstm_tc_kernel<<<blocks_for(nd), 256, 0, st>>>(
-            (__nv_bfloat16*)h->w_dec_tc, K_DEC, w->dec_lstm_w_ih, RNN + EMB, RNN, EMB, w->dec_lstm_w_ih, RNN + EMB, 0, RNN,
+            (__nv_bfloat16*)h->w_dec_tc, K_DEC, 1, w->dec_lstm_w_ih, RNN + EMB, RNN, EMB, w->dec_lstm_w_ih, RNN + EMB, 0, RNN,
             w->dec_lstm_w_hh, RNN, 0);
         TACO_LAUNCHED();
     }
