@@ -1,0 +1,146 @@
+"""Length-bucketed utterance sharding for multi-GPU inference (BASELINE config 4).
+
+Inference has no cross-utterance dependency: one process per GPU, weights replicated, every rank
+decodes its own batches, **no collective on the data path**.  Only the per-utterance results
+(lengths, timings) are gathered at the end.
+
+Two facts of the reference shape the plan:
+
+* ``Tacotron2.inference`` ignores ``text_lengths`` and attends padded positions (F8,
+  src/model.py:482-494, :305), so a padded batch does not reproduce the solo result of its shorter
+  rows.  Batches are therefore **exact-length**: every utterance of a batch has the same number of
+  phonemes.
+* A decoder step costs almost the same for 1 or 32 rows, so a batch costs ~ (frames of its longest
+  row) x step_time(B); decoded length grows with the text length.  Batches are dealt to ranks
+  longest-processing-time-first on that estimate, which keeps the tail imbalance small.
+
+Everything here is host logic (pure Python + torch.distributed); it runs identically under ``gloo``
+on CPU (tests/test_shard_cpu.py) and ``nccl`` on the GPU box.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+
+
+@dataclass
+class Batch:
+    """Utterance indices (into the caller's corpus) that share one text length."""
+    text_len: int
+    indices: List[int]
+    cost: float = 0.0
+
+
+@dataclass
+class Plan:
+    world_size: int
+    batches: List[Batch]
+    assignment: List[List[int]] = field(default_factory=list)     # rank -> indices into ``batches``
+
+    def load(self) -> List[float]:
+        return [sum(self.batches[i].cost for i in a) for a in self.assignment]
+
+    def imbalance(self) -> float:
+        """max rank load / mean rank load (1.0 = perfect)."""
+        load = self.load()
+        mean = sum(load) / max(1, len(load))
+        return max(load) / mean if mean > 0 else 1.0
+
+
+def step_time_us(batch_rows: int) -> float:
+    """Measured decoder step time on B200 (profiles/r1_v3_decoder_phase_times_fine.jsonl): nearly flat in B."""
+    pts = [(1, 26.0), (8, 33.0), (32, 36.0), (64, 51.0)]
+    if batch_rows <= pts[0][0]:
+        return pts[0][1]
+    for (b0, t0), (b1, t1) in zip(pts[:-1], pts[1:]):
+        if batch_rows <= b1:
+            return t0 + (t1 - t0) * (batch_rows - b0) / (b1 - b0)
+    return pts[-1][1] * batch_rows / pts[-1][0]
+
+
+def default_cost(text_len: int, rows: int, frames_per_phoneme: float = 5.5) -> float:
+    """Estimated microseconds of one batch: decode steps of its longest row x step time (+ a small fixed part)."""
+    return frames_per_phoneme * text_len * step_time_us(rows) + 3000.0
+
+
+def plan_buckets(text_lengths: Sequence[int], batch_size: int = 32,
+                 cost_fn: Callable[[int, int], float] = default_cost) -> List[Batch]:
+    """Exact-length buckets cut into batches of at most ``batch_size`` rows (input order kept inside a bucket)."""
+    if batch_size < 1:
+        raise ValueError("batch_size must be >= 1")
+    buckets: Dict[int, List[int]] = {}
+    for i, n in enumerate(text_lengths):
+        n = int(n)
+        if n < 1:
+            raise ValueError(f"utterance {i} has no phonemes")
+        buckets.setdefault(n, []).append(i)
+    batches = []
+    for n in sorted(buckets, reverse=True):
+        idx = buckets[n]
+        for k in range(0, len(idx), batch_size):
+            rows = idx[k:k + batch_size]
+            batches.append(Batch(n, rows, float(cost_fn(n, len(rows)))))
+    return batches
+
+
+def assign(batches: List[Batch], world_size: int) -> Plan:
+    """Longest-processing-time-first: heaviest batch to the least loaded rank.  Deterministic on every rank."""
+    if world_size < 1:
+        raise ValueError("world_size must be >= 1")
+    order = sorted(range(len(batches)), key=lambda i: (-batches[i].cost, i))
+    load = [0.0] * world_size
+    assignment: List[List[int]] = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        assignment[r].append(i)
+        load[r] += batches[i].cost
+    return Plan(world_size, batches, assignment)
+
+
+def make_plan(text_lengths: Sequence[int], world_size: int, batch_size: int = 32,
+              cost_fn: Callable[[int, int], float] = default_cost) -> Plan:
+    return assign(plan_buckets(text_lengths, batch_size, cost_fn), world_size)
+
+
+def run_shard(plan: Plan, rank: int, corpus: Sequence[torch.Tensor],
+              decode_fn: Callable[[torch.Tensor], Sequence[int]]) -> Dict[int, int]:
+    """Decode this rank's batches.  ``corpus[i]`` is the 1-D int64 phoneme-id tensor of utterance i;
+    ``decode_fn(ids (B,T)) -> per-row decoded lengths`` (e.g. a wrapper of
+    ``Tacotron2.inference_per_utterance``).  Returns {utterance index: decoded length}."""
+    out: Dict[int, int] = {}
+    for bi in plan.assignment[rank]:
+        b = plan.batches[bi]
+        ids = torch.stack([corpus[i] for i in b.indices], dim=0)
+        if ids.shape[1] != b.text_len:
+            raise ValueError(f"batch {bi}: utterances are not all {b.text_len} phonemes long")
+        lengths = [int(x) for x in decode_fn(ids)]
+        if len(lengths) != len(b.indices):
+            raise ValueError(f"decode_fn returned {len(lengths)} lengths for {len(b.indices)} rows")
+        out.update(zip(b.indices, lengths))
+    return out
+
+
+def gather_lengths(local: Dict[int, int], n_utterances: int, device: Optional[torch.device] = None) -> torch.Tensor:
+    """All ranks' decoded lengths as one (n_utterances,) int64 tensor on every rank.
+
+    One small all-reduce after the data path has finished (each utterance is written by exactly one rank; the
+    others contribute 0).  Without an initialised process group this is the identity.
+    """
+    import torch.distributed as dist
+    t = torch.zeros(n_utterances, dtype=torch.int64, device=device)
+    if local:
+        idx = torch.tensor(list(local.keys()), dtype=torch.int64, device=device)
+        val = torch.tensor(list(local.values()), dtype=torch.int64, device=device)
+        t[idx] = val
+    owners = torch.zeros(n_utterances, dtype=torch.int64, device=device)
+    if local:
+        owners[idx] = 1
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(owners, op=dist.ReduceOp.SUM)
+    if not bool((owners == 1).all()):
+        bad = (owners != 1).nonzero().flatten().tolist()[:8]
+        raise RuntimeError(f"sharding error: utterances {bad} were decoded {owners[bad].tolist()} times")
+    return t

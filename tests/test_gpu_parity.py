@@ -214,6 +214,30 @@ def test_c2_full_size_stop_lengths_exact():
     assert out[1].shape[1] == int(ref_len.min())
 
 
+def test_sharded_exact_length_batches_match_solo_runs():
+    """BASELINE config 4 (reduced): exact-length batches reproduce every utterance's solo (B=1) reference run,
+    decoded lengths exact (F8: padding would not)."""
+    from b200taco import shard
+    lens = [23, 17, 23, 20, 17, 23, 20, 17, 23, 20, 23, 17]
+    corpus = [synth.phoneme_ids(1, t, seed=100 + i)[0] for i, t in enumerate(lens)]
+    center = O.encoder(util.weights("stress", True), torch.stack([corpus[0], corpus[2]])).mean((0, 1))
+    sd = util.weights("planted", True, ctx_center=center)
+    m = gpu_model(sd)
+    plan = shard.make_plan(lens, world_size=1, batch_size=3)
+    assert all(lens[i] == b.text_len for b in plan.batches for i in b.indices)
+
+    def decode(ids):
+        return m.inference_per_utterance(ids.cuda())[4].tolist()
+
+    got = shard.gather_lengths(shard.run_shard(plan, 0, corpus, decode), len(lens)).tolist()
+    want = []
+    for c in corpus:
+        gate = O.tacotron2_inference(sd, c[None])[2]
+        want.append(int(O.per_utterance_lengths(gate)[0]))
+    assert got == want, (got, want)
+    assert len(set(want)) > 1                       # the stops really differ between utterances
+
+
 def test_long_horizon_default_init_1000_steps():
     """Default init never fires (F11): 1000 frames, error must not grow with the horizon."""
     ids = synth.phoneme_ids(2, 150, seed=1)
