@@ -330,14 +330,21 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything a library prints meanwhile (NCCL's version banner, the
+    # reference's debug prints) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         out = run_reference(args, rank, world)
     else:
         if world != args.gpus and rank == 0:
             print(f"[bench] WORLD_SIZE={world} but --gpus {args.gpus}; using WORLD_SIZE", file=sys.stderr)
         out = run_b200(args, rank, world, local_rank)
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if out is not None:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":

@@ -610,14 +610,17 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
         consumer_sync();
         if (TACO_SIG_POINT == 0 && sig != nullptr && tid == 0) *sig = sig_val;
         FT(1);
-        float wld[LOC_F];
-        {
-            const int a = tid & 127;
+        // energies: every thread owns two attention dims (a0, a0 + 64) and, per pass, four positions
+        const int a0 = tid & 63;
+        float wld[2][LOC_F];
 #pragma unroll
-            for (int f = 0; f < LOC_F; ++f) wld[f] = wld_s[f * ATT_DIM + a];
+        for (int f = 0; f < LOC_F; ++f) {
+            wld[0][f] = wld_s[f * ATT_DIM + a0];
+            wld[1][f] = wld_s[f * ATT_DIM + a0 + 64];
         }
-        const float pq = sc[P2Scratch::PQ + (tid & 127)] + sc[P2Scratch::PQ + 128 + (tid & 127)];
-        const float vw = v_s[tid & 127];
+        const float pq0 = sc[P2Scratch::PQ + a0] + sc[P2Scratch::PQ + 128 + a0];
+        const float pq1 = sc[P2Scratch::PQ + a0 + 64] + sc[P2Scratch::PQ + 128 + a0 + 64];
+        const float vw0 = v_s[a0], vw1 = v_s[a0 + 64];
         for (int tile = 0; tile < ntiles; ++tile) {
             const int tb = tile * TILE_POS;          // offset inside the slice
             // ---- location conv (src/model.py:125-126): 32 filters x (2 x 31 taps)
@@ -644,29 +647,37 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
             cp_async_wait_all();
             consumer_sync();
         FT(2);
-            // ---- energies (src/model.py:127-130): v . tanh(pq + pm + Wld loc); four positions per
-            // thread at a time (independent FMA chains, 128-bit reads of the location features), then
-            // the sum over the 128 attention dims: shuffle within the warp, 4 warp partials per position
+            // ---- energies (src/model.py:127-130): v . tanh(pq + pm + Wld loc).  The 128-bit broadcast reads of the
+            // location features bound this loop (LSU write-back), so each read feeds 8 FMAs: 2 dims x 4 positions
+            // per thread.  Sum over the 128 dims: two dims in the thread, shuffle within the warp, 2 warp partials.
             const int npl = min(TILE_POS, n - tb);
             {
-                const int a = tid & 127, hf = tid >> 7, wq4 = (tid >> 5) & 3;
-                for (int pl0 = hf * 4; pl0 < npl; pl0 += 8) {
-                    float x[4];
+                const int hf = tid >> 6, w2 = (tid >> 5) & 1;
+                for (int pl0 = hf * 4; pl0 < npl; pl0 += 16) {
+                    float x0[4], x1[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) x[j] = pq + sc[P2Scratch::PM + (pl0 + j) * ATT_DIM + a];
+                    for (int j = 0; j < 4; ++j) {
+                        x0[j] = pq0 + sc[P2Scratch::PM + (pl0 + j) * ATT_DIM + a0];
+                        x1[j] = pq1 + sc[P2Scratch::PM + (pl0 + j) * ATT_DIM + a0 + 64];
+                    }
 #pragma unroll
                     for (int f4 = 0; f4 < LOC_F; f4 += 4) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float4 l = *reinterpret_cast<const float4*>(sc + P2Scratch::LOC + (pl0 + j) * P2Scratch::LOC_LD + f4);
-                            x[j] = fmaf(wld[f4], l.x, x[j]);
-                            x[j] = fmaf(wld[f4 + 1], l.y, x[j]);
-                            x[j] = fmaf(wld[f4 + 2], l.z, x[j]);
-                            x[j] = fmaf(wld[f4 + 3], l.w, x[j]);
+                            x0[j] = fmaf(wld[0][f4], l.x, x0[j]);
+                            x1[j] = fmaf(wld[1][f4], l.x, x1[j]);
+                            x0[j] = fmaf(wld[0][f4 + 1], l.y, x0[j]);
+                            x1[j] = fmaf(wld[1][f4 + 1], l.y, x1[j]);
+                            x0[j] = fmaf(wld[0][f4 + 2], l.z, x0[j]);
+                            x1[j] = fmaf(wld[1][f4 + 2], l.z, x1[j]);
+                            x0[j] = fmaf(wld[0][f4 + 3], l.w, x0[j]);
+                            x1[j] = fmaf(wld[1][f4 + 3], l.w, x1[j]);
                         }
                     }
+                    float x[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) x[j] = vw * tanh_fast(x[j]);
+                    for (int j = 0; j < 4; ++j) x[j] = fmaf(vw0, tanh_fast(x0[j]), vw1 * tanh_fast(x1[j]));
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
@@ -674,7 +685,7 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
                     }
                     if (lane == 0) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) sc[P2Scratch::EPART + (pl0 + j) * 4 + wq4] = x[j];
+                        for (int j = 0; j < 4; ++j) sc[P2Scratch::EPART + (pl0 + j) * 4 + w2] = x[j];
                     }
                 }
             }
@@ -682,13 +693,18 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
         FT(3);
             if (tid < npl) {
                 const float* ep = sc + P2Scratch::EPART + tid * 4;
-                float e = ((ep[0] + ep[1]) + (ep[2] + ep[3]) + v_s[128]) * v_s[129];
+                float e = ((ep[0] + ep[1]) + v_s[128]) * v_s[129];
                 if (t0 + tb + tid >= len) e = -1e9f;                  // masked_fill, src/model.py:132
                 sc[P2Scratch::E + tb + tid] = e;
             }
             consumer_sync();
         FT(4);
         }
+        // ---- first 20 memory rows of the context sum: issued now, in flight during the softmax statistics ----
+        const float2* mrow = reinterpret_cast<const float2*>(p.memory + ((size_t)b * T + t0) * EMB) + tid;
+        float2 mv0[20];
+#pragma unroll
+        for (int j = 0; j < 20; ++j) mv0[j] = j < n ? __ldg(mrow + (size_t)j * (EMB / 2)) : make_float2(0.f, 0.f);
         // ---- slice-local softmax statistics (warp 0) ----
         if (warp == 0) {
             float m = -INFINITY;
@@ -712,8 +728,13 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
         // ---- slice-local un-normalised context: sum_t ew[t] * memory[b][t][:] ----
         float2 cacc = make_float2(0.f, 0.f);
         {
-            const float2* mrow = reinterpret_cast<const float2*>(p.memory + ((size_t)b * T + t0) * EMB) + tid;
-            int i = 0;
+#pragma unroll
+            for (int j = 0; j < 20; ++j) {
+                const float ew = j < n ? sc[P2Scratch::E + j] : 0.f;
+                cacc.x = fmaf(ew, mv0[j].x, cacc.x);
+                cacc.y = fmaf(ew, mv0[j].y, cacc.y);
+            }
+            int i = 20;
             for (; i + 20 <= n; i += 20) {                    // 20 rows (40 KB per CTA) in flight
                 float2 mv[20];
 #pragma unroll
