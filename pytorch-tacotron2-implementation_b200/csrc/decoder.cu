@@ -19,6 +19,8 @@
 // exchanged through the double-buffered "act" matrix [2816][BP] in global memory (L2).
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "handle.h"
 #include "umma.cuh"
 
@@ -63,7 +65,7 @@ struct KParams {
     float *mel, *gate, *align;
     int32_t *lengths, *steps_run;
     // scratch
-    float *act, *pqpart, *melpart, *melctx, *ctx_bj, *attn_prev, *attn_cum, *wtmp, *apart;
+    float *act, *pqpart, *melpart, *ctx_bj, *attn_prev, *attn_cum, *wtmp, *apart;
     float* zpart;                      // tcgen05 path: split-K partial gate sums [dst cta][src member][32 rows][BP]
     uint32_t* ctrl;
 };
@@ -105,14 +107,16 @@ struct Smem {
     static constexpr int OFF_CA = OFF_Z + 32 * BP * 4;                         // 8*BP
     static constexpr int OFF_CD = OFF_CA + 8 * BP * 4;
     static constexpr int OFF_H = OFF_CD + 8 * BP * 4;
-    static constexpr int OFF_BIAS = OFF_H + 8 * BP * 4;                        // 64
+    static constexpr int OFF_BIAS = OFF_H + 12 * BP * 4;                      // h[8][BP] + this CTA's 4 context rows cx[4][BP]                        // 64
     static constexpr int OFF_WQ = OFF_BIAS + 64 * 4;                           // 128*8
     static constexpr int OFF_WPROJ = OFF_WQ + 128 * 8 * 4;                     // 81*8 (pad 656)
-    static constexpr int OFF_WLOC = OFF_WPROJ + 656 * 4;                       // 32*63
+    static constexpr int OFF_WLOC = OFF_WPROJ + 984 * 4;                      // + ctx slice 81*4 (pad 328)                       // 32*63
     static constexpr int OFF_WLD = OFF_WLOC + 32 * 63 * 4;                     // 32*128
     static constexpr int OFF_V = OFF_WLD + 32 * 128 * 4;                       // 132
     static constexpr int OFF_MISC = OFF_V + 132 * 4;                           // 64 floats of flags/scalars
-    static constexpr int TOTAL = OFF_MISC + 64 * 4;
+    static constexpr int OFF_XCH = OFF_MISC + 64 * 4;                          // tensor-core path: split-K partials of the
+    static constexpr int XCH_BYTES = TC ? GS * ROWS_PER_CTA * BP * 4 : 0;      // four group members, written through DSMEM
+    static constexpr int TOTAL = OFF_XCH + XCH_BYTES;
     static_assert(TOTAL <= 227 * 1024, "shared memory budget");
     static_assert(STAGE_BYTES % 128 == 0 && W_BYTES % 128 == 0, "bulk copy alignment");
 };
@@ -211,6 +215,33 @@ __device__ __forceinline__ void consumer_sync() { named_bar_sync(1, NTC); }
 #ifndef TACO_SIG_POINT
 #define TACO_SIG_POINT 2
 #endif
+
+// ---- thread-block cluster helpers (tensor-core kernel: a split-K group is one cluster of GS CTAs) ----
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_bar_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 // CTA-local signal in shared memory (written by consumer thread 0, polled by the producer warp)
 __device__ __forceinline__ void wait_signal(const int* flag, int value) {
@@ -834,35 +865,6 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
     if (sig != nullptr && tid == 0) *sig = sig_val;       // CTAs without a work item
 }
 
-// P3 on the spare CTAs: context part of the projections + bias: melctx[b][o] for this CTA's rows o
-// (weights cached in shared memory at kernel start); one warp per utterance at a time.
-__device__ __forceinline__ void spare_melctx(const KParams& p, const uint8_t* stage_area, int cta, int ncta, int warp,
-                                             int lane) {
-    const int B = p.B;
-    const int nspare = ncta - GEMM_CTAS, sidx = cta - GEMM_CTAS;
-    const int rows_per = (PROJ_OUT + nspare - 1) / nspare;            // <= SPARE_ROWS
-    const int o0 = sidx * rows_per, nrow = max(0, min(PROJ_OUT, o0 + rows_per) - o0);
-    const float* wsm = reinterpret_cast<const float*>(stage_area);   // [rows][512], staged at kernel start
-    for (int b = warp; b < B && nrow > 0; b += NW) {
-        float4 c4[4];
-        const float4* csrc = reinterpret_cast<const float4*>(p.ctx_bj + (size_t)b * EMB) + lane * 4;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) c4[i] = __ldcg(csrc + i);
-        for (int r = 0; r < nrow; ++r) {
-            const float4* w4 = reinterpret_cast<const float4*>(wsm + r * EMB) + lane * 4;
-            float acc = 0.f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 w = w4[i];
-                acc = fmaf(w.x, c4[i].x, acc); acc = fmaf(w.y, c4[i].y, acc);
-                acc = fmaf(w.z, c4[i].z, acc); acc = fmaf(w.w, c4[i].w, acc);
-            }
-            acc = warp_sum(acc);
-            if (lane == 0) p.melctx[(size_t)b * PROJ_PAD + o0 + r] = acc + __ldg(p.proj_bias + o0 + r);
-        }
-    }
-}
-
 // P4: per utterance: sum projection partials -> mel frame, gate logit, stop rule (src/model.py:327 /
 // train.py:71-79), prenet of the next input frame (src/model.py:166-171).  Consumer warps of every CTA.
 template <int BP, bool TC>
@@ -886,7 +888,7 @@ __device__ __forceinline__ void projection_phase(const KParams& p, float* red, b
         consumer_sync();
         if (sig != nullptr && tid == 0) *sig = sig_val;
         if (tid < PROJ_OUT) {
-            const float v = sc[tid] + sc[128 + tid] + __ldcg(p.melctx + (size_t)b * PROJ_PAD + tid);
+            const float v = sc[tid] + sc[128 + tid] + __ldg(p.proj_bias + tid);
             sc[256 + tid] = v;                                  // mel frame (0..79), gate logit (80)
             if (q == 0 && out_idx >= 0) {
                 if (tid < N_MELS) p.mel[((size_t)b * p.max_steps + out_idx) * N_MELS + tid] = v;
@@ -982,6 +984,8 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
     float* bias_s = reinterpret_cast<float*>(smem + SM::OFF_BIAS);
     float* wq_s = reinterpret_cast<float*>(smem + SM::OFF_WQ);
     float* wproj_s = reinterpret_cast<float*>(smem + SM::OFF_WPROJ);
+    float* wpc_s = wproj_s + 656;
+    float* cx_s = h_s + 8 * BP;
     float* wloc_s = reinterpret_cast<float*>(smem + SM::OFF_WLOC);
     float* wld_s = reinterpret_cast<float*>(smem + SM::OFF_WLD);
     float* v_s = reinterpret_cast<float*>(smem + SM::OFF_V);
@@ -1010,13 +1014,8 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
         }
         for (int i = tid; i < 128 * 8; i += NT) wq_s[i] = p.wq_slices[(size_t)cta * 1024 + i];
         for (int i = tid; i < PROJ_OUT * 8; i += NT) wproj_s[i] = p.wproj_slices[(size_t)cta * PROJ_OUT * 8 + i];
-    }
-    if (!is_gemm) {
-        const int nspare = ncta - GEMM_CTAS, sidx = cta - GEMM_CTAS;
-        const int rows_per = (PROJ_OUT + nspare - 1) / nspare;
-        const int o0 = sidx * rows_per, nrow = max(0, min(PROJ_OUT, o0 + rows_per) - o0);
-        float* wsm = reinterpret_cast<float*>(pipe.stages);
-        for (int i = tid; i < nrow * EMB; i += NT) wsm[i] = p.wproj_ctxT[(size_t)(i % EMB) * PROJ_PAD + o0 + i / EMB];
+        // context part of the projections for this CTA's four context rows: wpc[o][j] = W[o][1024 + 4*cta + j]
+        for (int i = tid; i < PROJ_OUT * 4; i += NT) wpc_s[i] = p.wproj_ctxT[(size_t)(4 * cta + (i & 3)) * PROJ_PAD + (i >> 2)];
     }
     for (int i = tid; i < LOC_F * 2 * LOC_K; i += NT) wloc_s[(i / 62) * 63 + (i % 62)] = p.loc_conv[i];
     for (int i = tid; i < LOC_F * ATT_DIM; i += NT) wld_s[i] = p.loc_denseT[i];
@@ -1134,6 +1133,7 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                 g += NCH3;
                 PR::prefetch(pipe, g, NCH1, PRE1, rot1, lane, w_attn);         // next step's P1, across P4
             } else {
+                for (int i = tid; i < 4 * B; i += NTC) cx_s[(i & 3) * BP + (i >> 2)] = __ldcg(p.ctx_bj + (size_t)(i >> 2) * EMB + 4 * cta + (i & 3));
                 FT_RESET();
                 if constexpr (TC) {
                     gemm_tc<BP, WT>(pipe, g, NCH3, tmem, acc_bar, acc_phase, red, z_s, p.zpart, p.ctrl + CTRL_GCNT, gepoch,
@@ -1147,19 +1147,19 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                 lstm_pointwise<BP, TC>(z_s, bias_s + 32, cd_s, h_s, act_prv + (size_t)(ACT_DH + cta * UNITS_PER_CTA) * BP,
                                        act16_prv, ACT_DH + cta * UNITS_PER_CTA, B, tid);
                 FT(13);
-                // this CTA's slice of linear_projection / gate_layer (src/model.py:272-274)
+                // this CTA's slice of linear_projection / gate_layer (src/model.py:272-274): 8 decoder-h units + 4 context rows
                 for (int i = tid; i < PROJ_PAD * B; i += NTC) {
                     const int o = i % PROJ_PAD, b = i / PROJ_PAD;
                     if (o < PROJ_OUT) {
                         float sum = 0.f;
 #pragma unroll
                         for (int u = 0; u < UNITS_PER_CTA; ++u) sum = fmaf(wproj_s[o * 8 + u], h_s[u * BP + b], sum);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) sum = fmaf(wpc_s[o * 4 + j], cx_s[j * BP + b], sum);
                         p.melpart[((size_t)b * GEMM_CTAS + cta) * PROJ_PAD + o] = sum;
                     }
                 }
             }
-        } else if (!is_producer) {
-            spare_melctx(p, pipe.stages, cta, ncta, warp, lane);
         }
         grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
         stamp(2);
@@ -1283,21 +1283,26 @@ struct TcPipe {
 };
 
 // Consumer warps: accumulator (2*BP hi|lo rows x 128 gate rows of the group, this CTA's K share) -> split-K
-// exchange through L2 with the three other members -> z[row][b] of this CTA's own 8 hidden units.
-template <int BP>
+// exchange with the three other members -> z[row][b] of this CTA's own 8 hidden units.
+// CL (group = thread-block cluster): the partial of member `dst` is stored straight into dst's shared memory
+// (DSMEM), followed by one remote mbarrier arrive per peer; no L2 round trip, no polling on a global counter.
+// !CL: partials through L2 (zpart) and a release/acquire group counter.
+template <int BP, bool CL>
 __device__ __forceinline__ void tc_epilogue(uint32_t acc, uint64_t* acc_bar, uint32_t& acc_phase, float* red, float* z,
-                                            float* zpart, uint32_t* gcnt, uint32_t& gepoch, int cta, int warp, int lane,
-                                            int tid) {
+                                            float* zpart, uint32_t* gcnt, uint32_t& gepoch, float* xch, uint64_t* xbar,
+                                            int cta, int warp, int lane, int tid) {
     const int member = cta % GS, group = cta / GS;
     constexpr int EW = 2 * BP / 32;                     // warps whose TMEM lane quarter holds rows
     constexpr int PB = BP <= 32 ? 4 : 2;                // 32-column blocks staged in `red` per pass
     constexpr int RS = PB * 32 + 1;                     // red row stride
+    constexpr int SLICE = ROWS_PER_CTA * BP;            // floats of one member's partial
     static_assert(2 * BP * RS * 4 <= Smem<BP, __nv_bfloat16, true>::RED_BYTES, "epilogue staging must fit the red region");
     if (warp < EW) {
         mbar_wait(acc_bar, acc_phase);
         umma::fence_after_sync();
     }
     acc_phase ^= 1u;
+    const uint32_t xch_local = smem_u32(xch);
 #pragma unroll 1
     for (int pass = 0; pass < GS / PB; ++pass) {
         if (warp < EW) {
@@ -1313,43 +1318,71 @@ __device__ __forceinline__ void tc_epilogue(uint32_t acc, uint64_t* acc_bar, uin
         }
         consumer_sync();
         // hi + lo rows; columns [32*dst, 32*dst+32) are the gate rows of member dst
-        for (int i = tid; i < PB * ROWS_PER_CTA * BP; i += NTC) {
-            const int b = i % BP, c = (i / BP) % ROWS_PER_CTA, cbl = i / (BP * ROWS_PER_CTA);
+        for (int i = tid; i < PB * SLICE; i += NTC) {
+            const int b = i % BP, c = (i / BP) % ROWS_PER_CTA, cbl = i / SLICE;
             const int dst = pass * PB + cbl;
             const float v = red[b * RS + cbl * 32 + c] + red[(BP + b) * RS + cbl * 32 + c];
-            if (dst == member) z[c * BP + b] = v;       // own slice stays in shared memory
-            else zpart[(((size_t)(group * GS + dst)) * GS + member) * (ROWS_PER_CTA * BP) + c * BP + b] = v;
+            if constexpr (CL) {
+                // slot `member` of dst's exchange buffer (the own slot is a plain local store through the same window)
+                st_cluster_f32(mapa_u32(xch_local + (uint32_t)(member * SLICE + c * BP + b) * 4u, (uint32_t)dst), v);
+            } else {
+                if (dst == member) z[c * BP + b] = v;       // own slice stays in shared memory
+                else zpart[(((size_t)(group * GS + dst)) * GS + member) * SLICE + c * BP + b] = v;
+            }
         }
         consumer_sync();
     }
-    // group rendezvous: all four partial slices are in L2
     gepoch += 1;
-    if (tid == 0) {
-        red_release_add_u32(gcnt + group, 1u);
-        const uint32_t target = gepoch * GS;
-        if (ld_acquire_u32(gcnt + group) < target) {
+    if constexpr (CL) {
+        // the stores of all consumer threads are ordered before thread 0's release by the bar.sync above
+        if (tid == 0) {
+            const uint32_t bar_local = smem_u32(xbar);
+#pragma unroll
+            for (int r = 1; r < GS; ++r) mbar_arrive_remote_release(mapa_u32(bar_local, (uint32_t)((member + r) % GS)));
+        }
+        const uint32_t parity = (gepoch - 1u) & 1u;
+        if (!mbar_try_wait_acquire_cluster(xbar, parity)) {
             const uint64_t t0 = global_timer_ns();
-            while (ld_acquire_u32(gcnt + group) < target) {
+            while (!mbar_try_wait_acquire_cluster(xbar, parity)) {
                 if (global_timer_ns() - t0 > SPIN_TIMEOUT_NS) spin_fail();
             }
         }
-    }
-    consumer_sync();
-    for (int i = tid; i < ROWS_PER_CTA * BP; i += NTC) {
-        float accv = 0.f;
+        for (int i = tid; i < SLICE; i += NTC) {
+            float accv = 0.f;
 #pragma unroll
-        for (int src = 0; src < GS; ++src) {            // fixed order: bitwise reproducible
-            const float v = src == member ? z[i] : __ldcg(zpart + ((size_t)cta * GS + src) * (ROWS_PER_CTA * BP) + i);
-            accv += v;
+            for (int src = 0; src < GS; ++src) accv += xch[src * SLICE + i];      // fixed order: bitwise reproducible
+            z[i] = accv;
         }
-        red[i] = accv;
+        consumer_sync();
+    } else {
+        // group rendezvous: all four partial slices are in L2
+        if (tid == 0) {
+            red_release_add_u32(gcnt + group, 1u);
+            const uint32_t target = gepoch * GS;
+            if (ld_acquire_u32(gcnt + group) < target) {
+                const uint64_t t0 = global_timer_ns();
+                while (ld_acquire_u32(gcnt + group) < target) {
+                    if (global_timer_ns() - t0 > SPIN_TIMEOUT_NS) spin_fail();
+                }
+            }
+        }
+        consumer_sync();
+        for (int i = tid; i < SLICE; i += NTC) {
+            float accv = 0.f;
+#pragma unroll
+            for (int src = 0; src < GS; ++src) {            // fixed order: bitwise reproducible
+                const float v = src == member ? z[i] : __ldcg(zpart + ((size_t)cta * GS + src) * SLICE + i);
+                accv += v;
+            }
+            red[i] = accv;
+        }
+        consumer_sync();
+        for (int i = tid; i < SLICE; i += NTC) z[i] = red[i];
+        consumer_sync();
     }
-    consumer_sync();
-    for (int i = tid; i < ROWS_PER_CTA * BP; i += NTC) z[i] = red[i];
-    consumer_sync();
 }
 
-template <int BP>
+template <int BP, bool CL>
 __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
     using WT = __nv_bfloat16;
     using SM = Smem<BP, WT, true>;
@@ -1375,6 +1408,8 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
     float* bias_s = reinterpret_cast<float*>(smem + SM::OFF_BIAS);
     float* wq_s = reinterpret_cast<float*>(smem + SM::OFF_WQ);
     float* wproj_s = reinterpret_cast<float*>(smem + SM::OFF_WPROJ);
+    float* wpc_s = wproj_s + 656;
+    float* cx_s = h_s + 8 * BP;
     float* wloc_s = reinterpret_cast<float*>(smem + SM::OFF_WLOC);
     float* wld_s = reinterpret_cast<float*>(smem + SM::OFF_WLD);
     float* v_s = reinterpret_cast<float*>(smem + SM::OFF_V);
@@ -1383,7 +1418,9 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_TMEM);
     uint64_t* bar_dec = reinterpret_cast<uint64_t*>(smem + SM::OFF_ACCBAR + 16);
     uint64_t* bar_exit = reinterpret_cast<uint64_t*>(smem + SM::OFF_ACCBAR + 24);
-    static_assert(SM::OFF_ACCBAR + 32 <= 256, "barrier area");
+    uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + SM::OFF_ACCBAR + 32);
+    float* xch = reinterpret_cast<float*>(smem + SM::OFF_XCH);
+    static_assert(SM::OFF_ACCBAR + 40 <= 256, "barrier area");
 
     // ---- one-time setup ----
     if (tid == 0) {
@@ -1394,6 +1431,7 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
         mbar_init(bar_attn, 1);
         mbar_init(bar_dec, 1);
         mbar_init(bar_exit, 1);
+        mbar_init(xbar, GS - 1);                 // one remote arrive per peer and exchange
         fence_mbar_init();
         misc_s[1] = 0;
     }
@@ -1407,17 +1445,13 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
         }
         for (int i = tid; i < 128 * 8; i += NT_TC) wq_s[i] = p.wq_slices[(size_t)cta * 1024 + i];
         for (int i = tid; i < PROJ_OUT * 8; i += NT_TC) wproj_s[i] = p.wproj_slices[(size_t)cta * PROJ_OUT * 8 + i];
-    } else {
-        const int nspare = ncta - GEMM_CTAS, sidx = cta - GEMM_CTAS;
-        const int rows_per = (PROJ_OUT + nspare - 1) / nspare;
-        const int o0 = sidx * rows_per, nrow = max(0, min(PROJ_OUT, o0 + rows_per) - o0);
-        float* wsm = reinterpret_cast<float*>(pipe.stages);
-        for (int i = tid; i < nrow * EMB; i += NT_TC) wsm[i] = p.wproj_ctxT[(size_t)(i % EMB) * PROJ_PAD + o0 + i / EMB];
+        for (int i = tid; i < PROJ_OUT * 4; i += NT_TC) wpc_s[i] = p.wproj_ctxT[(size_t)(4 * cta + (i & 3)) * PROJ_PAD + (i >> 2)];
     }
     for (int i = tid; i < LOC_F * 2 * LOC_K; i += NT_TC) wloc_s[(i / 62) * 63 + (i % 62)] = p.loc_conv[i];
     for (int i = tid; i < LOC_F * ATT_DIM; i += NT_TC) wld_s[i] = p.loc_denseT[i];
     for (int i = tid; i < 130; i += NT_TC) v_s[i] = p.attn_v[i];
     __syncthreads();
+    if constexpr (CL) cluster_sync_all();        // peers' mbarriers are initialised before anyone arrives on them
     umma::fence_after_sync();
     const uint32_t tmem = is_gemm ? *tmem_slot : 0u;
     const uint32_t acc_attn = tmem, acc_dec = tmem + GN;
@@ -1494,7 +1528,8 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
                 __syncwarp();
             } else {
                 FT_RESET();
-                tc_epilogue<BP>(acc_attn, bar_attn, ph_attn, red, z_s, p.zpart, p.ctrl + CTRL_GCNT, gepoch, cta, warp, lane, tid);
+                tc_epilogue<BP, CL>(acc_attn, bar_attn, ph_attn, red, z_s, p.zpart, p.ctrl + CTRL_GCNT, gepoch, xch, xbar, cta, warp,
+                                    lane, tid);
                 FT(9);
                 lstm_pointwise<BP, true>(z_s, bias_s, ca_s, h_s, nullptr, act16_cur, ACT_AH + cta * UNITS_PER_CTA, B, tid);
                 FT(10);
@@ -1546,24 +1581,26 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
                 }
                 __syncwarp();
             } else {
+                for (int i = tid; i < 4 * B; i += NTC) cx_s[(i & 3) * BP + (i >> 2)] = __ldcg(p.ctx_bj + (size_t)(i >> 2) * EMB + 4 * cta + (i & 3));
                 FT_RESET();
-                tc_epilogue<BP>(acc_dec, bar_dec, ph_dec, red, z_s, p.zpart, p.ctrl + CTRL_GCNT, gepoch, cta, warp, lane, tid);
+                tc_epilogue<BP, CL>(acc_dec, bar_dec, ph_dec, red, z_s, p.zpart, p.ctrl + CTRL_GCNT, gepoch, xch, xbar, cta, warp,
+                                    lane, tid);
                 FT(12);
                 lstm_pointwise<BP, true>(z_s, bias_s + 32, cd_s, h_s, nullptr, act16_prv, ACT_DH + cta * UNITS_PER_CTA, B, tid);
                 FT(13);
-                // this CTA's slice of linear_projection / gate_layer (src/model.py:272-274)
+                // this CTA's slice of linear_projection / gate_layer (src/model.py:272-274): 8 decoder-h units + 4 context rows
                 for (int i = tid; i < PROJ_PAD * B; i += NTC) {
                     const int o = i % PROJ_PAD, b = i / PROJ_PAD;
                     if (o < PROJ_OUT) {
                         float sum = 0.f;
 #pragma unroll
                         for (int u = 0; u < UNITS_PER_CTA; ++u) sum = fmaf(wproj_s[o * 8 + u], h_s[u * BP + b], sum);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) sum = fmaf(wpc_s[o * 4 + j], cx_s[j * BP + b], sum);
                         p.melpart[((size_t)b * GEMM_CTAS + cta) * PROJ_PAD + o] = sum;
                     }
                 }
             }
-        } else if (is_consumer) {
-            spare_melctx(p, pipe.stages, cta, ncta, warp, lane);
         }
         grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
         stamp(2);
@@ -1609,13 +1646,59 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
     }
     umma::fence_before_sync();
     __syncthreads();
+    if constexpr (CL) cluster_sync_all();        // no CTA leaves while a peer may still write into its shared memory
     if (is_gemm && warp == 0) umma::tmem_dealloc(tmem, 2 * GN);
 }
 
+// Cooperative launch with the split-K groups as thread-block clusters of GS CTAs.  The grid is the largest
+// multiple of GS that is co-resident (B200: 33 clusters = 132 CTAs at this shared-memory size).
 template <int BP>
-int launch_tc(const KParams& kp, int ncta, cudaStream_t stream) {
+int tc_cluster_ctas(int num_sms) {
     using SM = Smem<BP, __nv_bfloat16, true>;
-    auto kern = decoder_tc_kernel<BP>;
+    auto kern = decoder_tc_kernel<BP, true>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(num_sms / GS * GS);
+    cfg.blockDim = dim3(NT_TC);
+    cfg.dynamicSmemBytes = SM::TOTAL;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = GS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int ncl = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    const int ctas = ncl * GS;
+    return ctas > num_sms / GS * GS ? num_sms / GS * GS : ctas;
+}
+
+template <int BP>
+int launch_tc(const KParams& kp, int ncta, bool clusters, cudaStream_t stream) {
+    using SM = Smem<BP, __nv_bfloat16, true>;
+    if (clusters) {
+        auto kern = decoder_tc_kernel<BP, true>;
+        TACO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(ncta);
+        cfg.blockDim = dim3(NT_TC);
+        cfg.dynamicSmemBytes = SM::TOTAL;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = GS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeCooperative;
+        at[1].val.cooperative = 1;
+        cfg.attrs = at; cfg.numAttrs = 2;
+        TACO_CUDA(cudaLaunchKernelEx(&cfg, kern, kp));
+        launch_counter()++;
+        return B200TACO_OK;
+    }
+    auto kern = decoder_tc_kernel<BP, false>;
     TACO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     int per_sm = 0;
     TACO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT_TC, SM::TOTAL));
@@ -1665,7 +1748,7 @@ int dispatch_bp(int BP, const KParams& kp, int ncta, cudaStream_t stream) {
 
 struct ScratchLayout {
     size_t act16, zpart;
-    size_t act, pqpart, melpart, melctx, ctx_bj, attn_prev, attn_cum, wtmp, apart, ctrl, total;
+    size_t act, pqpart, melpart, ctx_bj, attn_prev, attn_cum, wtmp, apart, ctrl, total;
     size_t zero_begin, zero_end;
 };
 
@@ -1685,7 +1768,6 @@ ScratchLayout scratch_layout(int B, int T) {
     L.zero_end = off;
     L.pqpart = take((size_t)B * GEMM_CTAS * ATT_DIM * 4);
     L.melpart = take((size_t)B * GEMM_CTAS * PROJ_PAD * 4);
-    L.melctx = take((size_t)B * PROJ_PAD * 4);
     L.ctx_bj = take((size_t)B * EMB * 4);
     L.wtmp = take((size_t)B * Tp * 4);
     L.apart = take((size_t)B * MAX_NS * APART * 4);
@@ -1730,8 +1812,19 @@ int decoder_run(const b200taco_handle* h, const DecoderArgs& a, cudaStream_t str
     const ScratchLayout L = scratch_layout(a.B, a.T);
     TACO_REQUIRE(a.scratch_bytes >= L.total, B200TACO_ERR_STATE, "decoder scratch too small: %zu < %zu",
                  a.scratch_bytes, L.total);
-    const int ncta = h->num_sms;
+    int ncta = h->num_sms;
     const int BP = decoder_batch_pad(a.B);
+    // tensor-core path: split-K groups as thread-block clusters (DSMEM exchange) when enough clusters are
+    // co-resident to hold the 128 GEMM CTAs plus at least one cluster of spare CTAs; TACO_TC_CLUSTERS=0 disables
+    bool clusters = false;
+    if (decoder_uses_tensor_cores(h, a.B)) {
+        static const bool allow = [] { const char* e = getenv("TACO_TC_CLUSTERS"); return !(e && e[0] == '0'); }();
+        const int cl = allow ? (BP == 32 ? tc_cluster_ctas<32>(h->num_sms) : tc_cluster_ctas<64>(h->num_sms)) : 0;
+        if (cl >= GEMM_CTAS) {
+            clusters = true;
+            ncta = cl;
+        }
+    }
     uint8_t* base = static_cast<uint8_t*>(a.scratch);
     TACO_CUDA(cudaMemsetAsync(base + L.zero_begin, 0, L.zero_end - L.zero_begin, stream));
 
@@ -1759,7 +1852,6 @@ int decoder_run(const b200taco_handle* h, const DecoderArgs& a, cudaStream_t str
     kp.zpart = reinterpret_cast<float*>(base + L.zpart);
     kp.pqpart = reinterpret_cast<float*>(base + L.pqpart);
     kp.melpart = reinterpret_cast<float*>(base + L.melpart);
-    kp.melctx = reinterpret_cast<float*>(base + L.melctx);
     kp.ctx_bj = reinterpret_cast<float*>(base + L.ctx_bj);
     kp.attn_prev = reinterpret_cast<float*>(base + L.attn_prev);
     kp.attn_cum = reinterpret_cast<float*>(base + L.attn_cum);
@@ -1769,8 +1861,8 @@ int decoder_run(const b200taco_handle* h, const DecoderArgs& a, cudaStream_t str
     const_cast<b200taco_handle*>(h)->last_profile = reinterpret_cast<const unsigned long long*>(kp.ctrl + CTRL_PROF);
     if (decoder_uses_tensor_cores(h, a.B)) {
         TACO_REQUIRE(h->w_attn_tc && h->w_dec_tc, B200TACO_ERR_STATE, "tensor-core weights not packed");
-        if (BP == 32) return launch_tc<32>(kp, ncta, stream);
-        return launch_tc<64>(kp, ncta, stream);
+        if (BP == 32) return launch_tc<32>(kp, ncta, clusters, stream);
+        return launch_tc<64>(kp, ncta, clusters, stream);
     }
     if (h->weight_dtype == 1) return dispatch_bp<float>(BP, kp, ncta, stream);
     return dispatch_bp<__nv_bfloat16>(BP, kp, ncta, stream);

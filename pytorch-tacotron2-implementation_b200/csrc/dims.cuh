@@ -26,7 +26,7 @@ constexpr int MAX_TEXT_LEN = 1024;   // encoder positions per utterance
 constexpr int GEMM_CTAS = 128;       // CTAs that own LSTM gate rows
 constexpr int UNITS_PER_CTA = RNN / GEMM_CTAS;     // 8 hidden units ...
 constexpr int ROWS_PER_CTA = 4 * UNITS_PER_CTA;    // ... = 32 gate rows (i,f,g,o of each unit)
-constexpr int MIN_CTAS = 136;        // GEMM CTAs + at least 8 spare CTAs for the ctx part of the projections
+constexpr int MIN_CTAS = GEMM_CTAS;  // every CTA beyond these only takes attention / projection work items
 
 // Activation exchange vector ("act"), one column per utterance:
 //   [ prenet out | context | attention h | decoder h ]
