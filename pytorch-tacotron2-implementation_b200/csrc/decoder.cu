@@ -594,12 +594,14 @@ __device__ __forceinline__ void gemm_tc(const Pipe& pipe, uint32_t& g, int nchun
 // P2: location-sensitive attention (src/model.py:117-148), consumer warps of every CTA.  One work item per
 // (utterance, slice of encoder positions); partial softmax/context per slice, the last slice to arrive
 // (atomic ticket) merges them - no extra grid barrier.
-template <int BP, bool TC>
+template <int BP, bool TC, bool CL = false>
 __device__ __forceinline__ void attention_phase(const KParams& p, float* red, const float* wld_s, const float* wloc_s,
                                                 const float* v_s, int* misc_s, int cur, int out_idx, int cta, int ncta,
                                                 int tid, int warp, int lane, float* act_cur, __nv_bfloat16* act16_cur,
                                                 bool timing, unsigned long long* t_fine, unsigned long long& t_flast,
-                                                volatile int* sig = nullptr, int sig_val = 0) {
+                                                volatile int* sig = nullptr, int sig_val = 0, float* apx = nullptr,
+                                                uint64_t* xbar2 = nullptr) {
+    static_assert(!CL || TC, "cluster merge belongs to the tensor-core kernel");
     // sig: set to sig_val once this CTA's latency-critical loads (pq partials, windows, first pm tile) have landed;
     // the tensor-core kernel's producer warp starts its background weight streaming only then
     const int B = p.B, T = p.T, prv = cur ^ 1;
@@ -765,27 +767,95 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
                 cacc.x = fmaf(ew, mv0[j].x, cacc.x);
                 cacc.y = fmaf(ew, mv0[j].y, cacc.y);
             }
-            int i = 20;
-            for (; i + 20 <= n; i += 20) {                    // 20 rows (40 KB per CTA) in flight
+            // remaining rows, 20 (40 KB per CTA) in flight at a time; the last batch is predicated, not serialised
+            for (int i = 20; i < n; i += 20) {
                 float2 mv[20];
 #pragma unroll
-                for (int j = 0; j < 20; ++j) mv[j] = __ldg(mrow + (size_t)(i + j) * (EMB / 2));
+                for (int j = 0; j < 20; ++j)
+                    mv[j] = i + j < n ? __ldg(mrow + (size_t)(i + j) * (EMB / 2)) : make_float2(0.f, 0.f);
 #pragma unroll
                 for (int j = 0; j < 20; ++j) {
-                    const float ew = sc[P2Scratch::E + i + j];
+                    const float ew = i + j < n ? sc[P2Scratch::E + i + j] : 0.f;
                     cacc.x = fmaf(ew, mv[j].x, cacc.x);
                     cacc.y = fmaf(ew, mv[j].y, cacc.y);
                 }
             }
-#pragma unroll 4
-            for (; i < n; ++i) {
-                const float2 mv = __ldg(mrow + (size_t)i * (EMB / 2));
-                const float ew = sc[P2Scratch::E + i];
-                cacc.x = fmaf(ew, mv.x, cacc.x);
-                cacc.y = fmaf(ew, mv.y, cacc.y);
-            }
         }
         if (TACO_SIG_POINT == 2 && sig != nullptr && tid == 0) *sig = sig_val;
+        if constexpr (CL) {
+            // The NS (2 or 4) slices of an utterance sit in one thread-block cluster (CTA = item).  Every slice
+            // sends its partial (max, sum, un-normalised context) to all its siblings through DSMEM and arrives on
+            // their mbarriers; then every CTA finishes ITS OWN share: the attention weights of its positions and
+            // 512/NS context rows.  No ticket atomic, no partials through L2.
+            if (NS > 1) {
+                const uint32_t rank = (uint32_t)cta % GS, base = rank / (uint32_t)NS * (uint32_t)NS;
+                const uint32_t slot = smem_u32(apx) + (uint32_t)sl * APART * 4u;
+                for (int q = 0; q < NS; ++q) {
+                    const uint32_t dst = mapa_u32(slot, base + q);
+                    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(dst + (4u + 2u * tid) * 4u), "f"(cacc.x),
+                                 "f"(cacc.y)
+                                 : "memory");
+                    if (tid == 0) {
+                        st_cluster_f32(dst, sc[P2Scratch::SC + 32]);
+                        st_cluster_f32(dst + 4u, sc[P2Scratch::SC + 33]);
+                    }
+                }
+                consumer_sync();
+                if (tid == 0) {
+                    const uint32_t bar_local = smem_u32(xbar2);
+                    for (int q = 0; q < NS; ++q)
+                        if (q != sl) mbar_arrive_remote_release(mapa_u32(bar_local, base + q));
+                }
+                if (!mbar_try_wait_acquire_cluster(xbar2, (uint32_t)cur)) {
+                    const uint64_t tw0 = global_timer_ns();
+                    while (!mbar_try_wait_acquire_cluster(xbar2, (uint32_t)cur)) {
+                        if (global_timer_ns() - tw0 > SPIN_TIMEOUT_NS) spin_fail();
+                    }
+                }
+        FT(6);
+                float M = -INFINITY;
+                for (int q = 0; q < NS; ++q) M = fmaxf(M, apx[q * APART]);
+                float scale[GS], S = 0.f;
+#pragma unroll
+                for (int q = 0; q < GS; ++q) {
+                    scale[q] = q < NS ? expf(apx[q * APART] - M) : 0.f;
+                    S += q < NS ? scale[q] * apx[q * APART + 1] : 0.f;
+                }
+                const float mine = expf(sc[P2Scratch::SC + 32] - M);
+                // attention weights of this slice: alignment output, prev, cum (src/model.py:142-145)
+                for (int i = tid; i < n; i += NTC) {
+                    const int t = t0 + i;
+                    const float w = sc[P2Scratch::E + i] * mine / S;
+                    prev_out[(size_t)b * p.Tp + t] = w;
+                    cum_out[(size_t)b * p.Tp + t] = __ldcg(cum_in + (size_t)b * p.Tp + t) + w;
+                    if (out_idx >= 0) p.align[((size_t)out_idx * B + b) * T + t] = w;
+                }
+                // context rows [sl * 512/NS, (sl+1) * 512/NS)
+                const int per = EMB / NS;
+                for (int d2 = tid; d2 < per / 2; d2 += NTC) {
+                    const int d = sl * per + 2 * d2;
+                    float2 c = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int q = 0; q < GS; ++q) {
+                        if (q < NS) {
+                            const float2 v = *reinterpret_cast<const float2*>(apx + q * APART + 4 + d);
+                            c.x = fmaf(scale[q], v.x, c.x);
+                            c.y = fmaf(scale[q], v.y, c.y);
+                        }
+                    }
+                    c.x = c.x / S;
+                    c.y = c.y / S;
+                    __nv_bfloat16 hx, lx, hy, ly;
+                    umma::split_bf16(c.x, hx, lx);
+                    umma::split_bf16(c.y, hy, ly);
+                    *reinterpret_cast<__nv_bfloat162*>(act16_cur + act16_off<BP>(b, ACT_CTX + d)) = __nv_bfloat162(hx, hy);
+                    *reinterpret_cast<__nv_bfloat162*>(act16_cur + act16_off<BP>(BP + b, ACT_CTX + d)) = __nv_bfloat162(lx, ly);
+                    *reinterpret_cast<float2*>(p.ctx_bj + (size_t)b * EMB + d) = c;
+                }
+        FT(8);
+                continue;
+            }
+        }
         float* part = p.apart + ((size_t)b * MAX_NS + sl) * APART;
         if (NS > 1) {
             reinterpret_cast<float2*>(part + 4)[tid] = cacc;
@@ -878,6 +948,17 @@ __device__ __forceinline__ void projection_phase(const KParams& p, float* red, b
     for (int item = cta; item < B * NQ; item += ncta) {
         const int b = item / NQ, q = item % NQ;
         consumer_sync();
+        // The prenet weights stream from L2 every step; their loads do not depend on this step's values, so each
+        // batch is issued one stage ahead of its use (first half of layer 1 before the partial sums, second half
+        // of layer 1 and the first batch of layer 2 before layer 1 is finished).
+        const float* w1src = p.prenet1T + tid;
+        const int nl = tid % RQ, kg = tid / RQ, kn = PRENET / NQ;
+        const float* w2src = p.prenet2T + (size_t)(kg * kn) * PRENET + q * RQ + nl;
+        float w1a[40];
+        if (!tf) {
+#pragma unroll
+            for (int i = 0; i < 40; ++i) w1a[i] = __ldg(w1src + (size_t)i * PRENET);
+        }
         {
             const int o = tid & 127, ig = tid >> 7;
             if (o < PROJ_OUT) {
@@ -910,33 +991,34 @@ __device__ __forceinline__ void projection_phase(const KParams& p, float* red, b
             }
         }
         if (tf) continue;
+        // second half of layer 1 and first batch of layer 2: in flight over the barrier and the first-half FMAs
+        float w1b[40], w2a[32];
+#pragma unroll
+        for (int i = 0; i < 40; ++i) w1b[i] = __ldg(w1src + (size_t)(40 + i) * PRENET);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) w2a[i] = __ldg(w2src + (size_t)i * PRENET);
         consumer_sync();
         // prenet layer 1 (all 256 outputs in every quarter CTA), eval mode: no dropout (F4)
         {
-            const float* wsrc = p.prenet1T + tid;
             float acc = 0.f;
-#pragma unroll 1
-            for (int o0 = 0; o0 < N_MELS; o0 += 40) {
-                float w[40];
 #pragma unroll
-                for (int i = 0; i < 40; ++i) w[i] = __ldg(wsrc + (size_t)(o0 + i) * PRENET);
+            for (int i = 0; i < 40; ++i) acc = fmaf(w1a[i], sc[256 + i], acc);
 #pragma unroll
-                for (int i = 0; i < 40; ++i) acc = fmaf(w[i], sc[256 + o0 + i], acc);
-            }
+            for (int i = 0; i < 40; ++i) acc = fmaf(w1b[i], sc[256 + 40 + i], acc);
             sc[384 + tid] = fmaxf(acc, 0.f);
         }
         consumer_sync();
         // prenet layer 2: this CTA's RQ outputs, k split over NQ thread groups
         {
-            const int nl = tid % RQ, kg = tid / RQ, kn = PRENET / NQ;
-            const float* wsrc = p.prenet2T + (size_t)(kg * kn) * PRENET + q * RQ + nl;
             const float* x = sc + 384 + kg * kn;
             float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc = fmaf(w2a[i], x[i], acc);
 #pragma unroll 1
-            for (int m0 = 0; m0 < kn; m0 += 32) {
+            for (int m0 = 32; m0 < kn; m0 += 32) {
                 float w[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) w[i] = __ldg(wsrc + (size_t)(m0 + i) * PRENET);
+                for (int i = 0; i < 32; ++i) w[i] = __ldg(w2src + (size_t)(m0 + i) * PRENET);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) acc = fmaf(w[i], x[m0 + i], acc);
             }
@@ -1419,8 +1501,10 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
     uint64_t* bar_dec = reinterpret_cast<uint64_t*>(smem + SM::OFF_ACCBAR + 16);
     uint64_t* bar_exit = reinterpret_cast<uint64_t*>(smem + SM::OFF_ACCBAR + 24);
     uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + SM::OFF_ACCBAR + 32);
+    uint64_t* xbar2 = reinterpret_cast<uint64_t*>(smem + SM::OFF_ACCBAR + 40);
     float* xch = reinterpret_cast<float*>(smem + SM::OFF_XCH);
-    static_assert(SM::OFF_ACCBAR + 40 <= 256, "barrier area");
+    static_assert(SM::OFF_ACCBAR + 48 <= 256, "barrier area");
+    static_assert(GS * APART * 4 <= SM::XCH_BYTES, "attention partials of the slice siblings alias the exchange buffer");
 
     // ---- one-time setup ----
     if (tid == 0) {
@@ -1432,6 +1516,7 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
         mbar_init(bar_dec, 1);
         mbar_init(bar_exit, 1);
         mbar_init(xbar, GS - 1);                 // one remote arrive per peer and exchange
+        mbar_init(xbar2, p.NS > 1 ? p.NS - 1 : 1);   // attention merge: one arrive per sibling slice and step
         fence_mbar_init();
         misc_s[1] = 0;
     }
@@ -1557,8 +1642,8 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
             if (lane == 0) TP::consume(pipe, g, 4, acc_dec, false);
             __syncwarp();
         } else if (is_consumer) {
-            attention_phase<BP, true>(p, red, wld_s, wloc_s, v_s, misc_s, cur, out_idx, cta, ncta, tid, warp, lane, act_cur,
-                                      act16_cur, timing, TACO_FINE_ARGS, misc_s + 1, 2 * s + 1);
+            attention_phase<BP, true, CL>(p, red, wld_s, wloc_s, v_s, misc_s, cur, out_idx, cta, ncta, tid, warp, lane, act_cur,
+                                          act16_cur, timing, TACO_FINE_ARGS, misc_s + 1, 2 * s + 1, xch, xbar2);
         }
         grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
         stamp(1);
@@ -1834,6 +1919,10 @@ int decoder_run(const b200taco_handle* h, const DecoderArgs& a, cudaStream_t str
     ns = ns < 1 ? 1 : (ns > MAX_NS ? MAX_NS : ns);
     // keep slices at least 8 positions long
     while (ns > 1 && (a.T + ns - 1) / ns < 8) --ns;
+    if (clusters) {
+        // the slices of an utterance must sit inside one cluster (CTA = work item): 1, 2 or 4 slices
+        ns = ns >= 4 ? 4 : (ns >= 2 ? 2 : 1);
+    }
     kp.NS = ns;
     kp.SL = (a.T + ns - 1) / ns;
     int nq = ncta / a.B;
