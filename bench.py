@@ -69,6 +69,8 @@ class ClockSampler:
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):
+        if os.environ.get("BENCH_NO_SAMPLER"):
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -174,14 +176,15 @@ def run_b200(args, rank, world, local_rank):
     eng.launch_count(reset=True)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    frames, dec_events, dec_steps = 0, [], 0
+    frames, dec_events, dec_steps, all_lengths = 0, [], 0, []
     for _ in range(args.steps):
         lengths, S, ev, _ = step_resident()
-        frames += int(lengths.sum().item())
+        all_lengths.append(lengths)             # summed after the timed region (no extra host sync per step)
         dec_events.append(ev)
         dec_steps += S + 1                      # + the discarded first decode step (F6)
     t1.record()
     barrier()
+    frames = int(torch.stack(all_lengths).sum().item())
     launches = eng.launch_count()
     clocks = sampler.stop()
     ms = t0.elapsed_time(t1)

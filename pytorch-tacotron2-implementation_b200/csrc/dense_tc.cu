@@ -349,7 +349,7 @@ int conv1d_channels_last_tc(const float* X, int ldx, const float* Wtc, const flo
                  "conv1d (tensor-core path): unsupported shape c_in %d c_out %d ldx %d ldy %d", c_in, c_out, ldx, ldy);
     if (n_rows <= 0) return B200TACO_OK;
     const int mtiles = (n_rows + TM - 1) / TM;
-    // num_sms == 0 ("precise"): always the narrowest tile = 8 accumulators; used for the encoder, whose output
+    // num_sms == 0 ("precise"): always the narrowest tile = 16 accumulators; used for the encoder, whose output
     // feeds a 1000-step recurrence (measured |error| vs fp32 SIMT: 8e-7 at NT=64, 3e-6 at NT=256)
     if (c_out == 80)
         return launch_nt<80>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream);
@@ -359,6 +359,8 @@ int conv1d_channels_last_tc(const float* X, int ldx, const float* Wtc, const flo
         return launch_nt<256>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream);
     if (forced == 128 && c_out % 128 == 0)
         return launch_nt<128>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream);
+    if (forced == 32 && c_out % 32 == 0)
+        return launch_nt<32>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream);
     if (forced == 64)
         return launch_nt<64>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream);
     // wide tiles when there is enough work to fill the machine, narrow ones to spread small problems over more SMs
@@ -366,7 +368,9 @@ int conv1d_channels_last_tc(const float* X, int ldx, const float* Wtc, const flo
         return launch_nt<256>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream);
     if (num_sms > 0 && c_out % 128 == 0 && mtiles * (c_out / 128) >= num_sms)
         return launch_nt<128>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream);
-    return launch_nt<64>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream);
+    if (num_sms > 0 || c_out % 32 != 0)
+        return launch_nt<64>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream);
+    return launch_nt<32>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream);
 }
 
 }  // namespace b200taco
