@@ -131,7 +131,7 @@ B200TACO_API int32_t b200taco_set_weight_dtype(b200taco_handle* h, int32_t dtype
 /*
  * Kernel selection for the LSTM gate contractions of the decoder.  AUTO (default): tcgen05 tensor-core
  * tiles (bf16 operands, hi/lo split activations, fp32 accumulators in TMEM) when the batch is large
- * enough to be a real GEMM (B >= 17) and the weights are stored bf16; the vectorised fp32 SIMT
+ * at least 4 (measured crossover: the batch tile of the tensor-core kernel is 32 rows whatever B) and the weights are stored bf16; the vectorised fp32 SIMT
  * contraction otherwise.  SIMT forces the latter (A/B measurements, bit-for-bit fp32 activations).
  */
 #define B200TACO_PATH_AUTO 0

@@ -113,7 +113,7 @@ class Tacotron2(nn.Module):
         # storage of the decoder LSTM matrices in the packed cache: "bf16" (default, half the
         # L2 traffic per step) or "fp32" (the reference's values bit for bit)
         self.lstm_weight_dtype = "bf16"
-        # "auto": tcgen05 tensor-core gate contractions when B >= 17 and bf16 weights; "simt": never
+        # "auto": tcgen05 tensor-core gate contractions when B >= 4 and bf16 weights; "simt": never
         self.decoder_path = "auto"
         # dense layers: "auto" = postnet / teacher-forced prenet on tcgen05 (3xTF32), encoder on fp32 CUDA cores;
         # "tc" = everything on tcgen05; "simt" = everything on CUDA cores (include/b200taco.h)

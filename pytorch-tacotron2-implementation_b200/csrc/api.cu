@@ -68,7 +68,7 @@ DecoderWs decoder_ws(void* base, int B, int T, int S_tf) {
         w.frames = c.f((size_t)S_tf * B * N_MELS);
         w.y1 = c.f((size_t)S_tf * B * PRENET);
         w.y2 = c.f((size_t)S_tf * B * PRENET);
-        w.p_all = c.f((size_t)S_tf * PRENET * decoder_batch_pad(B));
+        w.p_all = c.f((size_t)S_tf * PRENET * (decoder_batch_pad(B) < 32 ? 32 : decoder_batch_pad(B)));
     }
     w.total = c.off;
     return w;

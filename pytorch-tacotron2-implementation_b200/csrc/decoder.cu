@@ -41,6 +41,7 @@ constexpr int GS = 4;                       // tensor-core path: CTAs per split-
 constexpr int GN = GS * ROWS_PER_CTA;       // gate rows per group = N of one tcgen05.mma (128)
 constexpr int TILE_POS = 40;                // encoder positions per attention tile (8 groups x 5)
 constexpr int MAX_NS = 16;                  // max slices per utterance
+constexpr int TC_MIN_BATCH = 4;             // smallest batch that takes the tensor-core kernel
 constexpr int APART = 4 + EMB;              // per-slice partial: m, s, pad, pad, ctx[512]
 constexpr uint64_t SPIN_TIMEOUT_NS = 4000000000ull;
 
@@ -1846,7 +1847,8 @@ ScratchLayout scratch_layout(int B, int T) {
     // zero-initialised region first (state), then write-before-read buffers
     L.zero_begin = off;
     L.act = take((size_t)2 * ACT_ROWS * BP * 4);
-    L.act16 = take(BP >= 32 ? (size_t)2 * ACT_ROWS * 2 * BP * 2 : 0);     // hi/lo bf16 operand tiles (tensor-core path)
+    const int BPT = BP < 32 ? 32 : BP;                                    // batch tile of the tensor-core path
+    L.act16 = take((size_t)2 * ACT_ROWS * 2 * BPT * 2);                   // hi/lo bf16 operand tiles (tensor-core path)
     L.attn_prev = take((size_t)2 * B * Tp * 4);
     L.attn_cum = take((size_t)2 * B * Tp * 4);
     L.ctrl = take((size_t)CTRL_WORDS * 4);
@@ -1856,7 +1858,7 @@ ScratchLayout scratch_layout(int B, int T) {
     L.ctx_bj = take((size_t)B * EMB * 4);
     L.wtmp = take((size_t)B * Tp * 4);
     L.apart = take((size_t)B * MAX_NS * APART * 4);
-    L.zpart = take(BP >= 32 ? (size_t)GEMM_CTAS * GS * ROWS_PER_CTA * BP * 4 : 0);
+    L.zpart = take((size_t)GEMM_CTAS * GS * ROWS_PER_CTA * BPT * 4);
     L.total = off;
     return L;
 }
@@ -1865,12 +1867,21 @@ ScratchLayout scratch_layout(int B, int T) {
 
 bool decoder_uses_tensor_cores(const b200taco_handle* h, int B) {
     // tcgen05 only where batch x 4H is a real GEMM (north_star c); vectorised SIMT contraction otherwise
+    // (measured, profiles/r1_v8_decoder_phase_times.jsonl: the tensor-core kernel at its minimum batch tile of 32 is
+    // faster than the SIMT kernel from B = TC_MIN_BATCH up; TACO_TC_MIN_B overrides for measurements)
     if (h->decoder_path == 1) return false;
-    return h->weight_dtype == 0 && decoder_batch_pad(B) >= 32;
+    static const int min_b = [] { const char* e = getenv("TACO_TC_MIN_B"); return e ? atoi(e) : TC_MIN_BATCH; }();
+    return h->weight_dtype == 0 && B >= min_b;
+}
+
+// batch tile (columns of the activation operand) of the kernel that will run this batch
+static int batch_tile(const b200taco_handle* h, int B) {
+    const int bp = decoder_batch_pad(B);
+    return decoder_uses_tensor_cores(h, B) && bp < 32 ? 32 : bp;
 }
 
 int decoder_pack_p_all(const b200taco_handle* h, const float* Y, void* P, int B, int S, cudaStream_t stream) {
-    const int BP = decoder_batch_pad(B);
+    const int BP = batch_tile(h, B);
     if (decoder_uses_tensor_cores(h, B))
         p_all_pack_tc_kernel<<<2048, 256, 0, stream>>>(Y, static_cast<__nv_bfloat16*>(P), B, BP, S);
     else
@@ -1898,7 +1909,7 @@ int decoder_run(const b200taco_handle* h, const DecoderArgs& a, cudaStream_t str
     TACO_REQUIRE(a.scratch_bytes >= L.total, B200TACO_ERR_STATE, "decoder scratch too small: %zu < %zu",
                  a.scratch_bytes, L.total);
     int ncta = h->num_sms;
-    const int BP = decoder_batch_pad(a.B);
+    const int BP = batch_tile(h, a.B);
     // tensor-core path: split-K groups as thread-block clusters (DSMEM exchange) when enough clusters are
     // co-resident to hold the 128 GEMM CTAs plus at least one cluster of spare CTAs; TACO_TC_CLUSTERS=0 disables
     bool clusters = false;

@@ -7,7 +7,7 @@ struct b200taco_handle {
     int device = 0;
     int num_sms = 0;
     int weight_dtype = 0;           // 0 = bf16 LSTM matrices (default), 1 = fp32
-    int decoder_path = 0;           // 0 = auto (tcgen05 when batch >= 17 and bf16 weights), 1 = SIMT only
+    int decoder_path = 0;           // 0 = auto (tcgen05 when batch >= 4 and bf16 weights), 1 = SIMT only
     int dense_path = 0;             // 0 = tcgen05 3xTF32 dense layers (dense_tc.cu), 1 = fp32 SIMT (dense.cu)
     bool packed = false;
     const unsigned long long* last_profile = nullptr;   // device: phase timers of the last decoder launch
