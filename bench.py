@@ -232,8 +232,11 @@ def run_b200(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "stages_ms": stages_ms,
             "clocks": clocks,
-            "roofline": {"kernel": "decoder_kernel<32,bf16> (persistent, one launch per batch)", "bound": "hbm",
-                         "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+            "roofline": {"kernel": "decoder_tc_kernel<32> (persistent, one cooperative cluster launch per batch)", "bound": "hbm",
+                         "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch (1001 decode steps, B=32, T=150),
+                         # ncu --set full, profiles/r1_v8_decoder_ncu_full.md: the working set is L2 resident
+                         "traffic": 56_894_976, "traffic_unit": "bytes per launch (ncu, 1001-step launch)",
                          "peak_source": hbm_src, "bytes_per_decode_step": BYTES_PER_STEP_C2,
                          "decode_steps_per_launch": dec_steps / args.steps, "us_per_decode_step": dec_ms * 1e3 / dec_steps,
                          "kernel_share_of_step": dec_ms / ms,
