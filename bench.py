@@ -151,14 +151,21 @@ def run_b200(args, rank, world, local_rank):
         ev[4].record()
         return lengths, S, ev, post
 
+    e2e_host = {}
+
     def step_e2e():
         flush.zero_()
         ids = ids_host.to(dev, non_blocking=True)
         with contextlib.redirect_stdout(io.StringIO()):
             post, coarse, gate, aligns, lengths = model.inference_per_utterance(ids)
-        post_h = post.cpu()
-        lengths_h = lengths.cpu()
-        return int(lengths_h.sum()), post_h
+        # device -> host read of the results into pinned buffers (reused across steps)
+        if e2e_host.get("post") is None or e2e_host["post"].shape != post.shape:
+            e2e_host["post"] = torch.empty(post.shape, dtype=post.dtype, pin_memory=True)
+            e2e_host["lengths"] = torch.empty(lengths.shape, dtype=lengths.dtype, pin_memory=True)
+        e2e_host["post"].copy_(post, non_blocking=True)
+        e2e_host["lengths"].copy_(lengths, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return int(e2e_host["lengths"].sum()), e2e_host["post"]
 
     def barrier():
         if dist is not None:

@@ -24,7 +24,7 @@ from b200taco.model import Tacotron2  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--utterances", type=int, default=8192)
-    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=64)      # rows per launch: a step costs 31 us at 32 rows, 42 us at 64
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     dev = torch.device("cuda", local)

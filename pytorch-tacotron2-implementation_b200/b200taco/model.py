@@ -160,14 +160,29 @@ class Tacotron2(nn.Module):
     # ------------------------------------------------------------------ public API
     @torch.no_grad()
     def forward(self, text_inputs, mel_targets, text_lengths=None, use_postnet=True):
-        """Teacher-forced pass, src/model.py:454-480."""
+        """Teacher-forced pass, src/model.py:454-480.
+
+        Rows are independent in eval mode, so batches beyond the library's per-launch limit
+        (``engine.max_batch`` = 64 rows) run as consecutive launches over row chunks."""
         self._check_mode("Tacotron2.forward")
         if not self._projection_bias_initialized:
             self._maybe_init_projection_bias(mel_targets)
         eng = self._get_engine()
-        memory = eng.encoder(text_inputs)
-        coarse, gate, align = eng.decoder_teacher_forced(memory, mel_targets, text_lengths)
-        post = eng.postnet(coarse) if use_postnet else coarse
+        outs = []
+        for lo in range(0, text_inputs.shape[0], eng.max_batch):
+            hi = lo + eng.max_batch
+            memory = eng.encoder(text_inputs[lo:hi])
+            tl = text_lengths[lo:hi] if text_lengths is not None else None
+            coarse, gate, align = eng.decoder_teacher_forced(memory, mel_targets[lo:hi], tl)
+            post = eng.postnet(coarse) if use_postnet else coarse
+            outs.append((post, coarse, gate, align))
+        if len(outs) == 1:
+            post, coarse, gate, align = outs[0]
+        else:
+            post, coarse, gate = (torch.cat([o[i] for o in outs], dim=0) for i in range(3))
+            align = torch.cat([o[3] for o in outs], dim=1)              # (S, B, T)
+            if not use_postnet:
+                post = coarse                                           # src/model.py:479-480: the same tensor
         return post, coarse, gate, list(align.unbind(0))
 
     @torch.no_grad()
@@ -187,6 +202,35 @@ class Tacotron2(nn.Module):
                                                          STOP_PER_UTTERANCE)
         return post, coarse, gate, list(align.unbind(0)), lengths
 
+    @staticmethod
+    def _infer_chunked(eng, text_inputs, cap, thr, stop_mode):
+        """More rows than one launch carries: rows never interact, so the chunks decode one after the other.
+        Batch-wide stop (src/model.py:327) = the first step at which ANY row fires = the minimum over the chunks'
+        own stop steps; per-utterance stop: every chunk runs to its own longest row, results padded to the longest."""
+        parts = []
+        for lo in range(0, text_inputs.shape[0], eng.max_batch):
+            memory = eng.encoder(text_inputs[lo:lo + eng.max_batch])
+            parts.append(eng.decoder_infer(memory, cap, thr, stop_mode))
+        if stop_mode == STOP_BATCH_WIDE:
+            S = min(p[4] for p in parts)
+            lengths = torch.cat([torch.clamp(p[3], max=S) for p in parts])
+        else:
+            S = max(p[4] for p in parts)
+            lengths = torch.cat([p[3] for p in parts])
+
+        def fit(t, dim):          # truncate / zero-pad along the frame axis
+            n = t.shape[dim]
+            if n >= S:
+                return t.narrow(dim, 0, S)
+            pad = list(t.shape)
+            pad[dim] = S - n
+            return torch.cat([t, t.new_zeros(pad)], dim=dim)
+
+        coarse = torch.cat([fit(p[0], 1) for p in parts], dim=0)
+        gate = torch.cat([fit(p[1], 1) for p in parts], dim=0)
+        align = torch.cat([fit(p[2], 0) for p in parts], dim=1)
+        return coarse, gate, align, lengths, S
+
     def _infer(self, text_inputs, max_len_cap, gate_threshold, stop_mode):
         self._check_mode("Tacotron2.inference")
         thr = gate_threshold if gate_threshold is not None else self.decoder.gate_threshold
@@ -194,8 +238,11 @@ class Tacotron2(nn.Module):
         if max_len_cap:
             cap = min(cap, int(max_len_cap))
         eng = self._get_engine()
-        memory = eng.encoder(text_inputs)
-        coarse, gate, align, lengths, S = eng.decoder_infer(memory, cap, thr, stop_mode)
+        if text_inputs.shape[0] > eng.max_batch:
+            coarse, gate, align, lengths, S = self._infer_chunked(eng, text_inputs, cap, thr, stop_mode)
+        else:
+            memory = eng.encoder(text_inputs)
+            coarse, gate, align, lengths, S = eng.decoder_infer(memory, cap, thr, stop_mode)
         coarse = coarse.contiguous()
         if S >= cap:
             print(f"Warning! Reached decode cap ({cap}).")                  # src/model.py:330

@@ -238,6 +238,28 @@ def test_sharded_exact_length_batches_match_solo_runs():
     assert len(set(want)) > 1                       # the stops really differ between utterances
 
 
+def test_batches_beyond_one_launch_are_chunked():
+    """B > 64 rows: consecutive launches over row chunks reproduce the reference on the whole batch
+    (teacher-forced, and free-running with the batch-wide stop = earliest stop of any chunk)."""
+    B, T = 70, 21
+    ids = synth.phoneme_ids(B, T, seed=21)
+    center = O.encoder(util.weights("stress", True), ids[:2]).mean((0, 1))
+    sd = util.weights("planted", True, ctx_center=center)
+    m = gpu_model(sd)
+    out = m.inference(ids.cuda())
+    ref = O.tacotron2_inference(sd, ids)
+    assert out[1].shape == ref[1].shape and len(out[3]) == len(ref[3])
+    assert util.maxdiff(out[1].cpu(), ref[1]) <= TOL_MEL and util.maxdiff(out[0].cpu(), ref[0]) <= 5 * TOL_MEL
+    assert util.maxdiff(util.stack(out[3]).cpu(), util.stack(ref[3])) <= TOL_ALIGN
+    g = torch.Generator().manual_seed(3)
+    mel = (torch.randn(B, 80, 7, generator=g) * 2 - 5)
+    lens = torch.randint(5, T + 1, (B,), generator=g)
+    out = m(ids.cuda(), mel.cuda(), lens.cuda())
+    ref = O.tacotron2_forward(sd, ids, mel, lens)
+    assert util.maxdiff(out[1].cpu(), ref[1]) <= TOL_MEL and util.maxdiff(out[2].cpu(), ref[2]) <= TOL_MEL
+    assert util.maxdiff(util.stack(out[3]).cpu(), util.stack(ref[3])) <= TOL_ALIGN
+
+
 def test_long_horizon_default_init_1000_steps():
     """Default init never fires (F11): 1000 frames, error must not grow with the horizon."""
     ids = synth.phoneme_ids(2, 150, seed=1)
@@ -277,8 +299,9 @@ def test_errors():
     with pytest.raises(B200TacoError):
         m.inference(ids)
     m.eval()
-    with pytest.raises(B200TacoError):
-        m.inference(synth.phoneme_ids(65, 9).cuda())       # beyond b200taco_max_batch
+    with pytest.raises(B200TacoError):                     # one launch carries at most b200taco_max_batch rows ...
+        m._engine.encoder(synth.phoneme_ids(65, 9).cuda())
+    assert m.inference(synth.phoneme_ids(65, 9).cuda(), max_len_cap=3)[1].shape == (65, 3, 80)   # ... the module chunks
     with pytest.raises(B200TacoError):
         m.inference(synth.phoneme_ids(1, 2000).cuda())     # beyond b200taco_max_text_len
     assert m._engine.launch_count() > 0
