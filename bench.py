@@ -130,7 +130,9 @@ def run_b200(args, rank, world, local_rank):
     model = Tacotron2().eval()
     model._projection_bias_initialized = True
     model = model.to(dev)
-    ids_host = synth.phoneme_ids(B, T, seed=rank).pin_memory()       # every rank decodes its own utterances
+    # weak scaling: per-GPU work is FIXED as N grows, so every rank decodes its own copy of the same synthetic
+    # batch (corpus-level sharding with unequal utterances is BASELINE config 4, profiles/tools/c4_sharded.py)
+    ids_host = synth.phoneme_ids(B, T, seed=0).pin_memory()
     ids_dev = ids_host.to(dev)
     model.load_state_dict(planted_state_dict(model, ids_dev, synth))
     eng = model._get_engine()
@@ -233,7 +235,7 @@ def run_b200(args, rank, world, local_rank):
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "text_len": T, "cap": CAP,
                        "weights": "seed 1234 default init + planted stop counter (rate 8e-4, jitter 6e-3)",
                        "frames_counted": "sum of per-utterance decoded lengths",
-                       "l2": "flushed between steps (256 MiB device memset)", "sharding": f"dp{world}: one batch per rank per step"},
+                       "l2": "flushed between steps (256 MiB device memset)", "sharding": f"dp{world}: one batch per rank per step, same synthetic batch on every rank, no collective"},
             "e2e": {"value": e2e_frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": ids_host.numel() * 8,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
