@@ -294,7 +294,7 @@ struct Pipe {
 };
 
 // Consumer side of one LSTM gate contraction: acc[r][j] += W[k][lr*8+r] * act[k][lb*BPL+j].
-template <int BP, typename WT>
+template <int BP, typename WT, bool ZERO = true>
 __device__ __forceinline__ void gemm_consume(const Pipe& pipe, uint32_t& g, int nchunks, int warp, int lane,
                                              float (&acc)[8][Tile<BP>::BPL]) {
     using TL = Tile<BP, sizeof(WT)>;
@@ -303,10 +303,12 @@ __device__ __forceinline__ void gemm_consume(const Pipe& pipe, uint32_t& g, int 
     const int lk = lane % TL::LK;
     const int lb = (lane / TL::LK) % TL::LB;
     const int lr = lane / (TL::LK * TL::LB);
+    if constexpr (ZERO) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
+        for (int r = 0; r < 8; ++r)
 #pragma unroll
-        for (int j = 0; j < TL::BPL; ++j) acc[r][j] = 0.f;
+            for (int j = 0; j < TL::BPL; ++j) acc[r][j] = 0.f;
+    }
     for (int ch = 0; ch < nchunks; ++ch, ++g) {
         const uint32_t stage = g % STAGES, parity = (g / STAGES) & 1u;
         mbar_wait(&pipe.full[stage], parity);
@@ -601,7 +603,9 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
                                                 int tid, int warp, int lane, float* act_cur, __nv_bfloat16* act16_cur,
                                                 bool timing, unsigned long long* t_fine, unsigned long long& t_flast,
                                                 volatile int* sig = nullptr, int sig_val = 0, float* apx = nullptr,
-                                                uint64_t* xbar2 = nullptr) {
+                                                uint64_t* xbar2 = nullptr, bool rev = false) {
+    // rev: work items are dealt from the LAST CTA downwards, so that the CTAs beyond the 128 GEMM CTAs take them first
+    // (small batches of the SIMT kernel: the GEMM CTAs then spend this phase on their background contractions)
     static_assert(!CL || TC, "cluster merge belongs to the tensor-core kernel");
     // sig: set to sig_val once this CTA's latency-critical loads (pq partials, windows, first pm tile) have landed;
     // the tensor-core kernel's producer warp starts its background weight streaming only then
@@ -614,7 +618,7 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
     float* prev_out = p.attn_prev + (size_t)cur * B * p.Tp;
     float* cum_out = p.attn_cum + (size_t)cur * B * p.Tp;
     FT_RESET();
-    for (int item = cta; item < B * NS; item += ncta) {
+    for (int item = rev ? ncta - 1 - cta : cta; item < B * NS; item += ncta) {
         const int b = item / NS, sl = item % NS;
         const int t0 = sl * SL, t1 = min(T, t0 + SL), n = max(0, t1 - t0);
         const int len = p.text_lengths ? (int)p.text_lengths[b] : T;
@@ -941,12 +945,12 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
 template <int BP, bool TC>
 __device__ __forceinline__ void projection_phase(const KParams& p, float* red, bool tf, int out_idx, int cta, int ncta,
                                                  int tid, float* act_cur, __nv_bfloat16* act16_cur,
-                                                 volatile int* sig = nullptr, int sig_val = 0) {
+                                                 volatile int* sig = nullptr, int sig_val = 0, bool rev = false) {
     const int B = p.B;
     (void)act_cur; (void)act16_cur;
     float* sc = red;
     const int NQ = p.NQ, RQ = PRENET / NQ;
-    for (int item = cta; item < B * NQ; item += ncta) {
+    for (int item = rev ? ncta - 1 - cta : cta; item < B * NQ; item += ncta) {
         const int b = item / NQ, q = item % NQ;
         consumer_sync();
         // The prenet weights stream from L2 every step; their loads do not depend on this step's values, so each
@@ -1795,6 +1799,331 @@ int launch_tc(const KParams& kp, int ncta, bool clusters, cudaStream_t stream) {
     return B200TACO_OK;
 }
 
+
+// =======================================================================================================
+// SIMT decoder kernel with HOISTED gate contractions (batch tile <= 16: B <= 3, or fp32 weights / forced SIMT).
+// Same idea as decoder_tc_kernel, with fp32 register accumulators instead of TMEM: each CTA keeps the partial
+// pre-activations of its 32 gate rows for BOTH LSTMs in registers across the phases and adds every K range as
+// soon as its activations exist:
+//     phase A: += W_a[prenet] . p_t            -> attention LSTM cell      (1792 -> 256 rows on the critical path)
+//     phase B: += W_d[ah] . ah_t,  W_a[ah] . ah_t   (background of the attention phase)
+//     phase C: += W_d[ctx] . ctx_t             -> decoder LSTM cell        (2560 -> 512 rows on the critical path)
+//     phase D: += W_a[ctx] . ctx_t, W_d[dh] . dh_t  (background of the projection phase)
+// Attention / projection work items are dealt from the last CTA downwards (the >= 20 CTAs beyond the GEMM CTAs
+// first), so at B=1 the GEMM CTAs have nothing else to do in phases B and D.
+template <typename SM>
+struct SimtPipe {
+    static constexpr int STAGES = SM::NSTAGES;
+    // producer warp, all 32 lanes; mode 0: weights + activations, 1: weights only, 2: activations only
+    template <typename WT>
+    __device__ static __forceinline__ void produce(const Pipe& pipe, uint32_t g0, int n, int mode, int lane, const WT* wsrc,
+                                                   const uint8_t* abuf, int achunk0) {
+        int c = lane < STAGES ? (lane + STAGES - (int)(g0 % STAGES)) % STAGES : n;
+        const uint64_t t0 = global_timer_ns();
+        while (__any_sync(0xffffffffu, c < n)) {
+            if (c < n) {
+                const uint32_t g = g0 + c, stage = g % STAGES, parity = ((g / STAGES) & 1u) ^ 1u;
+                if (mode == 2 || mbar_test_wait(&pipe.empty[stage], parity)) {
+                    uint8_t* dst = pipe.stages + stage * SM::STAGE_BYTES;
+                    if (mode != 2) {
+                        mbar_arrive_expect_tx(&pipe.full[stage], SM::STAGE_BYTES);
+                        bulk_g2s(dst, reinterpret_cast<const uint8_t*>(wsrc) + (size_t)c * SM::W_BYTES, SM::W_BYTES, &pipe.full[stage]);
+                    }
+                    if (mode != 1)
+                        bulk_g2s(dst + SM::W_BYTES, abuf + (size_t)(achunk0 + c) * SM::A_BYTES, SM::A_BYTES, &pipe.full[stage]);
+                    c += STAGES;
+                } else if (global_timer_ns() - t0 > SPIN_TIMEOUT_NS) {
+                    spin_fail();
+                }
+            }
+        }
+    }
+};
+
+template <int BP, typename WT>
+__global__ void __launch_bounds__(NT, 1) decoder_simt_kernel(const KParams p) {
+    using SM = Smem<BP, WT, false>;
+    using SP = SimtPipe<SM>;
+    using TL = Tile<BP, sizeof(WT)>;
+    constexpr int STAGES = SM::NSTAGES;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cta = blockIdx.x, ncta = gridDim.x;
+    const bool is_gemm = cta < GEMM_CTAS;
+    const bool is_producer = warp == NW;
+    const int B = p.B;
+
+    Pipe pipe;
+    pipe.full = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
+    pipe.empty = pipe.full + STAGES;
+    pipe.stages = smem + SM::OFF_STAGE;
+    float* red = reinterpret_cast<float*>(smem + SM::OFF_RED);
+    float* z_s = reinterpret_cast<float*>(smem + SM::OFF_Z);
+    float* ca_s = reinterpret_cast<float*>(smem + SM::OFF_CA);
+    float* cd_s = reinterpret_cast<float*>(smem + SM::OFF_CD);
+    float* h_s = reinterpret_cast<float*>(smem + SM::OFF_H);
+    float* bias_s = reinterpret_cast<float*>(smem + SM::OFF_BIAS);
+    float* wq_s = reinterpret_cast<float*>(smem + SM::OFF_WQ);
+    float* wproj_s = reinterpret_cast<float*>(smem + SM::OFF_WPROJ);
+    float* wpc_s = wproj_s + 656;
+    float* cx_s = h_s + 8 * BP;
+    float* wloc_s = reinterpret_cast<float*>(smem + SM::OFF_WLOC);
+    float* wld_s = reinterpret_cast<float*>(smem + SM::OFF_WLD);
+    float* v_s = reinterpret_cast<float*>(smem + SM::OFF_V);
+    int* misc_s = reinterpret_cast<int*>(smem + SM::OFF_MISC);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&pipe.full[s], 1);
+            mbar_init(&pipe.empty[s], NW);
+        }
+        fence_mbar_init();
+    }
+    for (int i = tid; i < UNITS_PER_CTA * BP; i += NT) { ca_s[i] = 0.f; cd_s[i] = 0.f; h_s[i] = 0.f; }
+    if (is_gemm) {
+        for (int i = tid; i < 32; i += NT) {
+            bias_s[i] = p.bias_attn[cta * 32 + i];
+            bias_s[32 + i] = p.bias_dec[cta * 32 + i];
+        }
+        for (int i = tid; i < 128 * 8; i += NT) wq_s[i] = p.wq_slices[(size_t)cta * 1024 + i];
+        for (int i = tid; i < PROJ_OUT * 8; i += NT) wproj_s[i] = p.wproj_slices[(size_t)cta * PROJ_OUT * 8 + i];
+        for (int i = tid; i < PROJ_OUT * 4; i += NT) wpc_s[i] = p.wproj_ctxT[(size_t)(4 * cta + (i & 3)) * PROJ_PAD + (i >> 2)];
+    }
+    for (int i = tid; i < LOC_F * 2 * LOC_K; i += NT) wloc_s[(i / 62) * 63 + (i % 62)] = p.loc_conv[i];
+    for (int i = tid; i < LOC_F * ATT_DIM; i += NT) wld_s[i] = p.loc_denseT[i];
+    for (int i = tid; i < 130; i += NT) v_s[i] = p.attn_v[i];
+    __syncthreads();
+
+    // chunk geometry: K ranges of the act vector [prenet | ctx | ah | dh] in chunks of CK rows
+    constexpr int CK = SM::CK;
+    constexpr int NP = PRENET / CK, NC = EMB / CK, NH = RNN / CK;
+    static_assert(PRENET % CK == 0 && EMB % CK == 0 && RNN % CK == 0, "K ranges must be whole chunks");
+    constexpr int CH_P = 0, CH_CTX = NP, CH_AH = NP + NC, CH_DH = NP + NC + NH;        // act chunk of each range
+    constexpr size_t WCH = (size_t)CK * ROWS_PER_CTA;                                    // weight elements per chunk
+    const WT* w_attn = reinterpret_cast<const WT*>(p.w_attn) + (size_t)cta * K_ATTN * ROWS_PER_CTA;   // [p | ctx | ah]
+    const WT* w_dec = reinterpret_cast<const WT*>(p.w_dec) + (size_t)cta * K_DEC * ROWS_PER_CTA;      // [ctx | ah | dh]
+    const WT* wa_p = w_attn, *wa_ctx = w_attn + NP * WCH, *wa_ah = w_attn + (NP + NC) * WCH;
+    const WT* wd_ctx = w_dec, *wd_ah = w_dec + NC * WCH, *wd_dh = w_dec + (NC + NH) * WCH;
+    constexpr size_t ABUF_BYTES = (size_t)ACT_ROWS * BP * 4;
+    uint8_t* const abase = reinterpret_cast<uint8_t*>(p.act);
+
+    uint32_t epoch = 0;
+    uint32_t g = 0;             // ring position
+    const bool tf = p.mode == 1;
+    const int total_steps = tf ? p.max_steps : p.max_steps + 1;
+    int steps_done = 0;
+
+    const bool timing = cta == 0 && tid == 0;
+    unsigned long long t_phase[4] = {0ull, 0ull, 0ull, 0ull}, t_last = timing ? global_timer_ns() : 0ull;
+#ifdef TACO_PROFILE_FINE
+    unsigned long long t_fine[16] = {}, t_flast = 0ull;
+#endif
+    auto stamp = [&](int ph) {
+        if (timing) {
+            const unsigned long long now = global_timer_ns();
+            t_phase[ph] += now - t_last;
+            t_last = now;
+        }
+    };
+
+    // partial pre-activations of this CTA's 32 gate rows (this lane's share), both LSTMs; all state starts at zero,
+    // so the K ranges that a "step -1" would have contributed are zero as well
+    float acc_a[8][TL::BPL], acc_d[8][TL::BPL];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int j = 0; j < TL::BPL; ++j) { acc_a[r][j] = 0.f; acc_d[r][j] = 0.f; }
+    auto zero = [](float (&a)[8][TL::BPL]) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int j = 0; j < TL::BPL; ++j) a[r][j] = 0.f;
+    };
+    // ---- producer bookkeeping.  The weight stream of a step is a fixed cyclic sequence of L chunks:
+    //   [attn p (NP)] | [dec ah (NH)] [attn ah (NH)] | [dec ctx (NC)] | [attn ctx (NC)] [dec dh (NH)]
+    //        phase A            phase B                    phase C              phase D
+    // Weights never depend on the step, so they run ahead of the activation tiles by up to the ring depth
+    // (gw = chunks whose weights are issued, ga = chunks whose activation tile is issued, gw <= ga + STAGES: the
+    // stage of chunk q is free once chunk q - STAGES was consumed, which needs no further help from the producer
+    // iff its activations are already issued).
+    constexpr int L = NP + 3 * NH + 2 * NC;
+    constexpr int Q_B = NP, Q_C = NP + 2 * NH, Q_D = Q_C + NC;
+    uint32_t gw = 0, ga = 0;
+    // issue chunks [q0, q1) (global chunk numbers), mode as in SimtPipe::produce; a_cur/a_prv/p_all of step `st`
+    auto issue = [&](uint32_t q0, uint32_t q1, int mode, int st) {
+        const uint8_t* ac = abase + (size_t)(st & 1) * ABUF_BYTES;
+        const uint8_t* ap = abase + (size_t)((st & 1) ^ 1) * ABUF_BYTES;
+        while (q0 < q1) {
+            const int q = (int)(q0 % L);
+            const WT* w; const uint8_t* ab; int ach, jend;
+            if (q < Q_B) { w = wa_p + (size_t)q * WCH; ab = tf ? static_cast<const uint8_t*>(p.p_all) + (size_t)st * NP * SM::A_BYTES : ap; ach = CH_P + q; jend = Q_B; }
+            else if (q < Q_B + NH) { w = wd_ah + (size_t)(q - Q_B) * WCH; ab = ac; ach = CH_AH + q - Q_B; jend = Q_B + NH; }
+            else if (q < Q_C) { w = wa_ah + (size_t)(q - Q_B - NH) * WCH; ab = ac; ach = CH_AH + q - Q_B - NH; jend = Q_C; }
+            else if (q < Q_D) { w = wd_ctx + (size_t)(q - Q_C) * WCH; ab = ac; ach = CH_CTX + q - Q_C; jend = Q_D; }
+            else if (q < Q_D + NC) { w = wa_ctx + (size_t)(q - Q_D) * WCH; ab = ac; ach = CH_CTX + q - Q_D; jend = Q_D + NC; }
+            else { w = wd_dh + (size_t)(q - Q_D - NC) * WCH; ab = ap; ach = CH_DH + q - Q_D - NC; jend = L; }
+            const uint32_t n = min((uint32_t)(jend - q), q1 - q0);
+            SP::produce(pipe, q0, (int)n, mode, lane, w, ab, ach);
+            q0 += n;
+        }
+    };
+    // the activation tiles of the chunks of step `st` up to position qend (exclusive) have become available
+    auto advance = [&](int st, int qend) {
+        const uint32_t a_limit = (uint32_t)st * L + qend;
+        if (ga < gw) { const uint32_t e = min(gw, a_limit); issue(ga, e, 2, st); ga = e; }       // weights already in flight
+        if (ga < a_limit) { issue(ga, a_limit, 0, st); ga = a_limit; gw = a_limit; }
+        const uint32_t w_limit = min(ga + STAGES, (uint32_t)total_steps * L);
+        if (gw < w_limit) { issue(gw, w_limit, 1, st); gw = w_limit; }                          // run ahead with weights
+    };
+    if (is_gemm && is_producer) advance(0, 0);
+
+    for (int s = 0; s < total_steps; ++s) {
+        const int cur = s & 1, prv = cur ^ 1;
+        float* act_cur = p.act + (size_t)cur * ACT_ROWS * BP;
+        float* act_prv = p.act + (size_t)prv * ACT_ROWS * BP;
+        const uint8_t* a_cur = abase + (size_t)cur * ABUF_BYTES;
+        const uint8_t* a_prv = abase + (size_t)prv * ABUF_BYTES;
+        const int out_idx = tf ? s : s - 1;          // F6: decode step 0 of inference is discarded
+
+        // =============================== A: attention LSTM (critical: prenet rows) ===============================
+        if (is_gemm) {
+            if (is_producer) {
+                fence_proxy_async();
+                advance(s, Q_B);
+            } else {
+                FT_RESET();
+                gemm_consume<BP, WT, false>(pipe, g, NP, warp, lane, acc_a);
+                gemm_reduce<BP>(acc_a, red, z_s, warp, lane, tid);
+                zero(acc_a);
+                FT(9);
+                lstm_pointwise<BP, false>(z_s, bias_s, ca_s, h_s, act_cur + (size_t)(ACT_AH + cta * UNITS_PER_CTA) * BP, nullptr,
+                                          ACT_AH + cta * UNITS_PER_CTA, B, tid);
+                FT(10);
+                for (int i = tid; i < ATT_DIM * B; i += NTC) {       // query projection slice (src/model.py:123)
+                    const int a = i % ATT_DIM, b = i / ATT_DIM;
+                    float sum = 0.f;
+#pragma unroll
+                    for (int u = 0; u < UNITS_PER_CTA; ++u) sum = fmaf(wq_s[a * 8 + u], h_s[u * BP + b], sum);
+                    p.pqpart[((size_t)b * GEMM_CTAS + cta) * ATT_DIM + a] = sum;
+                }
+                FT(11);
+            }
+        }
+        grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
+        stamp(0);
+
+        // =============================== B: attention; background: ah_t ranges ===============================
+        if (is_producer) {
+            if (is_gemm) {
+                fence_proxy_async();
+                advance(s, Q_C);
+            }
+        } else {
+            attention_phase<BP, false>(p, red, wld_s, wloc_s, v_s, misc_s, cur, out_idx, cta, ncta, tid, warp, lane, act_cur,
+                                       nullptr, timing, TACO_FINE_ARGS, nullptr, 0, nullptr, nullptr, true);
+            if (is_gemm) {
+                gemm_consume<BP, WT, false>(pipe, g, NH, warp, lane, acc_d);
+                gemm_consume<BP, WT, false>(pipe, g, NH, warp, lane, acc_a);
+            }
+        }
+        grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
+        stamp(1);
+
+        // =============================== C: decoder LSTM (critical: context rows) ===============================
+        if (is_gemm) {
+            if (is_producer) {
+                fence_proxy_async();
+                advance(s, Q_D);
+            } else {
+                for (int i = tid; i < 4 * B; i += NTC) cx_s[(i & 3) * BP + (i >> 2)] = __ldcg(p.ctx_bj + (size_t)(i >> 2) * EMB + 4 * cta + (i & 3));
+                FT_RESET();
+                gemm_consume<BP, WT, false>(pipe, g, NC, warp, lane, acc_d);
+                gemm_reduce<BP>(acc_d, red, z_s, warp, lane, tid);
+                zero(acc_d);
+                FT(12);
+                lstm_pointwise<BP, false>(z_s, bias_s + 32, cd_s, h_s, act_prv + (size_t)(ACT_DH + cta * UNITS_PER_CTA) * BP, nullptr,
+                                          ACT_DH + cta * UNITS_PER_CTA, B, tid);
+                FT(13);
+                // linear_projection / gate_layer slice (src/model.py:272-274): 8 decoder-h units + 4 context rows
+                for (int i = tid; i < PROJ_PAD * B; i += NTC) {
+                    const int o = i % PROJ_PAD, b = i / PROJ_PAD;
+                    if (o < PROJ_OUT) {
+                        float sum = 0.f;
+#pragma unroll
+                        for (int u = 0; u < UNITS_PER_CTA; ++u) sum = fmaf(wproj_s[o * 8 + u], h_s[u * BP + b], sum);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) sum = fmaf(wpc_s[o * 4 + j], cx_s[j * BP + b], sum);
+                        p.melpart[((size_t)b * GEMM_CTAS + cta) * PROJ_PAD + o] = sum;
+                    }
+                }
+            }
+        }
+        grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
+        stamp(2);
+
+        // =============================== D: projection sums, stop rule, prenet; background: ctx_t, dh_t ranges =====
+        if (is_producer) {
+            if (is_gemm) {
+                fence_proxy_async();
+                advance(s, L);                                                       // dh_t lives in the other buffer
+            }
+        } else {
+            projection_phase<BP, false>(p, red, tf, out_idx, cta, ncta, tid, act_cur, nullptr, nullptr, 0, true);
+            if (is_gemm) {
+                gemm_consume<BP, WT, false>(pipe, g, NC, warp, lane, acc_a);
+                gemm_consume<BP, WT, false>(pipe, g, NH, warp, lane, acc_d);
+            }
+        }
+        steps_done = s + 1;
+        if (!tf) {
+            grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
+            stamp(3);
+            if (__ldcg(p.ctrl + CTRL_STOP) != 0u) break;
+        }
+    }
+
+    // ---- drain: weights of chunks that will never run are in flight: complete their stages ----
+    if (is_gemm && is_producer) {
+        for (uint32_t q = ga; q < gw; ++q) {
+            const uint32_t stage = q % STAGES;
+            if (lane == (int)stage) {
+                bulk_g2s(pipe.stages + stage * SM::STAGE_BYTES + SM::W_BYTES, abase, SM::A_BYTES, &pipe.full[stage]);
+                mbar_wait(&pipe.full[stage], (q / STAGES) & 1u);
+            }
+        }
+    }
+    if (cta == 0 && tid == 0) {
+        unsigned long long* prof = reinterpret_cast<unsigned long long*>(p.ctrl + CTRL_PROF);
+        for (int i = 0; i < 4; ++i) prof[i] = t_phase[i];
+        prof[4] = (unsigned long long)steps_done;
+#ifdef TACO_PROFILE_FINE
+        for (int i = 0; i < 16; ++i) prof[5 + i] = t_fine[i];
+#endif
+        const int S = tf ? p.max_steps : steps_done - 1;     // output frames (decode step 0 discarded)
+        *p.steps_run = S;
+        for (int b = 0; b < B; ++b) {
+            int len = S;
+            if (!tf && p.stop_mode == B200TACO_STOP_PER_UTTERANCE && __ldcg(p.ctrl + CTRL_DONE + b))
+                len = (int)__ldcg(p.ctrl + CTRL_LEN + b);
+            p.lengths[b] = len;
+        }
+    }
+}
+
+template <int BP, typename WT>
+int launch_simt(const KParams& kp, int ncta, cudaStream_t stream) {
+    using SM = Smem<BP, WT, false>;
+    auto kern = decoder_simt_kernel<BP, WT>;
+    TACO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    int per_sm = 0;
+    TACO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, SM::TOTAL));
+    TACO_REQUIRE(per_sm >= 1, B200TACO_ERR_UNSUPPORTED, "decoder kernel does not fit on an SM (smem %d B)", SM::TOTAL);
+    void* args[] = {const_cast<KParams*>(&kp)};
+    TACO_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(ncta), dim3(NT), args, SM::TOTAL, stream));
+    launch_counter()++;
+    return B200TACO_OK;
+}
+
 // prenet outputs Y[s*B + b][256] (fp32) -> the operand layout the chosen path streams per step
 __global__ void p_all_pack_simt_kernel(const float* __restrict__ Y, float* __restrict__ P, int B, int BP, int S) {
     const size_t total = (size_t)S * PRENET * BP;
@@ -1820,8 +2149,11 @@ __global__ void p_all_pack_tc_kernel(const float* __restrict__ Y, __nv_bfloat16*
 template <typename WT>
 int dispatch_bp(int BP, const KParams& kp, int ncta, cudaStream_t stream) {
     switch (BP) {
-        case 1: return launch<1, WT, false>(kp, ncta, stream);
-        case 2: return launch<2, WT, false>(kp, ncta, stream);
+        // batch tiles 1-2: hoisted contractions (measured B=1: 25.7 -> 22.0 us/step); from 4 rows up the attention /
+        // projection work items no longer fit on the CTAs beyond the GEMM CTAs and the one-contraction-per-phase
+        // kernel is faster (B=8 forced SIMT: 33 vs 37 us) - with bf16 weights those batches take the tensor-core kernel
+        case 1: return launch_simt<1, WT>(kp, ncta, stream);
+        case 2: return launch_simt<2, WT>(kp, ncta, stream);
         case 4: return launch<4, WT, false>(kp, ncta, stream);
         case 8: return launch<8, WT, false>(kp, ncta, stream);
         case 16: return launch<16, WT, false>(kp, ncta, stream);

@@ -300,7 +300,7 @@ def test_errors():
         m.inference(ids)
     m.eval()
     with pytest.raises(B200TacoError):                     # one launch carries at most b200taco_max_batch rows ...
-        m._engine.encoder(synth.phoneme_ids(65, 9).cuda())
+        m._get_engine().encoder(synth.phoneme_ids(65, 9).cuda())
     assert m.inference(synth.phoneme_ids(65, 9).cuda(), max_len_cap=3)[1].shape == (65, 3, 80)   # ... the module chunks
     with pytest.raises(B200TacoError):
         m.inference(synth.phoneme_ids(1, 2000).cuda())     # beyond b200taco_max_text_len
