@@ -250,6 +250,32 @@ B200TACO_API int32_t b200taco_debug_umma_gemm(const void* d_A, const void* d_B, 
 /* Number of kernels this library launched on this thread since the last reset. */
 B200TACO_API int64_t b200taco_launch_count(int32_t reset);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training (work in progress: first correct fp32 versions, stage by stage).
+ *
+ * Forward passes keep what the backward needs in a caller-owned "saved" buffer; the raw fp32 parameters
+ * (b200taco_weights, as in b200taco_pack_weights) are read directly.  Backward passes write gradients in
+ * the reference's parameter layouts into the buffers named by `grads`, a b200taco_weights-shaped struct
+ * whose pointers are the destinations (only the fields of the stage are touched).  Dropout masks are
+ * 0/1 float tensors drawn by the host RNG, laid out like the layer outputs; drop_scale = 1/(1-p).
+ * BatchNorm uses batch statistics over all rows (padding included, as the reference does); the batch mean and
+ * biased variance of layer i are left in the saved buffer for the host's running-statistics update.
+ *
+ * Postnet: PostNet.forward in train mode + residual, src/model.py:392-407, :476-477.
+ * saved layout per layer: z [B*S][c_out], y [B*S][c_out], mean [c_out], var [c_out], rstd [c_out].
+ */
+B200TACO_API size_t b200taco_postnet_train_saved_bytes(int32_t B, int32_t S);
+B200TACO_API size_t b200taco_postnet_train_scratch_bytes(int32_t B, int32_t S);
+B200TACO_API int32_t b200taco_postnet_train_fwd(b200taco_handle* h, const b200taco_weights* w, const float* d_coarse,
+                                                int32_t B, int32_t S, const float* const* d_masks, float drop_scale,
+                                                float* d_post, float* d_saved, size_t saved_bytes, float* d_scratch,
+                                                size_t scratch_bytes, void* stream);
+B200TACO_API int32_t b200taco_postnet_train_bwd(b200taco_handle* h, const b200taco_weights* w, const float* d_coarse,
+                                                int32_t B, int32_t S, const float* const* d_masks, float drop_scale,
+                                                const float* d_saved, const float* d_dpost, float* d_dcoarse,
+                                                const b200taco_weights* grads, float* d_scratch, size_t scratch_bytes,
+                                                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

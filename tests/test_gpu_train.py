@@ -1,0 +1,59 @@
+"""Training-mode stages (forward with batch statistics + dropout masks, hand-written backward) against torch
+autograd on the CPU train-mode oracle with the same masks.  Tolerances: fp32 everywhere, different summation
+order: 1e-4 relative to the largest gradient entry of each tensor."""
+import pytest
+import torch
+
+import util
+from b200taco import synth, train
+from b200taco.model import Tacotron2
+from oracle import train_oracle as TO
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    return float((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-12))
+
+
+@pytest.mark.parametrize("B,S,use_masks", [(2, 37, False), (3, 50, True), (8, 300, True)])
+def test_postnet_train_forward_backward(B, S, use_masks):
+    sd = util.weights()
+    g = torch.Generator().manual_seed(5)
+    for i in range(5):                               # non-trivial BatchNorm affine parameters
+        sd[f"postnet.convolutions.{i}.1.weight"] = 1 + 0.3 * torch.randn(sd[f"postnet.convolutions.{i}.1.weight"].shape, generator=g)
+        sd[f"postnet.convolutions.{i}.1.bias"] = 0.2 * torch.randn(sd[f"postnet.convolutions.{i}.1.bias"].shape, generator=g)
+    coarse = torch.randn(B, S, 80, generator=g) * 2 - 5
+    dpost = torch.randn(B, S, 80, generator=g)
+    masks = None
+    if use_masks:
+        masks = [(torch.rand(B * S, c, generator=g) >= 0.5).float() for c in (512, 512, 512, 512, 80)]
+    keys = train.postnet_param_keys()
+
+    # reference: autograd on the CPU oracle
+    ref_p = {k: sd[k].clone().requires_grad_(True) for k in keys}
+    ref_in = coarse.clone().requires_grad_(True)
+    ref_post, ref_stats = TO.postnet_train({**sd, **ref_p}, ref_in, masks)
+    ref_post.backward(dpost)
+
+    m = Tacotron2().eval()
+    m.load_state_dict(sd)
+    m = m.to("cuda:0")
+    eng = m._get_engine()
+    params = [dict(m.named_parameters())[k] for k in keys]
+    x = coarse.cuda().requires_grad_(True)
+    post = train.PostnetTrainFn.apply(eng, x, [mk.cuda() for mk in masks] if masks else None, *params)
+    post.backward(dpost.cuda())
+
+    assert rel_err(post.detach().cpu(), ref_post.detach()) <= 2e-5
+    assert rel_err(x.grad.cpu(), ref_in.grad) <= 1e-4
+    for k, p in zip(keys, params):
+        if k.endswith(".0.bias"):       # a conv bias in front of a batch-stat BatchNorm has zero gradient: both are rounding noise
+            assert float(p.grad.abs().max()) <= 1e-3 and float(ref_p[k].grad.abs().max()) <= 1e-3, k
+        else:
+            assert rel_err(p.grad.cpu(), ref_p[k].grad) <= 2e-4, k
+    # batch statistics left for the running-stat update
+    saved_stats = post.grad_fn.bn_stats if hasattr(post.grad_fn, "bn_stats") else None
+    if saved_stats is not None:
+        for (mean, var), (rm, rv) in zip(saved_stats, ref_stats):
+            assert rel_err(mean.cpu(), rm.detach()) <= 1e-5 and rel_err(var.cpu(), rv.detach()) <= 1e-4
