@@ -276,6 +276,23 @@ B200TACO_API int32_t b200taco_postnet_train_bwd(b200taco_handle* h, const b200ta
                                                 const b200taco_weights* grads, float* d_scratch, size_t scratch_bytes,
                                                 void* stream);
 
+
+/*
+ * Encoder in train mode: Encoder.forward with batch-statistics BatchNorm, src/model.py:50-77, and its backward
+ * (BiLSTM backward through time, convolution stack, embedding).  saved layout: x0 [B*T][512] | 3 x (z, y, mean, var,
+ * rstd) | xproj [B*T][2048] | per (b, t, direction): i, f, g, o, c, h (6 x 256).  Gradients of the encoder fields of
+ * `grads` are overwritten.
+ */
+B200TACO_API size_t b200taco_encoder_train_saved_bytes(int32_t B, int32_t T);
+B200TACO_API size_t b200taco_encoder_train_scratch_bytes(int32_t B, int32_t T);
+B200TACO_API int32_t b200taco_encoder_train_fwd(b200taco_handle* h, const b200taco_weights* w, const int64_t* d_ids,
+                                                int32_t B, int32_t T, float* d_memory, float* d_saved, size_t saved_bytes,
+                                                float* d_scratch, size_t scratch_bytes, void* stream);
+B200TACO_API int32_t b200taco_encoder_train_bwd(b200taco_handle* h, const b200taco_weights* w, const int64_t* d_ids,
+                                                int32_t B, int32_t T, const float* d_saved, const float* d_dmemory,
+                                                const b200taco_weights* grads, float* d_scratch, size_t scratch_bytes,
+                                                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,3 +36,36 @@ def postnet_train(sd, coarse, masks=None, p=0.5):
             m = masks[i].reshape(B, S, -1).transpose(1, 2)
             x = x * m / (1.0 - p)
     return coarse + x.transpose(1, 2), stats
+
+
+def encoder_train(sd, ids):
+    """Encoder.forward in train mode (src/model.py:50-77): embedding, 3 x relu(BN_batch(conv5)), BiLSTM over the full
+    padded length with zero initial state.  Returns memory (B,T,512) and the batch statistics per BatchNorm."""
+    x = F.embedding(ids, sd["encoder.embedding.weight"]).transpose(1, 2)
+    stats = []
+    i = 0
+    while f"encoder.convolutions.{i}.0.weight" in sd:
+        pre = f"encoder.convolutions.{i}"
+        w = sd[pre + ".0.weight"]
+        x, mean, var = _bn_train(F.conv1d(x, w, sd[pre + ".0.bias"], padding=(w.shape[2] - 1) // 2), sd, pre + ".1")
+        x = torch.relu(x)
+        stats.append((mean, var))
+        i += 1
+    x = x.transpose(1, 2)                                   # (B,T,512)
+    B, T, _ = x.shape
+    outs = []
+    for sfx, rev in (("", False), ("_reverse", True)):
+        w_ih, w_hh = sd["encoder.lstm.weight_ih_l0" + sfx], sd["encoder.lstm.weight_hh_l0" + sfx]
+        b = sd["encoder.lstm.bias_ih_l0" + sfx] + sd["encoder.lstm.bias_hh_l0" + sfx]
+        H = w_hh.shape[1]
+        h = x.new_zeros(B, H)
+        c = x.new_zeros(B, H)
+        hs = [None] * T
+        for t in (range(T - 1, -1, -1) if rev else range(T)):
+            z = x[:, t] @ w_ih.t() + h @ w_hh.t() + b
+            i_, f_, g_, o_ = z.chunk(4, dim=1)
+            c = torch.sigmoid(f_) * c + torch.sigmoid(i_) * torch.tanh(g_)
+            h = torch.sigmoid(o_) * torch.tanh(c)
+            hs[t] = h
+        outs.append(torch.stack(hs, dim=1))
+    return torch.cat(outs, dim=2), stats

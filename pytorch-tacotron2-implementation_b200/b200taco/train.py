@@ -7,7 +7,7 @@ PyTorch's generator on the device (0/1 floats) and passed down; BatchNorm runnin
 updated here from the batch statistics the kernels leave in the saved buffer
 (momentum 0.1, unbiased variance, as nn.BatchNorm1d does).
 
-Built so far: postnet (src/model.py:392-407 + residual :476-477).
+Built so far: postnet (src/model.py:392-407 + residual :476-477), encoder (src/model.py:50-77).
 """
 from __future__ import annotations
 
@@ -117,6 +117,66 @@ class PostnetTrainFn(torch.autograd.Function):
                                                  scratch.data_ptr(), scratch.numel() * 4, eng._stream()),
                   "b200taco_postnet_train_bwd")
         return (None, dcoarse, None) + tuple(grads[k] for k in ctx.keys)
+
+
+def encoder_param_keys():
+    keys = ["encoder.embedding.weight"]
+    for i in range(config.encoder_n_convolutions):
+        p = f"encoder.convolutions.{i}"
+        keys += [p + ".0.weight", p + ".0.bias", p + ".1.weight", p + ".1.bias"]
+    for s in ("", "_reverse"):
+        keys += [f"encoder.lstm.weight_ih_l0{s}", f"encoder.lstm.weight_hh_l0{s}", f"encoder.lstm.bias_ih_l0{s}",
+                 f"encoder.lstm.bias_hh_l0{s}"]
+    return keys
+
+
+class EncoderTrainFn(torch.autograd.Function):
+    """memory (B,T,512) = Encoder(ids) in train mode (batch-statistics BatchNorm; the reference's encoder has no
+    dropout, F3).  Inputs: engine, ids (B,T) int64, then the 21 encoder parameters in ``encoder_param_keys()`` order."""
+
+    @staticmethod
+    def forward(ctx, eng: Engine, ids, *params):
+        lib = eng._lib
+        ids = ids.to(dtype=torch.int64).contiguous()
+        B, T = ids.shape
+        dev = ids.device
+        keys = encoder_param_keys()
+        tensors = dict(zip(keys, [p.detach() for p in params]))
+        w, keep = _weights_struct(tensors, "encoder.")
+        saved = torch.empty(lib.b200taco_encoder_train_saved_bytes(B, T) // 4, dtype=torch.float32, device=dev)
+        scratch = torch.empty(lib.b200taco_encoder_train_scratch_bytes(B, T) // 4, dtype=torch.float32, device=dev)
+        memory = torch.empty(B, T, config.encoder_embedding_dim, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.b200taco_encoder_train_fwd(eng._h, C.byref(w), ids.data_ptr(), B, T, memory.data_ptr(), saved.data_ptr(),
+                                                 saved.numel() * 4, scratch.data_ptr(), scratch.numel() * 4, eng._stream()),
+                  "b200taco_encoder_train_fwd")
+        ctx.eng, ctx.keys = eng, keys
+        ctx.save_for_backward(ids, saved, *[p.detach() for p in params])
+        n, d = B * T, config.encoder_embedding_dim
+        ctx.bn_stats = []
+        off = n * d
+        for _ in range(config.encoder_n_convolutions):
+            off += 2 * n * d
+            ctx.bn_stats.append((saved[off:off + d], saved[off + d:off + 2 * d]))
+            off += 3 * d
+        return memory
+
+    @staticmethod
+    def backward(ctx, dmemory):
+        eng, lib = ctx.eng, ctx.eng._lib
+        ids, saved, *params = ctx.saved_tensors
+        B, T = ids.shape
+        dmemory = dmemory.contiguous()
+        tensors = dict(zip(ctx.keys, params))
+        w, keep = _weights_struct(tensors, "encoder.")
+        grads = {k: torch.empty_like(t) for k, t in tensors.items()}
+        g, keep2 = _weights_struct(grads, "encoder.")
+        scratch = torch.empty(lib.b200taco_encoder_train_scratch_bytes(B, T) // 4, dtype=torch.float32, device=ids.device)
+        with torch.cuda.device(ids.device):
+            check(lib.b200taco_encoder_train_bwd(eng._h, C.byref(w), ids.data_ptr(), B, T, saved.data_ptr(), dmemory.data_ptr(),
+                                                 C.byref(g), scratch.data_ptr(), scratch.numel() * 4, eng._stream()),
+                  "b200taco_encoder_train_bwd")
+        return (None, None) + tuple(grads[k] for k in ctx.keys)
 
 
 def draw_postnet_masks(B, S, device, generator=None):

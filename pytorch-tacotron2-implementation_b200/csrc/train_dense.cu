@@ -214,6 +214,30 @@ int conv_w_from_packed(float* w, const float* src, int c_out, int c_in, int taps
     return B200TACO_OK;
 }
 
+// dst[c] = sum_n src[n][c] for a dense [n][C] matrix
+int train_colsum(float* dst, const float* src, int n_rows, int C, cudaStream_t st) {
+    TACO_CUDA(cudaMemsetAsync(dst, 0, (size_t)C * sizeof(float), st));
+    const dim3 grid((C + 31) / 32, n_rows >= 4096 ? 32 : (n_rows >= 256 ? 8 : 1));
+    colreduce_kernel<3><<<grid, 256, 0, st>>>(src, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1.f, 0, n_rows, C,
+                                              dst, nullptr);
+    TACO_LAUNCHED();
+    return B200TACO_OK;
+}
+
+// dW[tap][ci][co] = sum_n X[n + tap - pad][ci] * dY[n][co]  (overwrites dW)
+int dense_wgrad(const float* X, int ldx, const float* dY, int ldy, float* dW, int n_rows, int seg_len, int c_in, int c_out,
+                int taps, cudaStream_t st) {
+    TACO_CUDA(cudaMemsetAsync(dW, 0, (size_t)taps * c_in * c_out * sizeof(float), st));
+    int chunks = 1;
+    const int tiles = ((c_in + 63) / 64) * ((c_out + 63) / 64) * taps;
+    while (tiles * chunks < 592 && n_rows / (chunks * 2) >= 256) chunks *= 2;
+    const int rows_per = ((n_rows + chunks - 1) / chunks + 15) / 16 * 16;
+    dense_wgrad_kernel<<<dim3((c_in + 63) / 64, (c_out + 63) / 64, taps * chunks), 256, 0, st>>>(
+        X, ldx, dY, ldy, dW, n_rows, seg_len, c_in, c_out, taps, rows_per);
+    TACO_LAUNCHED();
+    return B200TACO_OK;
+}
+
 size_t convbn_saved_floats(int n_rows, int c_out) { return (size_t)2 * n_rows * c_out + 3 * (size_t)c_out; }
 
 // Forward of one conv + BatchNorm(train) + activation + dropout layer.  `saved` receives z [n][co], y [n][co], mean[co],
