@@ -68,6 +68,12 @@ struct KParams {
     // scratch
     float *act, *pqpart, *melpart, *ctx_bj, *attn_prev, *attn_cum, *wtmp, *apart;
     float* zpart;                      // tcgen05 path: split-K partial gate sums [dst cta][src member][32 rows][BP]
+    // training (teacher-forced) only, null otherwise: per-step state kept for the backward pass and the dropout masks
+    // of the carried hidden states (src/model.py:262, :270).  Layouts [step][b][...]: gates = gate*1024 + unit (i,f,g,o
+    // post-activation), c, h (after dropout), ctx; masks are 0/1 floats.
+    float *sv_ga, *sv_ca, *sv_ah, *sv_gd, *sv_cd, *sv_dh, *sv_ctx;
+    const float *mask_a, *mask_d;
+    float drop_scale;
     uint32_t* ctrl;
 };
 
@@ -370,10 +376,29 @@ __device__ __forceinline__ void gemm_reduce(float (&acc)[8][Tile<BP>::BPL], floa
 
 // LSTMCell pointwise part (gate order i,f,g,o; src/model.py:195-203 via nn.LSTMCell).
 // z rows are unit*4+gate; c state stays in shared memory of the owning CTA.
+// training: where this step's gate activations / states go, and the dropout mask of the carried h
+struct PwSave {
+    float *gates, *c, *h;          // [b][4096], [b][1024], [b][1024] of this step (null: inference)
+    const float* mask;             // [b][1024] of this step or null
+    float scale;
+    int unit0;                     // first hidden unit of this CTA
+};
+__device__ __forceinline__ PwSave pw_save(float* g, float* c, float* h, const float* mask, float scale, int step, int B,
+                                          int unit0) {
+    PwSave sv;
+    sv.gates = g ? g + (size_t)step * B * 4 * RNN : nullptr;
+    sv.c = c ? c + (size_t)step * B * RNN : nullptr;
+    sv.h = h ? h + (size_t)step * B * RNN : nullptr;
+    sv.mask = mask ? mask + (size_t)step * B * RNN : nullptr;
+    sv.scale = scale;
+    sv.unit0 = unit0;
+    return sv;
+}
+
 template <int BP, bool TC>
 __device__ __forceinline__ void lstm_pointwise(const float* z, const float* bias, float* c_state, float* h_out,
                                                float* act_dst /* &act[buf][row0][0] */, __nv_bfloat16* act16_buf,
-                                               int k0, int B, int tid) {
+                                               int k0, int B, int tid, const PwSave& sv) {
     for (int i = tid; i < UNITS_PER_CTA * BP; i += NTC) {
         const int u = i / BP, b = i % BP;
         if (b < B) {
@@ -381,8 +406,17 @@ __device__ __forceinline__ void lstm_pointwise(const float* z, const float* bias
             const float zf = z[(u * 4 + 1) * BP + b] + bias[u * 4 + 1];
             const float zg = z[(u * 4 + 2) * BP + b] + bias[u * 4 + 2];
             const float zo = z[(u * 4 + 3) * BP + b] + bias[u * 4 + 3];
-            const float c = sigmoid_acc(zf) * c_state[i] + sigmoid_acc(zi) * tanhf(zg);
-            const float h = sigmoid_acc(zo) * tanhf(c);
+            const float gi = sigmoid_acc(zi), gf = sigmoid_acc(zf), gg = tanhf(zg), go = sigmoid_acc(zo);
+            const float c = gf * c_state[i] + gi * gg;
+            float h = go * tanhf(c);
+            if (sv.gates != nullptr) {          // training: keep what the backward needs, drop the carried h
+                const int unit = sv.unit0 + u;
+                float* gs = sv.gates + (size_t)b * 4 * RNN + unit;
+                gs[0] = gi; gs[RNN] = gf; gs[2 * RNN] = gg; gs[3 * RNN] = go;
+                sv.c[(size_t)b * RNN + unit] = c;
+                if (sv.mask != nullptr) h *= sv.mask[(size_t)b * RNN + unit] * sv.scale;
+                sv.h[(size_t)b * RNN + unit] = h;
+            }
             c_state[i] = c;
             h_out[i] = h;
             if constexpr (TC) {
@@ -856,6 +890,8 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
                     *reinterpret_cast<__nv_bfloat162*>(act16_cur + act16_off<BP>(b, ACT_CTX + d)) = __nv_bfloat162(hx, hy);
                     *reinterpret_cast<__nv_bfloat162*>(act16_cur + act16_off<BP>(BP + b, ACT_CTX + d)) = __nv_bfloat162(lx, ly);
                     *reinterpret_cast<float2*>(p.ctx_bj + (size_t)b * EMB + d) = c;
+                    if (p.sv_ctx != nullptr && out_idx >= 0)
+                        *reinterpret_cast<float2*>(p.sv_ctx + ((size_t)out_idx * B + b) * EMB + d) = c;
                 }
         FT(8);
                 continue;
@@ -925,6 +961,7 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
             act_cur[(size_t)(ACT_CTX + 2 * tid + 1) * BP + b] = cacc.y;
         }
         reinterpret_cast<float2*>(p.ctx_bj + (size_t)b * EMB)[tid] = cacc;
+        if (p.sv_ctx != nullptr && out_idx >= 0) reinterpret_cast<float2*>(p.sv_ctx + ((size_t)out_idx * B + b) * EMB)[tid] = cacc;
         // attention weights: alignment output, prev, cum (src/model.py:142-145)
         for (int t = tid; t < T; t += NTC) {
             float ew;
@@ -1188,7 +1225,8 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                 }
                 FT(9);
                 lstm_pointwise<BP, TC>(z_s, bias_s, ca_s, h_s, act_cur + (size_t)(ACT_AH + cta * UNITS_PER_CTA) * BP,
-                                       act16_cur, ACT_AH + cta * UNITS_PER_CTA, B, tid);
+                                       act16_cur, ACT_AH + cta * UNITS_PER_CTA, B, tid,
+                                       pw_save(p.sv_ga, p.sv_ca, p.sv_ah, p.mask_a, p.drop_scale, s, B, cta * UNITS_PER_CTA));
                 FT(10);
                 // this CTA's slice of the query projection (src/model.py:123): pqpart[b][cta][a]
                 for (int i = tid; i < ATT_DIM * B; i += NTC) {
@@ -1232,7 +1270,8 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                 }
                 FT(12);
                 lstm_pointwise<BP, TC>(z_s, bias_s + 32, cd_s, h_s, act_prv + (size_t)(ACT_DH + cta * UNITS_PER_CTA) * BP,
-                                       act16_prv, ACT_DH + cta * UNITS_PER_CTA, B, tid);
+                                       act16_prv, ACT_DH + cta * UNITS_PER_CTA, B, tid,
+                                       pw_save(p.sv_gd, p.sv_cd, p.sv_dh, p.mask_d, p.drop_scale, s, B, cta * UNITS_PER_CTA));
                 FT(13);
                 // this CTA's slice of linear_projection / gate_layer (src/model.py:272-274): 8 decoder-h units + 4 context rows
                 for (int i = tid; i < PROJ_PAD * B; i += NTC) {
@@ -1621,7 +1660,8 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
                 tc_epilogue<BP, CL>(acc_attn, bar_attn, ph_attn, red, z_s, p.zpart, p.ctrl + CTRL_GCNT, gepoch, xch, xbar, cta, warp,
                                     lane, tid);
                 FT(9);
-                lstm_pointwise<BP, true>(z_s, bias_s, ca_s, h_s, nullptr, act16_cur, ACT_AH + cta * UNITS_PER_CTA, B, tid);
+                lstm_pointwise<BP, true>(z_s, bias_s, ca_s, h_s, nullptr, act16_cur, ACT_AH + cta * UNITS_PER_CTA, B, tid,
+                                       pw_save(p.sv_ga, p.sv_ca, p.sv_ah, p.mask_a, p.drop_scale, s, B, cta * UNITS_PER_CTA));
                 FT(10);
                 // this CTA's slice of the query projection (src/model.py:123): pqpart[b][cta][a]
                 for (int i = tid; i < ATT_DIM * B; i += NTC) {
@@ -1676,7 +1716,8 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
                 tc_epilogue<BP, CL>(acc_dec, bar_dec, ph_dec, red, z_s, p.zpart, p.ctrl + CTRL_GCNT, gepoch, xch, xbar, cta, warp,
                                     lane, tid);
                 FT(12);
-                lstm_pointwise<BP, true>(z_s, bias_s + 32, cd_s, h_s, nullptr, act16_prv, ACT_DH + cta * UNITS_PER_CTA, B, tid);
+                lstm_pointwise<BP, true>(z_s, bias_s + 32, cd_s, h_s, nullptr, act16_prv, ACT_DH + cta * UNITS_PER_CTA, B, tid,
+                                       pw_save(p.sv_gd, p.sv_cd, p.sv_dh, p.mask_d, p.drop_scale, s, B, cta * UNITS_PER_CTA));
                 FT(13);
                 // this CTA's slice of linear_projection / gate_layer (src/model.py:272-274): 8 decoder-h units + 4 context rows
                 for (int i = tid; i < PROJ_PAD * B; i += NTC) {
@@ -1997,7 +2038,8 @@ __global__ void __launch_bounds__(NT, 1) decoder_simt_kernel(const KParams p) {
                 zero(acc_a);
                 FT(9);
                 lstm_pointwise<BP, false>(z_s, bias_s, ca_s, h_s, act_cur + (size_t)(ACT_AH + cta * UNITS_PER_CTA) * BP, nullptr,
-                                          ACT_AH + cta * UNITS_PER_CTA, B, tid);
+                                          ACT_AH + cta * UNITS_PER_CTA, B, tid,
+                                       pw_save(p.sv_ga, p.sv_ca, p.sv_ah, p.mask_a, p.drop_scale, s, B, cta * UNITS_PER_CTA));
                 FT(10);
                 for (int i = tid; i < ATT_DIM * B; i += NTC) {       // query projection slice (src/model.py:123)
                     const int a = i % ATT_DIM, b = i / ATT_DIM;
@@ -2042,7 +2084,8 @@ __global__ void __launch_bounds__(NT, 1) decoder_simt_kernel(const KParams p) {
                 zero(acc_d);
                 FT(12);
                 lstm_pointwise<BP, false>(z_s, bias_s + 32, cd_s, h_s, act_prv + (size_t)(ACT_DH + cta * UNITS_PER_CTA) * BP, nullptr,
-                                          ACT_DH + cta * UNITS_PER_CTA, B, tid);
+                                          ACT_DH + cta * UNITS_PER_CTA, B, tid,
+                                       pw_save(p.sv_gd, p.sv_cd, p.sv_dh, p.mask_d, p.drop_scale, s, B, cta * UNITS_PER_CTA));
                 FT(13);
                 // linear_projection / gate_layer slice (src/model.py:272-274): 8 decoder-h units + 4 context rows
                 for (int i = tid; i < PROJ_PAD * B; i += NTC) {
@@ -2278,6 +2321,8 @@ int decoder_run(const b200taco_handle* h, const DecoderArgs& a, cudaStream_t str
     kp.attn_v = h->attn_v;
     kp.memory = a.memory; kp.pm = a.pm; kp.p_all = a.p_all; kp.text_lengths = a.text_lengths;
     kp.mel = a.mel; kp.gate = a.gate; kp.align = a.align; kp.lengths = a.lengths; kp.steps_run = a.steps_run;
+    kp.sv_ga = a.sv_ga; kp.sv_ca = a.sv_ca; kp.sv_ah = a.sv_ah; kp.sv_gd = a.sv_gd; kp.sv_cd = a.sv_cd; kp.sv_dh = a.sv_dh;
+    kp.sv_ctx = a.sv_ctx; kp.mask_a = a.mask_a; kp.mask_d = a.mask_d; kp.drop_scale = a.drop_scale;
     kp.act = reinterpret_cast<float*>(base + L.act);
     kp.act16 = reinterpret_cast<__nv_bfloat16*>(base + L.act16);
     kp.w_attn_tc = h->w_attn_tc; kp.w_dec_tc = h->w_dec_tc;

@@ -94,6 +94,11 @@ struct DecoderArgs {
     int32_t* steps_run;           // (1)
     void* scratch;                // decoder_scratch_bytes()
     size_t scratch_bytes;
+    // training (teacher-forced mode only; all null / 0 otherwise): per-step state for the backward pass, dropout masks
+    float *sv_ga = nullptr, *sv_ca = nullptr, *sv_ah = nullptr, *sv_gd = nullptr, *sv_cd = nullptr, *sv_dh = nullptr,
+          *sv_ctx = nullptr;
+    const float *mask_a = nullptr, *mask_d = nullptr;
+    float drop_scale = 1.f;
 };
 size_t decoder_scratch_bytes(int B, int T);
 int decoder_batch_pad(int B);
