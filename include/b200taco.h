@@ -293,6 +293,32 @@ B200TACO_API int32_t b200taco_encoder_train_bwd(b200taco_handle* h, const b200ta
                                                 const b200taco_weights* grads, float* d_scratch, size_t scratch_bytes,
                                                 void* stream);
 
+
+/*
+ * Teacher-forced decoder in train mode: Decoder.forward, src/model.py:277-297, with dropout on both prenet layers
+ * (masks [S*B][256], rows ordered [step][b]) and on the carried attention / decoder LSTM hidden states (masks
+ * [S][B][1024]); the persistent decoder kernel runs the forward and leaves per-step gates, cell / hidden states and
+ * contexts in `d_saved`.  Needs b200taco_pack_weights with the current parameters first.  The backward walks the steps
+ * in reverse (LSTM cells, attention incl. location conv and cumulative weights, prenet, memory layer) and overwrites
+ * the decoder fields of `grads` and d_dmemory (B,T,512).  d_dalign (S,B,T) may be null.
+ */
+B200TACO_API size_t b200taco_decoder_train_saved_bytes(int32_t B, int32_t T, int32_t S);
+B200TACO_API size_t b200taco_decoder_train_scratch_bytes(int32_t B, int32_t T, int32_t S);
+B200TACO_API int32_t b200taco_decoder_train_fwd(b200taco_handle* h, const float* d_memory, const float* d_mel_targets,
+                                                const int64_t* d_text_lengths, int32_t B, int32_t T, int32_t S,
+                                                const float* d_mask_p1, const float* d_mask_p2, float prenet_scale,
+                                                const float* d_mask_a, const float* d_mask_d, float lstm_scale,
+                                                float* d_mel, float* d_gate, float* d_align, float* d_saved,
+                                                size_t saved_bytes, void* d_workspace, size_t workspace_bytes, void* stream);
+B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200taco_weights* w, const float* d_memory,
+                                                const int64_t* d_text_lengths, int32_t B, int32_t T, int32_t S,
+                                                const float* d_mask_p1, const float* d_mask_p2, float prenet_scale,
+                                                const float* d_mask_a, const float* d_mask_d, float lstm_scale,
+                                                const float* d_saved, const float* d_align, const float* d_dcoarse,
+                                                const float* d_dgate, const float* d_dalign, float* d_dmemory,
+                                                const b200taco_weights* grads, float* d_scratch, size_t scratch_bytes,
+                                                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

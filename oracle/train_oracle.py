@@ -69,3 +69,47 @@ def encoder_train(sd, ids):
             hs[t] = h
         outs.append(torch.stack(hs, dim=1))
     return torch.cat(outs, dim=2), stats
+
+
+def decoder_train(sd, memory, mel_targets, text_lengths=None, masks=None, p_prenet=0.5, p_lstm=0.1):
+    """Decoder.forward in train mode, src/model.py:277-297 with _decode_step :246-275: teacher forcing, dropout on both
+    prenet layers (p=0.5, :170) and on the CARRIED attention / decoder hidden states (p=0.1, :262, :270).
+    masks = dict(p1, p2: (S*B,256) rows ordered [step][b]; a, d: (S,B,1024)) of 0/1 floats, or None (no dropout).
+    Returns mel (B,S,80), gate (B,S), alignments (S,B,T)."""
+    from oracle import tacotron2_oracle as O
+    B, T, _ = memory.shape
+    S = mel_targets.shape[2]
+    mask = O.make_pad_mask(text_lengths, T) if text_lengths is not None else None
+    frames = mel_targets.transpose(1, 2)
+    frames = torch.cat([torch.zeros_like(frames[:, :1]), frames[:, :-1]], dim=1)
+    st = O.DecoderState(sd, memory, mask)
+    d = "decoder."
+    mels, gates, aligns = [], [], []
+    for i in range(S):
+        x = frames[:, i]
+        x = torch.relu(x @ sd[d + "prenet.layers.0.weight"].t())
+        if masks is not None:
+            x = x * masks["p1"][i * B:(i + 1) * B] / (1 - p_prenet)
+        x = torch.relu(x @ sd[d + "prenet.layers.1.weight"].t())
+        if masks is not None:
+            x = x * masks["p2"][i * B:(i + 1) * B] / (1 - p_prenet)
+        st.ah, st.ac = O._lstm_cell(torch.cat([x, st.ctx], dim=1), st.ah, st.ac,
+                                    sd[d + "attention_lstm.weight_ih"], sd[d + "attention_lstm.weight_hh"],
+                                    sd[d + "attention_lstm.bias_ih"], sd[d + "attention_lstm.bias_hh"])
+        if masks is not None:
+            st.ah = st.ah * masks["a"][i] / (1 - p_lstm)
+        e = O.attention_energies(sd, st, st.ah)
+        w = torch.softmax(e, dim=1)
+        st.prev_attn = w
+        st.cum_attn = st.cum_attn + w
+        st.ctx = torch.bmm(w[:, None, :], st.memory).squeeze(1)
+        st.dh, st.dc = O._lstm_cell(torch.cat([st.ah, st.ctx], dim=1), st.dh, st.dc,
+                                    sd[d + "decoder_lstm.weight_ih"], sd[d + "decoder_lstm.weight_hh"],
+                                    sd[d + "decoder_lstm.bias_ih"], sd[d + "decoder_lstm.bias_hh"])
+        if masks is not None:
+            st.dh = st.dh * masks["d"][i] / (1 - p_lstm)
+        proj_in = torch.cat([st.dh, st.ctx], dim=1)
+        mels.append(torch.addmm(sd[d + "linear_projection.bias"], proj_in, sd[d + "linear_projection.weight"].t()))
+        gates.append(torch.addmm(sd[d + "gate_layer.bias"], proj_in, sd[d + "gate_layer.weight"].t()))
+        aligns.append(w)
+    return torch.stack(mels, dim=1), torch.stack(gates, dim=1).squeeze(-1), torch.stack(aligns, dim=0)

@@ -103,6 +103,17 @@ SIGNATURES = {
     "b200taco_encoder_train_bwd": (C.c_int32, [C.c_void_p, C.POINTER(Weights), C.c_void_p, C.c_int32, C.c_int32,
                                                C.c_void_p, C.c_void_p, C.POINTER(Weights), C.c_void_p, C.c_size_t,
                                                C.c_void_p]),
+    "b200taco_decoder_train_saved_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "b200taco_decoder_train_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "b200taco_decoder_train_fwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                               C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_float,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                               C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b200taco_decoder_train_bwd": (C.c_int32, [C.c_void_p, C.POINTER(Weights), C.c_void_p, C.c_void_p,
+                                               C.c_int32, C.c_int32, C.c_int32,
+                                               C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_float,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.POINTER(Weights), C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 
 _lock = threading.Lock()

@@ -7,7 +7,8 @@ PyTorch's generator on the device (0/1 floats) and passed down; BatchNorm runnin
 updated here from the batch statistics the kernels leave in the saved buffer
 (momentum 0.1, unbiased variance, as nn.BatchNorm1d does).
 
-Built so far: postnet (src/model.py:392-407 + residual :476-477), encoder (src/model.py:50-77).
+Built so far: postnet (src/model.py:392-407 + residual :476-477), encoder (src/model.py:50-77), teacher-forced
+decoder (src/model.py:246-297).
 """
 from __future__ import annotations
 
@@ -177,6 +178,90 @@ class EncoderTrainFn(torch.autograd.Function):
                                                  C.byref(g), scratch.data_ptr(), scratch.numel() * 4, eng._stream()),
                   "b200taco_encoder_train_bwd")
         return (None, None) + tuple(grads[k] for k in ctx.keys)
+
+
+PRENET_P = 0.5            # PreNet dropout, src/model.py:170
+LSTM_P = config.p_attention_dropout if hasattr(config, "p_attention_dropout") else 0.1   # src/model.py:262, :270
+
+
+def decoder_param_keys():
+    d = "decoder."
+    keys = [d + "prenet.layers.0.weight", d + "prenet.layers.1.weight"]
+    keys += [d + "attention." + k for k in ("query_layer.weight", "memory_layer.weight", "location_conv.weight",
+                                            "location_dense.weight", "v.weight", "v.bias", "energy_scale")]
+    for m in ("attention_lstm", "decoder_lstm"):
+        keys += [d + f"{m}.{k}" for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+    keys += [d + "linear_projection.weight", d + "linear_projection.bias", d + "gate_layer.weight", d + "gate_layer.bias"]
+    return keys
+
+
+class DecoderTrainFn(torch.autograd.Function):
+    """(coarse (B,S,80), gate (B,S), align (S,B,T)) = Decoder.forward in train mode.  Inputs: engine (weights packed
+    from the CURRENT parameters), memory (B,T,512), mel_targets (B,80,S), text_lengths (B,) or None, masks dict
+    (p1, p2: (S*B,256); a, d: (S,B,1024)) or None, then the 21 decoder parameters in ``decoder_param_keys()`` order."""
+
+    @staticmethod
+    def forward(ctx, eng: Engine, memory, mel_targets, text_lengths, masks, *params):
+        lib = eng._lib
+        memory = memory.contiguous()
+        mel_targets = mel_targets.to(dtype=torch.float32).contiguous()
+        B, T, _ = memory.shape
+        S = mel_targets.shape[2]
+        dev = memory.device
+        tl = text_lengths.to(device=dev, dtype=torch.int64).contiguous() if text_lengths is not None else None
+        saved = torch.empty(lib.b200taco_decoder_train_saved_bytes(B, T, S) // 4, dtype=torch.float32, device=dev)
+        mel = torch.empty(B, S, config.n_mels, dtype=torch.float32, device=dev)
+        gate = torch.empty(B, S, dtype=torch.float32, device=dev)
+        align = torch.empty(S, B, T, dtype=torch.float32, device=dev)
+        ws, wsz = eng._workspace(B, T, S)
+        if masks is not None:
+            masks = {k: v.contiguous() for k, v in masks.items()}
+        mp = lambda k: masks[k].data_ptr() if masks is not None else None
+        ps = 1.0 / (1.0 - PRENET_P) if masks is not None else 1.0
+        ls = 1.0 / (1.0 - LSTM_P) if masks is not None else 1.0
+        with torch.cuda.device(dev):
+            check(lib.b200taco_decoder_train_fwd(eng._h, memory.data_ptr(), mel_targets.data_ptr(),
+                                                 tl.data_ptr() if tl is not None else None, B, T, S,
+                                                 mp("p1"), mp("p2"), C.c_float(ps), mp("a"), mp("d"), C.c_float(ls),
+                                                 mel.data_ptr(), gate.data_ptr(), align.data_ptr(), saved.data_ptr(),
+                                                 saved.numel() * 4, ws, wsz, eng._stream()), "b200taco_decoder_train_fwd")
+        ctx.eng, ctx.masks, ctx.scales, ctx.tl, ctx.keys = eng, masks, (ps, ls), tl, decoder_param_keys()
+        ctx.save_for_backward(memory, saved, align, *[p.detach() for p in params])
+        ctx.mark_non_differentiable()
+        return mel, gate, align
+
+    @staticmethod
+    def backward(ctx, dmel, dgate, dalign):
+        eng, lib = ctx.eng, ctx.eng._lib
+        memory, saved, align, *params = ctx.saved_tensors
+        B, T, _ = memory.shape
+        S = align.shape[0]
+        dev = memory.device
+        dmel = (dmel if dmel is not None else torch.zeros(B, S, config.n_mels, device=dev)).contiguous()
+        dgate = (dgate if dgate is not None else torch.zeros(B, S, device=dev)).contiguous()
+        dalign = dalign.contiguous() if dalign is not None else None
+        tensors = dict(zip(ctx.keys, params))
+        w, keep = _weights_struct(tensors, "decoder.")
+        grads = {k: torch.empty_like(t) for k, t in tensors.items()}
+        g, keep2 = _weights_struct(grads, "decoder.")
+        dmemory = torch.empty_like(memory)
+        scratch = torch.empty(lib.b200taco_decoder_train_scratch_bytes(B, T, S) // 4, dtype=torch.float32, device=dev)
+        masks, (ps, ls), tl = ctx.masks, ctx.scales, ctx.tl
+        mp = lambda k: masks[k].data_ptr() if masks is not None else None
+        with torch.cuda.device(dev):
+            check(lib.b200taco_decoder_train_bwd(eng._h, C.byref(w), memory.data_ptr(), tl.data_ptr() if tl is not None else None,
+                                                 B, T, S, mp("p1"), mp("p2"), C.c_float(ps), mp("a"), mp("d"), C.c_float(ls),
+                                                 saved.data_ptr(), align.data_ptr(), dmel.data_ptr(), dgate.data_ptr(),
+                                                 dalign.data_ptr() if dalign is not None else None, dmemory.data_ptr(),
+                                                 C.byref(g), scratch.data_ptr(), scratch.numel() * 4, eng._stream()),
+                  "b200taco_decoder_train_bwd")
+        return (None, dmemory, None, None, None) + tuple(grads[k] for k in ctx.keys)
+
+
+def draw_decoder_masks(B, S, device, generator=None):
+    r = lambda *shape, p: (torch.rand(*shape, device=device, generator=generator) >= p).float()
+    return {"p1": r(S * B, config.prenet_dim, p=PRENET_P), "p2": r(S * B, config.prenet_dim, p=PRENET_P),
+            "a": r(S, B, config.attention_rnn_dim, p=LSTM_P), "d": r(S, B, config.decoder_rnn_dim, p=LSTM_P)}
 
 
 def draw_postnet_masks(B, S, device, generator=None):

@@ -286,6 +286,86 @@ B200TACO_API int32_t b200taco_decoder_teacher_forced(b200taco_handle* h, const f
                        d_align, tail, tail + MAX_BATCH, d_workspace, ws.total, static_cast<cudaStream_t>(stream));
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Teacher-forced decoder in TRAIN mode (Decoder.forward with self.training, src/model.py:277-297): the same persistent
+// kernel, with dropout masks on the prenet outputs (p=0.5, :170) and on the carried LSTM hidden states (p=0.1, :262,
+// :270), keeping per-step state for the backward pass (train_api.cu: b200taco_decoder_train_bwd).
+// saved (floats): frames [S*B][80] | y1 [S*B][256] | y2 [S*B][256] | pm [B*T][128] | ga [S*B][4096] | ca [S*B][1024] |
+//                 ah [S*B][1024] | gd [S*B][4096] | cd [S*B][1024] | dh [S*B][1024] | ctx [S*B][512]
+}  // extern "C"
+namespace b200taco {
+DecSaved dec_saved(int B, int T, int S) {
+    DecSaved d{};
+    const size_t n = (size_t)S * B;
+    size_t off = 0;
+    d.frames = off; off += n * N_MELS;
+    d.y1 = off; off += n * PRENET;
+    d.y2 = off; off += n * PRENET;
+    d.pm = off; off += (size_t)B * T * ATT_DIM;
+    d.ga = off; off += n * 4 * RNN;
+    d.ca = off; off += n * RNN;
+    d.ah = off; off += n * RNN;
+    d.gd = off; off += n * 4 * RNN;
+    d.cd = off; off += n * RNN;
+    d.dh = off; off += n * RNN;
+    d.ctx = off; off += n * EMB;
+    d.total = off;
+    return d;
+}
+int relu_drop_fwd(float* y, const float* mask, float scale, size_t n, cudaStream_t st);
+}  // namespace b200taco
+extern "C" {
+
+B200TACO_API size_t b200taco_decoder_train_saved_bytes(int32_t B, int32_t T, int32_t S) {
+    return dec_saved(B, T, S).total * sizeof(float);
+}
+
+B200TACO_API int32_t b200taco_decoder_train_fwd(b200taco_handle* h, const float* d_memory, const float* d_mel_targets,
+                                                const int64_t* d_text_lengths, int32_t B, int32_t T, int32_t S,
+                                                const float* d_mask_p1, const float* d_mask_p2, float prenet_scale,
+                                                const float* d_mask_a, const float* d_mask_d, float lstm_scale, float* d_mel,
+                                                float* d_gate, float* d_align, float* d_saved, size_t saved_bytes,
+                                                void* d_workspace, size_t workspace_bytes, void* stream) {
+    TACO_TRY(check_handle(h, true));
+    TACO_TRY(check_shape(B, T));
+    TACO_REQUIRE(d_memory && d_mel_targets && d_mel && d_gate && d_align && d_saved && d_workspace && S >= 1, B200TACO_ERR_INVALID,
+                 "decoder_train_fwd: bad argument");
+    const DecSaved sv = dec_saved(B, T, S);
+    TACO_REQUIRE(saved_bytes >= sv.total * sizeof(float), B200TACO_ERR_STATE, "decoder_train_fwd: saved buffer too small");
+    const DecoderWs ws = decoder_ws(d_workspace, B, T, S);
+    TACO_REQUIRE(workspace_bytes >= ws.total + 1024, B200TACO_ERR_STATE, "decoder workspace too small: %zu < %zu", workspace_bytes,
+                 ws.total + 1024);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* frames = d_saved + sv.frames;
+    float* y1 = d_saved + sv.y1;
+    float* y2 = d_saved + sv.y2;
+    float* pm = d_saved + sv.pm;
+    const int n = S * B;
+    // fp32 CUDA-core dense layers throughout the training path (exact round-to-nearest accumulation)
+    TACO_TRY(conv1d_channels_last(d_memory, EMB, h->attn_memory_wT, nullptr, nullptr, nullptr, 0, pm, ATT_DIM, B * T, B * T, EMB,
+                                  ATT_DIM, 1, ACT_NONE, st));
+    tf_frames_kernel<<<(int)(((size_t)n * N_MELS + 255) / 256 > 2048 ? 2048 : ((size_t)n * N_MELS + 255) / 256), 256, 0, st>>>(
+        d_mel_targets, frames, B, S);
+    TACO_LAUNCHED();
+    TACO_TRY(conv1d_channels_last(frames, N_MELS, h->prenet1T, nullptr, nullptr, nullptr, 0, y1, PRENET, n, n, N_MELS, PRENET, 1,
+                                  ACT_RELU, st));
+    TACO_TRY(relu_drop_fwd(y1, d_mask_p1, prenet_scale, (size_t)n * PRENET, st));
+    TACO_TRY(conv1d_channels_last(y1, PRENET, h->prenet2T, nullptr, nullptr, nullptr, 0, y2, PRENET, n, n, PRENET, PRENET, 1,
+                                  ACT_RELU, st));
+    TACO_TRY(relu_drop_fwd(y2, d_mask_p2, prenet_scale, (size_t)n * PRENET, st));
+    TACO_TRY(decoder_pack_p_all(h, y2, ws.p_all, B, S, st));
+    int32_t* tail = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(d_workspace) + ws.total);
+    DecoderArgs a{};
+    a.B = B; a.T = T; a.max_steps = S; a.mode = 1; a.stop_mode = B200TACO_STOP_BATCH_WIDE; a.gate_threshold = 2.0f;
+    a.memory = d_memory; a.pm = pm; a.text_lengths = d_text_lengths; a.p_all = ws.p_all;
+    a.mel = d_mel; a.gate = d_gate; a.align = d_align; a.lengths = tail; a.steps_run = tail + MAX_BATCH;
+    a.scratch = ws.scratch; a.scratch_bytes = ws.scratch_bytes;
+    a.sv_ga = d_saved + sv.ga; a.sv_ca = d_saved + sv.ca; a.sv_ah = d_saved + sv.ah;
+    a.sv_gd = d_saved + sv.gd; a.sv_cd = d_saved + sv.cd; a.sv_dh = d_saved + sv.dh; a.sv_ctx = d_saved + sv.ctx;
+    a.mask_a = d_mask_a; a.mask_d = d_mask_d; a.drop_scale = lstm_scale;
+    return decoder_run(h, a, st);
+}
+
 B200TACO_API int32_t b200taco_postnet_fwd(b200taco_handle* h, const float* d_mel_coarse, int32_t B, int32_t S, float* d_mel_post,
                              void* d_workspace, size_t workspace_bytes, void* stream) {
     TACO_TRY(check_handle(h, true));

@@ -106,6 +106,10 @@ bool decoder_uses_tensor_cores(const b200taco_handle* h, int B);
 int decoder_pack_p_all(const b200taco_handle* h, const float* Y, void* P, int B, int S, cudaStream_t stream);
 int decoder_run(const b200taco_handle* h, const DecoderArgs& a, cudaStream_t stream);
 
+// api.cu: layout of the decoder's training "saved" buffer (float offsets)
+struct DecSaved { size_t frames, y1, y2, pm, ga, ca, ah, gd, cd, dh, ctx, total; };
+DecSaved dec_saved(int B, int T, int S);
+
 // measure.cu
 int measure_l2_read(void* d_buf, size_t bytes, int iters, float* gbps, cudaStream_t stream);
 int measure_sync_costs(long long* out8_host, cudaStream_t stream);

@@ -31,6 +31,22 @@ int bilstm_train_bwd(const float* whh_f, const float* whh_b, const float* d_out,
                      int B, int T, cudaStream_t st);
 int embedding_bwd(const int64_t* ids, const float* dx, float* dE, int n, cudaStream_t st);
 
+// train_decoder.cu
+int lstm_cell_bwd(const float* gates, const float* c, const float* c_prev, const float* dh_post, const float* mask, float scale,
+                  float* dc, float* dz, int B, cudaStream_t st);
+int attn_cumsum(const float* align, float* cum, int S, int BT, cudaStream_t st);
+int train_axpy(float* dst, int ld_dst, const float* a, int ld_a, int n, int cols, bool accumulate, cudaStream_t st);
+int relu_drop_bwd(const float* dy, const float* y, const float* mask, float scale, float* dx, size_t n, cudaStream_t st);
+size_t attention_bwd_scratch_floats(int B, int T);
+int attention_bwd(const float* w, const float* prev, const float* cum, const float* pq, const float* pm, const float* memory,
+                  const float* dctx, const float* dw_ext, const float* dprev_next, float* gsum, const int64_t* lengths,
+                  const float* Wloc, const float* Wld, const float* v, const float* vb, const float* escale, float* dmemory,
+                  float* dpm, float* dpq, float* dprev_out, float* dWld, float* dWloc, float* dv, float* dvb_scale, float* scratch,
+                  int B, int T, cudaStream_t st);
+int transpose_block(float* dst, int ldd, const float* src, int lds, int R, int C, cudaStream_t st);
+int assemble_dout(const float* d_coarse, const float* d_gate, float* dout, int B, int S, cudaStream_t st);
+int assemble_wpg(const float* wp, const float* wg, float* dst, cudaStream_t st);
+
 namespace {
 
 struct PostDims { int c_in[POST_CONVS], c_out[POST_CONVS]; };
@@ -265,6 +281,176 @@ B200TACO_API int32_t b200taco_encoder_train_bwd(b200taco_handle* h, const b200ta
         dy = dxi;
     }
     return embedding_bwd(d_ids, dy, const_cast<float*>(grads->enc_embedding), n, st);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Decoder backward (teacher-forced, train mode).  The host walks the steps in reverse; per step: projection^T,
+// decoder LSTM cell backward + input/recurrent data gradients, attention backward, query^T, attention LSTM cell
+// backward + data gradients.  Weight gradients are deferred to a few large reductions over all steps.
+namespace {
+struct DecScratch {
+    size_t dout, wpg, wqT, dzd, dza, dpq, dp, d_ah, d_dh, d_ctx, dca, dcd, tmp, tmp2, pq, P, gsum, cum, dpm, attn, dw, dvs, total;
+};
+DecScratch dec_scratch(int B, int T, int S) {
+    DecScratch d{};
+    const size_t n = (size_t)S * B;
+    size_t off = 0;
+    auto take = [&](size_t f) { size_t o = off; off += (f + 63) / 64 * 64; return o; };
+    d.dout = take(n * PROJ_PAD);
+    d.wpg = take((size_t)PROJ_PAD * (RNN + EMB));
+    d.wqT = take((size_t)RNN * ATT_DIM);
+    d.dzd = take(n * 4 * RNN);
+    d.dza = take(n * 4 * RNN);
+    d.dpq = take(n * ATT_DIM);
+    d.dp = take(n * PRENET * 2);                  // dp_all, then reused for the prenet backward (two buffers)
+    d.d_ah = take((size_t)B * RNN);
+    d.d_dh = take((size_t)B * RNN);
+    d.d_ctx = take((size_t)B * EMB);
+    d.dca = take((size_t)B * RNN);
+    d.dcd = take((size_t)B * RNN);
+    d.tmp = take((size_t)B * (RNN + EMB));
+    d.tmp2 = take((size_t)B * RNN);
+    d.pq = take((size_t)B * ATT_DIM);
+    d.P = take((size_t)2 * B * T);
+    d.gsum = take((size_t)B * T);
+    d.cum = take(n * T);
+    d.dpm = take((size_t)B * T * ATT_DIM);
+    d.attn = take(attention_bwd_scratch_floats(B, T));
+    d.dw = take((size_t)4 * RNN * (RNN + EMB));   // largest [in][out] weight gradient (1536 x 4096)
+    d.dvs = take(64);
+    d.total = off;
+    return d;
+}
+}  // namespace
+
+B200TACO_API size_t b200taco_decoder_train_scratch_bytes(int32_t B, int32_t T, int32_t S) {
+    return dec_scratch(B, T, S).total * sizeof(float);
+}
+
+B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200taco_weights* w, const float* d_memory,
+                                                const int64_t* d_text_lengths, int32_t B, int32_t T, int32_t S,
+                                                const float* d_mask_p1, const float* d_mask_p2, float prenet_scale,
+                                                const float* d_mask_a, const float* d_mask_d, float lstm_scale,
+                                                const float* d_saved, const float* d_align, const float* d_dcoarse,
+                                                const float* d_dgate, const float* d_dalign, float* d_dmemory,
+                                                const b200taco_weights* grads, float* d_scratch, size_t scratch_bytes,
+                                                void* stream) {
+    if (int e = check_train_handle(h)) return e;
+    TACO_REQUIRE(w && d_memory && d_saved && d_align && d_dcoarse && d_dgate && d_dmemory && grads && d_scratch,
+                 B200TACO_ERR_INVALID, "decoder_train_bwd: bad argument");
+    const DecScratch X = dec_scratch(B, T, S);
+    TACO_REQUIRE(scratch_bytes >= X.total * sizeof(float), B200TACO_ERR_STATE, "decoder_train_bwd: scratch too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const DecSaved sv = dec_saved(B, T, S);
+    const int n = S * B, BT = B * T;
+    float* sc = d_scratch;
+    float *dout = sc + X.dout, *wpg = sc + X.wpg, *wqT = sc + X.wqT, *dzd = sc + X.dzd, *dza = sc + X.dza, *dpq = sc + X.dpq,
+          *dp = sc + X.dp, *d_ah = sc + X.d_ah, *d_dh = sc + X.d_dh, *d_ctx = sc + X.d_ctx, *dca = sc + X.dca, *dcd = sc + X.dcd,
+          *tmp = sc + X.tmp, *tmp2 = sc + X.tmp2, *pq = sc + X.pq, *P = sc + X.P, *gsum = sc + X.gsum, *cum = sc + X.cum,
+          *dpm = sc + X.dpm, *attn = sc + X.attn, *dw = sc + X.dw, *dvs = sc + X.dvs;
+    const float *frames = d_saved + sv.frames, *y1 = d_saved + sv.y1, *y2 = d_saved + sv.y2, *pm = d_saved + sv.pm,
+                *ga = d_saved + sv.ga, *ca = d_saved + sv.ca, *ah = d_saved + sv.ah, *gd = d_saved + sv.gd, *cd = d_saved + sv.cd,
+                *dh = d_saved + sv.dh, *ctx = d_saved + sv.ctx;
+    auto G = [](const float* p) { return const_cast<float*>(p); };
+    auto dense = [&](const float* Xp, int ldx, const float* W, float* Y, int ldy, int rows, int c_in, int c_out, const float* R) {
+        return conv1d_channels_last(Xp, ldx, W, nullptr, nullptr, R, ldy, Y, ldy, rows, rows, c_in, c_out, 1, ACT_NONE, st);
+    };
+#define TT(expr) do { int _e = (expr); if (_e != B200TACO_OK) return _e; } while (0)
+
+    // ---- set-up
+    TT(assemble_dout(d_dcoarse, d_dgate, dout, B, S, st));
+    TT(assemble_wpg(w->proj_w, w->gate_w, wpg, st));
+    TT(transpose2d(wqT, w->attn_query_w, ATT_DIM, RNN, st));                    // (128,1024) -> [1024][128]
+    TT(attn_cumsum(d_align, cum, S, BT, st));
+    TACO_CUDA(cudaMemsetAsync(d_ah, 0, (X.tmp - X.d_ah) * sizeof(float), st));  // d_ah, d_dh, d_ctx, dca, dcd
+    TACO_CUDA(cudaMemsetAsync(gsum, 0, (size_t)BT * sizeof(float), st));
+    TACO_CUDA(cudaMemsetAsync(dpm, 0, (size_t)BT * ATT_DIM * sizeof(float), st));
+    TACO_CUDA(cudaMemsetAsync(d_dmemory, 0, (size_t)BT * EMB * sizeof(float), st));
+    TACO_CUDA(cudaMemsetAsync(dvs, 0, 64 * sizeof(float), st));
+    TACO_CUDA(cudaMemsetAsync(G(grads->attn_loc_dense_w), 0, (size_t)ATT_DIM * LOC_F * sizeof(float), st));
+    TACO_CUDA(cudaMemsetAsync(G(grads->attn_loc_conv_w), 0, (size_t)LOC_F * 2 * LOC_K * sizeof(float), st));
+    TACO_CUDA(cudaMemsetAsync(G(grads->attn_v_w), 0, (size_t)ATT_DIM * sizeof(float), st));
+
+    // ---- reverse walk over the decode steps
+    for (int t = S - 1; t >= 0; --t) {
+        const size_t r = (size_t)t * B;                       // first row of step t in the [S*B][...] buffers
+        // projections (src/model.py:272-274): proj_in = [dh_t | ctx_t]
+        TT(dense(dout + r * PROJ_PAD, PROJ_PAD, wpg, tmp, RNN + EMB, B, PROJ_PAD, RNN + EMB, nullptr));
+        TT(train_axpy(d_dh, RNN, tmp, RNN + EMB, B, RNN, true, st));
+        TT(train_axpy(d_ctx, EMB, tmp + RNN, RNN + EMB, B, EMB, true, st));
+        // decoder LSTM cell (input [ah_t | ctx_t], src/model.py:265-270)
+        TT(lstm_cell_bwd(gd + r * 4 * RNN, cd + r * RNN, t > 0 ? cd + (r - B) * RNN : nullptr, d_dh, d_mask_d ? d_mask_d + r * RNN : nullptr,
+                         lstm_scale, dcd, dzd + r * 4 * RNN, B, st));
+        TT(dense(dzd + r * 4 * RNN, 4 * RNN, w->dec_lstm_w_ih, tmp, RNN + EMB, B, 4 * RNN, RNN + EMB, nullptr));
+        TT(train_axpy(d_ah, RNN, tmp, RNN + EMB, B, RNN, true, st));
+        TT(train_axpy(d_ctx, EMB, tmp + RNN, RNN + EMB, B, EMB, true, st));
+        TT(dense(dzd + r * 4 * RNN, 4 * RNN, w->dec_lstm_w_hh, d_dh, RNN, B, 4 * RNN, RNN, nullptr));     // -> d dh_{t-1}
+        // attention (src/model.py:117-148)
+        TT(dense(ah + r * RNN, RNN, wqT, pq, ATT_DIM, B, RNN, ATT_DIM, nullptr));
+        TT(attention_bwd(d_align + r * T, t > 0 ? d_align + (r - B) * T : nullptr, cum + r * T, pq, pm, d_memory, d_ctx,
+                         d_dalign ? d_dalign + r * T : nullptr, t < S - 1 ? P + (size_t)((t + 1) & 1) * BT : nullptr, gsum,
+                         d_text_lengths, w->attn_loc_conv_w, w->attn_loc_dense_w, w->attn_v_w, w->attn_v_b, w->attn_energy_scale,
+                         d_dmemory, dpm, dpq + r * ATT_DIM, P + (size_t)(t & 1) * BT, G(grads->attn_loc_dense_w),
+                         G(grads->attn_loc_conv_w), G(grads->attn_v_w), dvs, attn, B, T, st));
+        TT(dense(dpq + r * ATT_DIM, ATT_DIM, w->attn_query_w, tmp2, RNN, B, ATT_DIM, RNN, nullptr));
+        TT(train_axpy(d_ah, RNN, tmp2, RNN, B, RNN, true, st));
+        // attention LSTM cell (input [p_t | ctx_{t-1}], src/model.py:256-262)
+        TT(lstm_cell_bwd(ga + r * 4 * RNN, ca + r * RNN, t > 0 ? ca + (r - B) * RNN : nullptr, d_ah, d_mask_a ? d_mask_a + r * RNN : nullptr,
+                         lstm_scale, dca, dza + r * 4 * RNN, B, st));
+        TT(dense(dza + r * 4 * RNN, 4 * RNN, w->attn_lstm_w_ih, tmp, PRENET + EMB, B, 4 * RNN, PRENET + EMB, nullptr));
+        TT(train_axpy(dp + r * PRENET, PRENET, tmp, PRENET + EMB, B, PRENET, false, st));
+        TT(train_axpy(d_ctx, EMB, tmp + PRENET, PRENET + EMB, B, EMB, false, st));                          // -> d ctx_{t-1}
+        TT(dense(dza + r * 4 * RNN, 4 * RNN, w->attn_lstm_w_hh, d_ah, RNN, B, 4 * RNN, RNN, nullptr));    // -> d ah_{t-1}
+    }
+
+    // ---- weight gradients: reductions over all steps, computed as [in][out] and transposed into the parameter layout
+    auto wgrad_into = [&](const float* Xp, int ldx, int c_in, const float* dY, int ldy, int c_out, int rows, float* dst, int ldd) {
+        if (int e = dense_wgrad(Xp, ldx, dY, ldy, dw, rows, rows, c_in, c_out, 1, st)) return e;
+        return transpose_block(dst, ldd, dw, c_out, c_in, c_out, st);         // dst[out][in]
+    };
+    // decoder LSTM: W_ih (4096 x [ah 1024 | ctx 512]), W_hh (4096 x 1024, input dh_{t-1})
+    TT(wgrad_into(ah, RNN, RNN, dzd, 4 * RNN, 4 * RNN, n, G(grads->dec_lstm_w_ih), RNN + EMB));
+    TT(wgrad_into(ctx, EMB, EMB, dzd, 4 * RNN, 4 * RNN, n, G(grads->dec_lstm_w_ih) + RNN, RNN + EMB));
+    TACO_CUDA(cudaMemsetAsync(G(grads->dec_lstm_w_hh), 0, (size_t)4 * RNN * RNN * sizeof(float), st));
+    if (S > 1) TT(wgrad_into(dh, RNN, RNN, dzd + (size_t)B * 4 * RNN, 4 * RNN, 4 * RNN, n - B, G(grads->dec_lstm_w_hh), RNN));
+    TT(train_colsum(G(grads->dec_lstm_b_ih), dzd, n, 4 * RNN, st));
+    TACO_CUDA(cudaMemcpyAsync(G(grads->dec_lstm_b_hh), grads->dec_lstm_b_ih, 4 * RNN * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // attention LSTM: W_ih (4096 x [p 256 | ctx_{t-1} 512]), W_hh (input ah_{t-1})
+    TT(wgrad_into(y2, PRENET, PRENET, dza, 4 * RNN, 4 * RNN, n, G(grads->attn_lstm_w_ih), PRENET + EMB));
+    TACO_CUDA(cudaMemsetAsync(dw, 0, (size_t)EMB * 4 * RNN * sizeof(float), st));
+    if (S > 1) TT(dense_wgrad(ctx, EMB, dza + (size_t)B * 4 * RNN, 4 * RNN, dw, n - B, n - B, EMB, 4 * RNN, 1, st));
+    TT(transpose_block(G(grads->attn_lstm_w_ih) + PRENET, PRENET + EMB, dw, 4 * RNN, EMB, 4 * RNN, st));
+    TACO_CUDA(cudaMemsetAsync(G(grads->attn_lstm_w_hh), 0, (size_t)4 * RNN * RNN * sizeof(float), st));
+    if (S > 1) TT(wgrad_into(ah, RNN, RNN, dza + (size_t)B * 4 * RNN, 4 * RNN, 4 * RNN, n - B, G(grads->attn_lstm_w_hh), RNN));
+    TT(train_colsum(G(grads->attn_lstm_b_ih), dza, n, 4 * RNN, st));
+    TACO_CUDA(cudaMemcpyAsync(G(grads->attn_lstm_b_hh), grads->attn_lstm_b_ih, 4 * RNN * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // query layer (128 x 1024)
+    TT(wgrad_into(ah, RNN, RNN, dpq, ATT_DIM, ATT_DIM, n, G(grads->attn_query_w), RNN));
+    // projections: [dh_t | ctx_t] -> 80 mel rows + 1 gate row (dout has 96 padded columns)
+    TT(dense_wgrad(dh, RNN, dout, PROJ_PAD, dw, n, n, RNN, PROJ_PAD, 1, st));
+    TT(transpose_block(G(grads->proj_w), RNN + EMB, dw, PROJ_PAD, RNN, N_MELS, st));
+    TT(transpose_block(G(grads->gate_w), RNN + EMB, dw + N_MELS, PROJ_PAD, RNN, 1, st));
+    TT(dense_wgrad(ctx, EMB, dout, PROJ_PAD, dw, n, n, EMB, PROJ_PAD, 1, st));
+    TT(transpose_block(G(grads->proj_w) + RNN, RNN + EMB, dw, PROJ_PAD, EMB, N_MELS, st));
+    TT(transpose_block(G(grads->gate_w) + RNN, RNN + EMB, dw + N_MELS, PROJ_PAD, EMB, 1, st));
+    TT(train_colsum(dw, dout, n, PROJ_PAD, st));
+    TACO_CUDA(cudaMemcpyAsync(G(grads->proj_b), dw, N_MELS * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TACO_CUDA(cudaMemcpyAsync(G(grads->gate_b), dw + N_MELS, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // attention scalars
+    TACO_CUDA(cudaMemcpyAsync(G(grads->attn_v_b), dvs, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TACO_CUDA(cudaMemcpyAsync(G(grads->attn_energy_scale), dvs + 1, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // memory layer (128 x 512): pm = memory . W^T
+    TT(wgrad_into(d_memory, EMB, EMB, dpm, ATT_DIM, ATT_DIM, BT, G(grads->attn_memory_w), EMB));
+    TT(dense(dpm, ATT_DIM, w->attn_memory_w, d_dmemory, EMB, BT, ATT_DIM, EMB, d_dmemory));               // dmemory += dpm . W
+    // prenet (src/model.py:166-171): y2 = drop(relu(y1 W2^T)), y1 = drop(relu(x W1^T))
+    float* dy2 = dp + (size_t)n * PRENET;
+    TT(relu_drop_bwd(dp, y2, d_mask_p2, prenet_scale, dy2, (size_t)n * PRENET, st));
+    TT(wgrad_into(y1, PRENET, PRENET, dy2, PRENET, PRENET, n, G(grads->prenet_w[1]), PRENET));
+    TT(dense(dy2, PRENET, w->prenet_w[1], dp, PRENET, n, PRENET, PRENET, nullptr));                       // d y1 (post-dropout)
+    TT(relu_drop_bwd(dp, y1, d_mask_p1, prenet_scale, dy2, (size_t)n * PRENET, st));
+    TT(wgrad_into(frames, N_MELS, N_MELS, dy2, PRENET, PRENET, n, G(grads->prenet_w[0]), N_MELS));
+#undef TT
+    return B200TACO_OK;
 }
 
 }  // extern "C"

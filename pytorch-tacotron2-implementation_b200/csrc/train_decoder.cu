@@ -1,0 +1,344 @@
+// Backward-pass kernels of the teacher-forced decoder (reference Decoder.forward / _decode_step in train mode,
+// src/model.py:246-297; LocationSensitiveAttention :117-148).  First correct fp32 versions: the host walks the decode
+// steps in reverse and launches these kernels plus dense-layer calls per step (train_api.cu).
+#include "handle.h"
+
+namespace b200taco {
+
+namespace {
+
+inline int blocks_for(size_t n) { return (int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256); }
+
+// ---- LSTMCell backward (pointwise part).  gates [B][4096] = i,f,g,o post-activation (gate*1024 + unit), c [B][1024],
+// c_prev [B][1024] or null (zero state), dh_post [B][1024] = gradient w.r.t. the (dropped) hidden state, mask or null,
+// dc [B][1024] carried cell gradient (in/out), dz [B][4096] gradient w.r.t. the gate pre-activations (out).
+__global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c, const float* __restrict__ c_prev,
+                                     const float* __restrict__ dh_post, const float* __restrict__ mask, float scale,
+                                     float* __restrict__ dc, float* __restrict__ dz, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * RNN) return;
+    const int b = i / RNN, u = i % RNN;
+    const float* g4 = gates + (size_t)b * 4 * RNN + u;
+    const float gi = g4[0], gf = g4[RNN], gg = g4[2 * RNN], go = g4[3 * RNN];
+    const float dh = dh_post[i] * (mask ? mask[i] * scale : 1.f);
+    const float tc = tanhf(c[i]);
+    const float dct = dc[i] + dh * go * (1.f - tc * tc);
+    const float cp = c_prev ? c_prev[i] : 0.f;
+    float* d4 = dz + (size_t)b * 4 * RNN + u;
+    d4[0] = dct * gg * gi * (1.f - gi);
+    d4[RNN] = dct * cp * gf * (1.f - gf);
+    d4[2 * RNN] = dct * gi * (1.f - gg * gg);
+    d4[3 * RNN] = dh * tc * go * (1.f - go);
+    dc[i] = dct * gf;
+}
+
+// cum[t] = sum_{tau < t} align[tau]  (exclusive prefix sum over the step axis), one thread per (b, position)
+__global__ void attn_cumsum_kernel(const float* __restrict__ align, float* __restrict__ cum, int S, int BT) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= BT) return;
+    float acc = 0.f;
+    for (int t = 0; t < S; ++t) {
+        cum[(size_t)t * BT + i] = acc;
+        acc += align[(size_t)t * BT + i];
+    }
+}
+
+// dst[i] (+)= a[i] elementwise helpers
+__global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ a, int n, int ld_dst, int ld_a, int cols, int accumulate) {
+    // dst[r][c] (+)= a[r][c] for r < n, c < cols with row strides ld_dst / ld_a
+    const size_t total = (size_t)n * cols;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = i / cols, cc = i % cols;
+        const float v = a[(size_t)r * ld_a + cc];
+        float* d = dst + (size_t)r * ld_dst + cc;
+        *d = accumulate ? *d + v : v;
+    }
+}
+
+// relu + dropout backward: dx = dy * mask * scale * (y > 0)   (y is the layer output AFTER dropout; y > 0 <=> relu' = 1 and kept)
+__global__ void relu_drop_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ mask,
+                                     float scale, float* __restrict__ dx, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float keep = mask ? mask[i] * scale : 1.f;
+        dx[i] = y[i] > 0.f ? dy[i] * keep : 0.f;
+    }
+}
+__global__ void relu_drop_fwd_kernel(float* __restrict__ y, const float* __restrict__ mask, float scale, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        y[i] = mask ? y[i] * mask[i] * scale : y[i];
+}
+
+// ---- attention backward of ONE decode step, one CTA per utterance.
+// Recomputes the location features and tanh arguments from the saved attention weights.
+//   in : w [B][T] (this step's weights), prev [B][T] or null (step 0), cum [B][T], pq [B][128] (Wq . ah_t), pm [B][T][128],
+//        memory [B][T][512], dctx [B][512], dw_ext [B][T] (external d(align) or null), dprev_next [B][T] (gradient that the
+//        NEXT step's location conv sent to its `prev` input = this step's weights), gsum [B][T] (sum over later steps of
+//        the gradients w.r.t. their `cum` inputs), lengths or null
+//   out: dmemory += , dpm += , dpq [B][128], dprev_out [B][T] (gradient w.r.t. THIS step's prev input), gsum += gradient
+//        w.r.t. this step's cum input, and the parameter gradients (atomically accumulated): dWld [128][32],
+//        dWloc [32][2][31], dv [128], dvb, dscale
+//   scratch per utterance: loc [T][32], dloc [T][32], dw [T]
+__global__ void __launch_bounds__(256) attention_bwd_kernel(
+    const float* __restrict__ w, const float* __restrict__ prev, const float* __restrict__ cum, const float* __restrict__ pq,
+    const float* __restrict__ pm, const float* __restrict__ memory, const float* __restrict__ dctx,
+    const float* __restrict__ dw_ext, const float* __restrict__ dprev_next, float* __restrict__ gsum,
+    const int64_t* __restrict__ lengths, const float* __restrict__ Wloc /* [32][2][31] */,
+    const float* __restrict__ Wld /* [128][32] */, const float* __restrict__ v /* [128] */, const float* __restrict__ vb_p,
+    const float* __restrict__ escale_p,
+    float* __restrict__ dmemory, float* __restrict__ dpm, float* __restrict__ dpq, float* __restrict__ dprev_out,
+    float* __restrict__ dWld, float* __restrict__ dWloc, float* __restrict__ dv, float* __restrict__ dvb_scale /* [2] */,
+    float* __restrict__ scratch, int B, int T) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int len = lengths ? (int)lengths[b] : T;
+    const float vb = vb_p[0], escale = escale_p[0];
+    __shared__ float dctx_s[EMB];
+    __shared__ float wloc_s[LOC_F * 2 * LOC_K];
+    __shared__ float wld_s[ATT_DIM * LOC_F];
+    __shared__ float v_s[ATT_DIM], pq_s[ATT_DIM], dpq_s[ATT_DIM], dv_s[ATT_DIM];
+    __shared__ float red_s[256];
+    __shared__ float tile_du[8][ATT_DIM];          // du of 8 positions at a time
+    __shared__ float tile_de[8];
+    float* loc = scratch + (size_t)b * T * (2 * LOC_F + 1);
+    float* dloc = loc + (size_t)T * LOC_F;
+    float* dwv = dloc + (size_t)T * LOC_F;
+    const float* wb = w + (size_t)b * T;
+    const float* pb = prev ? prev + (size_t)b * T : nullptr;
+    const float* cb = cum + (size_t)b * T;
+
+    for (int i = tid; i < EMB; i += 256) dctx_s[i] = dctx[(size_t)b * EMB + i];
+    for (int i = tid; i < LOC_F * 2 * LOC_K; i += 256) wloc_s[i] = Wloc[i];
+    for (int i = tid; i < ATT_DIM * LOC_F; i += 256) wld_s[i] = Wld[i];
+    if (tid < ATT_DIM) { v_s[tid] = v[tid]; pq_s[tid] = pq[(size_t)b * ATT_DIM + tid]; dpq_s[tid] = 0.f; dv_s[tid] = 0.f; }
+    __syncthreads();
+
+    // (a) dw[tau] = dctx . memory[tau] + external terms ; dmemory[tau] += w[tau] * dctx ; s = sum_tau w dw
+    float s_part = 0.f;
+    for (int tau = tid >> 5; tau < T; tau += 8) {          // one warp per position
+        const int lane = tid & 31;
+        const float* mrow = memory + ((size_t)b * T + tau) * EMB;
+        float* dmrow = dmemory + ((size_t)b * T + tau) * EMB;
+        const float wt = wb[tau];
+        float acc = 0.f;
+        for (int j = lane; j < EMB; j += 32) {
+            acc = fmaf(dctx_s[j], mrow[j], acc);
+            dmrow[j] += wt * dctx_s[j];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            float d = acc + (dw_ext ? dw_ext[(size_t)b * T + tau] : 0.f) + (dprev_next ? dprev_next[(size_t)b * T + tau] : 0.f) +
+                      gsum[(size_t)b * T + tau];
+            dwv[tau] = d;
+            s_part += wt * d;
+        }
+    }
+    red_s[tid] = s_part;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) red_s[tid] += red_s[tid + o];
+        __syncthreads();
+    }
+    const float s_all = red_s[0];
+    __syncthreads();
+
+    // (b) location conv recomputed: loc[tau][f] = sum_c sum_k Wloc[f][c][k] * in_c[tau + k - 15]
+    for (int i = tid; i < T * LOC_F; i += 256) {
+        const int tau = i / LOC_F, f = i % LOC_F;
+        float acc = 0.f;
+        for (int k = 0; k < LOC_K; ++k) {
+            const int tt = tau + k - (LOC_K - 1) / 2;
+            if (tt >= 0 && tt < T) {
+                acc = fmaf(wloc_s[(f * 2 + 0) * LOC_K + k], pb ? pb[tt] : 0.f, acc);
+                acc = fmaf(wloc_s[(f * 2 + 1) * LOC_K + k], cb[tt], acc);
+            }
+        }
+        loc[i] = acc;
+    }
+    __syncthreads();
+
+    // (c) per position: de -> du[a], dpq, dv, dvb, dscale, dpm ; 8 positions per pass, thread = (position p8, 32 dims)
+    float dvb_part = 0.f, dscale_part = 0.f;
+    for (int t0 = 0; t0 < T; t0 += 8) {
+        const int p8 = tid >> 5, lane = tid & 31, tau = t0 + p8;
+        float e_raw_part = 0.f;
+        float th[4], lfv[4];
+        if (tau < T) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int a = lane + 32 * q;
+                float lf = 0.f;
+                for (int f = 0; f < LOC_F; ++f) lf = fmaf(wld_s[a * LOC_F + f], loc[tau * LOC_F + f], lf);
+                lfv[q] = lf;
+                th[q] = tanhf(pq_s[a] + pm[((size_t)b * T + tau) * ATT_DIM + a] + lf);
+                e_raw_part = fmaf(v_s[a], th[q], e_raw_part);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) e_raw_part += __shfl_xor_sync(0xffffffffu, e_raw_part, o);
+        float de_raw = 0.f;
+        if (tau < T) {
+            const float e_raw = e_raw_part + vb;
+            // softmax backward; masked positions (energy filled with -1e9, src/model.py:132) pass no gradient
+            const float de = tau < len ? wb[tau] * (dwv[tau] - s_all) : 0.f;
+            de_raw = de * escale;
+            if (lane == 0) { dscale_part += de * e_raw; dvb_part += de_raw; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int a = lane + 32 * q;
+                const float du = de_raw * v_s[a] * (1.f - th[q] * th[q]);
+                tile_du[p8][a] = du;
+                dpm[((size_t)b * T + tau) * ATT_DIM + a] += du;
+                atomicAdd(&dv_s[a], de_raw * th[q]);
+                atomicAdd(&dpq_s[a], du);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) tile_du[p8][lane + 32 * q] = 0.f;
+        }
+        if (lane == 0) tile_de[p8] = de_raw;
+        __syncthreads();
+        // dloc[tau][f] = sum_a du[a] * Wld[a][f] ; dWld[a][f] += du[tau][a] * loc[tau][f]
+        {
+            const int f = tid & 31, pp = tid >> 5, tt = t0 + pp;
+            if (tt < T) {
+                float acc = 0.f;
+                for (int a = 0; a < ATT_DIM; ++a) acc = fmaf(tile_du[pp][a], wld_s[a * LOC_F + f], acc);
+                dloc[tt * LOC_F + f] = acc;
+            }
+        }
+        for (int i = tid; i < ATT_DIM * LOC_F; i += 256) {
+            const int a = i / LOC_F, f = i % LOC_F;
+            float acc = 0.f;
+            for (int pp = 0; pp < 8; ++pp)
+                if (t0 + pp < T) acc = fmaf(tile_du[pp][a], loc[(t0 + pp) * LOC_F + f], acc);
+            if (acc != 0.f) atomicAdd(dWld + i, acc);
+        }
+        __syncthreads();
+        (void)lfv;
+    }
+    // block sums of dvb / dscale
+    red_s[tid] = dvb_part;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (tid < o) red_s[tid] += red_s[tid + o]; __syncthreads(); }
+    if (tid == 0) atomicAdd(dvb_scale + 0, red_s[0]);
+    __syncthreads();
+    red_s[tid] = dscale_part;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (tid < o) red_s[tid] += red_s[tid + o]; __syncthreads(); }
+    if (tid == 0) atomicAdd(dvb_scale + 1, red_s[0]);
+    if (tid < ATT_DIM) {
+        dpq[(size_t)b * ATT_DIM + tid] = dpq_s[tid];
+        atomicAdd(dv + tid, dv_s[tid]);
+    }
+    __syncthreads();
+
+    // (d) location conv backward: dWloc[f][c][k] += sum_tau dloc[tau][f] * in_c[tau + k - 15]
+    for (int i = tid; i < LOC_F * 2 * LOC_K; i += 256) {
+        const int k = i % LOC_K, c = (i / LOC_K) % 2, f = i / (2 * LOC_K);
+        float acc = 0.f;
+        for (int tau = 0; tau < T; ++tau) {
+            const int tt = tau + k - (LOC_K - 1) / 2;
+            if (tt >= 0 && tt < T) acc = fmaf(dloc[tau * LOC_F + f], c == 0 ? (pb ? pb[tt] : 0.f) : cb[tt], acc);
+        }
+        atomicAdd(dWloc + i, acc);
+    }
+    //     d in_c[tt] = sum_f sum_k dloc[tt - k + 15][f] * Wloc[f][c][k]
+    for (int i = tid; i < 2 * T; i += 256) {
+        const int c = i / T, tt = i % T;
+        float acc = 0.f;
+        for (int k = 0; k < LOC_K; ++k) {
+            const int tau = tt - k + (LOC_K - 1) / 2;
+            if (tau >= 0 && tau < T)
+                for (int f = 0; f < LOC_F; ++f) acc = fmaf(dloc[tau * LOC_F + f], wloc_s[(f * 2 + c) * LOC_K + k], acc);
+        }
+        if (c == 0) dprev_out[(size_t)b * T + tt] = acc;
+        else gsum[(size_t)b * T + tt] += acc;
+    }
+}
+
+// dst[c][r] = src[r][c] for r < R, c < C (row strides ldd / lds)
+__global__ void transpose_block_kernel(float* __restrict__ dst, int ldd, const float* __restrict__ src, int lds, int R, int C) {
+    const size_t total = (size_t)R * C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = i % R, c = i / R;
+        dst[(size_t)c * ldd + r] = src[(size_t)r * lds + c];
+    }
+}
+// dout[s][b][96]: columns 0..79 = d_coarse[b][s][:], 80 = d_gate[b][s], rest 0
+__global__ void assemble_dout_kernel(const float* __restrict__ d_coarse, const float* __restrict__ d_gate, float* __restrict__ dout,
+                                     int B, int S) {
+    const size_t total = (size_t)S * B * PROJ_PAD;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int o = i % PROJ_PAD, b = (i / PROJ_PAD) % B, s = i / ((size_t)PROJ_PAD * B);
+        float v = 0.f;
+        if (o < N_MELS) v = d_coarse[((size_t)b * S + s) * N_MELS + o];
+        else if (o == N_MELS) v = d_gate[(size_t)b * S + s];
+        dout[i] = v;
+    }
+}
+// Wpg[96][1536]: rows 0..79 = linear_projection.weight, row 80 = gate_layer.weight, rest 0
+__global__ void assemble_wpg_kernel(const float* __restrict__ wp, const float* __restrict__ wg, float* __restrict__ dst) {
+    const int total = PROJ_PAD * (RNN + EMB);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = i % (RNN + EMB), o = i / (RNN + EMB);
+        dst[i] = o < N_MELS ? wp[(size_t)o * (RNN + EMB) + c] : (o == N_MELS ? wg[c] : 0.f);
+    }
+}
+
+}  // namespace
+
+int transpose_block(float* dst, int ldd, const float* src, int lds, int R, int C, cudaStream_t st) {
+    transpose_block_kernel<<<blocks_for((size_t)R * C), 256, 0, st>>>(dst, ldd, src, lds, R, C);
+    TACO_LAUNCHED();
+    return B200TACO_OK;
+}
+int assemble_dout(const float* d_coarse, const float* d_gate, float* dout, int B, int S, cudaStream_t st) {
+    assemble_dout_kernel<<<blocks_for((size_t)S * B * PROJ_PAD), 256, 0, st>>>(d_coarse, d_gate, dout, B, S);
+    TACO_LAUNCHED();
+    return B200TACO_OK;
+}
+int assemble_wpg(const float* wp, const float* wg, float* dst, cudaStream_t st) {
+    assemble_wpg_kernel<<<256, 256, 0, st>>>(wp, wg, dst);
+    TACO_LAUNCHED();
+    return B200TACO_OK;
+}
+
+int lstm_cell_bwd(const float* gates, const float* c, const float* c_prev, const float* dh_post, const float* mask, float scale,
+                  float* dc, float* dz, int B, cudaStream_t st) {
+    lstm_cell_bwd_kernel<<<(B * RNN + 255) / 256, 256, 0, st>>>(gates, c, c_prev, dh_post, mask, scale, dc, dz, B);
+    TACO_LAUNCHED();
+    return B200TACO_OK;
+}
+int attn_cumsum(const float* align, float* cum, int S, int BT, cudaStream_t st) {
+    attn_cumsum_kernel<<<(BT + 255) / 256, 256, 0, st>>>(align, cum, S, BT);
+    TACO_LAUNCHED();
+    return B200TACO_OK;
+}
+int train_axpy(float* dst, int ld_dst, const float* a, int ld_a, int n, int cols, bool accumulate, cudaStream_t st) {
+    axpy_kernel<<<blocks_for((size_t)n * cols), 256, 0, st>>>(dst, a, n, ld_dst, ld_a, cols, accumulate ? 1 : 0);
+    TACO_LAUNCHED();
+    return B200TACO_OK;
+}
+int relu_drop_bwd(const float* dy, const float* y, const float* mask, float scale, float* dx, size_t n, cudaStream_t st) {
+    relu_drop_bwd_kernel<<<blocks_for(n), 256, 0, st>>>(dy, y, mask, scale, dx, n);
+    TACO_LAUNCHED();
+    return B200TACO_OK;
+}
+int relu_drop_fwd(float* y, const float* mask, float scale, size_t n, cudaStream_t st) {
+    relu_drop_fwd_kernel<<<blocks_for(n), 256, 0, st>>>(y, mask, scale, n);
+    TACO_LAUNCHED();
+    return B200TACO_OK;
+}
+size_t attention_bwd_scratch_floats(int B, int T) { return (size_t)B * T * (2 * LOC_F + 1); }
+int attention_bwd(const float* w, const float* prev, const float* cum, const float* pq, const float* pm, const float* memory,
+                  const float* dctx, const float* dw_ext, const float* dprev_next, float* gsum, const int64_t* lengths,
+                  const float* Wloc, const float* Wld, const float* v, const float* vb, const float* escale, float* dmemory, float* dpm,
+                  float* dpq, float* dprev_out, float* dWld, float* dWloc, float* dv, float* dvb_scale, float* scratch, int B,
+                  int T, cudaStream_t st) {
+    attention_bwd_kernel<<<B, 256, 0, st>>>(w, prev, cum, pq, pm, memory, dctx, dw_ext, dprev_next, gsum, lengths, Wloc, Wld, v, vb,
+                                            escale, dmemory, dpm, dpq, dprev_out, dWld, dWloc, dv, dvb_scale, scratch, B, T);
+    TACO_LAUNCHED();
+    return B200TACO_OK;
+}
+
+}  // namespace b200taco

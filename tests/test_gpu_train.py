@@ -95,3 +95,47 @@ def test_encoder_train_forward_backward(B, T):
         else:
             d = (p.grad.cpu().double() - ref_p[k].grad.double()).abs() / ref_p[k].grad.double().abs().max()
             assert float(d.median()) <= 1e-3 and float(d.max()) <= 0.1, (k, float(d.median()), float(d.max()))
+
+
+@pytest.mark.parametrize("B,T,S,use_masks,use_lengths", [(2, 9, 3, False, False), (3, 21, 6, True, True), (5, 40, 12, True, True)])
+def test_decoder_train_forward_backward(B, T, S, use_masks, use_lengths):
+    """Teacher-forced decoder in train mode (B >= 4 takes the tensor-core kernel) + the reverse-step backward."""
+    sd = util.weights("stress", True)                      # bf16-representable weights: both sides see the same values
+    g = torch.Generator().manual_seed(9)
+    memory = torch.randn(B, T, 512, generator=g) * 0.3
+    mel_t = torch.randn(B, 80, S, generator=g) * 2 - 5
+    lens = torch.randint(max(1, T // 2), T + 1, (B,), generator=g) if use_lengths else None
+    if lens is not None:
+        lens[0] = T
+    dmel, dgate, dalign = torch.randn(B, S, 80, generator=g), torch.randn(B, S, generator=g), torch.randn(S, B, T, generator=g)
+    masks = None
+    if use_masks:
+        masks = {"p1": (torch.rand(S * B, 256, generator=g) >= 0.5).float(), "p2": (torch.rand(S * B, 256, generator=g) >= 0.5).float(),
+                 "a": (torch.rand(S, B, 1024, generator=g) >= 0.1).float(), "d": (torch.rand(S, B, 1024, generator=g) >= 0.1).float()}
+    keys = train.decoder_param_keys()
+    ref_p = {k: sd[k].clone().requires_grad_(True) for k in keys}
+    ref_mem = memory.clone().requires_grad_(True)
+    rm, rg, ra = TO.decoder_train({**sd, **ref_p}, ref_mem, mel_t, lens, masks)
+    (rm * dmel).sum().add((rg * dgate).sum()).add((ra * dalign).sum()).backward()
+
+    m = Tacotron2().eval()
+    m.load_state_dict(sd)
+    m = m.to("cuda:0")
+    eng = m._get_engine()
+    params = [dict(m.named_parameters())[k] for k in keys]
+    mem = memory.cuda().requires_grad_(True)
+    cm = {k: v.cuda() for k, v in masks.items()} if masks else None
+    mel, gate, align = train.DecoderTrainFn.apply(eng, mem, mel_t.cuda(), lens.cuda() if lens is not None else None, cm, *params)
+    assert rel_err(mel.detach().cpu(), rm.detach()) <= 2e-5 and rel_err(gate.detach().cpu(), rg.detach()) <= 2e-5
+    assert rel_err(align.detach().cpu(), ra.detach()) <= 2e-5
+    (mel * dmel.cuda()).sum().add((gate * dgate.cuda()).sum()).add((align * dalign.cuda()).sum()).backward()
+    errs = {k: rel_err(p.grad.cpu(), ref_p[k].grad) for k, p in zip(keys, params)}
+    errs["memory"] = rel_err(mem.grad.cpu(), ref_mem.grad)
+    # softmax ignores a constant added to every energy: d/d(v.bias) is zero up to rounding on both sides
+    vb = "decoder.attention.v.bias"
+    assert float(dict(zip(keys, params))[vb].grad.abs().max()) <= 1e-3 and float(ref_p[vb].grad.abs().max()) <= 1e-3
+    del errs[vb]
+    print({k: f"{v:.1e}" for k, v in errs.items()})
+    # prenet ReLU kinks aside (see the encoder test), everything is smooth: 1e-3 of the largest entry
+    for k, v in errs.items():
+        assert v <= 2e-3, (k, v)
