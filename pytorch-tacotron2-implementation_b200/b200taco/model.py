@@ -143,8 +143,8 @@ class Tacotron2(nn.Module):
     def _check_mode(self, what):
         if self.training:
             raise B200TacoError(
-                f"{what}: training-mode semantics (dropout, BatchNorm batch statistics, backward) are "
-                "not built yet in this round; call model.eval(). No PyTorch fallback is provided.")
+                f"{what}: free-running inference in train() mode is not supported (the reference only calls it in "
+                "eval mode, train.py:60, inference.py:66); call model.eval().")
 
     def _maybe_init_projection_bias(self, mel_targets):
         """F10 side effect, src/model.py:424-441: first forward sets the mel bias to the target mean."""
@@ -158,15 +158,48 @@ class Tacotron2(nn.Module):
                 self._projection_bias_initialized = True
 
     # ------------------------------------------------------------------ public API
-    @torch.no_grad()
     def forward(self, text_inputs, mel_targets, text_lengths=None, use_postnet=True):
-        """Teacher-forced pass, src/model.py:454-480.
-
-        Rows are independent in eval mode, so batches beyond the library's per-launch limit
-        (``engine.max_batch`` = 64 rows) run as consecutive launches over row chunks."""
-        self._check_mode("Tacotron2.forward")
+        """Teacher-forced pass, src/model.py:454-480.  eval(): inference kernels, no autograd.  train(): dropout,
+        BatchNorm batch statistics (running statistics updated) and autograd through the hand-written backward."""
         if not self._projection_bias_initialized:
             self._maybe_init_projection_bias(mel_targets)
+        if self.training:
+            return self._forward_train(text_inputs, mel_targets, text_lengths, use_postnet)
+        with torch.no_grad():
+            return self._forward_eval(text_inputs, mel_targets, text_lengths, use_postnet)
+
+    def _forward_train(self, text_inputs, mel_targets, text_lengths, use_postnet):
+        """Train-mode forward: three autograd stages over the C ABI (b200taco/train.py).  The dropout masks are drawn
+        here with PyTorch's device generator; one launch carries at most ``engine.max_batch`` rows and BatchNorm
+        statistics span the whole batch, so larger batches are not chunked."""
+        from . import train as T
+        eng = self._get_engine()                                   # (re)packs the decoder weights if a parameter changed
+        B, S = text_inputs.shape[0], mel_targets.shape[2]
+        if B > eng.max_batch:
+            raise B200TacoError(f"train-mode forward carries at most {eng.max_batch} rows per call (got {B})")
+        dev = text_inputs.device
+        named = dict(self.named_parameters())
+        enc_p = [named[k] for k in T.encoder_param_keys()]
+        dec_p = [named[k] for k in T.decoder_param_keys()]
+        post_p = [named[k] for k in T.postnet_param_keys()]
+        memory = T.EncoderTrainFn.apply(eng, text_inputs, *enc_p)
+        n_enc = B * text_inputs.shape[1]
+        for bn, (mean, var) in zip([c[1] for c in self.encoder.convolutions], eng._enc_bn_stats):
+            T.update_running_stats(bn, mean, var, n_enc)
+        if text_lengths is None:
+            text_lengths = torch.full((B,), text_inputs.shape[1], dtype=torch.long, device=dev)     # src/model.py:462-469
+        coarse, gate, align = T.DecoderTrainFn.apply(eng, memory, mel_targets, text_lengths, T.draw_decoder_masks(B, S, dev), *dec_p)
+        if use_postnet:
+            post = T.PostnetTrainFn.apply(eng, coarse, T.draw_postnet_masks(B, S, dev), *post_p)
+            for bn, (mean, var) in zip([c[1] for c in self.postnet.convolutions], eng._post_bn_stats):
+                T.update_running_stats(bn, mean, var, B * S)
+        else:
+            post = coarse
+        return post, coarse, gate, list(align.unbind(0))
+
+    def _forward_eval(self, text_inputs, mel_targets, text_lengths=None, use_postnet=True):
+        """Rows are independent in eval mode, so batches beyond the library's per-launch limit
+        (``engine.max_batch`` = 64 rows) run as consecutive launches over row chunks."""
         eng = self._get_engine()
         outs = []
         for lo in range(0, text_inputs.shape[0], eng.max_batch):

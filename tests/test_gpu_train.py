@@ -53,10 +53,8 @@ def test_postnet_train_forward_backward(B, S, use_masks):
         else:
             assert rel_err(p.grad.cpu(), ref_p[k].grad) <= 2e-4, k
     # batch statistics left for the running-stat update
-    saved_stats = post.grad_fn.bn_stats if hasattr(post.grad_fn, "bn_stats") else None
-    if saved_stats is not None:
-        for (mean, var), (rm, rv) in zip(saved_stats, ref_stats):
-            assert rel_err(mean.cpu(), rm.detach()) <= 1e-5 and rel_err(var.cpu(), rv.detach()) <= 1e-4
+    for (mean, var), (rm, rv) in zip(eng._post_bn_stats, ref_stats):
+        assert rel_err(mean.cpu(), rm.detach()) <= 1e-5 and rel_err(var.cpu(), rv.detach()) <= 1e-4
 
 
 @pytest.mark.parametrize("B,T", [(1, 7), (3, 19), (8, 60)])
@@ -139,3 +137,58 @@ def test_decoder_train_forward_backward(B, T, S, use_masks, use_lengths):
     # prenet ReLU kinks aside (see the encoder test), everything is smooth: 1e-3 of the largest entry
     for k, v in errs.items():
         assert v <= 2e-3, (k, v)
+
+
+def test_full_model_train_step_matches_reference_semantics():
+    """model.train(); model(...) end to end: loss.backward() fills every parameter's .grad; gradients equal torch autograd
+    on the train-mode oracle chain with the SAME dropout masks; BatchNorm running statistics move as nn.BatchNorm1d's."""
+    from b200taco import train as T
+    B, Tn, S = 4, 23, 7
+    sd = util.weights("stress", True)
+    ids = synth.phoneme_ids(B, Tn, seed=31)
+    g = torch.Generator().manual_seed(32)
+    mel_t = torch.randn(B, 80, S, generator=g) * 2 - 5
+    lens = torch.tensor([Tn, 20, 17, 12])
+    m = Tacotron2()
+    m.load_state_dict(sd)
+    m._projection_bias_initialized = True
+    m = m.to("cuda:0").train()
+    # record the masks the model draws
+    drawn = {}
+    dd, dp = T.draw_decoder_masks, T.draw_postnet_masks
+    T.draw_decoder_masks = lambda *a, **k: drawn.setdefault("dec", dd(*a, **k))
+    T.draw_postnet_masks = lambda *a, **k: drawn.setdefault("post", dp(*a, **k))
+    try:
+        post, coarse, gate, aligns = m(ids.cuda(), mel_t.cuda(), lens.cuda())
+    finally:
+        T.draw_decoder_masks, T.draw_postnet_masks = dd, dp
+    wl = torch.Generator().manual_seed(33)
+    wpost, wco, wg = torch.randn(B, S, 80, generator=wl), torch.randn(B, S, 80, generator=wl), torch.randn(B, S, generator=wl)
+    wal = torch.randn(S, B, Tn, generator=wl)
+    loss = (post * wpost.cuda()).sum() + (coarse * wco.cuda()).sum() + (gate * wg.cuda()).sum() + (torch.stack(aligns) * wal.cuda()).sum()
+    loss.backward()
+
+    ref_p = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    full = {**sd, **ref_p}
+    mem, enc_stats = TO.encoder_train(full, ids)
+    rc, rg, ra = TO.decoder_train(full, mem, mel_t, lens, {k: v.cpu() for k, v in drawn["dec"].items()})
+    rpost, post_stats = TO.postnet_train(full, rc, [x.cpu() for x in drawn["post"]])
+    ((rpost * wpost).sum() + (rc * wco).sum() + (rg * wg).sum() + (ra * wal).sum()).backward()
+
+    assert rel_err(post.detach().cpu(), rpost.detach()) <= 5e-5 and rel_err(coarse.detach().cpu(), rc.detach()) <= 2e-5
+    named = dict(m.named_parameters())
+    missing = [k for k, p in named.items() if p.grad is None]
+    assert not missing, missing
+    worst = {}
+    for k, p in named.items():
+        if k.endswith(".0.bias") or k.endswith("v.bias"):            # zero gradients (BatchNorm / softmax invariance)
+            continue
+        d = (p.grad.cpu().double() - ref_p[k].grad.double()).abs() / (ref_p[k].grad.double().abs().max() + 1e-12)
+        worst[k] = (float(d.median()), float(d.max()))
+        assert float(d.median()) <= 1e-3 and float(d.max()) <= 0.1, (k, worst[k])
+    # running statistics: momentum 0.1 from (0, 1), unbiased variance
+    bn = m.postnet.convolutions[0][1]
+    n = B * S
+    assert rel_err(bn.running_mean.cpu(), 0.1 * post_stats[0][0].detach()) <= 1e-4
+    assert rel_err(bn.running_var.cpu(), 0.9 + 0.1 * post_stats[0][1].detach() * n / (n - 1)) <= 1e-4
+    assert int(bn.num_batches_tracked) == 1
