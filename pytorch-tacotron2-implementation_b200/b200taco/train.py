@@ -62,6 +62,7 @@ class PostnetTrainFn(torch.autograd.Function):
     0/1 float tensors or None), then the 20 postnet parameters in ``postnet_param_keys()`` order."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)     # train.py runs the model under autocast
     def forward(ctx, eng: Engine, coarse, masks, *params):
         lib = eng._lib
         coarse = coarse.contiguous()
@@ -99,6 +100,7 @@ class PostnetTrainFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dpost):
         eng, lib = ctx.eng, ctx.eng._lib
         coarse, saved, *params = ctx.saved_tensors
@@ -137,6 +139,7 @@ class EncoderTrainFn(torch.autograd.Function):
     dropout, F3).  Inputs: engine, ids (B,T) int64, then the 21 encoder parameters in ``encoder_param_keys()`` order."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, eng: Engine, ids, *params):
         lib = eng._lib
         ids = ids.to(dtype=torch.int64).contiguous()
@@ -165,6 +168,7 @@ class EncoderTrainFn(torch.autograd.Function):
         return memory
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dmemory):
         eng, lib = ctx.eng, ctx.eng._lib
         ids, saved, *params = ctx.saved_tensors
@@ -203,6 +207,7 @@ class DecoderTrainFn(torch.autograd.Function):
     (p1, p2: (S*B,256); a, d: (S,B,1024)) or None, then the 21 decoder parameters in ``decoder_param_keys()`` order."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, eng: Engine, memory, mel_targets, text_lengths, masks, *params):
         lib = eng._lib
         memory = memory.contiguous()
@@ -229,10 +234,10 @@ class DecoderTrainFn(torch.autograd.Function):
                                                  saved.numel() * 4, ws, wsz, eng._stream()), "b200taco_decoder_train_fwd")
         ctx.eng, ctx.masks, ctx.scales, ctx.tl, ctx.keys = eng, masks, (ps, ls), tl, decoder_param_keys()
         ctx.save_for_backward(memory, saved, align, *[p.detach() for p in params])
-        ctx.mark_non_differentiable()
         return mel, gate, align
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dmel, dgate, dalign):
         eng, lib = ctx.eng, ctx.eng._lib
         memory, saved, align, *params = ctx.saved_tensors

@@ -192,3 +192,32 @@ def test_full_model_train_step_matches_reference_semantics():
     assert rel_err(bn.running_mean.cpu(), 0.1 * post_stats[0][0].detach()) <= 1e-4
     assert rel_err(bn.running_var.cpu(), 0.9 + 0.1 * post_stats[0][1].detach() * n / (n - 1)) <= 1e-4
     assert int(bn.num_batches_tracked) == 1
+
+
+def test_train_step_under_autocast_and_grad_scaler():
+    """The reference's training step runs under torch.autocast with a GradScaler (train.py:391-392, :510-524):
+    the stages take fp32 whatever the autocast state, and the backward is linear in the scaled loss."""
+    B, Tn, S = 4, 17, 5
+    m = Tacotron2()
+    m.load_state_dict(util.weights())
+    m._projection_bias_initialized = True
+    m = m.to("cuda:0").train()
+    ids = synth.phoneme_ids(B, Tn, seed=41).cuda()
+    mel_t = (torch.randn(B, 80, S, generator=torch.Generator().manual_seed(42)) * 2 - 5).cuda()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    scaler = torch.amp.GradScaler("cuda")
+    before = m.decoder.linear_projection.weight.detach().clone()
+    with torch.autocast("cuda", dtype=torch.float16):
+        post, coarse, gate, aligns = m(ids, mel_t, None)
+        loss = (post.float() - mel_t.transpose(1, 2)).abs().mean() + (coarse.float() - mel_t.transpose(1, 2)).abs().mean()
+    assert post.dtype == torch.float32
+    scaler.scale(loss).backward()
+    scaler.unscale_(opt)
+    norm = torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+    assert torch.isfinite(norm)
+    scaler.step(opt)
+    scaler.update()
+    assert not torch.equal(before, m.decoder.linear_projection.weight.detach())
+    m.eval()                                                 # the optimiser step invalidates the packed cache
+    out = m.inference(ids, max_len_cap=3)
+    assert torch.isfinite(out[0]).all()
