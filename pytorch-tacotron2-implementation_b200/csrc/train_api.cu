@@ -41,8 +41,10 @@ size_t attention_bwd_scratch_floats(int B, int T);
 int attention_bwd(const float* w, const float* prev, const float* cum, const float* pq, const float* pm, const float* memory,
                   const float* dctx, const float* dw_ext, const float* dprev_next, float* gsum, const int64_t* lengths,
                   const float* Wloc, const float* Wld, const float* v, const float* vb, const float* escale, float* dmemory,
-                  float* dpm, float* dpq, float* dprev_out, float* dWld, float* dWloc, float* dv, float* dvb_scale, float* scratch,
-                  int B, int T, cudaStream_t st);
+                  float* dpm, float* dpq, float* dprev_out, float* pacc, float* scratch, int B, int T, cudaStream_t st);
+constexpr int ATTN_PACC_F = ATT_DIM * LOC_F + LOC_F * 2 * LOC_K + ATT_DIM + 64;
+int skinny_gemm(const float* X, int ldx, const float* W, int ldw, float* out, int ldo, int B, int K, int N, bool accumulate,
+                cudaStream_t st);
 int transpose_block(float* dst, int ldd, const float* src, int lds, int R, int C, cudaStream_t st);
 int assemble_dout(const float* d_coarse, const float* d_gate, float* dout, int B, int S, cudaStream_t st);
 int assemble_wpg(const float* wp, const float* wg, float* dst, cudaStream_t st);
@@ -317,7 +319,7 @@ DecScratch dec_scratch(int B, int T, int S) {
     d.dpm = take((size_t)B * T * ATT_DIM);
     d.attn = take(attention_bwd_scratch_floats(B, T));
     d.dw = take((size_t)4 * RNN * (RNN + EMB));   // largest [in][out] weight gradient (1536 x 4096)
-    d.dvs = take(64);
+    d.dvs = take((size_t)B * ATTN_PACC_F + ATTN_PACC_F);   // per-utterance attention parameter-gradient accumulators + their sum
     d.total = off;
     return d;
 }
@@ -366,41 +368,37 @@ B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200ta
     TACO_CUDA(cudaMemsetAsync(gsum, 0, (size_t)BT * sizeof(float), st));
     TACO_CUDA(cudaMemsetAsync(dpm, 0, (size_t)BT * ATT_DIM * sizeof(float), st));
     TACO_CUDA(cudaMemsetAsync(d_dmemory, 0, (size_t)BT * EMB * sizeof(float), st));
-    TACO_CUDA(cudaMemsetAsync(dvs, 0, 64 * sizeof(float), st));
-    TACO_CUDA(cudaMemsetAsync(G(grads->attn_loc_dense_w), 0, (size_t)ATT_DIM * LOC_F * sizeof(float), st));
-    TACO_CUDA(cudaMemsetAsync(G(grads->attn_loc_conv_w), 0, (size_t)LOC_F * 2 * LOC_K * sizeof(float), st));
-    TACO_CUDA(cudaMemsetAsync(G(grads->attn_v_w), 0, (size_t)ATT_DIM * sizeof(float), st));
+    TACO_CUDA(cudaMemsetAsync(dvs, 0, ((size_t)B * ATTN_PACC_F + ATTN_PACC_F) * sizeof(float), st));
 
     // ---- reverse walk over the decode steps
     for (int t = S - 1; t >= 0; --t) {
         const size_t r = (size_t)t * B;                       // first row of step t in the [S*B][...] buffers
-        // projections (src/model.py:272-274): proj_in = [dh_t | ctx_t]
-        TT(dense(dout + r * PROJ_PAD, PROJ_PAD, wpg, tmp, RNN + EMB, B, PROJ_PAD, RNN + EMB, nullptr));
-        TT(train_axpy(d_dh, RNN, tmp, RNN + EMB, B, RNN, true, st));
-        TT(train_axpy(d_ctx, EMB, tmp + RNN, RNN + EMB, B, EMB, true, st));
+        // projections (src/model.py:272-274): proj_in = [dh_t | ctx_t]; the partial products are added straight onto the
+        // carried gradients (split-K skinny GEMMs, B <= 64 rows)
+        const float* dout_t = dout + r * PROJ_PAD;
+        TT(skinny_gemm(dout_t, PROJ_PAD, wpg, RNN + EMB, d_dh, RNN, B, PROJ_PAD, RNN, true, st));
+        TT(skinny_gemm(dout_t, PROJ_PAD, wpg + RNN, RNN + EMB, d_ctx, EMB, B, PROJ_PAD, EMB, true, st));
         // decoder LSTM cell (input [ah_t | ctx_t], src/model.py:265-270)
+        float* dzd_t = dzd + r * 4 * RNN;
         TT(lstm_cell_bwd(gd + r * 4 * RNN, cd + r * RNN, t > 0 ? cd + (r - B) * RNN : nullptr, d_dh, d_mask_d ? d_mask_d + r * RNN : nullptr,
-                         lstm_scale, dcd, dzd + r * 4 * RNN, B, st));
-        TT(dense(dzd + r * 4 * RNN, 4 * RNN, w->dec_lstm_w_ih, tmp, RNN + EMB, B, 4 * RNN, RNN + EMB, nullptr));
-        TT(train_axpy(d_ah, RNN, tmp, RNN + EMB, B, RNN, true, st));
-        TT(train_axpy(d_ctx, EMB, tmp + RNN, RNN + EMB, B, EMB, true, st));
-        TT(dense(dzd + r * 4 * RNN, 4 * RNN, w->dec_lstm_w_hh, d_dh, RNN, B, 4 * RNN, RNN, nullptr));     // -> d dh_{t-1}
+                         lstm_scale, dcd, dzd_t, B, st));
+        TT(skinny_gemm(dzd_t, 4 * RNN, w->dec_lstm_w_ih, RNN + EMB, d_ah, RNN, B, 4 * RNN, RNN, true, st));
+        TT(skinny_gemm(dzd_t, 4 * RNN, w->dec_lstm_w_ih + RNN, RNN + EMB, d_ctx, EMB, B, 4 * RNN, EMB, true, st));
+        TT(skinny_gemm(dzd_t, 4 * RNN, w->dec_lstm_w_hh, RNN, d_dh, RNN, B, 4 * RNN, RNN, false, st));       // -> d dh_{t-1}
         // attention (src/model.py:117-148)
-        TT(dense(ah + r * RNN, RNN, wqT, pq, ATT_DIM, B, RNN, ATT_DIM, nullptr));
+        TT(skinny_gemm(ah + r * RNN, RNN, wqT, ATT_DIM, pq, ATT_DIM, B, RNN, ATT_DIM, false, st));
         TT(attention_bwd(d_align + r * T, t > 0 ? d_align + (r - B) * T : nullptr, cum + r * T, pq, pm, d_memory, d_ctx,
                          d_dalign ? d_dalign + r * T : nullptr, t < S - 1 ? P + (size_t)((t + 1) & 1) * BT : nullptr, gsum,
                          d_text_lengths, w->attn_loc_conv_w, w->attn_loc_dense_w, w->attn_v_w, w->attn_v_b, w->attn_energy_scale,
-                         d_dmemory, dpm, dpq + r * ATT_DIM, P + (size_t)(t & 1) * BT, G(grads->attn_loc_dense_w),
-                         G(grads->attn_loc_conv_w), G(grads->attn_v_w), dvs, attn, B, T, st));
-        TT(dense(dpq + r * ATT_DIM, ATT_DIM, w->attn_query_w, tmp2, RNN, B, ATT_DIM, RNN, nullptr));
-        TT(train_axpy(d_ah, RNN, tmp2, RNN, B, RNN, true, st));
+                         d_dmemory, dpm, dpq + r * ATT_DIM, P + (size_t)(t & 1) * BT, dvs, attn, B, T, st));
+        TT(skinny_gemm(dpq + r * ATT_DIM, ATT_DIM, w->attn_query_w, RNN, d_ah, RNN, B, ATT_DIM, RNN, true, st));
         // attention LSTM cell (input [p_t | ctx_{t-1}], src/model.py:256-262)
+        float* dza_t = dza + r * 4 * RNN;
         TT(lstm_cell_bwd(ga + r * 4 * RNN, ca + r * RNN, t > 0 ? ca + (r - B) * RNN : nullptr, d_ah, d_mask_a ? d_mask_a + r * RNN : nullptr,
-                         lstm_scale, dca, dza + r * 4 * RNN, B, st));
-        TT(dense(dza + r * 4 * RNN, 4 * RNN, w->attn_lstm_w_ih, tmp, PRENET + EMB, B, 4 * RNN, PRENET + EMB, nullptr));
-        TT(train_axpy(dp + r * PRENET, PRENET, tmp, PRENET + EMB, B, PRENET, false, st));
-        TT(train_axpy(d_ctx, EMB, tmp + PRENET, PRENET + EMB, B, EMB, false, st));                          // -> d ctx_{t-1}
-        TT(dense(dza + r * 4 * RNN, 4 * RNN, w->attn_lstm_w_hh, d_ah, RNN, B, 4 * RNN, RNN, nullptr));    // -> d ah_{t-1}
+                         lstm_scale, dca, dza_t, B, st));
+        TT(skinny_gemm(dza_t, 4 * RNN, w->attn_lstm_w_ih, PRENET + EMB, dp + r * PRENET, PRENET, B, 4 * RNN, PRENET, false, st));
+        TT(skinny_gemm(dza_t, 4 * RNN, w->attn_lstm_w_ih + PRENET, PRENET + EMB, d_ctx, EMB, B, 4 * RNN, EMB, false, st));   // -> d ctx_{t-1}
+        TT(skinny_gemm(dza_t, 4 * RNN, w->attn_lstm_w_hh, RNN, d_ah, RNN, B, 4 * RNN, RNN, false, st));     // -> d ah_{t-1}
     }
 
     // ---- weight gradients: reductions over all steps, computed as [in][out] and transposed into the parameter layout
@@ -436,9 +434,18 @@ B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200ta
     TT(train_colsum(dw, dout, n, PROJ_PAD, st));
     TACO_CUDA(cudaMemcpyAsync(G(grads->proj_b), dw, N_MELS * sizeof(float), cudaMemcpyDeviceToDevice, st));
     TACO_CUDA(cudaMemcpyAsync(G(grads->gate_b), dw + N_MELS, sizeof(float), cudaMemcpyDeviceToDevice, st));
-    // attention scalars
-    TACO_CUDA(cudaMemcpyAsync(G(grads->attn_v_b), dvs, sizeof(float), cudaMemcpyDeviceToDevice, st));
-    TACO_CUDA(cudaMemcpyAsync(G(grads->attn_energy_scale), dvs + 1, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // attention parameters: sum of the per-utterance accumulators
+    {
+        float* tot = dvs + (size_t)B * ATTN_PACC_F;
+        TT(train_colsum(tot, dvs, B, ATTN_PACC_F, st));
+        const size_t f = sizeof(float);
+        TACO_CUDA(cudaMemcpyAsync(G(grads->attn_loc_dense_w), tot, ATT_DIM * LOC_F * f, cudaMemcpyDeviceToDevice, st));
+        TACO_CUDA(cudaMemcpyAsync(G(grads->attn_loc_conv_w), tot + ATT_DIM * LOC_F, LOC_F * 2 * LOC_K * f, cudaMemcpyDeviceToDevice, st));
+        TACO_CUDA(cudaMemcpyAsync(G(grads->attn_v_w), tot + ATT_DIM * LOC_F + LOC_F * 2 * LOC_K, ATT_DIM * f, cudaMemcpyDeviceToDevice, st));
+        TACO_CUDA(cudaMemcpyAsync(G(grads->attn_v_b), tot + ATT_DIM * LOC_F + LOC_F * 2 * LOC_K + ATT_DIM, f, cudaMemcpyDeviceToDevice, st));
+        TACO_CUDA(cudaMemcpyAsync(G(grads->attn_energy_scale), tot + ATT_DIM * LOC_F + LOC_F * 2 * LOC_K + ATT_DIM + 1, f,
+                                  cudaMemcpyDeviceToDevice, st));
+    }
     // memory layer (128 x 512): pm = memory . W^T
     TT(wgrad_into(d_memory, EMB, EMB, dpm, ATT_DIM, ATT_DIM, BT, G(grads->attn_memory_w), EMB));
     TT(dense(dpm, ATT_DIM, w->attn_memory_w, d_dmemory, EMB, BT, ATT_DIM, EMB, d_dmemory));               // dmemory += dpm . W

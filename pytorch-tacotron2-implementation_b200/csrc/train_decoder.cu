@@ -5,6 +5,8 @@
 
 namespace b200taco {
 
+constexpr int ATTN_PACC = ATT_DIM * LOC_F + LOC_F * 2 * LOC_K + ATT_DIM + 64;     // 4096 + 1984 + 128 + pad
+
 namespace {
 
 inline int blocks_for(size_t n) { return (int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256); }
@@ -77,7 +79,7 @@ __global__ void relu_drop_fwd_kernel(float* __restrict__ y, const float* __restr
 //   out: dmemory += , dpm += , dpq [B][128], dprev_out [B][T] (gradient w.r.t. THIS step's prev input), gsum += gradient
 //        w.r.t. this step's cum input, and the parameter gradients (atomically accumulated): dWld [128][32],
 //        dWloc [32][2][31], dv [128], dvb, dscale
-//   scratch per utterance: loc [T][32], dloc [T][32], dw [T]
+//   scratch per utterance: loc [T][32], dloc [T][32], dw [T], g [T][62]
 __global__ void __launch_bounds__(256) attention_bwd_kernel(
     const float* __restrict__ w, const float* __restrict__ prev, const float* __restrict__ cum, const float* __restrict__ pq,
     const float* __restrict__ pm, const float* __restrict__ memory, const float* __restrict__ dctx,
@@ -86,19 +88,27 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(
     const float* __restrict__ Wld /* [128][32] */, const float* __restrict__ v /* [128] */, const float* __restrict__ vb_p,
     const float* __restrict__ escale_p,
     float* __restrict__ dmemory, float* __restrict__ dpm, float* __restrict__ dpq, float* __restrict__ dprev_out,
-    float* __restrict__ dWld, float* __restrict__ dWloc, float* __restrict__ dv, float* __restrict__ dvb_scale /* [2] */,
+    float* __restrict__ pacc /* [B][ATTN_PACC]: per-utterance parameter-gradient accumulators (dWld | dWloc | dv | dvb, dscale) */,
     float* __restrict__ scratch, int B, int T) {
     const int b = blockIdx.x, tid = threadIdx.x;
     const int len = lengths ? (int)lengths[b] : T;
     const float vb = vb_p[0], escale = escale_p[0];
     __shared__ float dctx_s[EMB];
     __shared__ float wloc_s[LOC_F * 2 * LOC_K];
-    __shared__ float wld_s[ATT_DIM * LOC_F];
+    __shared__ float wld_s[ATT_DIM * (LOC_F + 1)];  // row stride 33: conflict-free both along a (lf) and along f (dloc)
+    __shared__ float loc_s[8][LOC_F];
     __shared__ float v_s[ATT_DIM], pq_s[ATT_DIM], dpq_s[ATT_DIM], dv_s[ATT_DIM];
     __shared__ float red_s[256];
     __shared__ float tile_du[8][ATT_DIM];          // du of 8 positions at a time
     __shared__ float tile_de[8];
-    float* loc = scratch + (size_t)b * T * (2 * LOC_F + 1);
+    float* dWld = pacc + (size_t)b * ATTN_PACC;            // only this CTA ever touches slice b: plain read-modify-write
+    float* dWloc = dWld + ATT_DIM * LOC_F;
+    float* dv = dWloc + LOC_F * 2 * LOC_K;
+    float* dvb_scale = dv + ATT_DIM;
+    float dwld_r[ATT_DIM * LOC_F / 256];                   // this thread's 16 entries of dWld, summed over all positions
+#pragma unroll
+    for (int i = 0; i < ATT_DIM * LOC_F / 256; ++i) dwld_r[i] = 0.f;
+    float* loc = scratch + (size_t)b * T * (2 * LOC_F + 1 + 2 * LOC_K);
     float* dloc = loc + (size_t)T * LOC_F;
     float* dwv = dloc + (size_t)T * LOC_F;
     const float* wb = w + (size_t)b * T;
@@ -107,7 +117,7 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(
 
     for (int i = tid; i < EMB; i += 256) dctx_s[i] = dctx[(size_t)b * EMB + i];
     for (int i = tid; i < LOC_F * 2 * LOC_K; i += 256) wloc_s[i] = Wloc[i];
-    for (int i = tid; i < ATT_DIM * LOC_F; i += 256) wld_s[i] = Wld[i];
+    for (int i = tid; i < ATT_DIM * LOC_F; i += 256) wld_s[(i / LOC_F) * (LOC_F + 1) + (i % LOC_F)] = Wld[i];
     if (tid < ATT_DIM) { v_s[tid] = v[tid]; pq_s[tid] = pq[(size_t)b * ATT_DIM + tid]; dpq_s[tid] = 0.f; dv_s[tid] = 0.f; }
     __syncthreads();
 
@@ -119,9 +129,16 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(
         float* dmrow = dmemory + ((size_t)b * T + tau) * EMB;
         const float wt = wb[tau];
         float acc = 0.f;
-        for (int j = lane; j < EMB; j += 32) {
-            acc = fmaf(dctx_s[j], mrow[j], acc);
-            dmrow[j] += wt * dctx_s[j];
+        float mv[EMB / 32], dv_[EMB / 32];
+#pragma unroll
+        for (int q = 0; q < EMB / 32; ++q) {              // all 32 loads of the row pair in flight
+            mv[q] = mrow[lane + 32 * q];
+            dv_[q] = dmrow[lane + 32 * q];
+        }
+#pragma unroll
+        for (int q = 0; q < EMB / 32; ++q) {
+            acc = fmaf(dctx_s[lane + 32 * q], mv[q], acc);
+            dmrow[lane + 32 * q] = dv_[q] + wt * dctx_s[lane + 32 * q];
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -160,6 +177,8 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(
     float dvb_part = 0.f, dscale_part = 0.f;
     for (int t0 = 0; t0 < T; t0 += 8) {
         const int p8 = tid >> 5, lane = tid & 31, tau = t0 + p8;
+        loc_s[p8][lane] = tau < T ? loc[tau * LOC_F + lane] : 0.f;
+        __syncwarp();
         float e_raw_part = 0.f;
         float th[4], lfv[4];
         if (tau < T) {
@@ -167,7 +186,7 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(
             for (int q = 0; q < 4; ++q) {
                 const int a = lane + 32 * q;
                 float lf = 0.f;
-                for (int f = 0; f < LOC_F; ++f) lf = fmaf(wld_s[a * LOC_F + f], loc[tau * LOC_F + f], lf);
+                for (int f = 0; f < LOC_F; ++f) lf = fmaf(wld_s[a * (LOC_F + 1) + f], loc_s[p8][f], lf);
                 lfv[q] = lf;
                 th[q] = tanhf(pq_s[a] + pm[((size_t)b * T + tau) * ATT_DIM + a] + lf);
                 e_raw_part = fmaf(v_s[a], th[q], e_raw_part);
@@ -202,16 +221,17 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(
             const int f = tid & 31, pp = tid >> 5, tt = t0 + pp;
             if (tt < T) {
                 float acc = 0.f;
-                for (int a = 0; a < ATT_DIM; ++a) acc = fmaf(tile_du[pp][a], wld_s[a * LOC_F + f], acc);
+                for (int a = 0; a < ATT_DIM; ++a) acc = fmaf(tile_du[pp][a], wld_s[a * (LOC_F + 1) + f], acc);
                 dloc[tt * LOC_F + f] = acc;
             }
         }
-        for (int i = tid; i < ATT_DIM * LOC_F; i += 256) {
-            const int a = i / LOC_F, f = i % LOC_F;
+#pragma unroll
+        for (int q = 0; q < ATT_DIM * LOC_F / 256; ++q) {
+            const int i = tid + q * 256, a = i / LOC_F, f = i % LOC_F;
             float acc = 0.f;
             for (int pp = 0; pp < 8; ++pp)
-                if (t0 + pp < T) acc = fmaf(tile_du[pp][a], loc[(t0 + pp) * LOC_F + f], acc);
-            if (acc != 0.f) atomicAdd(dWld + i, acc);
+                acc = fmaf(tile_du[pp][a], loc_s[pp][f], acc);        // rows past T hold zeros in both tiles
+            dwld_r[q] += acc;
         }
         __syncthreads();
         (void)lfv;
@@ -220,16 +240,18 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(
     red_s[tid] = dvb_part;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) { if (tid < o) red_s[tid] += red_s[tid + o]; __syncthreads(); }
-    if (tid == 0) atomicAdd(dvb_scale + 0, red_s[0]);
+    if (tid == 0) dvb_scale[0] += red_s[0];
     __syncthreads();
     red_s[tid] = dscale_part;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) { if (tid < o) red_s[tid] += red_s[tid + o]; __syncthreads(); }
-    if (tid == 0) atomicAdd(dvb_scale + 1, red_s[0]);
+    if (tid == 0) dvb_scale[1] += red_s[0];
     if (tid < ATT_DIM) {
         dpq[(size_t)b * ATT_DIM + tid] = dpq_s[tid];
-        atomicAdd(dv + tid, dv_s[tid]);
+        dv[tid] += dv_s[tid];
     }
+#pragma unroll
+    for (int q = 0; q < ATT_DIM * LOC_F / 256; ++q) dWld[tid + q * 256] += dwld_r[q];
     __syncthreads();
 
     // (d) location conv backward: dWloc[f][c][k] += sum_tau dloc[tau][f] * in_c[tau + k - 15]
@@ -240,19 +262,74 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(
             const int tt = tau + k - (LOC_K - 1) / 2;
             if (tt >= 0 && tt < T) acc = fmaf(dloc[tau * LOC_F + f], c == 0 ? (pb ? pb[tt] : 0.f) : cb[tt], acc);
         }
-        atomicAdd(dWloc + i, acc);
+        dWloc[i] += acc;
     }
-    //     d in_c[tt] = sum_f sum_k dloc[tt - k + 15][f] * Wloc[f][c][k]
+    //     d in_c[tt] = sum_k g[tt - k + 15][c][k],  g[tau][c][k] = sum_f dloc[tau][f] * Wloc[f][c][k]  (two parallel passes)
+    float* gck = dwv + T;                                      // [T][62]
+    for (int i = tid; i < T * 2 * LOC_K; i += 256) {
+        const int ck = i % (2 * LOC_K), tau = i / (2 * LOC_K);
+        float acc = 0.f;
+#pragma unroll 8
+        for (int f = 0; f < LOC_F; ++f) acc = fmaf(dloc[tau * LOC_F + f], wloc_s[f * 2 * LOC_K + ck], acc);
+        gck[i] = acc;
+    }
+    __syncthreads();
     for (int i = tid; i < 2 * T; i += 256) {
         const int c = i / T, tt = i % T;
         float acc = 0.f;
         for (int k = 0; k < LOC_K; ++k) {
             const int tau = tt - k + (LOC_K - 1) / 2;
-            if (tau >= 0 && tau < T)
-                for (int f = 0; f < LOC_F; ++f) acc = fmaf(dloc[tau * LOC_F + f], wloc_s[(f * 2 + c) * LOC_K + k], acc);
+            if (tau >= 0 && tau < T) acc += gck[tau * 2 * LOC_K + c * LOC_K + k];
         }
         if (c == 0) dprev_out[(size_t)b * T + tt] = acc;
         else gsum[(size_t)b * T + tt] += acc;
+    }
+}
+
+// out[b][n] += sum_k X[b][k] * W[k][n] for b < B <= 64: one 64 x 64 output tile per (blockIdx.x, K split blockIdx.y),
+// partial sums added atomically (out must hold the values to accumulate onto, e.g. zeros)
+__global__ void __launch_bounds__(256) skinny_gemm_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W,
+                                                          int ldw, float* __restrict__ out, int ldo, int B, int K, int N,
+                                                          int k_per) {
+    __shared__ __align__(16) float Xs[16][64 + 4];
+    __shared__ __align__(16) float Ws[16][64];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int n0 = blockIdx.x * 64, k0 = blockIdx.y * k_per, k1 = min(K, k0 + k_per);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int xm = tid >> 2, xq = tid & 3;              // X loader: row xm, k 4*xq..
+    const int wk = tid >> 4, wq = tid & 15;             // W loader: k row wk, cols 4*wq..
+    for (int kb = k0; kb < k1; kb += 16) {
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), wv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (xm < B) xv = *reinterpret_cast<const float4*>(X + (size_t)xm * ldx + kb + 4 * xq);
+        if (n0 + 4 * wq < N) wv = __ldg(reinterpret_cast<const float4*>(W + (size_t)(kb + wk) * ldw + n0 + 4 * wq));
+        Xs[4 * xq + 0][xm] = xv.x; Xs[4 * xq + 1][xm] = xv.y; Xs[4 * xq + 2][xm] = xv.z; Xs[4 * xq + 3][xm] = xv.w;
+        *reinterpret_cast<float4*>(&Ws[wk][4 * wq]) = wv;
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(&Xs[kk][4 * ty]);
+            const float4 b = *reinterpret_cast<const float4*>(&Ws[kk][4 * tx]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int b = 4 * ty + i;
+        if (b >= B) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + 4 * tx + j;
+            if (n < N) atomicAdd(out + (size_t)b * ldo + n, acc[i][j]);
+        }
     }
 }
 
@@ -286,6 +363,21 @@ __global__ void assemble_wpg_kernel(const float* __restrict__ wp, const float* _
 }
 
 }  // namespace
+
+// out (+)= X . W ; X [B][K] (ldx), W [K][N] (ldw), out [B][N] (ldo), B <= 64, K % 16 == 0, N % 4 == 0
+int skinny_gemm(const float* X, int ldx, const float* W, int ldw, float* out, int ldo, int B, int K, int N, bool accumulate,
+                cudaStream_t st) {
+    TACO_REQUIRE(B <= 64 && K % 16 == 0 && N % 4 == 0 && ldx % 4 == 0 && ldw % 4 == 0, B200TACO_ERR_INVALID,
+                 "skinny_gemm: unsupported shape B %d K %d N %d", B, K, N);
+    if (!accumulate) TACO_CUDA(cudaMemset2DAsync(out, (size_t)ldo * sizeof(float), 0, (size_t)N * sizeof(float), B, st));
+    const int ntiles = (N + 63) / 64;
+    int ks = 1;
+    while (ntiles * ks < 128 && K / (ks * 2) >= 64) ks *= 2;
+    const int k_per = ((K + ks - 1) / ks + 15) / 16 * 16;
+    skinny_gemm_kernel<<<dim3(ntiles, (K + k_per - 1) / k_per), 256, 0, st>>>(X, ldx, W, ldw, out, ldo, B, K, N, k_per);
+    TACO_LAUNCHED();
+    return B200TACO_OK;
+}
 
 int transpose_block(float* dst, int ldd, const float* src, int lds, int R, int C, cudaStream_t st) {
     transpose_block_kernel<<<blocks_for((size_t)R * C), 256, 0, st>>>(dst, ldd, src, lds, R, C);
@@ -329,14 +421,13 @@ int relu_drop_fwd(float* y, const float* mask, float scale, size_t n, cudaStream
     TACO_LAUNCHED();
     return B200TACO_OK;
 }
-size_t attention_bwd_scratch_floats(int B, int T) { return (size_t)B * T * (2 * LOC_F + 1); }
+size_t attention_bwd_scratch_floats(int B, int T) { return (size_t)B * T * (2 * LOC_F + 1 + 2 * LOC_K); }
 int attention_bwd(const float* w, const float* prev, const float* cum, const float* pq, const float* pm, const float* memory,
                   const float* dctx, const float* dw_ext, const float* dprev_next, float* gsum, const int64_t* lengths,
                   const float* Wloc, const float* Wld, const float* v, const float* vb, const float* escale, float* dmemory, float* dpm,
-                  float* dpq, float* dprev_out, float* dWld, float* dWloc, float* dv, float* dvb_scale, float* scratch, int B,
-                  int T, cudaStream_t st) {
+                  float* dpq, float* dprev_out, float* pacc, float* scratch, int B, int T, cudaStream_t st) {
     attention_bwd_kernel<<<B, 256, 0, st>>>(w, prev, cum, pq, pm, memory, dctx, dw_ext, dprev_next, gsum, lengths, Wloc, Wld, v, vb,
-                                            escale, dmemory, dpm, dpq, dprev_out, dWld, dWloc, dv, dvb_scale, scratch, B, T);
+                                            escale, dmemory, dpm, dpq, dprev_out, pacc, scratch, B, T);
     TACO_LAUNCHED();
     return B200TACO_OK;
 }
