@@ -302,13 +302,20 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(const float* __restric
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const int xm = tid >> 2, xq = tid & 3;              // X loader: row xm, k 4*xq..
     const int wk = tid >> 4, wq = tid & 15;             // W loader: k row wk, cols 4*wq..
-    for (int kb = k0; kb < k1; kb += 16) {
-        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), wv = make_float4(0.f, 0.f, 0.f, 0.f);
+    // register double buffering: the loads of tile kb+16 are in flight while tile kb is multiplied
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), wv = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch = [&](int kb) {
+        xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        wv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (xm < B) xv = *reinterpret_cast<const float4*>(X + (size_t)xm * ldx + kb + 4 * xq);
         if (n0 + 4 * wq < N) wv = __ldg(reinterpret_cast<const float4*>(W + (size_t)(kb + wk) * ldw + n0 + 4 * wq));
+    };
+    if (k0 < k1) fetch(k0);
+    for (int kb = k0; kb < k1; kb += 16) {
         Xs[4 * xq + 0][xm] = xv.x; Xs[4 * xq + 1][xm] = xv.y; Xs[4 * xq + 2][xm] = xv.z; Xs[4 * xq + 3][xm] = xv.w;
         *reinterpret_cast<float4*>(&Ws[wk][4 * wq]) = wv;
         __syncthreads();
+        if (kb + 16 < k1) fetch(kb + 16);
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk) {
             const float4 a = *reinterpret_cast<const float4*>(&Xs[kk][4 * ty]);
