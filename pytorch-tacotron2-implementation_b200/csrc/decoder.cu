@@ -34,7 +34,6 @@ constexpr int NT = NTC + 32;                // + producer warp
 // Producer lanes: a thread's bulk copies complete one at a time (~0.4 us each whatever the size, measured:
 // profiles/r1_stream_probe.txt), so every pipeline stage has its own issuing lane (lane == stage) and the
 // copies of different stages proceed in parallel; one lane per stage also keeps each stage's uses in order.
-constexpr int MMA_WARP = 4;                 // consumer warp whose lane 0 issues tcgen05.mma (tensor-core path)
 constexpr int TC_CK = 64;                   // k per pipeline chunk on the tensor-core path
 constexpr int TC_KG = TC_CK / 8;
 constexpr int GS = 4;                       // tensor-core path: CTAs per split-K group
@@ -512,120 +511,6 @@ struct Producer {
         }
     }
 };
-
-// Tensor-core gate contraction, split-K over a group of GS=4 CTAs (cta = 4*group + member):
-// the group owns 128 gate rows (32 hidden units); member r multiplies them with its quarter of the K range:
-//   D_r[2*BP (hi rows | lo rows) x 128] += A[:, K_r] . W_group[:, K_r]^T     (tcgen05.mma M=128, N=128, K=16)
-// One MMA costs ~128 cycles whatever N (measured), so N=128 with a quarter of the K steps is 4x cheaper than
-// N=32 over the whole K, and each CTA streams only a quarter of the activations.  The four partial sums meet
-// through L2: member r sends the 32-row slice of member r' to zpart[r'][r], a group counter (release/acquire)
-// separates send and receive, and every member ends up with z[row][b] of its own 8 hidden units.
-#ifdef TACO_PROFILE_FINE
-__device__ unsigned long long g_dbg[4];
-#endif
-
-template <int BP, typename WT>
-__device__ __forceinline__ void gemm_tc(const Pipe& pipe, uint32_t& g, int nchunks, uint32_t tmem, uint64_t* acc_bar,
-                                        uint32_t& acc_phase, float* red, float* z, float* zpart, uint32_t* gcnt,
-                                        uint32_t& gepoch, int cta, int warp, int lane, int tid) {
-    using SM = Smem<BP, WT, true>;
-    constexpr int STAGES = SM::NSTAGES;
-    if (warp == MMA_WARP) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma::instr_desc_bf16_f32(128, GN);
-            uint32_t gg = g;
-#ifdef TACO_PROFILE_FINE
-            unsigned long long tw = 0, tl0 = global_timer_ns();
-#endif
-            for (int ch = 0; ch < nchunks; ++ch, ++gg) {
-                const uint32_t stage = gg % STAGES, parity = (gg / STAGES) & 1u;
-#ifdef TACO_PROFILE_FINE
-                const unsigned long long tw0 = global_timer_ns();
-#endif
-                mbar_wait(&pipe.full[stage], parity);
-#ifdef TACO_PROFILE_FINE
-                tw += global_timer_ns() - tw0;
-#endif
-                umma::fence_after_sync();
-                const uint32_t w_addr = smem_u32(pipe.stages + stage * SM::STAGE_BYTES);
-                const uint32_t a_addr = w_addr + SM::W_BYTES;
-#pragma unroll
-                for (int ks = 0; ks < TC_CK / 16; ++ks)
-                    umma::mma_bf16(tmem, umma::smem_desc(a_addr + ks * 256, 128, TC_KG * 128),
-                                   umma::smem_desc(w_addr + ks * 256, 128, TC_KG * 128), idesc, ch > 0 || ks > 0);
-                umma::commit(&pipe.empty[stage]);       // stage is free once these MMAs have read it
-            }
-            umma::commit(acc_bar);
-#ifdef TACO_PROFILE_FINE
-            if (blockIdx.x == 0) {
-                atomicAdd(g_dbg + 0, tw);
-                atomicAdd(g_dbg + 1, global_timer_ns() - tl0);
-            }
-#endif
-        }
-        __syncwarp();
-    }
-    g += nchunks;
-    const int member = cta % GS, group = cta / GS;
-    constexpr int EW = 2 * BP / 32;                     // warps whose TMEM lane quarter holds rows
-    constexpr int PB = BP <= 32 ? 4 : 2;                // 32-column blocks staged in `red` per pass
-    constexpr int RS = PB * 32 + 1;                     // red row stride
-    static_assert(2 * BP * RS * 4 <= Smem<BP, WT, true>::RED_BYTES, "epilogue staging must fit the red region");
-    if (warp < EW) {
-        mbar_wait(acc_bar, acc_phase);
-        umma::fence_after_sync();
-    }
-    acc_phase ^= 1u;
-#pragma unroll 1
-    for (int pass = 0; pass < GS / PB; ++pass) {
-        if (warp < EW) {
-            const int m = warp * 32 + lane;
-#pragma unroll
-            for (int cbl = 0; cbl < PB; ++cbl) {
-                float v[32];
-                umma::tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + (pass * PB + cbl) * 32, v);
-#pragma unroll
-                for (int c = 0; c < 32; ++c) red[m * RS + cbl * 32 + c] = v[c];
-            }
-            umma::fence_before_sync();
-        }
-        consumer_sync();
-        // hi + lo rows; columns [32*dst, 32*dst+32) are the gate rows of member dst
-        for (int i = tid; i < PB * ROWS_PER_CTA * BP; i += NTC) {
-            const int b = i % BP, c = (i / BP) % ROWS_PER_CTA, cbl = i / (BP * ROWS_PER_CTA);
-            const int dst = pass * PB + cbl;
-            const float v = red[b * RS + cbl * 32 + c] + red[(BP + b) * RS + cbl * 32 + c];
-            if (dst == member) z[c * BP + b] = v;       // own slice stays in shared memory
-            else zpart[(((size_t)(group * GS + dst)) * GS + member) * (ROWS_PER_CTA * BP) + c * BP + b] = v;
-        }
-        consumer_sync();
-    }
-    // group rendezvous: all four partial slices are in L2
-    gepoch += 1;
-    if (tid == 0) {
-        red_release_add_u32(gcnt + group, 1u);
-        const uint32_t target = gepoch * GS;
-        if (ld_acquire_u32(gcnt + group) < target) {
-            const uint64_t t0 = global_timer_ns();
-            while (ld_acquire_u32(gcnt + group) < target) {
-                if (global_timer_ns() - t0 > SPIN_TIMEOUT_NS) spin_fail();
-            }
-        }
-    }
-    consumer_sync();
-    for (int i = tid; i < ROWS_PER_CTA * BP; i += NTC) {
-        float acc = 0.f;
-#pragma unroll
-        for (int src = 0; src < GS; ++src) {            // fixed order: bitwise reproducible
-            const float v = src == member ? z[i] : __ldcg(zpart + ((size_t)cta * GS + src) * (ROWS_PER_CTA * BP) + i);
-            acc += v;
-        }
-        red[i] = acc;
-    }
-    consumer_sync();
-    for (int i = tid; i < ROWS_PER_CTA * BP; i += NTC) z[i] = red[i];
-    consumer_sync();
-}
 
 // ---------------------------------------------------------------------------------------
 // P2: location-sensitive attention (src/model.py:117-148), consumer warps of every CTA.  One work item per
@@ -1126,10 +1011,7 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
         mbar_init(acc_bar, 1);
         fence_mbar_init();
     }
-    if constexpr (TC) {
-        if (is_gemm && warp == 0) umma::tmem_alloc(tmem_slot, GN);      // 128 fp32 columns x 128 lanes
-        umma::fence_before_sync();
-    }
+    static_assert(!TC, "the tensor-core path is decoder_tc_kernel");
     for (int i = tid; i < UNITS_PER_CTA * BP; i += NT) { ca_s[i] = 0.f; cd_s[i] = 0.f; h_s[i] = 0.f; }
     if (is_gemm) {
         for (int i = tid; i < 32; i += NT) {
@@ -1146,11 +1028,6 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
     for (int i = tid; i < 130; i += NT) v_s[i] = p.attn_v[i];
     __syncthreads();
 
-    uint32_t tmem = 0, acc_phase = 0, gepoch = 0;
-    if constexpr (TC) {
-        umma::fence_after_sync();
-        tmem = *tmem_slot;
-    }
     // per-CTA weight bytes are the same on both paths: 32 rows x K, or 128 rows x K/4 (split-K group)
     const WT* w_attn = reinterpret_cast<const WT*>(TC ? p.w_attn_tc : p.w_attn) + (size_t)cta * K_ATTN * ROWS_PER_CTA;
     const WT* w_dec = reinterpret_cast<const WT*>(TC ? p.w_dec_tc : p.w_dec) + (size_t)cta * K_DEC * ROWS_PER_CTA;
@@ -1215,10 +1092,7 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
                 PR::prefetch(pipe, g, NCH3, PRE3, rot3, lane, w_dec);          // across P2
             } else {
                 FT_RESET();
-                if constexpr (TC) {
-                    gemm_tc<BP, WT>(pipe, g, NCH1, tmem, acc_bar, acc_phase, red, z_s, p.zpart, p.ctrl + CTRL_GCNT, gepoch,
-                                    cta, warp, lane, tid);
-                } else {
+                {
                     float acc[8][Tile<BP>::BPL];
                     gemm_consume<BP, WT>(pipe, g, NCH1, warp, lane, acc);
                     gemm_reduce<BP>(acc, red, z_s, warp, lane, tid);
@@ -1260,10 +1134,7 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
             } else {
                 for (int i = tid; i < 4 * B; i += NTC) cx_s[(i & 3) * BP + (i >> 2)] = __ldcg(p.ctx_bj + (size_t)(i >> 2) * EMB + 4 * cta + (i & 3));
                 FT_RESET();
-                if constexpr (TC) {
-                    gemm_tc<BP, WT>(pipe, g, NCH3, tmem, acc_bar, acc_phase, red, z_s, p.zpart, p.ctrl + CTRL_GCNT, gepoch,
-                                    cta, warp, lane, tid);
-                } else {
+                {
                     float acc[8][Tile<BP>::BPL];
                     gemm_consume<BP, WT>(pipe, g, NCH3, warp, lane, acc);
                     gemm_reduce<BP>(acc, red, z_s, warp, lane, tid);
@@ -1321,11 +1192,6 @@ __global__ void __launch_bounds__(NT, 1) decoder_kernel(const KParams p) {
         }
     }
     (void)stopped;
-    if constexpr (TC) {
-        umma::fence_before_sync();
-        __syncthreads();
-        if (is_gemm && warp == 0) umma::tmem_dealloc(tmem, GN);
-    }
 }
 
 template <int BP, typename WT, bool TC>
