@@ -9,10 +9,11 @@ early exit (planted stop counter, SURVEY.md 8c/8d, stops land in ~[300, 900] fra
 encoder -> persistent decoder kernel -> postnet.  Frames counted = sum of the utterances'
 own decoded lengths.
 
-  value         frames/s with the phoneme ids already resident in HBM (device timed, CUDA events)
-  e2e           same metric through the public API (Tacotron2.inference_per_utterance) with HOST
-                pinned ids, host->device copy and device->host read of the results inside the
-                timed region
+  value         frames/s with the phoneme ids already resident in HBM (device timed, CUDA events); the K
+                batches go through the pipelined path (Tacotron2.inference_batches): the encoder of the
+                next batch and the postnet of the previous one overlap the persistent decoder kernel
+  e2e           same metric through the same public API with HOST pinned ids, host->device copy and
+                device->host read of the results (pinned) inside the timed region
   roofline      persistent decoder kernel: algorithmic bytes per decode step x
                 decode steps per launch / CUDA-event duration, against the measured HBM copy
                 bandwidth of MEASURED_PEAKS.json (the per-step working set is L2 resident, so the
@@ -153,68 +154,63 @@ def run_b200(args, rank, world, local_rank):
         ev[4].record()
         return lengths, S, ev, post
 
-    e2e_host = {}
-
-    def step_e2e():
+    def flush_l2():
         flush.zero_()
-        ids = ids_host.to(dev, non_blocking=True)
+
+    def run_pipelined(n, host):
+        """n batches through the pipelined public path (Tacotron2.inference_batches -> Engine.pipeline_infer): encoder /
+        postnet of neighbouring batches overlap the persistent decoder on separate streams.  Results of every batch are
+        complete inside this call.  Returns (frames, decoder event pairs, decoded steps per batch, last result)."""
+        timings, lens, Ss, last = [], [], [], None
+        feed = [ids_host if host else ids_dev] * n
         with contextlib.redirect_stdout(io.StringIO()):
-            post, coarse, gate, aligns, lengths = model.inference_per_utterance(ids)
-        # device -> host read of the results into pinned buffers (reused across steps)
-        if e2e_host.get("post") is None or e2e_host["post"].shape != post.shape:
-            e2e_host["post"] = torch.empty(post.shape, dtype=post.dtype, pin_memory=True)
-            e2e_host["lengths"] = torch.empty(lengths.shape, dtype=lengths.dtype, pin_memory=True)
-        e2e_host["post"].copy_(post, non_blocking=True)
-        e2e_host["lengths"].copy_(lengths, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        return int(e2e_host["lengths"].sum()), e2e_host["post"]
+            for res in eng.pipeline_infer(feed, CAP, 0.5, STOP_PER_UTTERANCE, to_host=host, pre_hook=flush_l2, timings=timings):
+                lens.append(res[7] if host else res[4])
+                Ss.append(res[5])
+                last = res
+        frames_ = int(torch.stack(lens).sum().item())
+        return frames_, timings, Ss, last
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---------------- value (device resident) ----------------
+    # ---------------- value (device resident ids, K batches pipelined) ----------------
     # the sampler starts before the warm-up: nvidia-smi's own start-up stalls CUDA calls of this process for
     # ~20 ms (measured), which must not land inside the timed region; its samples cover warm-up + timed steps
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for _ in range(args.warmup):
-        step_resident()
+    run_pipelined(args.warmup, False)
     barrier()
     eng.launch_count(reset=True)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    frames, dec_events, dec_steps, all_lengths = 0, [], 0, []
-    for _ in range(args.steps):
-        lengths, S, ev, _ = step_resident()
-        all_lengths.append(lengths)             # summed after the timed region (no extra host sync per step)
-        dec_events.append(ev)
-        dec_steps += S + 1                      # + the discarded first decode step (F6)
+    frames, dec_events, Ss, _ = run_pipelined(args.steps, False)
     t1.record()
     barrier()
-    frames = int(torch.stack(all_lengths).sum().item())
     launches = eng.launch_count()
     clocks = sampler.stop()
     ms = t0.elapsed_time(t1)
-    dec_ms = sum(ev[2].elapsed_time(ev[3]) for ev in dec_events)
-    stages_ms = {n: sum(ev[i].elapsed_time(ev[i + 1]) for ev in dec_events) / args.steps
+    dec_ms = sum(a.elapsed_time(b) for a, b in dec_events)
+    dec_steps = sum(S + 1 for S in Ss)                     # + the discarded first decode step (F6)
+
+    # ---------------- device time of the stages of ONE batch run one after the other (informational) ----------------
+    stage_runs = [step_resident() for _ in range(3)]
+    torch.cuda.synchronize(dev)
+    stages_ms = {n: sum(r[2][i].elapsed_time(r[2][i + 1]) for r in stage_runs) / len(stage_runs)
                  for i, n in enumerate(("l2_flush", "encoder", "decoder", "postnet"))}
 
-    # ---------------- e2e (host buffers, public API) ----------------
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
+    # ---------------- e2e (pinned host ids in, pinned host results out, public API) ----------------
+    run_pipelined(max(1, args.warmup // 2), True)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    e2e_frames, d2h = 0, 0
-    for _ in range(args.steps):
-        n, post_h = step_e2e()
-        e2e_frames += n
-        d2h = post_h.numel() * 4 + B * 4
+    e2e_frames, _, _, last = run_pipelined(args.steps, True)
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+    d2h = last[6].numel() * 4 + B * 4
 
     agg = torch.tensor([ms, e2e_ms, float(frames), float(e2e_frames), float(launches)], device=dev, dtype=torch.float64)
     if dist is not None:
@@ -235,7 +231,8 @@ def run_b200(args, rank, world, local_rank):
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "text_len": T, "cap": CAP,
                        "weights": "seed 1234 default init + planted stop counter (rate 8e-4, jitter 6e-3)",
                        "frames_counted": "sum of per-utterance decoded lengths",
-                       "l2": "flushed between steps (256 MiB device memset)", "sharding": f"dp{world}: one batch per rank per step, same synthetic batch on every rank, no collective"},
+                       "l2": "flushed before every decoder launch (256 MiB device memset on the decoder stream)",
+                       "pipeline": "K batches back to back: encoder(i+1) and postnet(i-1) overlap decoder(i) on separate CUDA streams", "sharding": f"dp{world}: one batch per rank per step, same synthetic batch on every rank, no collective"},
             "e2e": {"value": e2e_frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": ids_host.numel() * 8,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),

@@ -83,7 +83,7 @@ class Engine:
         self.dense_path = dense_path
         check(self._lib.b200taco_set_dense_path(self._h, {"auto": 0, "simt": 1, "tc": 2}[dense_path]), "b200taco_set_dense_path")
         self._packed_sig = None
-        self._ws = None
+        self._ws = {}            # one workspace per stage: stages of different batches overlap on different streams
         self.max_batch = self._lib.b200taco_max_batch()
         self.max_text_len = self._lib.b200taco_max_text_len()
 
@@ -99,11 +99,13 @@ class Engine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _workspace(self, B, T, S):
+    def _workspace(self, B, T, S, stage="decoder"):
         need = int(self._lib.b200taco_workspace_bytes(self._h, B, T, S))
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        return C.c_void_p(self._ws.data_ptr()), C.c_size_t(self._ws.numel())
+        ws = self._ws.get(stage)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._ws[stage] = ws
+        return C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel())
 
     def ensure_packed(self, tensors: dict) -> None:
         """(Re)pack when any parameter/buffer was replaced or modified in place."""
@@ -134,7 +136,7 @@ class Engine:
         B, T = ids.shape
         ids = ids.to(device=self.device, dtype=torch.int64).contiguous()
         memory = torch.empty(B, T, config.encoder_embedding_dim, dtype=torch.float32, device=self.device)
-        ws, wsz = self._workspace(B, T, 1)
+        ws, wsz = self._workspace(B, T, 1, "encoder")
         with torch.cuda.device(self.device):
             check(self._lib.b200taco_encoder_fwd(self._h, ids.data_ptr(), B, T, memory.data_ptr(),
                                                  ws, wsz, self._stream()), "b200taco_encoder_fwd")
@@ -187,11 +189,106 @@ class Engine:
         mel_coarse = mel_coarse.contiguous()
         B, S, _ = mel_coarse.shape
         out = torch.empty_like(mel_coarse)
-        ws, wsz = self._workspace(B, 1, S)
+        ws, wsz = self._workspace(B, 1, S, "postnet")
         with torch.cuda.device(self.device):
             check(self._lib.b200taco_postnet_fwd(self._h, mel_coarse.data_ptr(), B, S, out.data_ptr(),
                                                  ws, wsz, self._stream()), "b200taco_postnet_fwd")
         return out
+
+    # ------------------------------------------------------------------ pipelined corpus synthesis
+    def pipeline_infer(self, batches, max_steps: int, gate_threshold: float, stop_mode: int, to_host: bool = False,
+                       pre_hook=None, timings=None):
+        """Free-running inference of a sequence of id batches with the stages of consecutive batches overlapped.
+
+        The persistent decoder kernel occupies 132 of the 148 SMs for tens of milliseconds; the dense kernels of the
+        NEXT batch's encoder and of the PREVIOUS batch's postnet run meanwhile on the other SMs, on their own streams
+        (the cluster BiLSTM needs whole GPCs and runs between two decoder launches).  ``batches``: iterable of (B,T)
+        int64 id tensors, on the device or in (pinned) host memory.  Yields, in order, per batch
+        ``(post, coarse, gate, align, lengths, S)``; with ``to_host`` the mel tensors and lengths are copied into pinned
+        host buffers on the postnet stream.  Every result is complete when it is yielded.  ``pre_hook()`` runs on the
+        decoder stream before each decoder launch (benchmarks flush L2 there); ``timings`` collects an (start, end) CUDA event
+        pair around every decoder launch on the decoder stream.
+        """
+        dev = self.device
+        cur = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_streams"):
+            self._streams = tuple(torch.cuda.Stream(dev) for _ in range(3))
+        sE, sD, sP = self._streams
+        for s_ in (sE, sD, sP):
+            s_.wait_stream(cur)
+        it = iter(batches)
+
+        def prep(ids):
+            with torch.cuda.stream(sE):
+                ids_dev = ids.to(device=dev, dtype=torch.int64, non_blocking=True)
+                mem = self.encoder(ids_dev)
+                ev = torch.cuda.Event()
+                ev.record(sE)
+            return mem, ev
+
+        def launch_decoder(mem, ev_enc):
+            with torch.cuda.stream(sD):
+                sD.wait_event(ev_enc)
+                mem.record_stream(sD)
+                if pre_hook is not None:
+                    pre_hook()                        # on the decoder stream: never while a decoder kernel is running
+                if timings is not None:
+                    t0 = torch.cuda.Event(enable_timing=True)
+                    t0.record(sD)
+                out = self.decoder_infer(mem, max_steps, gate_threshold, stop_mode, sync=False)
+                if timings is not None:
+                    t1 = torch.cuda.Event(enable_timing=True)
+                    t1.record(sD)
+                    timings.append((t0, t1))
+                steps_h = torch.empty(1, dtype=torch.int32, pin_memory=True)
+                steps_h.copy_(out[4], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(sD)
+            return out, steps_h, ev
+
+        def finish(out, steps_h, ev_dec):
+            mel, gate, align, lengths, _ = out
+            ev_dec.synchronize()                      # host learns S; the next decoder launch is already queued
+            S = int(steps_h.item())
+            with torch.cuda.stream(sP):
+                sP.wait_event(ev_dec)
+                for t in (mel, gate, align, lengths):
+                    t.record_stream(sP)
+                coarse = mel[:, :S].contiguous()
+                post = self.postnet(coarse)
+                res = (post, coarse, gate[:, :S], align[:S], lengths, S)
+                if to_host:
+                    post_h = torch.empty(post.shape, dtype=post.dtype, pin_memory=True)
+                    len_h = torch.empty(lengths.shape, dtype=lengths.dtype, pin_memory=True)
+                    post_h.copy_(post, non_blocking=True)
+                    len_h.copy_(lengths, non_blocking=True)
+                    res = res + (post_h, len_h)
+                ev = torch.cuda.Event()
+                ev.record(sP)
+            return res, ev
+
+        try:
+            first = next(it)
+        except StopIteration:
+            return
+        mem, ev_enc = prep(first)
+        pending = launch_decoder(mem, ev_enc)
+        done = None
+        for ids in it:
+            mem, ev_enc = prep(ids)                   # encoder(i+1) overlaps decoder(i)
+            nxt = launch_decoder(mem, ev_enc)         # queued behind decoder(i) on the decoder stream
+            res, ev_post = finish(*pending)           # postnet(i) overlaps decoder(i+1)
+            if done is not None:
+                done[1].synchronize()
+                yield done[0]
+            done, pending = (res, ev_post), nxt
+        res, ev_post = finish(*pending)
+        if done is not None:
+            done[1].synchronize()
+            yield done[0]
+        ev_post.synchronize()
+        cur.wait_stream(sP)
+        yield res
 
     # ------------------------------------------------------------------ measurement aids
     def measure_l2_read_gbps(self, nbytes: int = 36 << 20, iters: int = 50) -> float:

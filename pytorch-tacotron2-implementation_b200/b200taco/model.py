@@ -264,6 +264,21 @@ class Tacotron2(nn.Module):
         align = torch.cat([fit(p[2], 0) for p in parts], dim=1)
         return coarse, gate, align, lengths, S
 
+    @torch.no_grad()
+    def inference_batches(self, batches, max_len_cap=None, gate_threshold=None, per_utterance=True, to_host=False):
+        """Corpus synthesis: free-running inference over an iterable of (B,T) id batches (device or pinned host
+        tensors), with the encoder / decoder / postnet of consecutive batches overlapped on separate CUDA streams
+        (``Engine.pipeline_infer``).  Yields per batch ``(mel_postnet, mel_coarse, gate_logits, alignments (S,B,T),
+        lengths, S)`` (+ pinned host copies of mel_postnet and lengths with ``to_host``).  Each batch is decoded
+        exactly as ``inference_per_utterance`` / ``inference`` would decode it alone."""
+        self._check_mode("Tacotron2.inference_batches")
+        thr = gate_threshold if gate_threshold is not None else self.decoder.gate_threshold
+        cap = self.decoder.max_decoder_steps
+        if max_len_cap:
+            cap = min(cap, int(max_len_cap))
+        eng = self._get_engine()
+        yield from eng.pipeline_infer(batches, cap, thr, STOP_PER_UTTERANCE if per_utterance else STOP_BATCH_WIDE, to_host)
+
     def _infer(self, text_inputs, max_len_cap, gate_threshold, stop_mode):
         self._check_mode("Tacotron2.inference")
         thr = gate_threshold if gate_threshold is not None else self.decoder.gate_threshold

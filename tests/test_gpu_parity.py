@@ -260,6 +260,23 @@ def test_batches_beyond_one_launch_are_chunked():
     assert util.maxdiff(util.stack(out[3]).cpu(), util.stack(ref[3])) <= TOL_ALIGN
 
 
+def test_pipelined_batches_equal_one_by_one():
+    """inference_batches overlaps the stages of consecutive batches on three streams; every batch must come out
+    bit-identical to decoding it alone (different shapes per batch, host and device inputs)."""
+    sd = util.weights("planted", True, ctx_center=O.encoder(util.weights("stress", True), synth.phoneme_ids(2, 30, seed=50)).mean((0, 1)))
+    m = gpu_model(sd)
+    batches = [synth.phoneme_ids(b, t, seed=60 + i) for i, (b, t) in enumerate([(5, 30), (32, 41), (3, 30), (8, 77), (1, 12)])]
+    solo = [m.inference_per_utterance(x.cuda()) for x in batches]
+    feed = [x.pin_memory() if i % 2 else x.cuda() for i, x in enumerate(batches)]
+    outs = list(m.inference_batches(feed, to_host=True))
+    assert len(outs) == len(batches)
+    for (post, coarse, gate, aligns, lengths), o in zip(solo, outs):
+        assert o[5] == coarse.shape[1] and torch.equal(o[4].cpu(), lengths.cpu())
+        assert torch.equal(o[0], post) and torch.equal(o[1], coarse) and torch.equal(o[2], gate)
+        assert torch.equal(o[3], torch.stack(aligns))
+        assert torch.equal(o[6], post.cpu()) and torch.equal(o[7], lengths.cpu())
+
+
 def test_long_horizon_default_init_1000_steps():
     """Default init never fires (F11): 1000 frames, error must not grow with the horizon."""
     ids = synth.phoneme_ids(2, 150, seed=1)
