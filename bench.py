@@ -10,8 +10,12 @@ encoder -> persistent decoder kernel -> postnet.  Frames counted = sum of the ut
 own decoded lengths.
 
   value         frames/s with the phoneme ids already resident in HBM (device timed, CUDA events); the K
-                batches go through the pipelined path (Tacotron2.inference_batches): the encoder of the
-                next batch and the postnet of the previous one overlap the persistent decoder kernel
+                batches go through the public corpus path (Tacotron2.inference_batches(continuous=True) ->
+                Engine.stream_infer): ONE persistent decoder launch keeps 32 rows live and refills a row from
+                the following batches as soon as its utterance stops (continuous batching; every utterance
+                is bit-identical to its batch-by-batch decode, tests/test_gpu_parity.py)
+  batch_by_batch  the same K batches with one decoder launch per batch (rows idle behind early stops),
+                encoder(i+1) / postnet(i-1) overlapping decoder(i) on separate streams
   e2e           same metric through the same public API with HOST pinned ids, host->device copy and
                 device->host read of the results (pinned) inside the timed region
   roofline      persistent decoder kernel: algorithmic bytes per decode step x
@@ -157,19 +161,25 @@ def run_b200(args, rank, world, local_rank):
     def flush_l2():
         flush.zero_()
 
-    def run_pipelined(n, host):
-        """n batches through the pipelined public path (Tacotron2.inference_batches -> Engine.pipeline_infer): encoder /
-        postnet of neighbouring batches overlap the persistent decoder on separate streams.  Results of every batch are
-        complete inside this call.  Returns (frames, decoder event pairs, decoded steps per batch, last result)."""
+    def run_pipelined(n, host, continuous=True):
+        """n batches through the public corpus path (Tacotron2.inference_batches -> Engine.stream_infer: continuous
+        batching, 32 live rows refilled as utterances stop; continuous=False -> Engine.pipeline_infer: one decoder launch
+        per batch).  Results of every batch are complete inside this call.
+        Returns (frames, decoder event pairs, decode steps executed, last result)."""
         timings, lens, Ss, last = [], [], [], None
         feed = [ids_host if host else ids_dev] * n
         with contextlib.redirect_stdout(io.StringIO()):
-            for res in eng.pipeline_infer(feed, CAP, 0.5, STOP_PER_UTTERANCE, to_host=host, pre_hook=flush_l2, timings=timings):
+            if continuous:
+                it = eng.stream_infer(feed, CAP, 0.5, to_host=host, pre_hook=flush_l2, timings=timings)
+            else:
+                it = eng.pipeline_infer(feed, CAP, 0.5, STOP_PER_UTTERANCE, to_host=host, pre_hook=flush_l2, timings=timings)
+            for res in it:
                 lens.append(res[7] if host else res[4])
                 Ss.append(res[5])
                 last = res
         frames_ = int(torch.stack(lens).sum().item())
-        return frames_, timings, Ss, last
+        steps_ = eng.last_stream_steps if continuous else sum(S + 1 for S in Ss)   # + the discarded first step (F6)
+        return frames_, timings, steps_, last
 
     def barrier():
         if dist is not None:
@@ -186,14 +196,24 @@ def run_b200(args, rank, world, local_rank):
     eng.launch_count(reset=True)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    frames, dec_events, Ss, _ = run_pipelined(args.steps, False)
+    frames, dec_events, dec_steps, _ = run_pipelined(args.steps, False)
     t1.record()
     barrier()
     launches = eng.launch_count()
     clocks = sampler.stop()
     ms = t0.elapsed_time(t1)
     dec_ms = sum(a.elapsed_time(b) for a, b in dec_events)
-    dec_steps = sum(S + 1 for S in Ss)                     # + the discarded first decode step (F6)
+
+    # ---------------- the same K batches, one decoder launch per batch (informational) ----------------
+    run_pipelined(1, False, continuous=False)
+    barrier()
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record()
+    bb_frames, bb_events, bb_steps, _ = run_pipelined(args.steps, False, continuous=False)
+    b1.record()
+    barrier()
+    bb_ms = b0.elapsed_time(b1)
+    bb_dec_ms = sum(a.elapsed_time(b) for a, b in bb_events)
 
     # ---------------- device time of the stages of ONE batch run one after the other (informational) ----------------
     stage_runs = [step_resident() for _ in range(3)]
@@ -202,7 +222,7 @@ def run_b200(args, rank, world, local_rank):
                  for i, n in enumerate(("l2_flush", "encoder", "decoder", "postnet"))}
 
     # ---------------- e2e (pinned host ids in, pinned host results out, public API) ----------------
-    run_pipelined(max(1, args.warmup // 2), True)
+    run_pipelined(args.steps, True)            # warm-up incl. the pinned result buffers of all K batches
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -231,20 +251,28 @@ def run_b200(args, rank, world, local_rank):
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "text_len": T, "cap": CAP,
                        "weights": "seed 1234 default init + planted stop counter (rate 8e-4, jitter 6e-3)",
                        "frames_counted": "sum of per-utterance decoded lengths",
-                       "l2": "flushed before every decoder launch (256 MiB device memset on the decoder stream)",
-                       "pipeline": "K batches back to back: encoder(i+1) and postnet(i-1) overlap decoder(i) on separate CUDA streams", "sharding": f"dp{world}: one batch per rank per step, same synthetic batch on every rank, no collective"},
+                       "l2": "flushed before every decoder launch (256 MiB device memset on the decoder stream); the K batches' "
+                             "encoder memory streams through the launch (123 MB at K=10)",
+                       "pipeline": "continuous batching: the K batches' utterances stream through the 32 rows of ONE persistent "
+                                   "decoder launch, a row is refilled from the next batch when its utterance stops; "
+                                   "encoders before, postnets after the launch",
+                       "sharding": f"dp{world}: one batch per rank per step, same synthetic batch on every rank, no collective"},
             "e2e": {"value": e2e_frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": ids_host.numel() * 8,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
+            "batch_by_batch": {"value": bb_frames / (bb_ms * 1e-3), "unit": UNIT, "ms_per_step": bb_ms / args.steps,
+                               "us_per_decode_step": bb_dec_ms * 1e3 / bb_steps, "decode_steps": bb_steps,
+                               "what": "one persistent decoder launch per batch (rows idle behind early stops), rank 0"},
             "stages_ms": stages_ms,
             "clocks": clocks,
-            "roofline": {"kernel": "decoder_tc_kernel<32> (persistent, one cooperative cluster launch per batch)", "bound": "hbm",
+            "roofline": {"kernel": "decoder_tc_kernel<32> (persistent, one cooperative cluster launch for the K batches)", "bound": "hbm",
                          "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch (1001 decode steps, B=32, T=150),
                          # ncu --set full, profiles/r1_v8_decoder_ncu_full.md: the working set is L2 resident
                          "traffic": 56_894_976, "traffic_unit": "bytes per launch (ncu, 1001-step launch)",
                          "peak_source": hbm_src, "bytes_per_decode_step": BYTES_PER_STEP_C2,
-                         "decode_steps_per_launch": dec_steps / args.steps, "us_per_decode_step": dec_ms * 1e3 / dec_steps,
+                         "decode_steps_per_launch": dec_steps / max(1, len(dec_events)), "us_per_decode_step": dec_ms * 1e3 / dec_steps,
+                         "row_occupancy": (frames / world + args.steps * B) / (dec_steps * B),
                          "kernel_share_of_step": dec_ms / ms,
                          "l2_read_peak_gbs_measured_live": l2_gbps, "frac_of_l2_read_peak": achieved / l2_gbps,
                          "note": "working set per decode step is L2 resident; HBM peak is the schema's denominator"},

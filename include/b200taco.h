@@ -187,6 +187,31 @@ B200TACO_API int32_t b200taco_decoder_infer(b200taco_handle* h, const float* d_m
                                void* d_workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Continuous batching of Decoder.inference (src/model.py:299-333) under the per-utterance stop rule
+ * (train.py:71-79): N utterances of EQUAL text length T stream through `rows` decoder rows of ONE persistent
+ * kernel.  A row whose utterance stopped (its own gate after >= 2 frames, or max_steps frames) takes the next
+ * utterance from the queue at the following decode step with freshly initialised state
+ * (Decoder._initialize_decoder_states, src/model.py:219-234, incl. the discarded first step, :310-316), so every
+ * utterance is decoded exactly as b200taco_decoder_infer(stop_mode = PER_UTTERANCE) decodes it in a batch of
+ * `rows`, without the idle row-steps behind early stops.  Tensor-core decoder kernel only: 4 <= rows <= 64,
+ * bf16 LSTM weights, N a multiple of rows.
+ *   d_memory (N,T,512)
+ *   d_mel (N,max_steps,80)  d_gate (N,max_steps)  d_align (N/rows,max_steps,rows,T): utterance u is row u % rows of
+ *   block u / rows.  Frames >= d_lengths[u] of utterance u are NOT written (zero-fill the buffers beforehand).
+ *   d_lengths (N) int32; d_steps_run (1) int32: decode steps the launch took.
+ *   d_lengths[u] is stored (system-scope release) the moment utterance u stops, after all of its frames: it may
+ *   point to zero-initialised MAPPED PINNED HOST memory, which the host polls to post-process finished utterances
+ *   (postnet, copies) on another stream while the launch is still decoding the rest.
+ * Workspace: b200taco_stream_workspace_bytes(h, N, rows, T).
+ */
+B200TACO_API size_t b200taco_stream_workspace_bytes(const b200taco_handle* h, int32_t N, int32_t rows, int32_t T);
+B200TACO_API int32_t b200taco_decoder_infer_stream(b200taco_handle* h, const float* d_memory, int32_t N, int32_t rows,
+                                      int32_t T, int32_t max_steps, float gate_threshold,
+                                      float* d_mel, float* d_gate, float* d_align,
+                                      int32_t* d_lengths, int32_t* d_steps_run,
+                                      void* d_workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Decoder.forward (teacher forcing), src/model.py:277-297, eval-mode dropout.
  *   d_mel_targets (B,80,S) as the reference receives them; d_text_lengths (B) int64 or
  *   NULL (= full length): positions >= length are masked with -1e9 (src/model.py:132).

@@ -132,10 +132,12 @@ class Engine:
         self._packed_sig = sig
 
     # ------------------------------------------------------------------ stages
-    def encoder(self, ids: torch.Tensor) -> torch.Tensor:
+    def encoder(self, ids: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
         B, T = ids.shape
         ids = ids.to(device=self.device, dtype=torch.int64).contiguous()
-        memory = torch.empty(B, T, config.encoder_embedding_dim, dtype=torch.float32, device=self.device)
+        memory = out if out is not None else torch.empty(B, T, config.encoder_embedding_dim, dtype=torch.float32,
+                                                         device=self.device)
+        assert memory.is_contiguous() and memory.shape == (B, T, config.encoder_embedding_dim)
         ws, wsz = self._workspace(B, T, 1, "encoder")
         with torch.cuda.device(self.device):
             check(self._lib.b200taco_encoder_fwd(self._h, ids.data_ptr(), B, T, memory.data_ptr(),
@@ -163,6 +165,35 @@ class Engine:
             return mel, gate, align, lengths, steps
         S = int(steps.item())            # the one host sync of an inference call
         return mel[:, :S], gate[:, :S], align[:S], lengths, S
+
+    def stream_supported(self, rows: int) -> bool:
+        """The utterance queue lives in the tensor-core decoder kernel (bf16 LSTM weights, >= 4 rows)."""
+        return self.weight_dtype == "bf16" and self.decoder_path == "auto" and 4 <= rows <= self.max_batch
+
+    def decoder_infer_stream(self, memory, rows: int, max_steps: int, gate_threshold: float):
+        """Continuous batching (b200taco_decoder_infer_stream): the N utterances of ``memory`` (N,T,512), N a multiple of
+        ``rows``, stream through ``rows`` decoder rows of one persistent kernel.  Returns, without synchronising,
+        ``mel (N,cap,80), gate (N,cap), align (N/rows,cap,rows,T), len_h (N+1)``; frames beyond an utterance's length
+        are zero.  ``len_h`` is PINNED HOST memory the kernel writes directly: ``len_h[u]`` becomes the length of
+        utterance u (> 0) the moment it stops, ``len_h[N]`` the decode steps of the launch when it ends."""
+        assert memory.is_contiguous()
+        N, T, _ = memory.shape
+        dev = self.device
+        mel = torch.zeros(N, max_steps, config.n_mels, dtype=torch.float32, device=dev)
+        gate = torch.zeros(N, max_steps, dtype=torch.float32, device=dev)
+        align = torch.zeros(N // rows, max_steps, rows, T, dtype=torch.float32, device=dev)
+        len_h = torch.zeros(N + 1, dtype=torch.int32).pin_memory()
+        need = int(self._lib.b200taco_stream_workspace_bytes(self._h, N, rows, T))
+        ws = self._ws.get("stream")
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            self._ws["stream"] = ws
+        with torch.cuda.device(dev):
+            check(self._lib.b200taco_decoder_infer_stream(
+                self._h, memory.data_ptr(), N, rows, T, max_steps, float(gate_threshold),
+                mel.data_ptr(), gate.data_ptr(), align.data_ptr(), len_h.data_ptr(), len_h.data_ptr() + 4 * N,
+                C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()), self._stream()), "b200taco_decoder_infer_stream")
+        return mel, gate, align, len_h
 
     def decoder_teacher_forced(self, memory, mel_targets, text_lengths):
         memory = memory.contiguous()
@@ -289,6 +320,110 @@ class Engine:
         ev_post.synchronize()
         cur.wait_stream(sP)
         yield res
+
+    def stream_infer(self, batches, max_steps: int, gate_threshold: float, to_host: bool = False, group_batches: int = 16,
+                     pre_hook=None, timings=None):
+        """Corpus synthesis with continuous batching: like ``pipeline_infer`` under the per-utterance stop rule, but the
+        utterances of up to ``group_batches`` consecutive batches (same shape (rows, T)) share ONE persistent decoder launch
+        whose rows are refilled from the following batches as their utterances stop (``decoder_infer_stream``), so no
+        row idles behind an early stop.  The kernel publishes every utterance's length in pinned host memory the moment it
+        stops; the host polls it and runs the postnet (and the copies to the host) of a batch on another stream as soon as
+        its last utterance is done, while the launch is still decoding the following batches.  Encoders of the next group
+        overlap the decoder launch of the current one.  Yields per batch, in order, what ``pipeline_infer`` yields; frames
+        of a row beyond its own length are zero (``pipeline_infer``: that row's continued decode)."""
+        import collections
+        import time
+        dev = self.device
+        cur = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_streams"):
+            self._streams = tuple(torch.cuda.Stream(dev) for _ in range(3))
+        sE, sD, sP = self._streams
+        for s_ in (sE, sD, sP):
+            s_.wait_stream(cur)
+        batches = list(batches)
+        if not batches:
+            return
+        rows, T = batches[0].shape
+        if any(tuple(b.shape) != (rows, T) for b in batches) or not self.stream_supported(rows):
+            raise B200TacoError("stream_infer needs batches of one shape (rows, T) with 4 <= rows <= 64 and the default "
+                                "(bf16, tensor-core) decoder; use pipeline_infer otherwise")
+        groups = [batches[i:i + group_batches] for i in range(0, len(batches), group_batches)]
+        self.last_stream_steps = 0                    # decode steps of all launches of this call
+
+        def prep(group):
+            with torch.cuda.stream(sE):
+                mem = torch.empty(len(group) * rows, T, config.encoder_embedding_dim, dtype=torch.float32, device=dev)
+                for i, ids in enumerate(group):
+                    ids_dev = ids.to(device=dev, dtype=torch.int64, non_blocking=True)
+                    self.encoder(ids_dev, out=mem[i * rows:(i + 1) * rows])
+                ev = torch.cuda.Event()
+                ev.record(sE)
+            return mem, ev
+
+        def launch_decoder(mem, ev_enc):
+            with torch.cuda.stream(sD):
+                sD.wait_event(ev_enc)
+                mem.record_stream(sD)
+                if pre_hook is not None:
+                    pre_hook()
+                if timings is not None:
+                    t0 = torch.cuda.Event(enable_timing=True)
+                    t0.record(sD)
+                out = self.decoder_infer_stream(mem, rows, max_steps, gate_threshold)
+                if timings is not None:
+                    t1 = torch.cuda.Event(enable_timing=True)
+                    t1.record(sD)
+                    timings.append((t0, t1))
+                ev = torch.cuda.Event()
+                ev.record(sD)
+            return out, ev
+
+        def finish(out, ev_dec):
+            """Generator over the batches of one launch, each post-processed as soon as its utterances have stopped."""
+            mel, gate, align, len_h = out
+            for t in (mel, gate, align):
+                t.record_stream(sP)
+            inflight = collections.deque()
+            for i in range(mel.shape[0] // rows):
+                lo, hi = i * rows, (i + 1) * rows
+                while int(len_h[lo:hi].min()) <= 0:          # pinned memory written by the running kernel
+                    if ev_dec.query():                        # launch over (or failed): the lengths are final
+                        ev_dec.synchronize()
+                        if int(len_h[lo:hi].min()) <= 0:
+                            raise B200TacoError("decoder launch ended with unfinished utterances")
+                        break
+                    time.sleep(2e-5)
+                S = int(len_h[lo:hi].max())
+                with torch.cuda.stream(sP):
+                    # no wait on the decoder stream: the kernel published these lengths after the frames themselves
+                    coarse = mel[lo:hi, :S].contiguous()
+                    post = self.postnet(coarse)
+                    lengths = len_h[lo:hi].to(dev, non_blocking=True)
+                    res = (post, coarse, gate[lo:hi, :S], align[i, :S], lengths, S)
+                    if to_host:
+                        post_h = torch.empty(post.shape, dtype=post.dtype, pin_memory=True)
+                        post_h.copy_(post, non_blocking=True)
+                        res = res + (post_h, len_h[lo:hi])
+                    ev = torch.cuda.Event()
+                    ev.record(sP)
+                inflight.append((res, ev))
+                while inflight and inflight[0][1].query():
+                    yield inflight.popleft()[0]
+            ev_dec.synchronize()
+            self.last_stream_steps += int(len_h[-1])
+            for res, ev in inflight:
+                ev.synchronize()
+                yield res
+
+        mem, ev_enc = prep(groups[0])
+        pending = launch_decoder(mem, ev_enc)
+        for group in groups[1:]:
+            mem, ev_enc = prep(group)                 # encoders of group g+1 overlap the decoder of group g
+            nxt = launch_decoder(mem, ev_enc)         # queued behind the launch of group g
+            yield from finish(*pending)
+            pending = nxt
+        yield from finish(*pending)
+        cur.wait_stream(sP)
 
     # ------------------------------------------------------------------ measurement aids
     def measure_l2_read_gbps(self, nbytes: int = 36 << 20, iters: int = 50) -> float:

@@ -265,18 +265,29 @@ class Tacotron2(nn.Module):
         return coarse, gate, align, lengths, S
 
     @torch.no_grad()
-    def inference_batches(self, batches, max_len_cap=None, gate_threshold=None, per_utterance=True, to_host=False):
+    def inference_batches(self, batches, max_len_cap=None, gate_threshold=None, per_utterance=True, to_host=False,
+                          continuous=False):
         """Corpus synthesis: free-running inference over an iterable of (B,T) id batches (device or pinned host
         tensors), with the encoder / decoder / postnet of consecutive batches overlapped on separate CUDA streams
         (``Engine.pipeline_infer``).  Yields per batch ``(mel_postnet, mel_coarse, gate_logits, alignments (S,B,T),
         lengths, S)`` (+ pinned host copies of mel_postnet and lengths with ``to_host``).  Each batch is decoded
-        exactly as ``inference_per_utterance`` / ``inference`` would decode it alone."""
+        exactly as ``inference_per_utterance`` / ``inference`` would decode it alone.
+
+        ``continuous=True`` (per-utterance stop rule, batches of one shape, >= 4 rows): continuous batching - the B
+        decoder rows of one persistent kernel are refilled from the following batches as their utterances stop
+        (``Engine.stream_infer``).  Every utterance's own frames ``[0, length)`` are bit-identical to the batch-by-batch
+        path; frames of a row beyond its own length are zero there instead of that row's continued decode."""
         self._check_mode("Tacotron2.inference_batches")
         thr = gate_threshold if gate_threshold is not None else self.decoder.gate_threshold
         cap = self.decoder.max_decoder_steps
         if max_len_cap:
             cap = min(cap, int(max_len_cap))
         eng = self._get_engine()
+        if continuous:
+            if not per_utterance:
+                raise ValueError("continuous batching decodes under the per-utterance stop rule")
+            yield from eng.stream_infer(batches, cap, thr, to_host)
+            return
         yield from eng.pipeline_infer(batches, cap, thr, STOP_PER_UTTERANCE if per_utterance else STOP_BATCH_WIDE, to_host)
 
     def _infer(self, text_inputs, max_len_cap, gate_threshold, stop_mode):

@@ -268,6 +268,44 @@ B200TACO_API int32_t b200taco_decoder_infer(b200taco_handle* h, const float* d_m
                        d_lengths, d_steps_run, d_workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+// Utterance queue: processed memory of all N utterances, then the scratch of a `rows`-row launch.
+static size_t stream_ws_bytes(int N, int rows, int T) {
+    return align_up((size_t)N * T * ATT_DIM * sizeof(float), 256) + decoder_scratch_bytes(rows, T) + 256;
+}
+
+B200TACO_API size_t b200taco_stream_workspace_bytes(const b200taco_handle*, int32_t N, int32_t rows, int32_t T) {
+    if (N < 1 || rows < 1 || rows > MAX_BATCH || T < 1 || T > MAX_TEXT_LEN) return 0;
+    return stream_ws_bytes(N, rows, T);
+}
+
+B200TACO_API int32_t b200taco_decoder_infer_stream(b200taco_handle* h, const float* d_memory, int32_t N, int32_t rows, int32_t T,
+                                                   int32_t max_steps, float gate_threshold, float* d_mel, float* d_gate,
+                                                   float* d_align, int32_t* d_lengths, int32_t* d_steps_run, void* d_workspace,
+                                                   size_t workspace_bytes, void* stream) {
+    TACO_TRY(check_handle(h, true));
+    TACO_TRY(check_shape(rows, T));
+    TACO_REQUIRE(d_memory && d_mel && d_gate && d_align && d_lengths && d_steps_run && d_workspace, B200TACO_ERR_INVALID,
+                 "decoder_infer_stream: null pointer");
+    TACO_REQUIRE(max_steps >= 1, B200TACO_ERR_INVALID, "max_steps must be >= 1 (got %d)", max_steps);
+    TACO_REQUIRE(N >= rows && N % rows == 0, B200TACO_ERR_INVALID,
+                 "decoder_infer_stream: %d utterances is not a positive multiple of %d rows", N, rows);
+    TACO_REQUIRE(workspace_bytes >= stream_ws_bytes(N, rows, T), B200TACO_ERR_STATE, "decoder workspace too small: %zu < %zu",
+                 workspace_bytes, stream_ws_bytes(N, rows, T));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* pm = static_cast<float*>(d_workspace);
+    uint8_t* scratch = static_cast<uint8_t*>(d_workspace) + align_up((size_t)N * T * ATT_DIM * sizeof(float), 256);
+    // processed_memory = memory_layer(memory), once per utterance (src/model.py:112)
+    TACO_TRY(dense_layer(h, d_memory, EMB, h->attn_memory_wT, h->attn_memory_wtc, nullptr, nullptr, nullptr, 0, pm, ATT_DIM, N * T,
+                         N * T, EMB, ATT_DIM, 1, ACT_NONE, true, st));
+    DecoderArgs a{};
+    a.B = rows; a.T = T; a.max_steps = max_steps; a.mode = 0; a.stop_mode = B200TACO_STOP_PER_UTTERANCE;
+    a.gate_threshold = gate_threshold; a.n_utts = N;
+    a.memory = d_memory; a.pm = pm; a.text_lengths = nullptr; a.p_all = nullptr;
+    a.mel = d_mel; a.gate = d_gate; a.align = d_align; a.lengths = d_lengths; a.steps_run = d_steps_run;
+    a.scratch = scratch; a.scratch_bytes = decoder_scratch_bytes(rows, T);
+    return decoder_run(h, a, st);
+}
+
 B200TACO_API int32_t b200taco_decoder_teacher_forced(b200taco_handle* h, const float* d_memory, const float* d_mel_targets,
                                         const int64_t* d_text_lengths, int32_t B, int32_t T, int32_t S, float* d_mel,
                                         float* d_gate, float* d_align, void* d_workspace, size_t workspace_bytes,

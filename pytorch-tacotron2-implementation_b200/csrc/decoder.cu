@@ -48,10 +48,18 @@ constexpr uint64_t SPIN_TIMEOUT_NS = 4000000000ull;
 constexpr int CTRL_BARRIER = 0, CTRL_STOP = 1, CTRL_FINISHED = 2, CTRL_TICKETS = 32, CTRL_DONE = 32 + MAX_BATCH,
               CTRL_LEN = 32 + 2 * MAX_BATCH, CTRL_PROF = 32 + 3 * MAX_BATCH /* 5 x u64 */,
               CTRL_GCNT = CTRL_PROF + 48 /* 32 group counters */,
-              CTRL_WORDS = CTRL_GCNT + GEMM_CTAS / GS;
+              // utterance queue (continuous batching, KParams::n_utts > 0): queue head, then per decoder row the utterance
+              // it carries (negative: -1 - last utterance, row retired) and the decode step at which that utterance began
+              CTRL_QHEAD = CTRL_GCNT + GEMM_CTAS / GS, CTRL_UTT = CTRL_QHEAD + 1, CTRL_START = CTRL_UTT + MAX_BATCH,
+              CTRL_WORDS = CTRL_START + MAX_BATCH;
+constexpr int ROW_START = MAX_BATCH;       // offset of the start steps inside a CTA's shared copy of the row table
 
 struct KParams {
     int B, T, Tp, NS, SL, NQ, max_steps, mode, stop_mode;
+    // continuous batching (0 = off): n_utts utterances of equal text length stream through the B decoder rows; a row whose
+    // utterance stopped takes the next one from the queue at the following decode step.  memory / pm / mel / gate /
+    // lengths are then indexed by utterance, align is (n_utts / B, max_steps, B, T).
+    int n_utts;
     float thr;
     const void* w_attn;
     const void* w_dec;
@@ -122,7 +130,8 @@ struct Smem {
     static constexpr int OFF_MISC = OFF_V + 132 * 4;                           // 64 floats of flags/scalars
     static constexpr int OFF_XCH = OFF_MISC + 64 * 4;                          // tensor-core path: split-K partials of the
     static constexpr int XCH_BYTES = TC ? GS * ROWS_PER_CTA * BP * 4 : 0;      // four group members, written through DSMEM
-    static constexpr int TOTAL = OFF_XCH + XCH_BYTES;
+    static constexpr int OFF_ROWS = OFF_XCH + XCH_BYTES;                       // tensor-core path: row table (utterance, start step)
+    static constexpr int TOTAL = OFF_ROWS + (TC ? 2 * MAX_BATCH * 4 : 0);
     static_assert(TOTAL <= 227 * 1024, "shared memory budget");
     static_assert(STAGE_BYTES % 128 == 0 && W_BYTES % 128 == 0, "bulk copy alignment");
 };
@@ -397,16 +406,23 @@ __device__ __forceinline__ PwSave pw_save(float* g, float* c, float* h, const fl
 template <int BP, bool TC>
 __device__ __forceinline__ void lstm_pointwise(const float* z, const float* bias, float* c_state, float* h_out,
                                                float* act_dst /* &act[buf][row0][0] */, __nv_bfloat16* act16_buf,
-                                               int k0, int B, int tid, const PwSave& sv) {
+                                               int k0, int B, int tid, const PwSave& sv, const int* rows = nullptr,
+                                               int step = 0, bool zero_z = false) {
+    // rows != null (continuous batching): a row that starts a new utterance at this step has zero carried state
+    // (Decoder._initialize_decoder_states, src/model.py:219-234): cell state 0, and - zero_z - all inputs of this
+    // contraction zero, whatever the accumulator gathered from the previous utterance in the background
     for (int i = tid; i < UNITS_PER_CTA * BP; i += NTC) {
         const int u = i / BP, b = i % BP;
         if (b < B) {
-            const float zi = z[(u * 4 + 0) * BP + b] + bias[u * 4 + 0];
-            const float zf = z[(u * 4 + 1) * BP + b] + bias[u * 4 + 1];
-            const float zg = z[(u * 4 + 2) * BP + b] + bias[u * 4 + 2];
-            const float zo = z[(u * 4 + 3) * BP + b] + bias[u * 4 + 3];
+            const bool fresh = rows != nullptr && rows[ROW_START + b] == step;
+            const float zs = fresh && zero_z ? 0.f : 1.f;
+            const float zi = zs * z[(u * 4 + 0) * BP + b] + bias[u * 4 + 0];
+            const float zf = zs * z[(u * 4 + 1) * BP + b] + bias[u * 4 + 1];
+            const float zg = zs * z[(u * 4 + 2) * BP + b] + bias[u * 4 + 2];
+            const float zo = zs * z[(u * 4 + 3) * BP + b] + bias[u * 4 + 3];
             const float gi = sigmoid_acc(zi), gf = sigmoid_acc(zf), gg = tanhf(zg), go = sigmoid_acc(zo);
-            const float c = gf * c_state[i] + gi * gg;
+            // explicit contraction: the plain and the utterance-queue instantiations must round identically
+            const float c = __fmaf_rn(gf, fresh ? 0.f : c_state[i], __fmul_rn(gi, gg));
             float h = go * tanhf(c);
             if (sv.gates != nullptr) {          // training: keep what the backward needs, drop the carried h
                 const int unit = sv.unit0 + u;
@@ -522,7 +538,8 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
                                                 int tid, int warp, int lane, float* act_cur, __nv_bfloat16* act16_cur,
                                                 bool timing, unsigned long long* t_fine, unsigned long long& t_flast,
                                                 volatile int* sig = nullptr, int sig_val = 0, float* apx = nullptr,
-                                                uint64_t* xbar2 = nullptr, bool rev = false) {
+                                                uint64_t* xbar2 = nullptr, bool rev = false, const int* rows = nullptr,
+                                                int step = 0) {
     // rev: work items are dealt from the LAST CTA downwards, so that the CTAs beyond the 128 GEMM CTAs take them first
     // (small batches of the SIMT kernel: the GEMM CTAs then spend this phase on their background contractions)
     static_assert(!CL || TC, "cluster merge belongs to the tensor-core kernel");
@@ -541,12 +558,25 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
         const int b = item / NS, sl = item % NS;
         const int t0 = sl * SL, t1 = min(T, t0 + SL), n = max(0, t1 - t0);
         const int len = p.text_lengths ? (int)p.text_lengths[b] : T;
+        // continuous batching: row b carries utterance mb since decode step rows[ROW_START + b]; its first step sees
+        // zero previous / cumulative attention weights (src/model.py:104-115); a retired row repeats its last
+        // utterance without writing anything the host reads
+        int mb = b, oi = out_idx;
+        bool fresh = false;
+        if (rows != nullptr) {
+            const int u = rows[b], st = rows[ROW_START + b];
+            mb = u >= 0 ? u : -1 - u;
+            fresh = step == st;
+            oi = u >= 0 ? step - st - 1 : -1;
+        }
+        const size_t align_row = rows != nullptr ? ((size_t)(mb / B) * p.max_steps + (oi < 0 ? 0 : oi)) * B + mb % B
+                                                 : (size_t)(oi < 0 ? 0 : oi) * B + b;
         consumer_sync();   // previous item's scratch is free
         const int ntiles = (n + TILE_POS - 1) / TILE_POS;
         // processed-memory tile 0: asynchronous copy, overlapped with the loads below
         auto issue_pm_tile = [&](int tb) {
             const int rows = min(TILE_POS, n - tb);
-            const float* src = p.pm + ((size_t)b * T + t0 + tb) * ATT_DIM;
+            const float* src = p.pm + ((size_t)mb * T + t0 + tb) * ATT_DIM;
             for (int i = tid; i < rows * (ATT_DIM / 4); i += NTC) cp_async16(sc + P2Scratch::PM + i * 4, src + i * 4);
         };
         issue_pm_tile(0);
@@ -554,7 +584,7 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
         const int wlen = ntiles * TILE_POS + LOC_K - 1 + 4;
         for (int i = tid; i < wlen; i += NTC) {
             const int t = t0 - (LOC_K - 1) / 2 + i;
-            const bool ok = t >= 0 && t < T;
+            const bool ok = t >= 0 && t < T && !fresh;
             sc[P2Scratch::WIN + i] = ok ? __ldcg(prev_in + (size_t)b * p.Tp + t) : 0.f;
             sc[P2Scratch::WIN + P2Scratch::WIN_LEN + i] = ok ? __ldcg(cum_in + (size_t)b * p.Tp + t) : 0.f;
         }
@@ -658,7 +688,7 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
         FT(4);
         }
         // ---- first 20 memory rows of the context sum: issued now, in flight during the softmax statistics ----
-        const float2* mrow = reinterpret_cast<const float2*>(p.memory + ((size_t)b * T + t0) * EMB) + tid;
+        const float2* mrow = reinterpret_cast<const float2*>(p.memory + ((size_t)mb * T + t0) * EMB) + tid;
         float2 mv0[20];
 #pragma unroll
         for (int j = 0; j < 20; ++j) mv0[j] = j < n ? __ldg(mrow + (size_t)j * (EMB / 2)) : make_float2(0.f, 0.f);
@@ -751,8 +781,8 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
                     const int t = t0 + i;
                     const float w = sc[P2Scratch::E + i] * mine / S;
                     prev_out[(size_t)b * p.Tp + t] = w;
-                    cum_out[(size_t)b * p.Tp + t] = __ldcg(cum_in + (size_t)b * p.Tp + t) + w;
-                    if (out_idx >= 0) p.align[((size_t)out_idx * B + b) * T + t] = w;
+                    cum_out[(size_t)b * p.Tp + t] = (fresh ? 0.f : __ldcg(cum_in + (size_t)b * p.Tp + t)) + w;
+                    if (oi >= 0) p.align[align_row * T + t] = w;
                 }
                 // context rows [sl * 512/NS, (sl+1) * 512/NS)
                 const int per = EMB / NS;
@@ -854,8 +884,8 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
             else ew = sc[P2Scratch::E + t];
             const float w = ew / S;
             prev_out[(size_t)b * p.Tp + t] = w;
-            cum_out[(size_t)b * p.Tp + t] = __ldcg(cum_in + (size_t)b * p.Tp + t) + w;
-            if (out_idx >= 0) p.align[((size_t)out_idx * B + b) * T + t] = w;
+            cum_out[(size_t)b * p.Tp + t] = (fresh ? 0.f : __ldcg(cum_in + (size_t)b * p.Tp + t)) + w;
+            if (oi >= 0) p.align[align_row * T + t] = w;
         }
         FT(8);
     }
@@ -867,13 +897,24 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
 template <int BP, bool TC>
 __device__ __forceinline__ void projection_phase(const KParams& p, float* red, bool tf, int out_idx, int cta, int ncta,
                                                  int tid, float* act_cur, __nv_bfloat16* act16_cur,
-                                                 volatile int* sig = nullptr, int sig_val = 0, bool rev = false) {
+                                                 volatile int* sig = nullptr, int sig_val = 0, bool rev = false,
+                                                 const int* rows = nullptr, int step = 0,
+                                                 __nv_bfloat16* act16_nxt = nullptr) {
     const int B = p.B;
     (void)act_cur; (void)act16_cur;
     float* sc = red;
     const int NQ = p.NQ, RQ = PRENET / NQ;
     for (int item = rev ? ncta - 1 - cta : cta; item < B * NQ; item += ncta) {
         const int b = item / NQ, q = item % NQ;
+        // continuous batching: outputs go to the utterance the row carries, at the utterance's own frame index
+        int ub = b, oi = out_idx;
+        bool live = true;
+        if (rows != nullptr) {
+            const int u = rows[b], st = rows[ROW_START + b];
+            live = u >= 0;
+            ub = live ? u : -1 - u;
+            oi = live ? step - st - 1 : -1;
+        }
         consumer_sync();
         // The prenet weights stream from L2 every step; their loads do not depend on this step's values, so each
         // batch is issued one stage ahead of its use (first half of layer 1 before the partial sums, second half
@@ -898,11 +939,30 @@ __device__ __forceinline__ void projection_phase(const KParams& p, float* red, b
         if (tid < PROJ_OUT) {
             const float v = sc[tid] + sc[128 + tid] + __ldg(p.proj_bias + tid);
             sc[256 + tid] = v;                                  // mel frame (0..79), gate logit (80)
-            if (q == 0 && out_idx >= 0) {
-                if (tid < N_MELS) p.mel[((size_t)b * p.max_steps + out_idx) * N_MELS + tid] = v;
-                else p.gate[(size_t)b * p.max_steps + out_idx] = v;
+            if (q == 0 && oi >= 0) {
+                if (tid < N_MELS) p.mel[((size_t)ub * p.max_steps + oi) * N_MELS + tid] = v;
+                else p.gate[(size_t)ub * p.max_steps + oi] = v;
             }
-            if (q == 0 && !tf && tid == N_MELS && out_idx >= 1) {
+            if (rows != nullptr) {
+                // utterance queue: a row whose utterance stopped (its own gate, train.py:71-79 with the steps > 1 guard of
+                // src/model.py:327, or the frame cap) takes the next queued utterance from the following decode step on
+                if (q == 0 && tid == N_MELS) {
+                    int refill = 0;
+                    if (live && ((oi >= 1 && sigmoid_acc(v) > p.thr) || oi + 1 >= p.max_steps)) {
+                        refill = 2;
+                        const uint32_t nxt = atomicAdd(p.ctrl + CTRL_QHEAD, 1u) + (uint32_t)B;
+                        if (nxt < (uint32_t)p.n_utts) {
+                            p.ctrl[CTRL_UTT + b] = nxt;
+                            p.ctrl[CTRL_START + b] = (uint32_t)(step + 1);
+                            refill = 3;
+                        } else {
+                            p.ctrl[CTRL_UTT + b] = (uint32_t)(-1 - ub);
+                        }
+                        if (atomicAdd(p.ctrl + CTRL_FINISHED, 1u) + 1u == (uint32_t)p.n_utts) atomicExch(p.ctrl + CTRL_STOP, 1u);
+                    }
+                    reinterpret_cast<int*>(sc)[340] = refill;
+                }
+            } else if (q == 0 && !tf && tid == N_MELS && out_idx >= 1) {
                 // stop rule: src/model.py:327 (batch-wide) or train.py:71-79 (per utterance)
                 const bool fired = sigmoid_acc(v) > p.thr;
                 if (fired) {
@@ -925,6 +985,24 @@ __device__ __forceinline__ void projection_phase(const KParams& p, float* red, b
 #pragma unroll
         for (int i = 0; i < 32; ++i) w2a[i] = __ldg(w2src + (size_t)i * PRENET);
         consumer_sync();
+        if constexpr (TC) {
+            // the utterance's length is published only now: the last frame's mel / gate stores of the other threads are
+            // ordered before it by the barrier above, its alignment rows by the grid barrier after phase B.  d_lengths may
+            // be mapped host memory that the host polls to post-process finished utterances while the launch goes on.
+            if (rows != nullptr && q == 0 && tid == N_MELS && (reinterpret_cast<const int*>(sc)[340] & 2) != 0) {
+                __threadfence_system();
+                *reinterpret_cast<volatile int32_t*>(p.lengths + ub) = oi + 1;
+            }
+            // the new utterance starts from a zero decoder hidden state: its rows of the operand that the next step's
+            // background contraction W[dh] . dh reads (the attention LSTM ignores its accumulator for a fresh row)
+            if (rows != nullptr && q == 0 && (reinterpret_cast<const int*>(sc)[340] & 1) != 0) {
+                const __nv_bfloat16 zero = __float2bfloat16(0.f);
+                for (int k = tid; k < RNN; k += NTC) {
+                    act16_nxt[act16_off<BP>(b, ACT_DH + k)] = zero;
+                    act16_nxt[act16_off<BP>(BP + b, ACT_DH + k)] = zero;
+                }
+            }
+        }
         // prenet layer 1 (all 256 outputs in every quarter CTA), eval mode: no dropout (F4)
         {
             float acc = 0.f;
@@ -1374,7 +1452,8 @@ __device__ __forceinline__ void tc_epilogue(uint32_t acc, uint64_t* acc_bar, uin
     }
 }
 
-template <int BP, bool CL>
+// ST: utterance queue (continuous batching) compiled in; the plain instantiation carries none of its code
+template <int BP, bool CL, bool ST>
 __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
     using WT = __nv_bfloat16;
     using SM = Smem<BP, WT, true>;
@@ -1413,6 +1492,9 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
     uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + SM::OFF_ACCBAR + 32);
     uint64_t* xbar2 = reinterpret_cast<uint64_t*>(smem + SM::OFF_ACCBAR + 40);
     float* xch = reinterpret_cast<float*>(smem + SM::OFF_XCH);
+    int* rows_s = reinterpret_cast<int*>(smem + SM::OFF_ROWS);
+    constexpr bool streaming = ST;
+    const int* const rows = ST ? rows_s : nullptr;
     static_assert(SM::OFF_ACCBAR + 48 <= 256, "barrier area");
     static_assert(GS * APART * 4 <= SM::XCH_BYTES, "attention partials of the slice siblings alias the exchange buffer");
 
@@ -1445,6 +1527,8 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
     for (int i = tid; i < LOC_F * 2 * LOC_K; i += NT_TC) wloc_s[(i / 62) * 63 + (i % 62)] = p.loc_conv[i];
     for (int i = tid; i < LOC_F * ATT_DIM; i += NT_TC) wld_s[i] = p.loc_denseT[i];
     for (int i = tid; i < 130; i += NT_TC) v_s[i] = p.attn_v[i];
+    // utterance queue: row b starts with utterance b at step 0 (start steps and the queue head are zero-initialised)
+    if (streaming && cta == 0 && tid < B) p.ctrl[CTRL_UTT + tid] = (uint32_t)tid;
     __syncthreads();
     if constexpr (CL) cluster_sync_all();        // peers' mbarriers are initialised before anyone arrives on them
     umma::fence_after_sync();
@@ -1467,7 +1551,9 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
     uint32_t epoch = 0;
     uint32_t g = 0;             // ring position: chunks issued (producer) / consumed (MMA thread)
     const bool tf = p.mode == 1;
-    const int total_steps = tf ? p.max_steps : p.max_steps + 1;
+    // utterance queue: every utterance takes at most max_steps + 1 decode steps of one row
+    const int total_steps = tf ? p.max_steps
+                               : (streaming ? (p.n_utts + B - 1) / B * (p.max_steps + 1) : p.max_steps + 1);
     int steps_done = 0;
 
     const bool timing = cta == 0 && tid == 0;
@@ -1505,6 +1591,16 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
         __nv_bfloat16* act16_cur = p.act16 + (size_t)cur * (ABUF_BYTES / 2);
         __nv_bfloat16* act16_prv = p.act16 + (size_t)prv * (ABUF_BYTES / 2);
         const int out_idx = tf ? s : s - 1;          // F6: decode step 0 of inference is discarded
+        // utterance queue: this step's row table (rows that stopped in the previous step's phase D were re-assigned
+        // there, before the barrier).  Loaded by the last two consumer warps - not TMEM readers of the epilogue at
+        // BP = 32 - while the critical chunk is in flight; the first use follows a consumer / CTA barrier.
+        if (streaming && tid >= NTC - MAX_BATCH && tid < NTC) {
+            const int i = tid - (NTC - MAX_BATCH);
+            if (i < B) {
+                rows_s[i] = s == 0 ? i : (int)__ldcg(p.ctrl + CTRL_UTT + i);
+                rows_s[ROW_START + i] = s == 0 ? 0 : (int)__ldcg(p.ctrl + CTRL_START + i);
+            }
+        }
 
         // =============================== A: attention LSTM (critical: prenet rows) ===============================
         if (is_gemm) {
@@ -1527,7 +1623,8 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
                                     lane, tid);
                 FT(9);
                 lstm_pointwise<BP, true>(z_s, bias_s, ca_s, h_s, nullptr, act16_cur, ACT_AH + cta * UNITS_PER_CTA, B, tid,
-                                       pw_save(p.sv_ga, p.sv_ca, p.sv_ah, p.mask_a, p.drop_scale, s, B, cta * UNITS_PER_CTA));
+                                       pw_save(p.sv_ga, p.sv_ca, p.sv_ah, p.mask_a, p.drop_scale, s, B, cta * UNITS_PER_CTA),
+                                       rows, s, true);
                 FT(10);
                 // this CTA's slice of the query projection (src/model.py:123): pqpart[b][cta][a]
                 for (int i = tid; i < ATT_DIM * B; i += NTC) {
@@ -1554,7 +1651,7 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
             __syncwarp();
         } else if (is_consumer) {
             attention_phase<BP, true, CL>(p, red, wld_s, wloc_s, v_s, misc_s, cur, out_idx, cta, ncta, tid, warp, lane, act_cur,
-                                          act16_cur, timing, TACO_FINE_ARGS, misc_s + 1, 2 * s + 1, xch, xbar2);
+                                          act16_cur, timing, TACO_FINE_ARGS, misc_s + 1, 2 * s + 1, xch, xbar2, false, rows, s);
         }
         grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
         stamp(1);
@@ -1583,7 +1680,8 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
                                     lane, tid);
                 FT(12);
                 lstm_pointwise<BP, true>(z_s, bias_s + 32, cd_s, h_s, nullptr, act16_prv, ACT_DH + cta * UNITS_PER_CTA, B, tid,
-                                       pw_save(p.sv_gd, p.sv_cd, p.sv_dh, p.mask_d, p.drop_scale, s, B, cta * UNITS_PER_CTA));
+                                       pw_save(p.sv_gd, p.sv_cd, p.sv_dh, p.mask_d, p.drop_scale, s, B, cta * UNITS_PER_CTA),
+                                       rows, s, false);
                 FT(13);
                 // this CTA's slice of linear_projection / gate_layer (src/model.py:272-274): 8 decoder-h units + 4 context rows
                 for (int i = tid; i < PROJ_PAD * B; i += NTC) {
@@ -1603,7 +1701,9 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
         stamp(2);
 
         // =============================== D: projection sums, stop rule, prenet; background: dh_t range ============
-        if (is_consumer) projection_phase<BP, true>(p, red, tf, out_idx, cta, ncta, tid, act_cur, act16_cur);
+        if (is_consumer)
+            projection_phase<BP, true>(p, red, tf, out_idx, cta, ncta, tid, act_cur, act16_cur, nullptr, 0, false, rows, s,
+                                       act16_prv);
         steps_done = s + 1;
         if (!tf) {
             grid_barrier(p.ctrl + CTRL_BARRIER, epoch, ncta);
@@ -1633,8 +1733,8 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
         for (int i = 0; i < 16; ++i) prof[5 + i] = t_fine[i];
 #endif
         const int S = tf ? p.max_steps : steps_done - 1;     // output frames (decode step 0 discarded)
-        *p.steps_run = S;
-        for (int b = 0; b < B; ++b) {
+        *p.steps_run = streaming ? steps_done : S;           // utterance queue: decode steps of the whole launch
+        for (int b = 0; b < B && !streaming; ++b) {
             int len = S;
             if (!tf && p.stop_mode == B200TACO_STOP_PER_UTTERANCE && __ldcg(p.ctrl + CTRL_DONE + b))
                 len = (int)__ldcg(p.ctrl + CTRL_LEN + b);
@@ -1652,7 +1752,7 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
 template <int BP>
 int tc_cluster_ctas(int num_sms) {
     using SM = Smem<BP, __nv_bfloat16, true>;
-    auto kern = decoder_tc_kernel<BP, true>;
+    auto kern = decoder_tc_kernel<BP, true, false>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL) != cudaSuccess) {
         cudaGetLastError();
         return 0;
@@ -1678,7 +1778,7 @@ template <int BP>
 int launch_tc(const KParams& kp, int ncta, bool clusters, cudaStream_t stream) {
     using SM = Smem<BP, __nv_bfloat16, true>;
     if (clusters) {
-        auto kern = decoder_tc_kernel<BP, true>;
+        auto kern = kp.n_utts > 0 ? decoder_tc_kernel<BP, true, true> : decoder_tc_kernel<BP, true, false>;
         TACO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(ncta);
@@ -1695,7 +1795,7 @@ int launch_tc(const KParams& kp, int ncta, bool clusters, cudaStream_t stream) {
         launch_counter()++;
         return B200TACO_OK;
     }
-    auto kern = decoder_tc_kernel<BP, false>;
+    auto kern = kp.n_utts > 0 ? decoder_tc_kernel<BP, false, true> : decoder_tc_kernel<BP, false, false>;
     TACO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     int per_sm = 0;
     TACO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT_TC, SM::TOTAL));
@@ -2144,6 +2244,13 @@ int decoder_run(const b200taco_handle* h, const DecoderArgs& a, cudaStream_t str
     TACO_REQUIRE(a.T >= 1 && a.T <= MAX_TEXT_LEN, B200TACO_ERR_UNSUPPORTED, "text length %d outside [1, %d]", a.T,
                  MAX_TEXT_LEN);
     TACO_REQUIRE(a.max_steps >= 1, B200TACO_ERR_INVALID, "max_steps must be >= 1");
+    if (a.n_utts > 0) {
+        TACO_REQUIRE(a.mode == 0 && decoder_uses_tensor_cores(h, a.B), B200TACO_ERR_UNSUPPORTED,
+                     "the utterance queue runs on the tensor-core decoder kernel only (free-running, bf16 LSTM weights, "
+                     ">= %d rows; got %d rows)", TC_MIN_BATCH, a.B);
+        TACO_REQUIRE(a.n_utts % a.B == 0, B200TACO_ERR_INVALID, "utterance count %d is not a multiple of the %d decoder rows",
+                     a.n_utts, a.B);
+    }
     TACO_REQUIRE(h->num_sms >= MIN_CTAS, B200TACO_ERR_UNSUPPORTED,
                  "the persistent decoder needs >= %d SMs (device has %d)", MIN_CTAS, h->num_sms);
     const ScratchLayout L = scratch_layout(a.B, a.T);
@@ -2167,6 +2274,7 @@ int decoder_run(const b200taco_handle* h, const DecoderArgs& a, cudaStream_t str
 
     KParams kp{};
     kp.B = a.B; kp.T = a.T; kp.Tp = (a.T + 3) / 4 * 4;
+    kp.n_utts = a.n_utts;
     int ns = ncta / a.B;
     ns = ns < 1 ? 1 : (ns > MAX_NS ? MAX_NS : ns);
     // keep slices at least 8 positions long

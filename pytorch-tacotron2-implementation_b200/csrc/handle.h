@@ -94,6 +94,9 @@ struct DecoderArgs {
     int32_t* steps_run;           // (1)
     void* scratch;                // decoder_scratch_bytes()
     size_t scratch_bytes;
+    // utterance queue (continuous batching; 0 = off): n_utts utterances of text length T stream through the B decoder
+    // rows; memory / pm / mel / gate / lengths are then per utterance and align is (n_utts / B, max_steps, B, T)
+    int n_utts = 0;
     // training (teacher-forced mode only; all null / 0 otherwise): per-step state for the backward pass, dropout masks
     float *sv_ga = nullptr, *sv_ca = nullptr, *sv_ah = nullptr, *sv_gd = nullptr, *sv_cd = nullptr, *sv_dh = nullptr,
           *sv_ctx = nullptr;

@@ -277,6 +277,33 @@ def test_pipelined_batches_equal_one_by_one():
         assert torch.equal(o[6], post.cpu()) and torch.equal(o[7], lengths.cpu())
 
 
+@pytest.mark.parametrize("rows,T,nb,cap", [(8, 41, 4, None), (32, 30, 3, None), (5, 41, 3, 9), (64, 23, 2, None)])
+def test_continuous_batching_equals_batch_by_batch(rows, T, nb, cap):
+    """Utterance queue (b200taco_decoder_infer_stream): rows of one persistent launch are refilled as utterances stop.
+    Every utterance must come out bit-identical to its batch-by-batch decode under the per-utterance rule: same length,
+    same frames / gate logits / alignments up to that length, zeros behind it."""
+    sd = util.weights("planted", True, ctx_center=O.encoder(util.weights("stress", True), synth.phoneme_ids(2, 30, seed=50)).mean((0, 1)))
+    m = gpu_model(sd)
+    batches = [synth.phoneme_ids(rows, T, seed=80 + i).cuda() for i in range(nb)]
+    solo = [m.inference_per_utterance(x, max_len_cap=cap) for x in batches]
+    outs = list(m.inference_batches(batches, max_len_cap=cap, continuous=True, to_host=True))
+    assert len(outs) == nb
+    spread = set()
+    for (post, coarse, gate, aligns, lengths), o in zip(solo, outs):
+        L = lengths.cpu()
+        assert torch.equal(o[4].cpu(), L) and torch.equal(o[7], L) and o[5] == int(L.max())
+        al = torch.stack(aligns)
+        for r in range(rows):
+            n = int(L[r])
+            spread.add(n)
+            assert torch.equal(o[1][r, :n], coarse[r, :n]) and torch.equal(o[2][r, :n], gate[r, :n])
+            assert torch.equal(o[3][:n, r], al[:n, r])
+            assert not o[1][r, n:].any() and not o[2][r, n:].any() and not o[3][n:, r].any()
+        assert torch.equal(o[6], o[0].cpu()) and o[0].shape == o[1].shape
+    assert cap is not None or len(spread) > 1, "the planted stop counter should give different lengths"
+    assert m._get_engine().last_stream_steps < sum(s[1].shape[1] + 1 for s in solo) or cap is not None
+
+
 def test_long_horizon_default_init_1000_steps():
     """Default init never fires (F11): 1000 frames, error must not grow with the horizon."""
     ids = synth.phoneme_ids(2, 150, seed=1)
