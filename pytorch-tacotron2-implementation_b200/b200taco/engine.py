@@ -353,9 +353,13 @@ class Engine:
         def prep(group):
             with torch.cuda.stream(sE):
                 mem = torch.empty(len(group) * rows, T, config.encoder_embedding_dim, dtype=torch.float32, device=dev)
+                ids_dev = torch.empty(len(group) * rows, T, dtype=torch.int64, device=dev)
                 for i, ids in enumerate(group):
-                    ids_dev = ids.to(device=dev, dtype=torch.int64, non_blocking=True)
-                    self.encoder(ids_dev, out=mem[i * rows:(i + 1) * rows])
+                    ids_dev[i * rows:(i + 1) * rows].copy_(ids, non_blocking=True)
+                # rows are independent in the encoder: as many utterances per launch as the library carries
+                per = max(rows, self.max_batch // rows * rows)
+                for lo in range(0, len(group) * rows, per):
+                    self.encoder(ids_dev[lo:lo + per], out=mem[lo:lo + per])
                 ev = torch.cuda.Event()
                 ev.record(sE)
             return mem, ev
