@@ -30,7 +30,10 @@ def main():
             for _ in range(2):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                eng.decoder_infer(mem, S, 0.5, STOP_BATCH_WIDE, sync=False)
+                if os.environ.get("STREAM") and eng.stream_supported(B):     # utterance-queue instantiation, no refills
+                    eng.decoder_infer_stream(mem, B, S, 0.5)
+                else:
+                    eng.decoder_infer(mem, S, 0.5, STOP_BATCH_WIDE, sync=False)
                 e1.record()
                 torch.cuda.synchronize()
             prof = eng.decoder_profile()

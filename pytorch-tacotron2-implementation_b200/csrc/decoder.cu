@@ -52,7 +52,8 @@ constexpr int CTRL_BARRIER = 0, CTRL_STOP = 1, CTRL_FINISHED = 2, CTRL_TICKETS =
               // it carries (negative: -1 - last utterance, row retired) and the decode step at which that utterance began
               CTRL_QHEAD = CTRL_GCNT + GEMM_CTAS / GS, CTRL_UTT = CTRL_QHEAD + 1, CTRL_START = CTRL_UTT + MAX_BATCH,
               CTRL_WORDS = CTRL_START + MAX_BATCH;
-constexpr int ROW_START = MAX_BATCH;       // offset of the start steps inside a CTA's shared copy of the row table
+constexpr int ROW_START = MAX_BATCH;       // offsets inside a CTA's shared copy of the row table: start steps,
+constexpr int ROW_ABASE = 2 * MAX_BATCH;   // first alignment row of the utterance ((u / B) * max_steps * B + u % B)
 
 // The persistent kernel's code (~165 KB) is far beyond the instruction caches and every warp walks it once per decode
 // step (ncu: sm__icc_request_hit_rate 72-84 %, stall_no_instruction up to 1.1 per issued instruction): what runs more than
@@ -148,7 +149,7 @@ struct Smem {
     static constexpr int OFF_XCH = OFF_MISC + 64 * 4;                          // tensor-core path: split-K partials of the
     static constexpr int XCH_BYTES = TC ? GS * ROWS_PER_CTA * BP * 4 : 0;      // four group members, written through DSMEM
     static constexpr int OFF_ROWS = OFF_XCH + XCH_BYTES;                       // tensor-core path: row table (utterance, start step)
-    static constexpr int TOTAL = OFF_ROWS + (TC ? 2 * MAX_BATCH * 4 : 0);
+    static constexpr int TOTAL = OFF_ROWS + (TC ? 3 * MAX_BATCH * 4 : 0);
     static_assert(TOTAL <= 227 * 1024, "shared memory budget");
     static_assert(STAGE_BYTES % 128 == 0 && W_BYTES % 128 == 0, "bulk copy alignment");
 };
@@ -594,8 +595,7 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
             fresh = step == st;
             oi = u >= 0 ? step - st - 1 : -1;
         }
-        const size_t align_row = rows != nullptr ? ((size_t)(mb / B) * p.max_steps + (oi < 0 ? 0 : oi)) * B + mb % B
-                                                 : (size_t)(oi < 0 ? 0 : oi) * B + b;
+        const size_t align_row = (size_t)(rows != nullptr ? rows[ROW_ABASE + b] : b) + (size_t)(oi < 0 ? 0 : oi) * B;
         consumer_sync();   // previous item's scratch is free
         const int ntiles = (n + TILE_POS - 1) / TILE_POS;
         // processed-memory tile 0: asynchronous copy, overlapped with the loads below
@@ -806,7 +806,8 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
                     const int t = t0 + i;
                     const float w = sc[P2Scratch::E + i] * mine / S;
                     prev_out[(size_t)b * p.Tp + t] = w;
-                    cum_out[(size_t)b * p.Tp + t] = (fresh ? 0.f : __ldcg(cum_in + (size_t)b * p.Tp + t)) + w;
+                    // cumulative weights of this slice are still in the window (zero for a fresh row): no reload from L2
+                    cum_out[(size_t)b * p.Tp + t] = sc[P2Scratch::WIN + P2Scratch::WIN_LEN + (LOC_K - 1) / 2 + i] + w;
                     if (oi >= 0) p.align[align_row * T + t] = w;
                 }
                 // context rows [sl * 512/NS, (sl+1) * 512/NS)
@@ -1626,8 +1627,11 @@ __global__ void __launch_bounds__(NT_TC, 1) decoder_tc_kernel(const KParams p) {
         if (streaming && tid >= NTC - MAX_BATCH && tid < NTC) {
             const int i = tid - (NTC - MAX_BATCH);
             if (i < B) {
-                rows_s[i] = s == 0 ? i : (int)__ldcg(p.ctrl + CTRL_UTT + i);
+                const int u = s == 0 ? i : (int)__ldcg(p.ctrl + CTRL_UTT + i);
+                rows_s[i] = u;
                 rows_s[ROW_START + i] = s == 0 ? 0 : (int)__ldcg(p.ctrl + CTRL_START + i);
+                const int ua = u >= 0 ? u : -1 - u;
+                rows_s[ROW_ABASE + i] = ua / B * p.max_steps * B + ua % B;
             }
         }
 
