@@ -267,9 +267,10 @@ def run_b200(args, rank, world, local_rank):
             "clocks": clocks,
             "roofline": {"kernel": "decoder_tc_kernel<32> (persistent, one cooperative cluster launch for the K batches)", "bound": "hbm",
                          "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch (1001 decode steps, B=32, T=150),
-                         # ncu --set full, profiles/r1_v8_decoder_ncu_full.md: the working set is L2 resident
-                         "traffic": 56_894_976, "traffic_unit": "bytes per launch (ncu, 1001-step launch)",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one continuous-batching launch (K=3 batches = 96
+                         # utterances, 2002 decode steps), ncu --set full, profiles/r1_v15_stream_decoder_ncu_full.md: 66.9 KB
+                         # of HBM traffic per decode step against 49.9 MB algorithmic - the working set is L2 resident
+                         "traffic": 133_841_152, "traffic_unit": "bytes per launch (ncu, launch of 96 utterances / 2002 decode steps)",
                          "peak_source": hbm_src, "bytes_per_decode_step": BYTES_PER_STEP_C2,
                          "decode_steps_per_launch": dec_steps / max(1, len(dec_events)), "us_per_decode_step": dec_ms * 1e3 / dec_steps,
                          "row_occupancy": (frames / world + args.steps * B) / (dec_steps * B),
