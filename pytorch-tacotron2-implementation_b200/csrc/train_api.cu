@@ -41,7 +41,12 @@ size_t attention_bwd_scratch_floats(int B, int T);
 int attention_bwd(const float* w, const float* prev, const float* cum, const float* pq, const float* pm, const float* memory,
                   const float* dctx, const float* dw_ext, const float* dprev_next, float* gsum, const int64_t* lengths,
                   const float* Wloc, const float* Wld, const float* v, const float* vb, const float* escale, float* dmemory,
-                  float* dpm, float* dpq, float* dprev_out, float* pacc, float* scratch, int B, int T, cudaStream_t st);
+                  float* dpm, float* dpq, float* dprev_out, float* pacc, float* scratch, float* dctx_out, int B, int T,
+                  cudaStream_t st);
+bool attention_bwd_defers_dmemory(int T);
+int skinny_gemm_multi(const float* X, int ldx, const float* W, int ldw, int B, int K, int nseg, float* const* outs, const int* ldos,
+                      const int* n_ends, const bool* acc, cudaStream_t st);
+int ctx_dmemory(const float* w, const float* dctx_all, float* dmemory, int S, int B, int T, cudaStream_t st);
 constexpr int ATTN_PACC_F = ATT_DIM * LOC_F + LOC_F * 2 * LOC_K + ATT_DIM + 64;
 int skinny_gemm(const float* X, int ldx, const float* W, int ldw, float* out, int ldo, int B, int K, int N, bool accumulate,
                 cudaStream_t st);
@@ -291,7 +296,7 @@ B200TACO_API int32_t b200taco_encoder_train_bwd(b200taco_handle* h, const b200ta
 // backward + data gradients.  Weight gradients are deferred to a few large reductions over all steps.
 namespace {
 struct DecScratch {
-    size_t dout, wpg, wqT, dzd, dza, dpq, dp, d_ah, d_dh, d_ctx, dca, dcd, tmp, tmp2, pq, P, gsum, cum, dpm, attn, dw, dvs, total;
+    size_t dout, wpg, wqT, dzd, dza, dpq, dp, d_ah, d_dh, d_ctx, dca, dcd, tmp, tmp2, pq, P, gsum, cum, dpm, attn, dw, dvs, wcat_d, wcat_a, dctx_all, total;
 };
 DecScratch dec_scratch(int B, int T, int S) {
     DecScratch d{};
@@ -320,6 +325,9 @@ DecScratch dec_scratch(int B, int T, int S) {
     d.attn = take(attention_bwd_scratch_floats(B, T));
     d.dw = take((size_t)4 * RNN * (RNN + EMB));   // largest [in][out] weight gradient (1536 x 4096)
     d.dvs = take((size_t)B * ATTN_PACC_F + ATTN_PACC_F);   // per-utterance attention parameter-gradient accumulators + their sum
+    d.wcat_d = take((size_t)4 * RNN * (2 * RNN + EMB));        // [W_ih | W_hh] of the decoder LSTM, [4096][2560]
+    d.wcat_a = take((size_t)4 * RNN * (PRENET + EMB + RNN));   // [W_ih | W_hh] of the attention LSTM, [4096][1792]
+    d.dctx_all = take(n * EMB);                   // d ctx_t of every step: the memory gradient is one contraction after the walk
     d.total = off;
     return d;
 }
@@ -349,7 +357,8 @@ B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200ta
     float *dout = sc + X.dout, *wpg = sc + X.wpg, *wqT = sc + X.wqT, *dzd = sc + X.dzd, *dza = sc + X.dza, *dpq = sc + X.dpq,
           *dp = sc + X.dp, *d_ah = sc + X.d_ah, *d_dh = sc + X.d_dh, *d_ctx = sc + X.d_ctx, *dca = sc + X.dca, *dcd = sc + X.dcd,
           *tmp = sc + X.tmp, *tmp2 = sc + X.tmp2, *pq = sc + X.pq, *P = sc + X.P, *gsum = sc + X.gsum, *cum = sc + X.cum,
-          *dpm = sc + X.dpm, *attn = sc + X.attn, *dw = sc + X.dw, *dvs = sc + X.dvs;
+          *dpm = sc + X.dpm, *attn = sc + X.attn, *dw = sc + X.dw, *dvs = sc + X.dvs, *dctx_all = sc + X.dctx_all, *wcat_d = sc + X.wcat_d,
+          *wcat_a = sc + X.wcat_a;
     const float *frames = d_saved + sv.frames, *y1 = d_saved + sv.y1, *y2 = d_saved + sv.y2, *pm = d_saved + sv.pm,
                 *ga = d_saved + sv.ga, *ca = d_saved + sv.ca, *ah = d_saved + sv.ah, *gd = d_saved + sv.gd, *cd = d_saved + sv.cd,
                 *dh = d_saved + sv.dh, *ctx = d_saved + sv.ctx;
@@ -364,6 +373,13 @@ B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200ta
     TT(assemble_wpg(w->proj_w, w->gate_w, wpg, st));
     TT(transpose2d(wqT, w->attn_query_w, ATT_DIM, RNN, st));                    // (128,1024) -> [1024][128]
     TT(attn_cumsum(d_align, cum, S, BT, st));
+    // [W_ih | W_hh] side by side: the three data gradients of a cell are one contraction over its gate gradients
+    constexpr int ND = 2 * RNN + EMB, NA = PRENET + EMB + RNN;
+    const size_t f4 = sizeof(float);
+    TACO_CUDA(cudaMemcpy2DAsync(wcat_d, ND * f4, w->dec_lstm_w_ih, (RNN + EMB) * f4, (RNN + EMB) * f4, 4 * RNN, cudaMemcpyDeviceToDevice, st));
+    TACO_CUDA(cudaMemcpy2DAsync(wcat_d + RNN + EMB, ND * f4, w->dec_lstm_w_hh, RNN * f4, RNN * f4, 4 * RNN, cudaMemcpyDeviceToDevice, st));
+    TACO_CUDA(cudaMemcpy2DAsync(wcat_a, NA * f4, w->attn_lstm_w_ih, (PRENET + EMB) * f4, (PRENET + EMB) * f4, 4 * RNN, cudaMemcpyDeviceToDevice, st));
+    TACO_CUDA(cudaMemcpy2DAsync(wcat_a + PRENET + EMB, NA * f4, w->attn_lstm_w_hh, RNN * f4, RNN * f4, 4 * RNN, cudaMemcpyDeviceToDevice, st));
     TACO_CUDA(cudaMemsetAsync(d_ah, 0, (X.tmp - X.d_ah) * sizeof(float), st));  // d_ah, d_dh, d_ctx, dca, dcd
     TACO_CUDA(cudaMemsetAsync(gsum, 0, (size_t)BT * sizeof(float), st));
     TACO_CUDA(cudaMemsetAsync(dpm, 0, (size_t)BT * ATT_DIM * sizeof(float), st));
@@ -376,29 +392,39 @@ B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200ta
         // projections (src/model.py:272-274): proj_in = [dh_t | ctx_t]; the partial products are added straight onto the
         // carried gradients (split-K skinny GEMMs, B <= 64 rows)
         const float* dout_t = dout + r * PROJ_PAD;
-        TT(skinny_gemm(dout_t, PROJ_PAD, wpg, RNN + EMB, d_dh, RNN, B, PROJ_PAD, RNN, true, st));
-        TT(skinny_gemm(dout_t, PROJ_PAD, wpg + RNN, RNN + EMB, d_ctx, EMB, B, PROJ_PAD, EMB, true, st));
+        {
+            float* outs[2] = {d_dh, d_ctx};
+            const int ldos[2] = {RNN, EMB}, ends[2] = {RNN, RNN + EMB};
+            const bool acc[2] = {true, true};
+            TT(skinny_gemm_multi(dout_t, PROJ_PAD, wpg, RNN + EMB, B, PROJ_PAD, 2, outs, ldos, ends, acc, st));
+        }
         // decoder LSTM cell (input [ah_t | ctx_t], src/model.py:265-270)
         float* dzd_t = dzd + r * 4 * RNN;
         TT(lstm_cell_bwd(gd + r * 4 * RNN, cd + r * RNN, t > 0 ? cd + (r - B) * RNN : nullptr, d_dh, d_mask_d ? d_mask_d + r * RNN : nullptr,
                          lstm_scale, dcd, dzd_t, B, st));
-        TT(skinny_gemm(dzd_t, 4 * RNN, w->dec_lstm_w_ih, RNN + EMB, d_ah, RNN, B, 4 * RNN, RNN, true, st));
-        TT(skinny_gemm(dzd_t, 4 * RNN, w->dec_lstm_w_ih + RNN, RNN + EMB, d_ctx, EMB, B, 4 * RNN, EMB, true, st));
-        TT(skinny_gemm(dzd_t, 4 * RNN, w->dec_lstm_w_hh, RNN, d_dh, RNN, B, 4 * RNN, RNN, false, st));       // -> d dh_{t-1}
+        {   // d ah_t +=, d ctx_t +=, d dh_{t-1} =
+            float* outs[3] = {d_ah, d_ctx, d_dh};
+            const int ldos[3] = {RNN, EMB, RNN}, ends[3] = {RNN, RNN + EMB, ND};
+            const bool acc[3] = {true, true, false};
+            TT(skinny_gemm_multi(dzd_t, 4 * RNN, wcat_d, ND, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
+        }
         // attention (src/model.py:117-148)
         TT(skinny_gemm(ah + r * RNN, RNN, wqT, ATT_DIM, pq, ATT_DIM, B, RNN, ATT_DIM, false, st));
         TT(attention_bwd(d_align + r * T, t > 0 ? d_align + (r - B) * T : nullptr, cum + r * T, pq, pm, d_memory, d_ctx,
                          d_dalign ? d_dalign + r * T : nullptr, t < S - 1 ? P + (size_t)((t + 1) & 1) * BT : nullptr, gsum,
                          d_text_lengths, w->attn_loc_conv_w, w->attn_loc_dense_w, w->attn_v_w, w->attn_v_b, w->attn_energy_scale,
-                         d_dmemory, dpm, dpq + r * ATT_DIM, P + (size_t)(t & 1) * BT, dvs, attn, B, T, st));
+                         d_dmemory, dpm, dpq + r * ATT_DIM, P + (size_t)(t & 1) * BT, dvs, attn, dctx_all + r * EMB, B, T, st));
         TT(skinny_gemm(dpq + r * ATT_DIM, ATT_DIM, w->attn_query_w, RNN, d_ah, RNN, B, ATT_DIM, RNN, true, st));
         // attention LSTM cell (input [p_t | ctx_{t-1}], src/model.py:256-262)
         float* dza_t = dza + r * 4 * RNN;
         TT(lstm_cell_bwd(ga + r * 4 * RNN, ca + r * RNN, t > 0 ? ca + (r - B) * RNN : nullptr, d_ah, d_mask_a ? d_mask_a + r * RNN : nullptr,
                          lstm_scale, dca, dza_t, B, st));
-        TT(skinny_gemm(dza_t, 4 * RNN, w->attn_lstm_w_ih, PRENET + EMB, dp + r * PRENET, PRENET, B, 4 * RNN, PRENET, false, st));
-        TT(skinny_gemm(dza_t, 4 * RNN, w->attn_lstm_w_ih + PRENET, PRENET + EMB, d_ctx, EMB, B, 4 * RNN, EMB, false, st));   // -> d ctx_{t-1}
-        TT(skinny_gemm(dza_t, 4 * RNN, w->attn_lstm_w_hh, RNN, d_ah, RNN, B, 4 * RNN, RNN, false, st));     // -> d ah_{t-1}
+        {   // d p_t =, d ctx_{t-1} =, d ah_{t-1} =
+            float* outs[3] = {dp + r * PRENET, d_ctx, d_ah};
+            const int ldos[3] = {PRENET, EMB, RNN}, ends[3] = {PRENET, PRENET + EMB, NA};
+            const bool acc[3] = {false, false, false};
+            TT(skinny_gemm_multi(dza_t, 4 * RNN, wcat_a, NA, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
+        }
     }
 
     // ---- weight gradients: reductions over all steps, computed as [in][out] and transposed into the parameter layout
@@ -446,6 +472,9 @@ B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200ta
         TACO_CUDA(cudaMemcpyAsync(G(grads->attn_energy_scale), tot + ATT_DIM * LOC_F + LOC_F * 2 * LOC_K + ATT_DIM + 1, f,
                                   cudaMemcpyDeviceToDevice, st));
     }
+    // context (src/model.py:147): dmemory[b][tau][:] = sum_t w_t[b][tau] * dctx_t[b][:], one [T x S] . [S x 512] contraction per
+    // utterance when the attention backward deferred it
+    if (attention_bwd_defers_dmemory(T)) TT(ctx_dmemory(d_align, dctx_all, d_dmemory, S, B, T, st));
     // memory layer (128 x 512): pm = memory . W^T
     TT(wgrad_into(d_memory, EMB, EMB, dpm, ATT_DIM, ATT_DIM, BT, G(grads->attn_memory_w), EMB));
     TT(dense(dpm, ATT_DIM, w->attn_memory_w, d_dmemory, EMB, BT, ATT_DIM, EMB, d_dmemory));               // dmemory += dpm . W

@@ -1,6 +1,8 @@
 // Backward-pass kernels of the teacher-forced decoder (reference Decoder.forward / _decode_step in train mode,
 // src/model.py:246-297; LocationSensitiveAttention :117-148).  First correct fp32 versions: the host walks the decode
 // steps in reverse and launches these kernels plus dense-layer calls per step (train_api.cu).
+#include <cstdlib>
+
 #include "handle.h"
 
 namespace b200taco {
@@ -286,11 +288,307 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(
     }
 }
 
+// ---- attention backward of ONE decode step, second version: one CTA of 512 threads per utterance, every intermediate
+// (attention windows, location features and their gradients) in SHARED memory, per-thread register accumulators for the
+// parameter gradients, no atomics.  The memory gradient  dmemory[b][tau][:] = sum_t w_t[tau] * dctx_t[:]  is NOT accumulated
+// here (it was a 2 x 19.6 MB read-modify-write per step at B=64): the kernel stores dctx_t into dctx_all[t] and the host
+// contracts  align^T . dctx_all  once per utterance after the walk.  T <= ATTN_V2_MAX_T (shared-memory budget).
+constexpr int ATTN_V2_NT = 512, ATTN_V2_NW = ATTN_V2_NT / 32, ATTN_V2_MAX_T = 320;
+constexpr int LOC_LD = LOC_F + 1;                       // row stride of loc / dloc / Wld tiles: conflict-free both ways
+constexpr int WLOC_LD = 2 * LOC_K + 1;                  // row stride of the location-conv weights (odd)
+__host__ __device__ constexpr int attn_v2_smem_floats(int T) {
+    return EMB + LOC_F * WLOC_LD + ATT_DIM * LOC_LD + 4 * ATT_DIM + 2 * (T + LOC_K - 1) + 2 * T + 2 * T * LOC_LD +
+           ATTN_V2_NW * ATT_DIM + 2 * ATTN_V2_NW * ATT_DIM + ATTN_V2_NT;
+}
+__global__ void __launch_bounds__(ATTN_V2_NT) attention_bwd_v2_kernel(
+    const float* __restrict__ w, const float* __restrict__ prev, const float* __restrict__ cum, const float* __restrict__ pq,
+    const float* __restrict__ pm, const float* __restrict__ memory, const float* __restrict__ dctx,
+    const float* __restrict__ dw_ext, const float* __restrict__ dprev_next, float* __restrict__ gsum,
+    const int64_t* __restrict__ lengths, const float* __restrict__ Wloc, const float* __restrict__ Wld,
+    const float* __restrict__ v, const float* __restrict__ vb_p, const float* __restrict__ escale_p,
+    float* __restrict__ dctx_out /* [B][512]: this step's slice of dctx_all */, float* __restrict__ dpm,
+    float* __restrict__ dpq, float* __restrict__ dprev_out, float* __restrict__ pacc, int B, int T) {
+    extern __shared__ __align__(16) float sm[];
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int len = lengths ? (int)lengths[b] : T;
+    const float vb = vb_p[0], escale = escale_p[0];
+    constexpr int HALO = (LOC_K - 1) / 2;
+    const int WL = T + LOC_K - 1;
+    float* dctx_s = sm;
+    float* wloc_s = dctx_s + EMB;
+    float* wld_s = wloc_s + LOC_F * WLOC_LD;
+    float* v_s = wld_s + ATT_DIM * LOC_LD;
+    float* pq_s = v_s + ATT_DIM;
+    float* win_p = pq_s + ATT_DIM + 2 * ATT_DIM;       // (two spare rows kept for alignment of the layout)
+    float* win_c = win_p + WL;
+    float* w_s = win_c + WL;
+    float* dw_s = w_s + T;
+    float* loc_s = dw_s + T;
+    float* dloc_s = loc_s + T * LOC_LD;
+    float* tile_du = dloc_s + T * LOC_LD;              // [NW][128]
+    float* accx = tile_du + ATTN_V2_NW * ATT_DIM;      // [2][NW][128]: dv / dpq partials of the warps
+    float* red_s = accx + 2 * ATTN_V2_NW * ATT_DIM;    // [NT]
+    float* dWld = pacc + (size_t)b * ATTN_PACC;        // only this CTA ever touches slice b: plain read-modify-write
+    float* dWloc = dWld + ATT_DIM * LOC_F;
+    float* dv = dWloc + LOC_F * 2 * LOC_K;
+    float* dvb_scale = dv + ATT_DIM;
+    const float* wb = w + (size_t)b * T;
+    const float* pb = prev ? prev + (size_t)b * T : nullptr;
+    const float* cb = cum + (size_t)b * T;
+
+    for (int i = tid; i < EMB; i += ATTN_V2_NT) {
+        const float d = dctx[(size_t)b * EMB + i];
+        dctx_s[i] = d;
+        dctx_out[(size_t)b * EMB + i] = d;
+    }
+    for (int i = tid; i < LOC_F * 2 * LOC_K; i += ATTN_V2_NT) wloc_s[(i / (2 * LOC_K)) * WLOC_LD + i % (2 * LOC_K)] = Wloc[i];
+    for (int i = tid; i < ATT_DIM * LOC_F; i += ATTN_V2_NT) wld_s[(i / LOC_F) * LOC_LD + (i % LOC_F)] = Wld[i];
+    if (tid < ATT_DIM) { v_s[tid] = v[tid]; pq_s[tid] = pq[(size_t)b * ATT_DIM + tid]; }
+    for (int i = tid; i < WL; i += ATTN_V2_NT) {
+        const int t = i - HALO;
+        const bool ok = t >= 0 && t < T;
+        win_p[i] = ok && pb ? pb[t] : 0.f;
+        win_c[i] = ok ? cb[t] : 0.f;
+    }
+    for (int i = tid; i < T; i += ATTN_V2_NT) w_s[i] = wb[i];
+    __syncthreads();
+
+    // (a) dw[tau] = dctx . memory[tau] + external terms ; s = sum_tau w dw.  One warp per position, two positions in flight.
+    float s_part = 0.f;
+    for (int tau0 = 2 * warp; tau0 < T; tau0 += 2 * ATTN_V2_NW) {
+        float4 m[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int tau = tau0 + r < T ? tau0 + r : tau0;
+            const float4* mrow = reinterpret_cast<const float4*>(memory + ((size_t)b * T + tau) * EMB);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) m[r][q] = __ldg(mrow + lane + 32 * q);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float acc = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 d = *reinterpret_cast<const float4*>(dctx_s + 4 * (lane + 32 * q));
+                acc = fmaf(d.x, m[r][q].x, acc); acc = fmaf(d.y, m[r][q].y, acc);
+                acc = fmaf(d.z, m[r][q].z, acc); acc = fmaf(d.w, m[r][q].w, acc);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            const int tau = tau0 + r;
+            if (lane == 0 && tau < T) {
+                const float d = acc + (dw_ext ? dw_ext[(size_t)b * T + tau] : 0.f) +
+                                (dprev_next ? dprev_next[(size_t)b * T + tau] : 0.f) + gsum[(size_t)b * T + tau];
+                dw_s[tau] = d;
+                s_part += w_s[tau] * d;
+            }
+        }
+    }
+    red_s[tid] = s_part;
+    // (b) location conv recomputed from the windows: loc[tau][f] = sum_c sum_k Wloc[f][c][k] * in_c[tau + k - 15]
+    for (int i = tid; i < T * LOC_F; i += ATTN_V2_NT) {
+        const int tau = i >> 5, f = i & 31;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < LOC_K; ++k) {
+            acc = fmaf(wloc_s[f * WLOC_LD + k], win_p[tau + k], acc);
+            acc = fmaf(wloc_s[f * WLOC_LD + LOC_K + k], win_c[tau + k], acc);
+        }
+        loc_s[tau * LOC_LD + f] = acc;
+    }
+    __syncthreads();
+    for (int o = ATTN_V2_NT / 2; o > 0; o >>= 1) {
+        if (tid < o) red_s[tid] += red_s[tid + o];
+        __syncthreads();
+    }
+    const float s_all = red_s[0];
+    __syncthreads();
+
+    // (c) per position (one warp each, lane = 4 attention dims): de -> du, dpm, partial dv / dpq / dvb / dscale;
+    //     dloc[tau][f] = sum_a du[a] Wld[a][f]; dWld[a][f] += du[tau][a] loc[tau][f] (register accumulators, 8 per thread)
+    float dvb_part = 0.f, dscale_part = 0.f;
+    float dv_r[4] = {0.f, 0.f, 0.f, 0.f}, dpq_r[4] = {0.f, 0.f, 0.f, 0.f};
+    float dwld_r[ATT_DIM * LOC_F / ATTN_V2_NT];
+#pragma unroll
+    for (int i = 0; i < ATT_DIM * LOC_F / ATTN_V2_NT; ++i) dwld_r[i] = 0.f;
+    for (int t0 = 0; t0 < T; t0 += ATTN_V2_NW) {
+        const int tau = t0 + warp;
+        float* du_row = tile_du + warp * ATT_DIM;
+        if (tau < T) {
+            float th[4], pmv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pmv[q] = __ldg(pm + ((size_t)b * T + tau) * ATT_DIM + lane + 32 * q);
+            float e_raw_part = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int a = lane + 32 * q;
+                float lf = 0.f;
+#pragma unroll
+                for (int f = 0; f < LOC_F; ++f) lf = fmaf(wld_s[a * LOC_LD + f], loc_s[tau * LOC_LD + f], lf);
+                th[q] = tanhf(pq_s[a] + pmv[q] + lf);
+                e_raw_part = fmaf(v_s[a], th[q], e_raw_part);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) e_raw_part += __shfl_xor_sync(0xffffffffu, e_raw_part, o);
+            const float e_raw = e_raw_part + vb;
+            // softmax backward; masked positions (energy filled with -1e9, src/model.py:132) pass no gradient
+            const float de = tau < len ? w_s[tau] * (dw_s[tau] - s_all) : 0.f;
+            const float de_raw = de * escale;
+            if (lane == 0) { dscale_part += de * e_raw; dvb_part += de_raw; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int a = lane + 32 * q;
+                const float du = de_raw * v_s[a] * (1.f - th[q] * th[q]);
+                du_row[a] = du;
+                float* dpm_p = dpm + ((size_t)b * T + tau) * ATT_DIM + a;
+                *dpm_p += du;
+                dv_r[q] = fmaf(de_raw, th[q], dv_r[q]);
+                dpq_r[q] += du;
+            }
+            __syncwarp();
+            float acc = 0.f;
+#pragma unroll 8
+            for (int a = 0; a < ATT_DIM; ++a) acc = fmaf(du_row[a], wld_s[a * LOC_LD + lane], acc);
+            dloc_s[tau * LOC_LD + lane] = acc;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) du_row[lane + 32 * q] = 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < ATT_DIM * LOC_F / ATTN_V2_NT; ++q) {
+            const int a = warp + ATTN_V2_NW * q;                  // entry (a, f = lane)
+            float acc = 0.f;
+#pragma unroll
+            for (int pp = 0; pp < ATTN_V2_NW; ++pp) {
+                const int tt = t0 + pp < T ? t0 + pp : T - 1;     // rows past T hold zeros in tile_du
+                acc = fmaf(tile_du[pp * ATT_DIM + a], loc_s[tt * LOC_LD + lane], acc);
+            }
+            dwld_r[q] += acc;
+        }
+        __syncthreads();
+    }
+    // warp partials of dv / dpq -> block sums
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        accx[warp * ATT_DIM + lane + 32 * q] = dv_r[q];
+        accx[(ATTN_V2_NW + warp) * ATT_DIM + lane + 32 * q] = dpq_r[q];
+    }
+    red_s[tid] = dvb_part;
+    __syncthreads();
+    if (tid < 2 * ATT_DIM) {
+        const int which = tid / ATT_DIM, a = tid % ATT_DIM;
+        float acc = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < ATTN_V2_NW; ++ww) acc += accx[(which * ATTN_V2_NW + ww) * ATT_DIM + a];
+        if (which == 0) dv[a] += acc;
+        else dpq[(size_t)b * ATT_DIM + a] = acc;
+    }
+    // dvb / dscale are produced by lane 0 of every warp only
+    if (tid == 0) {
+        float acc = 0.f;
+        for (int ww = 0; ww < ATTN_V2_NW; ++ww) acc += red_s[ww * 32];
+        dvb_scale[0] += acc;
+    }
+    __syncthreads();
+    red_s[tid] = dscale_part;
+    __syncthreads();
+    if (tid == 0) {
+        float acc = 0.f;
+        for (int ww = 0; ww < ATTN_V2_NW; ++ww) acc += red_s[ww * 32];
+        dvb_scale[1] += acc;
+    }
+#pragma unroll
+    for (int q = 0; q < ATT_DIM * LOC_F / ATTN_V2_NT; ++q) dWld[(warp + ATTN_V2_NW * q) * LOC_F + lane] += dwld_r[q];
+
+    // (d) location conv backward: dWloc[f][c][k] += sum_tau dloc[tau][f] * in_c[tau + k - 15]
+    for (int i = tid; i < LOC_F * 2 * LOC_K; i += ATTN_V2_NT) {
+        const int k = i % LOC_K, c = (i / LOC_K) % 2, f = i / (2 * LOC_K);
+        const float* win = c == 0 ? win_p : win_c;
+        float acc = 0.f;
+#pragma unroll 4
+        for (int tau = 0; tau < T; ++tau) acc = fmaf(dloc_s[tau * LOC_LD + f], win[tau + k], acc);
+        dWloc[i] += acc;
+    }
+    //     d in_c[tt] = sum_k sum_f dloc[tt - k + 15][f] * Wloc[f][c][k]
+    for (int i = tid; i < 2 * T; i += ATTN_V2_NT) {
+        const int c = i / T, tt = i % T;
+        float acc = 0.f;
+        for (int k = 0; k < LOC_K; ++k) {
+            const int tau = tt - k + HALO;
+            if (tau >= 0 && tau < T) {
+                const float* dl = dloc_s + tau * LOC_LD;
+                const float* wl = wloc_s + c * LOC_K + k;
+#pragma unroll 8
+                for (int f = 0; f < LOC_F; ++f) acc = fmaf(dl[f], wl[f * WLOC_LD], acc);
+            }
+        }
+        if (c == 0) dprev_out[(size_t)b * T + tt] = acc;
+        else gsum[(size_t)b * T + tt] += acc;
+    }
+}
+
+// Deferred context gradient (src/model.py:147): dmemory[b][tau][d] = sum_s w[s][b][tau] * dctx[s][b][d], one 64 x 64 tile of
+// (tau, d) per CTA, all S steps reduced in the CTA (plain stores, no atomics).  w (S,B,T), dctx (S,B,512), dmemory (B,T,512).
+__global__ void __launch_bounds__(256) ctx_dmemory_kernel(const float* __restrict__ w, const float* __restrict__ dctx,
+                                                          float* __restrict__ dmemory, int S, int B, int T) {
+    __shared__ __align__(16) float Ws[16][64 + 4];
+    __shared__ __align__(16) float Ds[16][64 + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int t0 = blockIdx.x * 64, d0 = blockIdx.y * 64, b = blockIdx.z;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int lr = tid >> 4, lc = (tid & 15) * 4;
+    for (int sb = 0; sb < S; sb += 16) {
+        const int sidx = sb + lr;
+        float4 wv = make_float4(0.f, 0.f, 0.f, 0.f), dv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sidx < S) {
+            const float* wrow = w + ((size_t)sidx * B + b) * T;          // rows are not 16-byte aligned in general
+            const int t = t0 + lc;
+            if (t < T) wv.x = wrow[t];
+            if (t + 1 < T) wv.y = wrow[t + 1];
+            if (t + 2 < T) wv.z = wrow[t + 2];
+            if (t + 3 < T) wv.w = wrow[t + 3];
+            dv = *reinterpret_cast<const float4*>(dctx + ((size_t)sidx * B + b) * EMB + d0 + lc);
+        }
+        *reinterpret_cast<float4*>(&Ws[lr][lc]) = wv;
+        *reinterpret_cast<float4*>(&Ds[lr][lc]) = dv;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&Ws[k][4 * ty]);
+            const float4 c = *reinterpret_cast<const float4*>(&Ds[k][4 * tx]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], cv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int t = t0 + 4 * ty + i;
+        if (t < T)
+            *reinterpret_cast<float4*>(dmemory + ((size_t)b * T + t) * EMB + d0 + 4 * tx) =
+                make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+}
+
 // out[b][n] += sum_k X[b][k] * W[k][n] for b < B <= 64: one 64 x 64 output tile per (blockIdx.x, K split blockIdx.y),
 // partial sums added atomically (out must hold the values to accumulate onto, e.g. zeros)
+// Column ranges of the product may go to different destinations (one launch for all contractions that share X, e.g. the
+// three data gradients of an LSTM cell): segment i covers columns [n_end[i-1], n_end[i]), boundaries are multiples of 64.
+struct SkinnyOut {
+    float* out[3];
+    int ldo[3];
+    int n_end[3];
+};
 __global__ void __launch_bounds__(256) skinny_gemm_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W,
-                                                          int ldw, float* __restrict__ out, int ldo, int B, int K, int N,
-                                                          int k_per) {
+                                                          int ldw, const SkinnyOut so, int B, int K, int N, int k_per) {
     __shared__ __align__(16) float Xs[16][64 + 4];
     __shared__ __align__(16) float Ws[16][64];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -328,6 +626,10 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(const float* __restric
         }
         __syncthreads();
     }
+    const int seg = n0 < so.n_end[0] ? 0 : (n0 < so.n_end[1] ? 1 : 2);
+    const int nb = seg == 0 ? 0 : so.n_end[seg - 1];
+    float* out = so.out[seg];
+    const int ldo = so.ldo[seg];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int b = 4 * ty + i;
@@ -335,7 +637,7 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(const float* __restric
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + 4 * tx + j;
-            if (n < N) atomicAdd(out + (size_t)b * ldo + n, acc[i][j]);
+            if (n < N) atomicAdd(out + (size_t)b * ldo + (n - nb), acc[i][j]);
         }
     }
 }
@@ -372,18 +674,38 @@ __global__ void assemble_wpg_kernel(const float* __restrict__ wp, const float* _
 }  // namespace
 
 // out (+)= X . W ; X [B][K] (ldx), W [K][N] (ldw), out [B][N] (ldo), B <= 64, K % 16 == 0, N % 4 == 0
-int skinny_gemm(const float* X, int ldx, const float* W, int ldw, float* out, int ldo, int B, int K, int N, bool accumulate,
-                cudaStream_t st) {
-    TACO_REQUIRE(B <= 64 && K % 16 == 0 && N % 4 == 0 && ldx % 4 == 0 && ldw % 4 == 0, B200TACO_ERR_INVALID,
-                 "skinny_gemm: unsupported shape B %d K %d N %d", B, K, N);
-    if (!accumulate) TACO_CUDA(cudaMemset2DAsync(out, (size_t)ldo * sizeof(float), 0, (size_t)N * sizeof(float), B, st));
+// out_i[b][n - n_begin_i] (+)= sum_k X[b][k] * W[k][n] for the column segments [n_begin_i, n_end_i) of one [K][N] matrix:
+// up to three destinations, each accumulated onto (acc[i]) or overwritten; n_end[nseg-1] = N.
+int skinny_gemm_multi(const float* X, int ldx, const float* W, int ldw, int B, int K, int nseg, float* const* outs, const int* ldos,
+                      const int* n_ends, const bool* acc, cudaStream_t st) {
+    const int N = n_ends[nseg - 1];
+    TACO_REQUIRE(B <= 64 && K % 16 == 0 && N % 4 == 0 && ldx % 4 == 0 && ldw % 4 == 0 && nseg >= 1 && nseg <= 3,
+                 B200TACO_ERR_INVALID, "skinny_gemm: unsupported shape B %d K %d N %d", B, K, N);
+    SkinnyOut so{};
+    for (int i = 0; i < 3; ++i) {
+        const int j = i < nseg ? i : nseg - 1;
+        so.out[i] = outs[j]; so.ldo[i] = ldos[j]; so.n_end[i] = i < nseg ? n_ends[i] : N;
+        if (i < nseg) {
+            const int nb = i == 0 ? 0 : n_ends[i - 1];
+            TACO_REQUIRE(i == nseg - 1 || n_ends[i] % 64 == 0, B200TACO_ERR_INVALID, "skinny_gemm: segment boundary %d", n_ends[i]);
+            if (!acc[i])
+                TACO_CUDA(cudaMemset2DAsync(outs[i], (size_t)ldos[i] * sizeof(float), 0, (size_t)(n_ends[i] - nb) * sizeof(float), B, st));
+        }
+    }
     const int ntiles = (N + 63) / 64;
     int ks = 1;
     while (ntiles * ks < 128 && K / (ks * 2) >= 64) ks *= 2;
     const int k_per = ((K + ks - 1) / ks + 15) / 16 * 16;
-    skinny_gemm_kernel<<<dim3(ntiles, (K + k_per - 1) / k_per), 256, 0, st>>>(X, ldx, W, ldw, out, ldo, B, K, N, k_per);
+    skinny_gemm_kernel<<<dim3(ntiles, (K + k_per - 1) / k_per), 256, 0, st>>>(X, ldx, W, ldw, so, B, K, N, k_per);
     TACO_LAUNCHED();
     return B200TACO_OK;
+}
+int skinny_gemm(const float* X, int ldx, const float* W, int ldw, float* out, int ldo, int B, int K, int N, bool accumulate,
+                cudaStream_t st) {
+    float* outs[1] = {out};
+    const int ldos[1] = {ldo}, n_ends[1] = {N};
+    const bool acc[1] = {accumulate};
+    return skinny_gemm_multi(X, ldx, W, ldw, B, K, 1, outs, ldos, n_ends, acc, st);
 }
 
 int transpose_block(float* dst, int ldd, const float* src, int lds, int R, int C, cudaStream_t st) {
@@ -429,10 +751,34 @@ int relu_drop_fwd(float* y, const float* mask, float scale, size_t n, cudaStream
     return B200TACO_OK;
 }
 size_t attention_bwd_scratch_floats(int B, int T) { return (size_t)B * T * (2 * LOC_F + 1 + 2 * LOC_K); }
+// the shared-memory version is used whenever the utterance fits (T <= 320); it defers the memory gradient (dctx_t is stored
+// to dctx_out, see attention_bwd_v2_kernel) - attention_bwd_defers_dmemory tells the caller which contract applies
+bool attention_bwd_defers_dmemory(int T) {
+    static const bool off = [] { const char* e = getenv("TACO_ATTN_BWD_V1"); return e && e[0] == '1'; }();
+    return !off && T <= ATTN_V2_MAX_T;
+}
+int ctx_dmemory(const float* w, const float* dctx_all, float* dmemory, int S, int B, int T, cudaStream_t st) {
+    ctx_dmemory_kernel<<<dim3((T + 63) / 64, EMB / 64, B), 256, 0, st>>>(w, dctx_all, dmemory, S, B, T);
+    TACO_LAUNCHED();
+    return B200TACO_OK;
+}
 int attention_bwd(const float* w, const float* prev, const float* cum, const float* pq, const float* pm, const float* memory,
                   const float* dctx, const float* dw_ext, const float* dprev_next, float* gsum, const int64_t* lengths,
                   const float* Wloc, const float* Wld, const float* v, const float* vb, const float* escale, float* dmemory, float* dpm,
-                  float* dpq, float* dprev_out, float* pacc, float* scratch, int B, int T, cudaStream_t st) {
+                  float* dpq, float* dprev_out, float* pacc, float* scratch, float* dctx_out, int B, int T, cudaStream_t st) {
+    if (attention_bwd_defers_dmemory(T)) {
+        const int smem = attn_v2_smem_floats(T) * (int)sizeof(float);
+        static bool configured = false;
+        if (!configured) {
+            TACO_CUDA(cudaFuncSetAttribute(attention_bwd_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           attn_v2_smem_floats(ATTN_V2_MAX_T) * (int)sizeof(float)));
+            configured = true;
+        }
+        attention_bwd_v2_kernel<<<B, ATTN_V2_NT, smem, st>>>(w, prev, cum, pq, pm, memory, dctx, dw_ext, dprev_next, gsum, lengths,
+                                                            Wloc, Wld, v, vb, escale, dctx_out, dpm, dpq, dprev_out, pacc, B, T);
+        TACO_LAUNCHED();
+        return B200TACO_OK;
+    }
     attention_bwd_kernel<<<B, 256, 0, st>>>(w, prev, cum, pq, pm, memory, dctx, dw_ext, dprev_next, gsum, lengths, Wloc, Wld, v, vb,
                                             escale, dmemory, dpm, dpq, dprev_out, pacc, scratch, B, T);
     TACO_LAUNCHED();
