@@ -32,14 +32,14 @@ int bilstm_train_bwd(const float* whh_f, const float* whh_b, const float* d_out,
 int embedding_bwd(const int64_t* ids, const float* dx, float* dE, int n, cudaStream_t st);
 
 // train_decoder.cu
-int lstm_cell_bwd(const float* gates, const float* c, const float* c_prev, const float* dh_post, const float* mask, float scale,
+int lstm_cell_bwd(const float* gates, const float* c, const float* c_prev, float* dh_post, const float* mask, float scale,
                   float* dc, float* dz, int B, cudaStream_t st);
 int attn_cumsum(const float* align, float* cum, int S, int BT, cudaStream_t st);
 int train_axpy(float* dst, int ld_dst, const float* a, int ld_a, int n, int cols, bool accumulate, cudaStream_t st);
 int relu_drop_bwd(const float* dy, const float* y, const float* mask, float scale, float* dx, size_t n, cudaStream_t st);
 size_t attention_bwd_scratch_floats(int B, int T);
 int attention_bwd(const float* w, const float* prev, const float* cum, const float* pq, const float* pm, const float* memory,
-                  const float* dctx, const float* dw_ext, const float* dprev_next, float* gsum, const int64_t* lengths,
+                  float* dctx, const float* dw_ext, const float* dprev_next, float* gsum, const int64_t* lengths,
                   const float* Wloc, const float* Wld, const float* v, const float* vb, const float* escale, float* dmemory,
                   float* dpm, float* dpq, float* dprev_out, float* pacc, float* scratch, float* dctx_out, int B, int T,
                   cudaStream_t st);
@@ -317,7 +317,7 @@ DecScratch dec_scratch(int B, int T, int S) {
     d.dcd = take((size_t)B * RNN);
     d.tmp = take((size_t)B * (RNN + EMB));
     d.tmp2 = take((size_t)B * RNN);
-    d.pq = take((size_t)B * ATT_DIM);
+    d.pq = take(n * ATT_DIM);                     // processed queries of all steps (recomputed once: ah . Wq^T)
     d.P = take((size_t)2 * B * T);
     d.gsum = take((size_t)B * T);
     d.cum = take(n * T);
@@ -381,6 +381,12 @@ B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200ta
     TACO_CUDA(cudaMemcpy2DAsync(wcat_a, NA * f4, w->attn_lstm_w_ih, (PRENET + EMB) * f4, (PRENET + EMB) * f4, 4 * RNN, cudaMemcpyDeviceToDevice, st));
     TACO_CUDA(cudaMemcpy2DAsync(wcat_a + PRENET + EMB, NA * f4, w->attn_lstm_w_hh, RNN * f4, RNN * f4, 4 * RNN, cudaMemcpyDeviceToDevice, st));
     TACO_CUDA(cudaMemsetAsync(d_ah, 0, (X.tmp - X.d_ah) * sizeof(float), st));  // d_ah, d_dh, d_ctx, dca, dcd
+    TACO_CUDA(cudaMemsetAsync(dp, 0, (size_t)n * PRENET * sizeof(float), st));   // the per-step GEMMs accumulate onto zeros
+    // processed queries (src/model.py:123) of all steps in one dense call instead of one skinny GEMM per step
+    TT(dense(ah, RNN, wqT, pq, ATT_DIM, n, RNN, ATT_DIM, nullptr));
+    // The consumers of the carried gradients (LSTM-cell backward: d ah / d dh; second attention backward: d ctx) zero them
+    // after reading, so the data-gradient GEMM that follows accumulates the previous step's gradient without a memset.
+    const bool v2 = attention_bwd_defers_dmemory(T);
     TACO_CUDA(cudaMemsetAsync(gsum, 0, (size_t)BT * sizeof(float), st));
     TACO_CUDA(cudaMemsetAsync(dpm, 0, (size_t)BT * ATT_DIM * sizeof(float), st));
     TACO_CUDA(cudaMemsetAsync(d_dmemory, 0, (size_t)BT * EMB * sizeof(float), st));
@@ -405,12 +411,11 @@ B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200ta
         {   // d ah_t +=, d ctx_t +=, d dh_{t-1} =
             float* outs[3] = {d_ah, d_ctx, d_dh};
             const int ldos[3] = {RNN, EMB, RNN}, ends[3] = {RNN, RNN + EMB, ND};
-            const bool acc[3] = {true, true, false};
+            const bool acc[3] = {true, true, true};
             TT(skinny_gemm_multi(dzd_t, 4 * RNN, wcat_d, ND, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
         }
         // attention (src/model.py:117-148)
-        TT(skinny_gemm(ah + r * RNN, RNN, wqT, ATT_DIM, pq, ATT_DIM, B, RNN, ATT_DIM, false, st));
-        TT(attention_bwd(d_align + r * T, t > 0 ? d_align + (r - B) * T : nullptr, cum + r * T, pq, pm, d_memory, d_ctx,
+        TT(attention_bwd(d_align + r * T, t > 0 ? d_align + (r - B) * T : nullptr, cum + r * T, pq + r * ATT_DIM, pm, d_memory, d_ctx,
                          d_dalign ? d_dalign + r * T : nullptr, t < S - 1 ? P + (size_t)((t + 1) & 1) * BT : nullptr, gsum,
                          d_text_lengths, w->attn_loc_conv_w, w->attn_loc_dense_w, w->attn_v_w, w->attn_v_b, w->attn_energy_scale,
                          d_dmemory, dpm, dpq + r * ATT_DIM, P + (size_t)(t & 1) * BT, dvs, attn, dctx_all + r * EMB, B, T, st));
@@ -422,7 +427,7 @@ B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200ta
         {   // d p_t =, d ctx_{t-1} =, d ah_{t-1} =
             float* outs[3] = {dp + r * PRENET, d_ctx, d_ah};
             const int ldos[3] = {PRENET, EMB, RNN}, ends[3] = {PRENET, PRENET + EMB, NA};
-            const bool acc[3] = {false, false, false};
+            const bool acc[3] = {true, v2, true};
             TT(skinny_gemm_multi(dza_t, 4 * RNN, wcat_a, NA, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
         }
     }

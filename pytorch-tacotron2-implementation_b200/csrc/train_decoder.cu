@@ -17,7 +17,7 @@ inline int blocks_for(size_t n) { return (int)((n + 255) / 256 > 4096 ? 4096 : (
 // c_prev [B][1024] or null (zero state), dh_post [B][1024] = gradient w.r.t. the (dropped) hidden state, mask or null,
 // dc [B][1024] carried cell gradient (in/out), dz [B][4096] gradient w.r.t. the gate pre-activations (out).
 __global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c, const float* __restrict__ c_prev,
-                                     const float* __restrict__ dh_post, const float* __restrict__ mask, float scale,
+                                     float* __restrict__ dh_post, const float* __restrict__ mask, float scale,
                                      float* __restrict__ dc, float* __restrict__ dz, int B) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * RNN) return;
@@ -25,6 +25,7 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, const floa
     const float* g4 = gates + (size_t)b * 4 * RNN + u;
     const float gi = g4[0], gf = g4[RNN], gg = g4[2 * RNN], go = g4[3 * RNN];
     const float dh = dh_post[i] * (mask ? mask[i] * scale : 1.f);
+    dh_post[i] = 0.f;          // consumed: the data-gradient GEMM that follows accumulates the previous step's gradient onto it
     const float tc = tanhf(c[i]);
     const float dct = dc[i] + dh * go * (1.f - tc * tc);
     const float cp = c_prev ? c_prev[i] : 0.f;
@@ -302,7 +303,7 @@ __host__ __device__ constexpr int attn_v2_smem_floats(int T) {
 }
 __global__ void __launch_bounds__(ATTN_V2_NT) attention_bwd_v2_kernel(
     const float* __restrict__ w, const float* __restrict__ prev, const float* __restrict__ cum, const float* __restrict__ pq,
-    const float* __restrict__ pm, const float* __restrict__ memory, const float* __restrict__ dctx,
+    const float* __restrict__ pm, const float* __restrict__ memory, float* __restrict__ dctx,
     const float* __restrict__ dw_ext, const float* __restrict__ dprev_next, float* __restrict__ gsum,
     const int64_t* __restrict__ lengths, const float* __restrict__ Wloc, const float* __restrict__ Wld,
     const float* __restrict__ v, const float* __restrict__ vb_p, const float* __restrict__ escale_p,
@@ -340,6 +341,7 @@ __global__ void __launch_bounds__(ATTN_V2_NT) attention_bwd_v2_kernel(
         const float d = dctx[(size_t)b * EMB + i];
         dctx_s[i] = d;
         dctx_out[(size_t)b * EMB + i] = d;
+        dctx[(size_t)b * EMB + i] = 0.f;      // consumed: the attention cell's data gradient accumulates d ctx_{t-1} onto it
     }
     for (int i = tid; i < LOC_F * 2 * LOC_K; i += ATTN_V2_NT) wloc_s[(i / (2 * LOC_K)) * WLOC_LD + i % (2 * LOC_K)] = Wloc[i];
     for (int i = tid; i < ATT_DIM * LOC_F; i += ATTN_V2_NT) wld_s[(i / LOC_F) * LOC_LD + (i % LOC_F)] = Wld[i];
@@ -693,8 +695,9 @@ int skinny_gemm_multi(const float* X, int ldx, const float* W, int ldw, int B, i
         }
     }
     const int ntiles = (N + 63) / 64;
+    static const int want = [] { const char* e = getenv("TACO_SKINNY_CTAS"); return e ? atoi(e) : 592; }();    // measured at B=64: 128 -> 592 CTAs = -20 ms per backward
     int ks = 1;
-    while (ntiles * ks < 128 && K / (ks * 2) >= 64) ks *= 2;
+    while (ntiles * ks < want && K / (ks * 2) >= 64) ks *= 2;
     const int k_per = ((K + ks - 1) / ks + 15) / 16 * 16;
     skinny_gemm_kernel<<<dim3(ntiles, (K + k_per - 1) / k_per), 256, 0, st>>>(X, ldx, W, ldw, so, B, K, N, k_per);
     TACO_LAUNCHED();
@@ -724,7 +727,7 @@ int assemble_wpg(const float* wp, const float* wg, float* dst, cudaStream_t st) 
     return B200TACO_OK;
 }
 
-int lstm_cell_bwd(const float* gates, const float* c, const float* c_prev, const float* dh_post, const float* mask, float scale,
+int lstm_cell_bwd(const float* gates, const float* c, const float* c_prev, float* dh_post, const float* mask, float scale,
                   float* dc, float* dz, int B, cudaStream_t st) {
     lstm_cell_bwd_kernel<<<(B * RNN + 255) / 256, 256, 0, st>>>(gates, c, c_prev, dh_post, mask, scale, dc, dz, B);
     TACO_LAUNCHED();
@@ -763,7 +766,7 @@ int ctx_dmemory(const float* w, const float* dctx_all, float* dmemory, int S, in
     return B200TACO_OK;
 }
 int attention_bwd(const float* w, const float* prev, const float* cum, const float* pq, const float* pm, const float* memory,
-                  const float* dctx, const float* dw_ext, const float* dprev_next, float* gsum, const int64_t* lengths,
+                  float* dctx, const float* dw_ext, const float* dprev_next, float* gsum, const int64_t* lengths,
                   const float* Wloc, const float* Wld, const float* v, const float* vb, const float* escale, float* dmemory, float* dpm,
                   float* dpq, float* dprev_out, float* pacc, float* scratch, float* dctx_out, int B, int T, cudaStream_t st) {
     if (attention_bwd_defers_dmemory(T)) {
