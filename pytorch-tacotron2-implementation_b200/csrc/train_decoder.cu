@@ -295,11 +295,11 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(
 // here (it was a 2 x 19.6 MB read-modify-write per step at B=64): the kernel stores dctx_t into dctx_all[t] and the host
 // contracts  align^T . dctx_all  once per utterance after the walk.  T <= ATTN_V2_MAX_T (shared-memory budget).
 constexpr int ATTN_V2_NT = 512, ATTN_V2_NW = ATTN_V2_NT / 32, ATTN_V2_MAX_T = 320;
-constexpr int LOC_LD = LOC_F + 1;                       // row stride of loc / dloc / Wld tiles: conflict-free both ways
+constexpr int LOC_LD = LOC_F + 4;                       // row stride of loc / dloc / Wld tiles: 16-byte rows, 9 x 16 B apart
 constexpr int WLOC_LD = 2 * LOC_K + 1;                  // row stride of the location-conv weights (odd)
 __host__ __device__ constexpr int attn_v2_smem_floats(int T) {
     return EMB + LOC_F * WLOC_LD + ATT_DIM * LOC_LD + 4 * ATT_DIM + 2 * (T + LOC_K - 1) + 2 * T + 2 * T * LOC_LD +
-           ATTN_V2_NW * ATT_DIM + 2 * ATTN_V2_NW * ATT_DIM + ATTN_V2_NT;
+           2 * ATTN_V2_NW * ATT_DIM + 2 * ATTN_V2_NW * ATT_DIM + ATTN_V2_NT;
 }
 __global__ void __launch_bounds__(ATTN_V2_NT) attention_bwd_v2_kernel(
     const float* __restrict__ w, const float* __restrict__ prev, const float* __restrict__ cum, const float* __restrict__ pq,
@@ -326,8 +326,8 @@ __global__ void __launch_bounds__(ATTN_V2_NT) attention_bwd_v2_kernel(
     float* dw_s = w_s + T;
     float* loc_s = dw_s + T;
     float* dloc_s = loc_s + T * LOC_LD;
-    float* tile_du = dloc_s + T * LOC_LD;              // [NW][128]
-    float* accx = tile_du + ATTN_V2_NW * ATT_DIM;      // [2][NW][128]: dv / dpq partials of the warps
+    float* tile_du = dloc_s + T * LOC_LD;              // [2 NW][128]: du of the 32 positions of a pass
+    float* accx = tile_du + 2 * ATTN_V2_NW * ATT_DIM;  // [2][NW][128]: dv / dpq partials of the warps
     float* red_s = accx + 2 * ATTN_V2_NW * ATT_DIM;    // [NT]
     float* dWld = pacc + (size_t)b * ATTN_PACC;        // only this CTA ever touches slice b: plain read-modify-write
     float* dWloc = dWld + ATT_DIM * LOC_F;
@@ -406,67 +406,106 @@ __global__ void __launch_bounds__(ATTN_V2_NT) attention_bwd_v2_kernel(
     const float s_all = red_s[0];
     __syncthreads();
 
-    // (c) per position (one warp each, lane = 4 attention dims): de -> du, dpm, partial dv / dpq / dvb / dscale;
-    //     dloc[tau][f] = sum_a du[a] Wld[a][f]; dWld[a][f] += du[tau][a] loc[tau][f] (register accumulators, 8 per thread)
+    // (c) per position: de -> du, dpm, partial dv / dpq / dvb / dscale; dloc[tau][f] = sum_a du[a] Wld[a][f];
+    //     dWld[a][f] += du[tau][a] loc[tau][f].  A pass covers 32 positions, TWO per warp (lane = 4 attention dims), so every
+    //     128-bit read of Wld feeds both; all shared-memory reads are 128 bits wide (the loop is shared-memory-bandwidth bound).
     float dvb_part = 0.f, dscale_part = 0.f;
     float dv_r[4] = {0.f, 0.f, 0.f, 0.f}, dpq_r[4] = {0.f, 0.f, 0.f, 0.f};
-    float dwld_r[ATT_DIM * LOC_F / ATTN_V2_NT];
+    float dwld_r[ATT_DIM * LOC_F / ATTN_V2_NT];            // entries a = 4 (warp + 16 g) + j, f = lane
 #pragma unroll
     for (int i = 0; i < ATT_DIM * LOC_F / ATTN_V2_NT; ++i) dwld_r[i] = 0.f;
-    for (int t0 = 0; t0 < T; t0 += ATTN_V2_NW) {
-        const int tau = t0 + warp;
-        float* du_row = tile_du + warp * ATT_DIM;
-        if (tau < T) {
-            float th[4], pmv[4];
+    for (int t0 = 0; t0 < T; t0 += 2 * ATTN_V2_NW) {
+        int tau[2];
+        bool ok[2];
+        float* du_row[2];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) pmv[q] = __ldg(pm + ((size_t)b * T + tau) * ATT_DIM + lane + 32 * q);
+        for (int r = 0; r < 2; ++r) {
+            tau[r] = t0 + r * ATTN_V2_NW + warp;
+            ok[r] = tau[r] < T;
+            if (!ok[r]) tau[r] = T - 1;                    // loads stay in range; results are discarded
+            du_row[r] = tile_du + (r * ATTN_V2_NW + warp) * ATT_DIM;
+        }
+        float pmv[2][4], lf[2][4], th[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                pmv[r][q] = __ldg(pm + ((size_t)b * T + tau[r]) * ATT_DIM + lane + 32 * q);
+                lf[r][q] = 0.f;
+            }
+        const float4* l0 = reinterpret_cast<const float4*>(loc_s + tau[0] * LOC_LD);
+        const float4* l1 = reinterpret_cast<const float4*>(loc_s + tau[1] * LOC_LD);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4* wr = reinterpret_cast<const float4*>(wld_s + (lane + 32 * q) * LOC_LD);
+#pragma unroll
+            for (int f4 = 0; f4 < LOC_F / 4; ++f4) {
+                const float4 wv = wr[f4], x = l0[f4], y = l1[f4];
+                lf[0][q] = fmaf(wv.x, x.x, lf[0][q]); lf[0][q] = fmaf(wv.y, x.y, lf[0][q]);
+                lf[0][q] = fmaf(wv.z, x.z, lf[0][q]); lf[0][q] = fmaf(wv.w, x.w, lf[0][q]);
+                lf[1][q] = fmaf(wv.x, y.x, lf[1][q]); lf[1][q] = fmaf(wv.y, y.y, lf[1][q]);
+                lf[1][q] = fmaf(wv.z, y.z, lf[1][q]); lf[1][q] = fmaf(wv.w, y.w, lf[1][q]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
             float e_raw_part = 0.f;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int a = lane + 32 * q;
-                float lf = 0.f;
-#pragma unroll
-                for (int f = 0; f < LOC_F; ++f) lf = fmaf(wld_s[a * LOC_LD + f], loc_s[tau * LOC_LD + f], lf);
-                th[q] = tanhf(pq_s[a] + pmv[q] + lf);
-                e_raw_part = fmaf(v_s[a], th[q], e_raw_part);
+                th[r][q] = tanhf(pq_s[a] + pmv[r][q] + lf[r][q]);
+                e_raw_part = fmaf(v_s[a], th[r][q], e_raw_part);
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) e_raw_part += __shfl_xor_sync(0xffffffffu, e_raw_part, o);
             const float e_raw = e_raw_part + vb;
             // softmax backward; masked positions (energy filled with -1e9, src/model.py:132) pass no gradient
-            const float de = tau < len ? w_s[tau] * (dw_s[tau] - s_all) : 0.f;
+            const float de = ok[r] && tau[r] < len ? w_s[tau[r]] * (dw_s[tau[r]] - s_all) : 0.f;
             const float de_raw = de * escale;
             if (lane == 0) { dscale_part += de * e_raw; dvb_part += de_raw; }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int a = lane + 32 * q;
-                const float du = de_raw * v_s[a] * (1.f - th[q] * th[q]);
-                du_row[a] = du;
-                float* dpm_p = dpm + ((size_t)b * T + tau) * ATT_DIM + a;
-                *dpm_p += du;
-                dv_r[q] = fmaf(de_raw, th[q], dv_r[q]);
+                const float du = de_raw * v_s[a] * (1.f - th[r][q] * th[r][q]);     // 0 for positions past T (de = 0)
+                du_row[r][a] = du;
+                if (ok[r]) {
+                    float* dpm_p = dpm + ((size_t)b * T + tau[r]) * ATT_DIM + a;
+                    *dpm_p += du;
+                }
+                dv_r[q] = fmaf(de_raw, th[r][q], dv_r[q]);
                 dpq_r[q] += du;
             }
-            __syncwarp();
-            float acc = 0.f;
-#pragma unroll 8
-            for (int a = 0; a < ATT_DIM; ++a) acc = fmaf(du_row[a], wld_s[a * LOC_LD + lane], acc);
-            dloc_s[tau * LOC_LD + lane] = acc;
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) du_row[lane + 32 * q] = 0.f;
+        }
+        __syncwarp();
+        {
+            float acc0 = 0.f, acc1 = 0.f;
+            const float4* d0 = reinterpret_cast<const float4*>(du_row[0]);
+            const float4* d1 = reinterpret_cast<const float4*>(du_row[1]);
+#pragma unroll 4
+            for (int a4 = 0; a4 < ATT_DIM / 4; ++a4) {
+                const float4 x = d0[a4], y = d1[a4];
+                const float w0 = wld_s[(4 * a4 + 0) * LOC_LD + lane], w1 = wld_s[(4 * a4 + 1) * LOC_LD + lane],
+                            w2 = wld_s[(4 * a4 + 2) * LOC_LD + lane], w3 = wld_s[(4 * a4 + 3) * LOC_LD + lane];
+                acc0 = fmaf(x.x, w0, acc0); acc0 = fmaf(x.y, w1, acc0); acc0 = fmaf(x.z, w2, acc0); acc0 = fmaf(x.w, w3, acc0);
+                acc1 = fmaf(y.x, w0, acc1); acc1 = fmaf(y.y, w1, acc1); acc1 = fmaf(y.z, w2, acc1); acc1 = fmaf(y.w, w3, acc1);
+            }
+            if (ok[0]) dloc_s[tau[0] * LOC_LD + lane] = acc0;
+            if (ok[1]) dloc_s[tau[1] * LOC_LD + lane] = acc1;
         }
         __syncthreads();
+#pragma unroll 4
+        for (int pp = 0; pp < 2 * ATTN_V2_NW; ++pp) {
+            const int tt = t0 + pp < T ? t0 + pp : T - 1;         // rows past T hold zeros in tile_du
+            const float l = loc_s[tt * LOC_LD + lane];
+            const float4* dr = reinterpret_cast<const float4*>(tile_du + pp * ATT_DIM);
 #pragma unroll
-        for (int q = 0; q < ATT_DIM * LOC_F / ATTN_V2_NT; ++q) {
-            const int a = warp + ATTN_V2_NW * q;                  // entry (a, f = lane)
-            float acc = 0.f;
-#pragma unroll
-            for (int pp = 0; pp < ATTN_V2_NW; ++pp) {
-                const int tt = t0 + pp < T ? t0 + pp : T - 1;     // rows past T hold zeros in tile_du
-                acc = fmaf(tile_du[pp * ATT_DIM + a], loc_s[tt * LOC_LD + lane], acc);
+            for (int g = 0; g < 2; ++g) {
+                const float4 d = dr[warp + ATTN_V2_NW * g];
+                dwld_r[4 * g + 0] = fmaf(d.x, l, dwld_r[4 * g + 0]);
+                dwld_r[4 * g + 1] = fmaf(d.y, l, dwld_r[4 * g + 1]);
+                dwld_r[4 * g + 2] = fmaf(d.z, l, dwld_r[4 * g + 2]);
+                dwld_r[4 * g + 3] = fmaf(d.w, l, dwld_r[4 * g + 3]);
             }
-            dwld_r[q] += acc;
         }
         __syncthreads();
     }
@@ -501,7 +540,8 @@ __global__ void __launch_bounds__(ATTN_V2_NT) attention_bwd_v2_kernel(
         dvb_scale[1] += acc;
     }
 #pragma unroll
-    for (int q = 0; q < ATT_DIM * LOC_F / ATTN_V2_NT; ++q) dWld[(warp + ATTN_V2_NW * q) * LOC_F + lane] += dwld_r[q];
+    for (int q = 0; q < ATT_DIM * LOC_F / ATTN_V2_NT; ++q)
+        dWld[(4 * (warp + ATTN_V2_NW * (q >> 2)) + (q & 3)) * LOC_F + lane] += dwld_r[q];
 
     // (d) location conv backward: dWloc[f][c][k] += sum_tau dloc[tau][f] * in_c[tau + k - 15]
     for (int i = tid; i < LOC_F * 2 * LOC_K; i += ATTN_V2_NT) {
@@ -519,10 +559,14 @@ __global__ void __launch_bounds__(ATTN_V2_NT) attention_bwd_v2_kernel(
         for (int k = 0; k < LOC_K; ++k) {
             const int tau = tt - k + HALO;
             if (tau >= 0 && tau < T) {
-                const float* dl = dloc_s + tau * LOC_LD;
+                const float4* dl = reinterpret_cast<const float4*>(dloc_s + tau * LOC_LD);
                 const float* wl = wloc_s + c * LOC_K + k;
-#pragma unroll 8
-                for (int f = 0; f < LOC_F; ++f) acc = fmaf(dl[f], wl[f * WLOC_LD], acc);
+#pragma unroll
+                for (int f4 = 0; f4 < LOC_F / 4; ++f4) {
+                    const float4 d = dl[f4];
+                    acc = fmaf(d.x, wl[(4 * f4 + 0) * WLOC_LD], acc); acc = fmaf(d.y, wl[(4 * f4 + 1) * WLOC_LD], acc);
+                    acc = fmaf(d.z, wl[(4 * f4 + 2) * WLOC_LD], acc); acc = fmaf(d.w, wl[(4 * f4 + 3) * WLOC_LD], acc);
+                }
             }
         }
         if (c == 0) dprev_out[(size_t)b * T + tt] = acc;
