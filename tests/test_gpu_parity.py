@@ -304,6 +304,24 @@ def test_continuous_batching_equals_batch_by_batch(rows, T, nb, cap):
     assert m._get_engine().last_stream_steps < sum(s[1].shape[1] + 1 for s in solo) or cap is not None
 
 
+def test_continuous_batching_rejects_what_it_cannot_run():
+    """The utterance queue lives in the tensor-core decoder kernel: other configurations fail loudly, nothing falls back."""
+    m = gpu_model(util.weights("default", True))
+    eng = m._get_engine()
+    mem = eng.encoder(synth.phoneme_ids(8, 20, seed=1).cuda())
+    with pytest.raises(B200TacoError, match="multiple"):
+        eng.decoder_infer_stream(mem[:7].contiguous(), 4, 10, 0.5)          # 7 utterances, 4 rows
+    with pytest.raises(B200TacoError, match="tensor-core"):
+        eng.decoder_infer_stream(mem[:4].contiguous(), 2, 10, 0.5)          # 2 rows: SIMT kernel territory
+    with pytest.raises(B200TacoError, match="one shape"):
+        list(eng.stream_infer([synth.phoneme_ids(8, 20, seed=1), synth.phoneme_ids(8, 21, seed=2)], 10, 0.5))
+    m32 = gpu_model(util.weights("default", False), weight_dtype="fp32")
+    with pytest.raises(B200TacoError, match="one shape|tensor-core"):
+        list(m32.inference_batches([synth.phoneme_ids(8, 20, seed=1).cuda()], max_len_cap=5, continuous=True))
+    with pytest.raises(ValueError):
+        list(m.inference_batches([synth.phoneme_ids(8, 20, seed=1).cuda()], per_utterance=False, continuous=True))
+
+
 def test_long_horizon_default_init_1000_steps():
     """Default init never fires (F11): 1000 frames, error must not grow with the horizon."""
     ids = synth.phoneme_ids(2, 150, seed=1)
