@@ -4,6 +4,8 @@
 // nn.Conv1d(padding=(k-1)/2) does: src/model.py:26-33, :349-357).  taps == 1 is nn.Linear.
 // fp32 SIMT tiles (64 rows x 64 channels, 4x4 per thread): exact-precision first version of
 // these layers; they are the tensor-core candidates named in DESIGN.md.
+#include <cstdlib>
+
 #include "handle.h"
 
 namespace b200taco {
@@ -99,6 +101,113 @@ __global__ void __launch_bounds__(256) conv_cl_kernel(const float* __restrict__ 
     }
 }
 
+// The same contract with 128 x 128 tiles and an 8 x 8 micro-tile per thread (two 4-wide halves 64 apart in each direction):
+// four 128-bit shared-memory reads feed 64 FMAs instead of two feeding 16, which is what bounds the 64 x 64 kernel
+// (32 TFLOP/s).  Every output element accumulates its (tap, channel) products in the same order as in conv_cl_kernel, so
+// the two kernels are bit-identical; this one is used when its tiles fill the machine.
+constexpr int BM2 = 128, BN2 = 128, LDS2 = BM2 + 4;
+template <int ACT>
+__global__ void __launch_bounds__(256) conv_cl128_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W,
+                                                         const float* __restrict__ scale, const float* __restrict__ shift,
+                                                         const float* __restrict__ R, int ldres, float* __restrict__ Y,
+                                                         int ldy, int n_rows, int seg_len, int c_in, int c_out, int taps) {
+    __shared__ __align__(16) float Xs[2][BK][LDS2];
+    __shared__ __align__(16) float Ws[2][BK][BN2];
+    const int tid = threadIdx.x;
+    const int row0 = blockIdx.x * BM2, co0 = blockIdx.y * BN2;
+    const int pad = (taps - 1) / 2;
+    const int tx = tid & 15, ty = tid >> 4;
+    // loader roles: X rows xm and xm + 64, channels 4*xq.. ; W k row wk, channels 4*wq.. and 64 + 4*wq..
+    const int xm = tid >> 2, xq = tid & 3;
+    const int wk = tid >> 4, wq = tid & 15;
+    const int kchunks = c_in / BK;
+    const int iters = taps * kchunks;
+    int xrow[2], xt[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        xrow[h] = row0 + xm + 64 * h;
+        xt[h] = xrow[h] % seg_len;
+    }
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    float4 xr[2], wr[2];
+    auto fetch = [&](int it) {
+        const int tap = it / kchunks, ci0 = (it % kchunks) * BK;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int tt = xt[h] + tap - pad;
+            xr[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (xrow[h] < n_rows && tt >= 0 && tt < seg_len)
+                xr[h] = __ldg(reinterpret_cast<const float4*>(X + (size_t)(xrow[h] + tap - pad) * ldx + ci0 + 4 * xq));
+            wr[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (co0 + 64 * h + 4 * wq < c_out)
+                wr[h] = __ldg(reinterpret_cast<const float4*>(W + ((size_t)tap * c_in + ci0 + wk) * c_out + co0 + 64 * h + 4 * wq));
+        }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            Xs[buf][4 * xq + 0][xm + 64 * h] = xr[h].x;
+            Xs[buf][4 * xq + 1][xm + 64 * h] = xr[h].y;
+            Xs[buf][4 * xq + 2][xm + 64 * h] = xr[h].z;
+            Xs[buf][4 * xq + 3][xm + 64 * h] = xr[h].w;
+            *reinterpret_cast<float4*>(&Ws[buf][wk][64 * h + 4 * wq]) = wr[h];
+        }
+    };
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    for (int it = 0; it < iters; ++it) {
+        const int buf = it & 1;
+        if (it + 1 < iters) fetch(it + 1);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&Xs[buf][kk][4 * ty]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&Xs[buf][kk][64 + 4 * ty]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Ws[buf][kk][4 * tx]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Ws[buf][kk][64 + 4 * tx]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (it + 1 < iters) stash(buf ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int hj = 0; hj < 2; ++hj) {
+        const int co = co0 + 64 * hj + 4 * tx;
+        if (co >= c_out) continue;
+        float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+        if (scale) { const float4 v = __ldg(reinterpret_cast<const float4*>(scale + co)); sc[0] = v.x; sc[1] = v.y; sc[2] = v.z; sc[3] = v.w; }
+        if (shift) { const float4 v = __ldg(reinterpret_cast<const float4*>(shift + co)); sh[0] = v.x; sh[1] = v.y; sh[2] = v.z; sh[3] = v.w; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = row0 + 64 * (i >> 2) + 4 * ty + (i & 3);
+            if (row >= n_rows) continue;
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float v = fmaf(acc[i][4 * hj + j], sc[j], sh[j]);
+                if (ACT == ACT_RELU) v = fmaxf(v, 0.f);
+                if (ACT == ACT_TANH) v = tanhf(v);
+                o[j] = v;
+            }
+            if (R) {
+                const float4 r = __ldg(reinterpret_cast<const float4*>(R + (size_t)row * ldres + co));
+                o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
+            }
+            *reinterpret_cast<float4*>(Y + (size_t)row * ldy + co) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
 __global__ void embedding_kernel(const int64_t* __restrict__ ids, const float* __restrict__ table, float* __restrict__ out,
                                  int n) {
     const int row = blockIdx.x, c = threadIdx.x * 4;
@@ -132,6 +241,30 @@ int conv1d_channels_last(const float* X, int ldx, const float* W, const float* s
                  "conv1d: c_in %d must be a multiple of %d, c_out %d / ldx %d / ldy %d multiples of 4", c_in, BK, c_out,
                  ldx, ldy);
     if (n_rows <= 0) return B200TACO_OK;
+    // wide tiles once they fill the machine (one CTA per SM); TACO_CONV128=0 keeps the 64 x 64 kernel (measurements)
+    static const bool wide = [] { const char* e = getenv("TACO_CONV128"); return !(e && e[0] == '0'); }();
+    static const int sms = [] { int d = 0, n = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+    // (>= 4 tiles per SM: with fewer, e.g. the 152 tiles of a 32-utterance encoder layer on 148 SMs, the last tiles run alone
+    // and the 64 x 64 kernel's finer tiles win - measured 2.82 vs 2.64 ms per encoder)
+    if (wide && c_out % BN2 == 0 && ((n_rows + BM2 - 1) / BM2) * (c_out / BN2) >= 4 * sms) {
+        dim3 grid2((n_rows + BM2 - 1) / BM2, c_out / BN2);
+        switch (act) {
+            case ACT_NONE:
+                conv_cl128_kernel<ACT_NONE><<<grid2, 256, 0, stream>>>(X, ldx, W, scale, shift, residual, ldres, Y, ldy, n_rows,
+                                                                      seg_len, c_in, c_out, taps);
+                break;
+            case ACT_RELU:
+                conv_cl128_kernel<ACT_RELU><<<grid2, 256, 0, stream>>>(X, ldx, W, scale, shift, residual, ldres, Y, ldy, n_rows,
+                                                                      seg_len, c_in, c_out, taps);
+                break;
+            default:
+                conv_cl128_kernel<ACT_TANH><<<grid2, 256, 0, stream>>>(X, ldx, W, scale, shift, residual, ldres, Y, ldy, n_rows,
+                                                                      seg_len, c_in, c_out, taps);
+                break;
+        }
+        TACO_LAUNCHED();
+        return B200TACO_OK;
+    }
     dim3 grid((n_rows + BM - 1) / BM, (c_out + BN - 1) / BN);
     switch (act) {
         case ACT_NONE:

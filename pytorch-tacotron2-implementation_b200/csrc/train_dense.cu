@@ -9,6 +9,8 @@
 //             db = sum_n dz ;  dW[tap][ci][co] = sum_n x[n + tap - pad][ci] * dz[n][co] ;  dx = conv(dz, W flipped^T)
 //
 // First correct version: fp32 SIMT everywhere, one kernel per step of the formulas above.
+#include <cstdlib>
+
 #include "handle.h"
 
 namespace b200taco {
@@ -164,6 +166,85 @@ __global__ void __launch_bounds__(256) dense_wgrad_kernel(const float* __restric
     }
 }
 
+// The same reduction with 128 x 128 tiles of (ci, co), an 8 x 8 micro-tile per thread and register double buffering of the
+// row slabs (the 64 x 64 kernel is bound by its shared-memory reads and exposes every load); plain stores when one CTA owns
+// the whole row range.
+__global__ void __launch_bounds__(256) dense_wgrad128_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ dY,
+                                                             int ldy, float* __restrict__ dW, int n_rows, int seg_len, int c_in,
+                                                             int c_out, int taps, int rows_per, int atomic) {
+    __shared__ __align__(16) float Xs[2][16][128 + 4];
+    __shared__ __align__(16) float Ys[2][16][128];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int ci0 = blockIdx.x * 128, co0 = blockIdx.y * 128;
+    const int tap = blockIdx.z % taps, chunk = blockIdx.z / taps;
+    const int pad = (taps - 1) / 2, sh = tap - pad;
+    const int r0 = chunk * rows_per, r1 = min(n_rows, r0 + rows_per);
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    const int lr = tid >> 5, lc = (tid & 31) * 4;                // loader: rows lr and lr + 8 of 16, 4 channels at lc
+    float4 xv[2], yv[2];
+    auto fetch = [&](int rb) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = rb + lr + 8 * h;
+            xv[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+            yv[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < r1) {
+                const int t = r % seg_len + sh;
+                if (t >= 0 && t < seg_len && ci0 + lc < c_in) xv[h] = __ldg(reinterpret_cast<const float4*>(X + (size_t)(r + sh) * ldx + ci0 + lc));
+                if (co0 + lc < c_out) yv[h] = __ldg(reinterpret_cast<const float4*>(dY + (size_t)r * ldy + co0 + lc));
+            }
+        }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            *reinterpret_cast<float4*>(&Xs[buf][lr + 8 * h][lc]) = xv[h];
+            *reinterpret_cast<float4*>(&Ys[buf][lr + 8 * h][lc]) = yv[h];
+        }
+    };
+    if (r0 < r1) {
+        fetch(r0);
+        stash(0);
+    }
+    __syncthreads();
+    int buf = 0;
+    for (int rb = r0; rb < r1; rb += 16, buf ^= 1) {
+        if (rb + 16 < r1) fetch(rb + 16);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&Xs[buf][k][4 * ty]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&Xs[buf][k][64 + 4 * ty]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Ys[buf][k][4 * tx]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Ys[buf][k][64 + 4 * tx]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (rb + 16 < r1) stash(buf ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int ci = ci0 + 64 * (i >> 2) + 4 * ty + (i & 3);
+        if (ci >= c_in) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int co = co0 + 64 * (j >> 2) + 4 * tx + (j & 3);
+            if (co >= c_out) continue;
+            float* dst = dW + ((size_t)tap * c_in + ci) * c_out + co;
+            if (atomic) atomicAdd(dst, acc[i][j]);
+            else *dst = acc[i][j];
+        }
+    }
+}
+
 // W[tap][ci][co] -> Wf[taps-1-tap][co][ci] (the data-gradient convolution uses the forward kernel with these weights)
 __global__ void flip_transpose_kernel(float* __restrict__ dst, const float* __restrict__ src, int taps, int c_in, int c_out) {
     const size_t total = (size_t)taps * c_in * c_out;
@@ -227,6 +308,18 @@ int train_colsum(float* dst, const float* src, int n_rows, int C, cudaStream_t s
 // dW[tap][ci][co] = sum_n X[n + tap - pad][ci] * dY[n][co]  (overwrites dW)
 int dense_wgrad(const float* X, int ldx, const float* dY, int ldy, float* dW, int n_rows, int seg_len, int c_in, int c_out,
                 int taps, cudaStream_t st) {
+    static const bool wide = [] { const char* e = getenv("TACO_WGRAD128"); return !(e && e[0] == '0'); }();
+    if (wide && c_in >= 128 && c_out >= 128) {
+        const int tiles2 = ((c_in + 127) / 128) * ((c_out + 127) / 128) * taps;
+        int chunks2 = 1;
+        while (tiles2 * chunks2 < 148 && n_rows / (chunks2 * 2) >= 256) chunks2 *= 2;
+        const int rows_per2 = ((n_rows + chunks2 - 1) / chunks2 + 15) / 16 * 16;
+        if (chunks2 > 1) TACO_CUDA(cudaMemsetAsync(dW, 0, (size_t)taps * c_in * c_out * sizeof(float), st));
+        dense_wgrad128_kernel<<<dim3((c_in + 127) / 128, (c_out + 127) / 128, taps * chunks2), 256, 0, st>>>(
+            X, ldx, dY, ldy, dW, n_rows, seg_len, c_in, c_out, taps, rows_per2, chunks2 > 1 ? 1 : 0);
+        TACO_LAUNCHED();
+        return B200TACO_OK;
+    }
     TACO_CUDA(cudaMemsetAsync(dW, 0, (size_t)taps * c_in * c_out * sizeof(float), st));
     int chunks = 1;
     const int tiles = ((c_in + 63) / 64) * ((c_out + 63) / 64) * taps;
