@@ -105,8 +105,9 @@ __global__ void __launch_bounds__(256) conv_cl_kernel(const float* __restrict__ 
 // four 128-bit shared-memory reads feed 64 FMAs instead of two feeding 16, which is what bounds the 64 x 64 kernel
 // (32 TFLOP/s).  Every output element accumulates its (tap, channel) products in the same order as in conv_cl_kernel, so
 // the two kernels are bit-identical; this one is used when its tiles fill the machine.
-constexpr int BM2 = 128, BN2 = 128, LDS2 = BM2 + 4;
-template <int ACT>
+// BN2 = 64: 128 x 64 tiles (8 x 4 micro-tile) - twice the tiles for problems that would not fill the machine with 128 x 128.
+constexpr int BM2 = 128, LDS2 = BM2 + 4;
+template <int ACT, int BN2>
 __global__ void __launch_bounds__(256) conv_cl128_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W,
                                                          const float* __restrict__ scale, const float* __restrict__ shift,
                                                          const float* __restrict__ R, int ldres, float* __restrict__ Y,
@@ -128,13 +129,14 @@ __global__ void __launch_bounds__(256) conv_cl128_kernel(const float* __restrict
         xrow[h] = row0 + xm + 64 * h;
         xt[h] = xrow[h] % seg_len;
     }
-    float acc[8][8];
+    constexpr int NH = BN2 / 64, NJ = 4 * NH;             // column halves, columns per thread
+    float acc[8][NJ];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
 
-    float4 xr[2], wr[2];
+    float4 xr[2], wr[NH];
     auto fetch = [&](int it) {
         const int tap = it / kchunks, ci0 = (it % kchunks) * BK;
 #pragma unroll
@@ -143,6 +145,9 @@ __global__ void __launch_bounds__(256) conv_cl128_kernel(const float* __restrict
             xr[h] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (xrow[h] < n_rows && tt >= 0 && tt < seg_len)
                 xr[h] = __ldg(reinterpret_cast<const float4*>(X + (size_t)(xrow[h] + tap - pad) * ldx + ci0 + 4 * xq));
+        }
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
             wr[h] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (co0 + 64 * h + 4 * wq < c_out)
                 wr[h] = __ldg(reinterpret_cast<const float4*>(W + ((size_t)tap * c_in + ci0 + wk) * c_out + co0 + 64 * h + 4 * wq));
@@ -155,8 +160,9 @@ __global__ void __launch_bounds__(256) conv_cl128_kernel(const float* __restrict
             Xs[buf][4 * xq + 1][xm + 64 * h] = xr[h].y;
             Xs[buf][4 * xq + 2][xm + 64 * h] = xr[h].z;
             Xs[buf][4 * xq + 3][xm + 64 * h] = xr[h].w;
-            *reinterpret_cast<float4*>(&Ws[buf][wk][64 * h + 4 * wq]) = wr[h];
         }
+#pragma unroll
+        for (int h = 0; h < NH; ++h) *reinterpret_cast<float4*>(&Ws[buf][wk][64 * h + 4 * wq]) = wr[h];
     };
     fetch(0);
     stash(0);
@@ -168,20 +174,23 @@ __global__ void __launch_bounds__(256) conv_cl128_kernel(const float* __restrict
         for (int kk = 0; kk < BK; ++kk) {
             const float4 a0 = *reinterpret_cast<const float4*>(&Xs[buf][kk][4 * ty]);
             const float4 a1 = *reinterpret_cast<const float4*>(&Xs[buf][kk][64 + 4 * ty]);
-            const float4 b0 = *reinterpret_cast<const float4*>(&Ws[buf][kk][4 * tx]);
-            const float4 b1 = *reinterpret_cast<const float4*>(&Ws[buf][kk][64 + 4 * tx]);
             const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float bv[NJ];
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+                const float4 b = *reinterpret_cast<const float4*>(&Ws[buf][kk][64 * h + 4 * tx]);
+                bv[4 * h + 0] = b.x; bv[4 * h + 1] = b.y; bv[4 * h + 2] = b.z; bv[4 * h + 3] = b.w;
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                for (int j = 0; j < NJ; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
         if (it + 1 < iters) stash(buf ^ 1);
         __syncthreads();
     }
 #pragma unroll
-    for (int hj = 0; hj < 2; ++hj) {
+    for (int hj = 0; hj < NH; ++hj) {
         const int co = co0 + 64 * hj + 4 * tx;
         if (co >= c_out) continue;
         float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
@@ -244,24 +253,26 @@ int conv1d_channels_last(const float* X, int ldx, const float* W, const float* s
     // wide tiles once they fill the machine (one CTA per SM); TACO_CONV128=0 keeps the 64 x 64 kernel (measurements)
     static const bool wide = [] { const char* e = getenv("TACO_CONV128"); return !(e && e[0] == '0'); }();
     static const int sms = [] { int d = 0, n = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
-    // (>= 4 tiles per SM: with fewer, e.g. the 152 tiles of a 32-utterance encoder layer on 148 SMs, the last tiles run alone
-    // and the 64 x 64 kernel's finer tiles win - measured 2.82 vs 2.64 ms per encoder)
-    if (wide && c_out % BN2 == 0 && ((n_rows + BM2 - 1) / BM2) * (c_out / BN2) >= 4 * sms) {
-        dim3 grid2((n_rows + BM2 - 1) / BM2, c_out / BN2);
-        switch (act) {
-            case ACT_NONE:
-                conv_cl128_kernel<ACT_NONE><<<grid2, 256, 0, stream>>>(X, ldx, W, scale, shift, residual, ldres, Y, ldy, n_rows,
-                                                                      seg_len, c_in, c_out, taps);
-                break;
-            case ACT_RELU:
-                conv_cl128_kernel<ACT_RELU><<<grid2, 256, 0, stream>>>(X, ldx, W, scale, shift, residual, ldres, Y, ldy, n_rows,
-                                                                      seg_len, c_in, c_out, taps);
-                break;
-            default:
-                conv_cl128_kernel<ACT_TANH><<<grid2, 256, 0, stream>>>(X, ldx, W, scale, shift, residual, ldres, Y, ldy, n_rows,
-                                                                      seg_len, c_in, c_out, taps);
-                break;
+    // 128-row tiles when they fill the machine with >= 4 tiles per SM (with fewer, e.g. the 152 tiles of a 32-utterance
+    // encoder layer at 128 x 128 on 148 SMs, the last tiles run alone and finer tiles win - measured): 128 x 128, else 128 x 64
+    const int mt2 = (n_rows + BM2 - 1) / BM2;
+    const int bn2 = !wide ? 0 : (c_out % 128 == 0 && mt2 * (c_out / 128) >= 4 * sms ? 128
+                                 : (c_out % 64 == 0 && mt2 * (c_out / 64) >= 4 * sms ? 64 : 0));
+    if (bn2 != 0) {
+        dim3 grid2(mt2, c_out / bn2);
+#define TACO_CL128(A, N)                                                                                                    \
+    conv_cl128_kernel<A, N><<<grid2, 256, 0, stream>>>(X, ldx, W, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, \
+                                                       c_in, c_out, taps)
+        if (bn2 == 128) {
+            if (act == ACT_NONE) TACO_CL128(ACT_NONE, 128);
+            else if (act == ACT_RELU) TACO_CL128(ACT_RELU, 128);
+            else TACO_CL128(ACT_TANH, 128);
+        } else {
+            if (act == ACT_NONE) TACO_CL128(ACT_NONE, 64);
+            else if (act == ACT_RELU) TACO_CL128(ACT_RELU, 64);
+            else TACO_CL128(ACT_TANH, 64);
         }
+#undef TACO_CL128
         TACO_LAUNCHED();
         return B200TACO_OK;
     }
