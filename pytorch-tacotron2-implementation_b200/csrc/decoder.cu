@@ -2312,6 +2312,15 @@ int decoder_run(const b200taco_handle* h, const DecoderArgs& a, cudaStream_t str
     kp.n_utts = a.n_utts;
     int ns = ncta / a.B;
     ns = ns < 1 ? 1 : (ns > MAX_NS ? MAX_NS : ns);
+    static const int ns_max = [] { const char* e = getenv("TACO_NS_MAX"); return e ? atoi(e) : MAX_NS; }();   // measurement knob
+    ns = ns > ns_max ? ns_max : ns;
+    // hoisted SIMT kernel (batch tiles 1-2): the work items are dealt to the CTAs beyond the 128 GEMM CTAs first, so one round of
+    // items on those CTAs beats more, shorter slices (measured B=2, T=200: 16 slices 13.5 us, 8 slices 11.5 us; the phase costs
+    // ~7.9 us + 0.16 us per position of a slice)
+    if (!decoder_uses_tensor_cores(h, a.B) && BP <= 2 && ncta > GEMM_CTAS) {
+        const int spare = (ncta - GEMM_CTAS) / a.B;
+        if (spare >= 4 && spare < ns) ns = spare;
+    }
     // keep slices at least 8 positions long
     while (ns > 1 && (a.T + ns - 1) / ns < 8) --ns;
     if (clusters) {
