@@ -840,19 +840,35 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
         }
         float* part = p.apart + ((size_t)b * MAX_NS + sl) * APART;
         if (NS > 1) {
+            // Slices of an utterance on different CTAs without a cluster: every slice publishes its partial (max, sum,
+            // un-normalised context) in L2, counts itself in, waits until all NS slices of the utterance are in, and then
+            // finishes ITS OWN share - the attention weights of its positions and 512/NS context dims - so nothing is
+            // serialised on a last arriver and the weights never leave shared memory.  One work item per CTA
+            // (B * NS <= grid size by construction), so the wait cannot deadlock.
             reinterpret_cast<float2*>(part + 4)[tid] = cacc;
             if (tid == 0) { part[0] = sc[P2Scratch::SC + 32]; part[1] = sc[P2Scratch::SC + 33]; }
-            for (int i = tid; i < n; i += NTC) p.wtmp[(size_t)b * p.Tp + t0 + i] = sc[P2Scratch::E + i];
             consumer_sync();
             if (tid == 0) {
-                // release: this CTA's partials (ordered by the bar.sync above); acquire: the others'
-                const uint32_t ticket = atom_add_acq_rel_gpu(p.ctrl + CTRL_TICKETS + b, 1u);
-                misc_s[0] = (ticket % (uint32_t)NS) == (uint32_t)(NS - 1);
+                // release: this CTA's partial (ordered by the bar.sync above); acquire: the others'
+                const uint32_t target = (uint32_t)NS * (uint32_t)((p.mode == 1 ? out_idx : out_idx + 1) + 1);
+                uint32_t seen = atom_add_acq_rel_gpu(p.ctrl + CTRL_TICKETS + b, 1u) + 1u;
+                if (seen < target) {
+                    const uint64_t tw0 = global_timer_ns();
+                    while (ld_acquire_u32(p.ctrl + CTRL_TICKETS + b) < target) {
+                        if (global_timer_ns() - tw0 > SPIN_TIMEOUT_NS) spin_fail();
+                    }
+                }
             }
             consumer_sync();
         FT(6);
-            if (!misc_s[0]) continue;
-            // last slice of this utterance: merge
+            // all partials: context partial of this thread's dims first (independent of the scales), then (max, sum)
+            const int per = (EMB + NS - 1) / NS;                  // context dims finished by this slice
+            const int d = sl * per + tid;
+            const bool mine_d = tid < per && d < EMB;
+            float cv[MAX_NS];
+#pragma unroll
+            for (int q = 0; q < MAX_NS; ++q)
+                cv[q] = q < NS && mine_d ? __ldcg(p.apart + ((size_t)b * MAX_NS + q) * APART + 4 + d) : 0.f;
             if (tid < 32) {
                 float m = -INFINITY;
                 if (tid < NS) m = __ldcg(p.apart + ((size_t)b * MAX_NS + tid) * APART);
@@ -868,25 +884,38 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
             }
             consumer_sync();
         FT(7);
-            cacc = make_float2(0.f, 0.f);
-            {
-                float2 cv[MAX_NS];
+            const float S = sc[P2Scratch::SC + 33];
+            if (mine_d) {
+                float c = 0.f;
 #pragma unroll
-                for (int q = 0; q < MAX_NS; ++q)
-                    cv[q] = q < NS ? __ldcg(reinterpret_cast<const float2*>(
-                                                p.apart + ((size_t)b * MAX_NS + q) * APART + 4) + tid)
-                                   : make_float2(0.f, 0.f);
-#pragma unroll
-                for (int q = 0; q < MAX_NS; ++q) {
-                    const float scale = q < NS ? sc[P2Scratch::SC + q] : 0.f;
-                    cacc.x = fmaf(scale, cv[q].x, cacc.x);
-                    cacc.y = fmaf(scale, cv[q].y, cacc.y);
+                for (int q = 0; q < MAX_NS; ++q) c = fmaf(q < NS ? sc[P2Scratch::SC + q] : 0.f, cv[q], c);
+                c = c / S;
+                if constexpr (TC) {
+                    __nv_bfloat16 hi, lo;
+                    umma::split_bf16(c, hi, lo);
+                    act16_cur[act16_off<BP>(b, ACT_CTX + d)] = hi;
+                    act16_cur[act16_off<BP>(BP + b, ACT_CTX + d)] = lo;
+                } else {
+                    act_cur[(size_t)(ACT_CTX + d) * BP + b] = c;
                 }
+                p.ctx_bj[(size_t)b * EMB + d] = c;
+                if (p.sv_ctx != nullptr && out_idx >= 0) p.sv_ctx[((size_t)out_idx * B + b) * EMB + d] = c;
             }
-        } else {
-            if (tid == 0) sc[P2Scratch::SC + 0] = 1.f;
-            consumer_sync();
+            // attention weights of this slice: alignment output, prev, cum (src/model.py:142-145)
+            const float mine = sc[P2Scratch::SC + sl];
+            for (int i = tid; i < n; i += NTC) {
+                const int t = t0 + i;
+                const float w = sc[P2Scratch::E + i] * mine / S;
+                prev_out[(size_t)b * p.Tp + t] = w;
+                cum_out[(size_t)b * p.Tp + t] = sc[P2Scratch::WIN + P2Scratch::WIN_LEN + (LOC_K - 1) / 2 + i] + w;
+                if (oi >= 0) p.align[align_row * T + t] = w;
+            }
+        FT(8);
+            continue;
         }
+        // a single slice: the whole utterance is here
+        if (tid == 0) sc[P2Scratch::SC + 0] = 1.f;
+        consumer_sync();
         const float S = sc[P2Scratch::SC + 33];
         cacc.x = cacc.x / S;
         cacc.y = cacc.y / S;
@@ -905,10 +934,7 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
         if (p.sv_ctx != nullptr && out_idx >= 0) reinterpret_cast<float2*>(p.sv_ctx + ((size_t)out_idx * B + b) * EMB)[tid] = cacc;
         // attention weights: alignment output, prev, cum (src/model.py:142-145)
         for (int t = tid; t < T; t += NTC) {
-            float ew;
-            if (NS > 1) ew = __ldcg(p.wtmp + (size_t)b * p.Tp + t) * sc[P2Scratch::SC + t / SL];
-            else ew = sc[P2Scratch::E + t];
-            const float w = ew / S;
+            const float w = sc[P2Scratch::E + t] / S;
             prev_out[(size_t)b * p.Tp + t] = w;
             cum_out[(size_t)b * p.Tp + t] = (fresh ? 0.f : __ldcg(cum_in + (size_t)b * p.Tp + t)) + w;
             if (oi >= 0) p.align[align_row * T + t] = w;
