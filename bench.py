@@ -191,7 +191,9 @@ def run_b200(args, rank, world, local_rank):
     # ~20 ms (measured), which must not land inside the timed region; its samples cover warm-up + timed steps
     sampler = ClockSampler(local_rank)
     sampler.start()
-    run_pipelined(args.warmup, False)
+    # warm-up: W batches, and never fewer than the timed K: one continuous-batching launch allocates its output buffers for all
+    # its batches at once, and the caching allocator must have seen that size before the timed region
+    run_pipelined(max(args.warmup, args.steps), False)
     barrier()
     eng.launch_count(reset=True)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -251,6 +253,7 @@ def run_b200(args, rank, world, local_rank):
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "text_len": T, "cap": CAP,
                        "weights": "seed 1234 default init + planted stop counter (rate 8e-4, jitter 6e-3)",
                        "frames_counted": "sum of per-utterance decoded lengths",
+                       "warmup_batches": max(args.warmup, args.steps),
                        "l2": "flushed before every decoder launch (256 MiB device memset on the decoder stream); the K batches' "
                              "encoder memory streams through the launch (123 MB at K=10)",
                        "pipeline": "continuous batching: the K batches' utterances stream through the 32 rows of ONE persistent "
