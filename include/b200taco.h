@@ -272,6 +272,16 @@ B200TACO_API int32_t b200taco_decoder_profile(b200taco_handle* h, int64_t* out, 
 B200TACO_API int32_t b200taco_debug_umma_gemm(const void* d_A, const void* d_B, float* d_D, int32_t K,
                                               int32_t variant, void* stream);
 
+/*
+ * Guided-attention target of the reference's loss (Tacotron2Loss.create_diagonal_attention_target, train.py:148-171), whose
+ * Python loop over B x S dominates a training step: target[b][t][p] = N(p; min(int(t L_b / S), L_b - 1), sigma_b) over
+ * p < L_b, normalised by (sum + 1e-8), zero for p >= L_b.
+ *   d_text_lengths (B) int64, d_sigma (B) float (the annealed width the caller computed, train.py:151-156),
+ *   d_target (B,S,Tmax) float.  No handle: the kernel reads no model state.
+ */
+B200TACO_API int32_t b200taco_guided_attention_target(const int64_t* d_text_lengths, const float* d_sigma, int32_t B, int32_t S,
+                                         int32_t Tmax, float* d_target, void* stream);
+
 /* Number of kernels this library launched on this thread since the last reset. */
 B200TACO_API int64_t b200taco_launch_count(int32_t reset);
 

@@ -85,6 +85,8 @@ SIGNATURES = {
                                                     C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200taco_postnet_fwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b200taco_guided_attention_target": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                                     C.c_void_p, C.c_void_p]),
     "b200taco_measure_l2_read": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_int32,
                                              C.POINTER(C.c_float), C.c_void_p]),
     "b200taco_measure_stream": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -38,6 +38,12 @@ attention_dim = 128
 location_n_filters = 32
 location_kernel_size = 31
 
+# Guided-attention schedule of the loss (src/config.py:51-54), read by b200taco.loss
+attention_initial_sigma_factor = 0.05
+attention_sigma_warmup_steps = 4000
+attention_min_sigma = 1.0
+attention_max_sigma_cap = 20.0
+
 # Post-net (src/config.py:57-59)
 postnet_embedding_dim = 512
 postnet_kernel_size = 5

@@ -1,0 +1,78 @@
+"""The reference's Tacotron2Loss (train.py:126-217): CPU oracle against golden vectors of the unmodified reference, and the
+device version (guided-attention target kernel through the C ABI) against both.
+
+Tolerances: losses 2e-6 relative (float32 sums in a different order), target 1e-6 absolute on values in [0, 1].
+"""
+import importlib.util
+import os
+
+import pytest
+import torch
+
+import util
+from oracle import loss_oracle as LO
+
+_spec = importlib.util.spec_from_file_location("make_golden_loss", os.path.join(util.GOLDEN, "make_golden_loss.py"))
+_mgl = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(_mgl)
+STEPS = (0, 2500, 9000)
+
+
+def rel(a, b):
+    return abs(float(a) - float(b)) / max(1e-12, abs(float(b)))
+
+
+@pytest.mark.parametrize("step", STEPS)
+def test_loss_oracle_matches_reference_golden(step):
+    g = util.golden("loss_b3")
+    outs, targets, tl = _mgl.loss_case()
+    total, mel, gate, kl, weight = LO.tacotron2_loss(outs, targets, tl, step)
+    want = g[f"s{step}_losses"]
+    for got, ref in zip((total, mel, gate, kl, weight), want):
+        assert rel(got, ref) <= 2e-6, (float(got), float(ref))
+    assert util.maxdiff(LO.diagonal_attention_target(tl, 12, step), g[f"s{step}_target"]) <= 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("step", STEPS)
+def test_device_loss_matches_reference_golden(step):
+    from b200taco.loss import Tacotron2Loss
+    g = util.golden("loss_b3")
+    outs, targets, tl = _mgl.loss_case()
+    dev = torch.device("cuda:0")
+    crit = Tacotron2Loss()
+    crit.global_step = step
+    outs_d = (outs[0].to(dev), outs[1].to(dev), outs[2].to(dev), [a.to(dev) for a in outs[3]])
+    targets_d = tuple(t.to(dev) for t in targets)
+    total, mel, gate, kl = crit(outs_d, targets_d, tl.to(dev))
+    want = g[f"s{step}_losses"]
+    for got, ref in zip((total, mel, gate, kl, crit.current_attention_weight), want):
+        assert rel(got, ref) <= 2e-6, (float(got), float(ref))
+    assert crit.global_step == step + 1
+    crit.global_step = step
+    tgt = crit.create_diagonal_attention_target(tl.to(dev), 12, outs_d[3])
+    assert util.maxdiff(tgt.cpu(), g[f"s{step}_target"]) <= 1e-6
+
+
+@pytest.mark.gpu
+def test_device_target_matches_oracle_at_training_size():
+    """B=64, 800 decoder steps, ragged text lengths up to 150 (BASELINE config 5 shape): kernel vs vectorised CPU oracle."""
+    from b200taco.loss import Tacotron2Loss
+    gen = torch.Generator().manual_seed(5)
+    tl = torch.randint(1, 151, (64,), generator=gen)
+    tl[0], tl[1] = 150, 1
+    for step in (0, 1234, 4000):
+        crit = Tacotron2Loss()
+        crit.global_step = step
+        tgt = crit.create_diagonal_attention_target(tl.cuda(), 800, [torch.zeros(64, 150, device="cuda")])
+        ref = LO.diagonal_attention_target(tl, 800, step)
+        assert tgt.shape == ref.shape == (64, 800, 150)
+        assert util.maxdiff(tgt.cpu(), ref) <= 1e-6
+        assert abs(crit.current_sigma - float(LO.sigma_schedule(tl, step).mean())) <= 1e-6
+
+
+def test_device_loss_has_no_cpu_fallback():
+    from b200taco._cabi import B200TacoError
+    from b200taco.loss import guided_attention_target
+    with pytest.raises(B200TacoError, match="CUDA"):
+        guided_attention_target(torch.tensor([3, 2]), torch.tensor([3.0, 3.0]), 4, 3)
