@@ -419,15 +419,22 @@ class Engine:
                 ev.synchronize()
                 yield res
 
-        mem, ev_enc = prep(groups[0])
-        pending = launch_decoder(mem, ev_enc)
-        for group in groups[1:]:
-            mem, ev_enc = prep(group)                 # encoders of group g+1 overlap the decoder of group g
-            nxt = launch_decoder(mem, ev_enc)         # queued behind the launch of group g
+        launched = []                                 # every launch writes into pinned host memory it was handed: never
+        try:                                          # let go of those buffers while a launch may still be running
+            mem, ev_enc = prep(groups[0])
+            pending = launch_decoder(mem, ev_enc)
+            launched.append(pending)
+            for group in groups[1:]:
+                mem, ev_enc = prep(group)             # encoders of group g+1 overlap the decoder of group g
+                nxt = launch_decoder(mem, ev_enc)     # queued behind the launch of group g
+                launched.append(nxt)
+                yield from finish(*pending)
+                pending = nxt
             yield from finish(*pending)
-            pending = nxt
-        yield from finish(*pending)
-        cur.wait_stream(sP)
+            cur.wait_stream(sP)
+        finally:                                      # also when the consumer abandons the generator or a stage raised
+            for _, ev in launched:
+                ev.synchronize()
 
     # ------------------------------------------------------------------ measurement aids
     def measure_l2_read_gbps(self, nbytes: int = 36 << 20, iters: int = 50) -> float:
