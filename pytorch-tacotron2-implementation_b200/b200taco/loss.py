@@ -1,10 +1,11 @@
 """``Tacotron2Loss`` of the reference (train.py:126-217) with its Python B x S loop on the device.
 
 Same constructor, attributes (``current_attention_weight``, ``global_step``, ``current_sigma`` ...), call signature and
-return value as the reference class, so ``train.py`` can use it unchanged.  The masked L1 / BCE / KL terms are the
-reference's own tensor expressions; what changes is ``create_diagonal_attention_target``: the reference fills the
-(B, T_dec, T_enc) target with a Python double loop (51,200 iterations and ``.item()`` syncs at B=64, 800 frames - seconds per
-step), here it is one kernel launch (``b200taco_guided_attention_target``).  CUDA tensors only; there is no CPU fallback.
+4-tuple result as the reference class, so ``train.py`` can use it unchanged (``criterion = Tacotron2Loss()``, train.py:333).
+The loss terms are small tensor expressions (``loss_terms`` below, device agnostic); the expensive part of the reference is
+``create_diagonal_attention_target``, a Python double loop over B x T_dec with ``.item()`` syncs (51,200 iterations at B=64
+and 800 frames: seconds per step).  Here the target is ONE kernel launch (``b200taco_guided_attention_target``, csrc/loss.cu).
+CUDA tensors only; there is no CPU fallback.
 """
 import ctypes as C
 
@@ -32,10 +33,48 @@ def guided_attention_target(text_lengths: torch.Tensor, sigma: torch.Tensor, num
     return out
 
 
+def annealed_sigma(text_lengths: torch.Tensor, global_step: int, warmup_steps: int) -> torch.Tensor:
+    """Width of the guided-attention Gaussian per utterance (train.py:151-156): from clamp(0.05 L, 3, 20) down to 1.0."""
+    start = (text_lengths.float() * config.attention_initial_sigma_factor).clamp(3.0, config.attention_max_sigma_cap)
+    done = min(1.0, global_step / float(warmup_steps))
+    return start - (start - config.attention_min_sigma) * done
+
+
+def masked_l1(pred: torch.Tensor, target: torch.Tensor, frame_is_pad: torch.Tensor) -> torch.Tensor:
+    """Mean absolute error over the mel bins of the real frames (train.py:182-193); pred/target (B,S,80), mask (B,S)."""
+    keep = (~frame_is_pad).unsqueeze(-1).to(pred.dtype)
+    n_valid = keep.sum() * pred.shape[-1]
+    return ((pred - target).abs() * keep).sum() / n_valid
+
+
+def guided_attention_terms(alignments, diagonal_target: torch.Tensor):
+    """KL(target || attention) per decoder step and the mean attention entropy (train.py:199-204)."""
+    attn = torch.stack(list(alignments), dim=1).clamp_min(1e-8)                  # (B, T_dec, T_enc)
+    log_attn = attn.log()
+    kl = F.kl_div(log_attn, diagonal_target, reduction="batchmean") / attn.shape[1]
+    entropy = -(attn * log_attn).sum(dim=2).mean()
+    return kl.clamp(max=150.0), entropy
+
+
+def loss_terms(model_outputs, targets, diagonal_target=None):
+    """(mel, gate, kl, entropy) of train.py:174-204; ``diagonal_target`` None = no guided-attention term."""
+    mel_post, mel_coarse, gate_logits, alignments = model_outputs
+    mel_target, gate_target, mel_lengths = targets
+    want = mel_target.transpose(1, 2)                                            # (B,80,S) -> (B,S,80)
+    frames = torch.arange(int(mel_lengths.max()), device=mel_lengths.device)
+    frame_is_pad = frames[None, :] >= mel_lengths[:, None]
+    mel = masked_l1(mel_coarse, want, frame_is_pad) + masked_l1(mel_post, want, frame_is_pad)
+    gate = F.binary_cross_entropy_with_logits(gate_logits, gate_target)
+    if diagonal_target is None:
+        return mel, gate, torch.zeros((), device=mel_coarse.device), None
+    kl, entropy = guided_attention_terms(alignments, diagonal_target)
+    return mel, gate, kl, entropy
+
+
 class Tacotron2Loss(nn.Module):
     def __init__(self):
         super().__init__()
-        # train.py:129-141
+        # attribute surface of train.py:129-141
         self.l1_loss = nn.L1Loss(reduction="none")
         self.bce_loss = nn.BCEWithLogitsLoss()
         self.attn_weight_start = 1.0
@@ -46,48 +85,31 @@ class Tacotron2Loss(nn.Module):
         self.sigma_warmup_steps = config.attention_sigma_warmup_steps
 
     def get_mask_from_lengths(self, lengths):
-        """train.py:143-147 (True where padding)."""
-        max_len = int(torch.max(lengths).item())
-        ids = torch.arange(0, max_len, device=lengths.device, dtype=torch.long)
-        return ~(ids < lengths.unsqueeze(1)).bool()
+        """True where padding (train.py:143-147)."""
+        frames = torch.arange(int(lengths.max().item()), device=lengths.device)
+        return frames[None, :] >= lengths[:, None]
 
     def create_diagonal_attention_target(self, text_lengths, num_steps, alignments):
-        """train.py:148-171, one kernel instead of the B x S loop."""
-        max_text_len = int(text_lengths.max().item())
-        init_sigma = torch.clamp(text_lengths.float() * config.attention_initial_sigma_factor, min=3.0,
-                                 max=config.attention_max_sigma_cap)
-        progress = min(1.0, self.global_step / float(self.sigma_warmup_steps))
-        sigma = init_sigma - (init_sigma - config.attention_min_sigma) * progress
+        """train.py:148-171 as one kernel launch."""
+        sigma = annealed_sigma(text_lengths, self.global_step, self.sigma_warmup_steps)
         self.current_sigma = float(sigma.mean().item())
-        return guided_attention_target(text_lengths.to(alignments[0].device), sigma, num_steps, max_text_len)
+        return guided_attention_target(text_lengths.to(alignments[0].device), sigma, num_steps, int(text_lengths.max().item()))
+
+    def attention_weight(self, entropy) -> float:
+        """Entropy-adaptive weight of the guided-attention term (train.py:205-210)."""
+        if entropy is None or float(entropy) > self.entropy_target:
+            return self.attn_weight_start
+        ratio = max(0.0, float(entropy) / self.entropy_target)
+        return max(self.min_attn_weight, self.attn_weight_start * ratio)
 
     def forward(self, model_outputs, targets, text_lengths=None):
-        mel_out_postnet, mel_out, gate_out, alignments = model_outputs
-        mel_target, gate_target, mel_lengths = targets
-        mel_target = mel_target.transpose(1, 2)
-        mask = self.get_mask_from_lengths(mel_lengths).unsqueeze(-1).expand(-1, -1, config.n_mels)
-        mel_loss_1 = self.l1_loss(mel_out, mel_target).masked_fill(mask, 0.0)
-        mel_loss_2 = self.l1_loss(mel_out_postnet, mel_target).masked_fill(mask, 0.0)
-        valid = (~mask).float().sum()
-        loss_mel = mel_loss_1.sum() / valid + mel_loss_2.sum() / valid
-        loss_gate = self.bce_loss(gate_out, gate_target)
-
-        attention_kl = torch.tensor(0.0, device=mel_out.device)
+        alignments = model_outputs[3]
+        target = None
         if len(alignments) > 1 and text_lengths is not None:
-            attn_weights = torch.stack(list(alignments), dim=1)                  # (B, T_dec, T_enc_max)
-            T_dec = attn_weights.shape[1]
-            diagonal_target = self.create_diagonal_attention_target(text_lengths, T_dec, alignments)
-            attn_safe = attn_weights.clamp_min(1e-8)
-            log_pred = attn_safe.log()
-            attention_kl = F.kl_div(log_pred, diagonal_target, reduction="batchmean") / T_dec
-            attention_kl = torch.clamp(attention_kl, max=150.0)
-            attn_entropy = -(attn_safe * log_pred).sum(dim=2).mean()
-            if attn_entropy <= self.entropy_target:
-                ratio = (attn_entropy / self.entropy_target).clamp_min(0.0)
-                self.current_attention_weight = max(self.min_attn_weight, self.attn_weight_start * ratio.item())
-            else:
-                self.current_attention_weight = self.attn_weight_start
-
-        total_loss = loss_mel + loss_gate + self.current_attention_weight * attention_kl
+            target = self.create_diagonal_attention_target(text_lengths, len(alignments), alignments)
+        loss_mel, loss_gate, attention_kl, entropy = loss_terms(model_outputs, targets, target)
+        if target is not None:
+            self.current_attention_weight = self.attention_weight(entropy)
+        total = loss_mel + loss_gate + self.current_attention_weight * attention_kl
         self.global_step += 1
-        return total_loss, loss_mel, loss_gate, attention_kl
+        return total, loss_mel, loss_gate, attention_kl

@@ -33,6 +33,24 @@ def test_loss_oracle_matches_reference_golden(step):
     assert util.maxdiff(LO.diagonal_attention_target(tl, 12, step), g[f"s{step}_target"]) <= 1e-6
 
 
+@pytest.mark.parametrize("step", STEPS)
+def test_product_loss_terms_match_reference_golden(step):
+    """The device-agnostic part of b200taco.loss (everything but the target kernel) on the CPU, fed the golden target."""
+    from b200taco.loss import Tacotron2Loss, annealed_sigma, loss_terms
+    g = util.golden("loss_b3")
+    outs, targets, tl = _mgl.loss_case()
+    mel, gate, kl, entropy = loss_terms(outs, targets, g[f"s{step}_target"])
+    crit = Tacotron2Loss()
+    weight = crit.attention_weight(entropy)
+    total = mel + gate + weight * kl
+    for got, ref in zip((total, mel, gate, kl, weight), g[f"s{step}_losses"]):
+        assert rel(got, ref) <= 2e-6, (float(got), float(ref))
+    assert util.maxdiff(annealed_sigma(tl, step, crit.sigma_warmup_steps), LO.sigma_schedule(tl, step)) == 0.0
+    # without text lengths there is no guided-attention term (train.py:196)
+    mel0, gate0, kl0, ent0 = loss_terms(outs, targets, None)
+    assert float(kl0) == 0.0 and ent0 is None and rel(mel0, mel) == 0.0
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("step", STEPS)
 def test_device_loss_matches_reference_golden(step):
