@@ -26,8 +26,8 @@ own decoded lengths.
                 bounded sample of the same workload, rank 0, N=1 only
   b1            BASELINE config 3: B=1, T=200 decoder step latency in microseconds
 
---impl reference times the reference's CPU implementation of the path (oracle port: the
-reference is Python and cannot travel to the GPU box) on the same config.
+--impl reference times the reference's own CPU implementation of the path: the unmodified reference model staged in
+oracle/_ref by oracle/make_ref.py (the oracle port only if that was never staged), same ids / weights / cap.
 N>1 (under torchrun): every rank decodes its own batches (weak scaling, no data-path collective).
 """
 import argparse
@@ -283,7 +283,7 @@ def run_b200(args, rank, world, local_rank):
         }
         if world == 1:
             out["b1"] = bench_b1(model, eng, synth, dev, l2_gbps, hbm)
-            out["cpu_baseline"] = cpu_baseline(synth, steps=1, cap=200)
+            out["cpu_baseline"] = cpu_baseline(synth, steps=3)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -319,46 +319,73 @@ def bench_b1(model, eng, synth, dev, l2_gbps, hbm):
             "x_of_l2_roofline": us / (BYTES_PER_STEP_C3 / l2_gbps / 1e3), "frac_of_hbm_peak": ach / hbm}
 
 
-def cpu_port_model(synth):
-    """CPU oracle port of the reference: same seeded weights, same synthetic ids (checker/baseline only)."""
+def _cpu_weights(synth, encoder_fn):
+    """The GPU arm's weight set on the CPU: seed 1234 default init + planted stop counter centred on this batch's mean
+    encoder output (computed by `encoder_fn` on the CPU; the GPU arm centres on its own encoder output, equal to ~1e-6),
+    decoder LSTM matrices rounded to bf16-representable values."""
     from b200taco.model import Tacotron2
     sd = synth.seeded_state_dict(Tacotron2)
-    with torch.no_grad():
-        synth.round_to_bf16_(sd)
-    return sd
-
-
-def cpu_baseline(synth, steps, cap):
-    from oracle import tacotron2_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
-    sd = cpu_port_model(synth)
     ids = synth.phoneme_ids(B, T, seed=0)
     with torch.no_grad():
-        O.tacotron2_inference(sd, ids, max_len_cap=10)                  # warm-up
+        center = encoder_fn(sd, ids).mean((0, 1))
+        synth.plant_stop_counter_(sd, ctx_center=center, **PLANT)
+        synth.round_to_bf16_(sd)
+    return sd, ids
+
+
+def cpu_baseline(synth, steps, cap=CAP):
+    """The reference's own CPU path on the host cores, same ids / weights / cap as the GPU arm.  `kind: "reference"` = the
+    unmodified reference model staged in oracle/_ref by oracle/make_ref.py (Tacotron2.inference, src/model.py:482);
+    `kind: "port"` (fallback when oracle/_ref was never staged) = oracle/tacotron2_oracle.py, which issues the same ATen ops.
+    The reference stops the whole batch when the FIRST row's gate fires (F7, src/model.py:327) and returns B x S frames;
+    its per-step cost does not depend on the step index, so B x S / t is its frame rate at batch 32 whatever S is."""
+    from oracle import tacotron2_oracle as O
+    from oracle.make_ref import load_reference
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = load_reference()
+    if ref is not None:
+        model = ref.Tacotron2().eval()
+        model._projection_bias_initialized = True
+
+        def enc(sd, ids):
+            model.load_state_dict(sd)
+            return model.encoder(ids)
+        sd, ids = _cpu_weights(synth, enc)
+        model.load_state_dict(sd)
+        run = lambda c: model.inference(ids, max_len_cap=c)           # noqa: E731
+        kind = "reference"
+    else:
+        sd, ids = _cpu_weights(synth, O.encoder)
+        run = lambda c: O.tacotron2_inference(sd, ids, max_len_cap=c)  # noqa: E731
+        kind = "port"
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):      # F6 debug prints
+        run(10)                                                           # warm-up
         t0 = time.perf_counter()
         for _ in range(steps):
-            out = O.tacotron2_inference(sd, ids, max_len_cap=cap)
+            out = run(cap)
         dt = time.perf_counter() - t0
     S = out[1].shape[1]
-    return {"value": steps * B * S / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{steps} x (B=32, T=150, decoder capped at {cap} frames, default init): encoder + "
-                      f"{cap + 1} decode steps + postnet; per-step cost is length independent",
-            "seconds": dt}
+    return {"value": steps * B * S / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{steps} x Tacotron2.inference(ids(32,150), max_len_cap={cap}) with the GPU arm's ids and weights (planted "
+                      f"stop counter): encoder + {S + 1} decode steps + postnet, batch-wide stop after {S} frames (F7), "
+                      f"frames counted = 32 x {S}",
+            "frames_per_call": B * S, "seconds": dt}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return None
     from b200taco import synth
-    cap = 100
-    cpu_baseline(synth, 1, 10)
     t0 = time.perf_counter()
-    r = cpu_baseline(synth, max(1, args.steps), cap)
+    r = cpu_baseline(synth, max(1, args.steps))
     ms = (time.perf_counter() - t0) * 1e3
     return {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["seconds"] * 1e3 / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": r["sample"], "device": "host CPU"},
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "text_len": T, "cap": CAP,
+                       "weights": "seed 1234 default init + planted stop counter (rate 8e-4, jitter 6e-3)",
+                       "frames_counted": "B x S of the reference's own batch-wide stop (every row is still unfinished at S)",
+                       "sample": r["sample"], "device": "host CPU", "arm": r["kind"]},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_ms": ms}

@@ -1851,7 +1851,10 @@ int launch_tc(const KParams& kp, int ncta, bool clusters, cudaStream_t stream) {
         at[0].val.clusterDim.x = GS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         at[1].id = cudaLaunchAttributeCooperative;
         at[1].val.cooperative = 1;
-        cfg.attrs = at; cfg.numAttrs = 2;
+        // TACO_TC_COOP=0 (profiling aid): plain cluster launch; the grid was sized by cudaOccupancyMaxActiveClusters, so on an
+        // otherwise idle device every CTA is still co-resident
+        static const bool coop = [] { const char* e = getenv("TACO_TC_COOP"); return !(e && e[0] == '0'); }();
+        cfg.attrs = at; cfg.numAttrs = coop ? 2 : 1;
         TACO_CUDA(cudaLaunchKernelEx(&cfg, kern, kp));
         launch_counter()++;
         return B200TACO_OK;
@@ -2236,7 +2239,7 @@ int dispatch_bp(int BP, const KParams& kp, int ncta, cudaStream_t stream) {
 
 struct ScratchLayout {
     size_t act16, zpart;
-    size_t act, pqpart, melpart, ctx_bj, attn_prev, attn_cum, wtmp, apart, ctrl, total;
+    size_t act, pqpart, melpart, ctx_bj, attn_prev, attn_cum, wtmp, apart, ctrl, res, total;
     size_t zero_begin, zero_end;
 };
 
@@ -2261,6 +2264,7 @@ ScratchLayout scratch_layout(int B, int T) {
     L.wtmp = take((size_t)B * Tp * 4);
     L.apart = take((size_t)B * MAX_NS * APART * 4);
     L.zpart = take((size_t)GEMM_CTAS * GS * ROWS_PER_CTA * BPT * 4);
+    L.res = take(decoder_res_scratch_bytes(B, T));                        // exchange ring of the resident kernel (decoder_res.cu)
     L.total = off;
     return L;
 }
@@ -2317,6 +2321,7 @@ int decoder_run(const b200taco_handle* h, const DecoderArgs& a, cudaStream_t str
     const ScratchLayout L = scratch_layout(a.B, a.T);
     TACO_REQUIRE(a.scratch_bytes >= L.total, B200TACO_ERR_STATE, "decoder scratch too small: %zu < %zu",
                  a.scratch_bytes, L.total);
+    if (decoder_res_supported(h, a)) return decoder_res_run(h, a, static_cast<uint8_t*>(a.scratch) + L.res, stream);
     int ncta = h->num_sms;
     const int BP = batch_tile(h, a.B);
     // tensor-core path: split-K groups as thread-block clusters (DSMEM exchange) when enough clusters are

@@ -109,6 +109,11 @@ bool decoder_uses_tensor_cores(const b200taco_handle* h, int B);
 int decoder_pack_p_all(const b200taco_handle* h, const float* Y, void* P, int B, int S, cudaStream_t stream);
 int decoder_run(const b200taco_handle* h, const DecoderArgs& a, cudaStream_t stream);
 
+// decoder_res.cu: weight-resident, barrier-free kernel for one or two free-running utterances (bf16 weights)
+bool decoder_res_supported(const b200taco_handle* h, const DecoderArgs& a);
+size_t decoder_res_scratch_bytes(int B, int T);
+int decoder_res_run(const b200taco_handle* h, const DecoderArgs& a, void* scratch, cudaStream_t stream);
+
 // api.cu: layout of the decoder's training "saved" buffer (float offsets)
 struct DecSaved { size_t frames, y1, y2, pm, ga, ca, ah, gd, cd, dh, ctx, total; };
 DecSaved dec_saved(int B, int T, int S);

@@ -148,8 +148,27 @@ def test_free_running_planted_stop_golden():
         assert util.maxdiff(coarse[b, :n].cpu(), gold["solo_mel_coarse"][b, :n]) <= TOL_MEL
 
 
+@pytest.mark.parametrize("B", [1, 2])
+def test_resident_small_batch_stop_rules_vs_oracle(B):
+    """B <= 2 free-running decodes take the weight-resident, barrier-free kernel (decoder_res.cu): its stop rules - batch wide
+    (F7, src/model.py:327), threshold override, frame cap, per utterance (train.py:71-79) - against the oracle, indices exact."""
+    gold = util.golden("infer_planted_b5_t41")
+    sd = util.weights("planted", True, ctx_center=gold["ctx_center"])
+    ids = synth.phoneme_ids(5, 41, seed=7)[:B].contiguous()
+    m = gpu_model(sd)
+    for kw in ({}, {"gate_threshold": 0.3}, {"max_len_cap": 9}):
+        with torch.no_grad():
+            ref = O.tacotron2_inference(sd, ids, **kw)
+        check(m.inference(ids.cuda(), **kw), dict(mel_post=ref[0], mel_coarse=ref[1], gate=ref[2], align=util.stack(ref[3])))
+    post, coarse, gate, aligns, lengths = m.inference_per_utterance(ids.cuda())
+    assert lengths.tolist() == gold["solo_lengths"][:B].tolist()
+    assert coarse.shape[1] == int(gold["solo_lengths"][:B].max())
+    for b, n in enumerate(lengths.tolist()):
+        assert util.maxdiff(coarse[b, :n].cpu(), gold["solo_mel_coarse"][b, :n]) <= TOL_MEL
+
+
 # ------------------------------------------------------------------ oracle on the same seeded inputs
-@pytest.mark.parametrize("B,T", [(1, 1), (1, 200), (2, 17), (3, 257), (7, 64), (8, 150), (13, 40), (16, 150),
+@pytest.mark.parametrize("B,T", [(1, 1), (1, 200), (1, 1024), (2, 17), (2, 200), (2, 600), (3, 257), (7, 64), (8, 150), (13, 40), (16, 150),
                                  (32, 150), (33, 90), (64, 150), (64, 7)])
 def test_shape_sweep_free_running_vs_oracle(B, T):
     """Every batch-tile specialisation (1,2,4,...,64) and slice count, stress weights (F12), 12 steps."""
