@@ -265,6 +265,12 @@ B200TACO_API int32_t b200taco_measure_sync_costs(int64_t* out8, void* stream);
 B200TACO_API int32_t b200taco_decoder_profile(b200taco_handle* h, int64_t* out, int32_t n, void* stream);
 
 /*
+ * Measurement aid: globaltimer values (ns) that thread 0 of every CTA of the weight-resident small-batch decoder kernel
+ * recorded at its stage boundaries during ONE decode step (environment TACO_RES_TRACE=<step> at launch time), 16 per CTA.
+ */
+B200TACO_API int32_t b200taco_decoder_trace(b200taco_handle* h, int64_t* out, int32_t n, void* stream);
+
+/*
  * Unit-test aid for the tcgen05 path: D[128][32] (fp32) = A[128][K] . B[32][K]^T with bf16
  * operands (row-major device arrays), one CTA, accumulators in TMEM.  K a multiple of 64.
  * variant 0 is the production descriptor convention; other values are bring-up experiments.
@@ -281,6 +287,59 @@ B200TACO_API int32_t b200taco_debug_umma_gemm(const void* d_A, const void* d_B, 
  */
 B200TACO_API int32_t b200taco_guided_attention_target(const int64_t* d_text_lengths, const float* d_sigma, int32_t B, int32_t S,
                                          int32_t Tmax, float* d_target, void* stream);
+
+/*
+ * The whole Tacotron2Loss.forward of the reference (train.py:173-217) on the device, every scalar left in device memory
+ * (the reference reads entropy and sigma back with .item() every step, train.py:151,157,208):
+ *   masked L1 of mel_coarse and mel_post (B,S,80) against mel_target (B,80,S) over the frames s < mel_lengths[b]
+ *   (train.py:176-192), BCE-with-logits of gate (B,S) against gate_target (B,S) (train.py:194), and - when d_align is not
+ *   NULL - KL(guided target || clamp_min(attention, 1e-8)) / B / S clamped to 150 and the mean attention entropy
+ *   (train.py:197-204) over align (S,B,T) with the guided target of b200taco_guided_attention_target recomputed on the fly,
+ *   then the entropy-adaptive weight (train.py:205-210: w_start if entropy > entropy_target else max(w_min, w_start *
+ *   entropy / entropy_target); without attention term the weight stays w_current) and the total (train.py:215).
+ *   d_out8: [mel, gate, kl, entropy, weight, total, kl before the clamp, number of valid mel bins].
+ *   d_scratch: b200taco_loss_scratch_bytes(B, S) bytes.  Three launches (two without attention term), fixed summation order.
+ * b200taco_loss_bwd: gradients with respect to mel_post, mel_coarse, gate and (d_g_align not NULL) the alignments for the
+ *   upstream gradient d_grad_out8 of the 8 results (entries 0, 1, 2, 5 are used; the weight is a constant as in the reference,
+ *   where it passes through .item()).
+ * b200taco_gate_targets: the stop-token targets of the training loop (train.py:505-508), out (B,S) = 1 from frame
+ *   mel_lengths[b] - 1 on, else 0.
+ */
+B200TACO_API int64_t b200taco_loss_scratch_bytes(int32_t B, int32_t S);
+B200TACO_API int32_t b200taco_loss_fwd(const float* d_mel_post, const float* d_mel_coarse, const float* d_mel_target,
+                                       const float* d_gate, const float* d_gate_target, const int64_t* d_mel_lengths,
+                                       const float* d_align, const int64_t* d_text_lengths, const float* d_sigma, int32_t B,
+                                       int32_t S, int32_t T, float w_start, float w_min, float entropy_target, float w_current,
+                                       float* d_scratch, float* d_out8, void* stream);
+B200TACO_API int32_t b200taco_loss_bwd(const float* d_mel_post, const float* d_mel_coarse, const float* d_mel_target,
+                                       const float* d_gate, const float* d_gate_target, const int64_t* d_mel_lengths,
+                                       const float* d_align, const int64_t* d_text_lengths, const float* d_sigma, int32_t B,
+                                       int32_t S, int32_t T, const float* d_out8, const float* d_grad_out8, float* d_g_post,
+                                       float* d_g_coarse, float* d_g_gate, float* d_g_align, void* stream);
+B200TACO_API int32_t b200taco_gate_targets(const int64_t* d_mel_lengths, int32_t B, int32_t S, float* d_out, void* stream);
+
+/*
+ * Vocoder hand-off.  The reference hands mel_outputs_postnet.transpose(1, 2), i.e. (B, 80, S), to the
+ * vocoder (inference.py:71) and trims every utterance to its own stop frame on the host (train.py:71-79).
+ * b200taco_postnet_fwd_vocoder = b200taco_postnet_fwd that ALSO writes the result channel major into d_mel_vocoder
+ * (B, 80, S_out), S_out <= S, zero from d_lengths[b] on (d_lengths NULL: nothing is zeroed), from the epilogue of the last
+ * postnet layer; b200taco_vocoder_layout does the same for an existing (B, S, 80) tensor.
+ */
+B200TACO_API int32_t b200taco_postnet_fwd_vocoder(b200taco_handle* h, const float* d_mel_coarse, int32_t B, int32_t S,
+                                                  const int32_t* d_lengths, int32_t S_out, float* d_mel_post, float* d_mel_vocoder,
+                                                  void* d_workspace, size_t workspace_bytes, void* stream);
+B200TACO_API int32_t b200taco_vocoder_layout(const float* d_mel, const int32_t* d_lengths, int32_t B, int32_t S, int32_t S_out,
+                                             float* d_out, void* stream);
+
+/*
+ * Batch assembly on the device (TextMelCollate.__call__, src/data_utils.py:45-84): the B ragged samples of a
+ * batch arrive as two flat arrays - text ids (sum of L_i int64) and mels (sample i stored (80, S_i) row major, sum of 80 S_i
+ * floats) - with offsets (B + 1 entries; mel offsets count FRAMES).  Row i of text_padded (B, Lmax) / mel_padded (B, 80, Smax)
+ * receives sample d_order[i] (the descending text-length order of src/data_utils.py:54-56), zero padded.
+ */
+B200TACO_API int32_t b200taco_collate(const int64_t* d_text_flat, const int64_t* d_text_offsets, const float* d_mel_flat,
+                                      const int64_t* d_mel_offsets, const int32_t* d_order, int32_t B, int32_t Lmax, int32_t Smax,
+                                      int64_t* d_text_padded, float* d_mel_padded, void* stream);
 
 /* Number of kernels this library launched on this thread since the last reset. */
 B200TACO_API int64_t b200taco_launch_count(int32_t reset);

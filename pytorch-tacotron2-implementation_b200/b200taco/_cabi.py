@@ -85,14 +85,24 @@ SIGNATURES = {
                                                     C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200taco_postnet_fwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b200taco_postnet_fwd_vocoder": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b200taco_vocoder_layout": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "b200taco_collate": (C.c_int32, [C.c_void_p] * 5 + [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200taco_guided_attention_target": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                                      C.c_void_p, C.c_void_p]),
+    "b200taco_loss_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "b200taco_loss_fwd": (C.c_int32, [C.c_void_p] * 9 + [C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200taco_loss_bwd": (C.c_int32, [C.c_void_p] * 9 + [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 7),
+    "b200taco_gate_targets": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "b200taco_measure_l2_read": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_int32,
                                              C.POINTER(C.c_float), C.c_void_p]),
     "b200taco_measure_stream": (C.c_int32, [C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                             C.POINTER(C.c_float), C.c_void_p]),
     "b200taco_measure_sync_costs": (C.c_int32, [C.POINTER(C.c_int64), C.c_void_p]),
     "b200taco_decoder_profile": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_void_p]),
+    "b200taco_decoder_trace": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_void_p]),
     "b200taco_debug_umma_gemm": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "b200taco_launch_count": (C.c_int64, [C.c_int32]),
     # ---- training (stage by stage, include/b200taco.h)

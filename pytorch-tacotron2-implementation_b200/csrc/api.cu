@@ -404,11 +404,11 @@ B200TACO_API int32_t b200taco_decoder_train_fwd(b200taco_handle* h, const float*
     return decoder_run(h, a, st);
 }
 
-B200TACO_API int32_t b200taco_postnet_fwd(b200taco_handle* h, const float* d_mel_coarse, int32_t B, int32_t S, float* d_mel_post,
-                             void* d_workspace, size_t workspace_bytes, void* stream) {
+static int postnet_run(b200taco_handle* h, const float* d_mel_coarse, int32_t B, int32_t S, float* d_mel_post, const ChannelMajorOut& cm,
+                       void* d_workspace, size_t workspace_bytes, void* stream, const char* who) {
     TACO_TRY(check_handle(h, true));
-    TACO_REQUIRE(d_mel_coarse && d_mel_post && d_workspace, B200TACO_ERR_INVALID, "postnet_fwd: null pointer");
-    TACO_REQUIRE(B >= 1 && S >= 1, B200TACO_ERR_INVALID, "postnet_fwd: B %d, S %d", B, S);
+    TACO_REQUIRE(d_mel_coarse && d_mel_post && d_workspace, B200TACO_ERR_INVALID, "%s: null pointer", who);
+    TACO_REQUIRE(B >= 1 && S >= 1, B200TACO_ERR_INVALID, "%s: B %d, S %d", who, B, S);
     const PostnetWs ws = postnet_ws(d_workspace, B, S);
     TACO_REQUIRE(workspace_bytes >= ws.total, B200TACO_ERR_STATE, "postnet workspace too small: %zu < %zu", workspace_bytes,
                  ws.total);
@@ -423,11 +423,26 @@ B200TACO_API int32_t b200taco_postnet_fwd(b200taco_handle* h, const float* d_mel
         float* dst = last ? d_mel_post : bufs[i & 1];
         TACO_TRY(dense_layer(h, src, c_in, h->post_conv_w[i], h->post_conv_wtc[i], h->post_conv_scale[i], h->post_conv_shift[i],
                                       last ? d_mel_coarse : nullptr, N_MELS, dst, c_out, n, S, c_in, c_out, POST_KERNEL,
-                                      last ? ACT_NONE : ACT_TANH, false, st));
+                                      last ? ACT_NONE : ACT_TANH, false, st, last ? cm : ChannelMajorOut()));
         src = dst;
         c_in = c_out;
     }
     return B200TACO_OK;
+}
+
+B200TACO_API int32_t b200taco_postnet_fwd(b200taco_handle* h, const float* d_mel_coarse, int32_t B, int32_t S, float* d_mel_post,
+                             void* d_workspace, size_t workspace_bytes, void* stream) {
+    return postnet_run(h, d_mel_coarse, B, S, d_mel_post, ChannelMajorOut(), d_workspace, workspace_bytes, stream, "postnet_fwd");
+}
+
+B200TACO_API int32_t b200taco_postnet_fwd_vocoder(b200taco_handle* h, const float* d_mel_coarse, int32_t B, int32_t S,
+                                                  const int32_t* d_lengths, int32_t S_out, float* d_mel_post, float* d_mel_vocoder,
+                                                  void* d_workspace, size_t workspace_bytes, void* stream) {
+    TACO_REQUIRE(d_mel_vocoder != nullptr && S_out >= 1 && S_out <= S, B200TACO_ERR_INVALID, "postnet_fwd_vocoder: S_out %d outside [1, %d]",
+                 S_out, S);
+    ChannelMajorOut cm;
+    cm.y = d_mel_vocoder; cm.lengths = d_lengths; cm.ld = S_out;
+    return postnet_run(h, d_mel_coarse, B, S, d_mel_post, cm, d_workspace, workspace_bytes, stream, "postnet_fwd_vocoder");
 }
 
 B200TACO_API int32_t b200taco_measure_l2_read(void* d_buf, size_t bytes, int32_t iters, float* gbps, void* stream) {
@@ -450,6 +465,16 @@ B200TACO_API int32_t b200taco_decoder_profile(b200taco_handle* h, int64_t* out, 
     TACO_REQUIRE(h->last_profile != nullptr, B200TACO_ERR_STATE, "decoder_profile: no decoder launch yet");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     TACO_CUDA(cudaMemcpyAsync(out, h->last_profile, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    TACO_CUDA(cudaStreamSynchronize(st));
+    return B200TACO_OK;
+}
+
+B200TACO_API int32_t b200taco_decoder_trace(b200taco_handle* h, int64_t* out, int32_t n, void* stream) {
+    TACO_TRY(check_handle(h, false));
+    TACO_REQUIRE(out != nullptr && n >= 1 && n <= 160 * 64 + 1024, B200TACO_ERR_INVALID, "decoder_trace: bad output (n=%d)", n);
+    TACO_REQUIRE(h->last_trace != nullptr, B200TACO_ERR_STATE, "decoder_trace: the last decoder launch recorded no trace (TACO_RES_TRACE)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TACO_CUDA(cudaMemcpyAsync(out, h->last_trace, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     TACO_CUDA(cudaStreamSynchronize(st));
     return B200TACO_OK;
 }

@@ -9,9 +9,15 @@
 //    the whole launch: the rows multiplied on the critical path (attention LSTM x prenet, decoder LSTM x context) and the
 //    attention LSTM x context rows in registers (40 packed bf16x2 registers per thread), the three 1024-wide recurrent /
 //    attention-hidden ranges in shared memory (192 KB).  No weight byte moves during the frame loop.
-//  * the remaining CTAs (20 on a B200) split into "attention" CTAs - each owns a slice of the encoder positions of one
-//    utterance (memory and processed memory resident in shared memory) and a few rows of the query projection - and
-//    "frame" CTAs, which own rows of the mel / gate projection and of the prenet (weights in registers / shared memory).
+//  * the remaining CTAs (20 on a B200) split into "attention" CTAs and 8 "frame" CTAs.  The attention CTAs of an utterance
+//    split the ATTENTION DIMENSIONS (and the context dimensions), not the encoder positions: each owns rows of the query
+//    projection, the matching columns of processed memory / location features for ALL positions, and a column slice of the
+//    encoder memory.  It needs nobody else's processed query (no exchange), publishes its partial energies e_j[t], sums
+//    everybody's partials, runs the (redundant, deterministic) softmax over all positions and finishes its own context
+//    dimensions: two exchanges per attention instead of four, and the attention weights never leave the CTA.  Location
+//    convolution and location dense layer (both bias free, src/model.py:96-101) are applied as ONE composed filter
+//    G[a][c][k] = sum_f W_dense[a][f] W_conv[f][c][k], so a CTA only computes its own attention dimensions.
+//    The frame CTAs own rows of the mel / gate projection and of the prenet (weights in registers / shared memory).
 //  * every value that crosses CTAs travels as a 64-bit word {fp32 value, step tag} written with one relaxed store and
 //    polled by its consumers (the "LL" protocol of collective libraries): data and flag arrive together, so an exchange
 //    costs one L2 write + one L2 read instead of fence + atomic + spin + dependent load, there is no grid barrier, and a
@@ -34,22 +40,25 @@ constexpr int RT = 512;                       // threads per CTA
 constexpr int RWARPS = RT / 32;
 constexpr int DEPTH = 4;                      // exchange ring depth (steps)
 constexpr int NREP = 4;                       // replicas of every broadcast vector: consumer CTA c polls replica c % NREP
-constexpr int PQR_MAX = RWARPS;               // query projection rows per attention CTA (one warp per row)
-constexpr int MPR_MAX = RWARPS;               // mel / gate projection rows per frame CTA (one warp per row, weights in registers)
-constexpr int P2R_MAX = 2 * RWARPS;           // prenet layer-2 rows per frame CTA
-constexpr int MIN_A = 18, MAX_A = 32;
+constexpr int NFR = 8;                        // frame CTAs
+constexpr int MPR = (PROJ_OUT + NFR - 1) / NFR;   // mel / gate projection rows per frame CTA (one warp per row, weights in registers)
+constexpr int MELW = 12;                      // exchange words per frame CTA (MPR padded to whole 32-byte sectors)
+constexpr int P2R = PRENET / NFR;             // prenet layer-2 rows per frame CTA (one half-warp per row)
+constexpr int MAX_NSL = 16;                   // attention CTAs per utterance
 constexpr int HALO = (LOC_K - 1) / 2;
-constexpr int PARTW = 8 + EMB;                // words per attention partial: max, sum, pad, context[512] at +8
-constexpr int LOC_LD = 36;
+constexpr int W0 = 16;                        // zeros in front of the attention-weight windows
+constexpr int TB = 4;                         // positions per work item of the location filter
+constexpr int NTAP = 2 * LOC_K;
 constexpr uint32_t STOP_BIT = 0x80000000u;
 constexpr uint32_t SPIN_LIMIT = 1u << 25;     // polls of one word before the kernel traps (~10 s)
 constexpr int PROF_WORDS = 24;
+constexpr int TRACE_EV = 64, TRACE_WORDS = 160 * TRACE_EV + 2 * 512;   // per-CTA event times of one decode step (measurement aid)
 
 static_assert(NREP == 4, "the four gate lanes of a hidden unit publish the four replicas");
-static_assert(RT == 4 * ATT_DIM && RT == EMB && RT == 2 * PRENET && 2 * RT == RNN, "thread maps");
+static_assert(RT == 2 * PRENET && MPR <= RWARPS && MPR <= MELW && P2R == 2 * RWARPS && MELW % 4 == 0, "thread maps");
 
 struct RParams {
-    int B, T, Tp, NATT, NFR, NSL, SL, DPC, PQR, MPR, P2R, max_steps, stop_mode, mem_resident, fine;
+    int B, T, Tp, NATT, NSL, DA, DC, max_steps, stop_mode, mem_resident, bg_sleep, bg_backoff;
     float thr;
     const uint32_t *w_attn, *w_dec;           // bf16 pairs: [128 cta][K][16 words], word w = rows (2w, 2w+1) of the CTA
     const float *bias_attn, *bias_dec, *wq_slices, *wproj_slices, *wproj_ctxT, *proj_bias, *prenet1T, *prenet2T, *loc_conv,
@@ -60,24 +69,24 @@ struct RParams {
     int32_t *lengths, *steps_run;
     uint64_t* xch;                            // exchange ring
     unsigned long long* prof;
+    unsigned long long* trace;               // [cta][TRACE_EV] globaltimer of step trace_step, or nullptr
+    int trace_step;
 };
 
 // word offsets of the exchanged vectors inside one ring slot
 struct XL {
-    int p, ah, ctx, dh, pq, part, mel, w, words;
+    int p, ah, ctx, dh, ep, mel, words;
 };
-__host__ __device__ inline XL xlayout(int BP, int Tp) {
+__host__ __device__ inline XL xlayout(int BP, int Tp, int NSL) {
     XL x;
     int o = 0;
     x.p = o;    o += NREP * BP * PRENET;      // prenet output            frame -> gate
     x.ah = o;   o += NREP * BP * RNN;         // attention hidden         gate -> gate, attention
     x.ctx = o;  o += NREP * BP * EMB;         // attention context        attention -> gate, frame
     x.dh = o;   o += NREP * BP * RNN;         // decoder hidden           gate -> gate, frame
-    x.pq = o;   o += BP * ATT_DIM;            // processed query          attention -> attention
-    x.part = o; o += MAX_A * PARTW;           // per-slice softmax/context partials  attention -> attention
-    x.mel = o;  o += BP * PROJ_PAD;           // mel frame + gate logit   frame -> frame, attention (gate)
-    x.w = o;    o += BP * Tp;                 // attention weights        attention -> attention (window halos)
-    x.words = (o + 1) & ~1;
+    x.ep = o;   o += BP * NSL * Tp;           // partial energies         attention -> attention (same utterance)
+    x.mel = o;  o += BP * NFR * MELW;         // mel frame + gate logit   frame -> frame, attention (gate)
+    x.words = (o + 15) & ~15;
     return x;
 }
 
@@ -97,30 +106,32 @@ __device__ __forceinline__ void ll_ld2(const uint64_t* p, uint64_t& a, uint64_t&
 __device__ __noinline__ void res_spin_fail() { __trap(); }
 __device__ __forceinline__ bool tag_ok(uint64_t w, uint32_t tag) { return (((uint32_t)(w >> 32) ^ tag) & ~STOP_BIT) == 0u; }
 
+// one word; every lane of the warp calls it (with its own address) and the warp leaves together
 __device__ __forceinline__ float ll_wait1(const uint64_t* p, uint32_t tag) {
     uint64_t w = ll_ld1(p);
-    if (!tag_ok(w, tag)) {
-        uint32_t n = 0;
-        do {
-            w = ll_ld1(p);
-            if (++n > SPIN_LIMIT) res_spin_fail();
-        } while (!tag_ok(w, tag));
+    uint32_t n = 0;
+    while (!__all_sync(0xffffffffu, tag_ok(w, tag))) {
+        w = ll_ld1(p);
+        if (++n > SPIN_LIMIT) res_spin_fail();
     }
     return __uint_as_float((uint32_t)w);
 }
 
-// n words (even, 16-byte aligned) -> n floats in shared memory; returns the OR of the words' stop bits
-__device__ __forceinline__ uint32_t ll_gather(const uint64_t* src, float* dst, int n, uint32_t tag, int tid) {
+// n words (even, 16-byte aligned) -> n floats in shared memory; returns the OR of the words' stop bits.  backoff_ns > 0:
+// a gather nobody is waiting for (the recurrent contractions of the NEXT cell evaluation) sleeps between polls, so that its
+// polling traffic does not sit in front of the stores and polls of the CTAs on the critical path
+__device__ __forceinline__ uint32_t ll_gather(const uint64_t* src, float* dst, int n, uint32_t tag, int tid, unsigned backoff_ns = 0) {
     uint32_t stop = 0u;
-    for (int i = tid; i < n / 2; i += RT) {
+    for (int i = tid; i < n / 2; i += RT) {              // n / 2 is a multiple of 32: whole warps
         uint64_t a, b;
         ll_ld2(src + 2 * i, a, b);
-        if (!(tag_ok(a, tag) && tag_ok(b, tag))) {
-            uint32_t it = 0;
-            do {
-                ll_ld2(src + 2 * i, a, b);
-                if (++it > SPIN_LIMIT) res_spin_fail();
-            } while (!(tag_ok(a, tag) && tag_ok(b, tag)));
+        uint32_t it = 0;
+        // the warp leaves the loop as ONE: a lane-wise exit splits the warp, and the shuffles / barriers behind a split warp
+        // were measured to cost ~2 us (divergent-shuffle slow path)
+        while (!__all_sync(0xffffffffu, tag_ok(a, tag) && tag_ok(b, tag))) {
+            if (backoff_ns) __nanosleep(backoff_ns);
+            ll_ld2(src + 2 * i, a, b);
+            if (++it > SPIN_LIMIT) res_spin_fail();
         }
         *reinterpret_cast<float2*>(dst + 2 * i) = make_float2(__uint_as_float((uint32_t)a), __uint_as_float((uint32_t)b));
         stop |= (uint32_t)((a | b) >> 32) & STOP_BIT;
@@ -212,6 +223,22 @@ __device__ __forceinline__ float lstm_cell(const float* z, const float* bias, fl
     return h;
 }
 
+#define RES_EVW(i)                                                                                 \
+    do {                                                                                           \
+        if (p.trace != nullptr && (threadIdx.x & 31) == 0 && s == p.trace_step)                    \
+            p.trace[(size_t)blockIdx.x * TRACE_EV + (i) + (threadIdx.x >> 5)] = global_timer_ns(); \
+    } while (0)
+#define RES_EVT(slot)                                                                              \
+    do {                                                                                           \
+        if (p.trace != nullptr && s == p.trace_step)                                               \
+            p.trace[160 * TRACE_EV + (slot) * 512 + threadIdx.x] = global_timer_ns();              \
+    } while (0)
+#define RES_EV(i)                                                                                  \
+    do {                                                                                           \
+        if (p.trace != nullptr && threadIdx.x == 0 && s == p.trace_step)                           \
+            p.trace[(size_t)blockIdx.x * TRACE_EV + (i)] = global_timer_ns();                      \
+    } while (0)
+
 // =====================================================================================================================
 // stop rule, evaluated identically by every frame / attention CTA from the published gate logits: batch wide
 // (src/model.py:327) or per utterance (train.py:71-79 with the steps > 1 guard)
@@ -274,13 +301,18 @@ __device__ __forceinline__ void gate_role(const RParams& p, uint8_t* smem, const
     float c_a = 0.f, c_d = 0.f;
     const int rep = cta % NREP, unit0 = cta * UNITS_PER_CTA;
     const int total_steps = p.max_steps + 1;
+    // phase timers of CTA 0 (b200taco_decoder_profile): accumulated in shared memory by thread 0, so that they cost no registers
+    __shared__ unsigned long long t_acc[PROF_WORDS];
     const bool timing = cta == 0 && tid == 0;
-    unsigned long long t_phase[4] = {0ull, 0ull, 0ull, 0ull}, t_last = timing ? global_timer_ns() : 0ull;
+    if (timing) {
+        for (int i = 0; i < PROF_WORDS; ++i) t_acc[i] = 0ull;
+        t_acc[PROF_WORDS - 1] = global_timer_ns();
+    }
     auto stamp = [&](int ph) {
         if (timing) {
             const unsigned long long now = global_timer_ns();
-            t_phase[ph] += now - t_last;
-            t_last = now;
+            t_acc[ph] += now - t_acc[PROF_WORDS - 1];
+            t_acc[PROF_WORDS - 1] = now;
         }
     };
     int steps_done = 0;
@@ -291,110 +323,183 @@ __device__ __forceinline__ void gate_role(const RParams& p, uint8_t* smem, const
         const uint32_t stop = ll_gather(X + xl.p + rep * BP * PRENET, xp, BP * PRENET, tag, tid);
         if (__syncthreads_or((int)stop)) break;
         if (s > 0) stamp(3);
+        RES_EV(0);
+        if (p.trace != nullptr && tid == 0 && s == p.trace_step + 1) p.trace[(size_t)blockIdx.x * TRACE_EV + 6] = global_timer_ns();
         gemv_reg<BP, 2>(wa_p, xp, PRENET, acc_a, lane);
         reduce_rows<BP>(acc_a, z_s, warp, lane);
         __syncthreads();
         if (warp < BP) lstm_cell(z_s + warp * ROWS_PER_CTA, bias_s, c_a, X + xl.ah + warp * RNN, BP * RNN, unit0, tag, lane);
         stamp(0);
+        RES_EV(1);
         // ---- background: both cells' rows of the new attention hidden state
-        ll_gather(X + xl.ah + rep * BP * RNN, xah, BP * RNN, tag, tid);
+        if (p.bg_sleep) __nanosleep(p.bg_sleep);
+        ll_gather(X + xl.ah + rep * BP * RNN, xah, BP * RNN, tag, tid, p.bg_backoff);
         __syncthreads();
         gemv_smem<BP>(sW + (1 * RWARPS + warp) * RNN, xah, acc_d, lane);
         gemv_smem<BP>(sW + (0 * RWARPS + warp) * RNN, xah, acc_a, lane);
+        RES_EV(5);
         // ---- decoder LSTM: only the context rows wait for the attention
         ll_gather(X + xl.ctx + rep * BP * EMB, xctx, BP * EMB, tag, tid);
         __syncthreads();
         stamp(1);
+        RES_EV(2);
         gemv_reg<BP, 4>(wd_c, xctx, EMB, acc_d, lane);
         reduce_rows<BP>(acc_d, z_s, warp, lane);
         __syncthreads();
         if (warp < BP)
             lstm_cell(z_s + warp * ROWS_PER_CTA, bias_s + ROWS_PER_CTA, c_d, X + xl.dh + warp * RNN, BP * RNN, unit0, tag, lane);
         stamp(2);
+        RES_EV(3);
         // ---- background: attention LSTM x context, decoder LSTM x new decoder hidden (both for the next step)
         gemv_reg<BP, 4>(wa_c, xctx, EMB, acc_a, lane);
-        ll_gather(X + xl.dh + rep * BP * RNN, xdh, BP * RNN, tag, tid);
+        if (p.bg_sleep) __nanosleep(p.bg_sleep);
+        ll_gather(X + xl.dh + rep * BP * RNN, xdh, BP * RNN, tag, tid, p.bg_backoff);
         __syncthreads();
         gemv_smem<BP>(sW + (2 * RWARPS + warp) * RNN, xdh, acc_d, lane);
+        RES_EV(4);
         steps_done = s + 1;
     }
     if (timing) {
-        for (int i = 0; i < 4; ++i) p.prof[i] = t_phase[i];
+        for (int i = 0; i < 4; ++i) p.prof[i] = t_acc[i];
         p.prof[4] = (unsigned long long)steps_done;
     }
 }
 
+// ---- reduction of N values per lane over the 32 lanes of a warp with N - 1 (+ log2(32 / N)) shuffles instead of 5 N:
+// every halving step a lane keeps one half of its values and receives the partner's partials of that half.  On return
+// the lane holds the warp total of value index  lane >> log2(32 / N)  (fixed summation order).
+template <int N>
+__device__ __forceinline__ float multi_reduce(float (&v)[N], int lane) {
+    static_assert(N == 8 || N == 16 || N == 32, "multi_reduce width");
+    constexpr int STEPS = N == 32 ? 5 : (N == 16 ? 4 : 3);
+#pragma unroll
+    for (int st = 0; st < STEPS; ++st) {
+        const int cnt = N >> st, off = 16 >> st;
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < cnt / 2; ++i) {
+            const float send = up ? v[i] : v[i + cnt / 2];
+            const float keep = up ? v[i + cnt / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    float r = v[0];
+#pragma unroll
+    for (int off = 16 >> STEPS; off > 0; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+    return r;
+}
+
+// two tagged words (16-byte aligned pair) straight into registers
+__device__ __forceinline__ uint32_t ll_wait2(const uint64_t* p, uint32_t tag, float& x0, float& x1) {
+    uint64_t a, b;
+    ll_ld2(p, a, b);
+    uint32_t it = 0;
+    while (!__all_sync(0xffffffffu, tag_ok(a, tag) && tag_ok(b, tag))) {
+        ll_ld2(p, a, b);
+        if (++it > SPIN_LIMIT) res_spin_fail();
+    }
+    x0 = __uint_as_float((uint32_t)a);
+    x1 = __uint_as_float((uint32_t)b);
+    return (uint32_t)((a | b) >> 32) & STOP_BIT;
+}
+
 // =====================================================================================================================
-// attention CTAs: location-sensitive attention (src/model.py:117-148) on a slice of one utterance's encoder positions
-// plus PQR rows of the query projection
+// attention CTAs: location-sensitive attention (src/model.py:117-148) of ONE utterance, split over its NSL CTAs by
+// attention dimension (DA <= RW dims each: query projection rows, processed memory, composed location filter, energies)
+// and by context dimension (DC dims each).  Every contraction is split over K so that a thread multiplies exactly the
+// words it polled (no staging of the incoming vector, no shared-memory traffic for weights: they sit in registers).
+constexpr int MEMR = 20;                      // encoder positions per thread whose memory column sits in registers
 struct ASmem {
-    int wloc, v, xah, pq, winp, winc, loc, pre, e, ew, stage, ms, mem, pm, total;
+    int G, red, pq, v, winp, winc, pm, pre, ew, mx, cpart, spart, mem, SP, total;
 };
-__host__ __device__ inline ASmem a_smem(int BP, int SL, int NSL, int DPC, bool resident) {
+template <int RW>
+__host__ __device__ inline ASmem a_smem(int T, int DA, int DC, bool mem_in_smem) {
     ASmem a;
-    const int SLp = (SL + 3) & ~3;
+    const int Tp = (T + 3) & ~3;
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
-    a.wloc = take(LOC_F * 63);
-    a.v = take(ATT_DIM + 4);
-    a.xah = take(BP * RNN);
-    a.pq = take(ATT_DIM);
-    a.winp = take(SLp + 96);
-    a.winc = take(SLp + 96);
-    a.loc = take((SLp + 16) * LOC_LD);
-    a.pre = take(SLp * ATT_DIM);
-    a.e = take(SLp + 4);
-    a.ew = take(SLp + 4);
-    a.stage = take(NSL * DPC);
-    a.ms = take(2 * MAX_A);
-    a.mem = take(resident ? SL * EMB : 0);
-    a.pm = take(resident ? SL * ATT_DIM : 0);
+    a.SP = ((Tp + TB + 15) / 32) * 32 + 16;           // row stride of pm / pre: 16 mod 32 (two rows never share a bank)
+    a.G = take(NTAP * RW);
+    a.red = take(RWARPS * RW);
+    a.pq = take(RW);
+    a.v = take(RW);
+    a.winp = take(Tp + 64);
+    a.winc = take(Tp + 64);
+    a.pm = take(DA * a.SP);
+    a.pre = take(DA * a.SP);
+    a.ew = take(Tp + 80);                             // position groups of the context contraction read whole float4s
+    a.mx = take(RWARPS);
+    a.cpart = take((RT / DC) * DC);
+    a.spart = take(RT / DC + 4);
+    a.mem = take(mem_in_smem ? T * DC : 0);
     a.total = o;
     return a;
 }
 
-template <int BP>
+template <int BP, int RW>
 __device__ __forceinline__ void attn_role(const RParams& p, uint8_t* smem, const XL& xl) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int j = (int)blockIdx.x - GEMM_CTAS, cta = blockIdx.x;
-    const int NSL = p.NSL, SL = p.SL, T = p.T, DPC = p.DPC, PQR = p.PQR;
+    const int NSL = p.NSL, T = p.T, Tp = p.Tp, DA = p.DA, DC = p.DC;
     const int b = j / NSL, sl = j % NSL;                       // NATT == BP * NSL
-    const int t0 = sl * SL, n = max(0, min(T, t0 + SL) - t0);
+    const int a0 = sl * DA, na = max(0, min(ATT_DIM, a0 + DA) - a0);
+    const int d0 = sl * DC, nd = max(0, min(EMB, d0 + DC) - d0);
     const int len = p.text_lengths ? (int)p.text_lengths[b] : T;
-    const ASmem L = a_smem(BP, SL, NSL, DPC, p.mem_resident != 0);
+    const int mem_mode = p.mem_resident;                       // 2: registers, 1: shared memory, 0: L2
+    const ASmem L = a_smem<RW>(T, DA, DC, mem_mode == 1);
+    const int SP = L.SP;
     float* sm = reinterpret_cast<float*>(smem);
-    float *wloc_s = sm + L.wloc, *v_s = sm + L.v, *xah = sm + L.xah, *pq_s = sm + L.pq, *winp = sm + L.winp, *winc = sm + L.winc,
-          *loc_s = sm + L.loc, *pre_s = sm + L.pre, *e_s = sm + L.e, *ew_s = sm + L.ew, *stage_s = sm + L.stage, *ms_s = sm + L.ms;
-    const int SLp = (SL + 3) & ~3;
+    float *G_s = sm + L.G, *red_s = sm + L.red, *pq_s = sm + L.pq, *v_s = sm + L.v, *winp = sm + L.winp, *winc = sm + L.winc, *pm_s = sm + L.pm,
+          *pre_s = sm + L.pre, *ew_s = sm + L.ew, *mx_s = sm + L.mx, *cpart_s = sm + L.cpart, *spart_s = sm + L.spart;
 
-    // ---- one-off: this warp's query-projection row and this thread's location-dense column into registers
-    const int pq_row = PQR * j + warp;
-    const bool has_row = warp < PQR && pq_row < ATT_DIM;
-    float wq[32], wld[LOC_F];
+    // ---- one-off.  Query projection: thread owns k = 2 tid, 2 tid + 1 of all own rows (registers)
+    float wq0[RW], wq1[RW];
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int k = jj * 128 + lane * 4 + i;
-            wq[jj * 4 + i] = has_row ? __ldg(p.wq_slices + ((size_t)(k >> 3) * ATT_DIM + pq_row) * 8 + (k & 7)) : 0.f;
-        }
-#pragma unroll
-    for (int f = 0; f < LOC_F; ++f) wld[f] = __ldg(p.loc_denseT + f * ATT_DIM + (tid & (ATT_DIM - 1)));
-    for (int i = tid; i < LOC_F * 2 * LOC_K; i += RT) wloc_s[(i / 62) * 63 + (i % 62)] = p.loc_conv[i];
-    for (int i = tid; i < ATT_DIM + 2; i += RT) v_s[i] = p.attn_v[i];
-    for (int i = tid; i < SLp + 96; i += RT) { winp[i] = 0.f; winc[i] = 0.f; }
-    const float* memP = p.memory + ((size_t)b * T + t0) * EMB;
-    const float* pmP = p.pm + ((size_t)b * T + t0) * ATT_DIM;
-    if (p.mem_resident) {
-        float *mem_s = sm + L.mem, *pm_s = sm + L.pm;
-        for (int i = tid; i < n * EMB / 4; i += RT) reinterpret_cast<float4*>(mem_s)[i] = __ldg(reinterpret_cast<const float4*>(memP) + i);
-        for (int i = tid; i < n * ATT_DIM / 4; i += RT) reinterpret_cast<float4*>(pm_s)[i] = __ldg(reinterpret_cast<const float4*>(pmP) + i);
-        memP = mem_s;
-        pmP = pm_s;
+    for (int r = 0; r < RW; ++r) {
+        const int k = 2 * tid;
+        wq0[r] = r < na ? __ldg(p.wq_slices + ((size_t)(k >> 3) * ATT_DIM + a0 + r) * 8 + (k & 7)) : 0.f;
+        wq1[r] = r < na ? __ldg(p.wq_slices + ((size_t)(k >> 3) * ATT_DIM + a0 + r) * 8 + (k & 7) + 1) : 0.f;
     }
+    for (int i = tid; i < RW; i += RT) v_s[i] = i < na ? __ldg(p.attn_v + a0 + i) : 0.f;        // energies: v of the own dims
+    // composed location filter G[(c,k)][a] = sum_f W_dense[a][f] W_conv[f][c][k]
+    for (int i = tid; i < NTAP * RW; i += RT) {
+        const int ck = i / RW, a = i % RW;
+        float g = 0.f;
+        if (a < na)
+            for (int f = 0; f < LOC_F; ++f) g = fmaf(__ldg(p.loc_denseT + f * ATT_DIM + a0 + a), __ldg(p.loc_conv + f * NTAP + ck), g);
+        G_s[i] = g;
+    }
+    for (int i = tid; i < Tp + 64; i += RT) { winp[i] = 0.f; winc[i] = 0.f; }
+    for (int i = tid; i < DA * SP; i += RT) { pm_s[i] = 0.f; pre_s[i] = 0.f; }
+    for (int i = tid; i < Tp + 80; i += RT) ew_s[i] = 0.f;
     __syncthreads();
-    const float4 va = *reinterpret_cast<const float4*>(v_s + (lane & 15) * 8), vb = *reinterpret_cast<const float4*>(v_s + (lane & 15) * 8 + 4);
-    const float v_bias = v_s[ATT_DIM], e_scale = v_s[ATT_DIM + 1];
+    for (int i = tid; i < T * na; i += RT) {
+        const int t = i / na, a = i % na;
+        pm_s[a * SP + t] = __ldg(p.pm + ((size_t)b * T + t) * ATT_DIM + a0 + a);
+    }
+    // context: thread (tg, d) owns positions [tg * PT, tg * PT + PT) of memory column d0 + d
+    const int NTG = RT / DC, PT = (((T + NTG - 1) / NTG) + 3) & ~3;
+    const int ctg = tid / DC, cd = tid % DC;               // also (replica, dim) of the thread that publishes a context dim
+    const bool c_on = ctg < NTG && cd < nd;
+    const float* memP = p.memory + (size_t)b * T * EMB + d0;
+    int mem_ld = EMB;
+    float memr[MEMR];
+#pragma unroll
+    for (int i = 0; i < MEMR; ++i) {
+        const int t = ctg * PT + i;
+        memr[i] = (mem_mode == 2 && c_on && i < PT && t < T) ? __ldg(memP + (size_t)t * EMB + cd) : 0.f;
+    }
+    if (mem_mode == 1) {
+        float* mem_s = sm + L.mem;
+        for (int i = tid; i < T * DC; i += RT) {
+            const int t = i / DC, d = i % DC;
+            mem_s[i] = d < nd ? __ldg(memP + (size_t)t * EMB + d) : 0.f;
+        }
+        memP = mem_s;
+        mem_ld = DC;
+    }
+    const float v_bias = p.attn_v[ATT_DIM], e_scale = p.attn_v[ATT_DIM + 1];
+    __syncthreads();
 
     const int total_steps = p.max_steps + 1;
     bool done[BP];
@@ -402,210 +507,220 @@ __device__ __forceinline__ void attn_role(const RParams& p, uint8_t* smem, const
 #pragma unroll
     for (int q = 0; q < BP; ++q) { done[q] = false; ulen[q] = 0; }
     const int rep = cta % NREP;
-    const bool ftiming = p.fine && j == 0 && tid == 0;
-    auto fnow = [&]() -> unsigned long long { return p.fine == 2 ? (unsigned long long)clock64() : global_timer_ns(); };
-    unsigned long long t_fine[9] = {}, t_fl = ftiming ? fnow() : 0ull;
-    auto fstamp = [&](int i) {
-        if (ftiming) {
-            const unsigned long long now = fnow();
-            t_fine[i] += now - t_fl;
-            t_fl = now;
-        }
-    };
+    const int ntb = (T + TB - 1) / TB;
+    const int al0 = sl * ((T + NSL - 1) / NSL), al1 = min(T, al0 + (T + NSL - 1) / NSL);     // alignment columns written by this CTA
 
     for (int s = 0; s < total_steps; ++s) {
         const uint32_t tag = (uint32_t)s + 1u;
         uint64_t* X = p.xch + (size_t)(s & (DEPTH - 1)) * xl.words;
         const int out_idx = s - 1;                                   // F6: decode step 0 is discarded
 
-        // ---- (0) before the attention hidden state arrives: windows of the previous / cumulative weights with their
-        // halos, location convolution, and pre[t][a] = pm[t][a] + Wld . loc[:, t]
+        // ---- (0) before the attention hidden state arrives: pre[a][t] = pm[a][t] + sum_{c,k} G[a][c][k] win_c[t + k - 15]
+        // (location conv + location dense, src/model.py:125-127); a work item = (TB positions, one attention dim)
         if (s > 0) {
-            const uint64_t* Xw = p.xch + (size_t)((s - 1) & (DEPTH - 1)) * xl.words + xl.w + (size_t)b * p.Tp;
-            for (int i = tid; i < n + 2 * HALO; i += RT) {
-                const int t = t0 - HALO + i;
-                if (t >= 0 && t < T) {
-                    const float w = ll_wait1(Xw + t, tag - 1u);
-                    winp[i] = w;
-                    winc[i] += w;
-                }
-            }
-            __syncthreads();
-        }
-        {   // location conv (src/model.py:125-126): 32 filters x (2 x 31 taps); a thread owns filter f at positions t, t+16
-            const int f = lane;
-            for (int t = warp; t < n; t += 2 * RWARPS) {
-                float a0 = 0.f, a1 = 0.f;
+            for (int it = tid; it < ntb * na; it += RT) {
+                const int tb = it / na, a = it % na, t0 = tb * TB;
+                float acc[TB];
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const float* x = (c ? winc : winp) + t;
+                for (int q = 0; q < TB; ++q) acc[q] = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {                      // rolled: the loop body is walked once per decode step
+                    const float* w = (c ? winc : winp) + W0 - HALO + t0;
+                    const float* gp = G_s + c * LOC_K * RW + a;
+                    float x[TB + LOC_K - 1];
+#pragma unroll
+                    for (int q = 0; q < TB - 1; ++q) x[q] = w[q];
 #pragma unroll
                     for (int k = 0; k < LOC_K; ++k) {
-                        const float w = wloc_s[f * 63 + c * LOC_K + k];
-                        a0 = fmaf(w, x[k], a0);
-                        a1 = fmaf(w, x[k + RWARPS], a1);
+                        x[k + TB - 1] = w[k + TB - 1];
+                        const float g = gp[k * RW];
+#pragma unroll
+                        for (int q = 0; q < TB; ++q) acc[q] = fmaf(g, x[q + k], acc[q]);
                     }
                 }
-                loc_s[t * LOC_LD + f] = a0;
-                loc_s[(t + RWARPS) * LOC_LD + f] = a1;       // rows n .. n+15 exist (never read when beyond n)
+                const float* pm_r = pm_s + a * SP + t0;
+                float* pre_r = pre_s + a * SP + t0;
+#pragma unroll
+                for (int q = 0; q < TB; ++q) pre_r[q] = pm_r[q] + acc[q];
             }
+        } else {
+            for (int i = tid; i < DA * SP; i += RT) pre_s[i] = pm_s[i];       // zero attention history
         }
         __syncthreads();
-        {   // location dense (src/model.py:127) + processed memory
-            const int a = tid & (ATT_DIM - 1), tq = tid >> 7;
-            for (int t = tq; t < n; t += 4) {
-                float x = pmP[(size_t)t * ATT_DIM + a];
-#pragma unroll
-                for (int f4 = 0; f4 < LOC_F; f4 += 4) {
-                    const float4 l = *reinterpret_cast<const float4*>(loc_s + t * LOC_LD + f4);
-                    x = fmaf(wld[f4], l.x, x);
-                    x = fmaf(wld[f4 + 1], l.y, x);
-                    x = fmaf(wld[f4 + 2], l.z, x);
-                    x = fmaf(wld[f4 + 3], l.w, x);
-                }
-                pre_s[t * ATT_DIM + a] = x;
-            }
-        }
-        fstamp(0);
+        RES_EV(0);
         // the previous frame's gate logits: every CTA evaluates the stop rule itself
         if (s > 0) {
             const uint64_t* Xm = p.xch + (size_t)((s - 1) & (DEPTH - 1)) * xl.words + xl.mel;
             float g[BP];
 #pragma unroll
-            for (int q = 0; q < BP; ++q) g[q] = ll_wait1(Xm + q * PROJ_PAD + N_MELS, tag - 1u);
+            for (int q = 0; q < BP; ++q) g[q] = ll_wait1(Xm + (q * NFR + N_MELS / MPR) * MELW + N_MELS % MPR, tag - 1u);
             if (stop_rule<BP>(p, g, out_idx - 1, done, ulen)) break;
         }
-        // ---- (1) attention hidden state -> this CTA's rows of the processed query (src/model.py:123), one warp per row
-        ll_gather(X + xl.ah + rep * BP * RNN, xah, BP * RNN, tag, tid);
-        __syncthreads();
-        fstamp(1);
-        if (warp < PQR) {
-#pragma unroll
-            for (int q = 0; q < BP; ++q) {
-                float acc = 0.f;
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    const float4 x4 = reinterpret_cast<const float4*>(xah + q * RNN)[jj * 32 + lane];
-                    acc = fmaf(wq[jj * 4 + 0], x4.x, acc);
-                    acc = fmaf(wq[jj * 4 + 1], x4.y, acc);
-                    acc = fmaf(wq[jj * 4 + 2], x4.z, acc);
-                    acc = fmaf(wq[jj * 4 + 3], x4.w, acc);
-                }
-                acc = warp_sum(acc);
-                if (lane == 0 && has_row) ll_st(X + xl.pq + q * ATT_DIM + pq_row, acc, tag);
-            }
-        }
-        fstamp(2);
-        // ---- (2) energies v . tanh(pq + pre) (src/model.py:128-132): one half-warp per position, 8 attention dims per lane
-        ll_gather(X + xl.pq + b * ATT_DIM, pq_s, ATT_DIM, tag, tid);
-        __syncthreads();
-        fstamp(3);
+        // ---- (1) attention hidden state -> own rows of the processed query (src/model.py:123): K split over the threads
         {
-            const int hl = lane & 15;
-            const float4 qa = *reinterpret_cast<const float4*>(pq_s + hl * 8), qb = *reinterpret_cast<const float4*>(pq_s + hl * 8 + 4);
-            for (int t = 2 * warp + (lane >> 4); t < ((n + 1) & ~1); t += 2 * RWARPS) {
-                const int tt = t < n ? t : n - 1;
-                const float4 ra = *reinterpret_cast<const float4*>(pre_s + tt * ATT_DIM + hl * 8);
-                const float4 rb = *reinterpret_cast<const float4*>(pre_s + tt * ATT_DIM + hl * 8 + 4);
-                float x0 = va.x * tanh_fast(qa.x + ra.x), x1 = va.y * tanh_fast(qa.y + ra.y);
-                x0 = fmaf(va.z, tanh_fast(qa.z + ra.z), x0);
-                x1 = fmaf(va.w, tanh_fast(qa.w + ra.w), x1);
-                x0 = fmaf(vb.x, tanh_fast(qb.x + rb.x), x0);
-                x1 = fmaf(vb.y, tanh_fast(qb.y + rb.y), x1);
-                x0 = fmaf(vb.z, tanh_fast(qb.z + rb.z), x0);
-                x1 = fmaf(vb.w, tanh_fast(qb.w + rb.w), x1);
-                float x = x0 + x1;
+            float x0, x1;
+            ll_wait2(X + xl.ah + (size_t)(rep * BP + b) * RNN + 2 * tid, tag, x0, x1);
+        RES_EV(1);
+            RES_EVW(16);
+            if (j == 0) RES_EVT(0);
+            float v[RW];
 #pragma unroll
-                for (int sh = 8; sh > 0; sh >>= 1) x += __shfl_xor_sync(0xffffffffu, x, sh);
-                if (hl == 0 && t < n) e_s[t] = t0 + t >= len ? -1e9f : (x + v_bias) * e_scale;     // masked_fill, src/model.py:132
-            }
+            for (int r = 0; r < RW; ++r) v[r] = fmaf(wq1[r], x1, wq0[r] * x0);
+            const float tot = multi_reduce<RW>(v, lane);
+            if ((lane & (32 / RW - 1)) == 0) red_s[warp * RW + lane / (32 / RW)] = tot;
+            RES_EVW(32);
         }
         __syncthreads();
-        // ---- (3) slice-local softmax statistics (every warp, redundantly) and un-normalised context partial
-        float m_loc = -INFINITY;
-        for (int i = lane; i < n; i += 32) m_loc = fmaxf(m_loc, e_s[i]);
-        m_loc = warp_max(m_loc);
-        if (tid < n) ew_s[tid] = expf(e_s[tid] - m_loc);
+        if (tid < RW) {
+            float acc = 0.f;
+#pragma unroll
+            for (int w = 0; w < RWARPS; ++w) acc += red_s[w * RW + tid];
+            pq_s[tid] = acc;
+        }
         __syncthreads();
-        fstamp(4);
+        RES_EV(2);
+        // ---- (2) partial energies over own dims, all positions (src/model.py:128): two lanes per position
         {
-            float c0 = 0.f, c1 = 0.f;
-            int i = 0;
-            for (; i + 1 < n; i += 2) {
-                c0 = fmaf(ew_s[i], memP[(size_t)i * EMB + tid], c0);
-                c1 = fmaf(ew_s[i + 1], memP[(size_t)(i + 1) * EMB + tid], c1);
+            const int h = lane & 1;
+            float pqr[RW / 2], vreg[RW / 2];
+#pragma unroll
+            for (int u = 0; u < RW / 2; ++u) { pqr[u] = pq_s[h + 2 * u]; vreg[u] = v_s[h + 2 * u]; }
+            for (int t = tid >> 1; t < ((T + 15) & ~15); t += RT / 2) {
+                const int tt = t < T ? t : T - 1;
+                float th[RW / 2];
+#pragma unroll
+                for (int u = 0; u < RW / 2; ++u) th[u] = tanh_fast(pqr[u] + pre_s[(h + 2 * u < DA ? h + 2 * u : 0) * SP + tt]);
+                float x0 = 0.f;
+#pragma unroll
+                for (int u = 0; u < RW / 2; ++u) x0 = fmaf(vreg[u], th[u], x0);
+                x0 += __shfl_xor_sync(0xffffffffu, x0, 1);
+                if (h == 0 && t < T) ll_st(X + xl.ep + (size_t)(b * NSL + sl) * Tp + t, x0, tag);
             }
-            if (i < n) c0 = fmaf(ew_s[i], memP[(size_t)i * EMB + tid], c0);
-            ll_st(X + xl.part + (size_t)j * PARTW + 8 + tid, c0 + c1, tag);
-            if (warp == RWARPS - 1) {
-                float ssum = 0.f;
-                for (int q = lane; q < n; q += 32) ssum += ew_s[q];
-                ssum = warp_sum(ssum);
-                if (lane == 0) {
-                    ll_st(X + xl.part + (size_t)j * PARTW, n > 0 ? m_loc : -INFINITY, tag);
-                    ll_st(X + xl.part + (size_t)j * PARTW + 1, ssum, tag);
+        }
+        RES_EV(3);
+        // ---- (3) everybody's partials -> energies (src/model.py:129-132), summed in slice order by every CTA alike;
+        // softmax numerator (src/model.py:139).  A thread keeps up to two positions (T <= 1024).
+        float e_own[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};     // both lanes of a pair hold the position
+        {
+            const uint64_t* Xe = X + xl.ep + (size_t)b * NSL * Tp;
+            // two lanes per position (slices q = h, h + 2, ..): half as many loads per poll round
+            const int h = lane & 1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int t = (tid >> 1) + i * (RT / 2);
+                if (warp * 16 + i * (RT / 2) < T) {                  // whole warps; lanes beyond T re-read position T - 1
+                    const int tt = t < T ? t : T - 1;
+                    float e;
+                    uint32_t it = 0;
+                    bool ok;
+                    do {                                             // all loads of a round in flight together
+                        e = 0.f;
+                        ok = true;
+#pragma unroll
+                        for (int q = 0; q < MAX_NSL / 2; ++q)
+                            if (2 * q + h < NSL) {
+                                const uint64_t w = ll_ld1(Xe + (size_t)(2 * q + h) * Tp + tt);
+                                ok = ok && tag_ok(w, tag);
+                                e += __uint_as_float((uint32_t)w);
+                            }
+                        if (++it > SPIN_LIMIT) res_spin_fail();
+                    } while (!__all_sync(0xffffffffu, ok));
+                    e += __shfl_xor_sync(0xffffffffu, e, 1);
+                    if (t < T) e_own[i] = t >= len ? -1e9f : (e + v_bias) * e_scale;
                 }
             }
+            RES_EVW(48);
+            const float m = warp_max(fmaxf(fmaxf(e_own[0], e_own[1]), fmaxf(e_own[2], e_own[3])));
+            if (lane == 0) mx_s[warp] = m;
         }
-        fstamp(5);
-        // ---- (4) merge: this CTA finishes context dims [sl * DPC, +DPC) of its utterance
-        const int d0 = sl * DPC, nd = max(0, min(EMB, d0 + DPC) - d0);
-        const uint64_t* Xp = X + xl.part + (size_t)b * NSL * PARTW;
-        for (int i = tid; i < NSL * nd; i += RT) {
-            const int q = i / nd, dd = i % nd;
-            stage_s[q * DPC + dd] = ll_wait1(Xp + (size_t)q * PARTW + 8 + d0 + dd, tag);
-        }
-        for (int i = RT - 1 - tid; i < 2 * NSL; i += RT) ms_s[i] = ll_wait1(Xp + (size_t)(i >> 1) * PARTW + (i & 1), tag);
         __syncthreads();
-        fstamp(6);
-        const float mq = lane < NSL ? ms_s[2 * lane] : -INFINITY;
-        const float Msc = warp_max(mq);
-        const float scale = lane < NSL ? expf(mq - Msc) : 0.f;
-        const float Ssum = warp_sum(lane < NSL ? scale * ms_s[2 * lane + 1] : 0.f);
-        const float mine = __shfl_sync(0xffffffffu, scale, sl);
-        if (warp * 32 < nd) {
-            const int dd = warp * 32 + lane;
-            float c = 0.f;
-            for (int q = 0; q < NSL; ++q) {
-                const float sq = __shfl_sync(0xffffffffu, scale, q);
-                c = fmaf(sq, dd < nd ? stage_s[q * DPC + dd] : 0.f, c);
-            }
-            c = c / Ssum;
-            if (dd < nd) {
+        RES_EV(4);
+        {
+            const float4 m0 = *reinterpret_cast<const float4*>(mx_s), m1 = *reinterpret_cast<const float4*>(mx_s + 4),
+                         m2 = *reinterpret_cast<const float4*>(mx_s + 8), m3 = *reinterpret_cast<const float4*>(mx_s + 12);
+            const float m = fmaxf(fmaxf(fmaxf(fmaxf(m0.x, m0.y), fmaxf(m0.z, m0.w)), fmaxf(fmaxf(m1.x, m1.y), fmaxf(m1.z, m1.w))),
+                                  fmaxf(fmaxf(fmaxf(m2.x, m2.y), fmaxf(m2.z, m2.w)), fmaxf(fmaxf(m3.x, m3.y), fmaxf(m3.z, m3.w))));
 #pragma unroll
-                for (int r = 0; r < NREP; ++r) ll_st(X + xl.ctx + (size_t)(r * BP + b) * EMB + d0 + dd, c, tag);
+            for (int i = 0; i < 4; ++i) {
+                const int t = (tid >> 1) + i * (RT / 2);
+                if (t < T && (lane & 1) == 0) ew_s[t] = expf(e_own[i] - m);
             }
         }
-        fstamp(8);
-        // ---- (5) attention weights of the slice: alignment output, next step's windows (src/model.py:142-145)
-        for (int i = tid; i < n; i += RT) {
-            const float w = ew_s[i] * mine / Ssum;
-            if (out_idx >= 0) p.align[((size_t)out_idx * p.B + b) * T + t0 + i] = w;
-            ll_st(X + xl.w + (size_t)b * p.Tp + t0 + i, w, tag);
+        __syncthreads();
+        RES_EV(5);
+        // ---- (4) own context dims (src/model.py:146) and the softmax denominator: NTG position groups x DC dims
+        if (ctg < NTG) {
+            float c0 = 0.f, c1 = 0.f, s0 = 0.f, s1 = 0.f;
+            const int tbeg = ctg * PT;
+            if (mem_mode == 2) {
+#pragma unroll
+                for (int i = 0; i < MEMR; i += 4) {
+                    if (i < PT) {
+                        const float4 e4 = *reinterpret_cast<const float4*>(ew_s + tbeg + i);      // zero beyond T
+                        c0 = fmaf(e4.x, memr[i], c0);
+                        c1 = fmaf(e4.y, memr[i + 1], c1);
+                        c0 = fmaf(e4.z, memr[i + 2], c0);
+                        c1 = fmaf(e4.w, memr[i + 3], c1);
+                        s0 += e4.x + e4.z;
+                        s1 += e4.y + e4.w;
+                    }
+                }
+            } else {
+                const int tend = min(T, tbeg + PT);
+                for (int t = tbeg; t < tend; ++t) {
+                    const float e = ew_s[t];
+                    c0 = fmaf(e, cd < nd ? memP[(size_t)t * mem_ld + cd] : 0.f, c0);
+                    s0 += e;
+                }
+            }
+            cpart_s[ctg * DC + cd] = c0 + c1;
+            if (cd == 0) spart_s[ctg] = s0 + s1;
         }
-        fstamp(7);
-    }
-    if (ftiming) {
-        for (int i = 0; i < 8; ++i) p.prof[5 + i] = t_fine[i];
-        p.prof[19] = t_fine[8];
+        __syncthreads();
+        RES_EV(6);
+        float Ssum = 0.f;
+#pragma unroll
+        for (int g = 0; g < RT / 32; ++g)                            // NTG <= 16 (DC >= 32)
+            if (g < NTG) Ssum += spart_s[g];
+        if (ctg < NREP) {
+            const int r = ctg, d = cd;
+            if (d < nd) {
+                float c = 0.f;
+#pragma unroll
+                for (int g = 0; g < RT / 32; ++g)
+                    if (g < NTG) c += cpart_s[g * DC + d];
+                ll_st(X + xl.ctx + (size_t)(r * BP + b) * EMB + d0 + d, c / Ssum, tag);
+            }
+        }
+        RES_EV(7);
+        // ---- (5) attention weights: alignment output (this CTA's columns), windows of the next step (src/model.py:142-145)
+        for (int t = tid; t < T; t += RT) {
+            const float w = ew_s[t] / Ssum;
+            winp[W0 + t] = w;
+            winc[W0 + t] += w;
+            if (out_idx >= 0 && t >= al0 && t < al1) p.align[((size_t)out_idx * p.B + b) * T + t] = w;
+        }
+        __syncthreads();
+        RES_EV(8);
     }
 }
 
 // =====================================================================================================================
 // frame CTAs: rows of linear_projection / gate_layer (src/model.py:272-274), the stop rule, and the prenet of the new frame
-// (src/model.py:166-171, eval mode: no dropout) -> input of the next decode step
+// (src/model.py:166-171, eval mode: no dropout) -> input of the next decode step.  All weights in registers, contractions
+// split over K like the attention CTAs'.
+constexpr int PRW = 16;                       // reduction width of the projection rows (MPR <= 16)
 struct FSmem {
-    int w2, xcat, mel, y1p, y1, total;
+    int red, mel, y1, red2, total;
 };
-__host__ __device__ inline FSmem f_smem(int BP, int P2R) {
+__host__ __device__ inline FSmem f_smem(int BP) {
     FSmem f;
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
-    f.w2 = take(P2R_MAX * PRENET);          // rows beyond P2R are zero
-    f.xcat = take(BP * (RNN + EMB));
+    f.red = take(BP * RWARPS * PRW);
     f.mel = take(BP * PROJ_PAD);
-    f.y1p = take(2 * BP * PRENET);
     f.y1 = take(BP * PRENET);
+    f.red2 = take(BP * RWARPS * 16);
     f.total = o;
     return f;
 }
@@ -614,43 +729,37 @@ template <int BP>
 __device__ __forceinline__ void frame_role(const RParams& p, uint8_t* smem, const XL& xl) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, cta = blockIdx.x;
     const int jf = (int)blockIdx.x - GEMM_CTAS - p.NATT;
-    const int MPR = p.MPR, P2R = p.P2R;
-    const FSmem L = f_smem(BP, P2R);
+    const FSmem L = f_smem(BP);
     float* sm = reinterpret_cast<float*>(smem);
-    float *w2_s = sm + L.w2, *xcat = sm + L.xcat, *mel_s = sm + L.mel, *y1p_s = sm + L.y1p, *y1_s = sm + L.y1;
-    constexpr int KC = RNN + EMB;                       // projection input [decoder hidden | context]
+    float *red_s = sm + L.red, *mel_s = sm + L.mel, *y1_s = sm + L.y1, *red2_s = sm + L.red2;
+    static_assert(MPR <= PRW && P2R == 32, "frame CTA thread maps");
 
-    // ---- one-off: this warp's projection row (warp w < MPR owns row MPR * jf + w; lane l owns k = 128 jj + 4 l + i of
-    // [decoder hidden | context]) and prenet layer 1 into registers
-    float wp[48], w1[40];
-    const int prow = MPR * jf + warp;
-    const bool has_prow = warp < MPR && prow < PROJ_OUT;
+    // ---- one-off: projection rows MPR * jf + r: thread owns decoder-hidden columns 2 tid, 2 tid + 1 and context column tid;
+    // prenet layer 1: thread = (output tid / 2, mel bins 40 (tid & 1) ..); prenet layer 2: thread = (input tid & 255, rows
+    // P2R jf + 16 (tid >> 8) ..)
+    float wp0[MPR], wp1[MPR], wpc[MPR], w1[40], w2[16];
 #pragma unroll
-    for (int jj = 0; jj < 12; ++jj)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int k = jj * 128 + lane * 4 + i;
-            float w = 0.f;
-            if (has_prow)
-                w = k < RNN ? __ldg(p.wproj_slices + ((size_t)(k >> 3) * PROJ_OUT + prow) * 8 + (k & 7))
-                            : __ldg(p.wproj_ctxT + (size_t)(k - RNN) * PROJ_PAD + prow);
-            wp[jj * 4 + i] = w;
-        }
-    const float pbias = has_prow ? __ldg(p.proj_bias + prow) : 0.f;
+    for (int r = 0; r < MPR; ++r) {
+        const int prow = MPR * jf + r, k = 2 * tid;
+        const bool ok = prow < PROJ_OUT;
+        wp0[r] = ok ? __ldg(p.wproj_slices + ((size_t)(k >> 3) * PROJ_OUT + prow) * 8 + (k & 7)) : 0.f;
+        wp1[r] = ok ? __ldg(p.wproj_slices + ((size_t)(k >> 3) * PROJ_OUT + prow) * 8 + (k & 7) + 1) : 0.f;
+        wpc[r] = ok ? __ldg(p.wproj_ctxT + (size_t)tid * PROJ_PAD + prow) : 0.f;
+    }
     {
-        const int o = tid & (PRENET - 1), half = tid >> 8;
+        const int o = tid >> 1, half = tid & 1;
 #pragma unroll
         for (int i = 0; i < 40; ++i) w1[i] = __ldg(p.prenet1T + (size_t)(40 * half + i) * PRENET + o);
-    }
-    for (int i = tid; i < P2R_MAX * PRENET; i += RT) {
-        const int k = i & (PRENET - 1), r = i >> 8, row = P2R * jf + r;
-        w2_s[r * PRENET + k] = r < P2R && row < PRENET ? __ldg(p.prenet2T + (size_t)k * PRENET + row) : 0.f;
+        const int k = tid & (PRENET - 1), rh = tid >> 8;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w2[i] = __ldg(p.prenet2T + (size_t)k * PRENET + P2R * jf + 16 * rh + i);
     }
     // prenet of the all-zero go frame (src/model.py:226) is zero (no biases): input of decode step 0
     for (int i = tid; i < P2R * BP * NREP; i += RT) {
-        const int r = i % P2R, rb = i / P2R, row = P2R * jf + r;          // rb = rep * BP + b
-        if (row < PRENET) ll_st(p.xch + xl.p + (size_t)rb * PRENET + row, 0.f, 1u);
+        const int r = i % P2R, rb = i / P2R;                                // rb = rep * BP + b
+        ll_st(p.xch + xl.p + (size_t)rb * PRENET + P2R * jf + r, 0.f, 1u);
     }
+    const float pbias = lane < MPR && MPR * jf + lane < PROJ_OUT ? __ldg(p.proj_bias + MPR * jf + lane) : 0.f;
     __syncthreads();
 
     const int total_steps = p.max_steps + 1;
@@ -660,16 +769,6 @@ __device__ __forceinline__ void frame_role(const RParams& p, uint8_t* smem, cons
 #pragma unroll
     for (int q = 0; q < BP; ++q) { done[q] = false; ulen[q] = 0; }
     const int rep = cta % NREP;
-    const bool ftiming = p.fine && jf == 0 && tid == 0;
-    auto fnow = [&]() -> unsigned long long { return p.fine == 2 ? (unsigned long long)clock64() : global_timer_ns(); };
-    unsigned long long t_fine[6] = {}, t_fl = ftiming ? fnow() : 0ull;
-    auto fstamp = [&](int i) {
-        if (ftiming) {
-            const unsigned long long now = fnow();
-            t_fine[i] += now - t_fl;
-            t_fl = now;
-        }
-    };
 
     for (int s = 0; s < total_steps; ++s) {
         const uint32_t tag = (uint32_t)s + 1u;
@@ -677,96 +776,94 @@ __device__ __forceinline__ void frame_role(const RParams& p, uint8_t* smem, cons
         const int out_idx = s - 1;                                   // F6: decode step 0 is discarded
         // ---- (1) context (arrives first) and decoder hidden state -> this CTA's projection rows
 #pragma unroll
-        for (int q = 0; q < BP; ++q) ll_gather(X + xl.ctx + (size_t)(rep * BP + q) * EMB, xcat + q * KC + RNN, EMB, tag, tid);
-        fstamp(0);
+        for (int q = 0; q < BP; ++q) {
+            const float xc = ll_wait1(X + xl.ctx + (size_t)(rep * BP + q) * EMB + tid, tag);
+        RES_EV(0);
+            float x0, x1;
+            ll_wait2(X + xl.dh + (size_t)(rep * BP + q) * RNN + 2 * tid, tag, x0, x1);
+            RES_EVW(16);
+            if (jf == 0) RES_EVT(1);
+        RES_EV(1);
+            float v[PRW];
 #pragma unroll
-        for (int q = 0; q < BP; ++q) ll_gather(X + xl.dh + (size_t)(rep * BP + q) * RNN, xcat + q * KC, RNN, tag, tid);
+            for (int r = 0; r < PRW; ++r) v[r] = r < MPR ? fmaf(wpc[r < MPR ? r : 0], xc, fmaf(wp1[r < MPR ? r : 0], x1, wp0[r < MPR ? r : 0] * x0)) : 0.f;
+            const float tot = multi_reduce<PRW>(v, lane);
+            if ((lane & 1) == 0) red_s[(q * RWARPS + warp) * PRW + (lane >> 1)] = tot;
+            RES_EVW(32);
+        }
         __syncthreads();
-        fstamp(1);
-        if (has_prow) {
+        RES_EV(8);
+        if (tid < BP * 32) {
+            const int q = tid >> 5, r = tid & 31, prow = MPR * jf + r;
+            if (r < MPR && prow < PROJ_OUT) {
+                float acc = 0.f;
 #pragma unroll
-            for (int q = 0; q < BP; ++q) {
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-                for (int jj = 0; jj < 12; ++jj) {
-                    const float4 x4 = reinterpret_cast<const float4*>(xcat + q * KC)[jj * 32 + lane];
-                    a0 = fmaf(wp[jj * 4 + 0], x4.x, a0);
-                    a1 = fmaf(wp[jj * 4 + 1], x4.y, a1);
-                    a2 = fmaf(wp[jj * 4 + 2], x4.z, a2);
-                    a3 = fmaf(wp[jj * 4 + 3], x4.w, a3);
+                for (int w = 0; w < RWARPS; ++w) acc += red_s[(q * RWARPS + w) * PRW + r];
+                const float v = acc + pbias;
+                if (out_idx >= 0) {
+                    if (prow < N_MELS) p.mel[((size_t)q * p.max_steps + out_idx) * N_MELS + prow] = v;
+                    else p.gate[(size_t)q * p.max_steps + out_idx] = v;
                 }
-                const float v = warp_sum((a0 + a1) + (a2 + a3)) + pbias;
-                if (lane == 0) {
-                    if (out_idx >= 0) {
-                        if (prow < N_MELS) p.mel[((size_t)q * p.max_steps + out_idx) * N_MELS + prow] = v;
-                        else p.gate[(size_t)q * p.max_steps + out_idx] = v;
-                    }
-                    ll_st(X + xl.mel + q * PROJ_PAD + prow, v, tag);
-                    if (prow == N_MELS) ll_st(X + xl.mel + q * PROJ_PAD + prow + 1, 0.f, tag);      // pad to an even word count
-                }
+                ll_st(X + xl.mel + (size_t)(q * NFR + jf) * MELW + r, v, tag);
             }
         }
-        fstamp(2);
+        RES_EV(2);
         // ---- (2) the whole frame: stop rule, prenet
-#pragma unroll
-        for (int q = 0; q < BP; ++q) ll_gather(X + xl.mel + q * PROJ_PAD, mel_s + q * PROJ_PAD, N_MELS + 2, tag, tid);
+        for (int i0 = warp * 32; i0 < BP * PROJ_OUT; i0 += RT) {          // whole warps; lanes beyond the end re-read the last word
+            const int i = min(i0 + lane, BP * PROJ_OUT - 1);
+            const int q = i / PROJ_OUT, row = i % PROJ_OUT;
+            mel_s[q * PROJ_PAD + row] = ll_wait1(X + xl.mel + (size_t)(q * NFR + row / MPR) * MELW + row % MPR, tag);
+        }
         __syncthreads();
-        fstamp(3);
+        RES_EV(3);
         float g[BP];
 #pragma unroll
         for (int q = 0; q < BP; ++q) g[q] = mel_s[q * PROJ_PAD + N_MELS];
         const bool stop = stop_rule<BP>(p, g, out_idx, done, ulen);
         steps_done = s + 1;
         if (s + 1 < total_steps) {
-            const int o = tid & (PRENET - 1), half = tid >> 8;
+            const int o = tid >> 1, half = tid & 1;
 #pragma unroll
             for (int q = 0; q < BP; ++q) {
-                float a0 = 0.f, a1 = 0.f;
+                float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
 #pragma unroll
                 for (int i = 0; i < 40; i += 4) {
                     const float4 m4 = *reinterpret_cast<const float4*>(mel_s + q * PROJ_PAD + 40 * half + i);
-                    a0 = fmaf(w1[i], m4.x, a0);
-                    a1 = fmaf(w1[i + 1], m4.y, a1);
-                    a0 = fmaf(w1[i + 2], m4.z, a0);
-                    a1 = fmaf(w1[i + 3], m4.w, a1);
+                    c0 = fmaf(w1[i], m4.x, c0);
+                    c1 = fmaf(w1[i + 1], m4.y, c1);
+                    c2 = fmaf(w1[i + 2], m4.z, c2);
+                    c3 = fmaf(w1[i + 3], m4.w, c3);
                 }
-                y1p_s[(half * BP + q) * PRENET + o] = a0 + a1;
+                float y = (c0 + c1) + (c2 + c3);
+                y += __shfl_xor_sync(0xffffffffu, y, 1);
+                if (half == 0) y1_s[q * PRENET + o] = fmaxf(y, 0.f);
             }
             __syncthreads();
-            if (tid < PRENET) {
-#pragma unroll
-                for (int q = 0; q < BP; ++q) y1_s[q * PRENET + tid] = fmaxf(y1p_s[q * PRENET + tid] + y1p_s[(BP + q) * PRENET + tid], 0.f);
-            }
-            __syncthreads();
-            fstamp(4);
+        RES_EV(4);
             uint64_t* Xn = p.xch + (size_t)((s + 1) & (DEPTH - 1)) * xl.words + xl.p;
             const uint32_t ntag = (tag + 1u) | (stop ? STOP_BIT : 0u);
-            {   // one half-warp per row: lane hl owns k = 64 jj + 4 hl + i
-                const int r = 2 * warp + (lane >> 4), hl = lane & 15, row = P2R * jf + r;
 #pragma unroll
-                for (int q = 0; q < BP; ++q) {
-                    float a0 = 0.f, a1 = 0.f;
+            for (int q = 0; q < BP; ++q) {
+                const float y = y1_s[q * PRENET + (tid & (PRENET - 1))];
+                float v[16];
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const float4 w4 = reinterpret_cast<const float4*>(w2_s + r * PRENET)[jj * 16 + hl];
-                        const float4 x4 = reinterpret_cast<const float4*>(y1_s + q * PRENET)[jj * 16 + hl];
-                        a0 = fmaf(w4.x, x4.x, a0);
-                        a1 = fmaf(w4.y, x4.y, a1);
-                        a0 = fmaf(w4.z, x4.z, a0);
-                        a1 = fmaf(w4.w, x4.w, a1);
-                    }
-                    float acc = a0 + a1;
+                for (int i = 0; i < 16; ++i) v[i] = w2[i] * y;
+                const float tot = multi_reduce<16>(v, lane);
+                if ((lane & 1) == 0) red2_s[(q * RWARPS + warp) * 16 + (lane >> 1)] = tot;
+            }
+            __syncthreads();
+            if (tid < BP * NREP * P2R) {       // thread = (utterance, replica, row): 8 warps hold the K halves of a row's 16-row group
+                const int r = tid % P2R, rq = tid / P2R, rr = rq % NREP, q = rq / NREP;
+                const int w0 = (r >> 4) * (RWARPS / 2);
+                float acc = 0.f;
 #pragma unroll
-                    for (int sh = 8; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
-                    acc = fmaxf(acc, 0.f);
-                    if (hl < NREP && r < P2R && row < PRENET) ll_st(Xn + (size_t)(hl * BP + q) * PRENET + row, acc, ntag);
-                }
+                for (int w = 0; w < RWARPS / 2; ++w) acc += red2_s[(q * RWARPS + w0 + w) * 16 + (r & 15)];
+                ll_st(Xn + (size_t)(rr * BP + q) * PRENET + P2R * jf + r, fmaxf(acc, 0.f), ntag);
             }
         }
-        fstamp(5);
+        RES_EV(5);
         if (stop) break;
     }
-    if (ftiming) for (int i = 0; i < 6; ++i) p.prof[13 + i] = t_fine[i];
     if (jf == 0 && tid == 0) {
         const int S = steps_done - 1;                  // output frames (decode step 0 discarded)
         *p.steps_run = S;
@@ -778,10 +875,10 @@ __device__ __forceinline__ void frame_role(const RParams& p, uint8_t* smem, cons
 template <int BP>
 __global__ void __launch_bounds__(RT, 1) decoder_res_kernel(const RParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const XL xl = xlayout(BP, p.Tp);
+    const XL xl = xlayout(BP, p.Tp, p.NSL);
     const int cta = blockIdx.x;
     if (cta < GEMM_CTAS) gate_role<BP>(p, smem, xl);
-    else if (cta < GEMM_CTAS + p.NATT) attn_role<BP>(p, smem, xl);
+    else if (cta < GEMM_CTAS + p.NATT) attn_role<BP, 16 * BP>(p, smem, xl);
     else frame_role<BP>(p, smem, xl);
 }
 
@@ -791,29 +888,34 @@ constexpr size_t gate_smem_bytes(int BP) {
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 
 struct Plan {
-    int NATT, NFR, NSL, SL, DPC, PQR, MPR, P2R, resident;
+    int NATT, NSL, DA, DC, resident;
     size_t smem;
 };
 bool make_plan(const b200taco_handle* h, int B, int T, Plan& pl) {
-    int na = h->num_sms - GEMM_CTAS;
-    if (na > MAX_A) na = MAX_A;
-    if (na < MIN_A) return false;
-    pl.NFR = na / 2;                                               // frame CTAs; the rest (a multiple of B) are attention CTAs
-    pl.NATT = (na - pl.NFR) / B * B;
-    pl.NSL = pl.NATT / B;
-    if (pl.NSL < 1 || pl.NSL > 32) return false;
-    pl.SL = (T + pl.NSL - 1) / pl.NSL;
-    pl.DPC = ((EMB + pl.NSL - 1) / pl.NSL + 1) & ~1;
-    pl.PQR = (ATT_DIM + pl.NATT - 1) / pl.NATT;
-    pl.MPR = (PROJ_OUT + pl.NFR - 1) / pl.NFR;
-    pl.P2R = (PRENET + pl.NFR - 1) / pl.NFR;
-    if (pl.PQR > PQR_MAX || pl.MPR > MPR_MAX || pl.P2R > P2R_MAX) return false;
-    const size_t g = gate_smem_bytes(B), f = (size_t)f_smem(B, pl.P2R).total * 4;
-    size_t a = (size_t)a_smem(B, pl.SL, pl.NSL, pl.DPC, true).total * 4;
-    pl.resident = 1;
-    if (a > SMEM_LIMIT) {
-        a = (size_t)a_smem(B, pl.SL, pl.NSL, pl.DPC, false).total * 4;
-        pl.resident = 0;
+    const int spare = h->num_sms - GEMM_CTAS - NFR;
+    if (spare < 2 * B || T > 2 * RT) return false;
+    pl.NSL = spare / B;
+    if (pl.NSL > MAX_NSL) pl.NSL = MAX_NSL;
+    pl.NATT = pl.NSL * B;
+    pl.DA = (ATT_DIM + pl.NSL - 1) / pl.NSL;
+    pl.DC = ((EMB + pl.NSL - 1) / pl.NSL + 3) & ~3;                 // whole 32-byte sectors per producer
+    if (pl.DA > 16 * B || NREP * pl.DC > RT || pl.DC < 32) return false;
+    const int NTG = RT / pl.DC, PT = (((T + NTG - 1) / NTG) + 3) & ~3;
+    const size_t g = gate_smem_bytes(B), f = (size_t)f_smem(B).total * 4;
+    auto a_bytes = [&](bool in_smem) {
+        return (size_t)(B == 1 ? a_smem<16>(T, pl.DA, pl.DC, in_smem) : a_smem<32>(T, pl.DA, pl.DC, in_smem)).total * 4;
+    };
+    size_t a;
+    if (PT <= MEMR) {
+        pl.resident = 2;                                            // memory columns in registers
+        a = a_bytes(false);
+    } else {
+        pl.resident = 1;
+        a = a_bytes(true);
+        if (a > SMEM_LIMIT) {
+            pl.resident = 0;
+            a = a_bytes(false);
+        }
     }
     pl.smem = g > a ? g : a;
     if (f > pl.smem) pl.smem = f;
@@ -847,7 +949,7 @@ bool decoder_res_supported(const b200taco_handle* h, const DecoderArgs& a) {
 size_t decoder_res_scratch_bytes(int B, int T) {
     if (B > 2) return 0;
     const int Tp = (T + 3) / 4 * 4;
-    return (size_t)DEPTH * xlayout(B, Tp).words * 8 + PROF_WORDS * 8;
+    return (size_t)DEPTH * xlayout(B, Tp, MAX_NSL).words * 8 + (PROF_WORDS + TRACE_WORDS) * 8;
 }
 
 int decoder_res_run(const b200taco_handle* h, const DecoderArgs& a, void* scratch, cudaStream_t stream) {
@@ -856,11 +958,11 @@ int decoder_res_run(const b200taco_handle* h, const DecoderArgs& a, void* scratc
     const size_t bytes = decoder_res_scratch_bytes(a.B, a.T);
     TACO_CUDA(cudaMemsetAsync(scratch, 0, bytes, stream));
     RParams rp{};
-    rp.B = a.B; rp.T = a.T; rp.Tp = (a.T + 3) / 4 * 4; rp.NATT = pl.NATT; rp.NFR = pl.NFR; rp.NSL = pl.NSL; rp.SL = pl.SL;
-    rp.DPC = pl.DPC; rp.PQR = pl.PQR; rp.MPR = pl.MPR; rp.P2R = pl.P2R;
+    rp.B = a.B; rp.T = a.T; rp.Tp = (a.T + 3) / 4 * 4; rp.NATT = pl.NATT; rp.NSL = pl.NSL; rp.DA = pl.DA; rp.DC = pl.DC;
     rp.max_steps = a.max_steps; rp.stop_mode = a.stop_mode; rp.mem_resident = pl.resident; rp.thr = a.gate_threshold;
-    static const int fine = [] { const char* e = getenv("TACO_RES_FINE"); return e ? atoi(e) : 0; }();
-    rp.fine = fine;
+    static const int bg_sleep = [] { const char* e = getenv("TACO_RES_BG_SLEEP"); return e ? atoi(e) : 0; }();
+    static const int bg_backoff = [] { const char* e = getenv("TACO_RES_BG_BACKOFF"); return e ? atoi(e) : 0; }();
+    rp.bg_sleep = bg_sleep; rp.bg_backoff = bg_backoff;
     rp.w_attn = static_cast<const uint32_t*>(h->w_attn); rp.w_dec = static_cast<const uint32_t*>(h->w_dec);
     rp.bias_attn = h->bias_attn; rp.bias_dec = h->bias_dec; rp.wq_slices = h->wq_slices; rp.wproj_slices = h->wproj_slices;
     rp.wproj_ctxT = h->wproj_ctxT; rp.proj_bias = h->proj_bias; rp.prenet1T = h->prenet1T; rp.prenet2T = h->prenet2T;
@@ -868,9 +970,13 @@ int decoder_res_run(const b200taco_handle* h, const DecoderArgs& a, void* scratc
     rp.memory = a.memory; rp.pm = a.pm; rp.text_lengths = a.text_lengths;
     rp.mel = a.mel; rp.gate = a.gate; rp.align = a.align; rp.lengths = a.lengths; rp.steps_run = a.steps_run;
     rp.xch = static_cast<uint64_t*>(scratch);
-    rp.prof = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(scratch) + bytes - PROF_WORDS * 8);
+    rp.prof = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(scratch) + bytes - (PROF_WORDS + TRACE_WORDS) * 8);
+    static const int trace_step = [] { const char* e = getenv("TACO_RES_TRACE"); return e ? atoi(e) : -1; }();
+    rp.trace = trace_step >= 0 ? rp.prof + PROF_WORDS : nullptr;
+    rp.trace_step = trace_step;
+    const_cast<b200taco_handle*>(h)->last_trace = rp.trace;
     const_cast<b200taco_handle*>(h)->last_profile = rp.prof;
-    const int ncta = GEMM_CTAS + pl.NATT + pl.NFR;
+    const int ncta = GEMM_CTAS + pl.NATT + NFR;
     return a.B == 1 ? launch_res<1>(rp, ncta, pl.smem, stream) : launch_res<2>(rp, ncta, pl.smem, stream);
 }
 

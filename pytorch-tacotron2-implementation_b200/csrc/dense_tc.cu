@@ -96,7 +96,7 @@ template <int NT, int ACT>
 __global__ void __launch_bounds__(NTHREADS, 1)
     conv_tc_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ Wtc, const float* __restrict__ scale,
                    const float* __restrict__ shift, const float* __restrict__ R, int ldres, float* __restrict__ Y, int ldy,
-                   int n_rows, int seg_len, int c_in, int c_out, int taps) {
+                   int n_rows, int seg_len, int c_in, int c_out, int taps, const ChannelMajorOut cm) {
     using C = Cfg<NT>;
     constexpr int STAGES = C::STAGES;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -262,6 +262,16 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                 float4* dst = reinterpret_cast<float4*>(Y + (size_t)row * ldy + co);
                 dst[0] = make_float4(o[0], o[1], o[2], o[3]);
                 dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+                if (cm.y != nullptr) {
+                    // second copy of the result in the vocoder's layout (B, c_out, cm.ld) (inference.py:71), zero from the
+                    // utterance's own length on (train.py:71-79); consecutive lanes = consecutive frames: coalesced per channel
+                    const int ub = row / seg_len, us = row - ub * seg_len;
+                    if (us < cm.ld) {
+                        const bool keep = cm.lengths == nullptr || us < cm.lengths[ub];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) cm.y[((size_t)ub * c_out + co + i) * cm.ld + us] = keep ? o[i] : 0.f;
+                    }
+                }
             }
         }
         umma::fence_before_sync();
@@ -289,7 +299,8 @@ __global__ void pack_dense_tc_kernel(float* __restrict__ dst, const float* __res
 
 template <int NT>
 int launch_nt(const float* X, int ldx, const float* Wtc, const float* scale, const float* shift, const float* R, int ldres,
-              float* Y, int ldy, int n_rows, int seg_len, int c_in, int c_out, int taps, int act, cudaStream_t stream) {
+              float* Y, int ldy, int n_rows, int seg_len, int c_in, int c_out, int taps, int act, cudaStream_t stream,
+              const ChannelMajorOut& cm) {
     using C = Cfg<NT>;
     dim3 grid((n_rows + TM - 1) / TM, c_out / NT);
 #define TACO_TC_CASE(A)                                                                                                 \
@@ -297,7 +308,7 @@ int launch_nt(const float* X, int ldx, const float* Wtc, const float* scale, con
         auto kern = conv_tc_kernel<NT, A>;                                                                              \
         TACO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));                   \
         kern<<<grid, NTHREADS, C::TOTAL, stream>>>(X, ldx, Wtc, scale, shift, R, ldres, Y, ldy, n_rows, seg_len, c_in,  \
-                                                   c_out, taps);                                                        \
+                                                   c_out, taps, cm);                                                    \
     }
     switch (act) {
         case ACT_NONE: TACO_TC_CASE(ACT_NONE) break;
@@ -313,7 +324,7 @@ int launch_nt(const float* X, int ldx, const float* Wtc, const float* scale, con
 
 int conv1d_channels_last_tc(const float* X, int ldx, const float* Wtc, const float* scale, const float* shift,
                             const float* residual, int ldres, float* Y, int ldy, int n_rows, int seg_len, int c_in,
-                            int c_out, int taps, int act, int num_sms, cudaStream_t stream);
+                            int c_out, int taps, int act, int num_sms, cudaStream_t stream, const ChannelMajorOut& cm);
 
 bool dense_tc_supported(int c_in, int c_out, int ldx, int ldy) {
     return c_in % KC == 0 && (c_out % 64 == 0 || c_out == 80) && ldx % 4 == 0 && ldy % 4 == 0;
@@ -331,20 +342,24 @@ int pack_dense_tc(float* dst, const float* w_tap_ci_co, int taps, int c_in, int 
 
 int dense_layer(const b200taco_handle* h, const float* X, int ldx, const float* W, const float* Wtc, const float* scale,
                 const float* shift, const float* residual, int ldres, float* Y, int ldy, int n_rows, int seg_len, int c_in,
-                int c_out, int taps, int act, bool precise, cudaStream_t stream) {
+                int c_out, int taps, int act, bool precise, cudaStream_t stream, const ChannelMajorOut& cm) {
     // AUTO: layers whose output feeds the 1000-step decoder recurrence ("precise": encoder, memory layer) stay on the
     // fp32 CUDA cores (round-to-nearest accumulation); everything else runs on the tensor cores.  TC: all of them.
     const bool tc = h->dense_path == B200TACO_PATH_TC || (h->dense_path == B200TACO_PATH_AUTO && !precise);
     if (tc && Wtc != nullptr && dense_tc_supported(c_in, c_out, ldx, ldy))
         return conv1d_channels_last_tc(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out,
-                                       taps, act, precise ? 0 : h->num_sms, stream);
-    return conv1d_channels_last(X, ldx, W, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act,
-                                stream);
+                                       taps, act, precise ? 0 : h->num_sms, stream, cm);
+    if (int e = conv1d_channels_last(X, ldx, W, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act,
+                                     stream))
+        return e;
+    // CUDA-core path: the vocoder layout is a separate pass over the result
+    if (cm.y != nullptr) return vocoder_layout(Y, ldy, cm.lengths, n_rows / seg_len, seg_len, c_out, cm.ld, cm.y, stream);
+    return B200TACO_OK;
 }
 
 int conv1d_channels_last_tc(const float* X, int ldx, const float* Wtc, const float* scale, const float* shift,
                             const float* residual, int ldres, float* Y, int ldy, int n_rows, int seg_len, int c_in,
-                            int c_out, int taps, int act, int num_sms, cudaStream_t stream) {
+                            int c_out, int taps, int act, int num_sms, cudaStream_t stream, const ChannelMajorOut& cm) {
     TACO_REQUIRE(dense_tc_supported(c_in, c_out, ldx, ldy), B200TACO_ERR_INVALID,
                  "conv1d (tensor-core path): unsupported shape c_in %d c_out %d ldx %d ldy %d", c_in, c_out, ldx, ldy);
     if (n_rows <= 0) return B200TACO_OK;
@@ -352,25 +367,25 @@ int conv1d_channels_last_tc(const float* X, int ldx, const float* Wtc, const flo
     // num_sms == 0 ("precise"): always the narrowest tile = 16 accumulators; used for the encoder, whose output
     // feeds a 1000-step recurrence (measured |error| vs fp32 SIMT: 8e-7 at NT=64, 3e-6 at NT=256)
     if (c_out == 80)
-        return launch_nt<80>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream);
+        return launch_nt<80>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream, cm);
     // measurement knob: TACO_DENSE_NT=64|128|256 forces the tile width (narrower tile = more accumulators)
     static const int forced = [] { const char* e = getenv("TACO_DENSE_NT"); return e ? atoi(e) : 0; }();
     if (forced == 256 && c_out % 256 == 0)
-        return launch_nt<256>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream);
+        return launch_nt<256>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream, cm);
     if (forced == 128 && c_out % 128 == 0)
-        return launch_nt<128>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream);
+        return launch_nt<128>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream, cm);
     if (forced == 32 && c_out % 32 == 0)
-        return launch_nt<32>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream);
+        return launch_nt<32>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream, cm);
     if (forced == 64)
-        return launch_nt<64>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream);
+        return launch_nt<64>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream, cm);
     // wide tiles when there is enough work to fill the machine, narrow ones to spread small problems over more SMs
     if (num_sms > 0 && c_out % 256 == 0 && mtiles * (c_out / 256) >= num_sms)
-        return launch_nt<256>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream);
+        return launch_nt<256>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream, cm);
     if (num_sms > 0 && c_out % 128 == 0 && mtiles * (c_out / 128) >= num_sms)
-        return launch_nt<128>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream);
+        return launch_nt<128>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream, cm);
     if (num_sms > 0 || c_out % 32 != 0)
-        return launch_nt<64>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream);
-    return launch_nt<32>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream);
+        return launch_nt<64>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream, cm);
+    return launch_nt<32>(X, ldx, Wtc, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act, stream, cm);
 }
 
 }  // namespace b200taco

@@ -11,6 +11,7 @@ struct b200taco_handle {
     int dense_path = 0;             // 0 = tcgen05 3xTF32 dense layers (dense_tc.cu), 1 = fp32 SIMT (dense.cu)
     bool packed = false;
     const unsigned long long* last_profile = nullptr;   // device: phase timers of the last decoder launch
+    const unsigned long long* last_trace = nullptr;     // device: per-CTA event times of one step (resident kernel, TACO_RES_TRACE=step)
 
     // one device allocation holding every packed tensor below
     void* arena = nullptr;
@@ -71,9 +72,19 @@ int transpose_bct_to_btc(const float* in, float* out, int B, int C, int T, cudaS
 bool dense_tc_supported(int c_in, int c_out, int ldx, int ldy);
 size_t dense_tc_weight_floats(int taps, int c_in, int c_out);
 int pack_dense_tc(float* dst, const float* w_tap_ci_co, int taps, int c_in, int c_out, cudaStream_t stream);
+// optional second copy of a layer's result, channel major (B, c_out, ld) and zero from lengths[b] on: the vocoder hand-off
+// layout (inference.py:71, train.py:71-79); y == nullptr: none
+struct ChannelMajorOut {
+    float* y = nullptr;
+    const int32_t* lengths = nullptr;
+    int ld = 0;
+};
 int dense_layer(const b200taco_handle* h, const float* X, int ldx, const float* W, const float* Wtc, const float* scale,
                 const float* shift, const float* residual, int ldres, float* Y, int ldy, int n_rows, int seg_len, int c_in,
-                int c_out, int taps, int act, bool precise, cudaStream_t stream);
+                int c_out, int taps, int act, bool precise, cudaStream_t stream, const ChannelMajorOut& cm = ChannelMajorOut());
+
+// data.cu : batch assembly (src/data_utils.py:45-84) and the vocoder hand-off layout as stand-alone passes
+int vocoder_layout(const float* mel, int ldm, const int32_t* lengths, int B, int S, int C, int S_out, float* out, cudaStream_t stream);
 
 // bilstm.cu
 int bilstm_recurrence(const b200taco_handle* h, const float* xproj, float* memory, int B, int T,
