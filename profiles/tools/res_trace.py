@@ -59,7 +59,7 @@ def main():
     print("gate ctx-in:", [ev[c][2] - t0 for c in range(128)])
     print("gate dh-out:", [ev[c][3] - t0 for c in range(128)])
     for c in (128, 133, 139, 140, 147):
-        print("cta", c, "per-warp words in:", [ev[c][16 + w] - t0 for w in range(16)], "reduced:", [ev[c][32 + w] - t0 for w in range(16)],
+        print("cta", c, "per-warp ep poll rounds:", [ev[c][16 + w] for w in range(16)] if c < 140 else "", "per-warp words in:", [ev[c][16 + w] - t0 for w in range(16)], "reduced:", [ev[c][32 + w] - t0 for w in range(16)],
               "ep gathered:", [ev[c][48 + w] - t0 for w in range(16)])
     print(json.dumps({"B": B, "T": T, "step": step, "gate": stats(ev[:128], GATE), "attention": stats(ev[128:128 + natt], ATTN),
                       "frame": stats(ev[128 + natt:128 + natt + 8], FRAME)}, indent=1))

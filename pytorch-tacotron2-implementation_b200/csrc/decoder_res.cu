@@ -57,8 +57,12 @@ constexpr int TRACE_EV = 64, TRACE_WORDS = 160 * TRACE_EV + 2 * 512;   // per-CT
 static_assert(NREP == 4, "the four gate lanes of a hidden unit publish the four replicas");
 static_assert(RT == 2 * PRENET && MPR <= RWARPS && MPR <= MELW && P2R == 2 * RWARPS && MELW % 4 == 0, "thread maps");
 
+struct ASmem {                                // shared-memory layout of an attention CTA (floats), computed by the host
+    int G, red, pq, v, winp, winc, pm, pre, ew, mx, cpart, spart, mem, SP, NTG, PT, total;
+};
+
 struct RParams {
-    int B, T, Tp, NATT, NSL, DA, DC, max_steps, stop_mode, mem_resident, bg_sleep, bg_backoff;
+    int B, T, Tp, Te, NATT, NSL, DA, DC, max_steps, stop_mode, mem_resident, bg_sleep, bg_backoff;
     float thr;
     const uint32_t *w_attn, *w_dec;           // bf16 pairs: [128 cta][K][16 words], word w = rows (2w, 2w+1) of the CTA
     const float *bias_attn, *bias_dec, *wq_slices, *wproj_slices, *wproj_ctxT, *proj_bias, *prenet1T, *prenet2T, *loc_conv,
@@ -71,20 +75,22 @@ struct RParams {
     unsigned long long* prof;
     unsigned long long* trace;               // [cta][TRACE_EV] globaltimer of step trace_step, or nullptr
     int trace_step;
+    ASmem as;
 };
 
 // word offsets of the exchanged vectors inside one ring slot
 struct XL {
     int p, ah, ctx, dh, ep, mel, words;
 };
-__host__ __device__ inline XL xlayout(int BP, int Tp, int NSL) {
+__host__ __device__ inline XL xlayout(int BP, int Te, int NSL) {
     XL x;
     int o = 0;
     x.p = o;    o += NREP * BP * PRENET;      // prenet output            frame -> gate
     x.ah = o;   o += NREP * BP * RNN;         // attention hidden         gate -> gate, attention
     x.ctx = o;  o += NREP * BP * EMB;         // attention context        attention -> gate, frame
     x.dh = o;   o += NREP * BP * RNN;         // decoder hidden           gate -> gate, frame
-    x.ep = o;   o += BP * NSL * Tp;           // partial energies         attention -> attention (same utterance)
+    x.ep = o;   o += BP * NSL * Te;           // partial energies         attention -> attention (same utterance); rows of Te = 16 n
+                                              // words: every 128-byte line is written by ONE store instruction
     x.mel = o;  o += BP * NFR * MELW;         // mel frame + gate logit   frame -> frame, attention (gate)
     x.words = (o + 15) & ~15;
     return x;
@@ -332,7 +338,7 @@ __device__ __forceinline__ void gate_role(const RParams& p, uint8_t* smem, const
         stamp(0);
         RES_EV(1);
         // ---- background: both cells' rows of the new attention hidden state
-        if (p.bg_sleep) __nanosleep(p.bg_sleep);
+        if (p.bg_sleep > 0) __nanosleep(p.bg_sleep);
         ll_gather(X + xl.ah + rep * BP * RNN, xah, BP * RNN, tag, tid, p.bg_backoff);
         __syncthreads();
         gemv_smem<BP>(sW + (1 * RWARPS + warp) * RNN, xah, acc_d, lane);
@@ -352,7 +358,7 @@ __device__ __forceinline__ void gate_role(const RParams& p, uint8_t* smem, const
         RES_EV(3);
         // ---- background: attention LSTM x context, decoder LSTM x new decoder hidden (both for the next step)
         gemv_reg<BP, 4>(wa_c, xctx, EMB, acc_a, lane);
-        if (p.bg_sleep) __nanosleep(p.bg_sleep);
+        if (p.bg_sleep > 0) __nanosleep(p.bg_sleep);
         ll_gather(X + xl.dh + rep * BP * RNN, xdh, BP * RNN, tag, tid, p.bg_backoff);
         __syncthreads();
         gemv_smem<BP>(sW + (2 * RWARPS + warp) * RNN, xdh, acc_d, lane);
@@ -408,17 +414,20 @@ __device__ __forceinline__ uint32_t ll_wait2(const uint64_t* p, uint32_t tag, fl
 // attention dimension (DA <= RW dims each: query projection rows, processed memory, composed location filter, energies)
 // and by context dimension (DC dims each).  Every contraction is split over K so that a thread multiplies exactly the
 // words it polled (no staging of the incoming vector, no shared-memory traffic for weights: they sit in registers).
-constexpr int MEMR = 20;                      // encoder positions per thread whose memory column sits in registers
-struct ASmem {
-    int G, red, pq, v, winp, winc, pm, pre, ew, mx, cpart, spart, mem, SP, total;
-};
+// T <= 256 (one lane pair per encoder position).  The loop body must stay well inside the 32 KB instruction cache: a body
+// of 46 KB was measured to run 3x slower than its instruction count (every line refetched from L2 every decode step), so
+// layouts come precomputed from the host and the memory columns have ONE home per instantiation (MM).
+constexpr int MEMR = 20;                      // MM == 2: encoder positions per thread whose memory column sits in registers
+constexpr int RES_MAX_T = 256;
 template <int RW>
-__host__ __device__ inline ASmem a_smem(int T, int DA, int DC, bool mem_in_smem) {
+__host__ inline ASmem a_smem(int T, int DA, int DC, bool mem_in_smem) {
     ASmem a;
     const int Tp = (T + 3) & ~3;
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
     a.SP = ((Tp + TB + 15) / 32) * 32 + 16;           // row stride of pm / pre: 16 mod 32 (two rows never share a bank)
+    a.NTG = RT / DC;                                  // position groups of the context contraction
+    a.PT = (((T + a.NTG - 1) / a.NTG) + 3) & ~3;      // positions per group
     a.G = take(NTAP * RW);
     a.red = take(RWARPS * RW);
     a.pq = take(RW);
@@ -427,30 +436,30 @@ __host__ __device__ inline ASmem a_smem(int T, int DA, int DC, bool mem_in_smem)
     a.winc = take(Tp + 64);
     a.pm = take(DA * a.SP);
     a.pre = take(DA * a.SP);
-    a.ew = take(Tp + 80);                             // position groups of the context contraction read whole float4s
+    a.ew = take(a.NTG * a.PT + 16);                   // position groups read whole float4s; zero beyond T
     a.mx = take(RWARPS);
-    a.cpart = take((RT / DC) * DC);
-    a.spart = take(RT / DC + 4);
-    a.mem = take(mem_in_smem ? T * DC : 0);
+    a.cpart = take(a.NTG * DC);
+    a.spart = take(RWARPS + 4);
+    a.mem = take(mem_in_smem ? a.NTG * a.PT * DC : 0);
     a.total = o;
     return a;
 }
 
-template <int BP, int RW>
+template <int BP, int RW, int MM>
 __device__ __forceinline__ void attn_role(const RParams& p, uint8_t* smem, const XL& xl) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int j = (int)blockIdx.x - GEMM_CTAS, cta = blockIdx.x;
-    const int NSL = p.NSL, T = p.T, Tp = p.Tp, DA = p.DA, DC = p.DC;
+    const int NSL = p.NSL, T = p.T, DA = p.DA, DC = p.DC;
     const int b = j / NSL, sl = j % NSL;                       // NATT == BP * NSL
     const int a0 = sl * DA, na = max(0, min(ATT_DIM, a0 + DA) - a0);
     const int d0 = sl * DC, nd = max(0, min(EMB, d0 + DC) - d0);
     const int len = p.text_lengths ? (int)p.text_lengths[b] : T;
-    const int mem_mode = p.mem_resident;                       // 2: registers, 1: shared memory, 0: L2
-    const ASmem L = a_smem<RW>(T, DA, DC, mem_mode == 1);
-    const int SP = L.SP;
+    const ASmem& L = p.as;
+    const int SP = L.SP, NTG = L.NTG, PT = L.PT;
     float* sm = reinterpret_cast<float*>(smem);
-    float *G_s = sm + L.G, *red_s = sm + L.red, *pq_s = sm + L.pq, *v_s = sm + L.v, *winp = sm + L.winp, *winc = sm + L.winc, *pm_s = sm + L.pm,
-          *pre_s = sm + L.pre, *ew_s = sm + L.ew, *mx_s = sm + L.mx, *cpart_s = sm + L.cpart, *spart_s = sm + L.spart;
+    float *G_s = sm + L.G, *red_s = sm + L.red, *pq_s = sm + L.pq, *v_s = sm + L.v, *winp = sm + L.winp, *winc = sm + L.winc,
+          *pm_s = sm + L.pm, *pre_s = sm + L.pre, *ew_s = sm + L.ew, *mx_s = sm + L.mx, *cpart_s = sm + L.cpart, *spart_s = sm + L.spart,
+          *mem_s = sm + L.mem;
 
     // ---- one-off.  Query projection: thread owns k = 2 tid, 2 tid + 1 of all own rows (registers)
     float wq0[RW], wq1[RW];
@@ -469,34 +478,32 @@ __device__ __forceinline__ void attn_role(const RParams& p, uint8_t* smem, const
             for (int f = 0; f < LOC_F; ++f) g = fmaf(__ldg(p.loc_denseT + f * ATT_DIM + a0 + a), __ldg(p.loc_conv + f * NTAP + ck), g);
         G_s[i] = g;
     }
-    for (int i = tid; i < Tp + 64; i += RT) { winp[i] = 0.f; winc[i] = 0.f; }
+    for (int i = tid; i < p.Tp + 64; i += RT) { winp[i] = 0.f; winc[i] = 0.f; }
     for (int i = tid; i < DA * SP; i += RT) { pm_s[i] = 0.f; pre_s[i] = 0.f; }
-    for (int i = tid; i < Tp + 80; i += RT) ew_s[i] = 0.f;
+    for (int i = tid; i < NTG * PT + 16; i += RT) ew_s[i] = 0.f;
     __syncthreads();
     for (int i = tid; i < T * na; i += RT) {
         const int t = i / na, a = i % na;
-        pm_s[a * SP + t] = __ldg(p.pm + ((size_t)b * T + t) * ATT_DIM + a0 + a);
+        const float v = __ldg(p.pm + ((size_t)b * T + t) * ATT_DIM + a0 + a);
+        pm_s[a * SP + t] = v;
+        pre_s[a * SP + t] = v;                                  // decode step 0: zero attention history
     }
-    // context: thread (tg, d) owns positions [tg * PT, tg * PT + PT) of memory column d0 + d
-    const int NTG = RT / DC, PT = (((T + NTG - 1) / NTG) + 3) & ~3;
-    const int ctg = tid / DC, cd = tid % DC;               // also (replica, dim) of the thread that publishes a context dim
-    const bool c_on = ctg < NTG && cd < nd;
-    const float* memP = p.memory + (size_t)b * T * EMB + d0;
-    int mem_ld = EMB;
-    float memr[MEMR];
+    // context: thread (ctg, cd) owns positions [ctg * PT, ctg * PT + PT) of memory column d0 + cd; the same pair is the
+    // (replica, dim) of the thread that publishes a context dim
+    const int ctg = tid / DC, cd = tid % DC;
+    const float* memG = p.memory + (size_t)b * T * EMB + d0;
+    float memr[MM == 2 ? MEMR : 1];
+    if (MM == 2) {
 #pragma unroll
-    for (int i = 0; i < MEMR; ++i) {
-        const int t = ctg * PT + i;
-        memr[i] = (mem_mode == 2 && c_on && i < PT && t < T) ? __ldg(memP + (size_t)t * EMB + cd) : 0.f;
-    }
-    if (mem_mode == 1) {
-        float* mem_s = sm + L.mem;
-        for (int i = tid; i < T * DC; i += RT) {
-            const int t = i / DC, d = i % DC;
-            mem_s[i] = d < nd ? __ldg(memP + (size_t)t * EMB + d) : 0.f;
+        for (int i = 0; i < MEMR; ++i) {
+            const int t = ctg * PT + i;
+            memr[i] = (ctg < NTG && cd < nd && i < PT && t < T) ? __ldg(memG + (size_t)t * EMB + cd) : 0.f;
         }
-        memP = mem_s;
-        mem_ld = DC;
+    } else {
+        for (int i = tid; i < NTG * PT * DC; i += RT) {
+            const int t = i / DC, d = i % DC;
+            mem_s[i] = (t < T && d < nd) ? __ldg(memG + (size_t)t * EMB + d) : 0.f;
+        }
     }
     const float v_bias = p.attn_v[ATT_DIM], e_scale = p.attn_v[ATT_DIM + 1];
     __syncthreads();
@@ -507,19 +514,23 @@ __device__ __forceinline__ void attn_role(const RParams& p, uint8_t* smem, const
 #pragma unroll
     for (int q = 0; q < BP; ++q) { done[q] = false; ulen[q] = 0; }
     const int rep = cta % NREP;
-    const int ntb = (T + TB - 1) / TB;
+    const int nitems = ((T + TB - 1) / TB) * na;
     const int al0 = sl * ((T + NSL - 1) / NSL), al1 = min(T, al0 + (T + NSL - 1) / NSL);     // alignment columns written by this CTA
+    const int et = tid >> 1, eh = lane & 1;                    // energies: lane pair (position, dim / slice parity)
+    const uint64_t* Xm_gate = p.xch + xl.mel + (N_MELS / MPR) * MELW + N_MELS % MPR;        // gate logit of utterance 0 in slot 0
 
+#pragma unroll 1
     for (int s = 0; s < total_steps; ++s) {
         const uint32_t tag = (uint32_t)s + 1u;
         uint64_t* X = p.xch + (size_t)(s & (DEPTH - 1)) * xl.words;
         const int out_idx = s - 1;                                   // F6: decode step 0 is discarded
 
-        // ---- (0) before the attention hidden state arrives: pre[a][t] = pm[a][t] + sum_{c,k} G[a][c][k] win_c[t + k - 15]
-        // (location conv + location dense, src/model.py:125-127); a work item = (TB positions, one attention dim)
         if (s > 0) {
-            for (int it = tid; it < ntb * na; it += RT) {
-                const int tb = it / na, a = it % na, t0 = tb * TB;
+            // ---- (0) before the attention hidden state arrives: pre[a][t] = pm[a][t] + sum_{c,k} G[a][c][k] win_c[t + k - 15]
+            // (location conv + location dense, src/model.py:125-127); a work item = (TB positions, one attention dim)
+#pragma unroll 1
+            for (int it = tid; it < nitems; it += RT) {
+                const int tb = it / na, a = it - tb * na, t0 = tb * TB;
                 float acc[TB];
 #pragma unroll
                 for (int q = 0; q < TB; ++q) acc[q] = 0.f;
@@ -543,32 +554,24 @@ __device__ __forceinline__ void attn_role(const RParams& p, uint8_t* smem, const
 #pragma unroll
                 for (int q = 0; q < TB; ++q) pre_r[q] = pm_r[q] + acc[q];
             }
-        } else {
-            for (int i = tid; i < DA * SP; i += RT) pre_s[i] = pm_s[i];       // zero attention history
-        }
-        __syncthreads();
-        RES_EV(0);
-        // the previous frame's gate logits: every CTA evaluates the stop rule itself
-        if (s > 0) {
-            const uint64_t* Xm = p.xch + (size_t)((s - 1) & (DEPTH - 1)) * xl.words + xl.mel;
+            __syncthreads();
+            RES_EV(0);
+            // the previous frame's gate logits: every CTA evaluates the stop rule itself
             float g[BP];
 #pragma unroll
-            for (int q = 0; q < BP; ++q) g[q] = ll_wait1(Xm + (q * NFR + N_MELS / MPR) * MELW + N_MELS % MPR, tag - 1u);
+            for (int q = 0; q < BP; ++q) g[q] = ll_wait1(Xm_gate + (size_t)((s - 1) & (DEPTH - 1)) * xl.words + q * NFR * MELW, tag - 1u);
             if (stop_rule<BP>(p, g, out_idx - 1, done, ulen)) break;
         }
         // ---- (1) attention hidden state -> own rows of the processed query (src/model.py:123): K split over the threads
         {
             float x0, x1;
             ll_wait2(X + xl.ah + (size_t)(rep * BP + b) * RNN + 2 * tid, tag, x0, x1);
-        RES_EV(1);
-            RES_EVW(16);
-            if (j == 0) RES_EVT(0);
+            RES_EV(1);
             float v[RW];
 #pragma unroll
             for (int r = 0; r < RW; ++r) v[r] = fmaf(wq1[r], x1, wq0[r] * x0);
             const float tot = multi_reduce<RW>(v, lane);
             if ((lane & (32 / RW - 1)) == 0) red_s[warp * RW + lane / (32 / RW)] = tot;
-            RES_EVW(32);
         }
         __syncthreads();
         if (tid < RW) {
@@ -580,57 +583,43 @@ __device__ __forceinline__ void attn_role(const RParams& p, uint8_t* smem, const
         __syncthreads();
         RES_EV(2);
         // ---- (2) partial energies over own dims, all positions (src/model.py:128): two lanes per position
-        {
-            const int h = lane & 1;
-            float pqr[RW / 2], vreg[RW / 2];
+        if (warp * 16 < T) {
+            const int tt = et < T ? et : T - 1;
+            float x0 = 0.f;
 #pragma unroll
-            for (int u = 0; u < RW / 2; ++u) { pqr[u] = pq_s[h + 2 * u]; vreg[u] = v_s[h + 2 * u]; }
-            for (int t = tid >> 1; t < ((T + 15) & ~15); t += RT / 2) {
-                const int tt = t < T ? t : T - 1;
-                float th[RW / 2];
-#pragma unroll
-                for (int u = 0; u < RW / 2; ++u) th[u] = tanh_fast(pqr[u] + pre_s[(h + 2 * u < DA ? h + 2 * u : 0) * SP + tt]);
-                float x0 = 0.f;
-#pragma unroll
-                for (int u = 0; u < RW / 2; ++u) x0 = fmaf(vreg[u], th[u], x0);
-                x0 += __shfl_xor_sync(0xffffffffu, x0, 1);
-                if (h == 0 && t < T) ll_st(X + xl.ep + (size_t)(b * NSL + sl) * Tp + t, x0, tag);
+            for (int u = 0; u < RW / 2; ++u) {
+                const int a = eh + 2 * u;
+                x0 = fmaf(v_s[a], tanh_fast(pq_s[a] + pre_s[(a < DA ? a : 0) * SP + tt]), x0);
             }
+            x0 += __shfl_xor_sync(0xffffffffu, x0, 1);
+            if (eh == 0 && et < T) ll_st(X + xl.ep + (size_t)(b * NSL + sl) * p.Te + et, x0, tag);
         }
         RES_EV(3);
-        // ---- (3) everybody's partials -> energies (src/model.py:129-132), summed in slice order by every CTA alike;
-        // softmax numerator (src/model.py:139).  A thread keeps up to two positions (T <= 1024).
-        float e_own[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};     // both lanes of a pair hold the position
+        // ---- (3) everybody's partials -> energies (src/model.py:129-132), summed in slice order by every CTA alike (the
+        // lane pair splits the slices even / odd); softmax numerator (src/model.py:139)
+        float e_own = -INFINITY;
+        if (warp * 16 < T) {
+            const uint64_t* Xe = X + xl.ep + (size_t)b * NSL * p.Te + (et < T ? et : T - 1);
+            float e;
+            uint32_t it = 0;
+            bool ok;
+            do {                                                 // all loads of a round in flight together
+                e = 0.f;
+                ok = true;
+#pragma unroll
+                for (int q = 0; q < MAX_NSL / 2; ++q)
+                    if (2 * q + eh < NSL) {
+                        const uint64_t w = ll_ld1(Xe + (size_t)(2 * q + eh) * p.Te);
+                        ok = ok && tag_ok(w, tag);
+                        e += __uint_as_float((uint32_t)w);
+                    }
+                if (++it > SPIN_LIMIT) res_spin_fail();
+            } while (!__all_sync(0xffffffffu, ok));
+            e += __shfl_xor_sync(0xffffffffu, e, 1);
+            if (et < T) e_own = et >= len ? -1e9f : (e + v_bias) * e_scale;
+        }
         {
-            const uint64_t* Xe = X + xl.ep + (size_t)b * NSL * Tp;
-            // two lanes per position (slices q = h, h + 2, ..): half as many loads per poll round
-            const int h = lane & 1;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int t = (tid >> 1) + i * (RT / 2);
-                if (warp * 16 + i * (RT / 2) < T) {                  // whole warps; lanes beyond T re-read position T - 1
-                    const int tt = t < T ? t : T - 1;
-                    float e;
-                    uint32_t it = 0;
-                    bool ok;
-                    do {                                             // all loads of a round in flight together
-                        e = 0.f;
-                        ok = true;
-#pragma unroll
-                        for (int q = 0; q < MAX_NSL / 2; ++q)
-                            if (2 * q + h < NSL) {
-                                const uint64_t w = ll_ld1(Xe + (size_t)(2 * q + h) * Tp + tt);
-                                ok = ok && tag_ok(w, tag);
-                                e += __uint_as_float((uint32_t)w);
-                            }
-                        if (++it > SPIN_LIMIT) res_spin_fail();
-                    } while (!__all_sync(0xffffffffu, ok));
-                    e += __shfl_xor_sync(0xffffffffu, e, 1);
-                    if (t < T) e_own[i] = t >= len ? -1e9f : (e + v_bias) * e_scale;
-                }
-            }
-            RES_EVW(48);
-            const float m = warp_max(fmaxf(fmaxf(e_own[0], e_own[1]), fmaxf(e_own[2], e_own[3])));
+            const float m = warp_max(e_own);
             if (lane == 0) mx_s[warp] = m;
         }
         __syncthreads();
@@ -640,23 +629,19 @@ __device__ __forceinline__ void attn_role(const RParams& p, uint8_t* smem, const
                          m2 = *reinterpret_cast<const float4*>(mx_s + 8), m3 = *reinterpret_cast<const float4*>(mx_s + 12);
             const float m = fmaxf(fmaxf(fmaxf(fmaxf(m0.x, m0.y), fmaxf(m0.z, m0.w)), fmaxf(fmaxf(m1.x, m1.y), fmaxf(m1.z, m1.w))),
                                   fmaxf(fmaxf(fmaxf(m2.x, m2.y), fmaxf(m2.z, m2.w)), fmaxf(fmaxf(m3.x, m3.y), fmaxf(m3.z, m3.w))));
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int t = (tid >> 1) + i * (RT / 2);
-                if (t < T && (lane & 1) == 0) ew_s[t] = expf(e_own[i] - m);
-            }
+            if (et < T && eh == 0) ew_s[et] = expf(e_own - m);
         }
         __syncthreads();
         RES_EV(5);
         // ---- (4) own context dims (src/model.py:146) and the softmax denominator: NTG position groups x DC dims
         if (ctg < NTG) {
             float c0 = 0.f, c1 = 0.f, s0 = 0.f, s1 = 0.f;
-            const int tbeg = ctg * PT;
-            if (mem_mode == 2) {
+            const float* ew_g = ew_s + ctg * PT;
+            if (MM == 2) {
 #pragma unroll
                 for (int i = 0; i < MEMR; i += 4) {
                     if (i < PT) {
-                        const float4 e4 = *reinterpret_cast<const float4*>(ew_s + tbeg + i);      // zero beyond T
+                        const float4 e4 = *reinterpret_cast<const float4*>(ew_g + i);      // zero beyond T
                         c0 = fmaf(e4.x, memr[i], c0);
                         c1 = fmaf(e4.y, memr[i + 1], c1);
                         c0 = fmaf(e4.z, memr[i + 2], c0);
@@ -666,11 +651,14 @@ __device__ __forceinline__ void attn_role(const RParams& p, uint8_t* smem, const
                     }
                 }
             } else {
-                const int tend = min(T, tbeg + PT);
-                for (int t = tbeg; t < tend; ++t) {
-                    const float e = ew_s[t];
-                    c0 = fmaf(e, cd < nd ? memP[(size_t)t * mem_ld + cd] : 0.f, c0);
-                    s0 += e;
+                const float* mp = mem_s + (size_t)ctg * PT * DC + cd;
+#pragma unroll 4
+                for (int i = 0; i < PT; i += 2) {
+                    const float2 e2 = *reinterpret_cast<const float2*>(ew_g + i);
+                    c0 = fmaf(e2.x, mp[(size_t)i * DC], c0);
+                    c1 = fmaf(e2.y, mp[(size_t)(i + 1) * DC], c1);
+                    s0 += e2.x;
+                    s1 += e2.y;
                 }
             }
             cpart_s[ctg * DC + cd] = c0 + c1;
@@ -680,25 +668,22 @@ __device__ __forceinline__ void attn_role(const RParams& p, uint8_t* smem, const
         RES_EV(6);
         float Ssum = 0.f;
 #pragma unroll
-        for (int g = 0; g < RT / 32; ++g)                            // NTG <= 16 (DC >= 32)
+        for (int g = 0; g < RWARPS; ++g)                             // NTG <= 16 (DC >= 32)
             if (g < NTG) Ssum += spart_s[g];
-        if (ctg < NREP) {
-            const int r = ctg, d = cd;
-            if (d < nd) {
-                float c = 0.f;
+        if (ctg < NREP && cd < nd) {
+            float c = 0.f;
 #pragma unroll
-                for (int g = 0; g < RT / 32; ++g)
-                    if (g < NTG) c += cpart_s[g * DC + d];
-                ll_st(X + xl.ctx + (size_t)(r * BP + b) * EMB + d0 + d, c / Ssum, tag);
-            }
+            for (int g = 0; g < RWARPS; ++g)
+                if (g < NTG) c += cpart_s[g * DC + cd];
+            ll_st(X + xl.ctx + (size_t)(ctg * BP + b) * EMB + d0 + cd, c / Ssum, tag);
         }
         RES_EV(7);
         // ---- (5) attention weights: alignment output (this CTA's columns), windows of the next step (src/model.py:142-145)
-        for (int t = tid; t < T; t += RT) {
-            const float w = ew_s[t] / Ssum;
-            winp[W0 + t] = w;
-            winc[W0 + t] += w;
-            if (out_idx >= 0 && t >= al0 && t < al1) p.align[((size_t)out_idx * p.B + b) * T + t] = w;
+        if (tid < T) {
+            const float w = ew_s[tid] / Ssum;
+            winp[W0 + tid] = w;
+            winc[W0 + tid] += w;
+            if (out_idx >= 0 && tid >= al0 && tid < al1) p.align[((size_t)out_idx * p.B + b) * T + tid] = w;
         }
         __syncthreads();
         RES_EV(8);
@@ -872,13 +857,13 @@ __device__ __forceinline__ void frame_role(const RParams& p, uint8_t* smem, cons
     }
 }
 
-template <int BP>
+template <int BP, int MM>
 __global__ void __launch_bounds__(RT, 1) decoder_res_kernel(const RParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const XL xl = xlayout(BP, p.Tp, p.NSL);
+    const XL xl = xlayout(BP, p.Te, p.NSL);
     const int cta = blockIdx.x;
     if (cta < GEMM_CTAS) gate_role<BP>(p, smem, xl);
-    else if (cta < GEMM_CTAS + p.NATT) attn_role<BP, 16 * BP>(p, smem, xl);
+    else if (cta < GEMM_CTAS + p.NATT) attn_role<BP, 16 * BP, MM>(p, smem, xl);
     else frame_role<BP>(p, smem, xl);
 }
 
@@ -889,11 +874,12 @@ constexpr size_t SMEM_LIMIT = 227 * 1024;
 
 struct Plan {
     int NATT, NSL, DA, DC, resident;
+    ASmem as;
     size_t smem;
 };
 bool make_plan(const b200taco_handle* h, int B, int T, Plan& pl) {
     const int spare = h->num_sms - GEMM_CTAS - NFR;
-    if (spare < 2 * B || T > 2 * RT) return false;
+    if (spare < 2 * B || T > RES_MAX_T) return false;
     pl.NSL = spare / B;
     if (pl.NSL > MAX_NSL) pl.NSL = MAX_NSL;
     pl.NATT = pl.NSL * B;
@@ -902,29 +888,17 @@ bool make_plan(const b200taco_handle* h, int B, int T, Plan& pl) {
     if (pl.DA > 16 * B || NREP * pl.DC > RT || pl.DC < 32) return false;
     const int NTG = RT / pl.DC, PT = (((T + NTG - 1) / NTG) + 3) & ~3;
     const size_t g = gate_smem_bytes(B), f = (size_t)f_smem(B).total * 4;
-    auto a_bytes = [&](bool in_smem) {
-        return (size_t)(B == 1 ? a_smem<16>(T, pl.DA, pl.DC, in_smem) : a_smem<32>(T, pl.DA, pl.DC, in_smem)).total * 4;
-    };
-    size_t a;
-    if (PT <= MEMR) {
-        pl.resident = 2;                                            // memory columns in registers
-        a = a_bytes(false);
-    } else {
-        pl.resident = 1;
-        a = a_bytes(true);
-        if (a > SMEM_LIMIT) {
-            pl.resident = 0;
-            a = a_bytes(false);
-        }
-    }
+    pl.resident = (B == 1 && PT <= MEMR) ? 2 : 1;                   // memory columns in registers / in shared memory
+    pl.as = B == 1 ? a_smem<16>(T, pl.DA, pl.DC, pl.resident == 1) : a_smem<32>(T, pl.DA, pl.DC, pl.resident == 1);
+    const size_t a = (size_t)pl.as.total * 4;
     pl.smem = g > a ? g : a;
     if (f > pl.smem) pl.smem = f;
     return pl.smem <= SMEM_LIMIT;
 }
 
-template <int BP>
+template <int BP, int MM>
 int launch_res(const RParams& rp, int ncta, size_t smem, cudaStream_t stream) {
-    auto kern = decoder_res_kernel<BP>;
+    auto kern = decoder_res_kernel<BP, MM>;
     TACO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     TACO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RT, smem));
@@ -948,8 +922,8 @@ bool decoder_res_supported(const b200taco_handle* h, const DecoderArgs& a) {
 
 size_t decoder_res_scratch_bytes(int B, int T) {
     if (B > 2) return 0;
-    const int Tp = (T + 3) / 4 * 4;
-    return (size_t)DEPTH * xlayout(B, Tp, MAX_NSL).words * 8 + (PROF_WORDS + TRACE_WORDS) * 8;
+    const int Te = (T + 15) / 16 * 16;
+    return (size_t)DEPTH * xlayout(B, Te, MAX_NSL).words * 8 + (PROF_WORDS + TRACE_WORDS) * 8;
 }
 
 int decoder_res_run(const b200taco_handle* h, const DecoderArgs& a, void* scratch, cudaStream_t stream) {
@@ -958,7 +932,7 @@ int decoder_res_run(const b200taco_handle* h, const DecoderArgs& a, void* scratc
     const size_t bytes = decoder_res_scratch_bytes(a.B, a.T);
     TACO_CUDA(cudaMemsetAsync(scratch, 0, bytes, stream));
     RParams rp{};
-    rp.B = a.B; rp.T = a.T; rp.Tp = (a.T + 3) / 4 * 4; rp.NATT = pl.NATT; rp.NSL = pl.NSL; rp.DA = pl.DA; rp.DC = pl.DC;
+    rp.B = a.B; rp.T = a.T; rp.Tp = (a.T + 3) / 4 * 4; rp.Te = (a.T + 15) / 16 * 16; rp.NATT = pl.NATT; rp.NSL = pl.NSL; rp.DA = pl.DA; rp.DC = pl.DC;
     rp.max_steps = a.max_steps; rp.stop_mode = a.stop_mode; rp.mem_resident = pl.resident; rp.thr = a.gate_threshold;
     static const int bg_sleep = [] { const char* e = getenv("TACO_RES_BG_SLEEP"); return e ? atoi(e) : 0; }();
     static const int bg_backoff = [] { const char* e = getenv("TACO_RES_BG_BACKOFF"); return e ? atoi(e) : 0; }();
@@ -977,7 +951,9 @@ int decoder_res_run(const b200taco_handle* h, const DecoderArgs& a, void* scratc
     const_cast<b200taco_handle*>(h)->last_trace = rp.trace;
     const_cast<b200taco_handle*>(h)->last_profile = rp.prof;
     const int ncta = GEMM_CTAS + pl.NATT + NFR;
-    return a.B == 1 ? launch_res<1>(rp, ncta, pl.smem, stream) : launch_res<2>(rp, ncta, pl.smem, stream);
+    rp.as = pl.as;
+    if (a.B == 2) return launch_res<2, 1>(rp, ncta, pl.smem, stream);
+    return pl.resident == 2 ? launch_res<1, 2>(rp, ncta, pl.smem, stream) : launch_res<1, 1>(rp, ncta, pl.smem, stream);
 }
 
 }  // namespace b200taco
