@@ -226,6 +226,39 @@ class Engine:
                                                  ws, wsz, self._stream()), "b200taco_postnet_fwd")
         return out
 
+    def postnet_for_vocoder(self, mel_coarse: torch.Tensor, lengths=None, frames=None):
+        """Postnet + vocoder hand-off in one pass: returns ``(mel_postnet (B,S,80), mel_vocoder (B,80,frames))``.  The second
+        tensor is what inference.py:71 builds with ``.transpose(1, 2)`` for the vocoder, written channel major by the epilogue
+        of the last postnet layer and zeroed from ``lengths[b]`` on (the per-utterance trim of train.py:71-79); ``frames``
+        (default S) cuts the frame axis, e.g. to the longest utterance."""
+        mel_coarse = mel_coarse.contiguous()
+        B, S, _ = mel_coarse.shape
+        frames = S if frames is None else int(frames)
+        out = torch.empty_like(mel_coarse)
+        voc = torch.empty(B, mel_coarse.shape[2], frames, dtype=torch.float32, device=mel_coarse.device)
+        if lengths is not None:
+            lengths = lengths.to(device=mel_coarse.device, dtype=torch.int32).contiguous()
+        ws, wsz = self._workspace(B, 1, S, "postnet")
+        with torch.cuda.device(self.device):
+            check(self._lib.b200taco_postnet_fwd_vocoder(self._h, mel_coarse.data_ptr(), B, S,
+                                                         lengths.data_ptr() if lengths is not None else None, frames,
+                                                         out.data_ptr(), voc.data_ptr(), ws, wsz, self._stream()),
+                  "b200taco_postnet_fwd_vocoder")
+        return out, voc
+
+    def vocoder_layout(self, mel: torch.Tensor, lengths=None, frames=None) -> torch.Tensor:
+        """(B,S,80) -> (B,80,frames) channel major, zero from ``lengths[b]`` on (inference.py:71, train.py:71-79)."""
+        mel = mel.contiguous()
+        B, S, _ = mel.shape
+        frames = S if frames is None else int(frames)
+        voc = torch.empty(B, mel.shape[2], frames, dtype=torch.float32, device=mel.device)
+        if lengths is not None:
+            lengths = lengths.to(device=mel.device, dtype=torch.int32).contiguous()
+        with torch.cuda.device(self.device):
+            check(self._lib.b200taco_vocoder_layout(mel.data_ptr(), lengths.data_ptr() if lengths is not None else None, B, S,
+                                                    frames, voc.data_ptr(), self._stream()), "b200taco_vocoder_layout")
+        return voc
+
     # ------------------------------------------------------------------ pipelined corpus synthesis
     def pipeline_infer(self, batches, max_steps: int, gate_threshold: float, stop_mode: int, to_host: bool = False,
                        pre_hook=None, timings=None):

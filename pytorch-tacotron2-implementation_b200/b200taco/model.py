@@ -235,6 +235,27 @@ class Tacotron2(nn.Module):
                                                          STOP_PER_UTTERANCE)
         return post, coarse, gate, list(align.unbind(0)), lengths
 
+    @torch.no_grad()
+    def inference_for_vocoder(self, text_inputs, max_len_cap=None, gate_threshold=None):
+        """Free-running inference that hands the mel straight to a vocoder: ``(mel_for_vocoder (B,80,S), lengths (B,))``.
+
+        The reference computes ``mel_outputs_postnet.transpose(1, 2)`` (inference.py:71) and trims each utterance at its own
+        stop frame on the host (train.py:71-79: first frame whose sigmoid(gate) > 0.5, plus one).  Here every row decodes
+        until its own gate fires, S is the longest utterance, and the last postnet layer writes the channel-major tensor
+        from its epilogue with the frames behind each row's length zeroed."""
+        self._check_mode("Tacotron2.inference_for_vocoder")
+        thr = gate_threshold if gate_threshold is not None else self.decoder.gate_threshold
+        cap = self.decoder.max_decoder_steps
+        if max_len_cap:
+            cap = min(cap, int(max_len_cap))
+        eng = self._get_engine()
+        if text_inputs.shape[0] > eng.max_batch:
+            coarse, _, _, lengths, S = self._infer_chunked(eng, text_inputs, cap, thr, STOP_PER_UTTERANCE)
+        else:
+            coarse, _, _, lengths, S = eng.decoder_infer(eng.encoder(text_inputs), cap, thr, STOP_PER_UTTERANCE)
+        _, voc = eng.postnet_for_vocoder(coarse.contiguous(), lengths, S)
+        return voc, lengths
+
     @staticmethod
     def _infer_chunked(eng, text_inputs, cap, thr, stop_mode):
         """More rows than one launch carries: rows never interact, so the chunks decode one after the other.

@@ -145,6 +145,36 @@ __device__ __forceinline__ uint32_t ll_gather(const uint64_t* src, float* dst, i
     return stop;
 }
 
+// Every broadcast vector exists in NREP copies at different addresses, and the L2 slice (and die) that owns an address is a
+// hash of it: a consumer on the far die sees a new value ~0.35 us later than one next to the owning slice (measured: the gate
+// CTAs of one die receive the prenet output that much later than the other die's).  Each thread therefore times a few loads
+// of ITS words in every copy once, per ring slot, and polls the copy that answers fastest: 2 bits per slot.
+__device__ __forceinline__ uint32_t pick_replicas(const uint64_t* xch, size_t slot_words, size_t vec_off, size_t rep_stride) {
+    uint32_t choice = 0u;
+    for (int slot = 0; slot < DEPTH; ++slot) {
+        long long best_t = 1ll << 40;
+        uint32_t best = 0u;
+        for (int r = 0; r < NREP; ++r) {
+            const uint64_t* q = xch + (size_t)slot * slot_words + vec_off + (size_t)r * rep_stride;
+            long long m = 1ll << 40;
+            for (int k = 0; k < 4; ++k) {
+                const long long t0 = clock64();
+                uint64_t z;
+                do {                                                  // the branch on the loaded value orders the clock reads
+                    const uint64_t w = ll_ld1(q);
+                    asm volatile("and.b64 %0, %1, 0;" : "=l"(z) : "l"(w));
+                } while (z != 0);
+                const long long dt = clock64() - t0;
+                m = dt < m ? dt : m;
+            }
+            if (m < best_t) { best_t = m; best = (uint32_t)r; }
+        }
+        choice |= best << (2 * slot);
+    }
+    return choice;
+}
+__device__ __forceinline__ int replica_of(uint32_t choice, int s) { return (int)((choice >> (2 * (s & (DEPTH - 1)))) & 3u); }
+
 // ---- gate-row contractions.  Warp w owns gate rows 2w, 2w+1 of the CTA (packed in one 32-bit word per k); lane l owns
 // k = 128 j + 4 l + i, so that both the weight vector and the activation vector of a lane are conflict-free 16-byte
 // shared-memory accesses.
@@ -301,6 +331,9 @@ __device__ __forceinline__ void gate_role(const RParams& p, uint8_t* smem, const
     }
     __syncthreads();
 
+    // the two vectors this CTA waits for on the critical path: thread i gathers words 2 i, 2 i + 1
+    const uint32_t rep_p = tid < BP * PRENET / 2 ? pick_replicas(p.xch, xl.words, xl.p + 2 * tid, BP * PRENET) : 0u;
+    const uint32_t rep_c = tid < BP * EMB / 2 ? pick_replicas(p.xch, xl.words, xl.ctx + 2 * tid, BP * EMB) : 0u;
     float acc_a[2][BP], acc_d[2][BP];
 #pragma unroll
     for (int b = 0; b < BP; ++b) { acc_a[0][b] = acc_a[1][b] = acc_d[0][b] = acc_d[1][b] = 0.f; }
@@ -326,7 +359,7 @@ __device__ __forceinline__ void gate_role(const RParams& p, uint8_t* smem, const
         const uint32_t tag = (uint32_t)s + 1u;
         uint64_t* X = p.xch + (size_t)(s & (DEPTH - 1)) * xl.words;
         // ---- attention LSTM: only the prenet rows wait for this step's input
-        const uint32_t stop = ll_gather(X + xl.p + rep * BP * PRENET, xp, BP * PRENET, tag, tid);
+        const uint32_t stop = ll_gather(X + xl.p + replica_of(rep_p, s) * BP * PRENET, xp, BP * PRENET, tag, tid);
         if (__syncthreads_or((int)stop)) break;
         if (s > 0) stamp(3);
         RES_EV(0);
@@ -345,7 +378,7 @@ __device__ __forceinline__ void gate_role(const RParams& p, uint8_t* smem, const
         gemv_smem<BP>(sW + (0 * RWARPS + warp) * RNN, xah, acc_a, lane);
         RES_EV(5);
         // ---- decoder LSTM: only the context rows wait for the attention
-        ll_gather(X + xl.ctx + rep * BP * EMB, xctx, BP * EMB, tag, tid);
+        ll_gather(X + xl.ctx + replica_of(rep_c, s) * BP * EMB, xctx, BP * EMB, tag, tid);
         __syncthreads();
         stamp(1);
         RES_EV(2);
@@ -417,7 +450,6 @@ __device__ __forceinline__ uint32_t ll_wait2(const uint64_t* p, uint32_t tag, fl
 // T <= 256 (one lane pair per encoder position).  The loop body must stay well inside the 32 KB instruction cache: a body
 // of 46 KB was measured to run 3x slower than its instruction count (every line refetched from L2 every decode step), so
 // layouts come precomputed from the host and the memory columns have ONE home per instantiation (MM).
-constexpr int MEMR = 20;                      // MM == 2: encoder positions per thread whose memory column sits in registers
 constexpr int RES_MAX_T = 256;
 template <int RW>
 __host__ inline ASmem a_smem(int T, int DA, int DC, bool mem_in_smem) {
@@ -436,7 +468,7 @@ __host__ inline ASmem a_smem(int T, int DA, int DC, bool mem_in_smem) {
     a.winc = take(Tp + 64);
     a.pm = take(DA * a.SP);
     a.pre = take(DA * a.SP);
-    a.ew = take(a.NTG * a.PT + 16);                   // position groups read whole float4s; zero beyond T
+    a.ew = take((a.NTG * a.PT > RES_MAX_T ? a.NTG * a.PT : RES_MAX_T) + 16);   // read as whole float4s; zero beyond T
     a.mx = take(RWARPS);
     a.cpart = take(a.NTG * DC);
     a.spart = take(RWARPS + 4);
@@ -480,7 +512,7 @@ __device__ __forceinline__ void attn_role(const RParams& p, uint8_t* smem, const
     }
     for (int i = tid; i < p.Tp + 64; i += RT) { winp[i] = 0.f; winc[i] = 0.f; }
     for (int i = tid; i < DA * SP; i += RT) { pm_s[i] = 0.f; pre_s[i] = 0.f; }
-    for (int i = tid; i < NTG * PT + 16; i += RT) ew_s[i] = 0.f;
+    for (int i = tid; i < (NTG * PT > RES_MAX_T ? NTG * PT : RES_MAX_T) + 16; i += RT) ew_s[i] = 0.f;
     __syncthreads();
     for (int i = tid; i < T * na; i += RT) {
         const int t = i / na, a = i % na;
@@ -488,10 +520,12 @@ __device__ __forceinline__ void attn_role(const RParams& p, uint8_t* smem, const
         pm_s[a * SP + t] = v;
         pre_s[a * SP + t] = v;                                  // decode step 0: zero attention history
     }
-    // context: thread (ctg, cd) owns positions [ctg * PT, ctg * PT + PT) of memory column d0 + cd; the same pair is the
-    // (replica, dim) of the thread that publishes a context dim
+    // context: thread (ctg, cd) owns positions [ctg PT, ctg PT + PT) of memory column d0 + cd, held in registers (MM == 2) or
+    // shared memory (MM == 1); the same pair is the (replica, dim) of the thread that publishes a context dim.  (A variant that
+    // finished every dim with one warp reduction - no shared-memory partials, no block barrier - measured 1 us SLOWER per step.)
     const int ctg = tid / DC, cd = tid % DC;
     const float* memG = p.memory + (size_t)b * T * EMB + d0;
+    constexpr int MEMR = 20;                                   // MM == 2: positions per thread held in registers
     float memr[MM == 2 ? MEMR : 1];
     if (MM == 2) {
 #pragma unroll
@@ -513,7 +547,7 @@ __device__ __forceinline__ void attn_role(const RParams& p, uint8_t* smem, const
     int ulen[BP];
 #pragma unroll
     for (int q = 0; q < BP; ++q) { done[q] = false; ulen[q] = 0; }
-    const int rep = cta % NREP;
+    const uint32_t rep_ah = pick_replicas(p.xch, xl.words, xl.ah + (size_t)b * RNN + 2 * tid, BP * RNN);
     const int nitems = ((T + TB - 1) / TB) * na;
     const int al0 = sl * ((T + NSL - 1) / NSL), al1 = min(T, al0 + (T + NSL - 1) / NSL);     // alignment columns written by this CTA
     const int et = tid >> 1, eh = lane & 1;                    // energies: lane pair (position, dim / slice parity)
@@ -565,7 +599,7 @@ __device__ __forceinline__ void attn_role(const RParams& p, uint8_t* smem, const
         // ---- (1) attention hidden state -> own rows of the processed query (src/model.py:123): K split over the threads
         {
             float x0, x1;
-            ll_wait2(X + xl.ah + (size_t)(rep * BP + b) * RNN + 2 * tid, tag, x0, x1);
+            ll_wait2(X + xl.ah + (size_t)(replica_of(rep_ah, s) * BP + b) * RNN + 2 * tid, tag, x0, x1);
             RES_EV(1);
             float v[RW];
 #pragma unroll
@@ -633,49 +667,52 @@ __device__ __forceinline__ void attn_role(const RParams& p, uint8_t* smem, const
         }
         __syncthreads();
         RES_EV(5);
-        // ---- (4) own context dims (src/model.py:146) and the softmax denominator: NTG position groups x DC dims
-        if (ctg < NTG) {
-            float c0 = 0.f, c1 = 0.f, s0 = 0.f, s1 = 0.f;
-            const float* ew_g = ew_s + ctg * PT;
-            if (MM == 2) {
+        // ---- (4) own context dims (src/model.py:146) and the softmax denominator
+        float Ssum;
+        {
+            if (ctg < NTG) {
+                float c0 = 0.f, c1 = 0.f, s0 = 0.f, s1 = 0.f;
+                const float* ew_g = ew_s + ctg * PT;
+                if (MM == 2) {
 #pragma unroll
-                for (int i = 0; i < MEMR; i += 4) {
-                    if (i < PT) {
-                        const float4 e4 = *reinterpret_cast<const float4*>(ew_g + i);      // zero beyond T
-                        c0 = fmaf(e4.x, memr[i], c0);
-                        c1 = fmaf(e4.y, memr[i + 1], c1);
-                        c0 = fmaf(e4.z, memr[i + 2], c0);
-                        c1 = fmaf(e4.w, memr[i + 3], c1);
-                        s0 += e4.x + e4.z;
-                        s1 += e4.y + e4.w;
+                    for (int i = 0; i < MEMR; i += 4) {
+                        if (i < PT) {
+                            const float4 e4 = *reinterpret_cast<const float4*>(ew_g + i);      // zero beyond T
+                            c0 = fmaf(e4.x, memr[i], c0);
+                            c1 = fmaf(e4.y, memr[i + 1], c1);
+                            c0 = fmaf(e4.z, memr[i + 2], c0);
+                            c1 = fmaf(e4.w, memr[i + 3], c1);
+                            s0 += e4.x + e4.z;
+                            s1 += e4.y + e4.w;
+                        }
+                    }
+                } else {
+                    const float* mp = mem_s + (size_t)ctg * PT * DC + cd;
+#pragma unroll 4
+                    for (int i = 0; i < PT; i += 2) {
+                        const float2 e2 = *reinterpret_cast<const float2*>(ew_g + i);
+                        c0 = fmaf(e2.x, mp[(size_t)i * DC], c0);
+                        c1 = fmaf(e2.y, mp[(size_t)(i + 1) * DC], c1);
+                        s0 += e2.x;
+                        s1 += e2.y;
                     }
                 }
-            } else {
-                const float* mp = mem_s + (size_t)ctg * PT * DC + cd;
-#pragma unroll 4
-                for (int i = 0; i < PT; i += 2) {
-                    const float2 e2 = *reinterpret_cast<const float2*>(ew_g + i);
-                    c0 = fmaf(e2.x, mp[(size_t)i * DC], c0);
-                    c1 = fmaf(e2.y, mp[(size_t)(i + 1) * DC], c1);
-                    s0 += e2.x;
-                    s1 += e2.y;
-                }
+                cpart_s[ctg * DC + cd] = c0 + c1;
+                if (cd == 0) spart_s[ctg] = s0 + s1;
             }
-            cpart_s[ctg * DC + cd] = c0 + c1;
-            if (cd == 0) spart_s[ctg] = s0 + s1;
-        }
-        __syncthreads();
-        RES_EV(6);
-        float Ssum = 0.f;
+            __syncthreads();
+            RES_EV(6);
+            Ssum = 0.f;
 #pragma unroll
-        for (int g = 0; g < RWARPS; ++g)                             // NTG <= 16 (DC >= 32)
-            if (g < NTG) Ssum += spart_s[g];
-        if (ctg < NREP && cd < nd) {
-            float c = 0.f;
+            for (int g = 0; g < RWARPS; ++g)                         // NTG <= 16 (DC >= 32)
+                if (g < NTG) Ssum += spart_s[g];
+            if (ctg < NREP && cd < nd) {
+                float c = 0.f;
 #pragma unroll
-            for (int g = 0; g < RWARPS; ++g)
-                if (g < NTG) c += cpart_s[g * DC + cd];
-            ll_st(X + xl.ctx + (size_t)(ctg * BP + b) * EMB + d0 + cd, c / Ssum, tag);
+                for (int g = 0; g < RWARPS; ++g)
+                    if (g < NTG) c += cpart_s[g * DC + cd];
+                ll_st(X + xl.ctx + (size_t)(ctg * BP + b) * EMB + d0 + cd, c / Ssum, tag);
+            }
         }
         RES_EV(7);
         // ---- (5) attention weights: alignment output (this CTA's columns), windows of the next step (src/model.py:142-145)
@@ -753,7 +790,12 @@ __device__ __forceinline__ void frame_role(const RParams& p, uint8_t* smem, cons
     int ulen[BP];
 #pragma unroll
     for (int q = 0; q < BP; ++q) { done[q] = false; ulen[q] = 0; }
-    const int rep = cta % NREP;
+    uint32_t rep_fc[BP], rep_fd[BP];
+#pragma unroll
+    for (int q = 0; q < BP; ++q) {
+        rep_fc[q] = pick_replicas(p.xch, xl.words, xl.ctx + (size_t)q * EMB + tid, BP * EMB);
+        rep_fd[q] = pick_replicas(p.xch, xl.words, xl.dh + (size_t)q * RNN + 2 * tid, BP * RNN);
+    }
 
     for (int s = 0; s < total_steps; ++s) {
         const uint32_t tag = (uint32_t)s + 1u;
@@ -762,10 +804,10 @@ __device__ __forceinline__ void frame_role(const RParams& p, uint8_t* smem, cons
         // ---- (1) context (arrives first) and decoder hidden state -> this CTA's projection rows
 #pragma unroll
         for (int q = 0; q < BP; ++q) {
-            const float xc = ll_wait1(X + xl.ctx + (size_t)(rep * BP + q) * EMB + tid, tag);
+            const float xc = ll_wait1(X + xl.ctx + (size_t)(replica_of(rep_fc[q], s) * BP + q) * EMB + tid, tag);
         RES_EV(0);
             float x0, x1;
-            ll_wait2(X + xl.dh + (size_t)(rep * BP + q) * RNN + 2 * tid, tag, x0, x1);
+            ll_wait2(X + xl.dh + (size_t)(replica_of(rep_fd[q], s) * BP + q) * RNN + 2 * tid, tag, x0, x1);
             RES_EVW(16);
             if (jf == 0) RES_EVT(1);
         RES_EV(1);
@@ -888,7 +930,8 @@ bool make_plan(const b200taco_handle* h, int B, int T, Plan& pl) {
     if (pl.DA > 16 * B || NREP * pl.DC > RT || pl.DC < 32) return false;
     const int NTG = RT / pl.DC, PT = (((T + NTG - 1) / NTG) + 3) & ~3;
     const size_t g = gate_smem_bytes(B), f = (size_t)f_smem(B).total * 4;
-    pl.resident = (B == 1 && PT <= MEMR) ? 2 : 1;                   // memory columns in registers / in shared memory
+    static const int mm_knob = [] { const char* e = getenv("TACO_RES_MM"); return e ? atoi(e) : 2; }();       // measurement knob
+    pl.resident = (B == 1 && mm_knob >= 2 && PT <= 20) ? 2 : 1;    // memory columns in registers / in shared memory
     pl.as = B == 1 ? a_smem<16>(T, pl.DA, pl.DC, pl.resident == 1) : a_smem<32>(T, pl.DA, pl.DC, pl.resident == 1);
     const size_t a = (size_t)pl.as.total * 4;
     pl.smem = g > a ? g : a;
