@@ -113,6 +113,12 @@ class Tacotron2(nn.Module):
         # storage of the decoder LSTM matrices in the packed cache: "bf16" (default, half the
         # L2 traffic per step) or "fp32" (the reference's values bit for bit)
         self.lstm_weight_dtype = "bf16"
+        # train-mode forward: None = the same packed cache as inference, i.e. MIXED PRECISION with the default "bf16" - the
+        # forward multiplies bf16-rounded decoder LSTM matrices (fp32 state and accumulation) while the hand-written backward
+        # differentiates with the fp32 master weights, as the reference's own loop does under torch.autocast (train.py:510);
+        # "fp32" = a second engine that packs the master weights unrounded (forward and backward see identical numbers)
+        self.train_lstm_weight_dtype = None
+        self._train_engine = None
         # "auto": tcgen05 tensor-core gate contractions when B >= 4 and bf16 weights; "simt": never
         self.decoder_path = "auto"
         # dense layers: "auto" = postnet / teacher-forced prenet on tcgen05 (3xTF32), encoder on fp32 CUDA cores;
@@ -135,9 +141,21 @@ class Tacotron2(nn.Module):
         self._engine.ensure_packed(self._tensors())
         return self._engine
 
+    def _get_train_engine(self) -> Engine:
+        want = self.train_lstm_weight_dtype or self.lstm_weight_dtype
+        if want == self.lstm_weight_dtype:
+            return self._get_engine()
+        dev = self.decoder.gate_layer.weight.device
+        if (self._train_engine is None or self._train_engine.device != dev or self._train_engine.weight_dtype != want
+                or self._train_engine.decoder_path != self.decoder_path or self._train_engine.dense_path != self.dense_path):
+            self._train_engine = Engine(dev, want, self.decoder_path, self.dense_path)
+        self._train_engine.ensure_packed(self._tensors())
+        return self._train_engine
+
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
         self._engine = None                             # .to(device) / .float(): rebuild lazily
+        self._train_engine = None
         return out
 
     def _check_mode(self, what):
@@ -173,7 +191,7 @@ class Tacotron2(nn.Module):
         here with PyTorch's device generator; one launch carries at most ``engine.max_batch`` rows and BatchNorm
         statistics span the whole batch, so larger batches are not chunked."""
         from . import train as T
-        eng = self._get_engine()                                   # (re)packs the decoder weights if a parameter changed
+        eng = self._get_train_engine()                             # (re)packs the decoder weights if a parameter changed
         B, S = text_inputs.shape[0], mel_targets.shape[2]
         if B > eng.max_batch:
             raise B200TacoError(f"train-mode forward carries at most {eng.max_batch} rows per call (got {B})")
