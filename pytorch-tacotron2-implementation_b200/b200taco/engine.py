@@ -60,6 +60,16 @@ def _hparams() -> _cabi.HParams:
     return _cabi.HParams(**config.as_hparams())
 
 
+def zero_beyond_lengths_(mel_coarse: torch.Tensor, lengths: torch.Tensor) -> torch.Tensor:
+    """Per-utterance stop rule: the rows of a batch keep decoding until the LAST one stops, so row b holds frames of a
+    continued decode behind its own length.  The postnet's five k=5 layers see 10 frames to either side; with those frames
+    zeroed, row b's ``mel_postnet[:length_b]`` is exactly what a solo run of utterance b (which ends at length_b, zero padding
+    behind it) produces - and the batch-by-batch and continuous-batching paths agree.  In place, asynchronous."""
+    S = mel_coarse.shape[1]
+    keep = torch.arange(S, device=mel_coarse.device)[None, :] < lengths.to(mel_coarse.device)[:, None]
+    return mel_coarse.mul_(keep[:, :, None].to(mel_coarse.dtype))
+
+
 class Engine:
     """One per model instance per device; not thread-safe."""
 
@@ -319,6 +329,8 @@ class Engine:
                 for t in (mel, gate, align, lengths):
                     t.record_stream(sP)
                 coarse = mel[:, :S].contiguous()
+                if stop_mode == STOP_PER_UTTERANCE:
+                    zero_beyond_lengths_(coarse, lengths)     # every row as if it had been decoded alone (see there)
                 post = self.postnet(coarse)
                 res = (post, coarse, gate[:, :S], align[:S], lengths, S)
                 if to_host:

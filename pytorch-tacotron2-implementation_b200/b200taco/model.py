@@ -22,7 +22,7 @@ import torch.nn as nn
 
 from . import config
 from ._cabi import B200TacoError
-from .engine import Engine, STOP_BATCH_WIDE, STOP_PER_UTTERANCE
+from .engine import Engine, STOP_BATCH_WIDE, STOP_PER_UTTERANCE, zero_beyond_lengths_
 
 
 def _conv_bn(c_in: int, c_out: int, k: int) -> nn.Sequential:
@@ -271,7 +271,7 @@ class Tacotron2(nn.Module):
             coarse, _, _, lengths, S = self._infer_chunked(eng, text_inputs, cap, thr, STOP_PER_UTTERANCE)
         else:
             coarse, _, _, lengths, S = eng.decoder_infer(eng.encoder(text_inputs), cap, thr, STOP_PER_UTTERANCE)
-        _, voc = eng.postnet_for_vocoder(coarse.contiguous(), lengths, S)
+        _, voc = eng.postnet_for_vocoder(zero_beyond_lengths_(coarse.contiguous(), lengths), lengths, S)
         return voc, lengths
 
     @staticmethod
@@ -342,6 +342,8 @@ class Tacotron2(nn.Module):
             memory = eng.encoder(text_inputs)
             coarse, gate, align, lengths, S = eng.decoder_infer(memory, cap, thr, stop_mode)
         coarse = coarse.contiguous()
+        if stop_mode == STOP_PER_UTTERANCE:
+            zero_beyond_lengths_(coarse, lengths)          # engine.zero_beyond_lengths_: every row as if decoded alone
         if S >= cap:
             print(f"Warning! Reached decode cap ({cap}).")                  # src/model.py:330
         if S < 3:

@@ -1851,9 +1851,16 @@ int launch_tc(const KParams& kp, int ncta, bool clusters, cudaStream_t stream) {
         at[0].val.clusterDim.x = GS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         at[1].id = cudaLaunchAttributeCooperative;
         at[1].val.cooperative = 1;
-        // TACO_TC_COOP=0 (profiling aid): plain cluster launch; the grid was sized by cudaOccupancyMaxActiveClusters, so on an
-        // otherwise idle device every CTA is still co-resident
-        static const bool coop = [] { const char* e = getenv("TACO_TC_COOP"); return !(e && e[0] == '0'); }();
+        // Nsight Compute cannot launch a grid that is BOTH cooperative and clustered (the driver answers LaunchFailed and the
+        // tool kills the process; measured with kernel and application replay), but it profiles the same grid as a plain cluster
+        // launch.  Under the tool's injection (it exports NV_NSIGHT_INJECTION_TRANSPORT_TYPE / NV_TPS_LAUNCH_TOKEN to its target),
+        // or with TACO_TC_COOP=0, the cooperative attribute is dropped: the grid was sized by cudaOccupancyMaxActiveClusters and
+        // a profiler serialises kernels, so every CTA is still co-resident.
+        static const bool coop = [] {
+            const char* e = getenv("TACO_TC_COOP");
+            if (e) return e[0] != '0';
+            return getenv("NV_NSIGHT_INJECTION_TRANSPORT_TYPE") == nullptr && getenv("NV_TPS_LAUNCH_TOKEN") == nullptr;
+        }();
         cfg.attrs = at; cfg.numAttrs = coop ? 2 : 1;
         TACO_CUDA(cudaLaunchKernelEx(&cfg, kern, kp));
         launch_counter()++;

@@ -22,6 +22,10 @@ pytestmark = pytest.mark.gpu
 
 TOL_MEL = 2e-5
 TOL_ALIGN = 2e-6
+# shape sweeps run on the STRESS weights (non-LSTM decoder matrices x 2.5, energy_scale 4.0) at the same
+# tolerances (largest errors measured over all shapes: mel 1.2e-7, gate 5e-6, postnet 2e-7, alignment 4e-7)
+SWEEP_TOL = TOL_MEL
+SWEEP_TOL_ALIGN = TOL_ALIGN
 
 
 def gpu_model(sd, weight_dtype="bf16"):
@@ -179,7 +183,7 @@ def test_shape_sweep_free_running_vs_oracle(B, T):
     with torch.no_grad():
         ref = O.tacotron2_inference(sd, ids, max_len_cap=12)
     gold = dict(mel_post=ref[0], mel_coarse=ref[1], gate=ref[2], align=util.stack(ref[3]))
-    check(out, gold, tol=5e-5, tol_align=5e-6)
+    check(out, gold, tol=SWEEP_TOL, tol_align=SWEEP_TOL_ALIGN)
 
 
 @pytest.mark.parametrize("B,T,S", [(1, 23, 9), (5, 77, 30), (32, 150, 20), (64, 33, 6)])
@@ -195,7 +199,7 @@ def test_shape_sweep_teacher_forced_vs_oracle(B, T, S):
     with torch.no_grad():
         ref = O.tacotron2_forward(sd, ids, mel, lengths)
     gold = dict(mel_post=ref[0], mel_coarse=ref[1], gate=ref[2], align=util.stack(ref[3]))
-    check(out, gold, tol=5e-5, tol_align=5e-6)
+    check(out, gold, tol=SWEEP_TOL, tol_align=SWEEP_TOL_ALIGN)
     al = util.stack(out[3]).cpu()
     for b in range(B):
         assert float(al[:, b, int(lengths[b]):].abs().max() if lengths[b] < T else 0.0) == 0.0   # masked positions
@@ -316,6 +320,8 @@ def test_continuous_batching_equals_batch_by_batch(rows, T, nb, cap):
             n = int(L[r])
             spread.add(n)
             assert torch.equal(o[1][r, :n], coarse[r, :n]) and torch.equal(o[2][r, :n], gate[r, :n])
+            assert torch.equal(o[0][r, :n], post[r, :n])                  # postnet saw zeros behind the row's length in both paths
+            assert not coarse[r, n:].any()
             assert torch.equal(o[3][:n, r], al[:n, r])
             assert not o[1][r, n:].any() and not o[2][r, n:].any() and not o[3][n:, r].any()
         assert torch.equal(o[6], o[0].cpu()) and o[0].shape == o[1].shape
@@ -386,3 +392,43 @@ def test_errors():
     with pytest.raises(B200TacoError):
         m.inference(synth.phoneme_ids(1, 2000).cuda())     # beyond b200taco_max_text_len
     assert m._engine.launch_count() > 0
+
+
+def test_stream_infer_c2_vs_oracle():
+    """The path bench.py times, at its own configuration, against the ORACLE (not against another CUDA path): continuous
+    batching (Engine.stream_infer) of K = 2 batches of 32 x 150 phonemes, the bench's planted stop counter (rate 8e-4, jitter
+    6e-3), cap 1000.  Per-utterance decoded lengths exact; mel_coarse / gate <= 2e-5, alignments <= 2e-6 and mel_postnet
+    <= 1e-4 up to each utterance's own length, zeros behind it.  The oracle decodes each batch with the batch-wide stop rule
+    disabled (threshold above 1) for as many frames as the longest utterance needs, and is trimmed per row by
+    train.py:71-79's rule; rows do not interact, so this is every utterance's solo decode."""
+    import bench
+    B, T, K = bench.B, bench.T, 2
+    sd0 = util.weights("default")
+    batches = [synth.phoneme_ids(B, T, seed=s) for s in (0, 17)]
+    with torch.no_grad():
+        center = O.encoder(sd0, batches[0]).mean((0, 1))
+    sd = util.weights("default")
+    with torch.no_grad():
+        synth.plant_stop_counter_(sd, ctx_center=center, **bench.PLANT)
+        synth.round_to_bf16_(sd)
+    m = gpu_model(sd)
+    outs = list(m.inference_batches([x.cuda() for x in batches], max_len_cap=bench.CAP, continuous=True))
+    assert len(outs) == K
+    for ids, (post, coarse, gate, align, lengths, S) in zip(batches, outs):
+        L = lengths.cpu().tolist()
+        with torch.no_grad():
+            ref = O.tacotron2_inference(sd, ids, max_len_cap=max(L), gate_threshold=2.0)       # never stops early
+        rpost, rcoarse, rgate, ralign = ref[0], ref[1], ref[2], util.stack(ref[3])
+        want = O.per_utterance_lengths(rgate).tolist()                                         # train.py:71-79 with the steps > 1 guard
+        assert L == want, [(a, b) for a, b in zip(L, want) if a != b]
+        assert S == max(L) and min(L) >= 200 and max(L) - min(L) >= 100       # a real spread of stop frames
+        from b200taco.engine import zero_beyond_lengths_
+        zc = zero_beyond_lengths_(rcoarse.clone(), torch.tensor(L))
+        with torch.no_grad():
+            rpost_solo = zc + O.postnet(sd, zc.transpose(1, 2)).transpose(1, 2)
+        for b, n in enumerate(L):
+            assert util.maxdiff(coarse[b, :n].cpu(), rcoarse[b, :n]) <= TOL_MEL
+            assert util.maxdiff(gate[b, :n].cpu(), rgate[b, :n]) <= TOL_MEL
+            assert util.maxdiff(align[:n, b].cpu(), ralign[:n, b]) <= TOL_ALIGN
+            assert util.maxdiff(post[b, :n].cpu(), rpost_solo[b, :n]) <= 5 * TOL_MEL
+            assert not coarse[b, n:].any() and not gate[b, n:].any()
