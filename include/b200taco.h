@@ -212,6 +212,19 @@ B200TACO_API int32_t b200taco_decoder_infer_stream(b200taco_handle* h, const flo
                                       void* d_workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Ragged continuous batching: as b200taco_decoder_infer_stream, for utterances of DIFFERENT text lengths in one launch.
+ * d_memory (N,T,512) holds every utterance's exact-length encoder output (the reference's Tacotron2.inference ignores
+ * text_lengths, src/model.py:482-494, so an utterance must be encoded and decoded at its own length) in rows padded to the common
+ * T with finite values (zeros); d_text_lengths (N) int64 are the true lengths.  Every utterance attends to its own positions only
+ * (masked_fill of src/model.py:131-132 per utterance): its frames, gate logits and alignments [:, :length] are those of its solo
+ * exact-length decode; alignment columns behind its length are 0.
+ */
+B200TACO_API int32_t b200taco_decoder_infer_stream_ragged(b200taco_handle* h, const float* d_memory, const int64_t* d_text_lengths,
+                                                          int32_t N, int32_t rows, int32_t T, int32_t max_steps, float gate_threshold,
+                                                          float* d_mel, float* d_gate, float* d_align, int32_t* d_lengths,
+                                                          int32_t* d_steps_run, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Decoder.forward (teacher forcing), src/model.py:277-297, eval-mode dropout.
  *   d_mel_targets (B,80,S) as the reference receives them; d_text_lengths (B) int64 or
  *   NULL (= full length): positions >= length are masked with -1e9 (src/model.py:132).
@@ -322,8 +335,12 @@ B200TACO_API int32_t b200taco_gate_targets(const int64_t* d_mel_lengths, int32_t
  * Vocoder hand-off.  The reference hands mel_outputs_postnet.transpose(1, 2), i.e. (B, 80, S), to the
  * vocoder (inference.py:71) and trims every utterance to its own stop frame on the host (train.py:71-79).
  * b200taco_postnet_fwd_vocoder = b200taco_postnet_fwd that ALSO writes the result channel major into d_mel_vocoder
- * (B, 80, S_out), S_out <= S, zero from d_lengths[b] on (d_lengths NULL: nothing is zeroed), from the epilogue of the last
- * postnet layer; b200taco_vocoder_layout does the same for an existing (B, S, 80) tensor.
+ * (B, 80, S_out), S_out <= S, from the epilogue of the last postnet layer (d_mel_vocoder NULL: no second copy).
+ * d_lengths (B) int32, may be NULL: utterance b has d_lengths[b] frames.  With lengths EVERY postnet layer writes zeros
+ * behind an utterance's own length, so each utterance's frames [0, length) are exactly those of a solo run at its own length
+ * (where the convolutions see zero padding behind the last frame) although the batch is as long as its longest member; the
+ * frames of d_mel_post and d_mel_vocoder behind the length are zero.  (d_mel_coarse is expected zero there as well: the
+ * residual is added as is.)  b200taco_vocoder_layout writes the layout for an existing (B, S, 80) tensor.
  */
 B200TACO_API int32_t b200taco_postnet_fwd_vocoder(b200taco_handle* h, const float* d_mel_coarse, int32_t B, int32_t S,
                                                   const int32_t* d_lengths, int32_t S_out, float* d_mel_post, float* d_mel_vocoder,

@@ -79,6 +79,11 @@ SIGNATURES = {
                                                   C.c_void_p, C.c_void_p, C.c_void_p,
                                                   C.c_void_p, C.c_void_p,
                                                   C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b200taco_decoder_infer_stream_ragged": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                                         C.c_int32, C.c_int32, C.c_float,
+                                                         C.c_void_p, C.c_void_p, C.c_void_p,
+                                                         C.c_void_p, C.c_void_p,
+                                                         C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200taco_decoder_teacher_forced": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                     C.c_int32, C.c_int32, C.c_int32,
                                                     C.c_void_p, C.c_void_p, C.c_void_p,

@@ -64,7 +64,8 @@ def zero_beyond_lengths_(mel_coarse: torch.Tensor, lengths: torch.Tensor) -> tor
     """Per-utterance stop rule: the rows of a batch keep decoding until the LAST one stops, so row b holds frames of a
     continued decode behind its own length.  The postnet's five k=5 layers see 10 frames to either side; with those frames
     zeroed, row b's ``mel_postnet[:length_b]`` is exactly what a solo run of utterance b (which ends at length_b, zero padding
-    behind it) produces - and the batch-by-batch and continuous-batching paths agree.  In place, asynchronous."""
+    behind it) produces - together with ``Engine.postnet(coarse, lengths)``, which also zeroes every intermediate layer behind
+    the row's length.  In place, asynchronous."""
     S = mel_coarse.shape[1]
     keep = torch.arange(S, device=mel_coarse.device)[None, :] < lengths.to(mel_coarse.device)[:, None]
     return mel_coarse.mul_(keep[:, :, None].to(mel_coarse.dtype))
@@ -180,12 +181,14 @@ class Engine:
         """The utterance queue lives in the tensor-core decoder kernel (bf16 LSTM weights, >= 4 rows)."""
         return self.weight_dtype == "bf16" and self.decoder_path == "auto" and 4 <= rows <= self.max_batch
 
-    def decoder_infer_stream(self, memory, rows: int, max_steps: int, gate_threshold: float):
+    def decoder_infer_stream(self, memory, rows: int, max_steps: int, gate_threshold: float, text_lengths=None):
         """Continuous batching (b200taco_decoder_infer_stream): the N utterances of ``memory`` (N,T,512), N a multiple of
         ``rows``, stream through ``rows`` decoder rows of one persistent kernel.  Returns, without synchronising,
         ``mel (N,cap,80), gate (N,cap), align (N/rows,cap,rows,T), len_h (N+1)``; frames beyond an utterance's length
         are zero.  ``len_h`` is PINNED HOST memory the kernel writes directly: ``len_h[u]`` becomes the length of
-        utterance u (> 0) the moment it stops, ``len_h[N]`` the decode steps of the launch when it ends."""
+        utterance u (> 0) the moment it stops, ``len_h[N]`` the decode steps of the launch when it ends.
+        ``text_lengths`` (N,) int64: ragged launch - ``memory`` rows are exact-length encoder outputs zero padded to T and every
+        utterance attends to its own length only (b200taco_decoder_infer_stream_ragged)."""
         assert memory.is_contiguous()
         N, T, _ = memory.shape
         dev = self.device
@@ -199,10 +202,19 @@ class Engine:
             ws = torch.empty(need, dtype=torch.uint8, device=dev)
             self._ws["stream"] = ws
         with torch.cuda.device(dev):
-            check(self._lib.b200taco_decoder_infer_stream(
-                self._h, memory.data_ptr(), N, rows, T, max_steps, float(gate_threshold),
-                mel.data_ptr(), gate.data_ptr(), align.data_ptr(), len_h.data_ptr(), len_h.data_ptr() + 4 * N,
-                C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()), self._stream()), "b200taco_decoder_infer_stream")
+            if text_lengths is None:
+                check(self._lib.b200taco_decoder_infer_stream(
+                    self._h, memory.data_ptr(), N, rows, T, max_steps, float(gate_threshold),
+                    mel.data_ptr(), gate.data_ptr(), align.data_ptr(), len_h.data_ptr(), len_h.data_ptr() + 4 * N,
+                    C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()), self._stream()), "b200taco_decoder_infer_stream")
+            else:
+                tl = text_lengths.to(device=dev, dtype=torch.int64).contiguous()
+                assert tl.shape == (N,)
+                self._keep = tl                                   # alive until the next launch on this engine
+                check(self._lib.b200taco_decoder_infer_stream_ragged(
+                    self._h, memory.data_ptr(), tl.data_ptr(), N, rows, T, max_steps, float(gate_threshold),
+                    mel.data_ptr(), gate.data_ptr(), align.data_ptr(), len_h.data_ptr(), len_h.data_ptr() + 4 * N,
+                    C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()), self._stream()), "b200taco_decoder_infer_stream_ragged")
         return mel, gate, align, len_h
 
     def decoder_teacher_forced(self, memory, mel_targets, text_lengths):
@@ -226,14 +238,23 @@ class Engine:
                 "b200taco_decoder_teacher_forced")
         return mel, gate, align
 
-    def postnet(self, mel_coarse: torch.Tensor) -> torch.Tensor:
+    def postnet(self, mel_coarse: torch.Tensor, lengths=None) -> torch.Tensor:
+        """mel_coarse (B,S,80) -> mel_postnet.  ``lengths`` (B,): per-utterance frame counts under the per-utterance stop rule -
+        every layer then writes zeros behind an utterance's own length, so ``out[b, :lengths[b]]`` is exactly the solo result
+        of utterance b (whose convolutions see zero padding behind its last frame); ``mel_coarse`` must be zero there."""
         mel_coarse = mel_coarse.contiguous()
         B, S, _ = mel_coarse.shape
         out = torch.empty_like(mel_coarse)
         ws, wsz = self._workspace(B, 1, S, "postnet")
         with torch.cuda.device(self.device):
-            check(self._lib.b200taco_postnet_fwd(self._h, mel_coarse.data_ptr(), B, S, out.data_ptr(),
-                                                 ws, wsz, self._stream()), "b200taco_postnet_fwd")
+            if lengths is None:
+                check(self._lib.b200taco_postnet_fwd(self._h, mel_coarse.data_ptr(), B, S, out.data_ptr(),
+                                                     ws, wsz, self._stream()), "b200taco_postnet_fwd")
+            else:
+                lengths = lengths.to(device=mel_coarse.device, dtype=torch.int32).contiguous()
+                check(self._lib.b200taco_postnet_fwd_vocoder(self._h, mel_coarse.data_ptr(), B, S, lengths.data_ptr(), S,
+                                                             out.data_ptr(), None, ws, wsz, self._stream()),
+                      "b200taco_postnet_fwd_vocoder")
         return out
 
     def postnet_for_vocoder(self, mel_coarse: torch.Tensor, lengths=None, frames=None):
@@ -331,7 +352,7 @@ class Engine:
                 coarse = mel[:, :S].contiguous()
                 if stop_mode == STOP_PER_UTTERANCE:
                     zero_beyond_lengths_(coarse, lengths)     # every row as if it had been decoded alone (see there)
-                post = self.postnet(coarse)
+                post = self.postnet(coarse, lengths if stop_mode == STOP_PER_UTTERANCE else None)
                 res = (post, coarse, gate[:, :S], align[:S], lengths, S)
                 if to_host:
                     post_h = torch.empty(post.shape, dtype=post.dtype, pin_memory=True)
@@ -365,6 +386,82 @@ class Engine:
         ev_post.synchronize()
         cur.wait_stream(sP)
         yield res
+
+    def stream_infer_ragged(self, utterances, max_steps: int, gate_threshold: float, rows: int = 64, launch_utterances: int = 2048,
+                            length_ratio: float = 1.35, to_host: bool = False):
+        """Corpus synthesis with continuous batching over utterances of DIFFERENT text lengths (BASELINE config 4).
+
+        ``utterances``: sequence of 1-D int64 id tensors (host).  The reference's inference takes no text lengths (F8), so
+        every utterance is ENCODED at its exact length (one encoder call per group of equal-length utterances) and its encoder
+        output is placed in a row padded to the launch's longest utterance; the decoder launch masks every utterance to its
+        own length, which reproduces its solo exact-length decode.  Launches are cut from the length-sorted corpus so that the
+        longest utterance of a launch is at most ``length_ratio`` x its shortest (attention work is spent on the padded width)
+        and hold at most ``launch_utterances`` utterances; a launch is filled up to a multiple of ``rows`` by repeating its own
+        utterances (results dropped).  Yields ``(index, mel_postnet (S,80), mel_coarse (S,80), gate (S,), alignments (S,T_i))``
+        per utterance, device tensors (pinned host tensors with ``to_host``), in completion order of the launches."""
+        import time
+        dev = self.device
+        if not self.stream_supported(rows):
+            raise B200TacoError("stream_infer_ragged needs 4 <= rows <= 64 and the default (bf16, tensor-core) decoder")
+        lens = [int(u.shape[0]) for u in utterances]
+        order = sorted(range(len(lens)), key=lambda i: (lens[i], i))
+        launches, cur_l = [], []
+        for i in order:
+            if cur_l and (len(cur_l) >= launch_utterances or lens[i] > length_ratio * lens[cur_l[0]]):
+                launches.append(cur_l)
+                cur_l = []
+            cur_l.append(i)
+        if cur_l:
+            launches.append(cur_l)
+        self.last_stream_steps = 0
+        for members in launches:
+            n_real = len(members)
+            members = members + [members[k % n_real] for k in range((-n_real) % rows)]      # fill the last rows
+            N, Tmax = len(members), max(lens[i] for i in members)
+            mem = torch.zeros(N, Tmax, config.encoder_embedding_dim, dtype=torch.float32, device=dev)
+            by_len = {}
+            for slot, i in enumerate(members[:n_real]):
+                by_len.setdefault(lens[i], []).append((slot, i))
+            for T_i, items in by_len.items():                        # exact-length encoder batches
+                for lo in range(0, len(items), self.max_batch):
+                    part = items[lo:lo + self.max_batch]
+                    ids = torch.stack([utterances[i] for _, i in part]).to(dev, non_blocking=True)
+                    mem[torch.tensor([s_ for s_, _ in part], device=dev), :T_i] = self.encoder(ids)
+            if N > n_real:
+                mem[n_real:] = mem[torch.tensor([k % n_real for k in range(N - n_real)], device=dev)]
+            tl = torch.tensor([lens[i] for i in members], dtype=torch.int64)
+            mel, gate, align, len_h = self.decoder_infer_stream(mem, rows, max_steps, gate_threshold, text_lengths=tl)
+            done_ev = torch.cuda.Event()
+            done_ev.record()
+            for c in range(N // rows):                               # postnet of a chunk as soon as its utterances have stopped
+                lo, hi = c * rows, (c + 1) * rows
+                while int(len_h[lo:hi].min()) <= 0:
+                    if done_ev.query():
+                        done_ev.synchronize()
+                        if int(len_h[lo:hi].min()) <= 0:
+                            raise B200TacoError("decoder launch ended with unfinished utterances")
+                        break
+                    time.sleep(2e-5)
+                S = int(len_h[lo:hi].max())
+                if not hasattr(self, "_streams"):
+                    self._streams = tuple(torch.cuda.Stream(dev) for _ in range(3))
+                sP = self._streams[2]
+                with torch.cuda.stream(sP):
+                    coarse = mel[lo:hi, :S].contiguous()              # zero behind every utterance's own length
+                    post = self.postnet(coarse, len_h[lo:hi].to(dev, non_blocking=True))
+                    if to_host:
+                        post = post.to("cpu", non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(sP)
+                ev.synchronize()
+                for r in range(rows):
+                    slot = lo + r
+                    if slot >= n_real:
+                        break
+                    i, n = members[slot], int(len_h[slot])
+                    yield i, post[r, :n], coarse[r, :n], gate[slot, :n], align[c, :n, r, :lens[i]]
+            done_ev.synchronize()
+            self.last_stream_steps += int(len_h[-1])
 
     def stream_infer(self, batches, max_steps: int, gate_threshold: float, to_host: bool = False, group_batches: int = 16,
                      pre_hook=None, timings=None):
@@ -446,8 +543,8 @@ class Engine:
                 with torch.cuda.stream(sP):
                     # no wait on the decoder stream: the kernel published these lengths after the frames themselves
                     coarse = mel[lo:hi, :S].contiguous()
-                    post = self.postnet(coarse)
                     lengths = len_h[lo:hi].to(dev, non_blocking=True)
+                    post = self.postnet(coarse, lengths)
                     res = (post, coarse, gate[lo:hi, :S], align[i, :S], lengths, S)
                     if to_host:
                         post_h = torch.empty(post.shape, dtype=post.dtype, pin_memory=True)

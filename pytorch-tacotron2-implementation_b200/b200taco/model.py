@@ -329,6 +329,21 @@ class Tacotron2(nn.Module):
             return
         yield from eng.pipeline_infer(batches, cap, thr, STOP_PER_UTTERANCE if per_utterance else STOP_BATCH_WIDE, to_host)
 
+    @torch.no_grad()
+    def inference_corpus(self, utterances, max_len_cap=None, gate_threshold=None, rows=64, to_host=False, **launch_args):
+        """Corpus synthesis over utterances of DIFFERENT lengths (BASELINE config 4): ``utterances`` is a sequence of 1-D id
+        tensors; every utterance is encoded and decoded at its own exact length (the reference's ``inference`` has no pad
+        mask, F8) under the per-utterance stop rule, ``rows`` of them at a time inside persistent decoder launches whose rows
+        are refilled as utterances stop (``Engine.stream_infer_ragged``).  Yields ``(index, mel_postnet (S_i,80), mel_coarse
+        (S_i,80), gate_logits (S_i,), alignments (S_i,T_i))`` per utterance, each equal to that utterance's solo
+        ``inference_per_utterance`` result."""
+        self._check_mode("Tacotron2.inference_corpus")
+        thr = gate_threshold if gate_threshold is not None else self.decoder.gate_threshold
+        cap = self.decoder.max_decoder_steps
+        if max_len_cap:
+            cap = min(cap, int(max_len_cap))
+        yield from self._get_engine().stream_infer_ragged(utterances, cap, thr, rows=rows, to_host=to_host, **launch_args)
+
     def _infer(self, text_inputs, max_len_cap, gate_threshold, stop_mode):
         self._check_mode("Tacotron2.inference")
         thr = gate_threshold if gate_threshold is not None else self.decoder.gate_threshold
@@ -349,5 +364,5 @@ class Tacotron2(nn.Module):
         if S < 3:
             print(f"[WARN] Very short mel length ({S}) - possible premature stop. "
                   f"Gate threshold={self.decoder.gate_threshold}")          # src/model.py:496-497
-        post = eng.postnet(coarse)
+        post = eng.postnet(coarse, lengths if stop_mode == STOP_PER_UTTERANCE else None)
         return post, coarse, gate.contiguous(), align, lengths

@@ -278,10 +278,9 @@ B200TACO_API size_t b200taco_stream_workspace_bytes(const b200taco_handle*, int3
     return stream_ws_bytes(N, rows, T);
 }
 
-B200TACO_API int32_t b200taco_decoder_infer_stream(b200taco_handle* h, const float* d_memory, int32_t N, int32_t rows, int32_t T,
-                                                   int32_t max_steps, float gate_threshold, float* d_mel, float* d_gate,
-                                                   float* d_align, int32_t* d_lengths, int32_t* d_steps_run, void* d_workspace,
-                                                   size_t workspace_bytes, void* stream) {
+static int32_t infer_stream(b200taco_handle* h, const float* d_memory, const int64_t* d_text_lengths, int32_t N, int32_t rows, int32_t T,
+                            int32_t max_steps, float gate_threshold, float* d_mel, float* d_gate, float* d_align, int32_t* d_lengths,
+                            int32_t* d_steps_run, void* d_workspace, size_t workspace_bytes, void* stream) {
     TACO_TRY(check_handle(h, true));
     TACO_TRY(check_shape(rows, T));
     TACO_REQUIRE(d_memory && d_mel && d_gate && d_align && d_lengths && d_steps_run && d_workspace, B200TACO_ERR_INVALID,
@@ -300,10 +299,27 @@ B200TACO_API int32_t b200taco_decoder_infer_stream(b200taco_handle* h, const flo
     DecoderArgs a{};
     a.B = rows; a.T = T; a.max_steps = max_steps; a.mode = 0; a.stop_mode = B200TACO_STOP_PER_UTTERANCE;
     a.gate_threshold = gate_threshold; a.n_utts = N;
-    a.memory = d_memory; a.pm = pm; a.text_lengths = nullptr; a.p_all = nullptr;
+    a.memory = d_memory; a.pm = pm; a.text_lengths = d_text_lengths; a.p_all = nullptr;
     a.mel = d_mel; a.gate = d_gate; a.align = d_align; a.lengths = d_lengths; a.steps_run = d_steps_run;
     a.scratch = scratch; a.scratch_bytes = decoder_scratch_bytes(rows, T);
     return decoder_run(h, a, st);
+}
+
+B200TACO_API int32_t b200taco_decoder_infer_stream(b200taco_handle* h, const float* d_memory, int32_t N, int32_t rows, int32_t T,
+                                                   int32_t max_steps, float gate_threshold, float* d_mel, float* d_gate,
+                                                   float* d_align, int32_t* d_lengths, int32_t* d_steps_run, void* d_workspace,
+                                                   size_t workspace_bytes, void* stream) {
+    return infer_stream(h, d_memory, nullptr, N, rows, T, max_steps, gate_threshold, d_mel, d_gate, d_align, d_lengths, d_steps_run,
+                        d_workspace, workspace_bytes, stream);
+}
+
+B200TACO_API int32_t b200taco_decoder_infer_stream_ragged(b200taco_handle* h, const float* d_memory, const int64_t* d_text_lengths,
+                                                          int32_t N, int32_t rows, int32_t T, int32_t max_steps, float gate_threshold,
+                                                          float* d_mel, float* d_gate, float* d_align, int32_t* d_lengths,
+                                                          int32_t* d_steps_run, void* d_workspace, size_t workspace_bytes, void* stream) {
+    TACO_REQUIRE(d_text_lengths != nullptr, B200TACO_ERR_INVALID, "decoder_infer_stream_ragged: null text lengths");
+    return infer_stream(h, d_memory, d_text_lengths, N, rows, T, max_steps, gate_threshold, d_mel, d_gate, d_align, d_lengths, d_steps_run,
+                        d_workspace, workspace_bytes, stream);
 }
 
 B200TACO_API int32_t b200taco_decoder_teacher_forced(b200taco_handle* h, const float* d_memory, const float* d_mel_targets,
@@ -421,9 +437,11 @@ static int postnet_run(b200taco_handle* h, const float* d_mel_coarse, int32_t B,
         const bool last = i == POST_CONVS - 1;
         const int c_out = last ? N_MELS : POST_DIM;
         float* dst = last ? d_mel_post : bufs[i & 1];
+        ChannelMajorOut opt = cm;                       // every layer zeroes the rows behind an utterance's own length ...
+        if (!last) opt.y = nullptr;                     // ... and the last one also writes the vocoder layout
         TACO_TRY(dense_layer(h, src, c_in, h->post_conv_w[i], h->post_conv_wtc[i], h->post_conv_scale[i], h->post_conv_shift[i],
                                       last ? d_mel_coarse : nullptr, N_MELS, dst, c_out, n, S, c_in, c_out, POST_KERNEL,
-                                      last ? ACT_NONE : ACT_TANH, false, st, last ? cm : ChannelMajorOut()));
+                                      last ? ACT_NONE : ACT_TANH, false, st, opt));
         src = dst;
         c_in = c_out;
     }
@@ -438,10 +456,11 @@ B200TACO_API int32_t b200taco_postnet_fwd(b200taco_handle* h, const float* d_mel
 B200TACO_API int32_t b200taco_postnet_fwd_vocoder(b200taco_handle* h, const float* d_mel_coarse, int32_t B, int32_t S,
                                                   const int32_t* d_lengths, int32_t S_out, float* d_mel_post, float* d_mel_vocoder,
                                                   void* d_workspace, size_t workspace_bytes, void* stream) {
-    TACO_REQUIRE(d_mel_vocoder != nullptr && S_out >= 1 && S_out <= S, B200TACO_ERR_INVALID, "postnet_fwd_vocoder: S_out %d outside [1, %d]",
-                 S_out, S);
+    TACO_REQUIRE(d_mel_vocoder == nullptr || (S_out >= 1 && S_out <= S), B200TACO_ERR_INVALID,
+                 "postnet_fwd_vocoder: S_out %d outside [1, %d]", S_out, S);
+    TACO_REQUIRE(d_mel_vocoder != nullptr || d_lengths != nullptr, B200TACO_ERR_INVALID, "postnet_fwd_vocoder: nothing to do beyond postnet_fwd");
     ChannelMajorOut cm;
-    cm.y = d_mel_vocoder; cm.lengths = d_lengths; cm.ld = S_out;
+    cm.y = d_mel_vocoder; cm.lengths = d_lengths; cm.ld = S_out; cm.zero_tail = d_lengths != nullptr;
     return postnet_run(h, d_mel_coarse, B, S, d_mel_post, cm, d_workspace, workspace_bytes, stream, "postnet_fwd_vocoder");
 }
 

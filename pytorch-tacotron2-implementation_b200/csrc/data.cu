@@ -53,7 +53,23 @@ __global__ void __launch_bounds__(256) vocoder_layout_kernel(const float* __rest
     }
 }
 
+__global__ void zero_tail_kernel(float* __restrict__ Y, int ldy, const int32_t* __restrict__ lengths, int S, int C) {
+    const int b = blockIdx.y, len = lengths[b];
+    const long long n = (long long)(S - len) * C;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int s = len + (int)(e / C), c = (int)(e % C);
+        Y[((size_t)b * S + s) * ldy + c] = 0.f;
+    }
+}
+
 }  // namespace
+
+int zero_tail_rows(float* Y, int ldy, const int32_t* lengths, int B, int S, int C, cudaStream_t stream) {
+    TACO_REQUIRE(B >= 1 && B <= 65535, B200TACO_ERR_INVALID, "zero_tail_rows: B %d", B);
+    zero_tail_kernel<<<dim3(32, B), 256, 0, stream>>>(Y, ldy, lengths, S, C);
+    TACO_LAUNCHED();
+    return B200TACO_OK;
+}
 
 int vocoder_layout(const float* mel, int ldm, const int32_t* lengths, int B, int S, int C, int S_out, float* out, cudaStream_t stream) {
     TACO_REQUIRE(B >= 1 && B <= 65535 && S >= 1 && C >= 1 && S_out >= 1, B200TACO_ERR_INVALID, "vocoder_layout: B %d S %d C %d S_out %d", B, S,

@@ -583,7 +583,6 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
     for (int item = rev ? ncta - 1 - cta : cta; item < B * NS; item += ncta) {
         const int b = item / NS, sl = item % NS;
         const int t0 = sl * SL, t1 = min(T, t0 + SL), n = max(0, t1 - t0);
-        const int len = p.text_lengths ? (int)p.text_lengths[b] : T;
         // continuous batching: row b carries utterance mb since decode step rows[ROW_START + b]; its first step sees
         // zero previous / cumulative attention weights (src/model.py:104-115); a retired row repeats its last
         // utterance without writing anything the host reads
@@ -595,6 +594,10 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
             fresh = step == st;
             oi = u >= 0 ? step - st - 1 : -1;
         }
+        // pad mask (src/model.py:131-132, :443-450); ragged continuous batching: the utterances of a launch are padded to a common
+        // T and every utterance attends to its own length only, which is exactly its exact-length solo decode (weights of the
+        // padded positions are 0, like the zero padding of the location convolution at the end of an exact-length utterance)
+        const int len = p.text_lengths ? (int)p.text_lengths[mb] : T;
         const size_t align_row = (size_t)(rows != nullptr ? rows[ROW_ABASE + b] : b) + (size_t)(oi < 0 ? 0 : oi) * B;
         consumer_sync();   // previous item's scratch is free
         const int ntiles = (n + TILE_POS - 1) / TILE_POS;

@@ -259,18 +259,20 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                     o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w;
                     o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
                 }
+                const int ub = row / seg_len, us = row - ub * seg_len;
+                const bool keep = cm.lengths == nullptr || us < cm.lengths[ub];
+                if (cm.zero_tail && !keep) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = 0.f;
+                }
                 float4* dst = reinterpret_cast<float4*>(Y + (size_t)row * ldy + co);
                 dst[0] = make_float4(o[0], o[1], o[2], o[3]);
                 dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-                if (cm.y != nullptr) {
+                if (cm.y != nullptr && us < cm.ld) {
                     // second copy of the result in the vocoder's layout (B, c_out, cm.ld) (inference.py:71), zero from the
                     // utterance's own length on (train.py:71-79); consecutive lanes = consecutive frames: coalesced per channel
-                    const int ub = row / seg_len, us = row - ub * seg_len;
-                    if (us < cm.ld) {
-                        const bool keep = cm.lengths == nullptr || us < cm.lengths[ub];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) cm.y[((size_t)ub * c_out + co + i) * cm.ld + us] = keep ? o[i] : 0.f;
-                    }
+                    for (int i = 0; i < 8; ++i) cm.y[((size_t)ub * c_out + co + i) * cm.ld + us] = keep ? o[i] : 0.f;
                 }
             }
         }
@@ -352,7 +354,9 @@ int dense_layer(const b200taco_handle* h, const float* X, int ldx, const float* 
     if (int e = conv1d_channels_last(X, ldx, W, scale, shift, residual, ldres, Y, ldy, n_rows, seg_len, c_in, c_out, taps, act,
                                      stream))
         return e;
-    // CUDA-core path: the vocoder layout is a separate pass over the result
+    // CUDA-core path: tail zeroing and the vocoder layout are separate passes over the result
+    if (cm.zero_tail && cm.lengths != nullptr)
+        if (int e = zero_tail_rows(Y, ldy, cm.lengths, n_rows / seg_len, seg_len, c_out, stream)) return e;
     if (cm.y != nullptr) return vocoder_layout(Y, ldy, cm.lengths, n_rows / seg_len, seg_len, c_out, cm.ld, cm.y, stream);
     return B200TACO_OK;
 }

@@ -72,12 +72,16 @@ int transpose_bct_to_btc(const float* in, float* out, int B, int C, int T, cudaS
 bool dense_tc_supported(int c_in, int c_out, int ldx, int ldy);
 size_t dense_tc_weight_floats(int taps, int c_in, int c_out);
 int pack_dense_tc(float* dst, const float* w_tap_ci_co, int taps, int c_in, int c_out, cudaStream_t stream);
-// optional second copy of a layer's result, channel major (B, c_out, ld) and zero from lengths[b] on: the vocoder hand-off
-// layout (inference.py:71, train.py:71-79); y == nullptr: none
+// per-utterance options of a layer over B utterances of seg_len rows each.
+//  y != nullptr: second copy of the result, channel major (B, c_out, ld) and zero from lengths[b] on: the vocoder hand-off
+//  layout (inference.py:71, train.py:71-79).
+//  zero_tail: the result rows of utterance b from lengths[b] on are written as ZERO - a convolution stack then sees exactly
+//  what it sees when utterance b is run alone at its own length (zero padding behind the last frame), layer by layer.
 struct ChannelMajorOut {
     float* y = nullptr;
     const int32_t* lengths = nullptr;
     int ld = 0;
+    bool zero_tail = false;
 };
 int dense_layer(const b200taco_handle* h, const float* X, int ldx, const float* W, const float* Wtc, const float* scale,
                 const float* shift, const float* residual, int ldres, float* Y, int ldy, int n_rows, int seg_len, int c_in,
@@ -85,6 +89,7 @@ int dense_layer(const b200taco_handle* h, const float* X, int ldx, const float* 
 
 // data.cu : batch assembly (src/data_utils.py:45-84) and the vocoder hand-off layout as stand-alone passes
 int vocoder_layout(const float* mel, int ldm, const int32_t* lengths, int B, int S, int C, int S_out, float* out, cudaStream_t stream);
+int zero_tail_rows(float* Y, int ldy, const int32_t* lengths, int B, int S, int C, cudaStream_t stream);
 
 // bilstm.cu
 int bilstm_recurrence(const b200taco_handle* h, const float* xproj, float* memory, int B, int T,

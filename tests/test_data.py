@@ -114,10 +114,17 @@ def test_vocoder_handoff_matches_reference_golden():
     for path in ("auto", "simt"):
         m.dense_path = path
         eng = m._get_engine()
-        post = eng.postnet(coarse)
-        post2, voc = eng.postnet_for_vocoder(coarse, lens, frames=45)
+        from b200taco.engine import zero_beyond_lengths_
+        zc = zero_beyond_lengths_(coarse.clone(), lens)
+        post = eng.postnet(zc, lens)                      # every layer zero behind a row's own length
+        post2, voc = eng.postnet_for_vocoder(zc, lens, frames=45)
         assert torch.equal(post, post2)
         assert torch.equal(voc.cpu(), DO.vocoder_layout(post.cpu(), lens.tolist()))
+        for b, n in enumerate(lens.tolist()):             # = the solo run of row b at its own length
+            solo = eng.postnet(zc[b:b + 1, :n].contiguous())
+            assert util.maxdiff(post[b, :n].cpu(), solo[0].cpu()) <= 1e-6 and not post[b, n:].any()
+        _, voc_all = eng.postnet_for_vocoder(coarse, None, frames=45)          # no lengths: plain transpose of the plain postnet
+        assert torch.equal(voc_all.cpu(), DO.vocoder_layout(eng.postnet(coarse).cpu()))
 
 
 @pytest.mark.gpu

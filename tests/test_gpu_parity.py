@@ -422,13 +422,41 @@ def test_stream_infer_c2_vs_oracle():
         want = O.per_utterance_lengths(rgate).tolist()                                         # train.py:71-79 with the steps > 1 guard
         assert L == want, [(a, b) for a, b in zip(L, want) if a != b]
         assert S == max(L) and min(L) >= 200 and max(L) - min(L) >= 100       # a real spread of stop frames
-        from b200taco.engine import zero_beyond_lengths_
-        zc = zero_beyond_lengths_(rcoarse.clone(), torch.tensor(L))
-        with torch.no_grad():
-            rpost_solo = zc + O.postnet(sd, zc.transpose(1, 2)).transpose(1, 2)
         for b, n in enumerate(L):
+            with torch.no_grad():                            # the utterance's solo postnet: its own frames, zero padding behind
+                solo = rcoarse[b:b + 1, :n]
+                rpost_b = (solo + O.postnet(sd, solo.transpose(1, 2)).transpose(1, 2))[0]
             assert util.maxdiff(coarse[b, :n].cpu(), rcoarse[b, :n]) <= TOL_MEL
             assert util.maxdiff(gate[b, :n].cpu(), rgate[b, :n]) <= TOL_MEL
             assert util.maxdiff(align[:n, b].cpu(), ralign[:n, b]) <= TOL_ALIGN
-            assert util.maxdiff(post[b, :n].cpu(), rpost_solo[b, :n]) <= 5 * TOL_MEL
+            assert util.maxdiff(post[b, :n].cpu(), rpost_b) <= 5 * TOL_MEL
             assert not coarse[b, n:].any() and not gate[b, n:].any()
+
+
+@pytest.mark.parametrize("rows,n_utts,cap", [(8, 37, 300), (32, 70, 300), (8, 19, 40)])
+def test_ragged_continuous_batching_matches_solo_runs(rows, n_utts, cap):
+    """Utterances of DIFFERENT text lengths in one persistent launch (Tacotron2.inference_corpus, BASELINE config 4): every
+    utterance must decode as it does alone at its exact length - decoded length exact, frames / gate / alignments within the
+    usual tolerances (the attention slices of a padded launch partition the positions differently, so not bit for bit).
+    Several launches (length ratio), launches filled up to a multiple of the rows, cap hits (two of the utterances never fire
+    their gate; the cap of 300 frames keeps the comparison of two float32 recurrences inside the horizon the tolerances are
+    stated for)."""
+    sd = util.weights("planted", True, ctx_center=O.encoder(util.weights("stress", True), synth.phoneme_ids(2, 30, seed=50)).mean((0, 1)))
+    m = gpu_model(sd)
+    g = torch.Generator().manual_seed(rows + n_utts)
+    lens = torch.randint(12, 48, (n_utts,), generator=g).tolist()
+    utts = [synth.phoneme_ids(1, L, seed=300 + i)[0] for i, L in enumerate(lens)]
+    got = {i: (post, coarse, gate, al) for i, post, coarse, gate, al in m.inference_corpus(utts, max_len_cap=cap, rows=rows)}
+    assert sorted(got) == list(range(n_utts))
+    spread = set()
+    for i, u in enumerate(utts):
+        post, coarse, gate, aligns, lengths = m.inference_per_utterance(u[None].cuda(), max_len_cap=cap)
+        n = int(lengths[0])
+        spread.add(n)
+        gp, gc, gg, ga = got[i]
+        assert gc.shape == (n, 80) and ga.shape == (n, lens[i]), (i, gc.shape, n)
+        # two CUDA paths, each within TOL of the oracle: 2 x TOL between them (the planted counter integrates over up to 1000 frames)
+        assert util.maxdiff(gc.cpu(), coarse[0, :n].cpu()) <= TOL_MEL and util.maxdiff(gg.cpu(), gate[0, :n].cpu()) <= 2 * TOL_MEL
+        assert util.maxdiff(ga.cpu(), torch.stack(aligns)[:n, 0].cpu()) <= 2 * TOL_ALIGN
+        assert util.maxdiff(gp.cpu(), post[0, :n].cpu()) <= 5 * TOL_MEL
+    assert cap < 100 or len(spread) > 3
