@@ -11,7 +11,8 @@ own decoded lengths.
 
   value         frames/s with the phoneme ids already resident in HBM (device timed, CUDA events); the K
                 batches go through the public corpus path (Tacotron2.inference_batches(continuous=True) ->
-                Engine.stream_infer): ONE persistent decoder launch keeps 32 rows live and refills a row from
+                Engine.stream_infer): ONE persistent decoder launch keeps 64 rows live (two 32-utterance batches side by
+                side; BENCH_LIVE_ROWS=32 for one) and refills a row from
                 the following batches as soon as its utterance stops (continuous batching; every utterance
                 is bit-identical to its batch-by-batch decode, tests/test_gpu_parity.py)
   batch_by_batch  the same K batches with one decoder launch per batch (rows idle behind early stops),
@@ -25,6 +26,12 @@ own decoded lengths.
   cpu_baseline  the CPU oracle port of the reference (torch CPU ops, all host threads) on a
                 bounded sample of the same workload, rank 0, N=1 only
   b1            BASELINE config 3: B=1, T=200 decoder step latency in microseconds
+  c4            BASELINE config 4 (every N): 8192 synthetic utterances, T ~ U{50..250}, sharded over the ranks (strong scaling,
+                no data-path collective), ragged continuous batching (Tacotron2.inference_corpus, 64 live rows)
+  c5            BASELINE config 5 (every N): teacher-forced training step fwd + loss + bwd + clip + Adam, B=64 / GPU, 800-frame
+                mels, T=150, gradients all-reduced by DistributedDataParallel over NCCL (weak scaling); ms/step, TFLOP/s against
+                the measured sustained bf16 peak, the all-reduce time left exposed, and at N=1 the reference's CPU step
+--workload c4 | c5 makes that leg the JSON line's headline (metric / value / unit); --skip-extra drops the b1 / c4 / c5 legs.
 
 --impl reference times the reference's own CPU implementation of the path: the unmodified reference model staged in
 oracle/_ref by oracle/make_ref.py (the oracle port only if that was never staged), same ids / weights / cap.
@@ -50,11 +57,22 @@ import torch  # noqa: E402
 METRIC = "mel frames/sec (batch 32)"
 UNIT = "frames/s"
 B, T, CAP = 32, 150, 1000
+LIVE_ROWS = int(os.environ.get("BENCH_LIVE_ROWS", "64"))      # decoder rows one continuous-batching launch keeps busy
 PLANT = dict(rate=8e-4, jitter=6e-3)                 # stops in ~[300, 900] frames (synth.plant_stop_counter_)
 WORKLOAD = "C2: free-running inference, B=32 x T=150 phonemes, cap 1000 frames, per-utterance stop-gate early exit"
 # algorithmic bytes per decoder step, bf16 LSTM weights + fp32 activations
 BYTES_PER_STEP_C2 = 36_379_942 + B * T * (128 + 512) * 4 + B * T * 16 + B * 37_508
+
+
+def bytes_per_step(rows):
+    """SURVEY.md 8(d) for `rows` utterances decoding side by side: the weights once, the activations per utterance."""
+    return 36_379_942 + rows * T * (128 + 512) * 4 + rows * T * 16 + rows * 37_508
 BYTES_PER_STEP_C3 = 36_379_942 + 1 * 200 * (128 + 512) * 4 + 200 * 16 + 37_508
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE continuous-batching launch, ncu --set full (profiles/r2_decoder_kernels_ncu_full.md)
+NCU_TRAFFIC = {32: 102_501_120}
+NCU_TRAFFIC_UNIT = {32: "bytes per launch (ncu, production cluster kernel, launch of 96 utterances / 2002 decode steps)"}
 
 
 def _peaks():
@@ -170,7 +188,7 @@ def run_b200(args, rank, world, local_rank):
         feed = [ids_host if host else ids_dev] * n
         with contextlib.redirect_stdout(io.StringIO()):
             if continuous:
-                it = eng.stream_infer(feed, CAP, 0.5, to_host=host, pre_hook=flush_l2, timings=timings)
+                it = eng.stream_infer(feed, CAP, 0.5, to_host=host, pre_hook=flush_l2, timings=timings, live_rows=LIVE_ROWS)
             else:
                 it = eng.pipeline_infer(feed, CAP, 0.5, STOP_PER_UTTERANCE, to_host=host, pre_hook=flush_l2, timings=timings)
             for res in it:
@@ -244,7 +262,8 @@ def run_b200(args, rank, world, local_rank):
     out = None
     if rank == 0:
         hbm, hbm_src = _peaks()
-        achieved = BYTES_PER_STEP_C2 * dec_steps / (dec_ms * 1e-3) / 1e9
+        live = B * max(m for m in range(max(1, LIVE_ROWS // B), 0, -1) if args.steps % m == 0)   # Engine.stream_infer's choice
+        achieved = bytes_per_step(live) * dec_steps / (dec_ms * 1e-3) / 1e9
         l2_gbps = eng.measure_l2_read_gbps(36 << 20, 40)
         out = {
             "metric": METRIC, "value": frames / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -256,38 +275,220 @@ def run_b200(args, rank, world, local_rank):
                        "warmup_batches": max(args.warmup, args.steps),
                        "l2": "flushed before every decoder launch (256 MiB device memset on the decoder stream); the K batches' "
                              "encoder memory streams through the launch (123 MB at K=10)",
-                       "pipeline": "continuous batching: the K batches' utterances stream through the 32 rows of ONE persistent "
-                                   "decoder launch, a row is refilled from the next batch when its utterance stops; "
-                                   "encoders before, postnets after the launch",
+                       "pipeline": f"continuous batching: the K batches' utterances stream through the {live} rows of ONE persistent "
+                                   f"decoder launch ({live // B} batch(es) of 32 side by side), a row is refilled from the next "
+                                   "batch when its utterance stops; encoders before, postnets after the launch",
+                       "live_rows": live,
                        "sharding": f"dp{world}: one batch per rank per step, same synthetic batch on every rank, no collective"},
             "e2e": {"value": e2e_frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": ids_host.numel() * 8,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                    "returns": "mel_postnet (B,S,80) + per-utterance lengths per batch, pinned host memory; mel_coarse, gate logits and "
+                               "alignments of the reference's 4-tuple stay on the device (yielded as device tensors)"},
             "gpu_launches": int(launches),
             "batch_by_batch": {"value": bb_frames / (bb_ms * 1e-3), "unit": UNIT, "ms_per_step": bb_ms / args.steps,
                                "us_per_decode_step": bb_dec_ms * 1e3 / bb_steps, "decode_steps": bb_steps,
                                "what": "one persistent decoder launch per batch (rows idle behind early stops), rank 0"},
             "stages_ms": stages_ms,
             "clocks": clocks,
-            "roofline": {"kernel": "decoder_tc_kernel<32> (persistent, one cooperative cluster launch for the K batches)", "bound": "hbm",
+            "roofline": {"kernel": f"decoder_tc_kernel<{live}> (persistent, one cooperative cluster launch for the K batches)", "bound": "hbm",
                          "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one continuous-batching launch (K=3 batches = 96
                          # utterances, 2002 decode steps), ncu --set full, profiles/r1_v15_stream_decoder_ncu_full.md: 66.9 KB
                          # of HBM traffic per decode step against 49.9 MB algorithmic - the working set is L2 resident
-                         "traffic": 133_841_152, "traffic_unit": "bytes per launch (ncu, launch of 96 utterances / 2002 decode steps)",
-                         "peak_source": hbm_src, "bytes_per_decode_step": BYTES_PER_STEP_C2,
+                         "traffic": NCU_TRAFFIC.get(live), "traffic_unit": NCU_TRAFFIC_UNIT.get(live),
+                         "peak_source": hbm_src, "bytes_per_decode_step": bytes_per_step(live),
                          "decode_steps_per_launch": dec_steps / max(1, len(dec_events)), "us_per_decode_step": dec_ms * 1e3 / dec_steps,
-                         "row_occupancy": (frames / world + args.steps * B) / (dec_steps * B),
+                         "row_occupancy": (frames / world + args.steps * B) / (dec_steps * live),
                          "kernel_share_of_step": dec_ms / ms,
                          "l2_read_peak_gbs_measured_live": l2_gbps, "frac_of_l2_read_peak": achieved / l2_gbps,
                          "note": "working set per decode step is L2 resident; HBM peak is the schema's denominator"},
         }
         if world == 1:
-            out["b1"] = bench_b1(model, eng, synth, dev, l2_gbps, hbm)
+            if not args.skip_extra:
+                out["b1"] = bench_b1(model, eng, synth, dev, l2_gbps, hbm)
             out["cpu_baseline"] = cpu_baseline(synth, steps=3)
+    if not args.skip_extra or args.workload != "c2":
+        # the other two multi-GPU configurations of BASELINE.json, driver visible: every rank takes part
+        c4 = c5 = None
+        if args.workload in ("c2", "c4"):
+            c4 = bench_c4(model, synth, dev, rank, world, dist)
+        del eng, model, flush
+        torch.cuda.empty_cache()
+        if args.workload in ("c2", "c5"):
+            c5 = bench_c5(synth, dev, rank, world, dist, local_rank)
+        if rank == 0:
+            if c4 is not None:
+                out["c4"] = c4
+            if c5 is not None:
+                out["c5"] = c5
+                if world == 1:
+                    cb = cpu_baseline_c5(synth)
+                    if cb is not None:
+                        out["c5"]["cpu_baseline"] = cb
+            head = {"c4": c4, "c5": c5}.get(args.workload)
+            if head is not None:                       # --workload c4 | c5: that leg is the headline of the line
+                out["c2"] = {k: out[k] for k in ("metric", "value", "unit", "ms_per_step", "scaling")}
+                out.update(metric=head["metric"], value=head["value"], unit=head["unit"], scaling=head["scaling"],
+                           ms_per_step=head.get("ms_per_step", head.get("seconds", 0.0) * 1e3))
+                out["config"] = dict(out["config"], workload=head["workload"])
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return out
+
+
+C4_UTTS, C4_ROWS = 8192, 64
+C5_B, C5_S, C5_T = 64, 800, 150
+C5_TFLOP = 7.55                     # fwd + bwd of one C5 step
+
+
+def bench_c4(model, synth, dev, rank, world, dist, n_utts=C4_UTTS, rows=C4_ROWS):
+    """BASELINE config 4: the corpus is sorted by text length and dealt round-robin to the ranks (every rank sees the same
+    length distribution: strong scaling without a collective); each rank streams its share through persistent launches of 64
+    live rows, utterances of different lengths side by side (ragged continuous batching), at least ~8 refills per row and
+    launch.  Timed on the device, max over ranks; frames = sum of the decoded lengths of all utterances."""
+    import random
+    rng = random.Random(0)
+    lens = [rng.randint(50, 250) for _ in range(n_utts)]
+    order = sorted(range(n_utts), key=lambda i: (lens[i], i))
+    mine = order[rank::world]
+    corpus = {i: synth.phoneme_ids(1, lens[i], seed=i)[0] for i in mine}
+    n_launch = max(1, min(4, len(mine) // (8 * rows)))
+    per_launch = (len(mine) + n_launch - 1) // n_launch
+
+    def run(idx):
+        frames = 0
+        with contextlib.redirect_stdout(io.StringIO()):
+            for _, _, coarse, _, _ in model.inference_corpus([corpus[i] for i in idx], rows=rows, launch_utterances=per_launch,
+                                                             length_ratio=1e9):
+                frames += coarse.shape[0]
+        return frames
+
+    run(mine[:: max(1, len(mine) // (2 * rows))][:2 * rows])          # warm-up: allocator, weight packing, both ends of the lengths
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    frames = run(mine)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    steps = model._get_engine().last_stream_steps
+    agg = torch.tensor([e0.elapsed_time(e1), float(frames), float(steps)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        mx = agg.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = agg.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        agg = torch.stack([mx[0], sm[1], sm[2]])
+    ms, frames, steps = float(agg[0]), float(agg[1]), float(agg[2])
+    return {"workload": f"C4: {n_utts} utterances, T~U{{50..250}}, length-sorted round-robin sharding over {world} rank(s), ragged "
+                        f"continuous batching with {rows} live rows, {n_launch} launch(es) per rank",
+            "metric": "mel frames/sec (sharded corpus)", "value": frames / (ms * 1e-3), "unit": UNIT, "scaling": "strong",
+            "seconds": ms * 1e-3, "frames": int(frames), "utterances": n_utts, "mean_frames_per_utterance": frames / n_utts,
+            "row_occupancy": (frames + n_utts) / (steps * rows) if steps else None}
+
+
+def bench_c5(synth, dev, rank, world, dist, local_rank, steps=2):
+    """BASELINE config 5: one training step = Tacotron2.forward (train mode) + b200taco.loss.Tacotron2Loss (fused, no host sync)
+    + backward (hand-written, csrc/train_*.cu) + gradient clipping + Adam, B=64 rows per GPU; under torchrun the gradients are
+    all-reduced by DistributedDataParallel (NCCL over NVLink).  The all-reduce time left exposed = step time with DDP minus the
+    same step inside ``no_sync()`` (no communication)."""
+    from b200taco.loss import Tacotron2Loss, gate_targets
+    from b200taco.model import Tacotron2
+    torch.manual_seed(synth.WEIGHT_SEED)
+    model = Tacotron2()
+    model._projection_bias_initialized = True
+    model = model.to(dev).train()
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank]) if world > 1 else model
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    crit = Tacotron2Loss()
+    Bc, S, Tn = C5_B, C5_S, C5_T
+    ids = synth.phoneme_ids(Bc, Tn, seed=1000 + rank).to(dev)
+    g = torch.Generator().manual_seed(100 + rank)
+    mel = (torch.randn(Bc, 80, S, generator=g) * 2 - 5).to(dev)
+    tl = torch.full((Bc,), Tn, dtype=torch.long, device=dev)
+    ml = torch.full((Bc,), S, dtype=torch.long, device=dev)
+    gt = gate_targets(ml, S)
+
+    def step(sync=True):
+        ctx = contextlib.nullcontext() if (sync or world == 1) else net.no_sync()
+        with ctx:
+            out = net(ids, mel, tl)
+            total, _, _, _ = crit(out, (mel, gt, ml), text_lengths=tl)
+            opt.zero_grad(set_to_none=True)
+            total.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        return total
+
+    def timed(n, sync=True):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            loss = step(sync)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1) / n], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t), float(loss)
+
+    step()                                                           # warm-up (allocator, DDP buckets)
+    ms, loss = timed(steps)
+    out = {"workload": f"C5: training step fwd + Tacotron2Loss + bwd + clip + Adam, B={Bc}/GPU, T={Tn}, {S}-frame mels"
+                       + (", DistributedDataParallel (NCCL all-reduce of 112.6 MB fp32 gradients)" if world > 1 else ""),
+           "metric": "training mel frames/sec", "value": world * Bc * S / (ms * 1e-3), "unit": UNIT, "scaling": "weak",
+           "ms_per_step": ms, "tflops_per_gpu": C5_TFLOP / (ms * 1e-3), "loss": loss}
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            peak = float(json.load(f).get("bf16_tflops_sustained", 0.0))
+        if peak > 0:
+            out["frac_of_sustained_bf16_peak"] = out["tflops_per_gpu"] / peak
+            out["peak_tflops_sustained_measured"] = peak
+    if world > 1:
+        ms_nosync, _ = timed(steps, sync=False)
+        out["ms_per_step_without_allreduce"] = ms_nosync
+        out["exposed_allreduce_ms"] = ms - ms_nosync
+    return out
+
+
+def cpu_baseline_c5(synth, Bc=16, S=100, Tn=C5_T):
+    """The reference's own training step on the host cores (oracle/_ref = the unmodified reference model, train mode, L1 + BCE
+    loss, backward, Adam) on a bounded sample, scaled per frame (B=16, S=100)."""
+    from oracle.make_ref import load_reference
+    ref = load_reference()
+    if ref is None:
+        return None
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(synth.WEIGHT_SEED)
+    model = ref.Tacotron2()
+    model._projection_bias_initialized = True
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    ids = synth.phoneme_ids(Bc, Tn, seed=1)
+    mel = torch.randn(Bc, 80, S, generator=torch.Generator().manual_seed(2)) * 2 - 5
+    tl = torch.full((Bc,), Tn, dtype=torch.long)
+
+    def step():
+        post, coarse, gate, _ = model(ids, mel, tl)
+        tgt = mel.transpose(1, 2)
+        loss = (post - tgt).abs().mean() + (coarse - tgt).abs().mean() + \
+            torch.nn.functional.binary_cross_entropy_with_logits(gate, torch.zeros_like(gate))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+    with contextlib.redirect_stdout(io.StringIO()):
+        step()
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+    return {"value": Bc * S / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+            "sample": f"one training step (fwd + L1/BCE loss + bwd + clip + Adam) of the unmodified reference at B={Bc}, T={Tn}, {S} frames",
+            "seconds": dt}
 
 
 def bench_b1(model, eng, synth, dev, l2_gbps, hbm):
@@ -377,6 +578,16 @@ def run_reference(args, rank, world):
         return None
     from b200taco import synth
     t0 = time.perf_counter()
+    if args.workload == "c5":
+        r = cpu_baseline_c5(synth)
+        ms = (time.perf_counter() - t0) * 1e3
+        return {"impl": "reference", "metric": "training mel frames/sec", "value": r["value"], "unit": UNIT, "n_gpus": world,
+                "steps": 1, "warmup": 1, "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "C5 (CPU sample): " + r["sample"], "device": "host CPU", "arm": r["kind"]},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "wall_ms": ms}
     r = cpu_baseline(synth, max(1, args.steps))
     ms = (time.perf_counter() - t0) * 1e3
     return {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world,
@@ -397,6 +608,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"])
+    ap.add_argument("--skip-extra", action="store_true", help="C2 only: no b1 / c4 / c5 legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -305,7 +305,7 @@ class Tacotron2(nn.Module):
 
     @torch.no_grad()
     def inference_batches(self, batches, max_len_cap=None, gate_threshold=None, per_utterance=True, to_host=False,
-                          continuous=False):
+                          continuous=False, live_rows=64):
         """Corpus synthesis: free-running inference over an iterable of (B,T) id batches (device or pinned host
         tensors), with the encoder / decoder / postnet of consecutive batches overlapped on separate CUDA streams
         (``Engine.pipeline_infer``).  Yields per batch ``(mel_postnet, mel_coarse, gate_logits, alignments (S,B,T),
@@ -325,7 +325,7 @@ class Tacotron2(nn.Module):
         if continuous:
             if not per_utterance:
                 raise ValueError("continuous batching decodes under the per-utterance stop rule")
-            yield from eng.stream_infer(batches, cap, thr, to_host)
+            yield from eng.stream_infer(batches, cap, thr, to_host, live_rows=live_rows)
             return
         yield from eng.pipeline_infer(batches, cap, thr, STOP_PER_UTTERANCE if per_utterance else STOP_BATCH_WIDE, to_host)
 
