@@ -463,7 +463,7 @@ class Engine:
             done_ev.synchronize()
             self.last_stream_steps += int(len_h[-1])
 
-    def stream_infer(self, batches, max_steps: int, gate_threshold: float, to_host: bool = False, group_batches: int = 16,
+    def stream_infer(self, batches, max_steps: int, gate_threshold: float, to_host: bool = False, group_batches: int = 32,
                      pre_hook=None, timings=None, live_rows=None):
         """Corpus synthesis with continuous batching: like ``pipeline_infer`` under the per-utterance stop rule, but the
         utterances of up to ``group_batches`` consecutive batches (same shape (rows, T)) share ONE persistent decoder launch
@@ -492,7 +492,12 @@ class Engine:
         if any(tuple(b.shape) != (rows, T) for b in batches) or not self.stream_supported(rows):
             raise B200TacoError("stream_infer needs batches of one shape (rows, T) with 4 <= rows <= 64 and the default "
                                 "(bf16, tensor-core) decoder; use pipeline_infer otherwise")
-        groups = [batches[i:i + group_batches] for i in range(0, len(batches), group_batches)]
+        # launches of (nearly) equal size, an even number of batches each where possible (two batches decode side by side):
+        # the drain at the end of a launch costs the same whatever its length, so neither a short last launch nor an odd one
+        n_groups = (len(batches) + group_batches - 1) // group_batches
+        per = (len(batches) + n_groups - 1) // n_groups
+        per += per % 2 if per < len(batches) else 0
+        groups = [batches[i:i + per] for i in range(0, len(batches), per)]
         self.last_stream_steps = 0                    # decode steps of all launches of this call
 
         def prep(group):

@@ -305,9 +305,19 @@ int train_colsum(float* dst, const float* src, int n_rows, int C, cudaStream_t s
     return B200TACO_OK;
 }
 
+bool dense_wgrad_tc_supported(int n_rows, int c_in, int c_out);
+int dense_wgrad_tc(const float* X, int ldx, const float* dY, int ldy, float* dW, int n_rows, int seg_len, int c_in, int c_out, int taps,
+                   int num_sms, cudaStream_t st);
+
 // dW[tap][ci][co] = sum_n X[n + tap - pad][ci] * dY[n][co]  (overwrites dW)
 int dense_wgrad(const float* X, int ldx, const float* dY, int ldy, float* dW, int n_rows, int seg_len, int c_in, int c_out,
                 int taps, cudaStream_t st) {
+    if (dense_wgrad_tc_supported(n_rows, c_in, c_out)) {     // tensor cores (3xTF32), train_wgrad_tc.cu
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        return dense_wgrad_tc(X, ldx, dY, ldy, dW, n_rows, seg_len, c_in, c_out, taps, sms, st);
+    }
     static const bool wide = [] { const char* e = getenv("TACO_WGRAD128"); return !(e && e[0] == '0'); }();
     if (wide && c_in >= 128 && c_out >= 128) {
         const int tiles2 = ((c_in + 127) / 128) * ((c_out + 127) / 128) * taps;
@@ -388,14 +398,8 @@ int convbn_train_bwd(const float* dY, const float* X, int ldx, const float* Wp, 
     colreduce_kernel<3><<<grid, 256, 0, st>>>(dz, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1.f, 0, n_rows,
                                               c_out, db, nullptr);
     TACO_LAUNCHED();
-    // weight gradient: rows split so that ~4 waves of CTAs are in flight
-    int chunks = 1;
-    const int tiles = ((c_in + 63) / 64) * ((c_out + 63) / 64) * taps;
-    while (tiles * chunks < 592 && n_rows / (chunks * 2) >= 256) chunks *= 2;
-    const int rows_per = ((n_rows + chunks - 1) / chunks + 15) / 16 * 16;
-    dense_wgrad_kernel<<<dim3((c_in + 63) / 64, (c_out + 63) / 64, taps * chunks), 256, 0, st>>>(
-        X, ldx, dz, c_out, dWp, n_rows, seg_len, c_in, c_out, taps, rows_per);
-    TACO_LAUNCHED();
+    // weight gradient (tensor cores where the channel counts allow, train_wgrad_tc.cu)
+    if (int e = dense_wgrad(X, ldx, dz, c_out, dWp, n_rows, seg_len, c_in, c_out, taps, st)) return e;
     if (dX != nullptr) {
         flip_transpose_kernel<<<blocks_for((size_t)taps * c_in * c_out), 256, 0, st>>>(wflip, Wp, taps, c_in, c_out);
         TACO_LAUNCHED();

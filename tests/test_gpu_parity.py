@@ -9,6 +9,8 @@ exp/tanh implementations differ from the reference's CPU kernels):
 "bf16" = decoder LSTM matrices stored as bf16 in the packed cache; the reference side then
 uses the same bf16-representable values, so the tolerance is unchanged.
 """
+import os
+
 import pytest
 import torch
 
@@ -33,6 +35,8 @@ def gpu_model(sd, weight_dtype="bf16"):
     m.load_state_dict(sd)
     m._projection_bias_initialized = True
     m.lstm_weight_dtype = weight_dtype
+    if os.environ.get("TACO_TEST_DENSE_PATH"):           # experiment knob: run the whole file on another dense-layer path
+        m.dense_path = os.environ["TACO_TEST_DENSE_PATH"]
     return m.to("cuda:0")
 
 
