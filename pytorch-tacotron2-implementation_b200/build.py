@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libb200taco.so")
-SOURCES = ["api.cu", "pack.cu", "dense.cu", "dense_tc.cu", "bilstm.cu", "decoder.cu", "decoder_res.cu", "measure.cu", "umma_test.cu", "train_dense.cu", "train_wgrad_tc.cu", "train_lstm.cu", "train_decoder.cu", "train_api.cu", "loss.cu", "data.cu"]
+SOURCES = ["api.cu", "pack.cu", "dense.cu", "dense_tc.cu", "bilstm.cu", "decoder.cu", "decoder_res.cu", "measure.cu", "umma_test.cu", "train_dense.cu", "train_wgrad_tc.cu", "train_skinny_tc.cu", "train_lstm.cu", "train_decoder.cu", "train_api.cu", "loss.cu", "data.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

@@ -48,6 +48,11 @@ int skinny_gemm_multi(const float* X, int ldx, const float* W, int ldw, int B, i
                       const int* n_ends, const bool* acc, cudaStream_t st);
 int ctx_dmemory(const float* w, const float* dctx_all, float* dmemory, int S, int B, int T, cudaStream_t st);
 constexpr int ATTN_PACC_F = ATT_DIM * LOC_F + LOC_F * 2 * LOC_K + ATT_DIM + 64;
+size_t skinny_tc_packed_bytes(int K, int N);
+bool skinny_tc_supported(int B, int K, int N, int nseg, const int* n_ends);
+int pack_skinny_tc(void* dst, const float* W, int ldw, int K, int N, cudaStream_t st);
+int skinny_gemm_multi_tc(const float* X, int ldx, const void* Wp, int B, int K, int nseg, float* const* outs, const int* ldos,
+                         const int* n_ends, const bool* acc, cudaStream_t st);
 int skinny_gemm(const float* X, int ldx, const float* W, int ldw, float* out, int ldo, int B, int K, int N, bool accumulate,
                 cudaStream_t st);
 int transpose_block(float* dst, int ldd, const float* src, int lds, int R, int C, cudaStream_t st);
@@ -296,7 +301,8 @@ B200TACO_API int32_t b200taco_encoder_train_bwd(b200taco_handle* h, const b200ta
 // backward + data gradients.  Weight gradients are deferred to a few large reductions over all steps.
 namespace {
 struct DecScratch {
-    size_t dout, wpg, wqT, dzd, dza, dpq, dp, d_ah, d_dh, d_ctx, dca, dcd, tmp, tmp2, pq, P, gsum, cum, dpm, attn, dw, dvs, wcat_d, wcat_a, dctx_all, total;
+    size_t dout, wpg, wqT, dzd, dza, dpq, dp, d_ah, d_dh, d_ctx, dca, dcd, tmp, tmp2, pq, P, gsum, cum, dpm, attn, dw, dvs, wcat_d, wcat_a, dctx_all,
+        wpk_d, wpk_a, total;
 };
 DecScratch dec_scratch(int B, int T, int S) {
     DecScratch d{};
@@ -328,6 +334,8 @@ DecScratch dec_scratch(int B, int T, int S) {
     d.wcat_d = take((size_t)4 * RNN * (2 * RNN + EMB));        // [W_ih | W_hh] of the decoder LSTM, [4096][2560]
     d.wcat_a = take((size_t)4 * RNN * (PRENET + EMB + RNN));   // [W_ih | W_hh] of the attention LSTM, [4096][1792]
     d.dctx_all = take(n * EMB);                   // d ctx_t of every step: the memory gradient is one contraction after the walk
+    d.wpk_d = take((size_t)4 * RNN * (2 * RNN + EMB) / 2);       // the same two matrices as bf16 UMMA tiles (train_skinny_tc.cu)
+    d.wpk_a = take((size_t)4 * RNN * (PRENET + EMB + RNN) / 2);
     d.total = off;
     return d;
 }
@@ -380,6 +388,15 @@ B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200ta
     TACO_CUDA(cudaMemcpy2DAsync(wcat_d + RNN + EMB, ND * f4, w->dec_lstm_w_hh, RNN * f4, RNN * f4, 4 * RNN, cudaMemcpyDeviceToDevice, st));
     TACO_CUDA(cudaMemcpy2DAsync(wcat_a, NA * f4, w->attn_lstm_w_ih, (PRENET + EMB) * f4, (PRENET + EMB) * f4, 4 * RNN, cudaMemcpyDeviceToDevice, st));
     TACO_CUDA(cudaMemcpy2DAsync(wcat_a + PRENET + EMB, NA * f4, w->attn_lstm_w_hh, RNN * f4, RNN * f4, 4 * RNN, cudaMemcpyDeviceToDevice, st));
+    // mixed precision (the forward multiplied bf16-rounded LSTM matrices): the per-step data gradients run on the tensor cores with
+    // the same bf16 values; an fp32-weight handle (train_lstm_weight_dtype = "fp32") keeps the fp32 CUDA-core contraction
+    const int ends_d[3] = {RNN, RNN + EMB, ND}, ends_a[3] = {PRENET, PRENET + EMB, NA};
+    const bool tc_skinny = h->weight_dtype == 0 && skinny_tc_supported(B, 4 * RNN, ND, 3, ends_d) && skinny_tc_supported(B, 4 * RNN, NA, 3, ends_a);
+    void *wpk_d = sc + X.wpk_d, *wpk_a = sc + X.wpk_a;
+    if (tc_skinny) {
+        TT(pack_skinny_tc(wpk_d, wcat_d, ND, 4 * RNN, ND, st));
+        TT(pack_skinny_tc(wpk_a, wcat_a, NA, 4 * RNN, NA, st));
+    }
     TACO_CUDA(cudaMemsetAsync(d_ah, 0, (X.tmp - X.d_ah) * sizeof(float), st));  // d_ah, d_dh, d_ctx, dca, dcd
     TACO_CUDA(cudaMemsetAsync(dp, 0, (size_t)n * PRENET * sizeof(float), st));   // the per-step GEMMs accumulate onto zeros
     // processed queries (src/model.py:123) of all steps in one dense call instead of one skinny GEMM per step
@@ -412,7 +429,8 @@ B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200ta
             float* outs[3] = {d_ah, d_ctx, d_dh};
             const int ldos[3] = {RNN, EMB, RNN}, ends[3] = {RNN, RNN + EMB, ND};
             const bool acc[3] = {true, true, true};
-            TT(skinny_gemm_multi(dzd_t, 4 * RNN, wcat_d, ND, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
+            if (tc_skinny) TT(skinny_gemm_multi_tc(dzd_t, 4 * RNN, wpk_d, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
+            else TT(skinny_gemm_multi(dzd_t, 4 * RNN, wcat_d, ND, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
         }
         // attention (src/model.py:117-148)
         TT(attention_bwd(d_align + r * T, t > 0 ? d_align + (r - B) * T : nullptr, cum + r * T, pq + r * ATT_DIM, pm, d_memory, d_ctx,
@@ -428,7 +446,8 @@ B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200ta
             float* outs[3] = {dp + r * PRENET, d_ctx, d_ah};
             const int ldos[3] = {PRENET, EMB, RNN}, ends[3] = {PRENET, PRENET + EMB, NA};
             const bool acc[3] = {true, v2, true};
-            TT(skinny_gemm_multi(dza_t, 4 * RNN, wcat_a, NA, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
+            if (tc_skinny) TT(skinny_gemm_multi_tc(dza_t, 4 * RNN, wpk_a, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
+            else TT(skinny_gemm_multi(dza_t, 4 * RNN, wcat_a, NA, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
         }
     }
 
