@@ -71,8 +71,10 @@ BYTES_PER_STEP_C3 = 36_379_942 + 1 * 200 * (128 + 512) * 4 + 200 * 16 + 37_508
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE continuous-batching launch, ncu --set full (profiles/r2_decoder_kernels_ncu_full.md)
-NCU_TRAFFIC = {32: 102_501_120}
-NCU_TRAFFIC_UNIT = {32: "bytes per launch (ncu, production cluster kernel, launch of 96 utterances / 2002 decode steps)"}
+NCU_TRAFFIC = {32: 102_501_120, 64: 1_463_833_400}
+NCU_TRAFFIC_UNIT = {32: "bytes per launch (ncu, production cluster kernel, launch of 96 utterances / 2002 decode steps)",
+                    64: "bytes per launch (ncu, production cluster kernel, launch of 128 utterances / 1475 decode steps = 0.99 MB of HBM "
+                        "traffic per decode step against 63.5 MB algorithmic: the working set is L2 resident)"}
 
 
 def _peaks():

@@ -17,7 +17,7 @@ import bench  # noqa: E402
 from b200taco import synth  # noqa: E402
 from b200taco.model import Tacotron2  # noqa: E402
 
-K, CAP = int(os.environ.get("K", 3)), int(os.environ.get("CAP", 1000))
+K, CAP, ROWS = int(os.environ.get("K", 3)), int(os.environ.get("CAP", 1000)), int(os.environ.get("ROWS", 32))
 dev = torch.device("cuda", 0)
 torch.manual_seed(synth.WEIGHT_SEED)
 m = Tacotron2().eval()
@@ -28,6 +28,6 @@ m.load_state_dict(bench.planted_state_dict(m, ids, synth))
 eng = m._get_engine()
 mem = torch.cat([eng.encoder(ids) for _ in range(K)])
 torch.cuda.synchronize()
-mel, gate, align, len_h = eng.decoder_infer_stream(mem, bench.B, CAP, 0.5)
+mel, gate, align, len_h = eng.decoder_infer_stream(mem, ROWS, CAP, 0.5)
 torch.cuda.synchronize()
 print("utterances", mem.shape[0], "frames", int(len_h[:-1].sum()), "decode steps", int(len_h[-1]))
