@@ -29,6 +29,7 @@ def build(force=False, verbose=False):
     os.makedirs(obj_dir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "b200taco.h"))
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "b200taco_debug.h"))
     objs, procs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)

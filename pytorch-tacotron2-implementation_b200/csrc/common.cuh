@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include "../../include/b200taco.h"
+#include "../../include/b200taco_debug.h"
 #include "dims.cuh"
 
 namespace b200taco {

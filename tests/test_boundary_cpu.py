@@ -26,8 +26,11 @@ def lib():
     return _cabi.lib()
 
 
-def declared_symbols():
-    src = open(HEADER).read()
+DEBUG_HEADER = os.path.join(ROOT, "include", "b200taco_debug.h")     # measurement / bring-up aids, outside the product ABI
+
+
+def declared_symbols(with_debug=True):
+    src = open(HEADER).read() + (open(DEBUG_HEADER).read() if with_debug else "")
     return sorted(set(re.findall(r"B200TACO_API\s+[\w\s\*]+?\b(b200taco_\w+)\s*\(", src)))
 
 
@@ -36,7 +39,9 @@ def test_header_symbols_all_exported_and_bound(lib):
     assert len(names) >= 14
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/b200taco.h but not exported"
-    assert sorted(_cabi.SIGNATURES) == names          # the ctypes table covers exactly the header
+    assert sorted(_cabi.SIGNATURES) == names          # the ctypes table covers exactly the two headers
+    product = declared_symbols(with_debug=False)      # the product ABI carries no measurement / debug entry points
+    assert not [n for n in product if "measure" in n or "debug" in n or "trace" in n or "profile" in n], product
     assert lib.b200taco_abi_version() == _cabi.ABI_VERSION
     assert lib.b200taco_max_batch() == 64 and lib.b200taco_max_text_len() >= 512
 
