@@ -345,15 +345,19 @@ C5_TFLOP = 7.55                     # fwd + bwd of one C5 step
 
 
 def bench_c4(model, synth, dev, rank, world, dist, n_utts=C4_UTTS, rows=C4_ROWS):
-    """BASELINE config 4: the corpus is sorted by text length and dealt round-robin to the ranks (every rank sees the same
-    length distribution: strong scaling without a collective); each rank streams its share through persistent launches of 64
+    """BASELINE config 4: the corpus is sorted by text length and its exact-length groups are dealt round-robin to the ranks
+    (every rank sees the same length distribution: strong scaling without a collective); each rank streams its share through persistent launches of 64
     live rows, utterances of different lengths side by side (ragged continuous batching), at least ~8 refills per row and
     launch.  Timed on the device, max over ranks; frames = sum of the decoded lengths of all utterances."""
     import random
     rng = random.Random(0)
     lens = [rng.randint(50, 250) for _ in range(n_utts)]
     order = sorted(range(n_utts), key=lambda i: (lens[i], i))
-    mine = order[rank::world]
+    # whole exact-length groups per rank, lengths dealt round-robin (rank r takes the lengths L = r mod N): every rank sees the
+    # same length distribution, and an utterance's encoder batch (all utterances of its length) is not split over the ranks -
+    # dealing single utterances round-robin left every rank with all 201 lengths, i.e. 201 small encoder launches per rank
+    # whatever N (37 % of the time at N=8)
+    mine = [i for i in order if lens[i] % world == rank]
     corpus = {i: synth.phoneme_ids(1, lens[i], seed=i)[0] for i in mine}
     n_launch = max(1, min(4, len(mine) // (8 * rows)))
     per_launch = (len(mine) + n_launch - 1) // n_launch
@@ -382,7 +386,7 @@ def bench_c4(model, synth, dev, rank, world, dist, n_utts=C4_UTTS, rows=C4_ROWS)
         sm = agg.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         agg = torch.stack([mx[0], sm[1], sm[2]])
     ms, frames, steps = float(agg[0]), float(agg[1]), float(agg[2])
-    return {"workload": f"C4: {n_utts} utterances, T~U{{50..250}}, length-sorted round-robin sharding over {world} rank(s), ragged "
+    return {"workload": f"C4: {n_utts} utterances, T~U{{50..250}}, exact-length groups dealt round-robin over {world} rank(s), ragged "
                         f"continuous batching with {rows} live rows, {n_launch} launch(es) per rank",
             "metric": "mel frames/sec (sharded corpus)", "value": frames / (ms * 1e-3), "unit": UNIT, "scaling": "strong",
             "seconds": ms * 1e-3, "frames": int(frames), "utterances": n_utts, "mean_frames_per_utterance": frames / n_utts,

@@ -354,6 +354,8 @@ class Engine:
                     zero_beyond_lengths_(coarse, lengths)     # every row as if it had been decoded alone (see there)
                 post = self.postnet(coarse, lengths if stop_mode == STOP_PER_UTTERANCE else None)
                 res = (post, coarse, gate[:, :S], align[:S], lengths, S)
+                for t_ in (post, coarse):                 # allocated on this side stream, consumed on the caller's stream
+                    t_.record_stream(cur)
                 if to_host:
                     post_h = torch.empty(post.shape, dtype=post.dtype, pin_memory=True)
                     len_h = torch.empty(lengths.shape, dtype=lengths.dtype, pin_memory=True)
@@ -561,6 +563,8 @@ class Engine:
                     lengths = len_h[lo:hi].to(dev, non_blocking=True)
                     post = self.postnet(coarse, lengths)
                     res = (post, coarse, gate[lo:hi, :S], align[lo // live, :S, lo % live:lo % live + rows], lengths, S)
+                    for t_ in (post, coarse, lengths):        # allocated on this side stream, consumed on the caller's stream
+                        t_.record_stream(cur)
                     if to_host:
                         post_h = torch.empty(post.shape, dtype=post.dtype, pin_memory=True)
                         post_h.copy_(post, non_blocking=True)

@@ -85,7 +85,8 @@ class PostnetTrainFn(torch.autograd.Function):
         ctx.eng, ctx.masks, ctx.scale, ctx.keys = eng, masks, scale, keys
         ctx.save_for_backward(coarse, saved, *[p.detach() for p in params])
         ctx.bn_stats = PostnetTrainFn._bn_stats(saved, B * S)
-        eng._post_bn_stats = ctx.bn_stats              # also readable when no graph is recorded (torch.no_grad)
+        # clones: the engine must not keep the multi-hundred-MB `saved` buffer alive after the backward
+        eng._post_bn_stats = [(m.clone(), v.clone()) for m, v in ctx.bn_stats]
         return post
 
     @staticmethod
@@ -164,7 +165,7 @@ class EncoderTrainFn(torch.autograd.Function):
             off += 2 * n * d
             ctx.bn_stats.append((saved[off:off + d], saved[off + d:off + 2 * d]))
             off += 3 * d
-        eng._enc_bn_stats = ctx.bn_stats
+        eng._enc_bn_stats = [(m.clone(), v.clone()) for m, v in ctx.bn_stats]
         return memory
 
     @staticmethod
