@@ -352,12 +352,11 @@ def bench_c4(model, synth, dev, rank, world, dist, n_utts=C4_UTTS, rows=C4_ROWS)
     import random
     rng = random.Random(0)
     lens = [rng.randint(50, 250) for _ in range(n_utts)]
-    order = sorted(range(n_utts), key=lambda i: (lens[i], i))
-    # whole exact-length groups per rank, lengths dealt round-robin (rank r takes the lengths L = r mod N): every rank sees the
-    # same length distribution, and an utterance's encoder batch (all utterances of its length) is not split over the ranks -
-    # dealing single utterances round-robin left every rank with all 201 lengths, i.e. 201 small encoder launches per rank
-    # whatever N (37 % of the time at N=8)
-    mine = [i for i in order if lens[i] % world == rank]
+    # whole exact-length groups per rank, lengths dealt round-robin (b200taco.shard.deal_length_groups): dealing single
+    # utterances round-robin left every rank with all 201 lengths, i.e. 201 small encoder launches per rank whatever N
+    # (37 % of the time at N=8)
+    from b200taco import shard
+    mine = shard.deal_length_groups(lens, world, rank)
     corpus = {i: synth.phoneme_ids(1, lens[i], seed=i)[0] for i in mine}
     n_launch = max(1, min(4, len(mine) // (8 * rows)))
     per_launch = (len(mine) + n_launch - 1) // n_launch

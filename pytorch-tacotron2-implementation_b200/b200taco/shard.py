@@ -144,3 +144,31 @@ def gather_lengths(local: Dict[int, int], n_utterances: int, device: Optional[to
         bad = (owners != 1).nonzero().flatten().tolist()[:8]
         raise RuntimeError(f"sharding error: utterances {bad} were decoded {owners[bad].tolist()} times")
     return t
+
+
+def deal_length_groups(text_lengths: Sequence[int], world_size: int, rank: int) -> List[int]:
+    """Sharding for the ragged continuous-batching path (``Tacotron2.inference_corpus``, bench.py's C4 leg): the utterance
+    indices of ``rank``, sorted by text length.  WHOLE exact-length groups go to one rank - an utterance is encoded at its own
+    length (F8), one encoder launch per length and rank, so splitting a length over the ranks would multiply the small
+    encoder launches.  The distinct lengths are walked in ascending blocks of ``world_size``; inside a block every rank
+    receives exactly one group, the largest group going to the rank with the fewest utterances so far: every rank spans the
+    whole length range (the same length distribution, hence the same attention cost per decode step) with utterance counts
+    within a few percent (the decode length of an utterance does not depend on its text length).  No communication: every
+    rank derives its share from the same lengths."""
+    if not 0 <= rank < world_size:
+        raise ValueError(f"rank {rank} outside [0, {world_size})")
+    groups: Dict[int, List[int]] = {}
+    for i, n in enumerate(text_lengths):
+        groups.setdefault(int(n), []).append(i)
+    distinct = sorted(groups)
+    load = [0] * world_size
+    mine: List[int] = []
+    for lo in range(0, len(distinct), world_size):
+        free = list(range(world_size))
+        for n in sorted(distinct[lo:lo + world_size], key=lambda n: (-len(groups[n]), n)):
+            r = min(free, key=lambda q: (load[q], q))
+            free.remove(r)
+            load[r] += len(groups[n])
+            if r == rank:
+                mine += groups[n]
+    return sorted(mine, key=lambda i: (text_lengths[i], i))

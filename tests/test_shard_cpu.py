@@ -99,3 +99,25 @@ def test_two_rank_gloo_run_and_gather():
 def test_gather_detects_double_decoding():
     with pytest.raises(RuntimeError):
         shard.gather_lengths({0: 5}, 2)                    # utterance 1 was never decoded
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_length_groups_are_dealt_whole_and_balanced(world):
+    """Sharding of the ragged continuous-batching path: every utterance on exactly one rank, no exact-length group split over
+    the ranks, utterance counts and summed text lengths within 7 % of each other, every rank spanning the whole length range."""
+    lens = corpus_lengths()
+    shares = [shard.deal_length_groups(lens, world, r) for r in range(world)]
+    assert sorted(i for s_ in shares for i in s_) == list(range(len(lens)))
+    owner = {}
+    for r, s_ in enumerate(shares):
+        assert [lens[i] for i in s_] == sorted(lens[i] for i in s_)            # sorted by length: launches are length ranges
+        for i in s_:
+            assert owner.setdefault(lens[i], r) == r                           # a length never appears on two ranks
+    counts = [len(s_) for s_ in shares]
+    work = [sum(lens[i] for i in s_) for s_ in shares]
+    assert max(counts) <= 1.07 * min(counts) and max(work) <= 1.07 * min(work)     # granularity: one group = 41 utterances of 1024
+    if world > 1:
+        for s_ in shares:
+            assert min(lens[i] for i in s_) < 60 and max(lens[i] for i in s_) > 240
+    with pytest.raises(ValueError):
+        shard.deal_length_groups(lens, world, world)
