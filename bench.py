@@ -347,8 +347,8 @@ C5_TFLOP = 7.55                     # fwd + bwd of one C5 step
 def bench_c4(model, synth, dev, rank, world, dist, n_utts=C4_UTTS, rows=C4_ROWS):
     """BASELINE config 4: the corpus is sorted by text length and its exact-length groups are dealt round-robin to the ranks
     (every rank sees the same length distribution: strong scaling without a collective); each rank streams its share through persistent launches of 64
-    live rows, utterances of different lengths side by side (ragged continuous batching), at least ~8 refills per row and
-    launch.  Timed on the device, max over ranks; frames = sum of the decoded lengths of all utterances."""
+    live rows, utterances of different lengths side by side (ragged continuous batching), at least ~16 refills per row and
+    launch (an utterance shorter than the launch's padded length only pays for its own positions).  Timed on the device, max over ranks; frames = sum of the decoded lengths of all utterances."""
     import random
     rng = random.Random(0)
     lens = [rng.randint(50, 250) for _ in range(n_utts)]
@@ -358,7 +358,7 @@ def bench_c4(model, synth, dev, rank, world, dist, n_utts=C4_UTTS, rows=C4_ROWS)
     from b200taco import shard
     mine = shard.deal_length_groups(lens, world, rank)
     corpus = {i: synth.phoneme_ids(1, lens[i], seed=i)[0] for i in mine}
-    n_launch = max(1, min(4, len(mine) // (8 * rows)))
+    n_launch = max(1, min(4, len(mine) // (16 * rows)))           # >= ~16 refills per row and launch: the drain of a launch is fixed
     per_launch = (len(mine) + n_launch - 1) // n_launch
 
     def run(idx):

@@ -582,7 +582,7 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
     FT_RESET();
     for (int item = rev ? ncta - 1 - cta : cta; item < B * NS; item += ncta) {
         const int b = item / NS, sl = item % NS;
-        const int t0 = sl * SL, t1 = min(T, t0 + SL), n = max(0, t1 - t0);
+        const int t0 = sl * SL, t1 = min(T, t0 + SL);
         // continuous batching: row b carries utterance mb since decode step rows[ROW_START + b]; its first step sees
         // zero previous / cumulative attention weights (src/model.py:104-115); a retired row repeats its last
         // utterance without writing anything the host reads
@@ -598,6 +598,12 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
         // T and every utterance attends to its own length only, which is exactly its exact-length solo decode (weights of the
         // padded positions are 0, like the zero padding of the location convolution at the end of an exact-length utterance)
         const int len = p.text_lengths ? (int)p.text_lengths[mb] : T;
+        // positions of this slice that are worked on.  Ragged launch: an utterance shorter than the launch's padded T only pays
+        // for its own positions plus the reach of the location convolution (15; those positions are masked, get weight 0 and
+        // keep the windows behind the last real position zero); whatever lies further back can only influence masked
+        // positions.  The output buffers of a continuous-batching launch are zero initialised by the caller.
+        int n = max(0, t1 - t0);
+        if (rows != nullptr && p.text_lengths != nullptr) n = max(0, min(n, len + 16 - t0));
         const size_t align_row = (size_t)(rows != nullptr ? rows[ROW_ABASE + b] : b) + (size_t)(oi < 0 ? 0 : oi) * B;
         consumer_sync();   // previous item's scratch is free
         const int ntiles = (n + TILE_POS - 1) / TILE_POS;
