@@ -181,7 +181,7 @@ def run_b200(args, rank, world, local_rank):
     def flush_l2():
         flush.zero_()
 
-    def run_pipelined(n, host, continuous=True):
+    def run_pipelined(n, host, continuous=True, everything=False):
         """n batches through the public corpus path (Tacotron2.inference_batches -> Engine.stream_infer: continuous
         batching, 32 live rows refilled as utterances stop; continuous=False -> Engine.pipeline_infer: one decoder launch
         per batch).  Results of every batch are complete inside this call.
@@ -190,7 +190,8 @@ def run_b200(args, rank, world, local_rank):
         feed = [ids_host if host else ids_dev] * n
         with contextlib.redirect_stdout(io.StringIO()):
             if continuous:
-                it = eng.stream_infer(feed, CAP, 0.5, to_host=host, pre_hook=flush_l2, timings=timings, live_rows=LIVE_ROWS)
+                it = eng.stream_infer(feed, CAP, 0.5, to_host="all" if everything else host, pre_hook=flush_l2, timings=timings,
+                                      live_rows=LIVE_ROWS)
             else:
                 it = eng.pipeline_infer(feed, CAP, 0.5, STOP_PER_UTTERANCE, to_host=host, pre_hook=flush_l2, timings=timings)
             for res in it:
@@ -253,13 +254,25 @@ def run_b200(args, rank, world, local_rank):
     barrier()
     e2e_ms = e0.elapsed_time(e1)
     d2h = last[6].numel() * 4 + B * 4
+    # the same with the reference's WHOLE 4-tuple copied to the host (mel_coarse, gate logits and alignments too)
+    run_pipelined(args.steps, True, everything=True)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    full_frames, _, _, last_full = run_pipelined(args.steps, True, everything=True)
+    f1.record()
+    barrier()
+    full_ms = f0.elapsed_time(f1)
+    d2h_full = sum(t.numel() * t.element_size() for t in last_full[6:])
 
-    agg = torch.tensor([ms, e2e_ms, float(frames), float(e2e_frames), float(launches)], device=dev, dtype=torch.float64)
+    agg = torch.tensor([ms, e2e_ms, float(frames), float(e2e_frames), float(launches), full_ms, float(full_frames)], device=dev,
+                       dtype=torch.float64)
     if dist is not None:
         mx = agg.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = agg.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         ms, e2e_ms = float(mx[0]), float(mx[1])
         frames, e2e_frames, launches = float(sm[2]), float(sm[3]), float(sm[4])
+        full_ms, full_frames = float(mx[5]), float(sm[6])
 
     out = None
     if rank == 0:
@@ -286,6 +299,10 @@ def run_b200(args, rank, world, local_rank):
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
                     "returns": "mel_postnet (B,S,80) + per-utterance lengths per batch, pinned host memory; mel_coarse, gate logits and "
                                "alignments of the reference's 4-tuple stay on the device (yielded as device tensors)"},
+            "e2e_full": {"value": full_frames / (full_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": ids_host.numel() * 8,
+                         "d2h_bytes_per_step": d2h_full, "ms_per_step": full_ms / args.steps,
+                         "returns": "the reference's whole 4-tuple per batch in pinned host memory: mel_postnet, mel_coarse, gate logits, "
+                                    "alignments (S,32,150), + lengths"},
             "gpu_launches": int(launches),
             "batch_by_batch": {"value": bb_frames / (bb_ms * 1e-3), "unit": UNIT, "ms_per_step": bb_ms / args.steps,
                                "us_per_decode_step": bb_dec_ms * 1e3 / bb_steps, "decode_steps": bb_steps,

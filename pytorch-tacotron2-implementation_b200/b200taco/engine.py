@@ -475,6 +475,8 @@ class Engine:
         its last utterance is done, while the launch is still decoding the following batches.  Encoders of the next group
         overlap the decoder launch of the current one.  Yields per batch, in order, what ``pipeline_infer`` yields; frames
         of a row beyond its own length are zero (``pipeline_infer``: that row's continued decode).
+        ``to_host``: True copies mel_postnet (+ lengths) of every batch into pinned host memory; ``"all"`` also mel_coarse, the gate
+        logits and the alignments (the reference's whole 4-tuple), appended to the yielded tuple in that order.
         ``live_rows``: decoder rows one launch keeps busy - a multiple of the batch size, at most 64 (None: the batch size).
         A decode step of 64 rows costs ~1.4x a step of 32 (it is latency, not bandwidth), so two 32-utterance batches decoding
         side by side finish ~40 % sooner; results per utterance do not depend on it."""
@@ -569,6 +571,13 @@ class Engine:
                         post_h = torch.empty(post.shape, dtype=post.dtype, pin_memory=True)
                         post_h.copy_(post, non_blocking=True)
                         res = res + (post_h, len_h[lo:hi])
+                        if to_host == "all":      # the reference's whole 4-tuple: also mel_coarse, gate logits, alignments
+                            extra = []
+                            for t_ in (coarse, res[2], res[3]):
+                                h_ = torch.empty(t_.shape, dtype=t_.dtype, pin_memory=True)
+                                h_.copy_(t_, non_blocking=True)
+                                extra.append(h_)
+                            res = res + tuple(extra)
                     ev = torch.cuda.Event()
                     ev.record(sP)
                 inflight.append((res, ev))

@@ -464,3 +464,18 @@ def test_ragged_continuous_batching_matches_solo_runs(rows, n_utts, cap):
         assert util.maxdiff(ga.cpu(), torch.stack(aligns)[:n, 0].cpu()) <= 2 * TOL_ALIGN
         assert util.maxdiff(gp.cpu(), post[0, :n].cpu()) <= 5 * TOL_MEL
     assert cap < 100 or len(spread) > 3
+
+
+def test_continuous_batching_whole_tuple_to_host():
+    """to_host="all": the reference's whole 4-tuple of every batch lands in pinned host memory, equal to the device tensors."""
+    m = gpu_model(util.weights("default", True))
+    batches = [synth.phoneme_ids(8, 21, seed=90 + i).cuda() for i in range(2)]
+    outs = list(m._get_engine().stream_infer(batches, 9, 0.5, to_host="all", live_rows=16))
+    assert len(outs) == 2
+    for o in outs:
+        post, coarse, gate, align, lengths, S = o[:6]
+        post_h, len_h, coarse_h, gate_h, align_h = o[6:]
+        assert all(t.is_pinned() for t in (post_h, coarse_h, gate_h, align_h))
+        assert torch.equal(post_h, post.cpu()) and torch.equal(coarse_h, coarse.cpu())
+        assert torch.equal(gate_h, gate.cpu()) and torch.equal(align_h, align.cpu()) and len_h.tolist() == lengths.tolist()
+        assert align_h.shape == (S, 8, 21)
