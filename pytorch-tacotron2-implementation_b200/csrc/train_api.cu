@@ -330,7 +330,7 @@ DecScratch dec_scratch(int B, int T, int S) {
     d.dpm = take((size_t)B * T * ATT_DIM);
     d.attn = take(attention_bwd_scratch_floats(B, T));
     d.dw = take((size_t)4 * RNN * (RNN + EMB));   // largest [in][out] weight gradient (1536 x 4096)
-    d.dvs = take((size_t)B * ATTN_PACC_F + ATTN_PACC_F);   // per-utterance attention parameter-gradient accumulators + their sum
+    d.dvs = take((size_t)2 * B * ATTN_PACC_F + ATTN_PACC_F);   // attention parameter-gradient accumulators (two per utterance: one per CTA of the pair) + their sum
     d.wcat_d = take((size_t)4 * RNN * (2 * RNN + EMB));        // [W_ih | W_hh] of the decoder LSTM, [4096][2560]
     d.wcat_a = take((size_t)4 * RNN * (PRENET + EMB + RNN));   // [W_ih | W_hh] of the attention LSTM, [4096][1792]
     d.dctx_all = take(n * EMB);                   // d ctx_t of every step: the memory gradient is one contraction after the walk
@@ -407,7 +407,7 @@ B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200ta
     TACO_CUDA(cudaMemsetAsync(gsum, 0, (size_t)BT * sizeof(float), st));
     TACO_CUDA(cudaMemsetAsync(dpm, 0, (size_t)BT * ATT_DIM * sizeof(float), st));
     TACO_CUDA(cudaMemsetAsync(d_dmemory, 0, (size_t)BT * EMB * sizeof(float), st));
-    TACO_CUDA(cudaMemsetAsync(dvs, 0, ((size_t)B * ATTN_PACC_F + ATTN_PACC_F) * sizeof(float), st));
+    TACO_CUDA(cudaMemsetAsync(dvs, 0, ((size_t)2 * B * ATTN_PACC_F + ATTN_PACC_F) * sizeof(float), st));
 
     // ---- reverse walk over the decode steps
     for (int t = S - 1; t >= 0; --t) {
@@ -486,8 +486,8 @@ B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200ta
     TACO_CUDA(cudaMemcpyAsync(G(grads->gate_b), dw + N_MELS, sizeof(float), cudaMemcpyDeviceToDevice, st));
     // attention parameters: sum of the per-utterance accumulators
     {
-        float* tot = dvs + (size_t)B * ATTN_PACC_F;
-        TT(train_colsum(tot, dvs, B, ATTN_PACC_F, st));
+        float* tot = dvs + (size_t)2 * B * ATTN_PACC_F;
+        TT(train_colsum(tot, dvs, 2 * B, ATTN_PACC_F, st));
         const size_t f = sizeof(float);
         TACO_CUDA(cudaMemcpyAsync(G(grads->attn_loc_dense_w), tot, ATT_DIM * LOC_F * f, cudaMemcpyDeviceToDevice, st));
         TACO_CUDA(cudaMemcpyAsync(G(grads->attn_loc_conv_w), tot + ATT_DIM * LOC_F, LOC_F * 2 * LOC_K * f, cudaMemcpyDeviceToDevice, st));

@@ -1,9 +1,13 @@
 // Backward-pass kernels of the teacher-forced decoder (reference Decoder.forward / _decode_step in train mode,
 // src/model.py:246-297; LocationSensitiveAttention :117-148).  First correct fp32 versions: the host walks the decode
 // steps in reverse and launches these kernels plus dense-layer calls per step (train_api.cu).
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 
 #include "handle.h"
+
+namespace cg = cooperative_groups;
 
 namespace b200taco {
 
@@ -574,6 +578,314 @@ __global__ void __launch_bounds__(ATTN_V2_NT) attention_bwd_v2_kernel(
     }
 }
 
+// ---- third version: the same computation with the positions of an utterance split over a CLUSTER OF TWO CTAs (2 B = 128 CTAs
+// instead of 64 on the 148 SMs; the kernel is bound by shared-memory bandwidth and dependent latency inside one SM, so two SMs per
+// utterance nearly halve it).  CTA r owns positions [r Th, r Th + n).  What crosses the pair goes through DSMEM:
+//   - the softmax-backward scalar  s = sum_tau w dw   (each CTA adds its partial into the peer, cluster.sync #1),
+//   - the query gradient dpq (CTA 1 sends its 128 partial sums to CTA 0, which stores the total),
+//   - 15 halo rows of dloc on each side of the cut for the transposed location convolution (read from the peer after
+//     cluster.sync #2; cluster.sync #3 keeps the peer resident until they are read).
+// Parameter-gradient partials go to accumulator slice 2 b + r (2 B slices, summed once after the walk).  T >= ATTN_V3_MIN_T.
+constexpr int ATTN_V3_MIN_T = 48;
+__host__ __device__ constexpr int attn_v3_half(int T) { return (((T + 1) >> 1) + 3) & ~3; }
+__host__ __device__ constexpr int attn_v3_smem_floats(int T) {
+    return EMB + LOC_F * WLOC_LD + ATT_DIM * LOC_LD + 5 * ATT_DIM + 2 * (attn_v3_half(T) + LOC_K - 1) + 2 * attn_v3_half(T) +
+           attn_v3_half(T) * LOC_LD + (attn_v3_half(T) + LOC_K - 1) * LOC_LD + 2 * ATTN_V2_NW * ATT_DIM + 2 * ATTN_V2_NW * ATT_DIM +
+           ATTN_V2_NT;
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_V2_NT) attention_bwd_v3_kernel(
+    const float* __restrict__ w, const float* __restrict__ prev, const float* __restrict__ cum, const float* __restrict__ pq,
+    const float* __restrict__ pm, const float* __restrict__ memory, float* __restrict__ dctx,
+    const float* __restrict__ dw_ext, const float* __restrict__ dprev_next, float* __restrict__ gsum,
+    const int64_t* __restrict__ lengths, const float* __restrict__ Wloc, const float* __restrict__ Wld,
+    const float* __restrict__ v, const float* __restrict__ vb_p, const float* __restrict__ escale_p,
+    float* __restrict__ dctx_out, float* __restrict__ dpm, float* __restrict__ dpq, float* __restrict__ dprev_out,
+    float* __restrict__ pacc /* [2 B][ATTN_PACC] */, int B, int T) {
+    extern __shared__ __align__(16) float sm[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    // "both CTAs are running" (required before the first DSMEM access): arrive now, wait just before that access
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    const int b = blockIdx.x >> 1, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int len = lengths ? (int)lengths[b] : T;
+    const float vb = vb_p[0], escale = escale_p[0];
+    constexpr int HALO = (LOC_K - 1) / 2;
+    const int Th = attn_v3_half(T);
+    const int p0 = rank * Th, n = rank == 0 ? Th : T - Th;          // own positions [p0, p0 + n); both >= HALO (T >= 48)
+    const int WLh = Th + LOC_K - 1;                                  // layout strides use Th on both CTAs (peer addressing)
+    float* dctx_s = sm;
+    float* wloc_s = dctx_s + EMB;
+    float* wld_s = wloc_s + LOC_F * WLOC_LD;
+    float* v_s = wld_s + ATT_DIM * LOC_LD;
+    float* pq_s = v_s + ATT_DIM;
+    float* xch_dpq = pq_s + ATT_DIM;                   // written by the peer (CTA 1 -> CTA 0)
+    float* own_dpq = xch_dpq + ATT_DIM;
+    float* xch_s = own_dpq + ATT_DIM;                  // [0] written by the peer; rest of the row spare
+    float* win_p = xch_s + ATT_DIM;                    // [n + 30]: conv inputs at positions p0 - 15 ...
+    float* win_c = win_p + WLh;
+    float* w_s = win_c + WLh;
+    float* dw_s = w_s + Th;
+    float* loc_s = dw_s + Th;
+    float* dloc_s = loc_s + Th * LOC_LD;               // [n + 30] rows: row i = position p0 - 15 + i (halo rows from the peer / zero)
+    float* tile_du = dloc_s + WLh * LOC_LD;
+    float* accx = tile_du + 2 * ATTN_V2_NW * ATT_DIM;
+    float* red_s = accx + 2 * ATTN_V2_NW * ATT_DIM;
+    float* dWld = pacc + (size_t)blockIdx.x * ATTN_PACC;
+    float* dWloc = dWld + ATT_DIM * LOC_F;
+    float* dv = dWloc + LOC_F * 2 * LOC_K;
+    float* dvb_scale = dv + ATT_DIM;
+    const float* wb = w + (size_t)b * T;
+    const float* pb = prev ? prev + (size_t)b * T : nullptr;
+    const float* cb = cum + (size_t)b * T;
+
+    for (int i = tid; i < EMB; i += ATTN_V2_NT) {
+        const float d = dctx[(size_t)b * EMB + i];
+        dctx_s[i] = d;
+        if (rank == 0) dctx_out[(size_t)b * EMB + i] = d;
+    }
+    for (int i = tid; i < LOC_F * 2 * LOC_K; i += ATTN_V2_NT) wloc_s[(i / (2 * LOC_K)) * WLOC_LD + i % (2 * LOC_K)] = Wloc[i];
+    for (int i = tid; i < ATT_DIM * LOC_F; i += ATTN_V2_NT) wld_s[(i / LOC_F) * LOC_LD + (i % LOC_F)] = Wld[i];
+    if (tid < ATT_DIM) { v_s[tid] = v[tid]; pq_s[tid] = pq[(size_t)b * ATT_DIM + tid]; }
+    for (int i = tid; i < n + LOC_K - 1; i += ATTN_V2_NT) {
+        const int t = p0 - HALO + i;
+        const bool ok = t >= 0 && t < T;
+        win_p[i] = ok && pb ? pb[t] : 0.f;
+        win_c[i] = ok ? cb[t] : 0.f;
+    }
+    for (int i = tid; i < n; i += ATTN_V2_NT) w_s[i] = wb[p0 + i];
+    __syncthreads();
+
+    // (a) dw of the own positions, partial s
+    float s_part = 0.f;
+    for (int j0 = 2 * warp; j0 < n; j0 += 2 * ATTN_V2_NW) {
+        float4 m[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int j = j0 + r < n ? j0 + r : j0;
+            const float4* mrow = reinterpret_cast<const float4*>(memory + ((size_t)b * T + p0 + j) * EMB);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) m[r][q] = __ldg(mrow + lane + 32 * q);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float acc = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 d = *reinterpret_cast<const float4*>(dctx_s + 4 * (lane + 32 * q));
+                acc = fmaf(d.x, m[r][q].x, acc); acc = fmaf(d.y, m[r][q].y, acc);
+                acc = fmaf(d.z, m[r][q].z, acc); acc = fmaf(d.w, m[r][q].w, acc);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            const int j = j0 + r;
+            if (lane == 0 && j < n) {
+                const size_t g = (size_t)b * T + p0 + j;
+                const float d = acc + (dw_ext ? dw_ext[g] : 0.f) + (dprev_next ? dprev_next[g] : 0.f) + gsum[g];
+                dw_s[j] = d;
+                s_part += w_s[j] * d;
+            }
+        }
+    }
+    red_s[tid] = s_part;
+    // (b) location features of the own positions
+    for (int i = tid; i < n * LOC_F; i += ATTN_V2_NT) {
+        const int j = i >> 5, f = i & 31;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < LOC_K; ++k) {
+            acc = fmaf(wloc_s[f * WLOC_LD + k], win_p[j + k], acc);
+            acc = fmaf(wloc_s[f * WLOC_LD + LOC_K + k], win_c[j + k], acc);
+        }
+        loc_s[j * LOC_LD + f] = acc;
+    }
+    // halo rows of dloc that no CTA owns (positions < 0 and >= T) are zero
+    for (int i = tid; i < HALO * LOC_LD; i += ATTN_V2_NT) dloc_s[(rank == 0 ? 0 : (HALO + n) * LOC_LD) + i] = 0.f;
+    __syncthreads();
+    for (int o = ATTN_V2_NT / 2; o > 0; o >>= 1) {
+        if (tid < o) red_s[tid] += red_s[tid + o];
+        __syncthreads();
+    }
+    const float s_own = red_s[0];
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+    if (tid == 0) *cluster.map_shared_rank(xch_s, rank ^ 1) = s_own;
+    cluster.sync();                                                  // #1 (also orders the reads of red_s[0] before its reuse)
+    const float s_all = rank == 0 ? s_own + xch_s[0] : xch_s[0] + s_own;
+    if (rank == 0)                                                   // consumed (the peer read it before it arrived at #1)
+        for (int i = tid; i < EMB; i += ATTN_V2_NT) dctx[(size_t)b * EMB + i] = 0.f;
+
+    // (c) per position, exactly as in the second version, over the own positions
+    float dvb_part = 0.f, dscale_part = 0.f;
+    float dv_r[4] = {0.f, 0.f, 0.f, 0.f}, dpq_r[4] = {0.f, 0.f, 0.f, 0.f};
+    float dwld_r[ATT_DIM * LOC_F / ATTN_V2_NT];
+#pragma unroll
+    for (int i = 0; i < ATT_DIM * LOC_F / ATTN_V2_NT; ++i) dwld_r[i] = 0.f;
+    for (int t0 = 0; t0 < n; t0 += 2 * ATTN_V2_NW) {
+        int jj[2];
+        bool ok[2];
+        float* du_row[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            jj[r] = t0 + r * ATTN_V2_NW + warp;
+            ok[r] = jj[r] < n;
+            if (!ok[r]) jj[r] = n - 1;
+            du_row[r] = tile_du + (r * ATTN_V2_NW + warp) * ATT_DIM;
+        }
+        float pmv[2][4], lf[2][4], th[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                pmv[r][q] = __ldg(pm + ((size_t)b * T + p0 + jj[r]) * ATT_DIM + lane + 32 * q);
+                lf[r][q] = 0.f;
+            }
+        const float4* l0 = reinterpret_cast<const float4*>(loc_s + jj[0] * LOC_LD);
+        const float4* l1 = reinterpret_cast<const float4*>(loc_s + jj[1] * LOC_LD);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4* wr = reinterpret_cast<const float4*>(wld_s + (lane + 32 * q) * LOC_LD);
+#pragma unroll
+            for (int f4 = 0; f4 < LOC_F / 4; ++f4) {
+                const float4 wv = wr[f4], x = l0[f4], y = l1[f4];
+                lf[0][q] = fmaf(wv.x, x.x, lf[0][q]); lf[0][q] = fmaf(wv.y, x.y, lf[0][q]);
+                lf[0][q] = fmaf(wv.z, x.z, lf[0][q]); lf[0][q] = fmaf(wv.w, x.w, lf[0][q]);
+                lf[1][q] = fmaf(wv.x, y.x, lf[1][q]); lf[1][q] = fmaf(wv.y, y.y, lf[1][q]);
+                lf[1][q] = fmaf(wv.z, y.z, lf[1][q]); lf[1][q] = fmaf(wv.w, y.w, lf[1][q]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float e_raw_part = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int a = lane + 32 * q;
+                th[r][q] = tanhf(pq_s[a] + pmv[r][q] + lf[r][q]);
+                e_raw_part = fmaf(v_s[a], th[r][q], e_raw_part);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) e_raw_part += __shfl_xor_sync(0xffffffffu, e_raw_part, o);
+            const float e_raw = e_raw_part + vb;
+            const float de = ok[r] && p0 + jj[r] < len ? w_s[jj[r]] * (dw_s[jj[r]] - s_all) : 0.f;
+            const float de_raw = de * escale;
+            if (lane == 0) { dscale_part += de * e_raw; dvb_part += de_raw; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int a = lane + 32 * q;
+                const float du = de_raw * v_s[a] * (1.f - th[r][q] * th[r][q]);
+                du_row[r][a] = du;
+                if (ok[r]) {
+                    float* dpm_p = dpm + ((size_t)b * T + p0 + jj[r]) * ATT_DIM + a;
+                    *dpm_p += du;
+                }
+                dv_r[q] = fmaf(de_raw, th[r][q], dv_r[q]);
+                dpq_r[q] += du;
+            }
+        }
+        __syncwarp();
+        {
+            float acc0 = 0.f, acc1 = 0.f;
+            const float4* d0 = reinterpret_cast<const float4*>(du_row[0]);
+            const float4* d1 = reinterpret_cast<const float4*>(du_row[1]);
+#pragma unroll 4
+            for (int a4 = 0; a4 < ATT_DIM / 4; ++a4) {
+                const float4 x = d0[a4], y = d1[a4];
+                const float w0 = wld_s[(4 * a4 + 0) * LOC_LD + lane], w1 = wld_s[(4 * a4 + 1) * LOC_LD + lane],
+                            w2 = wld_s[(4 * a4 + 2) * LOC_LD + lane], w3 = wld_s[(4 * a4 + 3) * LOC_LD + lane];
+                acc0 = fmaf(x.x, w0, acc0); acc0 = fmaf(x.y, w1, acc0); acc0 = fmaf(x.z, w2, acc0); acc0 = fmaf(x.w, w3, acc0);
+                acc1 = fmaf(y.x, w0, acc1); acc1 = fmaf(y.y, w1, acc1); acc1 = fmaf(y.z, w2, acc1); acc1 = fmaf(y.w, w3, acc1);
+            }
+            if (ok[0]) dloc_s[(HALO + jj[0]) * LOC_LD + lane] = acc0;
+            if (ok[1]) dloc_s[(HALO + jj[1]) * LOC_LD + lane] = acc1;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int pp = 0; pp < 2 * ATTN_V2_NW; ++pp) {
+            const int j = t0 + pp < n ? t0 + pp : n - 1;          // rows past n hold zeros in tile_du
+            const float l = loc_s[j * LOC_LD + lane];
+            const float4* dr = reinterpret_cast<const float4*>(tile_du + pp * ATT_DIM);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const float4 d = dr[warp + ATTN_V2_NW * g];
+                dwld_r[4 * g + 0] = fmaf(d.x, l, dwld_r[4 * g + 0]);
+                dwld_r[4 * g + 1] = fmaf(d.y, l, dwld_r[4 * g + 1]);
+                dwld_r[4 * g + 2] = fmaf(d.z, l, dwld_r[4 * g + 2]);
+                dwld_r[4 * g + 3] = fmaf(d.w, l, dwld_r[4 * g + 3]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        accx[warp * ATT_DIM + lane + 32 * q] = dv_r[q];
+        accx[(ATTN_V2_NW + warp) * ATT_DIM + lane + 32 * q] = dpq_r[q];
+    }
+    red_s[tid] = dvb_part;
+    __syncthreads();
+    if (tid < 2 * ATT_DIM) {
+        const int which = tid / ATT_DIM, a = tid % ATT_DIM;
+        float acc = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < ATTN_V2_NW; ++ww) acc += accx[(which * ATTN_V2_NW + ww) * ATT_DIM + a];
+        if (which == 0) dv[a] += acc;
+        else if (rank == 0) own_dpq[a] = acc;
+        else cluster.map_shared_rank(xch_dpq, 0)[a] = acc;
+    }
+    if (tid == 0) {
+        float acc = 0.f;
+        for (int ww = 0; ww < ATTN_V2_NW; ++ww) acc += red_s[ww * 32];
+        dvb_scale[0] += acc;
+    }
+    __syncthreads();
+    red_s[tid] = dscale_part;
+    __syncthreads();
+    if (tid == 0) {
+        float acc = 0.f;
+        for (int ww = 0; ww < ATTN_V2_NW; ++ww) acc += red_s[ww * 32];
+        dvb_scale[1] += acc;
+    }
+#pragma unroll
+    for (int q = 0; q < ATT_DIM * LOC_F / ATTN_V2_NT; ++q)
+        dWld[(4 * (warp + ATTN_V2_NW * (q >> 2)) + (q & 3)) * LOC_F + lane] += dwld_r[q];
+
+    cluster.sync();                                                  // #2: dloc of both halves complete, dpq partial delivered
+    if (rank == 0 && tid < ATT_DIM) dpq[(size_t)b * ATT_DIM + tid] = own_dpq[tid] + xch_dpq[tid];
+    {   // the 15 rows next to the cut come from the peer: CTA 0 needs the peer's first rows, CTA 1 the last rows of CTA 0
+        const float* peer = cluster.map_shared_rank(dloc_s, rank ^ 1);
+        const int src_row = rank == 0 ? HALO : Th, dst_row = rank == 0 ? HALO + n : 0;
+        for (int i = tid; i < HALO * LOC_F; i += ATTN_V2_NT) {
+            const int rr = i >> 5, f = i & 31;
+            dloc_s[(dst_row + rr) * LOC_LD + f] = peer[(src_row + rr) * LOC_LD + f];
+        }
+    }
+    cluster.sync();                                                  // #3: halo rows in place; the peer may exit
+
+    // (d) location conv backward over the own positions: dWloc[f][c][k] += sum_j dloc[j][f] * in_c[j + k - 15]
+    for (int i = tid; i < LOC_F * 2 * LOC_K; i += ATTN_V2_NT) {
+        const int k = i % LOC_K, c = (i / LOC_K) % 2, f = i / (2 * LOC_K);
+        const float* win = c == 0 ? win_p : win_c;
+        float acc = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < n; ++j) acc = fmaf(dloc_s[(HALO + j) * LOC_LD + f], win[j + k], acc);
+        dWloc[i] += acc;
+    }
+    //     d in_c[tt] = sum_k sum_f dloc[tt - k + 15][f] * Wloc[f][c][k]; rows outside [0, T) are zero rows of dloc_s
+    for (int i = tid; i < 2 * n; i += ATTN_V2_NT) {
+        const int c = i / n, j = i % n;
+        float acc = 0.f;
+        for (int k = 0; k < LOC_K; ++k) {
+            const float4* dl = reinterpret_cast<const float4*>(dloc_s + (j - k + 2 * HALO) * LOC_LD);
+            const float* wl = wloc_s + c * LOC_K + k;
+#pragma unroll
+            for (int f4 = 0; f4 < LOC_F / 4; ++f4) {
+                const float4 d = dl[f4];
+                acc = fmaf(d.x, wl[(4 * f4 + 0) * WLOC_LD], acc); acc = fmaf(d.y, wl[(4 * f4 + 1) * WLOC_LD], acc);
+                acc = fmaf(d.z, wl[(4 * f4 + 2) * WLOC_LD], acc); acc = fmaf(d.w, wl[(4 * f4 + 3) * WLOC_LD], acc);
+            }
+        }
+        if (c == 0) dprev_out[(size_t)b * T + p0 + j] = acc;
+        else gsum[(size_t)b * T + p0 + j] += acc;
+    }
+}
+
 // Deferred context gradient (src/model.py:147): dmemory[b][tau][d] = sum_s w[s][b][tau] * dctx[s][b][d], one 64 x 64 tile of
 // (tau, d) per CTA, all S steps reduced in the CTA (plain stores, no atomics).  w (S,B,T), dctx (S,B,512), dmemory (B,T,512).
 __global__ void __launch_bounds__(256) ctx_dmemory_kernel(const float* __restrict__ w, const float* __restrict__ dctx,
@@ -813,6 +1125,20 @@ int attention_bwd(const float* w, const float* prev, const float* cum, const flo
                   float* dctx, const float* dw_ext, const float* dprev_next, float* gsum, const int64_t* lengths,
                   const float* Wloc, const float* Wld, const float* v, const float* vb, const float* escale, float* dmemory, float* dpm,
                   float* dpq, float* dprev_out, float* pacc, float* scratch, float* dctx_out, int B, int T, cudaStream_t st) {
+    static const bool no_v3 = [] { const char* e = getenv("TACO_ATTN_BWD_V2"); return e && e[0] == '1'; }();
+    if (attention_bwd_defers_dmemory(T) && T >= ATTN_V3_MIN_T && !no_v3) {
+        const int smem = attn_v3_smem_floats(T) * (int)sizeof(float);
+        static bool configured3 = false;
+        if (!configured3) {
+            TACO_CUDA(cudaFuncSetAttribute(attention_bwd_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           attn_v3_smem_floats(ATTN_V2_MAX_T) * (int)sizeof(float)));
+            configured3 = true;
+        }
+        attention_bwd_v3_kernel<<<2 * B, ATTN_V2_NT, smem, st>>>(w, prev, cum, pq, pm, memory, dctx, dw_ext, dprev_next, gsum, lengths,
+                                                                Wloc, Wld, v, vb, escale, dctx_out, dpm, dpq, dprev_out, pacc, B, T);
+        TACO_LAUNCHED();
+        return B200TACO_OK;
+    }
     if (attention_bwd_defers_dmemory(T)) {
         const int smem = attn_v2_smem_floats(T) * (int)sizeof(float);
         static bool configured = false;

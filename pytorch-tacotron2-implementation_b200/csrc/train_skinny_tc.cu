@@ -10,7 +10,12 @@
 //   warps 0-3  A loaders: dZ rows (k contiguous) -> hi / lo bf16 -> K-major no-swizzle core matrices
 //   warp 4     one elected lane streams the pre-packed weight tile (16 KB per stage) with cp.async.bulk
 //   warp 5     one elected lane issues 4 tcgen05.mma.kind::f16 (K = 16 each) per stage
-//   epilogue   warps 0-3 read their TMEM lane quarter and add hi and lo rows onto the destination with atomics (split-K)
+//   epilogue   all 16 loader warps read TMEM (lane quarter x 32-column group) into a padded shared-memory tile, hi and lo rows are
+//              added there, and the 64 x 128 result goes onto the destination with COALESCED atomics (a warp = 128 consecutive
+//              bytes of one row).  The first version added hi and lo separately with one row per lane: 2.6 M scattered atomics
+//              per call were most of its 45 us.
+//   grid       (N / 128 column tiles) x (K splits); the 64 k-chunks are dealt as evenly as possible to floor(SMs / tiles) splits so
+//              that the whole call is ONE wave (it was 160 CTAs = two waves for the 2560-column cell)
 #include <cstdlib>
 
 #include "handle.h"
@@ -32,6 +37,8 @@ constexpr int ST_GROUPS = 4;                   // loader groups: group g fills t
 constexpr int ST_LOADERS = 4 * ST_GROUPS;
 constexpr int ST_THREADS = (ST_LOADERS + 2) * 32;
 constexpr int ST_NACC = 4;
+constexpr int ST_RED_LD = ST_N + 1;            // row stride of the epilogue tile: lanes = rows on the way in, = columns on the way out
+static_assert(128 * ST_RED_LD * 4 <= ST_STAGES * ST_STAGE, "the epilogue tile reuses the pipeline stages");
 
 struct SkinnySegs {
     float* out[3];
@@ -43,15 +50,17 @@ __device__ __forceinline__ void st_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
-__device__ __forceinline__ void st_tmem_ld_32x8(uint32_t taddr, float (&v)[8]) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr)
-                 : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+__device__ __forceinline__ void st_tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // W fp32 [K][N] (ldw) -> bf16 tiles [N / 128][K / 64][128 n x 64 k] in the UMMA K-major no-swizzle layout
@@ -66,7 +75,7 @@ __global__ void pack_skinny_kernel(__nv_bfloat16* __restrict__ dst, const float*
 }
 
 __global__ void __launch_bounds__(ST_THREADS, 1)
-    skinny_tc_kernel(const float* __restrict__ X, int ldx, const __nv_bfloat16* __restrict__ Wp, const SkinnySegs so, int B, int K, int k_per) {
+    skinny_tc_kernel(const float* __restrict__ X, int ldx, const __nv_bfloat16* __restrict__ Wp, const SkinnySegs so, int B, int K) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + ST_STAGES;
@@ -76,9 +85,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nt = blockIdx.x, n0 = nt * ST_N;
-    const int k0 = blockIdx.y * k_per, k1 = min(K, k0 + k_per);
-    const int iters = (k1 - k0) / ST_K;
     const int kchunks = K / ST_K;
+    const int c0 = (int)(((long long)blockIdx.y * kchunks) / gridDim.y), c1 = (int)(((long long)(blockIdx.y + 1) * kchunks) / gridDim.y);
+    const int k0 = c0 * ST_K;
+    const int iters = c1 - c0;
 
     if (tid == 0) {
         for (int s = 0; s < ST_STAGES; ++s) {
@@ -178,30 +188,41 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
     }
     __syncwarp();
 
-    if (warp < 4 && iters > 0) {
-        st_wait(acc_bar, 0);
-        umma::fence_after_sync();
-        const int row = warp * 32 + lane, b = row & 63;                 // rows 64.. are the lo parts of rows 0..63
-        const int seg = n0 < so.n_end[0] ? 0 : (n0 < so.n_end[1] ? 1 : 2);
-        const int nb = seg == 0 ? 0 : so.n_end[seg - 1];
-        float* dst = so.out[seg] + (size_t)b * so.ldo[seg] + (n0 - nb);
-        const int nacc = min(ST_NACC, iters * (ST_K / 16));
+    // ---------------------------------------------------------------- epilogue (iters is uniform over the CTA)
+    if (iters > 0) {
+        float* red = reinterpret_cast<float*>(stages);                  // [128 hi|lo rows][ST_RED_LD]; every MMA has read its stage
+        if (warp < ST_LOADERS) {
+            st_wait(acc_bar, 0);
+            umma::fence_after_sync();
+            const int q = warp & 3, cg = warp >> 2;                     // TMEM lane quarter, 32-column group
+            const int nacc = min(ST_NACC, iters * (ST_K / 16));
+            float* rrow = red + (q * 32 + lane) * ST_RED_LD + cg * 32;
 #pragma unroll 1
-        for (int c = 0; c < ST_N; c += 8) {
-            float v[8];
-            st_tmem_ld_32x8(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
-            for (int a = 1; a < nacc; ++a) {
-                float u[8];
-                st_tmem_ld_32x8(tmem + ((uint32_t)(warp * 32) << 16) + a * ST_N + c, u);
+            for (int hc = 0; hc < 32; hc += 16) {
+                float v[16];
+                st_tmem_ld_32x16(tmem + ((uint32_t)(q * 32) << 16) + cg * 32 + hc, v);
+                for (int a = 1; a < nacc; ++a) {
+                    float u[16];
+                    st_tmem_ld_32x16(tmem + ((uint32_t)(q * 32) << 16) + a * ST_N + cg * 32 + hc, u);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] += u[i];
+                    for (int i = 0; i < 16; ++i) v[i] += u[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) rrow[hc + i] = v[i];
             }
-            if (b < B) {
+            umma::fence_before_sync();
+        }
+        __syncthreads();
+        if (warp < ST_LOADERS) {
+            const int seg = n0 < so.n_end[0] ? 0 : (n0 < so.n_end[1] ? 1 : 2);
+            const int nb = seg == 0 ? 0 : so.n_end[seg - 1];
+            float* dst = so.out[seg] + (n0 - nb);
+            for (int b = warp; b < B; b += ST_LOADERS) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) atomicAdd(dst + c + i, v[i]);
+                for (int c = 0; c < ST_N; c += 32)
+                    atomicAdd(dst + (size_t)b * so.ldo[seg] + c + lane, red[b * ST_RED_LD + c + lane] + red[(64 + b) * ST_RED_LD + c + lane]);
             }
         }
-        umma::fence_before_sync();
     }
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, 512);
@@ -241,15 +262,18 @@ int skinny_gemm_multi_tc(const float* X, int ldx, const void* Wp, int B, int K, 
         }
     }
     const int ntiles = N / ST_N;
-    int ks = 1;
-    while (ntiles * ks * 2 <= 160 && K / (ks * 2) >= 4 * ST_K) ks *= 2;
-    const int k_per = K / ks;
+    static const int sms = [] { int d = 0, n = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n > 0 ? n : 148; }();
+    // one wave: as many K splits as fit next to the column tiles, at least 4 k-chunks each (TACO_SKINNY_KS overrides: measurements)
+    static const int forced_ks = [] { const char* e = getenv("TACO_SKINNY_KS"); return e ? atoi(e) : 0; }();
+    int ks = forced_ks > 0 ? forced_ks : sms / ntiles;
+    ks = ks < 1 ? 1 : (ks > K / (4 * ST_K) ? K / (4 * ST_K) : ks);
+    if (ks < 1) ks = 1;
     static bool attr = false;
     if (!attr) {
         TACO_CUDA(cudaFuncSetAttribute(skinny_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_TOTAL));
         attr = true;
     }
-    skinny_tc_kernel<<<dim3(ntiles, ks), ST_THREADS, ST_TOTAL, st>>>(X, ldx, static_cast<const __nv_bfloat16*>(Wp), so, B, K, k_per);
+    skinny_tc_kernel<<<dim3(ntiles, ks), ST_THREADS, ST_TOTAL, st>>>(X, ldx, static_cast<const __nv_bfloat16*>(Wp), so, B, K);
     TACO_LAUNCHED();
     return B200TACO_OK;
 }

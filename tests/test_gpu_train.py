@@ -95,7 +95,9 @@ def test_encoder_train_forward_backward(B, T):
             assert float(d.median()) <= 1e-3 and float(d.max()) <= 0.1, (k, float(d.median()), float(d.max()))
 
 
-@pytest.mark.parametrize("B,T,S,use_masks,use_lengths", [(2, 9, 3, False, False), (3, 21, 6, True, True), (5, 40, 12, True, True)])
+@pytest.mark.parametrize("B,T,S,use_masks,use_lengths", [(2, 9, 3, False, False), (3, 21, 6, True, True), (5, 40, 12, True, True),
+                                                                  # T >= 48: the attention backward runs as a two-CTA cluster per utterance
+                                                                  (3, 48, 5, True, True), (4, 77, 7, True, True), (2, 150, 4, False, False)])
 def test_decoder_train_forward_backward(B, T, S, use_masks, use_lengths):
     """Teacher-forced decoder in train mode (B >= 4 takes the tensor-core kernel) + the reverse-step backward."""
     sd = util.weights("stress", True)                      # bf16-representable weights: both sides see the same values
