@@ -54,6 +54,14 @@ B200TACO_API int32_t b200taco_decoder_profile(b200taco_handle* h, int64_t* out, 
 B200TACO_API int32_t b200taco_decoder_trace(b200taco_handle* h, int64_t* out, int32_t n, void* stream);
 
 /*
+ * Measurement aid: phase times (ns, summed over launches since the last reset) of CTA 0 of the training attention backward
+ * (attention_bwd_v3_kernel) when the process runs with TACO_ATTN_TIMES=1: out8[0] loads, [1] dw / s of CTA 0's first
+ * warp, [2] location features, [3] reduction + first cluster exchange, [4] per-position pass, [5] reductions + halo exchange,
+ * [6] location-filter gradient, [7] location-input gradient.  Synchronises the device.
+ */
+B200TACO_API int32_t b200taco_attn_bwd_phase_ns(uint64_t* out8, int32_t reset);
+
+/*
  * Unit-test aid for the tcgen05 path: D[128][32] (fp32) = A[128][K] . B[32][K]^T with bf16
  * operands (row-major device arrays), one CTA, accumulators in TMEM.  K a multiple of 64.
  * variant 0 is the production descriptor convention; other values are bring-up experiments.

@@ -63,6 +63,19 @@ def main():
     torch.cuda.synchronize(dev)
     plain_ms = e0.elapsed_time(e1)
 
+    phase_text = ""
+    if os.environ.get("TACO_ATTN_TIMES") == "1":
+        import ctypes
+        from b200taco import _cabi
+        buf = (ctypes.c_uint64 * 8)()
+        _cabi.lib().b200taco_attn_bwd_phase_ns(buf, 1)
+        step()
+        _cabi.lib().b200taco_attn_bwd_phase_ns(buf, 1)
+        names = ["loads", "dw + s (first warp)", "location features", "reduction + cluster exchange 1", "per-position pass",
+                 "reductions + halo exchange", "location-filter gradient", "location-input gradient"]
+        phase_text = "\n\nattention_bwd_v3_kernel, CTA 0, us per launch (TIMED instantiation): " + ", ".join(
+            f"{n} {buf[i] / S / 1e3:.2f}" for i, n in enumerate(names)) + f"; sum {sum(buf) / S / 1e3:.2f}"
+
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         step()
         torch.cuda.synchronize(dev)
@@ -91,7 +104,7 @@ def main():
         if tot / total < 0.001:
             continue
         lines.append(f"| `{name[:110]}` | {n} | {tot / 1e3:.2f} | {tot / n:.1f} | {100 * tot / total:.1f} % |")
-    text = "\n".join(lines)
+    text = "\n".join(lines) + phase_text
     print(text)
     if args.out:
         os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)

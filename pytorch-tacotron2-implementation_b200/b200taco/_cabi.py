@@ -108,6 +108,7 @@ SIGNATURES = {
     "b200taco_measure_sync_costs": (C.c_int32, [C.POINTER(C.c_int64), C.c_void_p]),
     "b200taco_decoder_profile": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_void_p]),
     "b200taco_decoder_trace": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_void_p]),
+    "b200taco_attn_bwd_phase_ns": (C.c_int32, [C.POINTER(C.c_uint64), C.c_int32]),
     "b200taco_debug_umma_gemm": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "b200taco_launch_count": (C.c_int64, [C.c_int32]),
     # ---- training (stage by stage, include/b200taco.h)

@@ -72,6 +72,7 @@ int transpose_bct_to_btc(const float* in, float* out, int B, int C, int T, cudaS
 bool dense_tc_supported(int c_in, int c_out, int ldx, int ldy);
 size_t dense_tc_weight_floats(int taps, int c_in, int c_out);
 int pack_dense_tc(float* dst, const float* w_tap_ci_co, int taps, int c_in, int c_out, cudaStream_t stream);
+constexpr int TRAIN_CONV_TC_MIN_ROWS = 1024;    // training convolutions with at least this many rows run on the tensor cores
 // per-utterance options of a layer over B utterances of seg_len rows each.
 //  y != nullptr: second copy of the result, channel major (B, c_out, ld) and zero from lengths[b] on: the vocoder hand-off
 //  layout (inference.py:71, train.py:71-79).

@@ -20,15 +20,16 @@ inline int blocks_for(size_t n) { return (int)((n + 255) / 256 > 4096 ? 4096 : (
 // ---- LSTMCell backward (pointwise part).  gates [B][4096] = i,f,g,o post-activation (gate*1024 + unit), c [B][1024],
 // c_prev [B][1024] or null (zero state), dh_post [B][1024] = gradient w.r.t. the (dropped) hidden state, mask or null,
 // dc [B][1024] carried cell gradient (in/out), dz [B][4096] gradient w.r.t. the gate pre-activations (out).
+// dh_extra [B][ld_extra] (nullable): a second addend of dh_post that is not carried (the projection's gradient of this step).
 __global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c, const float* __restrict__ c_prev,
-                                     float* __restrict__ dh_post, const float* __restrict__ mask, float scale,
-                                     float* __restrict__ dc, float* __restrict__ dz, int B) {
+                                     float* __restrict__ dh_post, const float* __restrict__ dh_extra, int ld_extra,
+                                     const float* __restrict__ mask, float scale, float* __restrict__ dc, float* __restrict__ dz, int B) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * RNN) return;
     const int b = i / RNN, u = i % RNN;
     const float* g4 = gates + (size_t)b * 4 * RNN + u;
     const float gi = g4[0], gf = g4[RNN], gg = g4[2 * RNN], go = g4[3 * RNN];
-    const float dh = dh_post[i] * (mask ? mask[i] * scale : 1.f);
+    const float dh = (dh_post[i] + (dh_extra ? dh_extra[(size_t)b * ld_extra + u] : 0.f)) * (mask ? mask[i] * scale : 1.f);
     dh_post[i] = 0.f;          // consumed: the data-gradient GEMM that follows accumulates the previous step's gradient onto it
     const float tc = tanhf(c[i]);
     const float dct = dc[i] + dh * go * (1.f - tc * tc);
@@ -587,12 +588,24 @@ __global__ void __launch_bounds__(ATTN_V2_NT) attention_bwd_v2_kernel(
 //     cluster.sync #2; cluster.sync #3 keeps the peer resident until they are read).
 // Parameter-gradient partials go to accumulator slice 2 b + r (2 B slices, summed once after the walk).  T >= ATTN_V3_MIN_T.
 constexpr int ATTN_V3_MIN_T = 48;
+constexpr int ATTN_V3_G_LD = 2 * LOC_K + 3;      // odd row stride of the g[tau][c][k] tile (location-input gradient)
+static_assert(ATTN_V2_NT == LOC_F * 2 * 8 && 8 * 4 >= LOC_K, "dWloc mapping: thread = (feature, channel, group of 4 taps)");
+static_assert(ATTN_V2_NT == 8 * 64 && 2 * LOC_K <= 64 && LOC_F == 32, "g mapping: thread = (row group, channel-tap)");
 __host__ __device__ constexpr int attn_v3_half(int T) { return (((T + 1) >> 1) + 3) & ~3; }
 __host__ __device__ constexpr int attn_v3_smem_floats(int T) {
     return EMB + LOC_F * WLOC_LD + ATT_DIM * LOC_LD + 5 * ATT_DIM + 2 * (attn_v3_half(T) + LOC_K - 1) + 2 * attn_v3_half(T) +
            attn_v3_half(T) * LOC_LD + (attn_v3_half(T) + LOC_K - 1) * LOC_LD + 2 * ATTN_V2_NW * ATT_DIM + 2 * ATTN_V2_NW * ATT_DIM +
-           ATTN_V2_NT;
+           ATTN_V2_NT + (attn_v3_half(T) + LOC_K - 1) * ATTN_V3_G_LD;
 }
+// phase times of CTA 0 (TIMED instantiation only, TACO_ATTN_TIMES=1; read with b200taco_attn_bwd_phase_ns, debug header)
+__device__ unsigned long long g_attn_phase_ns[8];
+#define ATTN_T(i)                                                            \
+    if (TIMED && blockIdx.x == 0 && tid == 0) {                              \
+        const unsigned long long now_ = global_timer_ns();                   \
+        atomicAdd(&g_attn_phase_ns[i], now_ - t_prev_);                      \
+        t_prev_ = now_;                                                      \
+    }
+template <bool TIMED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_V2_NT) attention_bwd_v3_kernel(
     const float* __restrict__ w, const float* __restrict__ prev, const float* __restrict__ cum, const float* __restrict__ pq,
     const float* __restrict__ pm, const float* __restrict__ memory, float* __restrict__ dctx,
@@ -600,7 +613,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_V2_NT) attentio
     const int64_t* __restrict__ lengths, const float* __restrict__ Wloc, const float* __restrict__ Wld,
     const float* __restrict__ v, const float* __restrict__ vb_p, const float* __restrict__ escale_p,
     float* __restrict__ dctx_out, float* __restrict__ dpm, float* __restrict__ dpq, float* __restrict__ dprev_out,
-    float* __restrict__ pacc /* [2 B][ATTN_PACC] */, int B, int T) {
+    float* __restrict__ pacc /* [2 B][ATTN_PACC] */, const float* __restrict__ dctx_extra /* [B][ld_extra], nullable: added to dctx */,
+    int ld_extra, int B, int T) {
     extern __shared__ __align__(16) float sm[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
@@ -630,6 +644,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_V2_NT) attentio
     float* tile_du = dloc_s + WLh * LOC_LD;
     float* accx = tile_du + 2 * ATTN_V2_NW * ATT_DIM;
     float* red_s = accx + 2 * ATTN_V2_NW * ATT_DIM;
+    float* g_s = red_s + ATTN_V2_NT;                   // [n + 30][ATTN_V3_G_LD]
     float* dWld = pacc + (size_t)blockIdx.x * ATTN_PACC;
     float* dWloc = dWld + ATT_DIM * LOC_F;
     float* dv = dWloc + LOC_F * 2 * LOC_K;
@@ -637,9 +652,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_V2_NT) attentio
     const float* wb = w + (size_t)b * T;
     const float* pb = prev ? prev + (size_t)b * T : nullptr;
     const float* cb = cum + (size_t)b * T;
+    unsigned long long t_prev_ = TIMED ? global_timer_ns() : 0ull;
 
     for (int i = tid; i < EMB; i += ATTN_V2_NT) {
-        const float d = dctx[(size_t)b * EMB + i];
+        const float d = dctx[(size_t)b * EMB + i] + (dctx_extra ? dctx_extra[(size_t)b * ld_extra + i] : 0.f);
         dctx_s[i] = d;
         if (rank == 0) dctx_out[(size_t)b * EMB + i] = d;
     }
@@ -654,6 +670,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_V2_NT) attentio
     }
     for (int i = tid; i < n; i += ATTN_V2_NT) w_s[i] = wb[p0 + i];
     __syncthreads();
+    ATTN_T(0)                                                        // loads
 
     // (a) dw of the own positions, partial s
     float s_part = 0.f;
@@ -687,20 +704,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_V2_NT) attentio
         }
     }
     red_s[tid] = s_part;
-    // (b) location features of the own positions
-    for (int i = tid; i < n * LOC_F; i += ATTN_V2_NT) {
-        const int j = i >> 5, f = i & 31;
-        float acc = 0.f;
+    ATTN_T(1)                                                        // (a) of this thread's warp
+    // (b) location features of the own positions: lane = feature, a warp takes 8 consecutive positions at a time and slides an
+    //     8-entry window over the conv input, so one weight and ONE new input feed 8 FMAs (the first version read two shared-memory
+    //     words per FMA and was bound by that: 4.1 us)
+    for (int j0 = warp * 8; j0 < n; j0 += ATTN_V2_NW * 8) {
+        float acc[8];
 #pragma unroll
-        for (int k = 0; k < LOC_K; ++k) {
-            acc = fmaf(wloc_s[f * WLOC_LD + k], win_p[j + k], acc);
-            acc = fmaf(wloc_s[f * WLOC_LD + LOC_K + k], win_c[j + k], acc);
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            const float* win = (c == 0 ? win_p : win_c) + j0;     // reads past the own window (tail block) land in the next array; discarded
+            const float* wl = wloc_s + lane * WLOC_LD + c * LOC_K;
+            float x[8];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) x[i] = win[i];
+#pragma unroll
+            for (int kk = 0; kk < LOC_K; ++kk) {
+                x[(kk + 7) & 7] = win[kk + 7];
+                const float wv = wl[kk];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaf(wv, x[(kk + i) & 7], acc[i]);
+            }
         }
-        loc_s[j * LOC_LD + f] = acc;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (j0 + i < n) loc_s[(j0 + i) * LOC_LD + lane] = acc[i];
     }
     // halo rows of dloc that no CTA owns (positions < 0 and >= T) are zero
     for (int i = tid; i < HALO * LOC_LD; i += ATTN_V2_NT) dloc_s[(rank == 0 ? 0 : (HALO + n) * LOC_LD) + i] = 0.f;
     __syncthreads();
+    ATTN_T(2)                                                        // (b) + waiting for the slowest warp of (a)
     for (int o = ATTN_V2_NT / 2; o > 0; o >>= 1) {
         if (tid < o) red_s[tid] += red_s[tid + o];
         __syncthreads();
@@ -713,12 +747,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_V2_NT) attentio
     if (rank == 0)                                                   // consumed (the peer read it before it arrived at #1)
         for (int i = tid; i < EMB; i += ATTN_V2_NT) dctx[(size_t)b * EMB + i] = 0.f;
 
+    ATTN_T(3)                                                        // block reduction + cluster.sync #1
     // (c) per position, exactly as in the second version, over the own positions
     float dvb_part = 0.f, dscale_part = 0.f;
     float dv_r[4] = {0.f, 0.f, 0.f, 0.f}, dpq_r[4] = {0.f, 0.f, 0.f, 0.f};
     float dwld_r[ATT_DIM * LOC_F / ATTN_V2_NT];
 #pragma unroll
     for (int i = 0; i < ATT_DIM * LOC_F / ATTN_V2_NT; ++i) dwld_r[i] = 0.f;
+    // the processed-memory rows of a pass are fetched one pass ahead (an L2 round trip per pass was exposed otherwise)
+    float pmn[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            pmn[r][q] = __ldg(pm + ((size_t)b * T + p0 + min(r * ATTN_V2_NW + warp, n - 1)) * ATT_DIM + lane + 32 * q);
     for (int t0 = 0; t0 < n; t0 += 2 * ATTN_V2_NW) {
         int jj[2];
         bool ok[2];
@@ -735,9 +777,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_V2_NT) attentio
         for (int r = 0; r < 2; ++r)
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                pmv[r][q] = __ldg(pm + ((size_t)b * T + p0 + jj[r]) * ATT_DIM + lane + 32 * q);
+                pmv[r][q] = pmn[r][q];
                 lf[r][q] = 0.f;
             }
+        if (t0 + 2 * ATTN_V2_NW < n) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    pmn[r][q] = __ldg(pm + ((size_t)b * T + p0 + min(t0 + 2 * ATTN_V2_NW + r * ATTN_V2_NW + warp, n - 1)) * ATT_DIM + lane + 32 * q);
+        }
         const float4* l0 = reinterpret_cast<const float4*>(loc_s + jj[0] * LOC_LD);
         const float4* l1 = reinterpret_cast<const float4*>(loc_s + jj[1] * LOC_LD);
 #pragma unroll
@@ -772,10 +821,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_V2_NT) attentio
                 const int a = lane + 32 * q;
                 const float du = de_raw * v_s[a] * (1.f - th[r][q] * th[r][q]);
                 du_row[r][a] = du;
-                if (ok[r]) {
-                    float* dpm_p = dpm + ((size_t)b * T + p0 + jj[r]) * ATT_DIM + a;
-                    *dpm_p += du;
-                }
+                // exactly one add per element and launch (deterministic); a reduction does not make the warp wait for the old value
+                if (ok[r]) atomicAdd(dpm + ((size_t)b * T + p0 + jj[r]) * ATT_DIM + a, du);
                 dv_r[q] = fmaf(de_raw, th[r][q], dv_r[q]);
                 dpq_r[q] += du;
             }
@@ -813,6 +860,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_V2_NT) attentio
         }
         __syncthreads();
     }
+    ATTN_T(4)                                                        // (c)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         accx[warp * ATT_DIM + lane + 32 * q] = dv_r[q];
@@ -857,34 +905,63 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_V2_NT) attentio
         }
     }
     cluster.sync();                                                  // #3: halo rows in place; the peer may exit
+    ATTN_T(5)                                                        // reductions, cluster.sync #2, halo copy, cluster.sync #3
 
-    // (d) location conv backward over the own positions: dWloc[f][c][k] += sum_j dloc[j][f] * in_c[j + k - 15]
-    for (int i = tid; i < LOC_F * 2 * LOC_K; i += ATTN_V2_NT) {
-        const int k = i % LOC_K, c = (i / LOC_K) % 2, f = i / (2 * LOC_K);
-        const float* win = c == 0 ? win_p : win_c;
-        float acc = 0.f;
+    // (d) location conv backward over the own positions: dWloc[f][c][k] += sum_j dloc[j][f] * in_c[j + k - 15].
+    //     thread = (f, c, 4 consecutive taps): per position one dloc value and one NEW window value feed 4 FMAs
+    {
+        const int f = tid >> 4, c = (tid >> 3) & 1, k0 = (tid & 7) * 4;
+        const float* win = (c == 0 ? win_p : win_c) + k0;            // tap 31 does not exist: its column reads one word past the window
+        const float* dl = dloc_s + HALO * LOC_LD + f;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        float w0 = win[0], w1 = win[1], w2 = win[2];
 #pragma unroll 4
-        for (int j = 0; j < n; ++j) acc = fmaf(dloc_s[(HALO + j) * LOC_LD + f], win[j + k], acc);
-        dWloc[i] += acc;
+        for (int j = 0; j < n; ++j) {
+            const float w3 = win[j + 3];
+            const float d = dl[j * LOC_LD];
+            a0 = fmaf(d, w0, a0); a1 = fmaf(d, w1, a1); a2 = fmaf(d, w2, a2); a3 = fmaf(d, w3, a3);
+            w0 = w1; w1 = w2; w2 = w3;
+        }
+        float* o = dWloc + f * 2 * LOC_K + c * LOC_K + k0;
+        o[0] += a0; o[1] += a1; o[2] += a2;
+        if (k0 + 3 < LOC_K) o[3] += a3;
     }
-    //     d in_c[tt] = sum_k sum_f dloc[tt - k + 15][f] * Wloc[f][c][k]; rows outside [0, T) are zero rows of dloc_s
-    for (int i = tid; i < 2 * n; i += ATTN_V2_NT) {
-        const int c = i / n, j = i % n;
-        float acc = 0.f;
-        for (int k = 0; k < LOC_K; ++k) {
-            const float4* dl = reinterpret_cast<const float4*>(dloc_s + (j - k + 2 * HALO) * LOC_LD);
-            const float* wl = wloc_s + c * LOC_K + k;
+    ATTN_T(6)                                                        // dWloc
+    //     d in_c[tt] = sum_k g[tt - k + 15][c][k],  g[tau][c][k] = sum_f dloc[tau][f] * Wloc[f][c][k]: the filter column of a
+    //     thread stays in registers while it walks over the rows (halo rows included; rows outside [0, T) are zero)
+    {
+        const int ck = tid & 63, grp = tid >> 6;
+        if (ck < 2 * LOC_K) {
+            float wreg[LOC_F];
 #pragma unroll
-            for (int f4 = 0; f4 < LOC_F / 4; ++f4) {
-                const float4 d = dl[f4];
-                acc = fmaf(d.x, wl[(4 * f4 + 0) * WLOC_LD], acc); acc = fmaf(d.y, wl[(4 * f4 + 1) * WLOC_LD], acc);
-                acc = fmaf(d.z, wl[(4 * f4 + 2) * WLOC_LD], acc); acc = fmaf(d.w, wl[(4 * f4 + 3) * WLOC_LD], acc);
+            for (int f = 0; f < LOC_F; ++f) wreg[f] = wloc_s[f * WLOC_LD + ck];
+            for (int r = grp; r < n + 2 * HALO; r += 8) {
+                const float4* dl = reinterpret_cast<const float4*>(dloc_s + r * LOC_LD);
+                float acc = 0.f;
+#pragma unroll
+                for (int f4 = 0; f4 < LOC_F / 4; ++f4) {
+                    const float4 d = dl[f4];
+                    acc = fmaf(d.x, wreg[4 * f4 + 0], acc); acc = fmaf(d.y, wreg[4 * f4 + 1], acc);
+                    acc = fmaf(d.z, wreg[4 * f4 + 2], acc); acc = fmaf(d.w, wreg[4 * f4 + 3], acc);
+                }
+                g_s[r * ATTN_V3_G_LD + ck] = acc;
             }
         }
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * n; i += ATTN_V2_NT) {
+        const int c = i / n, j = i % n;
+        const float* gp = g_s + (j + 2 * HALO) * ATTN_V3_G_LD + c * LOC_K;     // row of tap 0; tap k sits k rows up, k words right
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < LOC_K; ++k) acc += gp[k - k * ATTN_V3_G_LD];
         if (c == 0) dprev_out[(size_t)b * T + p0 + j] = acc;
         else gsum[(size_t)b * T + p0 + j] += acc;
     }
+    __syncthreads();
+    ATTN_T(7)                                                        // d in_c
 }
+#undef ATTN_T
 
 // Deferred context gradient (src/model.py:147): dmemory[b][tau][d] = sum_s w[s][b][tau] * dctx[s][b][d], one 64 x 64 tile of
 // (tau, d) per CTA, all S steps reduced in the CTA (plain stores, no atomics).  w (S,B,T), dctx (S,B,512), dmemory (B,T,512).
@@ -1083,9 +1160,9 @@ int assemble_wpg(const float* wp, const float* wg, float* dst, cudaStream_t st) 
     return B200TACO_OK;
 }
 
-int lstm_cell_bwd(const float* gates, const float* c, const float* c_prev, float* dh_post, const float* mask, float scale,
+int lstm_cell_bwd(const float* gates, const float* c, const float* c_prev, float* dh_post, const float* dh_extra, int ld_extra, const float* mask, float scale,
                   float* dc, float* dz, int B, cudaStream_t st) {
-    lstm_cell_bwd_kernel<<<(B * RNN + 255) / 256, 256, 0, st>>>(gates, c, c_prev, dh_post, mask, scale, dc, dz, B);
+    lstm_cell_bwd_kernel<<<(B * RNN + 255) / 256, 256, 0, st>>>(gates, c, c_prev, dh_post, dh_extra, ld_extra, mask, scale, dc, dz, B);
     TACO_LAUNCHED();
     return B200TACO_OK;
 }
@@ -1116,6 +1193,14 @@ bool attention_bwd_defers_dmemory(int T) {
     static const bool off = [] { const char* e = getenv("TACO_ATTN_BWD_V1"); return e && e[0] == '1'; }();
     return !off && T <= ATTN_V2_MAX_T;
 }
+int attn_bwd_phase_ns(unsigned long long* out8, int reset) {
+    if (out8 != nullptr) TACO_CUDA(cudaMemcpyFromSymbol(out8, g_attn_phase_ns, sizeof(g_attn_phase_ns)));
+    if (reset) {
+        const unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        TACO_CUDA(cudaMemcpyToSymbol(g_attn_phase_ns, z, sizeof(z)));
+    }
+    return B200TACO_OK;
+}
 int ctx_dmemory(const float* w, const float* dctx_all, float* dmemory, int S, int B, int T, cudaStream_t st) {
     ctx_dmemory_kernel<<<dim3((T + 63) / 64, EMB / 64, B), 256, 0, st>>>(w, dctx_all, dmemory, S, B, T);
     TACO_LAUNCHED();
@@ -1124,21 +1209,29 @@ int ctx_dmemory(const float* w, const float* dctx_all, float* dmemory, int S, in
 int attention_bwd(const float* w, const float* prev, const float* cum, const float* pq, const float* pm, const float* memory,
                   float* dctx, const float* dw_ext, const float* dprev_next, float* gsum, const int64_t* lengths,
                   const float* Wloc, const float* Wld, const float* v, const float* vb, const float* escale, float* dmemory, float* dpm,
-                  float* dpq, float* dprev_out, float* pacc, float* scratch, float* dctx_out, int B, int T, cudaStream_t st) {
+                  float* dpq, float* dprev_out, float* pacc, float* scratch, float* dctx_out, const float* dctx_extra, int ld_extra,
+                  int B, int T, cudaStream_t st) {
     static const bool no_v3 = [] { const char* e = getenv("TACO_ATTN_BWD_V2"); return e && e[0] == '1'; }();
     if (attention_bwd_defers_dmemory(T) && T >= ATTN_V3_MIN_T && !no_v3) {
         const int smem = attn_v3_smem_floats(T) * (int)sizeof(float);
+        static const bool timed = [] { const char* e = getenv("TACO_ATTN_TIMES"); return e && e[0] == '1'; }();
         static bool configured3 = false;
         if (!configured3) {
-            TACO_CUDA(cudaFuncSetAttribute(attention_bwd_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            TACO_CUDA(cudaFuncSetAttribute(attention_bwd_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           attn_v3_smem_floats(ATTN_V2_MAX_T) * (int)sizeof(float)));
+            TACO_CUDA(cudaFuncSetAttribute(attention_bwd_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            attn_v3_smem_floats(ATTN_V2_MAX_T) * (int)sizeof(float)));
             configured3 = true;
         }
-        attention_bwd_v3_kernel<<<2 * B, ATTN_V2_NT, smem, st>>>(w, prev, cum, pq, pm, memory, dctx, dw_ext, dprev_next, gsum, lengths,
-                                                                Wloc, Wld, v, vb, escale, dctx_out, dpm, dpq, dprev_out, pacc, B, T);
+        auto kern = timed ? attention_bwd_v3_kernel<true> : attention_bwd_v3_kernel<false>;
+        kern<<<2 * B, ATTN_V2_NT, smem, st>>>(w, prev, cum, pq, pm, memory, dctx, dw_ext, dprev_next, gsum, lengths, Wloc, Wld, v, vb, escale,
+                                              dctx_out, dpm, dpq, dprev_out, pacc, dctx_extra, ld_extra, B, T);
         TACO_LAUNCHED();
         return B200TACO_OK;
     }
+    // the older kernels take the extra addend as a separate pass
+    if (dctx_extra != nullptr)
+        if (int e = train_axpy(dctx, EMB, dctx_extra, ld_extra, B, EMB, true, st)) return e;
     if (attention_bwd_defers_dmemory(T)) {
         const int smem = attn_v2_smem_floats(T) * (int)sizeof(float);
         static bool configured = false;

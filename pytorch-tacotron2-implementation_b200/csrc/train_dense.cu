@@ -345,17 +345,34 @@ size_t convbn_saved_floats(int n_rows, int c_out) { return (size_t)2 * n_rows * 
 
 // Forward of one conv + BatchNorm(train) + activation + dropout layer.  `saved` receives z [n][co], y [n][co], mean[co],
 // var[co] (biased), rstd[co]; y is also the layer output.  Wp = weights as [tap][ci][co].
+// The convolutions of the training passes run on the tensor cores (conv_tc_kernel, 3xTF32 at fp32 accuracy, dense_tc.cu)
+// when the caller supplies `wtc` (room for the pre-split weight planes, dense_tc_weight_floats) and the problem is large
+// enough to fill the machine; small problems (the golden-vector tests) keep the bit-reproducible CUDA-core kernel.
+// TACO_TRAIN_CONV_TC=0 disables it (measurements).
+int conv1d_channels_last_tc(const float* X, int ldx, const float* Wtc, const float* scale, const float* shift,
+                            const float* residual, int ldres, float* Y, int ldy, int n_rows, int seg_len, int c_in,
+                            int c_out, int taps, int act, int num_sms, cudaStream_t stream, const ChannelMajorOut& cm);
+static int train_conv(const float* X, int ldx, const float* Wp, float* wtc, const float* shift, float* Y, int ldy, int n_rows,
+                      int seg_len, int c_in, int c_out, int taps, cudaStream_t st) {
+    static const bool allow = [] { const char* e = getenv("TACO_TRAIN_CONV_TC"); return !(e && e[0] == '0'); }();
+    static const int sms = [] { int d = 0, n = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n > 0 ? n : 148; }();
+    if (allow && wtc != nullptr && n_rows >= TRAIN_CONV_TC_MIN_ROWS && dense_tc_supported(c_in, c_out, ldx, ldy)) {
+        if (int e = pack_dense_tc(wtc, Wp, taps, c_in, c_out, st)) return e;
+        return conv1d_channels_last_tc(X, ldx, wtc, nullptr, shift, nullptr, 0, Y, ldy, n_rows, seg_len, c_in, c_out, taps, ACT_NONE,
+                                       sms, st, ChannelMajorOut{});
+    }
+    return conv1d_channels_last(X, ldx, Wp, nullptr, shift, nullptr, 0, Y, ldy, n_rows, seg_len, c_in, c_out, taps, ACT_NONE, st);
+}
+
 int convbn_train_fwd(const float* X, int ldx, const float* Wp, const float* conv_b, const float* gamma, const float* beta,
                      const float* mask, float drop_scale, int act, float* saved, int n_rows, int seg_len, int c_in, int c_out,
-                     int taps, cudaStream_t st) {
+                     int taps, float* wtc, cudaStream_t st) {
     float* z = saved;
     float* y = z + (size_t)n_rows * c_out;
     float* mean = y + (size_t)n_rows * c_out;
     float* var = mean + c_out;
     float* rstd = var + c_out;
-    if (int e = conv1d_channels_last(X, ldx, Wp, nullptr, conv_b, nullptr, 0, z, c_out, n_rows, seg_len, c_in, c_out, taps,
-                                     ACT_NONE, st))
-        return e;
+    if (int e = train_conv(X, ldx, Wp, wtc, conv_b, z, c_out, n_rows, seg_len, c_in, c_out, taps, st)) return e;
     TACO_CUDA(cudaMemsetAsync(mean, 0, 3 * (size_t)c_out * sizeof(float), st));
     const dim3 grid((c_out + 31) / 32, n_rows >= 4096 ? 32 : (n_rows >= 256 ? 8 : 1));
     colreduce_kernel<0><<<grid, 256, 0, st>>>(z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1.f, 0, n_rows,
@@ -379,7 +396,7 @@ int convbn_train_fwd(const float* X, int ldx, const float* Wp, const float* conv
 int convbn_train_bwd(const float* dY, const float* X, int ldx, const float* Wp, const float* gamma, const float* beta,
                      const float* mask, float drop_scale, int act, const float* saved, float* dX, int lddx, float* dWp,
                      float* db, float* dgamma, float* dbeta, float* dz, float* wflip, int n_rows, int seg_len, int c_in,
-                     int c_out, int taps, cudaStream_t st) {
+                     int c_out, int taps, float* wtc, cudaStream_t st) {
     const float* z = saved;
     const float* mean = z + (size_t)2 * n_rows * c_out;
     const float* rstd = mean + 2 * c_out;
@@ -403,9 +420,7 @@ int convbn_train_bwd(const float* dY, const float* X, int ldx, const float* Wp, 
     if (dX != nullptr) {
         flip_transpose_kernel<<<blocks_for((size_t)taps * c_in * c_out), 256, 0, st>>>(wflip, Wp, taps, c_in, c_out);
         TACO_LAUNCHED();
-        if (int e = conv1d_channels_last(dz, c_out, wflip, nullptr, nullptr, nullptr, 0, dX, lddx, n_rows, seg_len, c_out, c_in,
-                                         taps, ACT_NONE, st))
-            return e;
+        if (int e = train_conv(dz, c_out, wflip, wtc, nullptr, dX, lddx, n_rows, seg_len, c_out, c_in, taps, st)) return e;
     }
     return B200TACO_OK;
 }
