@@ -55,9 +55,9 @@ B200TACO_API int32_t b200taco_decoder_trace(b200taco_handle* h, int64_t* out, in
 
 /*
  * Measurement aid: phase times (ns, summed over launches since the last reset) of CTA 0 of the training attention backward
- * (attention_bwd_v3_kernel) when the process runs with TACO_ATTN_TIMES=1: out8[0] loads, [1] dw / s of CTA 0's first
- * warp, [2] location features, [3] reduction + first cluster exchange, [4] per-position pass, [5] reductions + halo exchange,
- * [6] location-filter gradient, [7] location-input gradient.  Synchronises the device.
+ * (attention_bwd_v3_kernel) when the process runs with TACO_ATTN_TIMES=1: out8[0] loads of weights and saved activations, [1] location
+ * features, [2] wait for the preceding kernel + d ctx + dw / s, [3] reduction + first cluster exchange, [4] per-position pass,
+ * [5] reductions + halo exchange, [6] location-filter gradient, [7] location-input gradient.  Synchronises the device.
  */
 B200TACO_API int32_t b200taco_attn_bwd_phase_ns(uint64_t* out8, int32_t reset);
 

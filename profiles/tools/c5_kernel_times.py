@@ -71,7 +71,7 @@ def main():
         _cabi.lib().b200taco_attn_bwd_phase_ns(buf, 1)
         step()
         _cabi.lib().b200taco_attn_bwd_phase_ns(buf, 1)
-        names = ["loads", "dw + s (first warp)", "location features", "reduction + cluster exchange 1", "per-position pass",
+        names = ["loads", "location features", "wait + dctx + dw/s", "reduction + cluster exchange 1", "per-position pass",
                  "reductions + halo exchange", "location-filter gradient", "location-input gradient"]
         phase_text = "\n\nattention_bwd_v3_kernel, CTA 0, us per launch (TIMED instantiation): " + ", ".join(
             f"{n} {buf[i] / S / 1e3:.2f}" for i, n in enumerate(names)) + f"; sum {sum(buf) / S / 1e3:.2f}"

@@ -42,6 +42,25 @@ int64_t& launch_counter();
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+#ifdef __CUDACC__
+// kernel<<<grid, block, smem, st>>>(args...) with programmatic stream serialization (see pdl_wait); TACO_PDL=0 launches normally
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ------------------------------------------------------------------ device: math
 #ifdef __CUDACC__
 
@@ -140,6 +159,13 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+
+// Programmatic dependent launch (the per-step kernels of the training reverse walk): a kernel launched with launch_pdl may start
+// while its predecessor in the stream is still running; everything it does before pdl_wait() must touch only data that no kernel
+// of the chain writes (weights, saved forward activations, its own shared memory).  pdl_trigger() lets the NEXT kernel of the
+// chain be scheduled as soon as every CTA of this one is running.  Both are no-ops in a normally launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // bf16 pair (packed in one 32-bit word, element 0 in the low half) -> two floats
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }

@@ -13,6 +13,11 @@ namespace b200taco {
 
 constexpr int ATTN_PACC = ATT_DIM * LOC_F + LOC_F * 2 * LOC_K + ATT_DIM + 64;     // 4096 + 1984 + 128 + pad
 
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("TACO_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 namespace {
 
 inline int blocks_for(size_t n) { return (int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256); }
@@ -24,6 +29,8 @@ inline int blocks_for(size_t n) { return (int)((n + 255) / 256 > 4096 ? 4096 : (
 __global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c, const float* __restrict__ c_prev,
                                      float* __restrict__ dh_post, const float* __restrict__ dh_extra, int ld_extra,
                                      const float* __restrict__ mask, float scale, float* __restrict__ dc, float* __restrict__ dz, int B) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * RNN) return;
     const int b = i / RNN, u = i % RNN;
@@ -654,11 +661,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_V2_NT) attentio
     const float* cb = cum + (size_t)b * T;
     unsigned long long t_prev_ = TIMED ? global_timer_ns() : 0ull;
 
-    for (int i = tid; i < EMB; i += ATTN_V2_NT) {
-        const float d = dctx[(size_t)b * EMB + i] + (dctx_extra ? dctx_extra[(size_t)b * ld_extra + i] : 0.f);
-        dctx_s[i] = d;
-        if (rank == 0) dctx_out[(size_t)b * EMB + i] = d;
-    }
+    // ---- everything that depends only on weights and saved forward activations comes first: under programmatic dependent
+    //      launch this part (and the location features (b)) overlaps the tail of the preceding kernel of the walk
+    pdl_trigger();
     for (int i = tid; i < LOC_F * 2 * LOC_K; i += ATTN_V2_NT) wloc_s[(i / (2 * LOC_K)) * WLOC_LD + i % (2 * LOC_K)] = Wloc[i];
     for (int i = tid; i < ATT_DIM * LOC_F; i += ATTN_V2_NT) wld_s[(i / LOC_F) * LOC_LD + (i % LOC_F)] = Wld[i];
     if (tid < ATT_DIM) { v_s[tid] = v[tid]; pq_s[tid] = pq[(size_t)b * ATT_DIM + tid]; }
@@ -669,9 +674,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_V2_NT) attentio
         win_c[i] = ok ? cb[t] : 0.f;
     }
     for (int i = tid; i < n; i += ATTN_V2_NT) w_s[i] = wb[p0 + i];
+    // halo rows of dloc that no CTA owns (positions < 0 and >= T) are zero
+    for (int i = tid; i < HALO * LOC_LD; i += ATTN_V2_NT) dloc_s[(rank == 0 ? 0 : (HALO + n) * LOC_LD) + i] = 0.f;
     __syncthreads();
     ATTN_T(0)                                                        // loads
-
+    // (b) location features of the own positions: lane = feature, a warp takes 8 consecutive positions at a time and slides an
+    //     8-entry window over the conv input, so one weight and ONE new input feed 8 FMAs (the first version read two shared-memory
+    //     words per FMA and was bound by that: 4.1 us)
+    for (int j0 = warp * 8; j0 < n; j0 += ATTN_V2_NW * 8) {
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            const float* win = (c == 0 ? win_p : win_c) + j0;     // reads past the own window (tail block) land in the next array; discarded
+            const float* wl = wloc_s + lane * WLOC_LD + c * LOC_K;
+            float x[8];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) x[i] = win[i];
+#pragma unroll
+            for (int kk = 0; kk < LOC_K; ++kk) {
+                x[(kk + 7) & 7] = win[kk + 7];
+                const float wv = wl[kk];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaf(wv, x[(kk + i) & 7], acc[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (j0 + i < n) loc_s[(j0 + i) * LOC_LD + lane] = acc[i];
+    }
+    ATTN_T(1)                                                        // (b) location features
+    pdl_wait();                                                      // ---- from here on: gradients produced by the preceding kernels
+    for (int i = tid; i < EMB; i += ATTN_V2_NT) {
+        const float d = dctx[(size_t)b * EMB + i] + (dctx_extra ? dctx_extra[(size_t)b * ld_extra + i] : 0.f);
+        dctx_s[i] = d;
+        if (rank == 0) dctx_out[(size_t)b * EMB + i] = d;
+    }
+    __syncthreads();
     // (a) dw of the own positions, partial s
     float s_part = 0.f;
     for (int j0 = 2 * warp; j0 < n; j0 += 2 * ATTN_V2_NW) {
@@ -704,37 +744,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_V2_NT) attentio
         }
     }
     red_s[tid] = s_part;
-    ATTN_T(1)                                                        // (a) of this thread's warp
-    // (b) location features of the own positions: lane = feature, a warp takes 8 consecutive positions at a time and slides an
-    //     8-entry window over the conv input, so one weight and ONE new input feed 8 FMAs (the first version read two shared-memory
-    //     words per FMA and was bound by that: 4.1 us)
-    for (int j0 = warp * 8; j0 < n; j0 += ATTN_V2_NW * 8) {
-        float acc[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-            const float* win = (c == 0 ? win_p : win_c) + j0;     // reads past the own window (tail block) land in the next array; discarded
-            const float* wl = wloc_s + lane * WLOC_LD + c * LOC_K;
-            float x[8];
-#pragma unroll
-            for (int i = 0; i < 7; ++i) x[i] = win[i];
-#pragma unroll
-            for (int kk = 0; kk < LOC_K; ++kk) {
-                x[(kk + 7) & 7] = win[kk + 7];
-                const float wv = wl[kk];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] = fmaf(wv, x[(kk + i) & 7], acc[i]);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (j0 + i < n) loc_s[(j0 + i) * LOC_LD + lane] = acc[i];
-    }
-    // halo rows of dloc that no CTA owns (positions < 0 and >= T) are zero
-    for (int i = tid; i < HALO * LOC_LD; i += ATTN_V2_NT) dloc_s[(rank == 0 ? 0 : (HALO + n) * LOC_LD) + i] = 0.f;
     __syncthreads();
-    ATTN_T(2)                                                        // (b) + waiting for the slowest warp of (a)
+    ATTN_T(2)                                                        // waiting for the predecessor + dctx + (a)
     for (int o = ATTN_V2_NT / 2; o > 0; o >>= 1) {
         if (tid < o) red_s[tid] += red_s[tid + o];
         __syncthreads();
@@ -1026,6 +1037,8 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(const float* __restric
                                                           int ldw, const SkinnyOut so, int B, int K, int N, int k_per) {
     __shared__ __align__(16) float Xs[16][64 + 4];
     __shared__ __align__(16) float Ws[16][64];
+    pdl_trigger();
+    pdl_wait();
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int n0 = blockIdx.x * 64, k0 = blockIdx.y * k_per, k1 = min(K, k0 + k_per);
     float acc[4][4];
@@ -1132,7 +1145,7 @@ int skinny_gemm_multi(const float* X, int ldx, const float* W, int ldw, int B, i
     int ks = 1;
     while (ntiles * ks < want && K / (ks * 2) >= 64) ks *= 2;
     const int k_per = ((K + ks - 1) / ks + 15) / 16 * 16;
-    skinny_gemm_kernel<<<dim3(ntiles, (K + k_per - 1) / k_per), 256, 0, st>>>(X, ldx, W, ldw, so, B, K, N, k_per);
+    TACO_CUDA(launch_pdl(skinny_gemm_kernel, dim3(ntiles, (K + k_per - 1) / k_per), dim3(256), 0, st, X, ldx, W, ldw, so, B, K, N, k_per));
     TACO_LAUNCHED();
     return B200TACO_OK;
 }
@@ -1162,7 +1175,8 @@ int assemble_wpg(const float* wp, const float* wg, float* dst, cudaStream_t st) 
 
 int lstm_cell_bwd(const float* gates, const float* c, const float* c_prev, float* dh_post, const float* dh_extra, int ld_extra, const float* mask, float scale,
                   float* dc, float* dz, int B, cudaStream_t st) {
-    lstm_cell_bwd_kernel<<<(B * RNN + 255) / 256, 256, 0, st>>>(gates, c, c_prev, dh_post, dh_extra, ld_extra, mask, scale, dc, dz, B);
+    TACO_CUDA(launch_pdl(lstm_cell_bwd_kernel, dim3((B * RNN + 255) / 256), dim3(256), 0, st, gates, c, c_prev, dh_post, dh_extra, ld_extra, mask,
+                         scale, dc, dz, B));
     TACO_LAUNCHED();
     return B200TACO_OK;
 }
@@ -1224,8 +1238,8 @@ int attention_bwd(const float* w, const float* prev, const float* cum, const flo
             configured3 = true;
         }
         auto kern = timed ? attention_bwd_v3_kernel<true> : attention_bwd_v3_kernel<false>;
-        kern<<<2 * B, ATTN_V2_NT, smem, st>>>(w, prev, cum, pq, pm, memory, dctx, dw_ext, dprev_next, gsum, lengths, Wloc, Wld, v, vb, escale,
-                                              dctx_out, dpm, dpq, dprev_out, pacc, dctx_extra, ld_extra, B, T);
+        TACO_CUDA(launch_pdl(kern, dim3(2 * B), dim3(ATTN_V2_NT), smem, st, w, prev, cum, pq, pm, memory, dctx, dw_ext, dprev_next, gsum, lengths, Wloc,
+                             Wld, v, vb, escale, dctx_out, dpm, dpq, dprev_out, pacc, dctx_extra, ld_extra, B, T));
         TACO_LAUNCHED();
         return B200TACO_OK;
     }

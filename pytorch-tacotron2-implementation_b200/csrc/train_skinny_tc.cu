@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
     const int k0 = c0 * ST_K;
     const int iters = c1 - c0;
 
+    pdl_trigger();
     if (tid == 0) {
         for (int s = 0; s < ST_STAGES; ++s) {
             mbar_init(&full[s], 4 + 1);                      // four loader warps + the weight producer's expect_tx arrive
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
                 }
             }
         };
+        pdl_wait();               // dZ comes from the preceding kernel; barriers, TMEM and the first weight tiles are set up by now
         if (grp < iters) fetch(grp);
         for (int it = grp; it < iters; it += ST_GROUPS) {
             const int stage = it % ST_STAGES;
@@ -273,7 +275,7 @@ int skinny_gemm_multi_tc(const float* X, int ldx, const void* Wp, int B, int K, 
         TACO_CUDA(cudaFuncSetAttribute(skinny_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_TOTAL));
         attr = true;
     }
-    skinny_tc_kernel<<<dim3(ntiles, ks), ST_THREADS, ST_TOTAL, st>>>(X, ldx, static_cast<const __nv_bfloat16*>(Wp), so, B, K);
+    TACO_CUDA(launch_pdl(skinny_tc_kernel, dim3(ntiles, ks), dim3(ST_THREADS), ST_TOTAL, st, X, ldx, static_cast<const __nv_bfloat16*>(Wp), so, B, K));
     TACO_LAUNCHED();
     return B200TACO_OK;
 }
