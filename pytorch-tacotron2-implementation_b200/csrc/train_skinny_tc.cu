@@ -37,6 +37,10 @@ constexpr int ST_GROUPS = 4;                   // loader groups: group g fills t
 constexpr int ST_LOADERS = 4 * ST_GROUPS;
 constexpr int ST_THREADS = (ST_LOADERS + 2) * 32;
 constexpr int ST_NACC = 4;
+// A loader group goes from iteration it to it + ST_GROUPS after the stage of it - ST_STAGES was released; the parity wait on the next
+// stage is only unambiguous if the release of it + ST_GROUPS - 2 ST_STAGES has happened by then, i.e. ST_GROUPS <= ST_STAGES (with 4
+// groups on 3 stages a group ran two phases ahead, passed the wait on the "preceding phase" and over-arrived on the full barrier).
+static_assert(ST_GROUPS <= ST_STAGES, "loader groups may not outnumber the pipeline stages");
 constexpr int ST_RED_LD = ST_N + 1;            // row stride of the epilogue tile: lanes = rows on the way in, = columns on the way out
 static_assert(128 * ST_RED_LD * 4 <= ST_STAGES * ST_STAGE, "the epilogue tile reuses the pipeline stages");
 
