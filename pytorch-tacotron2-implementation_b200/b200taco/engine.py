@@ -417,8 +417,12 @@ class Engine:
             launches.append(cur_l)
         self.last_stream_steps = 0
         for members in launches:
+            # queue order inside a launch: LONGEST text first.  A row takes the next utterance when its own stops, so the launch
+            # ends with every row on one of the shortest utterances and the idle tail (rows waiting for the last ones to stop) is
+            # half a SHORT utterance per row instead of half a long one (5 % -> 1 % of a 1024-utterance launch).
+            members = members[::-1]
             n_real = len(members)
-            members = members + [members[k % n_real] for k in range((-n_real) % rows)]      # fill the last rows
+            members = members + [members[n_real - 1 - k % n_real] for k in range((-n_real) % rows)]   # fill the last rows (shortest)
             N, Tmax = len(members), max(lens[i] for i in members)
             mem = torch.zeros(N, Tmax, config.encoder_embedding_dim, dtype=torch.float32, device=dev)
             by_len = {}
@@ -430,7 +434,7 @@ class Engine:
                     ids = torch.stack([utterances[i] for _, i in part]).to(dev, non_blocking=True)
                     mem[torch.tensor([s_ for s_, _ in part], device=dev), :T_i] = self.encoder(ids)
             if N > n_real:
-                mem[n_real:] = mem[torch.tensor([k % n_real for k in range(N - n_real)], device=dev)]
+                mem[n_real:] = mem[torch.tensor([n_real - 1 - k % n_real for k in range(N - n_real)], device=dev)]
             tl = torch.tensor([lens[i] for i in members], dtype=torch.int64)
             mel, gate, align, len_h = self.decoder_infer_stream(mem, rows, max_steps, gate_threshold, text_lengths=tl)
             done_ev = torch.cuda.Event()
