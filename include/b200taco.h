@@ -172,6 +172,17 @@ B200TACO_API int32_t b200taco_encoder_fwd(b200taco_handle* h, const int64_t* d_i
                              float* d_memory, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * The same for a batch of utterances of DIFFERENT lengths padded to T: row b of d_memory, positions [0, d_lengths[b]), is what
+ * Encoder.forward returns for that utterance ALONE at its exact length - the reference's inference encodes one unpadded
+ * utterance at a time (inference.py:66, F8: no text lengths, no packing) - and is zero behind it.  The convolutions see zeros
+ * behind an utterance's length at every layer, the reverse LSTM direction starts at its last position.
+ * d_ids (B,T) int64 (anything behind the lengths), d_lengths (B) int32 in [1, T].
+ */
+B200TACO_API int32_t b200taco_encoder_fwd_ragged(b200taco_handle* h, const int64_t* d_ids, const int32_t* d_lengths, int32_t B,
+                                                 int32_t T, float* d_memory, void* d_workspace, size_t workspace_bytes,
+                                                 void* stream);
+
+/*
  * Decoder.inference, src/model.py:299-333, as one persistent kernel: the discarded first
  * step, the frame loop and the stop rule all run on the device.
  *   d_memory (B,T,512); max_steps = min(max_decoder_steps, max_len_cap)

@@ -68,6 +68,8 @@ SIGNATURES = {
     "b200taco_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     "b200taco_encoder_fwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b200taco_encoder_fwd_ragged": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                                C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200taco_decoder_infer": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                            C.c_int32, C.c_float, C.c_int32,
                                            C.c_void_p, C.c_void_p, C.c_void_p,

@@ -200,27 +200,48 @@ B200TACO_API size_t b200taco_workspace_bytes(const b200taco_handle* h, int32_t B
     return need;
 }
 
+static int encoder_run(b200taco_handle* h, const int64_t* d_ids, const int32_t* d_lengths, int B, int T, float* d_memory,
+                       void* d_workspace, size_t workspace_bytes, cudaStream_t st) {
+    const EncoderWs ws = encoder_ws(d_workspace, B, T);
+    TACO_REQUIRE(workspace_bytes >= ws.total, B200TACO_ERR_STATE, "encoder workspace too small: %zu < %zu", workspace_bytes,
+                 ws.total);
+    const int n = B * T;
+    TACO_TRY(embedding_gather(d_ids, h->enc_emb, ws.x0, n, st));
+    // ragged batch: what lies behind an utterance's own length is ZERO at the input of every convolution, like the zero padding
+    // of its exact-length solo run (the padded ids would otherwise leak into its last two positions per layer)
+    ChannelMajorOut tail{};
+    tail.lengths = d_lengths;
+    tail.zero_tail = d_lengths != nullptr;
+    if (d_lengths != nullptr) TACO_TRY(zero_tail_rows(ws.x0, EMB, d_lengths, B, T, EMB, st));
+    float* src = ws.x0;
+    float* dst = ws.x1;
+    for (int i = 0; i < ENC_CONVS; ++i) {
+        TACO_TRY(dense_layer(h, src, EMB, h->enc_conv_w[i], h->enc_conv_wtc[i], h->enc_conv_scale[i], h->enc_conv_shift[i], nullptr, 0,
+                                      dst, EMB, n, T, EMB, EMB, ENC_KERNEL, ACT_RELU, true, st, tail));
+        float* t = src; src = dst; dst = t;
+    }
+    TACO_TRY(dense_layer(h, src, EMB, h->enc_lstm_wih, h->enc_lstm_wih_tc, nullptr, h->enc_lstm_bias, nullptr, 0, ws.xproj, 8 * ENC_H, n,
+                                  n, EMB, 8 * ENC_H, 1, ACT_NONE, true, st));
+    TACO_TRY(bilstm_recurrence(h, ws.xproj, d_memory, B, T, st, d_lengths));
+    if (d_lengths != nullptr) TACO_TRY(zero_tail_rows(d_memory, EMB, d_lengths, B, T, EMB, st));
+    return B200TACO_OK;
+}
+
 B200TACO_API int32_t b200taco_encoder_fwd(b200taco_handle* h, const int64_t* d_ids, int32_t B, int32_t T, float* d_memory,
                              void* d_workspace, size_t workspace_bytes, void* stream) {
     TACO_TRY(check_handle(h, true));
     TACO_TRY(check_shape(B, T));
     TACO_REQUIRE(d_ids && d_memory && d_workspace, B200TACO_ERR_INVALID, "encoder_fwd: null pointer");
-    const EncoderWs ws = encoder_ws(d_workspace, B, T);
-    TACO_REQUIRE(workspace_bytes >= ws.total, B200TACO_ERR_STATE, "encoder workspace too small: %zu < %zu", workspace_bytes,
-                 ws.total);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int n = B * T;
-    TACO_TRY(embedding_gather(d_ids, h->enc_emb, ws.x0, n, st));
-    float* src = ws.x0;
-    float* dst = ws.x1;
-    for (int i = 0; i < ENC_CONVS; ++i) {
-        TACO_TRY(dense_layer(h, src, EMB, h->enc_conv_w[i], h->enc_conv_wtc[i], h->enc_conv_scale[i], h->enc_conv_shift[i], nullptr, 0,
-                                      dst, EMB, n, T, EMB, EMB, ENC_KERNEL, ACT_RELU, true, st));
-        float* t = src; src = dst; dst = t;
-    }
-    TACO_TRY(dense_layer(h, src, EMB, h->enc_lstm_wih, h->enc_lstm_wih_tc, nullptr, h->enc_lstm_bias, nullptr, 0, ws.xproj, 8 * ENC_H, n,
-                                  n, EMB, 8 * ENC_H, 1, ACT_NONE, true, st));
-    return bilstm_recurrence(h, ws.xproj, d_memory, B, T, st);
+    return encoder_run(h, d_ids, nullptr, B, T, d_memory, d_workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+B200TACO_API int32_t b200taco_encoder_fwd_ragged(b200taco_handle* h, const int64_t* d_ids, const int32_t* d_lengths, int32_t B,
+                                                 int32_t T, float* d_memory, void* d_workspace, size_t workspace_bytes,
+                                                 void* stream) {
+    TACO_TRY(check_handle(h, true));
+    TACO_TRY(check_shape(B, T));
+    TACO_REQUIRE(d_ids && d_lengths && d_memory && d_workspace, B200TACO_ERR_INVALID, "encoder_fwd_ragged: null pointer");
+    return encoder_run(h, d_ids, d_lengths, B, T, d_memory, d_workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 static int run_decoder(b200taco_handle* h, int mode, const float* d_memory, const float* d_mel_targets,

@@ -10,6 +10,11 @@
 //   * h_{t-1} (256 x 8) sits in shared memory of every CTA, double buffered; after the
 //     cell update each CTA scatters its 32 x 8 new h values into all 8 CTAs through
 //     distributed shared memory, then one cluster barrier ends the step.
+//
+// Ragged batches (lengths != null, b200taco_encoder_fwd_ragged): every utterance is run over ITS OWN positions [0, len) - the
+// reverse direction starts at len - 1 with the zero state - which is exactly its exact-length solo run (the reference's
+// inference encodes one unpadded utterance at a time, inference.py:66); a cluster walks max(len) of its 8 utterances and rows
+// behind an utterance's length are not written (the caller zeroes them).
 #include <cooperative_groups.h>
 
 #include "handle.h"
@@ -28,7 +33,7 @@ constexpr int KH = ENC_H / 2;      // 128 k per thread
 
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256, 1)
     bilstm_kernel(const float* __restrict__ whh /* [2][8][128][256] */, const float* __restrict__ xproj /* [B*T][2048] */,
-                  float* __restrict__ out /* [B][T][512] */, int B, int T) {
+                  float* __restrict__ out /* [B][T][512] */, const int32_t* __restrict__ lengths /* [B] or null */, int B, int T) {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = cluster.block_rank();
     const int cid = blockIdx.x / CL;            // cluster index: direction-major
@@ -55,15 +60,22 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256, 1)
     // cell role: thread (unit = tid/8, utterance = tid%8)
     const int cu = tid >> 3, cb = tid & 7;
     const bool cvalid = b0 + cb < B;
+    const int len_b = cvalid ? (lengths ? min(T, max(0, (int)lengths[b0 + cb])) : T) : 0;
+    int steps = T;
+    if (lengths) {                              // the same value in every CTA of the cluster
+        steps = 0;
+        for (int b = b0; b < min(B, b0 + BG); ++b) steps = max(steps, min(T, max(0, (int)lengths[b])));
+    }
     float c_state = 0.f;
     cluster.sync();
 
-    for (int step = 0; step < T; ++step) {
-        const int t = dir ? T - 1 - step : step;
+    for (int step = 0; step < steps; ++step) {
+        const int t = dir ? len_b - 1 - step : step;
+        const bool active = step < len_b;       // an utterance that ran out of positions idles (its h column is read by nobody else)
         const int cur = step & 1, nxt = cur ^ 1;
         // input projection of this position (independent of h: issue the loads first)
         float xin[4] = {0.f, 0.f, 0.f, 0.f};
-        if (cvalid) {
+        if (active) {
             const float* xp = xproj + ((size_t)(b0 + cb) * T + t) * (8 * ENC_H) + dir * 4 * ENC_H + rank * UPC + cu;
 #pragma unroll
             for (int g = 0; g < 4; ++g) xin[g] = __ldg(xp + g * ENC_H);
@@ -92,7 +104,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256, 1)
         __syncthreads();
         // LSTM cell, gate order i,f,g,o (rows of a unit are unit*4 + gate)
         float h = 0.f;
-        if (cvalid) {
+        if (active) {
             const float zi = z_s[cu * 4 + 0][cb] + xin[0];
             const float zf = z_s[cu * 4 + 1][cb] + xin[1];
             const float zg = z_s[cu * 4 + 2][cb] + xin[2];
@@ -111,9 +123,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256, 1)
 
 }  // namespace
 
-int bilstm_recurrence(const b200taco_handle* h, const float* xproj, float* memory, int B, int T, cudaStream_t stream) {
+int bilstm_recurrence(const b200taco_handle* h, const float* xproj, float* memory, int B, int T, cudaStream_t stream,
+                      const int32_t* lengths) {
     const int ngroups = (B + BG - 1) / BG;
-    bilstm_kernel<<<2 * ngroups * CL, 256, 0, stream>>>(h->enc_lstm_whh, xproj, memory, B, T);
+    bilstm_kernel<<<2 * ngroups * CL, 256, 0, stream>>>(h->enc_lstm_whh, xproj, memory, lengths, B, T);
     TACO_LAUNCHED();
     return B200TACO_OK;
 }

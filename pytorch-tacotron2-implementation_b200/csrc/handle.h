@@ -93,8 +93,8 @@ int vocoder_layout(const float* mel, int ldm, const int32_t* lengths, int B, int
 int zero_tail_rows(float* Y, int ldy, const int32_t* lengths, int B, int S, int C, cudaStream_t stream);
 
 // bilstm.cu
-int bilstm_recurrence(const b200taco_handle* h, const float* xproj, float* memory, int B, int T,
-                      cudaStream_t stream);
+int bilstm_recurrence(const b200taco_handle* h, const float* xproj, float* memory, int B, int T, cudaStream_t stream,
+                      const int32_t* lengths = nullptr);
 
 // decoder.cu
 struct DecoderArgs {

@@ -60,6 +60,31 @@ def test_encoder_golden():
     assert util.maxdiff(mem.cpu(), util.golden("encoder_b3_t19")["memory"]) <= 2e-6
 
 
+@pytest.mark.parametrize("n_utts,lo,hi", [(5, 3, 30), (19, 12, 48), (64, 100, 150)])
+def test_ragged_encoder_equals_exact_length_solo_runs(n_utts, lo, hi):
+    """b200taco_encoder_fwd_ragged: utterances of different lengths padded into one batch; every row must be BIT FOR BIT what the
+    encoder returns for that utterance alone at its exact length (the reference's inference encodes one unpadded utterance at a
+    time), and zero behind its length - whatever the padded ids are.  The solo run itself is held to the oracle."""
+    sd = util.weights()
+    eng = gpu_model(sd)._get_engine()
+    g = torch.Generator().manual_seed(n_utts)
+    lens = torch.randint(lo, hi + 1, (n_utts,), generator=g)
+    lens[0] = hi
+    T = int(lens.max())
+    utts = [synth.phoneme_ids(1, int(L), seed=700 + i)[0] for i, L in enumerate(lens)]
+    ids = torch.randint(0, 70, (n_utts, T), generator=g)                      # garbage behind every utterance's length
+    for i, u in enumerate(utts):
+        ids[i, :len(u)] = u
+    mem = eng.encoder(ids.cuda(), lengths=lens.cuda())
+    for i, u in enumerate(utts):
+        solo = eng.encoder(u[None].cuda())
+        L = len(u)
+        assert torch.equal(mem[i, :L], solo[0]), (i, L, util.maxdiff(mem[i, :L].cpu(), solo[0].cpu()))
+        assert not mem[i, L:].any()
+    ref = O.encoder(sd, utts[1][None])
+    assert util.maxdiff(mem[1, :len(utts[1])].cpu(), ref[0]) <= 2e-6
+
+
 def test_postnet_golden():
     m = gpu_model(util.weights())
     g = torch.Generator().manual_seed(11)
