@@ -582,7 +582,6 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
     FT_RESET();
     for (int item = rev ? ncta - 1 - cta : cta; item < B * NS; item += ncta) {
         const int b = item / NS, sl = item % NS;
-        const int t0 = sl * SL, t1 = min(T, t0 + SL);
         // continuous batching: row b carries utterance mb since decode step rows[ROW_START + b]; its first step sees
         // zero previous / cumulative attention weights (src/model.py:104-115); a retired row repeats its last
         // utterance without writing anything the host reads
@@ -602,6 +601,11 @@ __device__ __forceinline__ void attention_phase(const KParams& p, float* red, co
         // for its own positions plus the reach of the location convolution (15; those positions are masked, get weight 0 and
         // keep the windows behind the last real position zero); whatever lies further back can only influence masked
         // positions.  The output buffers of a continuous-batching launch are zero initialised by the caller.
+        // The NS slices of a ragged utterance split ITS OWN span evenly (not the launch's padded T): the phase ends with the slowest
+        // CTA, and with the queue sorted by length the live utterances are of similar length at any time.
+        int SLu = SL;
+        if (rows != nullptr && p.text_lengths != nullptr) SLu = (min(T, len + 16) + NS - 1) / NS;
+        const int t0 = sl * SLu, t1 = min(T, t0 + SLu);
         int n = max(0, t1 - t0);
         if (rows != nullptr && p.text_lengths != nullptr) n = max(0, min(n, len + 16 - t0));
         const size_t align_row = (size_t)(rows != nullptr ? rows[ROW_ABASE + b] : b) + (size_t)(oi < 0 ? 0 : oi) * B;
