@@ -362,18 +362,18 @@ C5_TFLOP = 7.55                     # fwd + bwd of one C5 step
 
 
 def bench_c4(model, synth, dev, rank, world, dist, n_utts=C4_UTTS, rows=C4_ROWS):
-    """BASELINE config 4: the corpus is sorted by text length and its exact-length groups are dealt round-robin to the ranks
+    """BASELINE config 4: the corpus is sorted by text length and dealt utterance by utterance to the ranks
     (every rank sees the same length distribution: strong scaling without a collective); each rank streams its share through persistent launches of 64
     live rows, utterances of different lengths side by side (ragged continuous batching), at least ~16 refills per row and
     launch (an utterance shorter than the launch's padded length only pays for its own positions).  Timed on the device, max over ranks; frames = sum of the decoded lengths of all utterances."""
     import random
     rng = random.Random(0)
     lens = [rng.randint(50, 250) for _ in range(n_utts)]
-    # whole exact-length groups per rank, lengths dealt round-robin (b200taco.shard.deal_length_groups): dealing single
-    # utterances round-robin left every rank with all 201 lengths, i.e. 201 small encoder launches per rank whatever N
-    # (37 % of the time at N=8)
+    # the length-sorted corpus dealt utterance by utterance in snake order (b200taco.shard.deal_sorted): the ranks' summed lengths
+    # agree to 0.06 %.  (Before the encoder took ragged batches an utterance was encoded in a batch of its own exact length, and
+    # whole exact-length groups had to go to one rank - shard.deal_length_groups, 4.2 % imbalance.)
     from b200taco import shard
-    mine = shard.deal_length_groups(lens, world, rank)
+    mine = shard.deal_sorted(lens, world, rank)
     corpus = {i: synth.phoneme_ids(1, lens[i], seed=i)[0] for i in mine}
     n_launch = max(1, min(4, len(mine) // (16 * rows)))           # >= ~16 refills per row and launch: the drain of a launch is fixed
     per_launch = (len(mine) + n_launch - 1) // n_launch
@@ -402,7 +402,7 @@ def bench_c4(model, synth, dev, rank, world, dist, n_utts=C4_UTTS, rows=C4_ROWS)
         sm = agg.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         agg = torch.stack([mx[0], sm[1], sm[2]])
     ms, frames, steps = float(agg[0]), float(agg[1]), float(agg[2])
-    return {"workload": f"C4: {n_utts} utterances, T~U{{50..250}}, exact-length groups dealt round-robin over {world} rank(s), ragged "
+    return {"workload": f"C4: {n_utts} utterances, T~U{{50..250}}, length-sorted corpus dealt in snake order over {world} rank(s), ragged "
                         f"continuous batching with {rows} live rows, {n_launch} launch(es) per rank",
             "metric": "mel frames/sec (sharded corpus)", "value": frames / (ms * 1e-3), "unit": UNIT, "scaling": "strong",
             "seconds": ms * 1e-3, "frames": int(frames), "utterances": n_utts, "mean_frames_per_utterance": frames / n_utts,

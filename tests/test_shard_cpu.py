@@ -121,3 +121,22 @@ def test_length_groups_are_dealt_whole_and_balanced(world):
             assert min(lens[i] for i in s_) < 60 and max(lens[i] for i in s_) > 240
     with pytest.raises(ValueError):
         shard.deal_length_groups(lens, world, world)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_sorted_snake_dealing_is_a_balanced_partition(world):
+    """Sharding used by bench.py's C4 leg since the encoder takes ragged batches: every utterance on exactly one rank, counts
+    within one, summed text lengths within 0.5 %, every share sorted by length and spanning the whole range, deterministic."""
+    lens = corpus_lengths()
+    shares = [shard.deal_sorted(lens, world, r) for r in range(world)]
+    assert sorted(i for s_ in shares for i in s_) == list(range(len(lens)))
+    counts = [len(s_) for s_ in shares]
+    work = [sum(lens[i] for i in s_) for s_ in shares]
+    assert max(counts) - min(counts) <= 1 and max(work) <= 1.005 * min(work)
+    for s_ in shares:
+        assert [lens[i] for i in s_] == sorted(lens[i] for i in s_)
+        if world > 1:
+            assert min(lens[i] for i in s_) < 60 and max(lens[i] for i in s_) > 240
+    assert shares == [shard.deal_sorted(list(lens), world, r) for r in range(world)]
+    with pytest.raises(ValueError):
+        shard.deal_sorted(lens, world, -1)
