@@ -44,9 +44,10 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 #ifdef __CUDACC__
 // kernel<<<grid, block, smem, st>>>(args...) with programmatic stream serialization (see pdl_wait); TACO_PDL=0 launches normally
-bool pdl_enabled();
+bool pdl_enabled(int which);
+enum PdlKernel { PDL_CELL = 0, PDL_SKINNY_TC = 1, PDL_ATTENTION = 2, PDL_SKINNY = 3 };
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+inline cudaError_t launch_pdl(int which, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -56,7 +57,7 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = pdl_enabled(which) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 #endif

@@ -33,7 +33,7 @@ int embedding_bwd(const int64_t* ids, const float* dx, float* dE, int n, cudaStr
 
 // train_decoder.cu
 int lstm_cell_bwd(const float* gates, const float* c, const float* c_prev, float* dh_post, const float* dh_extra, int ld_extra, const float* mask, float scale,
-                  float* dc, float* dz, int B, cudaStream_t st);
+                  float* dc, float* dz, void* dz_tiles, int B, cudaStream_t st);
 int attn_cumsum(const float* align, float* cum, int S, int BT, cudaStream_t st);
 int train_axpy(float* dst, int ld_dst, const float* a, int ld_a, int n, int cols, bool accumulate, cudaStream_t st);
 int relu_drop_bwd(const float* dy, const float* y, const float* mask, float scale, float* dx, size_t n, cudaStream_t st);
@@ -52,7 +52,8 @@ constexpr int ATTN_PACC_F = ATT_DIM * LOC_F + LOC_F * 2 * LOC_K + ATT_DIM + 64;
 size_t skinny_tc_packed_bytes(int K, int N);
 bool skinny_tc_supported(int B, int K, int N, int nseg, const int* n_ends);
 int pack_skinny_tc(void* dst, const float* W, int ldw, int K, int N, cudaStream_t st);
-int skinny_gemm_multi_tc(const float* X, int ldx, const void* Wp, int B, int K, int nseg, float* const* outs, const int* ldos,
+size_t skinny_tc_act_bytes(int K);
+int skinny_gemm_multi_tc(const void* Xp, const void* Wp, int B, int K, int nseg, float* const* outs, const int* ldos,
                          const int* n_ends, const bool* acc, cudaStream_t st);
 int skinny_gemm(const float* X, int ldx, const float* W, int ldw, float* out, int ldo, int B, int K, int N, bool accumulate,
                 cudaStream_t st);
@@ -308,7 +309,7 @@ B200TACO_API int32_t b200taco_encoder_train_bwd(b200taco_handle* h, const b200ta
 namespace {
 struct DecScratch {
     size_t dout, wpg, wqT, dzd, dza, dpq, dp, d_ah, d_dh, d_ctx, dca, dcd, tmp, tmp2, pq, P, gsum, cum, dpm, attn, dw, dvs, wcat_d, wcat_a, dctx_all,
-        wpk_d, wpk_a, dproj, total;
+        wpk_d, wpk_a, dproj, dzt, total;
 };
 DecScratch dec_scratch(int B, int T, int S) {
     DecScratch d{};
@@ -343,6 +344,7 @@ DecScratch dec_scratch(int B, int T, int S) {
     d.wpk_d = take((size_t)4 * RNN * (2 * RNN + EMB) / 2);       // the same two matrices as bf16 UMMA tiles (train_skinny_tc.cu)
     d.wpk_a = take((size_t)4 * RNN * (PRENET + EMB + RNN) / 2);
     d.dproj = take(n * (RNN + EMB));              // gradient of the projection inputs [dh_t | ctx_t] of every step (one dense call)
+    d.dzt = take(2 * skinny_tc_act_bytes(4 * RNN) / sizeof(float));   // this step's gate gradients of both cells as hi/lo bf16 UMMA tiles
     d.total = off;
     return d;
 }
@@ -400,7 +402,10 @@ B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200ta
     const int ends_d[3] = {RNN, RNN + EMB, ND}, ends_a[3] = {PRENET, PRENET + EMB, NA};
     const bool tc_skinny = h->weight_dtype == 0 && skinny_tc_supported(B, 4 * RNN, ND, 3, ends_d) && skinny_tc_supported(B, 4 * RNN, NA, 3, ends_a);
     void *wpk_d = sc + X.wpk_d, *wpk_a = sc + X.wpk_a;
+    void* dzt_d = tc_skinny ? static_cast<void*>(sc + X.dzt) : nullptr;
+    void* dzt_a = tc_skinny ? static_cast<void*>(reinterpret_cast<uint8_t*>(sc + X.dzt) + skinny_tc_act_bytes(4 * RNN)) : nullptr;
     if (tc_skinny) {
+        TACO_CUDA(cudaMemsetAsync(sc + X.dzt, 0, 2 * skinny_tc_act_bytes(4 * RNN), st));     // rows >= B of the tiles stay zero
         TT(pack_skinny_tc(wpk_d, wcat_d, ND, 4 * RNN, ND, st));
         TT(pack_skinny_tc(wpk_a, wcat_a, NA, 4 * RNN, NA, st));
     }
@@ -427,12 +432,12 @@ B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200ta
         // decoder LSTM cell (input [ah_t | ctx_t], src/model.py:265-270)
         float* dzd_t = dzd + r * 4 * RNN;
         TT(lstm_cell_bwd(gd + r * 4 * RNN, cd + r * RNN, t > 0 ? cd + (r - B) * RNN : nullptr, d_dh, dproj_t, RNN + EMB, d_mask_d ? d_mask_d + r * RNN : nullptr,
-                         lstm_scale, dcd, dzd_t, B, st));
+                         lstm_scale, dcd, dzd_t, dzt_d, B, st));
         {   // d ah_t +=, d ctx_t +=, d dh_{t-1} =
             float* outs[3] = {d_ah, d_ctx, d_dh};
             const int ldos[3] = {RNN, EMB, RNN}, ends[3] = {RNN, RNN + EMB, ND};
             const bool acc[3] = {true, true, true};
-            if (tc_skinny) TT(skinny_gemm_multi_tc(dzd_t, 4 * RNN, wpk_d, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
+            if (tc_skinny) TT(skinny_gemm_multi_tc(dzt_d, wpk_d, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
             else TT(skinny_gemm_multi(dzd_t, 4 * RNN, wcat_d, ND, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
         }
         // attention (src/model.py:117-148)
@@ -445,12 +450,12 @@ B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200ta
         // attention LSTM cell (input [p_t | ctx_{t-1}], src/model.py:256-262)
         float* dza_t = dza + r * 4 * RNN;
         TT(lstm_cell_bwd(ga + r * 4 * RNN, ca + r * RNN, t > 0 ? ca + (r - B) * RNN : nullptr, d_ah, nullptr, 0, d_mask_a ? d_mask_a + r * RNN : nullptr,
-                         lstm_scale, dca, dza_t, B, st));
+                         lstm_scale, dca, dza_t, dzt_a, B, st));
         {   // d p_t =, d ctx_{t-1} =, d ah_{t-1} =
             float* outs[3] = {dp + r * PRENET, d_ctx, d_ah};
             const int ldos[3] = {PRENET, EMB, RNN}, ends[3] = {PRENET, PRENET + EMB, NA};
             const bool acc[3] = {true, v2, true};
-            if (tc_skinny) TT(skinny_gemm_multi_tc(dza_t, 4 * RNN, wpk_a, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
+            if (tc_skinny) TT(skinny_gemm_multi_tc(dzt_a, wpk_a, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
             else TT(skinny_gemm_multi(dza_t, 4 * RNN, wcat_a, NA, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
         }
     }

@@ -6,6 +6,7 @@
 #include <cstdlib>
 
 #include "handle.h"
+#include "umma.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -13,9 +14,10 @@ namespace b200taco {
 
 constexpr int ATTN_PACC = ATT_DIM * LOC_F + LOC_F * 2 * LOC_K + ATT_DIM + 64;     // 4096 + 1984 + 128 + pad
 
-bool pdl_enabled() {
-    static const bool on = [] { const char* e = getenv("TACO_PDL"); return !(e && e[0] == '0'); }();
-    return on;
+// TACO_PDL = bit mask of the kernels launched with programmatic stream serialization (PdlKernel; measurements), default all
+bool pdl_enabled(int which) {
+    static const int mask = [] { const char* e = getenv("TACO_PDL"); return e ? atoi(e) : 15; }();
+    return (mask >> which) & 1;
 }
 
 namespace {
@@ -28,9 +30,10 @@ inline int blocks_for(size_t n) { return (int)((n + 255) / 256 > 4096 ? 4096 : (
 // dh_extra [B][ld_extra] (nullable): a second addend of dh_post that is not carried (the projection's gradient of this step).
 __global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c, const float* __restrict__ c_prev,
                                      float* __restrict__ dh_post, const float* __restrict__ dh_extra, int ld_extra,
-                                     const float* __restrict__ mask, float scale, float* __restrict__ dc, float* __restrict__ dz, int B) {
-    pdl_trigger();
+                                     const float* __restrict__ mask, float scale, float* __restrict__ dc, float* __restrict__ dz,
+                                     __nv_bfloat16* __restrict__ dzp, int B) {
     pdl_wait();
+    pdl_trigger();          // only now: the NEXT kernel of the chain may start its set-up while this one works (run-ahead of one kernel)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * RNN) return;
     const int b = i / RNN, u = i % RNN;
@@ -42,11 +45,23 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, const floa
     const float dct = dc[i] + dh * go * (1.f - tc * tc);
     const float cp = c_prev ? c_prev[i] : 0.f;
     float* d4 = dz + (size_t)b * 4 * RNN + u;
-    d4[0] = dct * gg * gi * (1.f - gi);
-    d4[RNN] = dct * cp * gf * (1.f - gf);
-    d4[2 * RNN] = dct * gi * (1.f - gg * gg);
-    d4[3 * RNN] = dh * tc * go * (1.f - go);
+    const float dzv[4] = {dct * gg * gi * (1.f - gi), dct * cp * gf * (1.f - gf), dct * gi * (1.f - gg * gg), dh * tc * go * (1.f - go)};
+#pragma unroll
+    for (int g = 0; g < 4; ++g) d4[g * RNN] = dzv[g];
     dc[i] = dct * gf;
+    // second copy for the tensor-core data-gradient GEMM that follows (skinny_tc_kernel): hi/lo bf16, rows b and 64 + b of the
+    // M = 128 operand, as UMMA K-major tiles [k / 64][128 x 64] that the TMA engine copies straight into its pipeline stages
+    if (dzp != nullptr) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int k = g * RNN + u;
+            __nv_bfloat16 hi, lo;
+            umma::split_bf16(dzv[g], hi, lo);
+            __nv_bfloat16* tile = dzp + (size_t)(k >> 6) * (128 * 64);
+            tile[umma::tile_offset(b, k & 63, 8)] = hi;
+            tile[umma::tile_offset(64 + b, k & 63, 8)] = lo;
+        }
+    }
 }
 
 // cum[t] = sum_{tau < t} align[tau]  (exclusive prefix sum over the step axis), one thread per (b, position)
@@ -662,8 +677,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_V2_NT) attentio
     unsigned long long t_prev_ = TIMED ? global_timer_ns() : 0ull;
 
     // ---- everything that depends only on weights and saved forward activations comes first: under programmatic dependent
-    //      launch this part (and the location features (b)) overlaps the tail of the preceding kernel of the walk
-    pdl_trigger();
+    //      launch this part (and the location features (b)) overlaps the preceding kernel of the walk
     for (int i = tid; i < LOC_F * 2 * LOC_K; i += ATTN_V2_NT) wloc_s[(i / (2 * LOC_K)) * WLOC_LD + i % (2 * LOC_K)] = Wloc[i];
     for (int i = tid; i < ATT_DIM * LOC_F; i += ATTN_V2_NT) wld_s[(i / LOC_F) * LOC_LD + (i % LOC_F)] = Wld[i];
     if (tid < ATT_DIM) { v_s[tid] = v[tid]; pq_s[tid] = pq[(size_t)b * ATT_DIM + tid]; }
@@ -706,6 +720,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_V2_NT) attentio
     }
     ATTN_T(1)                                                        // (b) location features
     pdl_wait();                                                      // ---- from here on: gradients produced by the preceding kernels
+    pdl_trigger();
     for (int i = tid; i < EMB; i += ATTN_V2_NT) {
         const float d = dctx[(size_t)b * EMB + i] + (dctx_extra ? dctx_extra[(size_t)b * ld_extra + i] : 0.f);
         dctx_s[i] = d;
@@ -1037,8 +1052,8 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(const float* __restric
                                                           int ldw, const SkinnyOut so, int B, int K, int N, int k_per) {
     __shared__ __align__(16) float Xs[16][64 + 4];
     __shared__ __align__(16) float Ws[16][64];
-    pdl_trigger();
     pdl_wait();
+    pdl_trigger();          // only now: the NEXT kernel of the chain may start its set-up while this one works (run-ahead of one kernel)
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int n0 = blockIdx.x * 64, k0 = blockIdx.y * k_per, k1 = min(K, k0 + k_per);
     float acc[4][4];
@@ -1145,7 +1160,7 @@ int skinny_gemm_multi(const float* X, int ldx, const float* W, int ldw, int B, i
     int ks = 1;
     while (ntiles * ks < want && K / (ks * 2) >= 64) ks *= 2;
     const int k_per = ((K + ks - 1) / ks + 15) / 16 * 16;
-    TACO_CUDA(launch_pdl(skinny_gemm_kernel, dim3(ntiles, (K + k_per - 1) / k_per), dim3(256), 0, st, X, ldx, W, ldw, so, B, K, N, k_per));
+    TACO_CUDA(launch_pdl(PDL_SKINNY, skinny_gemm_kernel, dim3(ntiles, (K + k_per - 1) / k_per), dim3(256), 0, st, X, ldx, W, ldw, so, B, K, N, k_per));
     TACO_LAUNCHED();
     return B200TACO_OK;
 }
@@ -1174,9 +1189,10 @@ int assemble_wpg(const float* wp, const float* wg, float* dst, cudaStream_t st) 
 }
 
 int lstm_cell_bwd(const float* gates, const float* c, const float* c_prev, float* dh_post, const float* dh_extra, int ld_extra, const float* mask, float scale,
-                  float* dc, float* dz, int B, cudaStream_t st) {
-    TACO_CUDA(launch_pdl(lstm_cell_bwd_kernel, dim3((B * RNN + 255) / 256), dim3(256), 0, st, gates, c, c_prev, dh_post, dh_extra, ld_extra, mask,
-                         scale, dc, dz, B));
+                  float* dc, float* dz, void* dz_tiles, int B, cudaStream_t st) {
+    TACO_REQUIRE(dz_tiles == nullptr || B <= 64, B200TACO_ERR_INVALID, "lstm_cell_bwd: tile image needs B <= 64");
+    TACO_CUDA(launch_pdl(PDL_CELL, lstm_cell_bwd_kernel, dim3((B * RNN + 255) / 256), dim3(256), 0, st, gates, c, c_prev, dh_post, dh_extra, ld_extra, mask,
+                         scale, dc, dz, static_cast<__nv_bfloat16*>(dz_tiles), B));
     TACO_LAUNCHED();
     return B200TACO_OK;
 }
@@ -1238,7 +1254,7 @@ int attention_bwd(const float* w, const float* prev, const float* cum, const flo
             configured3 = true;
         }
         auto kern = timed ? attention_bwd_v3_kernel<true> : attention_bwd_v3_kernel<false>;
-        TACO_CUDA(launch_pdl(kern, dim3(2 * B), dim3(ATTN_V2_NT), smem, st, w, prev, cum, pq, pm, memory, dctx, dw_ext, dprev_next, gsum, lengths, Wloc,
+        TACO_CUDA(launch_pdl(PDL_ATTENTION, kern, dim3(2 * B), dim3(ATTN_V2_NT), smem, st, w, prev, cum, pq, pm, memory, dctx, dw_ext, dprev_next, gsum, lengths, Wloc,
                              Wld, v, vb, escale, dctx_out, dpm, dpq, dprev_out, pacc, dctx_extra, ld_extra, B, T));
         TACO_LAUNCHED();
         return B200TACO_OK;
