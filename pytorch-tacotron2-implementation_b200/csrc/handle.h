@@ -141,4 +141,17 @@ int measure_sync_costs(long long* out8_host, cudaStream_t stream);
 int measure_stream_probe(void* d_buf, size_t per_cta, int ctas, int iters, int mode, int chunk, int depth, float* gbps_per_sm,
                          cudaStream_t stream);
 
+// train_decoder.cu
+// What follows the attention backward in the reverse walk, fused into its tail when `Wq` is set: the query layer's data gradient
+// d ah_t += dpq_t . Wq (src/model.py:123) and the pointwise backward of the attention-LSTM cell (both CTAs of the pair hold the
+// summed dpq; CTA r takes the units [512 r, 512 r + 512) of its utterance, one per thread) - two kernels less in the chain.
+struct AttnCellTail {
+    const float* Wq;            // (128, 1024) query_layer.weight, null = not fused
+    float* d_ah;                // [B][1024] carried gradient of the attention hidden state (consumed: zeroed)
+    const float *gates, *c, *c_prev, *mask;
+    float scale;
+    float *dc, *dz;
+    __nv_bfloat16* dzp;
+};
+
 }  // namespace b200taco

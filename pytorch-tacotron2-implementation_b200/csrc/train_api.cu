@@ -42,8 +42,9 @@ int attention_bwd(const float* w, const float* prev, const float* cum, const flo
                   float* dctx, const float* dw_ext, const float* dprev_next, float* gsum, const int64_t* lengths,
                   const float* Wloc, const float* Wld, const float* v, const float* vb, const float* escale, float* dmemory,
                   float* dpm, float* dpq, float* dprev_out, float* pacc, float* scratch, float* dctx_out,
-                  const float* dctx_extra, int ld_extra, int B, int T, cudaStream_t st);
+                  const float* dctx_extra, int ld_extra, const AttnCellTail* tail, int B, int T, cudaStream_t st);
 bool attention_bwd_defers_dmemory(int T);
+bool attention_bwd_fuses_cell(int T);
 int attn_bwd_phase_ns(unsigned long long* out8, int reset);
 int skinny_gemm_multi(const float* X, int ldx, const float* W, int ldw, int B, int K, int nseg, float* const* outs, const int* ldos,
                       const int* n_ends, const bool* acc, cudaStream_t st);
@@ -420,6 +421,7 @@ B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200ta
     // The consumers of the carried gradients (LSTM-cell backward: d ah / d dh; second attention backward: d ctx) zero them
     // after reading, so the data-gradient GEMM that follows accumulates the previous step's gradient without a memset.
     const bool v2 = attention_bwd_defers_dmemory(T);
+    const bool fuse_cell = attention_bwd_fuses_cell(T);
     TACO_CUDA(cudaMemsetAsync(gsum, 0, (size_t)BT * sizeof(float), st));
     TACO_CUDA(cudaMemsetAsync(dpm, 0, (size_t)BT * ATT_DIM * sizeof(float), st));
     TACO_CUDA(cudaMemsetAsync(d_dmemory, 0, (size_t)BT * EMB * sizeof(float), st));
@@ -440,17 +442,23 @@ B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200ta
             if (tc_skinny) TT(skinny_gemm_multi_tc(dzt_d, wpk_d, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
             else TT(skinny_gemm_multi(dzd_t, 4 * RNN, wcat_d, ND, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
         }
-        // attention (src/model.py:117-148)
+        // attention (src/model.py:117-148); with the cluster kernel its tail also does the query layer's data gradient and the
+        // pointwise backward of the attention-LSTM cell (input [p_t | ctx_{t-1}], src/model.py:256-262)
+        float* dza_t = dza + r * 4 * RNN;
+        AttnCellTail tail{};
+        tail.Wq = w->attn_query_w; tail.d_ah = d_ah; tail.gates = ga + r * 4 * RNN; tail.c = ca + r * RNN;
+        tail.c_prev = t > 0 ? ca + (r - B) * RNN : nullptr; tail.mask = d_mask_a ? d_mask_a + r * RNN : nullptr; tail.scale = lstm_scale;
+        tail.dc = dca; tail.dz = dza_t; tail.dzp = static_cast<__nv_bfloat16*>(dzt_a);
         TT(attention_bwd(d_align + r * T, t > 0 ? d_align + (r - B) * T : nullptr, cum + r * T, pq + r * ATT_DIM, pm, d_memory, d_ctx,
                          d_dalign ? d_dalign + r * T : nullptr, t < S - 1 ? P + (size_t)((t + 1) & 1) * BT : nullptr, gsum,
                          d_text_lengths, w->attn_loc_conv_w, w->attn_loc_dense_w, w->attn_v_w, w->attn_v_b, w->attn_energy_scale,
                          d_dmemory, dpm, dpq + r * ATT_DIM, P + (size_t)(t & 1) * BT, dvs, attn, dctx_all + r * EMB, dproj_t + RNN, RNN + EMB,
-                         B, T, st));
-        TT(skinny_gemm(dpq + r * ATT_DIM, ATT_DIM, w->attn_query_w, RNN, d_ah, RNN, B, ATT_DIM, RNN, true, st));
-        // attention LSTM cell (input [p_t | ctx_{t-1}], src/model.py:256-262)
-        float* dza_t = dza + r * 4 * RNN;
-        TT(lstm_cell_bwd(ga + r * 4 * RNN, ca + r * RNN, t > 0 ? ca + (r - B) * RNN : nullptr, d_ah, nullptr, 0, d_mask_a ? d_mask_a + r * RNN : nullptr,
-                         lstm_scale, dca, dza_t, dzt_a, B, st));
+                         fuse_cell ? &tail : nullptr, B, T, st));
+        if (!fuse_cell) {
+            TT(skinny_gemm(dpq + r * ATT_DIM, ATT_DIM, w->attn_query_w, RNN, d_ah, RNN, B, ATT_DIM, RNN, true, st));
+            TT(lstm_cell_bwd(ga + r * 4 * RNN, ca + r * RNN, t > 0 ? ca + (r - B) * RNN : nullptr, d_ah, nullptr, 0, d_mask_a ? d_mask_a + r * RNN : nullptr,
+                             lstm_scale, dca, dza_t, dzt_a, B, st));
+        }
         {   // d p_t =, d ctx_{t-1} =, d ah_{t-1} =
             float* outs[3] = {dp + r * PRENET, d_ctx, d_ah};
             const int ldos[3] = {PRENET, EMB, RNN}, ends[3] = {PRENET, PRENET + EMB, NA};

@@ -24,23 +24,14 @@ namespace {
 
 inline int blocks_for(size_t n) { return (int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256); }
 
-// ---- LSTMCell backward (pointwise part).  gates [B][4096] = i,f,g,o post-activation (gate*1024 + unit), c [B][1024],
-// c_prev [B][1024] or null (zero state), dh_post [B][1024] = gradient w.r.t. the (dropped) hidden state, mask or null,
-// dc [B][1024] carried cell gradient (in/out), dz [B][4096] gradient w.r.t. the gate pre-activations (out).
-// dh_extra [B][ld_extra] (nullable): a second addend of dh_post that is not carried (the projection's gradient of this step).
-__global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c, const float* __restrict__ c_prev,
-                                     float* __restrict__ dh_post, const float* __restrict__ dh_extra, int ld_extra,
-                                     const float* __restrict__ mask, float scale, float* __restrict__ dc, float* __restrict__ dz,
-                                     __nv_bfloat16* __restrict__ dzp, int B) {
-    pdl_wait();
-    pdl_trigger();          // only now: the NEXT kernel of the chain may start its set-up while this one works (run-ahead of one kernel)
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * RNN) return;
-    const int b = i / RNN, u = i % RNN;
+// One (utterance, unit) of the LSTMCell backward: dh = gradient w.r.t. the hidden state BEFORE dropout.  Shared by
+// lstm_cell_bwd_kernel and the tail of attention_bwd_v3_kernel.
+__device__ __forceinline__ void lstm_cell_bwd_unit(const float* __restrict__ gates, const float* __restrict__ c,
+                                                   const float* __restrict__ c_prev, float dh, float* __restrict__ dc,
+                                                   float* __restrict__ dz, __nv_bfloat16* __restrict__ dzp, int b, int u) {
+    const int i = b * RNN + u;
     const float* g4 = gates + (size_t)b * 4 * RNN + u;
     const float gi = g4[0], gf = g4[RNN], gg = g4[2 * RNN], go = g4[3 * RNN];
-    const float dh = (dh_post[i] + (dh_extra ? dh_extra[(size_t)b * ld_extra + u] : 0.f)) * (mask ? mask[i] * scale : 1.f);
-    dh_post[i] = 0.f;          // consumed: the data-gradient GEMM that follows accumulates the previous step's gradient onto it
     const float tc = tanhf(c[i]);
     const float dct = dc[i] + dh * go * (1.f - tc * tc);
     const float cp = c_prev ? c_prev[i] : 0.f;
@@ -62,6 +53,24 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, const floa
             tile[umma::tile_offset(64 + b, k & 63, 8)] = lo;
         }
     }
+}
+
+// ---- LSTMCell backward (pointwise part).  gates [B][4096] = i,f,g,o post-activation (gate*1024 + unit), c [B][1024],
+// c_prev [B][1024] or null (zero state), dh_post [B][1024] = gradient w.r.t. the (dropped) hidden state, mask or null,
+// dc [B][1024] carried cell gradient (in/out), dz [B][4096] gradient w.r.t. the gate pre-activations (out).
+// dh_extra [B][ld_extra] (nullable): a second addend of dh_post that is not carried (the projection's gradient of this step).
+__global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c, const float* __restrict__ c_prev,
+                                     float* __restrict__ dh_post, const float* __restrict__ dh_extra, int ld_extra,
+                                     const float* __restrict__ mask, float scale, float* __restrict__ dc, float* __restrict__ dz,
+                                     __nv_bfloat16* __restrict__ dzp, int B) {
+    pdl_wait();
+    pdl_trigger();          // only now: the NEXT kernel of the chain may start its set-up while this one works (run-ahead of one kernel)
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * RNN) return;
+    const int b = i / RNN, u = i % RNN;
+    const float dh = (dh_post[i] + (dh_extra ? dh_extra[(size_t)b * ld_extra + u] : 0.f)) * (mask ? mask[i] * scale : 1.f);
+    dh_post[i] = 0.f;          // consumed: the data-gradient GEMM that follows accumulates the previous step's gradient onto it
+    lstm_cell_bwd_unit(gates, c, c_prev, dh, dc, dz, dzp, b, u);
 }
 
 // cum[t] = sum_{tau < t} align[tau]  (exclusive prefix sum over the step axis), one thread per (b, position)
@@ -610,6 +619,7 @@ __global__ void __launch_bounds__(ATTN_V2_NT) attention_bwd_v2_kernel(
 //     cluster.sync #2; cluster.sync #3 keeps the peer resident until they are read).
 // Parameter-gradient partials go to accumulator slice 2 b + r (2 B slices, summed once after the walk).  T >= ATTN_V3_MIN_T.
 constexpr int ATTN_V3_MIN_T = 48;
+static_assert(2 * ATTN_V2_NT == RNN, "fused cell tail: one thread of the CTA pair per attention-LSTM unit");
 constexpr int ATTN_V3_G_LD = 2 * LOC_K + 3;      // odd row stride of the g[tau][c][k] tile (location-input gradient)
 static_assert(ATTN_V2_NT == LOC_F * 2 * 8 && 8 * 4 >= LOC_K, "dWloc mapping: thread = (feature, channel, group of 4 taps)");
 static_assert(ATTN_V2_NT == 8 * 64 && 2 * LOC_K <= 64 && LOC_F == 32, "g mapping: thread = (row group, channel-tap)");
@@ -636,7 +646,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_V2_NT) attentio
     const float* __restrict__ v, const float* __restrict__ vb_p, const float* __restrict__ escale_p,
     float* __restrict__ dctx_out, float* __restrict__ dpm, float* __restrict__ dpq, float* __restrict__ dprev_out,
     float* __restrict__ pacc /* [2 B][ATTN_PACC] */, const float* __restrict__ dctx_extra /* [B][ld_extra], nullable: added to dctx */,
-    int ld_extra, int B, int T) {
+    int ld_extra, const AttnCellTail tail, int B, int T) {
     extern __shared__ __align__(16) float sm[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
@@ -900,8 +910,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_V2_NT) attentio
 #pragma unroll
         for (int ww = 0; ww < ATTN_V2_NW; ++ww) acc += accx[(which * ATTN_V2_NW + ww) * ATT_DIM + a];
         if (which == 0) dv[a] += acc;
-        else if (rank == 0) own_dpq[a] = acc;
-        else cluster.map_shared_rank(xch_dpq, 0)[a] = acc;
+        else {
+            own_dpq[a] = acc;
+            if (rank == 1 || tail.Wq != nullptr) cluster.map_shared_rank(xch_dpq, rank ^ 1)[a] = acc;
+        }
     }
     if (tid == 0) {
         float acc = 0.f;
@@ -922,6 +934,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_V2_NT) attentio
 
     cluster.sync();                                                  // #2: dloc of both halves complete, dpq partial delivered
     if (rank == 0 && tid < ATT_DIM) dpq[(size_t)b * ATT_DIM + tid] = own_dpq[tid] + xch_dpq[tid];
+    if (tail.Wq != nullptr) {
+        // the same sum on both CTAs (CTA 0's partial first), then this thread's unit of the query^T product and of the cell
+        const int u = rank * ATTN_V2_NT + tid;
+        float q = 0.f;
+        const float* wq = tail.Wq + u;
+#pragma unroll 8
+        for (int a = 0; a < ATT_DIM; ++a) {
+            const float d = rank == 0 ? own_dpq[a] + xch_dpq[a] : xch_dpq[a] + own_dpq[a];
+            q = fmaf(d, __ldg(wq + (size_t)a * RNN), q);
+        }
+        const int i = b * RNN + u;
+        const float dh = (tail.d_ah[i] + q) * (tail.mask ? tail.mask[i] * tail.scale : 1.f);
+        tail.d_ah[i] = 0.f;
+        lstm_cell_bwd_unit(tail.gates, tail.c, tail.c_prev, dh, tail.dc, tail.dz, tail.dzp, b, u);
+    }
     {   // the 15 rows next to the cut come from the peer: CTA 0 needs the peer's first rows, CTA 1 the last rows of CTA 0
         const float* peer = cluster.map_shared_rank(dloc_s, rank ^ 1);
         const int src_row = rank == 0 ? HALO : Th, dst_row = rank == 0 ? HALO + n : 0;
@@ -1223,6 +1250,12 @@ bool attention_bwd_defers_dmemory(int T) {
     static const bool off = [] { const char* e = getenv("TACO_ATTN_BWD_V1"); return e && e[0] == '1'; }();
     return !off && T <= ATTN_V2_MAX_T;
 }
+// true when attention_bwd runs the cluster kernel for this T, i.e. when the caller may hand it the query^T / cell tail
+bool attention_bwd_fuses_cell(int T) {
+    static const bool no_v3 = [] { const char* e = getenv("TACO_ATTN_BWD_V2"); return e && e[0] == '1'; }();
+    static const bool no_fuse = [] { const char* e = getenv("TACO_ATTN_FUSE_CELL"); return e && e[0] == '0'; }();
+    return attention_bwd_defers_dmemory(T) && T >= ATTN_V3_MIN_T && !no_v3 && !no_fuse;
+}
 int attn_bwd_phase_ns(unsigned long long* out8, int reset) {
     if (out8 != nullptr) TACO_CUDA(cudaMemcpyFromSymbol(out8, g_attn_phase_ns, sizeof(g_attn_phase_ns)));
     if (reset) {
@@ -1240,7 +1273,7 @@ int attention_bwd(const float* w, const float* prev, const float* cum, const flo
                   float* dctx, const float* dw_ext, const float* dprev_next, float* gsum, const int64_t* lengths,
                   const float* Wloc, const float* Wld, const float* v, const float* vb, const float* escale, float* dmemory, float* dpm,
                   float* dpq, float* dprev_out, float* pacc, float* scratch, float* dctx_out, const float* dctx_extra, int ld_extra,
-                  int B, int T, cudaStream_t st) {
+                  const AttnCellTail* tail, int B, int T, cudaStream_t st) {
     static const bool no_v3 = [] { const char* e = getenv("TACO_ATTN_BWD_V2"); return e && e[0] == '1'; }();
     if (attention_bwd_defers_dmemory(T) && T >= ATTN_V3_MIN_T && !no_v3) {
         const int smem = attn_v3_smem_floats(T) * (int)sizeof(float);
@@ -1255,10 +1288,11 @@ int attention_bwd(const float* w, const float* prev, const float* cum, const flo
         }
         auto kern = timed ? attention_bwd_v3_kernel<true> : attention_bwd_v3_kernel<false>;
         TACO_CUDA(launch_pdl(PDL_ATTENTION, kern, dim3(2 * B), dim3(ATTN_V2_NT), smem, st, w, prev, cum, pq, pm, memory, dctx, dw_ext, dprev_next, gsum, lengths, Wloc,
-                             Wld, v, vb, escale, dctx_out, dpm, dpq, dprev_out, pacc, dctx_extra, ld_extra, B, T));
+                             Wld, v, vb, escale, dctx_out, dpm, dpq, dprev_out, pacc, dctx_extra, ld_extra, tail ? *tail : AttnCellTail{}, B, T));
         TACO_LAUNCHED();
         return B200TACO_OK;
     }
+    TACO_REQUIRE(tail == nullptr, B200TACO_ERR_STATE, "attention_bwd: the fused cell tail needs the cluster kernel (attention_bwd_fuses_cell)");
     // the older kernels take the extra addend as a separate pass
     if (dctx_extra != nullptr)
         if (int e = train_axpy(dctx, EMB, dctx_extra, ld_extra, B, EMB, true, st)) return e;
