@@ -152,6 +152,15 @@ struct AttnCellTail {
     float scale;
     float *dc, *dz;
     __nv_bfloat16* dzp;
+    // second cell, optional (gates2 != null): the DECODER-LSTM cell backward of the PREVIOUS decode step t - 1.  Its input d dh_{t-1}
+    // was completed by the data-gradient GEMM that precedes this kernel, so it needs nothing this kernel computes; it rides along
+    // to take one more kernel out of the chain.  dh2 [B][1024] carried (consumed: zeroed), dh2_extra [B][ld2] the projection's share.
+    float* dh2;
+    const float* dh2_extra;
+    int ld2;
+    const float *gates2, *c2, *c_prev2, *mask2;
+    float *dc2, *dz2;
+    __nv_bfloat16* dzp2;
 };
 
 }  // namespace b200taco

@@ -54,6 +54,9 @@ size_t skinny_tc_packed_bytes(int K, int N);
 bool skinny_tc_supported(int B, int K, int N, int nseg, const int* n_ends);
 int pack_skinny_tc(void* dst, const float* W, int ldw, int K, int N, cudaStream_t st);
 size_t skinny_tc_act_bytes(int K);
+int skinny_gemm_pair_tc(const void* Xp0, const void* Wp0, int nseg0, float* const* outs0, const int* ldos0, const int* n_ends0, const bool* acc0,
+                        const void* Xp1, const void* Wp1, int nseg1, float* const* outs1, const int* ldos1, const int* n_ends1, const bool* acc1,
+                        int B, int K, cudaStream_t st);
 int skinny_gemm_multi_tc(const void* Xp, const void* Wp, int B, int K, int nseg, float* const* outs, const int* ldos,
                          const int* n_ends, const bool* acc, cudaStream_t st);
 int skinny_gemm(const float* X, int ldx, const float* W, int ldw, float* out, int ldo, int B, int K, int N, bool accumulate,
@@ -422,25 +425,40 @@ B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200ta
     // after reading, so the data-gradient GEMM that follows accumulates the previous step's gradient without a memset.
     const bool v2 = attention_bwd_defers_dmemory(T);
     const bool fuse_cell = attention_bwd_fuses_cell(T);
+    static const bool pair_gemm = [] { const char* e = getenv("TACO_SKINNY_PAIR"); return !(e && e[0] == '0'); }();
     TACO_CUDA(cudaMemsetAsync(gsum, 0, (size_t)BT * sizeof(float), st));
     TACO_CUDA(cudaMemsetAsync(dpm, 0, (size_t)BT * ATT_DIM * sizeof(float), st));
     TACO_CUDA(cudaMemsetAsync(d_dmemory, 0, (size_t)BT * EMB * sizeof(float), st));
     TACO_CUDA(cudaMemsetAsync(dvs, 0, ((size_t)2 * B * ATTN_PACC_F + ATTN_PACC_F) * sizeof(float), st));
 
     // ---- reverse walk over the decode steps
+    // decoder LSTM of step t (input [ah_t | ctx_t], src/model.py:265-270): cell backward (the projection's share of d dh_t comes from
+    // dproj) and the data gradients d ah_t +=, d ctx_t +=, d dh_{t-1} =.  With the fused tail the cell backward of step t - 1 rides
+    // in the attention backward of step t (its input is complete once the data-gradient GEMM of step t is), and the GEMM of step
+    // t - 1 follows the attention-LSTM GEMM of step t: three kernels per decode step.
+    auto dec_cell = [&](int t) -> int {
+        const size_t r = (size_t)t * B;
+        return lstm_cell_bwd(gd + r * 4 * RNN, cd + r * RNN, t > 0 ? cd + (r - B) * RNN : nullptr, d_dh, dproj + r * (RNN + EMB), RNN + EMB,
+                             d_mask_d ? d_mask_d + r * RNN : nullptr, lstm_scale, dcd, dzd + r * 4 * RNN, dzt_d, B, st);
+    };
+    auto dec_gemm = [&](int t) -> int {
+        const size_t r = (size_t)t * B;
+        float* outs[3] = {d_ah, d_ctx, d_dh};
+        const int ldos[3] = {RNN, EMB, RNN}, ends[3] = {RNN, RNN + EMB, ND};
+        const bool acc[3] = {true, true, true};
+        if (tc_skinny) return skinny_gemm_multi_tc(dzt_d, wpk_d, B, 4 * RNN, 3, outs, ldos, ends, acc, st);
+        return skinny_gemm_multi(dzd + r * 4 * RNN, 4 * RNN, wcat_d, ND, B, 4 * RNN, 3, outs, ldos, ends, acc, st);
+    };
+    if (fuse_cell) {
+        TT(dec_cell(S - 1));
+        TT(dec_gemm(S - 1));
+    }
     for (int t = S - 1; t >= 0; --t) {
         const size_t r = (size_t)t * B;                       // first row of step t in the [S*B][...] buffers
         const float* dproj_t = dproj + r * (RNN + EMB);
-        // decoder LSTM cell (input [ah_t | ctx_t], src/model.py:265-270)
-        float* dzd_t = dzd + r * 4 * RNN;
-        TT(lstm_cell_bwd(gd + r * 4 * RNN, cd + r * RNN, t > 0 ? cd + (r - B) * RNN : nullptr, d_dh, dproj_t, RNN + EMB, d_mask_d ? d_mask_d + r * RNN : nullptr,
-                         lstm_scale, dcd, dzd_t, dzt_d, B, st));
-        {   // d ah_t +=, d ctx_t +=, d dh_{t-1} =
-            float* outs[3] = {d_ah, d_ctx, d_dh};
-            const int ldos[3] = {RNN, EMB, RNN}, ends[3] = {RNN, RNN + EMB, ND};
-            const bool acc[3] = {true, true, true};
-            if (tc_skinny) TT(skinny_gemm_multi_tc(dzt_d, wpk_d, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
-            else TT(skinny_gemm_multi(dzd_t, 4 * RNN, wcat_d, ND, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
+        if (!fuse_cell) {
+            TT(dec_cell(t));
+            TT(dec_gemm(t));
         }
         // attention (src/model.py:117-148); with the cluster kernel its tail also does the query layer's data gradient and the
         // pointwise backward of the attention-LSTM cell (input [p_t | ctx_{t-1}], src/model.py:256-262)
@@ -449,6 +467,12 @@ B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200ta
         tail.Wq = w->attn_query_w; tail.d_ah = d_ah; tail.gates = ga + r * 4 * RNN; tail.c = ca + r * RNN;
         tail.c_prev = t > 0 ? ca + (r - B) * RNN : nullptr; tail.mask = d_mask_a ? d_mask_a + r * RNN : nullptr; tail.scale = lstm_scale;
         tail.dc = dca; tail.dz = dza_t; tail.dzp = static_cast<__nv_bfloat16*>(dzt_a);
+        if (t > 0) {                                          // decoder-LSTM cell backward of step t - 1
+            const size_t r1 = r - B;
+            tail.dh2 = d_dh; tail.dh2_extra = dproj + r1 * (RNN + EMB); tail.ld2 = RNN + EMB; tail.gates2 = gd + r1 * 4 * RNN;
+            tail.c2 = cd + r1 * RNN; tail.c_prev2 = t > 1 ? cd + (r1 - B) * RNN : nullptr; tail.mask2 = d_mask_d ? d_mask_d + r1 * RNN : nullptr;
+            tail.dc2 = dcd; tail.dz2 = dzd + r1 * 4 * RNN; tail.dzp2 = static_cast<__nv_bfloat16*>(dzt_d);
+        }
         TT(attention_bwd(d_align + r * T, t > 0 ? d_align + (r - B) * T : nullptr, cum + r * T, pq + r * ATT_DIM, pm, d_memory, d_ctx,
                          d_dalign ? d_dalign + r * T : nullptr, t < S - 1 ? P + (size_t)((t + 1) & 1) * BT : nullptr, gsum,
                          d_text_lengths, w->attn_loc_conv_w, w->attn_loc_dense_w, w->attn_v_w, w->attn_v_b, w->attn_energy_scale,
@@ -459,12 +483,21 @@ B200TACO_API int32_t b200taco_decoder_train_bwd(b200taco_handle* h, const b200ta
             TT(lstm_cell_bwd(ga + r * 4 * RNN, ca + r * RNN, t > 0 ? ca + (r - B) * RNN : nullptr, d_ah, nullptr, 0, d_mask_a ? d_mask_a + r * RNN : nullptr,
                              lstm_scale, dca, dza_t, dzt_a, B, st));
         }
-        {   // d p_t =, d ctx_{t-1} =, d ah_{t-1} =
+        {   // d p_t =, d ctx_{t-1} =, d ah_{t-1} =   (and, fused walk: the decoder LSTM's d ah_{t-1} +=, d ctx_{t-1} +=, d dh_{t-2} = of step
+            // t - 1 in the same launch: the two GEMMs are independent once both cell backwards ran in the attention kernel)
             float* outs[3] = {dp + r * PRENET, d_ctx, d_ah};
             const int ldos[3] = {PRENET, EMB, RNN}, ends[3] = {PRENET, PRENET + EMB, NA};
             const bool acc[3] = {true, v2, true};
-            if (tc_skinny) TT(skinny_gemm_multi_tc(dzt_a, wpk_a, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
-            else TT(skinny_gemm_multi(dza_t, 4 * RNN, wcat_a, NA, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
+            float* outs_d[3] = {d_ah, d_ctx, d_dh};
+            const int ldos_d[3] = {RNN, EMB, RNN}, ends_dd[3] = {RNN, RNN + EMB, ND};
+            const bool acc_d[3] = {true, true, true};
+            if (fuse_cell && t > 0 && tc_skinny && pair_gemm) {
+                TT(skinny_gemm_pair_tc(dzt_a, wpk_a, 3, outs, ldos, ends, acc, dzt_d, wpk_d, 3, outs_d, ldos_d, ends_dd, acc_d, B, 4 * RNN, st));
+            } else {
+                if (tc_skinny) TT(skinny_gemm_multi_tc(dzt_a, wpk_a, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
+                else TT(skinny_gemm_multi(dza_t, 4 * RNN, wcat_a, NA, B, 4 * RNN, 3, outs, ldos, ends, acc, st));
+                if (fuse_cell && t > 0) TT(dec_gemm(t - 1));
+            }
         }
     }
 

@@ -948,6 +948,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ATTN_V2_NT) attentio
         const float dh = (tail.d_ah[i] + q) * (tail.mask ? tail.mask[i] * tail.scale : 1.f);
         tail.d_ah[i] = 0.f;
         lstm_cell_bwd_unit(tail.gates, tail.c, tail.c_prev, dh, tail.dc, tail.dz, tail.dzp, b, u);
+        if (tail.gates2 != nullptr) {
+            const float dh2 = (tail.dh2[i] + (tail.dh2_extra ? tail.dh2_extra[(size_t)b * tail.ld2 + u] : 0.f)) *
+                              (tail.mask2 ? tail.mask2[i] * tail.scale : 1.f);
+            tail.dh2[i] = 0.f;
+            lstm_cell_bwd_unit(tail.gates2, tail.c2, tail.c_prev2, dh2, tail.dc2, tail.dz2, tail.dzp2, b, u);
+        }
     }
     {   // the 15 rows next to the cut come from the peer: CTA 0 needs the peer's first rows, CTA 1 the last rows of CTA 0
         const float* peer = cluster.map_shared_rank(dloc_s, rank ^ 1);

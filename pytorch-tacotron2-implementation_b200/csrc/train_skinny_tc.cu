@@ -49,6 +49,15 @@ struct SkinnySegs {
     int ldo[3];
     int n_end[3];
 };
+// one GEMM of a launch: activations (tile image), packed weights, destinations, number of 128-column tiles.  A launch carries one or
+// two independent problems of the same K (the column tiles of the second follow those of the first in blockIdx.x): the two cells'
+// data gradients of the reverse walk are adjacent and independent once the cell backward kernels are fused into the attention backward.
+struct SkinnyProb {
+    const __nv_bfloat16* Ap;
+    const __nv_bfloat16* Wp;
+    SkinnySegs so;
+    int ntiles;
+};
 
 __device__ __forceinline__ void st_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
@@ -79,8 +88,7 @@ __global__ void pack_skinny_kernel(__nv_bfloat16* __restrict__ dst, const float*
 }
 
 __global__ void __launch_bounds__(ST_THREADS, 1)
-    skinny_tc_kernel(const __nv_bfloat16* __restrict__ Ap /* dZ as hi/lo tiles [K / 64][128 x 64] */, const __nv_bfloat16* __restrict__ Wp,
-                     const SkinnySegs so, int B, int K) {
+    skinny_tc_kernel(const SkinnyProb p0, const SkinnyProb p1, int B, int K) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + ST_STAGES;
@@ -89,7 +97,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
     uint8_t* stages = smem + ST_OFF;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nt = blockIdx.x, n0 = nt * ST_N;
+    const bool second = (int)blockIdx.x >= p0.ntiles;
+    const SkinnyProb& pr = second ? p1 : p0;
+    const __nv_bfloat16* __restrict__ Ap = pr.Ap;          // dZ as hi/lo tiles [K / 64][128 x 64]
+    const __nv_bfloat16* __restrict__ Wp = pr.Wp;
+    const SkinnySegs& so = pr.so;
+    const int nt = second ? blockIdx.x - p0.ntiles : blockIdx.x, n0 = nt * ST_N;
     const int kchunks = K / ST_K;
     const int c0 = (int)(((long long)blockIdx.y * kchunks) / gridDim.y), c1 = (int)(((long long)(blockIdx.y + 1) * kchunks) / gridDim.y);
     const int iters = c1 - c0;
@@ -215,22 +228,27 @@ int pack_skinny_tc(void* dst, const float* W, int ldw, int K, int N, cudaStream_
 }
 
 // out_i[b][n - n_begin_i] (+)= sum_k X[b][k] * W[k][n] for the column segments of one packed [K][N] matrix (see skinny_gemm_multi)
-// Xp: the activations as hi/lo bf16 tiles (skinny_tc_act_bytes; rows >= B zero)
-int skinny_gemm_multi_tc(const void* Xp, const void* Wp, int B, int K, int nseg, float* const* outs, const int* ldos,
-                         const int* n_ends, const bool* acc, cudaStream_t st) {
+// Xp: the activations as hi/lo bf16 tiles (skinny_tc_act_bytes; rows >= B zero).  skinny_gemm_pair_tc: two such problems in one launch.
+static int make_prob(SkinnyProb& pr, const void* Xp, const void* Wp, int B, int K, int nseg, float* const* outs, const int* ldos, const int* n_ends,
+                     const bool* acc, cudaStream_t st) {
     const int N = n_ends[nseg - 1];
     TACO_REQUIRE(skinny_tc_supported(B, K, N, nseg, n_ends), B200TACO_ERR_INVALID, "skinny_gemm_tc: unsupported shape B %d K %d N %d",
                  B, K, N);
-    SkinnySegs so{};
+    pr.Ap = static_cast<const __nv_bfloat16*>(Xp);
+    pr.Wp = static_cast<const __nv_bfloat16*>(Wp);
+    pr.ntiles = N / ST_N;
     for (int i = 0; i < 3; ++i) {
         const int j = i < nseg ? i : nseg - 1;
-        so.out[i] = outs[j]; so.ldo[i] = ldos[j]; so.n_end[i] = i < nseg ? n_ends[i] : N;
+        pr.so.out[i] = outs[j]; pr.so.ldo[i] = ldos[j]; pr.so.n_end[i] = i < nseg ? n_ends[i] : N;
         if (i < nseg && !acc[i]) {
             const int nb = i == 0 ? 0 : n_ends[i - 1];
             TACO_CUDA(cudaMemset2DAsync(outs[i], (size_t)ldos[i] * sizeof(float), 0, (size_t)(n_ends[i] - nb) * sizeof(float), B, st));
         }
     }
-    const int ntiles = N / ST_N;
+    return B200TACO_OK;
+}
+static int launch_probs(const SkinnyProb& p0, const SkinnyProb& p1, int B, int K, cudaStream_t st) {
+    const int ntiles = p0.ntiles + p1.ntiles;
     static const int sms = [] { int d = 0, n = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n > 0 ? n : 148; }();
     // one wave: as many K splits as fit next to the column tiles, at least 4 k-chunks each (TACO_SKINNY_KS overrides: measurements)
     static const int forced_ks = [] { const char* e = getenv("TACO_SKINNY_KS"); return e ? atoi(e) : 0; }();
@@ -242,10 +260,23 @@ int skinny_gemm_multi_tc(const void* Xp, const void* Wp, int B, int K, int nseg,
         TACO_CUDA(cudaFuncSetAttribute(skinny_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_TOTAL));
         attr = true;
     }
-    TACO_CUDA(launch_pdl(PDL_SKINNY_TC, skinny_tc_kernel, dim3(ntiles, ks), dim3(ST_THREADS), ST_TOTAL, st, static_cast<const __nv_bfloat16*>(Xp),
-                         static_cast<const __nv_bfloat16*>(Wp), so, B, K));
+    TACO_CUDA(launch_pdl(PDL_SKINNY_TC, skinny_tc_kernel, dim3(ntiles, ks), dim3(ST_THREADS), ST_TOTAL, st, p0, p1, B, K));
     TACO_LAUNCHED();
     return B200TACO_OK;
+}
+int skinny_gemm_multi_tc(const void* Xp, const void* Wp, int B, int K, int nseg, float* const* outs, const int* ldos,
+                         const int* n_ends, const bool* acc, cudaStream_t st) {
+    SkinnyProb p0{}, p1{};
+    if (int e = make_prob(p0, Xp, Wp, B, K, nseg, outs, ldos, n_ends, acc, st)) return e;
+    return launch_probs(p0, p1, B, K, st);
+}
+int skinny_gemm_pair_tc(const void* Xp0, const void* Wp0, int nseg0, float* const* outs0, const int* ldos0, const int* n_ends0, const bool* acc0,
+                        const void* Xp1, const void* Wp1, int nseg1, float* const* outs1, const int* ldos1, const int* n_ends1, const bool* acc1,
+                        int B, int K, cudaStream_t st) {
+    SkinnyProb p0{}, p1{};
+    if (int e = make_prob(p0, Xp0, Wp0, B, K, nseg0, outs0, ldos0, n_ends0, acc0, st)) return e;
+    if (int e = make_prob(p1, Xp1, Wp1, B, K, nseg1, outs1, ldos1, n_ends1, acc1, st)) return e;
+    return launch_probs(p0, p1, B, K, st);
 }
 
 }  // namespace b200taco
