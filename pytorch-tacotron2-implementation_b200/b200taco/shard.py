@@ -190,3 +190,32 @@ def deal_sorted(text_lengths: Sequence[int], world_size: int, rank: int) -> List
         if (k if rnd % 2 == 0 else world_size - 1 - k) == rank:
             mine.append(i)
     return mine
+
+
+def plan_ragged_launches(text_lengths: Sequence[int], rows: int, launch_utterances: int = 2048,
+                         length_ratio: float = 1.35) -> List[tuple]:
+    """Launch plan of the ragged continuous-batching path (``Engine.stream_infer_ragged``): the corpus is sorted by text length and
+    cut into launches of at most ``launch_utterances`` utterances whose longest text is at most ``length_ratio`` x the shortest
+    (attention work is spent on the padded width).  Inside a launch the queue runs LONGEST text first - a row takes the next
+    utterance when its own stops, so the launch ends on the shortest utterances and the live utterances are of similar length at
+    any time - and is filled up to a multiple of ``rows`` with repeats of its shortest utterances (results dropped).
+    Returns ``[(queue, n_real), ...]``: ``queue`` = utterance indices in queue order, the first ``n_real`` of them real."""
+    if rows < 1 or launch_utterances < 1:
+        raise ValueError("rows and launch_utterances must be positive")
+    lens = [int(n) for n in text_lengths]
+    order = sorted(range(len(lens)), key=lambda i: (lens[i], i))
+    launches, cur = [], []
+    for i in order:
+        if cur and (len(cur) >= launch_utterances or lens[i] > length_ratio * lens[cur[0]]):
+            launches.append(cur)
+            cur = []
+        cur.append(i)
+    if cur:
+        launches.append(cur)
+    plan = []
+    for members in launches:
+        queue = members[::-1]
+        n_real = len(queue)
+        queue = queue + [queue[n_real - 1 - k % n_real] for k in range((-n_real) % rows)]
+        plan.append((queue, n_real))
+    return plan

@@ -140,3 +140,27 @@ def test_sorted_snake_dealing_is_a_balanced_partition(world):
     assert shares == [shard.deal_sorted(list(lens), world, r) for r in range(world)]
     with pytest.raises(ValueError):
         shard.deal_sorted(lens, world, -1)
+
+
+def test_ragged_launch_plan():
+    """Launch plan of the ragged continuous-batching path: every utterance queued exactly once, launches are length ranges within
+    the ratio and the size cap, the queue of a launch runs longest text first and is filled up to a multiple of the rows with
+    repeats of its shortest utterances."""
+    lens = corpus_lengths()
+    plan = shard.plan_ragged_launches(lens, rows=64, launch_utterances=2048, length_ratio=1.35)
+    real = [i for q, n in plan for i in q[:n]]
+    assert sorted(real) == list(range(len(lens)))
+    prev_max = 0
+    for q, n in plan:
+        assert len(q) % 64 == 0 and 0 < n <= 2048 and len(q) - n < 64
+        ql = [lens[i] for i in q[:n]]
+        assert ql == sorted(ql, reverse=True) and max(ql) <= 1.35 * min(ql)
+        assert min(ql) >= prev_max                                   # launches are ascending length ranges
+        prev_max = max(ql)
+        assert set(q[n:]) <= set(q[max(0, n - (len(q) - n)):n])      # the fill repeats the shortest utterances of the launch
+    one = shard.plan_ragged_launches(lens[:100], rows=8, launch_utterances=10 ** 6, length_ratio=1e9)
+    assert len(one) == 1 and one[0][1] == 100 and len(one[0][0]) == 104
+    assert one[0][0][100:] == [one[0][0][99 - k] for k in range(4)]  # fill = the shortest ones, shortest first
+    assert shard.plan_ragged_launches([], rows=8) == []
+    with pytest.raises(ValueError):
+        shard.plan_ragged_launches(lens, rows=0)
