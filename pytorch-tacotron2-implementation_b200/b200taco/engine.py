@@ -402,35 +402,22 @@ class Engine:
         """Corpus synthesis with continuous batching over utterances of DIFFERENT text lengths (BASELINE config 4).
 
         ``utterances``: sequence of 1-D int64 id tensors (host).  The reference's inference takes no text lengths (F8), so
-        every utterance is ENCODED at its exact length (one encoder call per group of equal-length utterances) and its encoder
-        output is placed in a row padded to the launch's longest utterance; the decoder launch masks every utterance to its
-        own length, which reproduces its solo exact-length decode.  Launches are cut from the length-sorted corpus so that the
-        longest utterance of a launch is at most ``length_ratio`` x its shortest (attention work is spent on the padded width)
-        and hold at most ``launch_utterances`` utterances; a launch is filled up to a multiple of ``rows`` by repeating its own
-        utterances (results dropped).  Yields ``(index, mel_postnet (S,80), mel_coarse (S,80), gate (S,), alignments (S,T_i))``
-        per utterance, device tensors (pinned host tensors with ``to_host``), in completion order of the launches."""
+        every utterance is ENCODED over its own positions only (ragged encoder batches of neighbours of the length-sorted
+        queue, ``Engine.encoder(lengths=...)``: bit for bit its exact-length solo encoding) and its encoder output is placed in
+        a row padded to the launch's longest utterance; the decoder launch masks every utterance to its own length, which
+        reproduces its solo exact-length decode.  The launch plan (length-sorted corpus, at most ``launch_utterances``
+        utterances and a length spread of at most ``length_ratio`` per launch, longest text first inside a launch, filled up to
+        a multiple of ``rows``) is ``shard.plan_ragged_launches``.  Yields ``(index, mel_postnet (S,80), mel_coarse (S,80),
+        gate (S,), alignments (S,T_i))`` per utterance, device tensors (pinned host tensors with ``to_host``), in completion
+        order of the launches."""
         import time
+        from . import shard
         dev = self.device
         if not self.stream_supported(rows):
             raise B200TacoError("stream_infer_ragged needs 4 <= rows <= 64 and the default (bf16, tensor-core) decoder")
         lens = [int(u.shape[0]) for u in utterances]
-        order = sorted(range(len(lens)), key=lambda i: (lens[i], i))
-        launches, cur_l = [], []
-        for i in order:
-            if cur_l and (len(cur_l) >= launch_utterances or lens[i] > length_ratio * lens[cur_l[0]]):
-                launches.append(cur_l)
-                cur_l = []
-            cur_l.append(i)
-        if cur_l:
-            launches.append(cur_l)
         self.last_stream_steps = 0
-        for members in launches:
-            # queue order inside a launch: LONGEST text first.  A row takes the next utterance when its own stops, so the launch
-            # ends with every row on one of the shortest utterances and the idle tail (rows waiting for the last ones to stop) is
-            # half a SHORT utterance per row instead of half a long one (5 % -> 1 % of a 1024-utterance launch).
-            members = members[::-1]
-            n_real = len(members)
-            members = members + [members[n_real - 1 - k % n_real] for k in range((-n_real) % rows)]   # fill the last rows (shortest)
+        for members, n_real in shard.plan_ragged_launches(lens, rows, launch_utterances, length_ratio):
             N, Tmax = len(members), max(lens[i] for i in members)
             mem = torch.zeros(N, Tmax, config.encoder_embedding_dim, dtype=torch.float32, device=dev)
             # ragged encoder batches: max_batch neighbours of the length-sorted queue at a time, padded to the longest of them, every
